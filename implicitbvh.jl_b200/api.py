@@ -1,0 +1,675 @@
+"""Host-side mirror of the ImplicitBVH.jl public API for the hot path, over the C ABI.
+
+Same names, argument meaning and error behaviour as the reference (src/ImplicitBVH.jl:20-24 exports):
+`BVH`, `BVHOptions`, `BVHTraversal`, `traverse`, `traverse_rays`, `default_start_level`,
+`ImplicitTree`, `memory_index`, `level_indices`, `isvirtual`, `DefaultMortonAlgorithm`,
+`LVTTraversal`. Julia is not available in this image, so this Python layer plays the role of the
+Julia methods that would `ccall` libibvh_b200.so; torch is used only for device
+memory and streams. Nothing here computes on the CPU: every geometric result comes from the CUDA
+kernels, and the module refuses to work without the shared library and a CUDA device.
+
+Device arrays of isbits structs are `DeviceArray`s: a torch.uint8 tensor of raw bytes plus the numpy
+structured dtype that describes one element (the stand-in for `CuVector{BoundingVolume{...}}`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional, Union
+
+import numpy as np
+import torch
+
+from . import _capi as capi
+from ._capi import BBOX, BSPHERE
+
+
+# ---------------------------------------------------------------------------------------------
+# errors (the reference throws ArgumentError / DomainError; both are ValueErrors here)
+# ---------------------------------------------------------------------------------------------
+class ArgumentError(ValueError):
+    pass
+
+
+class DomainError(ValueError):
+    pass
+
+
+class CudaError(RuntimeError):
+    pass
+
+
+def _raise(code: int, handle=None, what: str = ""):
+    msg = f"{what}: {capi.status_string(code)}"
+    if code == capi.ERR_ARGUMENT:
+        raise ArgumentError(msg)
+    if code == capi.ERR_DOMAIN:
+        raise DomainError(msg)
+    if code in (capi.ERR_CUDA, capi.ERR_ALLOC) and handle is not None:
+        msg += " — " + capi.lib().ibvh_last_error(handle).decode()
+    if code == capi.ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise CudaError(msg)
+
+
+# ---------------------------------------------------------------------------------------------
+# isbits layouts (SURVEY.md §8 layout table)
+# ---------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class VolumeType:
+    """`BSphere{T}` / `BBox{T}` as a type object (bsphere.jl:26-29, bbox.jl:35-38)."""
+    kind: int
+    float_bytes: int = 4
+
+    @property
+    def dtype(self) -> np.dtype:
+        f = {4: np.float32, 8: np.float64}[self.float_bytes]
+        if self.kind == BSPHERE:
+            return np.dtype([("x", f, 3), ("r", f)])
+        return np.dtype([("lo", f, 3), ("up", f, 3)])
+
+    def __repr__(self):
+        return f"{'BSphere' if self.kind == BSPHERE else 'BBox'}{{Float{8 * self.float_bytes}}}"
+
+
+def BSphere(T=np.float32) -> VolumeType:
+    return VolumeType(BSPHERE, np.dtype(T).itemsize)
+
+
+def BBox(T=np.float32) -> VolumeType:
+    return VolumeType(BBOX, np.dtype(T).itemsize)
+
+
+def leaf_dtype(vol: VolumeType, index=np.int32, morton=np.uint32) -> np.dtype:
+    """BoundingVolume{V, I, M} (bounding_volumes.jl:55-59), natural alignment."""
+    return np.dtype([("volume", vol.dtype), ("index", np.dtype(index)), ("morton", np.dtype(morton))], align=True)
+
+
+def pair_dtype(index=np.int32) -> np.dtype:
+    """IndexPair{I} (traverse/traverse.jl:6)."""
+    return np.dtype([("a", np.dtype(index)), ("b", np.dtype(index))])
+
+
+def _volume_of_dtype(dt: np.dtype) -> Optional[VolumeType]:
+    if dt.names == ("x", "r"):
+        return VolumeType(BSPHERE, dt["r"].itemsize)
+    if dt.names == ("lo", "up"):
+        return VolumeType(BBOX, dt["lo"].base.itemsize)
+    return None
+
+
+def bspheres(centers, radii, T=np.float32) -> np.ndarray:
+    """Convenience: array of BSphere{T} from (n,3) centres and (n,) radii."""
+    centers = np.asarray(centers, T).reshape(-1, 3)
+    out = np.zeros(len(centers), BSphere(T).dtype)
+    out["x"] = centers
+    out["r"] = np.asarray(radii, T)
+    return out
+
+
+def bboxes(lo, up, T=np.float32) -> np.ndarray:
+    lo = np.asarray(lo, T).reshape(-1, 3)
+    out = np.zeros(len(lo), BBox(T).dtype)
+    out["lo"] = lo
+    out["up"] = np.asarray(up, T).reshape(-1, 3)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# device arrays
+# ---------------------------------------------------------------------------------------------
+class DeviceArray:
+    """A vector of isbits structs in device (or pinned host) memory: raw bytes + element dtype."""
+
+    def __init__(self, tensor: torch.Tensor, dtype: np.dtype):
+        assert tensor.dtype == torch.uint8 and tensor.dim() == 1 and tensor.is_contiguous()
+        self.dtype = np.dtype(dtype)
+        assert tensor.numel() % self.dtype.itemsize == 0
+        self.tensor = tensor
+
+    @classmethod
+    def empty(cls, n: int, dtype, device) -> "DeviceArray":
+        dtype = np.dtype(dtype)
+        return cls(torch.empty(int(n) * dtype.itemsize, dtype=torch.uint8, device=device), dtype)
+
+    @classmethod
+    def from_numpy(cls, arr: np.ndarray, device=None, pin: bool = False) -> "DeviceArray":
+        arr = np.ascontiguousarray(arr)
+        t = torch.from_numpy(arr.view(np.uint8).reshape(-1))
+        if pin:
+            t = t.pin_memory()
+        if device is not None:
+            t = t.to(device, non_blocking=True)
+        return cls(t, arr.dtype)
+
+    def to(self, device) -> "DeviceArray":
+        return DeviceArray(self.tensor.to(device, non_blocking=True), self.dtype)
+
+    def numpy(self) -> np.ndarray:
+        return self.tensor.cpu().numpy().view(self.dtype)
+
+    def __len__(self):
+        return self.tensor.numel() // self.dtype.itemsize
+
+    def __getitem__(self, s: slice) -> "DeviceArray":
+        assert isinstance(s, slice) and s.step in (None, 1)
+        a, b, _ = s.indices(len(self))
+        it = self.dtype.itemsize
+        return DeviceArray(self.tensor[a * it:max(a, b) * it], self.dtype)
+
+    @property
+    def ptr(self) -> int:
+        return self.tensor.data_ptr()
+
+    @property
+    def device(self):
+        return self.tensor.device
+
+    @property
+    def is_cuda(self):
+        return self.tensor.is_cuda
+
+    def __repr__(self):
+        return f"DeviceArray({len(self)} x {self.dtype.itemsize} B on {self.device})"
+
+
+# ---------------------------------------------------------------------------------------------
+# handles (one per device)
+# ---------------------------------------------------------------------------------------------
+_handles = {}
+
+
+def _device_index(device) -> int:
+    if not torch.cuda.is_available():
+        raise CudaError("no CUDA device available; ibvh-b200 has no CPU fallback")
+    d = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    if d.type != "cuda":
+        raise CudaError("ibvh-b200 runs on CUDA devices only; there is no CPU fallback")
+    return d.index if d.index is not None else torch.cuda.current_device()
+
+
+def get_handle(device=None):
+    if not torch.cuda.is_available():
+        raise CudaError("no CUDA device available; ibvh-b200 has no CPU fallback")
+    idx = _device_index(device)
+    h = _handles.get(idx)
+    if h is None:
+        out = C.c_void_p()
+        rc = capi.lib().ibvh_create(C.byref(out), idx)
+        if rc != capi.OK:
+            _raise(rc, None, "ibvh_create")
+        h = out
+        _handles[idx] = h
+    return h
+
+
+def _stream_ptr(device_index: int) -> int:
+    return torch.cuda.current_stream(device_index).cuda_stream
+
+
+# ---------------------------------------------------------------------------------------------
+# options (utils.jl:34-93), Morton algorithm (morton/default.jl:22-42), traversal algorithm tag
+# ---------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class DefaultMortonAlgorithm:
+    exemplar: type = np.uint32
+    compute_extrema: bool = True
+    mins: tuple = (float("nan"),) * 3
+    maxs: tuple = (float("nan"),) * 3
+
+    def __post_init__(self):
+        if np.dtype(self.exemplar) not in (np.dtype(np.uint16), np.dtype(np.uint32), np.dtype(np.uint64)):
+            raise ArgumentError("Morton type must be UInt16, UInt32 or UInt64")
+
+    @property
+    def eltype(self) -> np.dtype:
+        return np.dtype(self.exemplar)
+
+
+@dataclass(frozen=True)
+class BVHOptions:
+    index: type = np.int32
+    morton: DefaultMortonAlgorithm = field(default_factory=DefaultMortonAlgorithm)
+    num_threads: int = 1
+    min_mortons_per_thread: int = 100
+    min_sorts_per_thread: int = 100
+    min_boundings_per_thread: int = 100
+    min_traversals_per_thread: int = 100
+    block_size: int = 256
+
+    def __post_init__(self):
+        for name in ("num_threads", "min_mortons_per_thread", "min_sorts_per_thread", "min_boundings_per_thread",
+                     "min_traversals_per_thread", "block_size"):
+            if not getattr(self, name) > 0:                       # utils.jl:74-79
+                raise ArgumentError(f"{name} > 0 must hold")
+        if np.dtype(self.index) not in (np.dtype(np.int32), np.dtype(np.int64)):
+            raise NotImplementedError("index type must be Int32 or Int64 in this build")
+
+    @property
+    def index_dtype(self) -> np.dtype:
+        return np.dtype(self.index)
+
+
+class LVTTraversal:
+    """Leaf-vs-tree traversal (traverse/leaf_vs_tree/leaf_vs_tree.jl:1)."""
+
+    def __repr__(self):
+        return "LVTTraversal()"
+
+
+# ---------------------------------------------------------------------------------------------
+# implicit tree (implicit_tree.jl) — host-only integer math done by the C library
+# ---------------------------------------------------------------------------------------------
+class ImplicitTree:
+    def __init__(self, num_leaves: int):
+        t = capi.Tree()
+        rc = capi.lib().ibvh_tree_shape(int(num_leaves), C.byref(t), None)
+        if rc == capi.ERR_DOMAIN:
+            raise DomainError(f"{num_leaves}: must have at least one geometry!")      # implicit_tree.jl:78-80
+        self._c = t
+        self.levels, self.real_leaves, self.real_nodes = t.levels, t.real_leaves, t.real_nodes
+        self.virtual_leaves, self.virtual_nodes = t.virtual_leaves, t.virtual_nodes
+
+    def skips(self) -> np.ndarray:
+        t = capi.Tree()
+        s = (C.c_int64 * 64)()
+        capi.lib().ibvh_tree_shape(self.real_leaves, C.byref(t), s)
+        return np.array(s[: self.levels], np.int64)
+
+    def __repr__(self):
+        return f"ImplicitTree(levels: {self.levels}, real_leaves: {self.real_leaves})"
+
+
+def memory_index(tree: ImplicitTree, implicit_index: int) -> int:
+    if not (1 <= implicit_index <= 2 ** tree.levels - 1):
+        raise IndexError(implicit_index)
+    return int(capi.lib().ibvh_memory_index(C.byref(tree._c), int(implicit_index)))
+
+
+def level_indices(tree: ImplicitTree, level: int):
+    if not (1 <= level <= tree.levels):
+        raise IndexError(level)
+    a, b = C.c_int64(), C.c_int64()
+    capi.lib().ibvh_level_indices(C.byref(tree._c), int(level), C.byref(a), C.byref(b))
+    return int(a.value), int(b.value)
+
+
+def isvirtual(tree: ImplicitTree, implicit_index: int) -> bool:
+    if not (1 <= implicit_index <= 2 ** tree.levels - 1):
+        raise IndexError(implicit_index)
+    return bool(capi.lib().ibvh_isvirtual(C.byref(tree._c), int(implicit_index)))
+
+
+# ---------------------------------------------------------------------------------------------
+# BVH (build.jl:155-271)
+# ---------------------------------------------------------------------------------------------
+def _types(leaf_vol: VolumeType, node: VolumeType, index: np.dtype, morton: np.dtype) -> capi.Types:
+    return capi.Types(leaf_vol.kind, leaf_vol.float_bytes, index.itemsize, morton.itemsize, node.kind, 0)
+
+
+class BVH:
+    """`BVH(bounding_volumes, node_type=BBox{Float32}; built_level=1, cache=nothing, options=BVHOptions())`.
+
+    `bounding_volumes`: numpy structured array or DeviceArray of raw volumes (BSphere/BBox: wrapped on
+    device, index = position) or of BoundingVolume structs (sorted IN PLACE when already on the device,
+    as in the reference, build.jl:147-152). Fields mirror build.jl:155-166.
+    """
+
+    def __init__(self, bounding_volumes: Union[np.ndarray, DeviceArray], node_type: VolumeType = None, *,
+                 built_level: Union[int, float] = 1, cache: Optional["BVH"] = None, options: BVHOptions = None,
+                 device=None):
+        options = options or BVHOptions()
+        node_type = node_type or BBox(np.float32)
+        lib = capi.lib()
+        if isinstance(bounding_volumes, np.ndarray):
+            dev = torch.device("cuda", _device_index(device))
+            src = DeviceArray.from_numpy(bounding_volumes, device=dev)
+        else:
+            src = bounding_volumes
+            if not src.is_cuda:
+                src = src.to(torch.device("cuda", _device_index(device)))
+        didx = src.device.index
+        self._handle = get_handle(src.device)
+        I, M = options.index_dtype, options.morton.eltype
+        n = len(src)
+
+        vol = _volume_of_dtype(src.dtype)
+        wrapped_input = vol is None
+        if wrapped_input:
+            if src.dtype.names != ("volume", "index", "morton"):
+                raise ArgumentError("bounding_volumes must be BSphere / BBox volumes or BoundingVolume structs")
+            vol = _volume_of_dtype(src.dtype["volume"])
+            # check_bounding_volume_types, build.jl:355-361
+            if src.dtype["index"] != I:
+                raise ArgumentError(f"BoundingVolume index type {src.dtype['index']} does not match BVHOptions index_exemplar type {I}")
+            if src.dtype["morton"] != M:
+                raise ArgumentError(f"BoundingVolume morton type {src.dtype['morton']} does not match BVHOptions morton type {M}")
+        if node_type.float_bytes != vol.float_bytes:
+            raise NotImplementedError("node float type must equal the leaf float type in this build")
+        ldt = leaf_dtype(vol, I, M)
+        self.types = _types(vol, node_type, I, M)
+        assert ldt.itemsize == lib.ibvh_leaf_bytes(C.byref(self.types))
+
+        if n < 1:
+            raise DomainError(f"{n}: must have at least one geometry!")
+        self.tree = ImplicitTree(n)
+
+        # skips: reuse from cache (build.jl:232-239)
+        if cache is not None and cache.skips.dtype != I:
+            raise ArgumentError("eltype(cache.skips) === I must hold")
+        self.skips = torch.from_numpy(self.tree.skips().astype(I)).to(src.device, non_blocking=True)
+
+        # built level (build.jl:309-325)
+        out = C.c_int64()
+        if isinstance(built_level, (int, np.integer)) and not isinstance(built_level, bool):
+            rc = lib.ibvh_compute_build_level(self.tree.levels, 0, int(built_level), 0.0, C.byref(out))
+        elif isinstance(built_level, (float, np.floating)):
+            rc = lib.ibvh_compute_build_level(self.tree.levels, 1, 0, float(built_level), C.byref(out))
+        else:
+            raise TypeError("built_level (the level to build BVH up to) must be Integer or AbstractFloat")
+        if rc != capi.OK:
+            _raise(rc, self._handle, "compute_build_level")
+        self.built_level = int(out.value)
+
+        # nodes: reuse from cache when the type matches (build.jl:256-263)
+        num_nodes = self.tree.real_nodes - self.tree.real_leaves
+        self.node_type = node_type
+        if cache is not None:
+            if cache.nodes.dtype != node_type.dtype:
+                raise ArgumentError("eltype(cache.nodes) === N must hold")
+            if len(cache.nodes) == num_nodes and cache.nodes.device == src.device:
+                self.nodes = cache.nodes
+            else:
+                self.nodes = DeviceArray.empty(num_nodes, node_type.dtype, src.device)
+        else:
+            self.nodes = DeviceArray.empty(num_nodes, node_type.dtype, src.device)
+
+        if wrapped_input:
+            self.leaves = src
+            d_vol = None
+        else:
+            self.leaves = DeviceArray.empty(n, ldt, src.device)
+            d_vol = src.ptr
+        self._volumes_keepalive = src
+
+        m = options.morton
+        mins = (C.c_double * 3)(*[float(x) for x in m.mins])
+        maxs = (C.c_double * 3)(*[float(x) for x in m.maxs])
+        with torch.cuda.device(didx):
+            rc = lib.ibvh_build(self._handle, d_vol, self.leaves.ptr, n, C.byref(self.types),
+                                self.nodes.ptr if num_nodes > 0 else None, self.built_level,
+                                1 if m.compute_extrema else 0, mins, maxs, _stream_ptr(didx))
+        if rc != capi.OK:
+            _raise(rc, self._handle, "ibvh_build")
+
+    # -- helpers ---------------------------------------------------------------------------------
+    def _c_bvh(self) -> capi.Bvh:
+        return capi.Bvh(self.leaves.ptr, self.nodes.ptr if len(self.nodes) else None, len(self.leaves), self.built_level, self.types)
+
+    @property
+    def index_dtype(self) -> np.dtype:
+        return self.leaves.dtype["index"]
+
+    def __repr__(self):
+        return (f"BVH\n  built_level: {self.built_level}\n  tree:        {self.tree}\n  skips:       ({len(self.skips)},)\n"
+                f"  nodes:       {self.nodes}\n  leaves:      {self.leaves}\n")
+
+
+# ---------------------------------------------------------------------------------------------
+# traversal results (traverse/traverse.jl:54-108)
+# ---------------------------------------------------------------------------------------------
+class BVHTraversal:
+    def __init__(self, start_level1: int, start_level2: int, num_checks: int, num_contacts: int,
+                 cache1: DeviceArray, cache2: DeviceArray):
+        self.start_level1, self.start_level2 = int(start_level1), int(start_level2)
+        self.num_checks, self.num_contacts = int(num_checks), int(num_contacts)
+        self.cache1, self.cache2 = cache1, cache2
+
+    @property
+    def contacts(self) -> DeviceArray:
+        """view(cache1, 1:num_contacts) — traverse/traverse.jl:98-104."""
+        return self.cache1[: self.num_contacts]
+
+    def __repr__(self):
+        return (f"BVHTraversal\n  start_level1: {self.start_level1}\n  start_level2: {self.start_level2}\n"
+                f"  num_checks:   {self.num_checks}\n  num_contacts: {self.num_contacts}\n"
+                f"  cache1:       {self.cache1}\n  cache2:       {self.cache2}\n")
+
+
+def default_start_level(bvh: BVH, alg=None) -> int:
+    """leaf_vs_tree/leaf_vs_tree.jl:4-6."""
+    if alg is not None and not isinstance(alg, LVTTraversal):
+        raise ArgumentError(f"default_start_level not implemented for: {alg}")
+    return max(1, bvh.built_level)
+
+
+def _check_narrow(narrow):
+    if narrow is not None:
+        raise NotImplementedError("custom `narrow` closures cannot cross the C ABI (SURVEY.md §8f-3); only the default is supported")
+
+
+def _run_two_phase(call, handle, device, I: np.dtype, nqueries: int, cache: Optional[BVHTraversal], ordered: bool,
+                   reference_shaped: bool):
+    """The reference's count -> accumulate -> allocate/grow -> write protocol (traverse_single.jl:23-78),
+    with `cache1`/`cache2` reused and grown only when too small."""
+    pdt = pair_dtype(I)
+    flags = capi.TRAVERSE_ORDERED if ordered else capi.TRAVERSE_UNORDERED
+    if reference_shaped:
+        flags |= capi.TRAVERSE_REFERENCE_SHAPED
+    if cache is not None:
+        if cache.cache2.dtype != I:
+            raise ArgumentError("eltype(cache.cache2) === I must hold")
+        if cache.cache1.dtype != pdt:
+            raise ArgumentError("eltype(cache.cache1) === IndexPair{I} must hold")
+        cache2 = cache.cache2 if (len(cache.cache2) >= nqueries and cache.cache2.device == device) else DeviceArray.empty(nqueries, I, device)
+        cache1 = cache.cache1 if cache.cache1.device == device else DeviceArray.empty(0, pdt, device)
+    else:
+        cache2 = DeviceArray.empty(nqueries, I, device)
+        cache1 = None
+    total = C.c_int64(0)
+    if cache1 is not None and len(cache1) > 0:
+        rc = call(flags, cache2.ptr, cache1.ptr, len(cache1), total)
+        if rc == capi.OK:
+            return int(total.value), cache1, cache2
+        if rc != capi.ERR_CAPACITY:
+            _raise(rc, handle, "traverse")
+        need = int(total.value)
+        cache1 = DeviceArray.empty(need, pdt, device)
+        second = (flags | capi.TRAVERSE_COUNTS_VALID) if ordered else flags
+        rc = call(second, cache2.ptr, cache1.ptr, need, total)
+        if rc != capi.OK:
+            _raise(rc, handle, "traverse")
+        return int(total.value), cache1, cache2
+    # no usable contacts buffer yet: count pass, allocate exactly, write pass
+    rc = call(capi.TRAVERSE_ORDERED | (capi.TRAVERSE_REFERENCE_SHAPED if reference_shaped else 0), cache2.ptr, None, 0, total)
+    if rc != capi.OK:
+        _raise(rc, handle, "traverse (count)")
+    need = int(total.value)
+    cache1 = DeviceArray.empty(need, pdt, device)
+    if need == 0:
+        return 0, cache1, cache2
+    second = (flags | capi.TRAVERSE_COUNTS_VALID) if ordered else flags
+    rc = call(second, cache2.ptr, cache1.ptr, need, total)
+    if rc != capi.OK:
+        _raise(rc, handle, "traverse (write)")
+    return int(total.value), cache1, cache2
+
+
+def traverse(bvh: BVH, bvh2=None, alg=None, *, start_level: Optional[int] = None, start_level1: Optional[int] = None,
+             start_level2: Optional[int] = None, narrow=None, cache: Optional[BVHTraversal] = None, options: BVHOptions = None,
+             ordered: bool = True, reference_shaped: bool = False, query_range=None) -> BVHTraversal:
+    """`traverse(bvh[, bvh2], LVTTraversal(); start_level[1,2], narrow, cache, options)`.
+
+    Extensions over the reference signature (all keyword-only, defaults reproduce the reference):
+    `ordered=False` selects the one-pass unordered emission, `reference_shaped=True` the proxy of the
+    reference's own GPU kernel, `query_range=(begin, count)` restricts the query leaves (multi-GPU shard).
+    """
+    if bvh2 is not None and not isinstance(bvh2, BVH):       # traverse(bvh, alg)
+        alg, bvh2 = bvh2, None
+    if alg is not None and not isinstance(alg, LVTTraversal):
+        raise ArgumentError(f"Traversal algorithm not implemented: {alg}")
+    _check_narrow(narrow)
+    lib = capi.lib()
+    qb, qc = (0, -1) if query_range is None else (int(query_range[0]), int(query_range[1]))
+
+    if bvh2 is None:
+        sl = default_start_level(bvh) if start_level is None else int(start_level)
+        if not (bvh.built_level <= sl <= bvh.tree.levels <= 32):                      # traverse_single.jl:9-11
+            raise ArgumentError("bvh.built_level <= start_level <= bvh.tree.levels <= 32 must hold")
+        I = bvh.index_dtype
+        device = bvh.leaves.device
+        if bvh.tree.real_nodes <= 1:                                                  # traverse_single.jl:17-21
+            return BVHTraversal(sl, 0, 0, 0, DeviceArray.empty(0, pair_dtype(I), device), DeviceArray.empty(0, I, device))
+        cb = bvh._c_bvh()
+        nq = len(bvh.leaves) if qc < 0 else qc
+
+        def call(flags, p_counts, p_contacts, capacity, total):
+            params = capi.TraverseParams(sl, qb, qc, flags, 0, 0)
+            with torch.cuda.device(device.index):
+                return lib.ibvh_traverse_single(bvh._handle, C.byref(cb), C.byref(params), p_counts, p_contacts, capacity,
+                                                C.byref(total), _stream_ptr(device.index))
+
+        total, c1, c2 = _run_two_phase(call, bvh._handle, device, I, nq, cache, ordered, reference_shaped)
+        return BVHTraversal(sl, 0, 0, total, c1, c2)
+
+    # pair — traverse_pair.jl:1-116
+    sl1 = default_start_level(bvh) if start_level1 is None else int(start_level1)
+    sl2 = default_start_level(bvh2) if start_level2 is None else int(start_level2)
+    if not (bvh.built_level <= sl1 <= bvh.tree.levels <= 32):
+        raise ArgumentError("bvh1.built_level <= start_level1 <= bvh1.tree.levels <= 32 must hold")
+    if not (bvh2.built_level <= sl2 <= bvh2.tree.levels <= 32):
+        raise ArgumentError("bvh2.built_level <= start_level2 <= bvh2.tree.levels <= 32 must hold")
+    if bvh.index_dtype != bvh2.index_dtype:
+        raise ArgumentError("get_index_type(bvh2) === I must hold")
+    if bvh.leaves.device != bvh2.leaves.device:
+        raise ArgumentError("both BVHs must live on the same device")
+    flip = not (len(bvh.leaves) >= len(bvh2.leaves))                                  # traverse_pair.jl:16-36
+    queries, target, sl_t = (bvh2, bvh, sl1) if flip else (bvh, bvh2, sl2)
+    I = bvh.index_dtype
+    device = bvh.leaves.device
+    cq, ct = queries._c_bvh(), target._c_bvh()
+    nq = len(queries.leaves) if qc < 0 else qc
+
+    def call(flags, p_counts, p_contacts, capacity, total):
+        params = capi.TraverseParams(sl_t, qb, qc, flags, 1 if flip else 0, 0)
+        with torch.cuda.device(device.index):
+            return lib.ibvh_traverse_pair(bvh._handle, C.byref(cq), C.byref(ct), C.byref(params), p_counts, p_contacts, capacity,
+                                          C.byref(total), _stream_ptr(device.index))
+
+    total, c1, c2 = _run_two_phase(call, bvh._handle, device, I, nq, cache, ordered, reference_shaped)
+    return BVHTraversal(sl1, sl2, 0, total, c1, c2)
+
+
+def traverse_rays(bvh: BVH, points, directions, alg=None, *, start_level: int = 1, narrow=None,
+                  cache: Optional[BVHTraversal] = None, options: BVHOptions = None, ordered: bool = True,
+                  id_base: int = 0) -> BVHTraversal:
+    """`traverse_rays(bvh, points, directions, LVTTraversal(); start_level=1, narrow, cache, options)`.
+
+    `points` / `directions`: (3, R) numpy arrays (the reference's column-major 3xR matrices), or torch
+    CUDA tensors of shape (R, 3) — the same memory layout — in the BVH float type.
+    """
+    if alg is not None and not isinstance(alg, LVTTraversal):
+        raise ArgumentError(f"Raytracing algorithm not implemented: {alg}")
+    _check_narrow(narrow)
+    lib = capi.lib()
+    T = {4: np.float32, 8: np.float64}[bvh.types.float_bytes]
+    device = bvh.leaves.device
+
+    def to_dev(a):
+        if isinstance(a, torch.Tensor):
+            if a.dim() != 2 or a.shape[1] != 3:
+                raise ArgumentError("device ray arrays must have shape (R, 3)")
+            return a.to(device=device, dtype={4: torch.float32, 8: torch.float64}[bvh.types.float_bytes]).contiguous()
+        a = np.asarray(a)
+        if a.ndim != 2 or a.shape[0] != 3:                                           # leaf_vs_tree.jl:13
+            raise ArgumentError("size(points, 1) == size(directions, 1) == 3 must hold")
+        return torch.from_numpy(np.ascontiguousarray(a.T.astype(T))).to(device, non_blocking=True)
+
+    p, d = to_dev(points), to_dev(directions)
+    if p.shape != d.shape:                                                            # leaf_vs_tree.jl:14
+        raise ArgumentError("size(points, 2) == size(directions, 2) must hold")
+    if not (bvh.built_level <= start_level <= bvh.tree.levels <= 32):
+        raise ArgumentError("bvh.built_level <= start_level <= bvh.tree.levels <= 32 must hold")
+    I = bvh.index_dtype
+    nrays = p.shape[0]
+    if nrays == 0:                                                                    # leaf_vs_tree.jl:22-26
+        return BVHTraversal(start_level, 0, 0, 0, DeviceArray.empty(0, pair_dtype(I), device), DeviceArray.empty(0, pair_dtype(I), device))
+    cb = bvh._c_bvh()
+
+    def call(flags, p_counts, p_contacts, capacity, total):
+        params = capi.TraverseParams(int(start_level), 0, -1, flags, 0, int(id_base))
+        with torch.cuda.device(device.index):
+            return lib.ibvh_traverse_rays(bvh._handle, C.byref(cb), p.data_ptr(), d.data_ptr(), nrays, C.byref(params), p_counts,
+                                          p_contacts, capacity, C.byref(total), _stream_ptr(device.index))
+
+    total, c1, c2 = _run_two_phase(call, bvh._handle, device, I, nrays, cache, ordered, False)
+    return BVHTraversal(start_level, 0, 0, total, c1, c2)
+
+
+# ---------------------------------------------------------------------------------------------
+# stage-level entry points (for parity tests / profiling of one stage)
+# ---------------------------------------------------------------------------------------------
+def wrap_bounding_volumes(volumes: Union[np.ndarray, DeviceArray], options: BVHOptions = None, device=None) -> DeviceArray:
+    """build.jl:328-352."""
+    options = options or BVHOptions()
+    src = DeviceArray.from_numpy(volumes, device=torch.device("cuda", _device_index(device))) if isinstance(volumes, np.ndarray) else volumes
+    vol = _volume_of_dtype(src.dtype)
+    if vol is None:
+        raise ArgumentError("expected raw BSphere / BBox volumes")
+    ldt = leaf_dtype(vol, options.index_dtype, options.morton.eltype)
+    out = DeviceArray.empty(len(src), ldt, src.device)
+    types = _types(vol, BBox({4: np.float32, 8: np.float64}[vol.float_bytes]), options.index_dtype, options.morton.eltype)
+    h = get_handle(src.device)
+    with torch.cuda.device(src.device.index):
+        rc = capi.lib().ibvh_wrap(h, src.ptr, len(src), C.byref(types), out.ptr, _stream_ptr(src.device.index))
+    if rc != capi.OK:
+        _raise(rc, h, "ibvh_wrap")
+    return out
+
+
+def _leaf_types(leaves: DeviceArray, node: VolumeType = None) -> capi.Types:
+    vol = _volume_of_dtype(leaves.dtype["volume"])
+    node = node or BBox({4: np.float32, 8: np.float64}[vol.float_bytes])
+    return _types(vol, node, leaves.dtype["index"], leaves.dtype["morton"])
+
+
+def morton_encode(leaves: DeviceArray, options: BVHOptions = None):
+    """`morton_encode!(bounding_volumes, options)` (morton/morton.jl:28-35): in place; returns (mins, maxs) used."""
+    options = options or BVHOptions()
+    if leaves.dtype["morton"] != options.morton.eltype:                               # morton.jl:38-42
+        raise ArgumentError(f"Bounding volume Morton type {leaves.dtype['morton']} does not match options Morton type {options.morton.eltype}")
+    types = _leaf_types(leaves)
+    h = get_handle(leaves.device)
+    m = options.morton
+    mins = (C.c_double * 3)(*[float(x) for x in m.mins])
+    maxs = (C.c_double * 3)(*[float(x) for x in m.maxs])
+    omin, omax = (C.c_double * 3)(), (C.c_double * 3)()
+    with torch.cuda.device(leaves.device.index):
+        rc = capi.lib().ibvh_morton_encode(h, leaves.ptr, len(leaves), C.byref(types), 1 if m.compute_extrema else 0, mins, maxs,
+                                           omin, omax, _stream_ptr(leaves.device.index))
+    if rc != capi.OK:
+        _raise(rc, h, "ibvh_morton_encode")
+    return np.array(omin[:]), np.array(omax[:])
+
+
+def sort_leaves(leaves: DeviceArray):
+    types = _leaf_types(leaves)
+    h = get_handle(leaves.device)
+    with torch.cuda.device(leaves.device.index):
+        rc = capi.lib().ibvh_sort_leaves(h, leaves.ptr, len(leaves), C.byref(types), _stream_ptr(leaves.device.index))
+    if rc != capi.OK:
+        _raise(rc, h, "ibvh_sort_leaves")
+
+
+def aggregate(leaves: DeviceArray, node_type: VolumeType = None, built_level: int = 1) -> DeviceArray:
+    types = _leaf_types(leaves, node_type)
+    node_type = node_type or BBox({4: np.float32, 8: np.float64}[types.float_bytes])
+    n = len(leaves)
+    nodes = DeviceArray.empty(int(capi.lib().ibvh_num_nodes(n)), node_type.dtype, leaves.device)
+    h = get_handle(leaves.device)
+    with torch.cuda.device(leaves.device.index):
+        rc = capi.lib().ibvh_aggregate(h, leaves.ptr, n, C.byref(types), nodes.ptr if len(nodes) else None, int(built_level),
+                                       _stream_ptr(leaves.device.index))
+    if rc != capi.OK:
+        _raise(rc, h, "ibvh_aggregate")
+    return nodes

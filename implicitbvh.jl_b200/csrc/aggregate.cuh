@@ -1,0 +1,150 @@
+// aggregate.cuh — gather of the Morton-sorted leaves fused with the bottom-up bounding-volume merge.
+// Replaces the tail of the BVH constructor: the struct movement of AK.sort! (src/build.jl:248-253)
+// and aggregate_oibvh! / _aggregate_last_level_at! / _aggregate_level_at! (src/build.jl:366-523).
+//
+// B200 design: one CTA owns a tile of TILE consecutive *sorted* leaf positions. It gathers the tile's
+// leaves through the sort permutation into shared memory, streams them back to the caller's leaf
+// array with coalesced vector stores, and — because the implicit tree maps a tile of 2^k leaves onto
+// a contiguous run of 2^(k-j) nodes on each of the k levels above — merges up to log2(TILE) levels
+// entirely in shared memory, writing each level's run out once. The remaining top levels are walked
+// by re-running the same tile scheme on the last written level (a handful of CTAs), so a 10 M-leaf
+// tree needs 3 launches instead of the reference's 24 dependent per-level launches.
+#pragma once
+#include "common.cuh"
+
+namespace ibvh {
+
+// Source record of the gather: a wrapped leaf (in-place path: the copy streamed out by the encode
+// kernel) or a raw volume (wrap path: index = original position + 1, build.jl:345-349).
+template <class L, class SRC> struct GatherSrc;
+template <class L> struct GatherSrc<L, L> {
+    static IBVH_D L make(const L* src, uint32_t p, typename L::mor_t key) { L l = src[p]; l.morton = key; return l; }
+};
+template <class L> struct GatherSrc<L, typename L::vol_t> {
+    static IBVH_D L make(const typename L::vol_t* src, uint32_t p, typename L::mor_t key) {
+        L l;
+        unsigned char* b = (unsigned char*)&l;
+#pragma unroll
+        for (int k = 0; k < (int)sizeof(L); ++k) b[k] = 0;
+        l.volume = src[p];
+        l.index = (typename L::idx_t)(p + 1u);
+        l.morton = key;
+        return l;
+    }
+};
+
+struct LevelPlan {
+    int32_t src_level;       // level whose nodes (or leaves, if == levels) are the tile input
+    int32_t stop_level;      // lowest level (numerically) this launch produces: max(built_level, src_level - log2(TILE))
+};
+
+// Merge the levels above a tile whose input volumes sit in shared memory.
+//   in_count: number of input slots of the tile (TILE); tile index t; input level `lvl_in`.
+//   sbuf0/sbuf1: ping-pong node buffers of TILE/2 and TILE/4 entries.
+template <class N, int TILE, int THREADS, class LOADPAIR>
+IBVH_D void merge_tile_levels(N* nodes, const TreeInfo& ti, int lvl_in, int stop_level, int64_t tile, N* sbuf0, N* sbuf1, LOADPAIR first_level) {
+    // first produced level: lvl_in - 1, from the tile input through `first_level(j, left_only)`
+    int lvl = lvl_in - 1;
+    int count = TILE / 2;
+    N* cur = sbuf0;
+    N* nxt = sbuf1;
+    {
+        const int64_t base = tile * count;                 // 0-based index within level `lvl`
+        const int64_t nreal = ti.level_nreal[lvl];
+        const int64_t nreal_child = ti.level_nreal[lvl + 1];
+        for (int j = threadIdx.x; j < count; j += THREADS) {
+            int64_t gi = base + j;
+            if (gi < nreal) {
+                bool right_virtual = (2 * gi + 1) >= nreal_child;
+                N v = first_level(j, right_virtual);
+                cur[j] = v;
+                if (lvl >= stop_level) nodes[ti.level_start[lvl] + gi] = v;
+            }
+        }
+    }
+    __syncthreads();
+    while (lvl - 1 >= stop_level && count > 1) {
+        lvl -= 1;
+        count >>= 1;
+        const int64_t base = tile * count;
+        const int64_t nreal = ti.level_nreal[lvl];
+        const int64_t nreal_child = ti.level_nreal[lvl + 1];
+        for (int j = threadIdx.x; j < count; j += THREADS) {
+            int64_t gi = base + j;
+            if (gi < nreal) {
+                // _aggregate_level_at!, build.jl:503-523: right child virtual -> copy the left child
+                N v = ((2 * gi + 1) >= nreal_child) ? cur[2 * j] : merge(cur[2 * j], cur[2 * j + 1]);
+                nxt[j] = v;
+                nodes[ti.level_start[lvl] + gi] = v;
+            }
+        }
+        __syncthreads();
+        N* t = cur; cur = nxt; nxt = t;
+    }
+}
+
+// Gather + write-back + bottom levels. Dynamic shared memory: TILE leaves + TILE/2 + TILE/4 nodes.
+// GATHER == false: leaves are already sorted in `leaves` (stand-alone ibvh_aggregate): no permutation,
+// no write-back.
+template <class L, class SRC, class N, int TILE, int THREADS, bool GATHER>
+__global__ void __launch_bounds__(THREADS) gather_merge_kernel(const SRC* __restrict__ src, const uint32_t* __restrict__ perm,
+                                                              const typename L::mor_t* __restrict__ keys_sorted,
+                                                              L* leaves, N* nodes, TreeInfo ti, int stop_level) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    L* sleaf = (L*)smem_raw;
+    N* sbuf0 = (N*)(smem_raw + ((sizeof(L) * TILE + 15) & ~size_t(15)));
+    N* sbuf1 = sbuf0 + TILE / 2;
+    const int64_t tile = blockIdx.x;
+    const int64_t base = tile * TILE;
+    const int tile_n = (int)min((int64_t)TILE, ti.n - base);
+
+    if constexpr (GATHER) {
+        for (int j = threadIdx.x; j < tile_n; j += THREADS) {
+            uint32_t p = perm[base + j];
+            sleaf[j] = GatherSrc<L, SRC>::make(src, p, keys_sorted[base + j]);
+        }
+        __syncthreads();
+        // coalesced write-back of the tile (sizeof(L) is a multiple of 4; full tiles are 16-byte multiples)
+        const size_t bytes = (size_t)tile_n * sizeof(L);
+        unsigned char* dst = (unsigned char*)(leaves + base);
+        if ((bytes & 15) == 0 && ((uintptr_t)dst & 15) == 0) {
+            const uint4* s4 = (const uint4*)smem_raw;
+            uint4* d4 = (uint4*)dst;
+            for (size_t k = threadIdx.x; k < bytes / 16; k += THREADS) d4[k] = s4[k];
+        } else {
+            const uint32_t* s1 = (const uint32_t*)smem_raw;
+            uint32_t* d1 = (uint32_t*)dst;
+            for (size_t k = threadIdx.x; k < bytes / 4; k += THREADS) d1[k] = s1[k];
+        }
+    } else {
+        for (int j = threadIdx.x; j < tile_n; j += THREADS) sleaf[j] = leaves[base + j];
+        __syncthreads();
+    }
+    if (ti.levels < 2) return;
+    // _aggregate_last_level_at!, build.jl:427-457
+    merge_tile_levels<N, TILE, THREADS>(nodes, ti, ti.levels, stop_level, tile, sbuf0, sbuf1,
+        [&](int j, bool right_virtual) -> N {
+            return right_virtual ? NodeOps<N>::convert(sleaf[2 * j].volume)
+                                 : NodeOps<N>::merge_leaves(sleaf[2 * j].volume, sleaf[2 * j + 1].volume);
+        });
+}
+
+// Upper levels: tile input = nodes of level `src_level` already in global memory.
+template <class N, int TILE, int THREADS>
+__global__ void __launch_bounds__(THREADS) merge_levels_kernel(N* nodes, TreeInfo ti, int src_level, int stop_level) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    N* sin = (N*)smem_raw;
+    N* sbuf0 = sin + TILE;
+    N* sbuf1 = sbuf0 + TILE / 2;
+    const int64_t tile = blockIdx.x;
+    const int64_t base = tile * TILE;
+    const int64_t nreal_in = ti.level_nreal[src_level];
+    const int tile_n = (int)max((int64_t)0, min((int64_t)TILE, nreal_in - base));
+    const N* in = nodes + ti.level_start[src_level] + base;
+    for (int j = threadIdx.x; j < tile_n; j += THREADS) sin[j] = in[j];
+    __syncthreads();
+    merge_tile_levels<N, TILE, THREADS>(nodes, ti, src_level, stop_level, tile, sbuf0, sbuf1,
+        [&](int j, bool right_virtual) -> N { return right_virtual ? sin[2 * j] : merge(sin[2 * j], sin[2 * j + 1]); });
+}
+
+}  // namespace ibvh

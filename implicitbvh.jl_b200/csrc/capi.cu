@@ -1,0 +1,741 @@
+// capi.cu — extern "C" entry points of libibvh_b200.so (declared in include/ibvh.h): argument
+// checks mirroring the reference's @argcheck's, type dispatch onto the kernel templates, workspace
+// carving and the launch sequences. No CPU fallback: without a device every call fails loudly.
+#include <climits>
+#include <cmath>
+#include <new>
+
+#include "aggregate.cuh"
+#include "common.cuh"
+#include "handle.cuh"
+#include "morton.cuh"
+#include "radix_sort.cuh"
+#include "traverse.cuh"
+
+using namespace ibvh;
+
+namespace {
+
+template <class X> struct Tag { using type = X; };
+
+// ---- type dispatch --------------------------------------------------------------------------------
+template <class V, class F> int dispatch_im(const ibvh_types_t& t, F&& f) {
+    if (t.index_bytes == 4) {
+        if (t.morton_bytes == 2) return f(Tag<Leaf<V, int32_t, uint16_t>>{});
+        if (t.morton_bytes == 4) return f(Tag<Leaf<V, int32_t, uint32_t>>{});
+        if (t.morton_bytes == 8) return f(Tag<Leaf<V, int32_t, uint64_t>>{});
+    } else if (t.index_bytes == 8) {
+        if (t.morton_bytes == 2) return f(Tag<Leaf<V, int64_t, uint16_t>>{});
+        if (t.morton_bytes == 4) return f(Tag<Leaf<V, int64_t, uint32_t>>{});
+        if (t.morton_bytes == 8) return f(Tag<Leaf<V, int64_t, uint64_t>>{});
+    }
+    return IBVH_ERR_UNSUPPORTED;
+}
+template <class F> int dispatch_leaf(const ibvh_types_t& t, F&& f) {
+    if (t.float_bytes == 4) {
+        if (t.leaf_kind == IBVH_BSPHERE) return dispatch_im<BSphere<float>>(t, f);
+        if (t.leaf_kind == IBVH_BBOX) return dispatch_im<BBox<float>>(t, f);
+    }
+#ifdef IBVH_ENABLE_F64
+    if (t.float_bytes == 8) {
+        if (t.leaf_kind == IBVH_BSPHERE) return dispatch_im<BSphere<double>>(t, f);
+        if (t.leaf_kind == IBVH_BBOX) return dispatch_im<BBox<double>>(t, f);
+    }
+#endif
+    return IBVH_ERR_UNSUPPORTED;
+}
+// node type for a leaf type: BBox nodes for everything; BSphere nodes only over BSphere leaves
+// (the reference has no BSphere(::BBox) conversion, merge.jl).
+template <class L, class F> int dispatch_node(const ibvh_types_t& t, F&& f) {
+    using T = typename L::value_type;
+    if (t.node_kind == IBVH_BBOX) return f(Tag<BBox<T>>{});
+    if (t.node_kind == IBVH_BSPHERE) {
+        if constexpr (L::vol_t::kind == IBVH_BSPHERE) return f(Tag<BSphere<T>>{});
+        else return IBVH_ERR_ARGUMENT;
+    }
+    return IBVH_ERR_UNSUPPORTED;
+}
+
+bool types_ok(const ibvh_types_t* t) {
+    if (!t) return false;
+    if (t->leaf_kind != IBVH_BSPHERE && t->leaf_kind != IBVH_BBOX) return false;
+    if (t->node_kind != IBVH_BSPHERE && t->node_kind != IBVH_BBOX) return false;
+    if (t->float_bytes != 4 && t->float_bytes != 8) return false;
+    if (t->index_bytes != 4 && t->index_bytes != 8) return false;
+    if (t->morton_bytes != 2 && t->morton_bytes != 4 && t->morton_bytes != 8) return false;
+    return true;
+}
+
+int grid_for(int64_t n, int threads, int per_thread, int cap) {
+    int64_t g = (n + (int64_t)threads * per_thread - 1) / ((int64_t)threads * per_thread);
+    if (g < 1) g = 1;
+    if (g > cap) g = cap;
+    return (int)g;
+}
+
+#define IBVH_LAUNCH_CHECK(h, what)                                                   \
+    do {                                                                             \
+        cudaError_t _e = cudaGetLastError();                                         \
+        if (_e != cudaSuccess) { (h)->set_cuda_error(_e, what); return IBVH_ERR_CUDA; } \
+    } while (0)
+
+// ---- radix sort driver ---------------------------------------------------------------------------------
+// keysA holds the input keys; hist holds the raw per-pass histograms. On return the sorted keys / the
+// permutation are in *keys_out / *vals_out (one of the ping-pong buffers).
+template <class M>
+int sort_pairs(ibvh_handle* h, M* keysA, M* keysB, uint32_t* valsA, uint32_t* valsB, int64_t n, uint32_t* hist,
+               uint32_t* lookback, uint32_t* tickets, cudaStream_t st, M** keys_out, uint32_t** vals_out) {
+    constexpr int P = radix_passes<M>();
+    const int64_t tiles = (n + sort_tile<M>() - 1) / sort_tile<M>();
+    { ProfScope _ps(h, st, "scan_hist_kernel");
+    scan_hist_kernel<<<P, 256, 0, st>>>(hist);
+    }
+    IBVH_LAUNCH_CHECK(h, "scan_hist_kernel");
+    M* kin = keysA; M* kout = keysB;
+    uint32_t* vin = nullptr; uint32_t* vout = valsB; uint32_t* vother = valsA;
+    for (int p = 0; p < P; ++p) {
+        { ProfScope _ps(h, st, "onesweep_kernel");
+        onesweep_kernel<M><<<(unsigned)tiles, kSortThreads, 0, st>>>(kin, kout, vin, vout, n, hist + p * kRadixBins,
+                                                                    lookback + (size_t)p * tiles * kRadixBins, tickets + p, p * kRadixBits);
+        }
+        IBVH_LAUNCH_CHECK(h, "onesweep_kernel");
+        M* tk = kin; kin = kout; kout = tk;
+        uint32_t* nv = vout; vout = vother; vother = nv; vin = nv;
+    }
+    *keys_out = kin;
+    *vals_out = vin;
+    return IBVH_OK;
+}
+
+constexpr int kMergeTile = 1024;
+constexpr int kMergeThreads = 256;
+constexpr int kMergeLevels = 10;   // log2(kMergeTile)
+
+template <class L, class N> size_t gather_smem_bytes() {
+    return ((sizeof(L) * kMergeTile + 15) & ~size_t(15)) + sizeof(N) * (kMergeTile / 2 + kMergeTile / 4);
+}
+template <class N> size_t merge_smem_bytes() { return sizeof(N) * (kMergeTile + kMergeTile / 2 + kMergeTile / 4); }
+
+// upper levels after the tile kernel produced levels-1 .. levels-kMergeLevels
+template <class N>
+int merge_upper_levels(ibvh_handle* h, N* nodes, const TreeInfo& ti, int stop_level, cudaStream_t st) {
+    int src = ti.levels - kMergeLevels;
+    {   // function attributes are per device: set on every call (cheap)
+        cudaError_t e = cudaFuncSetAttribute(merge_levels_kernel<N, kMergeTile, kMergeThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)merge_smem_bytes<N>());
+        if (e != cudaSuccess) { h->set_cuda_error(e, "cudaFuncSetAttribute(merge_levels)"); return IBVH_ERR_CUDA; }
+    }
+    while (src > stop_level) {
+        int stop = src - kMergeLevels > stop_level ? src - kMergeLevels : stop_level;
+        int64_t tiles = (ti.level_nreal[src] + kMergeTile - 1) / kMergeTile;
+        { ProfScope _ps(h, st, "merge_levels_kernel");
+        merge_levels_kernel<N, kMergeTile, kMergeThreads><<<(unsigned)tiles, kMergeThreads, merge_smem_bytes<N>(), st>>>(nodes, ti, src, stop);
+        }
+        IBVH_LAUNCH_CHECK(h, "merge_levels_kernel");
+        src -= kMergeLevels;
+    }
+    return IBVH_OK;
+}
+
+template <class L, class SRC, class N, bool GATHER>
+int launch_gather_merge(ibvh_handle* h, const SRC* src, const uint32_t* perm, const typename L::mor_t* keys_sorted, L* leaves, N* nodes,
+                        const TreeInfo& ti, int stop_level, cudaStream_t st) {
+    auto kern = gather_merge_kernel<L, SRC, N, kMergeTile, kMergeThreads, GATHER>;
+    {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gather_smem_bytes<L, N>());
+        if (e != cudaSuccess) { h->set_cuda_error(e, "cudaFuncSetAttribute(gather_merge)"); return IBVH_ERR_CUDA; }
+    }
+    int64_t tiles = (ti.n + kMergeTile - 1) / kMergeTile;
+    { ProfScope _ps(h, st, "gather_merge_kernel");
+    kern<<<(unsigned)tiles, kMergeThreads, gather_smem_bytes<L, N>(), st>>>(src, perm, keys_sorted, leaves, nodes, ti, stop_level);
+    }
+    IBVH_LAUNCH_CHECK(h, "gather_merge_kernel");
+    return IBVH_OK;
+}
+
+struct SortScratch {
+    void* keysA; void* keysB; uint32_t* valsA; uint32_t* valsB; uint32_t* hist; uint32_t* lookback; uint32_t* tickets; void* copy;
+};
+
+template <class L> size_t build_workspace_bytes(int64_t n, bool need_copy) {
+    using M = typename L::mor_t;
+    constexpr int P = radix_passes<M>();
+    const int64_t tiles = (n + sort_tile<M>() - 1) / sort_tile<M>();
+    size_t b = 0;
+    b += 2 * ibvh_handle::padded((size_t)n * sizeof(M));
+    b += 2 * ibvh_handle::padded((size_t)n * 4);
+    b += ibvh_handle::padded((size_t)P * kRadixBins * 4);
+    b += ibvh_handle::padded((size_t)P * tiles * kRadixBins * 4);
+    if (need_copy) b += ibvh_handle::padded((size_t)n * sizeof(L));
+    return b + 4096;
+}
+
+template <class L> int carve_sort_scratch(ibvh_handle* h, int64_t n, bool need_copy, SortScratch* s, cudaStream_t st) {
+    using M = typename L::mor_t;
+    constexpr int P = radix_passes<M>();
+    if (n >= (int64_t(1) << 30)) { h->set_error("n >= 2^30 leaves not supported by the 32-bit look-back words of this build"); return IBVH_ERR_UNSUPPORTED; }
+    const int64_t tiles = (n + sort_tile<M>() - 1) / sort_tile<M>();
+    int rc = h->reserve(build_workspace_bytes<L>(n, need_copy));
+    if (rc != IBVH_OK) return rc;
+    h->reset();
+    s->keysA = h->alloc<M>(n); s->keysB = h->alloc<M>(n);
+    s->valsA = h->alloc<uint32_t>(n); s->valsB = h->alloc<uint32_t>(n);
+    s->hist = h->alloc<uint32_t>((size_t)P * kRadixBins);
+    s->lookback = h->alloc<uint32_t>((size_t)P * tiles * kRadixBins);
+    s->copy = need_copy ? (void*)h->alloc<L>(n) : nullptr;
+    s->tickets = (uint32_t*)(h->d_small + kSmallTickets);
+    if (!s->keysA || !s->keysB || !s->valsA || !s->valsB || !s->hist || !s->lookback || (need_copy && !s->copy)) { h->set_error("workspace carve failed"); return IBVH_ERR_ALLOC; }
+    IBVH_CUDA_TRY(h, cudaMemsetAsync(s->lookback, 0, (size_t)P * tiles * kRadixBins * 4, st));
+    return IBVH_OK;
+}
+
+// user-supplied bounds -> device (6 T's) through the pinned block
+template <class T> int upload_user_bounds(ibvh_handle* h, const double* mins, const double* maxs, cudaStream_t st, T** d_out) {
+    if (!mins || !maxs) return IBVH_ERR_ARGUMENT;
+    // the pinned block may still be in flight from a previous call on this stream: wait for it
+    IBVH_CUDA_TRY(h, cudaStreamSynchronize(st));
+    T* hp = (T*)(h->h_pinned + 1024);
+    for (int k = 0; k < 3; ++k) { hp[k] = (T)mins[k]; hp[3 + k] = (T)maxs[k]; }
+    T* d = (T*)(h->d_small + kSmallBoundsF + 128);
+    IBVH_CUDA_TRY(h, cudaMemcpyAsync(d, hp, 6 * sizeof(T), cudaMemcpyHostToDevice, st));
+    *d_out = d;
+    return IBVH_OK;
+}
+
+template <class T> int read_used_bounds(ibvh_handle* h, double* out_mins, double* out_maxs, cudaStream_t st) {
+    if (!out_mins && !out_maxs) return IBVH_OK;
+    T* hp = (T*)(h->h_pinned + 2048);
+    IBVH_CUDA_TRY(h, cudaMemcpyAsync(hp, h->d_small + kSmallBoundsF, 6 * sizeof(T), cudaMemcpyDeviceToHost, st));
+    IBVH_CUDA_TRY(h, cudaStreamSynchronize(st));
+    for (int k = 0; k < 3; ++k) { if (out_mins) out_mins[k] = (double)hp[k]; if (out_maxs) out_maxs[k] = (double)hp[3 + k]; }
+    return IBVH_OK;
+}
+
+// bounds + encode. SRC == L (in place, optional copy) or SRC == volume (wrap path)
+template <class L, class SRC, bool COPY>
+int launch_encode(ibvh_handle* h, const SRC* src, int64_t n, int compute_extrema, const double* mins, const double* maxs,
+                  typename L::mor_t* keys, L* copy, uint32_t* hist, uint32_t* tickets, cudaStream_t st) {
+    using T = typename L::value_type;
+    using M = typename L::mor_t;
+    using Ord = typename OrdOf<T>::type;
+    constexpr int P = radix_passes<M>();
+    Ord* bounds = (Ord*)(h->d_small + kSmallBounds);
+    T* used = (T*)(h->d_small + kSmallBoundsF);
+    T* user = nullptr;
+    if (!compute_extrema) { int rc = upload_user_bounds<T>(h, mins, maxs, st, &user); if (rc != IBVH_OK) return rc; }
+    { ProfScope _ps(h, st, "init_build_kernel");
+    init_build_kernel<T><<<8, 256, 0, st>>>(bounds, hist, P * kRadixBins, tickets, 16);
+    }
+    IBVH_LAUNCH_CHECK(h, "init_build_kernel");
+    const int grid = grid_for(n, 256, 4, h->sm_count * 8);
+    if (compute_extrema) {
+        { ProfScope _ps(h, st, "bounds_kernel");
+        bounds_kernel<SRC, T><<<grid, 256, 0, st>>>(src, n, bounds);
+        }
+        IBVH_LAUNCH_CHECK(h, "bounds_kernel");
+    }
+    { ProfScope _ps(h, st, "encode_kernel");
+    encode_kernel<SRC, L, COPY><<<grid, 256, 0, st>>>(src, n, compute_extrema ? bounds : nullptr, user, used, keys, copy, hist);
+    }
+    IBVH_LAUNCH_CHECK(h, "encode_kernel");
+    return IBVH_OK;
+}
+
+// ---- BVH(...) pipeline -----------------------------------------------------------------------------------
+template <class L, class N>
+int build_impl(ibvh_handle* h, const void* d_volumes, void* d_leaves, int64_t n, void* d_nodes, int64_t built_level,
+               int compute_extrema, const double* mins, const double* maxs, cudaStream_t st) {
+    using M = typename L::mor_t;
+    using V = typename L::vol_t;
+    ibvh_tree_t tree;
+    int rc = make_tree(n, &tree);
+    if (rc != IBVH_OK) return rc;
+    if (built_level < 1 || built_level > tree.levels) return IBVH_ERR_ARGUMENT;      // build.jl:314
+    const bool wrap = d_volumes != nullptr;
+    SortScratch s;
+    rc = carve_sort_scratch<L>(h, n, !wrap, &s, st);
+    if (rc != IBVH_OK) return rc;
+    if (wrap) rc = launch_encode<L, V, false>(h, (const V*)d_volumes, n, compute_extrema, mins, maxs, (M*)s.keysA, nullptr, s.hist, s.tickets, st);
+    else rc = launch_encode<L, L, true>(h, (const L*)d_leaves, n, compute_extrema, mins, maxs, (M*)s.keysA, (L*)s.copy, s.hist, s.tickets, st);
+    if (rc != IBVH_OK) return rc;
+    M* keys_sorted; uint32_t* perm;
+    rc = sort_pairs<M>(h, (M*)s.keysA, (M*)s.keysB, s.valsA, s.valsB, n, s.hist, s.lookback, s.tickets, st, &keys_sorted, &perm);
+    if (rc != IBVH_OK) return rc;
+    TreeInfo ti = make_tree_info(tree);
+    // the level above the leaves is always produced (build.jl:369), further levels down to built_level
+    int stop_level = (int)(built_level < tree.levels - 1 ? built_level : tree.levels - 1);
+    if (stop_level < 1) stop_level = 1;
+    if (wrap) rc = launch_gather_merge<L, V, N, true>(h, (const V*)d_volumes, perm, keys_sorted, (L*)d_leaves, (N*)d_nodes, ti, stop_level, st);
+    else rc = launch_gather_merge<L, L, N, true>(h, (const L*)s.copy, perm, keys_sorted, (L*)d_leaves, (N*)d_nodes, ti, stop_level, st);
+    if (rc != IBVH_OK) return rc;
+    if (tree.real_nodes >= 2) rc = merge_upper_levels<N>(h, (N*)d_nodes, ti, stop_level, st);
+    return rc;
+}
+
+// ---- traversal driver ---------------------------------------------------------------------------------------
+template <class I>
+int scan_counts(ibvh_handle* h, I* counts, int64_t n, long long* block_sums, unsigned long long* d_total, cudaStream_t st) {
+    const int64_t blocks = (n + kScanTile - 1) / kScanTile;
+    { ProfScope _ps(h, st, "scan_reduce_kernel");
+    scan_reduce_kernel<I><<<(unsigned)blocks, kScanThreads, 0, st>>>(counts, n, block_sums);
+    }
+    IBVH_LAUNCH_CHECK(h, "scan_reduce_kernel");
+    { ProfScope _ps(h, st, "scan_block_sums_kernel");
+    scan_block_sums_kernel<<<1, 1024, 0, st>>>(block_sums, blocks, d_total);
+    }
+    IBVH_LAUNCH_CHECK(h, "scan_block_sums_kernel");
+    { ProfScope _ps(h, st, "scan_apply_kernel");
+    scan_apply_kernel<I><<<(unsigned)blocks, kScanThreads, 0, st>>>(counts, n, block_sums);
+    }
+    IBVH_LAUNCH_CHECK(h, "scan_apply_kernel");
+    return IBVH_OK;
+}
+
+int read_total(ibvh_handle* h, unsigned long long* d_total, int64_t* out, cudaStream_t st) {
+    unsigned long long* hp = (unsigned long long*)h->h_pinned;
+    IBVH_CUDA_TRY(h, cudaMemcpyAsync(hp, d_total, 8, cudaMemcpyDeviceToHost, st));
+    IBVH_CUDA_TRY(h, cudaStreamSynchronize(st));
+    *out = (int64_t)*hp;
+    return IBVH_OK;
+}
+
+template <int KIND, int MODE, bool PACKET, class LQ, class LT, class N, class I>
+int launch_traverse(ibvh_handle* h, const LQ* qleaves, const typename LT::value_type* points, const typename LT::value_type* dirs,
+                    const DBvh<LT, N>& bvh, const TraverseArgs& a, I* counts, IndexPair<I>* contacts, cudaStream_t st) {
+    if (a.q_count <= 0) return IBVH_OK;
+    if constexpr (PACKET) {
+        const int64_t warps = (a.q_count + 31) / 32;
+        const int64_t blocks = (warps + kPacketWarps - 1) / kPacketWarps;
+        { ProfScope _ps(h, st, "lvt_packet_kernel");
+        lvt_packet_kernel<KIND, MODE, LQ, LT, N, I><<<(unsigned)blocks, kPacketWarps * 32, 0, st>>>(qleaves, bvh, a, counts, contacts);
+        }
+        IBVH_LAUNCH_CHECK(h, "lvt_packet_kernel");
+    } else {
+        const int64_t blocks = (a.q_count + 127) / 128;
+        { ProfScope _ps(h, st, "lvt_thread_kernel");
+        lvt_thread_kernel<KIND, MODE, LQ, LT, N, I><<<(unsigned)blocks, 128, 0, st>>>(qleaves, points, dirs, bvh, a, counts, contacts);
+        }
+        IBVH_LAUNCH_CHECK(h, "lvt_thread_kernel");
+    }
+    return IBVH_OK;
+}
+
+template <int KIND, bool PACKET, class LQ, class LT, class N, class I>
+int traverse_impl(ibvh_handle* h, const LQ* qleaves, const typename LT::value_type* points, const typename LT::value_type* dirs,
+                  const DBvh<LT, N>& bvh, TraverseArgs a, uint32_t flags, void* d_counts, void* d_contacts, int64_t capacity,
+                  int64_t* num_contacts, cudaStream_t st) {
+    unsigned long long* d_total = (unsigned long long*)(h->d_small + kSmallTotal);
+    a.total = d_total;
+    a.stats = nullptr;
+    a.capacity = d_contacts ? capacity : 0;
+    *num_contacts = 0;
+    if (a.q_count <= 0) return IBVH_OK;
+    const bool unordered = (flags & IBVH_TRAVERSE_UNORDERED) != 0 && d_contacts != nullptr;
+    int rc;
+    if (unordered) {
+        IBVH_CUDA_TRY(h, cudaMemsetAsync(d_total, 0, 8, st));
+        rc = launch_traverse<KIND, kAtomic, PACKET, LQ, LT, N, I>(h, qleaves, points, dirs, bvh, a, (I*)nullptr, (IndexPair<I>*)d_contacts, st);
+        if (rc != IBVH_OK) return rc;
+        rc = read_total(h, d_total, num_contacts, st);
+        if (rc != IBVH_OK) return rc;
+        return *num_contacts > capacity ? IBVH_ERR_CAPACITY : IBVH_OK;
+    }
+    // ordered: count -> inclusive scan -> (read total) -> write
+    const int64_t blocks = (a.q_count + kScanTile - 1) / kScanTile;
+    size_t need = ibvh_handle::padded((size_t)blocks * 8) + (d_counts ? 0 : ibvh_handle::padded((size_t)a.q_count * sizeof(I))) + 4096;
+    rc = h->reserve(need);
+    if (rc != IBVH_OK) return rc;
+    h->reset();
+    long long* block_sums = h->alloc<long long>(blocks);
+    I* counts = d_counts ? (I*)d_counts : h->alloc<I>(a.q_count);
+    if (!block_sums || !counts) { h->set_error("workspace carve failed"); return IBVH_ERR_ALLOC; }
+    if ((flags & IBVH_TRAVERSE_COUNTS_VALID) && d_counts && d_contacts) {
+        // second pass only (traverse_single.jl:75): the total is the last entry of the scan
+        I* hp = (I*)(h->h_pinned + 64);
+        IBVH_CUDA_TRY(h, cudaMemcpyAsync(hp, counts + (a.q_count - 1), sizeof(I), cudaMemcpyDeviceToHost, st));
+        IBVH_CUDA_TRY(h, cudaStreamSynchronize(st));
+        *num_contacts = (int64_t)*hp;
+        if (*num_contacts == 0) return IBVH_OK;
+        if (*num_contacts > capacity) return IBVH_ERR_CAPACITY;
+        return launch_traverse<KIND, kWrite, PACKET, LQ, LT, N, I>(h, qleaves, points, dirs, bvh, a, counts, (IndexPair<I>*)d_contacts, st);
+    }
+    rc = launch_traverse<KIND, kCount, PACKET, LQ, LT, N, I>(h, qleaves, points, dirs, bvh, a, counts, (IndexPair<I>*)nullptr, st);
+    if (rc != IBVH_OK) return rc;
+    rc = scan_counts<I>(h, counts, a.q_count, block_sums, d_total, st);
+    if (rc != IBVH_OK) return rc;
+    rc = read_total(h, d_total, num_contacts, st);
+    if (rc != IBVH_OK) return rc;
+    if (!d_contacts || *num_contacts == 0) return IBVH_OK;
+    if (*num_contacts > capacity) return IBVH_ERR_CAPACITY;
+    return launch_traverse<KIND, kWrite, PACKET, LQ, LT, N, I>(h, qleaves, points, dirs, bvh, a, counts, (IndexPair<I>*)d_contacts, st);
+}
+
+int check_bvh(const ibvh_bvh_t* b, ibvh_tree_t* tree) {
+    if (!b || !types_ok(&b->types)) return IBVH_ERR_ARGUMENT;
+    int rc = make_tree(b->n, tree);
+    if (rc != IBVH_OK) return rc;
+    if (tree->levels > 32) return IBVH_ERR_ARGUMENT;                                 // traverse_single.jl:10
+    if (!b->d_leaves) return IBVH_ERR_ARGUMENT;
+    if (tree->real_nodes - tree->real_leaves > 0 && !b->d_nodes) return IBVH_ERR_ARGUMENT;
+    return IBVH_OK;
+}
+
+void shard_range(const ibvh_traverse_params_t* p, int64_t nq, int64_t* begin, int64_t* count) {
+    int64_t b = p->query_begin < 0 ? 0 : p->query_begin;
+    if (b > nq) b = nq;
+    int64_t c = p->query_count < 0 ? nq - b : p->query_count;
+    if (b + c > nq) c = nq - b;
+    *begin = b; *count = c;
+}
+
+}  // namespace
+
+// =================================================================================================================
+extern "C" {
+
+int ibvh_version(void) { return IBVH_VERSION; }
+
+const char* ibvh_status_string(int s) {
+    switch (s) {
+        case IBVH_OK: return "ok";
+        case IBVH_ERR_ARGUMENT: return "ArgumentError";
+        case IBVH_ERR_DOMAIN: return "DomainError";
+        case IBVH_ERR_UNSUPPORTED: return "unsupported type combination";
+        case IBVH_ERR_CUDA: return "CUDA error";
+        case IBVH_ERR_CAPACITY: return "contacts capacity too small";
+        case IBVH_ERR_ALLOC: return "workspace allocation failed";
+    }
+    return "unknown";
+}
+const char* ibvh_last_error(const ibvh_handle_t* h) { return h ? h->err : "null handle"; }
+
+// ---- host-only --------------------------------------------------------------------------------------------
+int ibvh_tree_shape(int64_t n, ibvh_tree_t* tree, int64_t* skips) {
+    if (!tree) return IBVH_ERR_ARGUMENT;
+    int rc = make_tree(n, tree);
+    if (rc != IBVH_OK) return rc;
+    if (skips) for (int64_t l = 1; l <= tree->levels; ++l) skips[l - 1] = skip_of_level(*tree, l);
+    return IBVH_OK;
+}
+int64_t ibvh_memory_index(const ibvh_tree_t* t, int64_t implicit_index) {                 // implicit_tree.jl:128-148
+    int64_t level = ilog2_floor_u64((uint64_t)implicit_index) + 1;
+    return implicit_index - skip_of_level(*t, level);
+}
+int ibvh_level_indices(const ibvh_tree_t* t, int64_t level, int64_t* start, int64_t* stop) {   // :156-171
+    if (level < 1 || level > t->levels) return IBVH_ERR_ARGUMENT;
+    *start = ibvh_memory_index(t, int64_t(1) << (level - 1));
+    int64_t nreal = (int64_t(1) << (level - 1)) - shr64(t->virtual_leaves, t->levels - level);
+    *stop = *start + nreal - 1;
+    return IBVH_OK;
+}
+int ibvh_isvirtual(const ibvh_tree_t* t, int64_t implicit_index) {                         // :191-199
+    int64_t level = ilog2_floor_u64((uint64_t)implicit_index) + 1;
+    int64_t level_first = int64_t(1) << (level - 1);
+    int64_t nreal = level_first - shr64(t->virtual_leaves, t->levels - level);
+    return implicit_index - level_first + 1 > nreal ? 1 : 0;
+}
+int ibvh_compute_build_level(int64_t levels, int is_float, int64_t ilevel, double flevel, int64_t* out) {   // build.jl:309-325
+    if (!out) return IBVH_ERR_ARGUMENT;
+    if (!is_float) {
+        if (ilevel < 1 || ilevel > levels) return IBVH_ERR_ARGUMENT;
+        *out = ilevel;
+    } else {
+        if (!(flevel >= 0.0 && flevel <= 1.0)) return IBVH_ERR_ARGUMENT;
+        *out = (int64_t)nearbyint((double)levels + (double)(1 - levels) * flevel);   // round half to even
+    }
+    return IBVH_OK;
+}
+int64_t ibvh_volume_bytes(int32_t kind, int32_t float_bytes) {
+    if (float_bytes != 4 && float_bytes != 8) return -1;
+    if (kind == IBVH_BSPHERE) return 4 * float_bytes;
+    if (kind == IBVH_BBOX) return 6 * float_bytes;
+    return -1;
+}
+int64_t ibvh_leaf_bytes(const ibvh_types_t* t) {
+    if (!types_ok(t)) return -1;
+    int64_t v = ibvh_volume_bytes(t->leaf_kind, t->float_bytes);
+    int64_t align = t->float_bytes;
+    if (t->index_bytes > align) align = t->index_bytes;
+    if (t->morton_bytes > align) align = t->morton_bytes;
+    int64_t off = (v + t->index_bytes - 1) / t->index_bytes * t->index_bytes + t->index_bytes;
+    off = (off + t->morton_bytes - 1) / t->morton_bytes * t->morton_bytes + t->morton_bytes;
+    return (off + align - 1) / align * align;
+}
+int64_t ibvh_num_nodes(int64_t n) {
+    ibvh_tree_t t;
+    if (make_tree(n, &t) != IBVH_OK) return -1;
+    return t.real_nodes - t.real_leaves;
+}
+
+// ---- handle -------------------------------------------------------------------------------------------------
+int ibvh_create(ibvh_handle_t** out, int device) {
+    if (!out) return IBVH_ERR_ARGUMENT;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || device < 0 || device >= count) { cudaGetLastError(); return IBVH_ERR_CUDA; }
+    ibvh_handle* h = new (std::nothrow) ibvh_handle();
+    if (!h) return IBVH_ERR_ALLOC;
+    h->device = device;
+    DeviceGuard g(device);
+    cudaDeviceProp prop;
+    if (!g.ok || cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete h; cudaGetLastError(); return IBVH_ERR_CUDA; }
+    h->sm_count = prop.multiProcessorCount;
+    if (cudaMalloc((void**)&h->d_small, ibvh_handle::kSmallBytes) != cudaSuccess ||
+        cudaMallocHost((void**)&h->h_pinned, ibvh_handle::kPinnedBytes) != cudaSuccess) {
+        if (h->d_small) cudaFree(h->d_small);
+        delete h; cudaGetLastError();
+        return IBVH_ERR_ALLOC;
+    }
+    cudaMemset(h->d_small, 0, ibvh_handle::kSmallBytes);
+    *out = h;
+    return IBVH_OK;
+}
+int ibvh_destroy(ibvh_handle_t* h) {
+    if (!h) return IBVH_OK;
+    DeviceGuard g(h->device);
+    if (h->ws) cudaFree(h->ws);
+    if (h->d_small) cudaFree(h->d_small);
+    if (h->h_pinned) cudaFreeHost(h->h_pinned);
+    delete h;
+    return IBVH_OK;
+}
+int64_t ibvh_workspace_query(const ibvh_types_t* types, int64_t n) {
+    if (!types_ok(types) || n < 1) return -1;
+    int64_t out = -1;
+    dispatch_leaf(*types, [&](auto tag) -> int { using L = typename decltype(tag)::type; out = (int64_t)build_workspace_bytes<L>(n, true); return IBVH_OK; });
+    return out;
+}
+int64_t ibvh_workspace_bytes(const ibvh_handle_t* h) { return h ? (int64_t)h->ws_bytes : -1; }
+int ibvh_release_workspace(ibvh_handle_t* h) {
+    if (!h) return IBVH_ERR_ARGUMENT;
+    DeviceGuard g(h->device);
+    if (h->ws) { IBVH_CUDA_TRY(h, cudaFree(h->ws)); h->ws = nullptr; h->ws_bytes = 0; }
+    return IBVH_OK;
+}
+
+// ---- build stages ---------------------------------------------------------------------------------------------
+int ibvh_wrap(ibvh_handle_t* h, const void* d_volumes, int64_t n, const ibvh_types_t* types, void* d_leaves, void* stream) {
+    if (!h || !types_ok(types) || n < 0) return IBVH_ERR_ARGUMENT;
+    if (n == 0) return IBVH_OK;
+    if (!d_volumes || !d_leaves) return IBVH_ERR_ARGUMENT;
+    DeviceGuard g(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    return dispatch_leaf(*types, [&](auto tag) -> int {
+        using L = typename decltype(tag)::type;
+        { ProfScope _ps(h, st, "wrap_kernel");
+        wrap_kernel<L><<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const typename L::vol_t*)d_volumes, n, (L*)d_leaves);
+        }
+        IBVH_LAUNCH_CHECK(h, "wrap_kernel");
+        return (int)IBVH_OK;
+    });
+}
+
+int ibvh_morton_encode(ibvh_handle_t* h, void* d_leaves, int64_t n, const ibvh_types_t* types, int compute_extrema,
+                       const double* mins, const double* maxs, double* out_mins, double* out_maxs, void* stream) {
+    if (!h || !types_ok(types) || n < 0) return IBVH_ERR_ARGUMENT;
+    if (n == 0) return IBVH_OK;                                              // default.jl:49
+    if (!d_leaves) return IBVH_ERR_ARGUMENT;
+    DeviceGuard g(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    return dispatch_leaf(*types, [&](auto tag) -> int {
+        using L = typename decltype(tag)::type; using M = typename L::mor_t; using T = typename L::value_type;
+        constexpr int P = radix_passes<M>();
+        int rc = h->reserve(ibvh_handle::padded((size_t)n * sizeof(M)) + ibvh_handle::padded(P * kRadixBins * 4) + 4096);
+        if (rc != IBVH_OK) return rc;
+        h->reset();
+        M* keys = h->alloc<M>(n);
+        uint32_t* hist = h->alloc<uint32_t>(P * kRadixBins);
+        rc = launch_encode<L, L, false>(h, (const L*)d_leaves, n, compute_extrema, mins, maxs, keys, nullptr, hist, (uint32_t*)(h->d_small + kSmallTickets), st);
+        if (rc != IBVH_OK) return rc;
+        { ProfScope _ps(h, st, "scatter_morton_kernel");
+        scatter_morton_kernel<L><<<(unsigned)((n + 255) / 256), 256, 0, st>>>((L*)d_leaves, n, keys);
+        }
+        IBVH_LAUNCH_CHECK(h, "scatter_morton_kernel");
+        return read_used_bounds<T>(h, out_mins, out_maxs, st);
+    });
+}
+
+int ibvh_sort_leaves(ibvh_handle_t* h, void* d_leaves, int64_t n, const ibvh_types_t* types, void* stream) {
+    if (!h || !types_ok(types) || n < 0) return IBVH_ERR_ARGUMENT;
+    if (n == 0) return IBVH_OK;
+    if (!d_leaves) return IBVH_ERR_ARGUMENT;
+    DeviceGuard g(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    return dispatch_leaf(*types, [&](auto tag) -> int {
+        using L = typename decltype(tag)::type; using M = typename L::mor_t; using T = typename L::value_type;
+        constexpr int P = radix_passes<M>();
+        SortScratch s;
+        int rc = carve_sort_scratch<L>(h, n, true, &s, st);
+        if (rc != IBVH_OK) return rc;
+        { ProfScope _ps(h, st, "init_build_kernel");
+        init_build_kernel<T><<<8, 256, 0, st>>>((typename OrdOf<T>::type*)(h->d_small + kSmallBounds), s.hist, P * kRadixBins, s.tickets, 16);
+        }
+        IBVH_LAUNCH_CHECK(h, "init_build_kernel");
+        { ProfScope _ps(h, st, "extract_keys_kernel");
+        extract_keys_kernel<L><<<grid_for(n, 256, 4, h->sm_count * 8), 256, 0, st>>>((const L*)d_leaves, n, (M*)s.keysA, (L*)s.copy, s.hist);
+        }
+        IBVH_LAUNCH_CHECK(h, "extract_keys_kernel");
+        M* keys_sorted; uint32_t* perm;
+        rc = sort_pairs<M>(h, (M*)s.keysA, (M*)s.keysB, s.valsA, s.valsB, n, s.hist, s.lookback, s.tickets, st, &keys_sorted, &perm);
+        if (rc != IBVH_OK) return rc;
+        ibvh_tree_t tree; make_tree(n, &tree);
+        TreeInfo ti = make_tree_info(tree);
+        // gather only: stop_level above every level => no node is written
+        return launch_gather_merge<L, L, BBox<T>, true>(h, (const L*)s.copy, perm, keys_sorted, (L*)d_leaves, (BBox<T>*)nullptr, ti, INT_MAX, st);
+    });
+}
+
+int ibvh_aggregate(ibvh_handle_t* h, const void* d_leaves, int64_t n, const ibvh_types_t* types, void* d_nodes, int64_t built_level, void* stream) {
+    if (!h || !types_ok(types)) return IBVH_ERR_ARGUMENT;
+    ibvh_tree_t tree;
+    int rc = make_tree(n, &tree);
+    if (rc != IBVH_OK) return rc;
+    if (built_level < 1 || built_level > tree.levels) return IBVH_ERR_ARGUMENT;
+    if (tree.real_nodes < 2) return IBVH_OK;                               // build.jl:266
+    if (!d_leaves || !d_nodes) return IBVH_ERR_ARGUMENT;
+    DeviceGuard g(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    return dispatch_leaf(*types, [&](auto tag) -> int {
+        using L = typename decltype(tag)::type;
+        return dispatch_node<L>(*types, [&](auto ntag) -> int {
+            using N = typename decltype(ntag)::type;
+            TreeInfo ti = make_tree_info(tree);
+            int stop_level = (int)(built_level < tree.levels - 1 ? built_level : tree.levels - 1);
+            int r = launch_gather_merge<L, L, N, false>(h, (const L*)nullptr, nullptr, nullptr, (L*)d_leaves, (N*)d_nodes, ti, stop_level, st);
+            if (r != IBVH_OK) return r;
+            return merge_upper_levels<N>(h, (N*)d_nodes, ti, stop_level, st);
+        });
+    });
+}
+
+int ibvh_build(ibvh_handle_t* h, const void* d_volumes, void* d_leaves, int64_t n, const ibvh_types_t* types, void* d_nodes,
+               int64_t built_level, int compute_extrema, const double* mins, const double* maxs, void* stream) {
+    if (!h || !types_ok(types)) return IBVH_ERR_ARGUMENT;
+    if (n < 1) return IBVH_ERR_DOMAIN;                                     // implicit_tree.jl:78-80
+    if (!d_leaves) return IBVH_ERR_ARGUMENT;
+    if (ibvh_num_nodes(n) > 0 && !d_nodes) return IBVH_ERR_ARGUMENT;
+    DeviceGuard g(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    return dispatch_leaf(*types, [&](auto tag) -> int {
+        using L = typename decltype(tag)::type;
+        return dispatch_node<L>(*types, [&](auto ntag) -> int {
+            using N = typename decltype(ntag)::type;
+            return build_impl<L, N>(h, d_volumes, d_leaves, n, d_nodes, built_level, compute_extrema, mins, maxs, st);
+        });
+    });
+}
+
+// ---- traversals ---------------------------------------------------------------------------------------------------
+int ibvh_traverse_single(ibvh_handle_t* h, const ibvh_bvh_t* bvh, const ibvh_traverse_params_t* p, void* d_counts, void* d_contacts,
+                         int64_t capacity, int64_t* num_contacts, void* stream) {
+    if (!h || !p || !num_contacts) return IBVH_ERR_ARGUMENT;
+    ibvh_tree_t tree;
+    int rc = check_bvh(bvh, &tree);
+    if (rc != IBVH_OK) return rc;
+    if (!(bvh->built_level <= p->start_level && p->start_level <= tree.levels)) return IBVH_ERR_ARGUMENT;   // traverse_single.jl:9-11
+    *num_contacts = 0;
+    if (tree.real_nodes <= 1) return IBVH_OK;                               // traverse_single.jl:17-21
+    DeviceGuard g(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    return dispatch_leaf(bvh->types, [&](auto tag) -> int {
+        using L = typename decltype(tag)::type; using I = typename L::idx_t;
+        return dispatch_node<L>(bvh->types, [&](auto ntag) -> int {
+            using N = typename decltype(ntag)::type;
+            DBvh<L, N> d{(const L*)bvh->d_leaves, (const N*)bvh->d_nodes, make_tree_info(tree)};
+            TraverseArgs a{};
+            shard_range(p, bvh->n, &a.q_begin, &a.q_count);
+            a.start_level = (int32_t)p->start_level;
+            a.flip = 0;
+            if (p->flags & IBVH_TRAVERSE_REFERENCE_SHAPED)
+                return traverse_impl<kSingle, false, L, L, N, I>(h, d.leaves, nullptr, nullptr, d, a, p->flags, d_counts, d_contacts, capacity, num_contacts, st);
+            return traverse_impl<kSingle, true, L, L, N, I>(h, d.leaves, nullptr, nullptr, d, a, p->flags, d_counts, d_contacts, capacity, num_contacts, st);
+        });
+    });
+}
+
+int ibvh_traverse_pair(ibvh_handle_t* h, const ibvh_bvh_t* queries, const ibvh_bvh_t* target, const ibvh_traverse_params_t* p,
+                       void* d_counts, void* d_contacts, int64_t capacity, int64_t* num_contacts, void* stream) {
+    if (!h || !p || !num_contacts || !queries || !target) return IBVH_ERR_ARGUMENT;
+    ibvh_tree_t tq, tt;
+    if (!types_ok(&queries->types) || queries->n < 1 || !queries->d_leaves) return IBVH_ERR_ARGUMENT;
+    int rc = make_tree(queries->n, &tq);
+    if (rc != IBVH_OK) return rc;
+    rc = check_bvh(target, &tt);
+    if (rc != IBVH_OK) return rc;
+    if (tq.levels > 32) return IBVH_ERR_ARGUMENT;
+    // both trees must share leaf / index / node types (traverse_pair.jl:50-52)
+    const ibvh_types_t &a1 = queries->types, &a2 = target->types;
+    if (a1.leaf_kind != a2.leaf_kind || a1.float_bytes != a2.float_bytes || a1.index_bytes != a2.index_bytes ||
+        a1.morton_bytes != a2.morton_bytes || a1.node_kind != a2.node_kind) return IBVH_ERR_ARGUMENT;
+    if (!(target->built_level <= p->start_level && p->start_level <= tt.levels)) return IBVH_ERR_ARGUMENT;   // traverse_pair.jl:11-12
+    *num_contacts = 0;
+    DeviceGuard g(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    return dispatch_leaf(target->types, [&](auto tag) -> int {
+        using L = typename decltype(tag)::type; using I = typename L::idx_t;
+        return dispatch_node<L>(target->types, [&](auto ntag) -> int {
+            using N = typename decltype(ntag)::type;
+            DBvh<L, N> d{(const L*)target->d_leaves, (const N*)target->d_nodes, make_tree_info(tt)};
+            TraverseArgs a{};
+            shard_range(p, queries->n, &a.q_begin, &a.q_count);
+            a.start_level = (int32_t)p->start_level;
+            a.flip = p->flip ? 1 : 0;
+            if (p->flags & IBVH_TRAVERSE_REFERENCE_SHAPED)
+                return traverse_impl<kPair, false, L, L, N, I>(h, (const L*)queries->d_leaves, nullptr, nullptr, d, a, p->flags, d_counts, d_contacts, capacity, num_contacts, st);
+            return traverse_impl<kPair, true, L, L, N, I>(h, (const L*)queries->d_leaves, nullptr, nullptr, d, a, p->flags, d_counts, d_contacts, capacity, num_contacts, st);
+        });
+    });
+}
+
+int ibvh_traverse_rays(ibvh_handle_t* h, const ibvh_bvh_t* bvh, const void* d_points, const void* d_directions, int64_t nrays,
+                       const ibvh_traverse_params_t* p, void* d_counts, void* d_contacts, int64_t capacity, int64_t* num_contacts, void* stream) {
+    if (!h || !p || !num_contacts || nrays < 0) return IBVH_ERR_ARGUMENT;
+    ibvh_tree_t tree;
+    int rc = check_bvh(bvh, &tree);
+    if (rc != IBVH_OK) return rc;
+    if (!(bvh->built_level <= p->start_level && p->start_level <= tree.levels)) return IBVH_ERR_ARGUMENT;   // leaf_vs_tree.jl:11-15
+    *num_contacts = 0;
+    if (nrays == 0) return IBVH_OK;                                           // leaf_vs_tree.jl:22-26
+    if (!d_points || !d_directions) return IBVH_ERR_ARGUMENT;
+    DeviceGuard g(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    return dispatch_leaf(bvh->types, [&](auto tag) -> int {
+        using L = typename decltype(tag)::type; using I = typename L::idx_t; using T = typename L::value_type;
+        return dispatch_node<L>(bvh->types, [&](auto ntag) -> int {
+            using N = typename decltype(ntag)::type;
+            DBvh<L, N> d{(const L*)bvh->d_leaves, (const N*)bvh->d_nodes, make_tree_info(tree)};
+            TraverseArgs a{};
+            shard_range(p, nrays, &a.q_begin, &a.q_count);
+            a.start_level = (int32_t)p->start_level;
+            a.flip = 0;
+            a.id_base = p->id_base;
+            return traverse_impl<kRays, false, L, L, N, I>(h, (const L*)nullptr, (const T*)d_points, (const T*)d_directions, d, a, p->flags,
+                                                           d_counts, d_contacts, capacity, num_contacts, st);
+        });
+    });
+}
+
+int ibvh_profile_enable(ibvh_handle_t* h, int on) {
+    if (!h) return IBVH_ERR_ARGUMENT;
+    h->prof_on = on != 0;
+    h->prof_n = 0;
+    return IBVH_OK;
+}
+int ibvh_profile_count(ibvh_handle_t* h) { return h ? h->prof_n : -1; }
+int ibvh_profile_get(ibvh_handle_t* h, int i, char* name, int name_cap, float* ms) {
+    if (!h || i < 0 || i >= h->prof_n || !ms) return IBVH_ERR_ARGUMENT;
+    DeviceGuard g(h->device);
+    IBVH_CUDA_TRY(h, cudaEventSynchronize(h->prof_ev[i][1]));
+    IBVH_CUDA_TRY(h, cudaEventElapsedTime(ms, h->prof_ev[i][0], h->prof_ev[i][1]));
+    if (name && name_cap > 0) { snprintf(name, (size_t)name_cap, "%s", h->prof_name[i]); }
+    return IBVH_OK;
+}
+int ibvh_profile_reset(ibvh_handle_t* h) { if (!h) return IBVH_ERR_ARGUMENT; h->prof_n = 0; return IBVH_OK; }
+
+int ibvh_last_traversal_stats(ibvh_handle_t* h, int64_t out[3]) {
+    if (!h || !out) return IBVH_ERR_ARGUMENT;
+    for (int k = 0; k < 3; ++k) out[k] = h->last_stats[k];
+    return IBVH_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,204 @@
+// common.cuh — device-side restatement of the reference's scalar layer (L1–L3 in SURVEY.md §1):
+// isbits layouts, merges, contact / ray predicates and implicit-tree index math.
+//
+// Bit-exactness contract (SURVEY.md §7 "hard parts"): this translation unit set is compiled with
+// -fmad=false (Julia never contracts a*b+c), default -prec-div=true -prec-sqrt=true -ftz=false, and
+// every expression keeps the reference's left-to-right association.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ibvh.h"
+
+#define IBVH_HD __host__ __device__ __forceinline__
+#define IBVH_D __device__ __forceinline__
+
+namespace ibvh {
+
+// ---- layouts (bsphere.jl:26-29, bbox.jl:35-38, bounding_volumes.jl:55-59, traverse.jl:6) ----
+template <class T> struct BSphere { T x[3]; T r; using value_type = T; static constexpr int kind = IBVH_BSPHERE; };
+template <class T> struct BBox    { T lo[3]; T up[3]; using value_type = T; static constexpr int kind = IBVH_BBOX; };
+template <class V, class I, class M> struct Leaf {
+    V volume; I index; M morton;
+    using vol_t = V; using idx_t = I; using mor_t = M; using value_type = typename V::value_type;
+};
+template <class I> struct IndexPair { I a, b; };
+
+static_assert(sizeof(Leaf<BSphere<float>, int32_t, uint32_t>) == 24, "layout");
+static_assert(sizeof(Leaf<BSphere<float>, int32_t, uint16_t>) == 24, "layout");
+static_assert(sizeof(Leaf<BSphere<float>, int64_t, uint64_t>) == 32, "layout");
+static_assert(sizeof(Leaf<BBox<float>, int32_t, uint32_t>) == 32, "layout");
+static_assert(sizeof(Leaf<BBox<float>, int64_t, uint64_t>) == 40, "layout");
+
+// ---- utils.jl:163-181 -------------------------------------------------------------------------
+template <class T> IBVH_HD T minimum2(T a, T b) { return a < b ? a : b; }
+template <class T> IBVH_HD T maximum2(T a, T b) { return a > b ? a : b; }
+template <class T> IBVH_HD T dist3sq(const T* x, const T* y) {
+    T d0 = (x[0] - y[0]) * (x[0] - y[0]);
+    T d1 = (x[1] - y[1]) * (x[1] - y[1]);
+    T d2 = (x[2] - y[2]) * (x[2] - y[2]);
+    return (d0 + d1) + d2;
+}
+IBVH_HD float ibvh_sqrt(float x) { return sqrtf(x); }
+IBVH_HD double ibvh_sqrt(double x) { return sqrt(x); }
+IBVH_HD float ibvh_abs(float x) { return fabsf(x); }
+IBVH_HD double ibvh_abs(double x) { return fabs(x); }
+
+// ---- center (bsphere.jl:142, bbox.jl:100-102) ---------------------------------------------------
+template <class T> IBVH_HD void center(const BSphere<T>& b, T c[3]) { c[0] = b.x[0]; c[1] = b.x[1]; c[2] = b.x[2]; }
+template <class T> IBVH_HD void center(const BBox<T>& b, T c[3]) {
+    c[0] = T(0.5) * (b.lo[0] + b.up[0]);
+    c[1] = T(0.5) * (b.lo[1] + b.up[1]);
+    c[2] = T(0.5) * (b.lo[2] + b.up[2]);
+}
+
+// ---- merge.jl -----------------------------------------------------------------------------------
+template <class T> IBVH_HD BBox<T> to_box(const BSphere<T>& a) {          // merge.jl:47-51
+    BBox<T> o;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { o.lo[k] = a.x[k] - a.r; o.up[k] = a.x[k] + a.r; }
+    return o;
+}
+template <class T> IBVH_HD BBox<T> merge(const BBox<T>& a, const BBox<T>& b) {   // merge.jl:30-43
+    BBox<T> o;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { o.lo[k] = minimum2(a.lo[k], b.lo[k]); o.up[k] = maximum2(a.up[k], b.up[k]); }
+    return o;
+}
+template <class T> IBVH_HD BBox<T> merge_to_box(const BSphere<T>& a, const BSphere<T>& b) {  // merge.jl:58-81
+    T length = ibvh_sqrt(dist3sq(a.x, b.x));
+    if (length + a.r <= b.r) return to_box(b);
+    if (length + b.r <= a.r) return to_box(a);
+    BBox<T> o;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        o.lo[k] = minimum2(a.x[k] - a.r, b.x[k] - b.r);
+        o.up[k] = maximum2(a.x[k] + a.r, b.x[k] + b.r);
+    }
+    return o;
+}
+template <class T> IBVH_HD BSphere<T> merge(const BSphere<T>& a, const BSphere<T>& b) {     // merge.jl:2-26
+    T length = ibvh_sqrt(dist3sq(a.x, b.x));
+    if (length + a.r <= b.r) return b;
+    if (length + b.r <= a.r) return a;
+    T frac = T(0.5) * ((b.r - a.r) / length + T(1));
+    BSphere<T> o;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) o.x[k] = a.x[k] + frac * (b.x[k] - a.x[k]);
+    o.r = T(0.5) * ((length + a.r) + b.r);
+    return o;
+}
+
+// NodeType(leaf.volume) / NodeType(l.volume, r.volume) — build.jl:438-453
+template <class N> struct NodeOps;
+template <class T> struct NodeOps<BBox<T>> {
+    static IBVH_HD BBox<T> convert(const BBox<T>& v) { return v; }
+    static IBVH_HD BBox<T> convert(const BSphere<T>& v) { return to_box(v); }
+    static IBVH_HD BBox<T> merge_leaves(const BBox<T>& a, const BBox<T>& b) { return merge(a, b); }
+    static IBVH_HD BBox<T> merge_leaves(const BSphere<T>& a, const BSphere<T>& b) { return merge_to_box(a, b); }
+};
+template <class T> struct NodeOps<BSphere<T>> {
+    static IBVH_HD BSphere<T> convert(const BSphere<T>& v) { return v; }
+    static IBVH_HD BSphere<T> merge_leaves(const BSphere<T>& a, const BSphere<T>& b) { return merge(a, b); }
+};
+
+// ---- iscontact.jl:2-28 -----------------------------------------------------------------------------
+template <class T> IBVH_HD bool iscontact(const BSphere<T>& a, const BSphere<T>& b) {
+    return dist3sq(a.x, b.x) <= (a.r + b.r) * (a.r + b.r);
+}
+template <class T> IBVH_HD bool iscontact(const BBox<T>& a, const BBox<T>& b) {
+    return (a.up[0] >= b.lo[0] && a.lo[0] <= b.up[0]) &&
+           (a.up[1] >= b.lo[1] && a.lo[1] <= b.up[1]) &&
+           (a.up[2] >= b.lo[2] && a.lo[2] <= b.up[2]);
+}
+
+// ---- isintersection.jl:1-65 --------------------------------------------------------------------------
+template <class T> IBVH_HD bool isintersection(const BBox<T>& b, const T p[3], const T d[3]) {
+    T inv0 = T(1) / d[0], inv1 = T(1) / d[1], inv2 = T(1) / d[2];
+    T t1 = (b.lo[0] - p[0]) * inv0;
+    T t2 = (b.up[0] - p[0]) * inv0;
+    T tmin = minimum2(t1, t2);
+    T tmax = maximum2(t1, t2);
+    t1 = (b.lo[1] - p[1]) * inv1;
+    t2 = (b.up[1] - p[1]) * inv1;
+    tmin = maximum2(tmin, minimum2(t1, t2));
+    tmax = minimum2(tmax, maximum2(t1, t2));
+    t1 = (b.lo[2] - p[2]) * inv2;
+    t2 = (b.up[2] - p[2]) * inv2;
+    tmin = maximum2(tmin, minimum2(t1, t2));
+    tmax = minimum2(tmax, maximum2(t1, t2));
+    return (tmin <= tmax) && (tmax >= T(0));
+}
+template <class T> IBVH_HD bool isintersection(const BSphere<T>& s, const T p[3], const T d[3]) {
+    T a = (d[0] * d[0] + d[1] * d[1]) + d[2] * d[2];
+    T b = T(2) * (((p[0] - s.x[0]) * d[0] + (p[1] - s.x[1]) * d[1]) + (p[2] - s.x[2]) * d[2]);
+    T c = (((p[0] - s.x[0]) * (p[0] - s.x[0]) + (p[1] - s.x[1]) * (p[1] - s.x[1])) +
+           (p[2] - s.x[2]) * (p[2] - s.x[2])) - s.r * s.r;
+    T disc = b * b - (T(4) * a) * c;
+    if (disc >= T(0)) {
+        if (b <= T(0)) return true;
+        return T(0) >= c;
+    }
+    return false;
+}
+
+// ---- implicit tree (implicit_tree.jl) — 0-based helpers used by the kernels ---------------------------
+// Levels are 1-based (root = level 1, leaves = level `levels`). Within a level, nodes are numbered
+// 0-based: implicit index = 2^(level-1) + i. Julia precedence: a - b >> c == a - (b >> c).
+struct TreeInfo {
+    int32_t levels;
+    int64_t n;                 // real leaves
+    int64_t virtual_leaves;
+    int64_t level_start[34];   // level_start[l] = 0-based memory position of the first node of level l (l = 1..levels-1)
+    int64_t level_nreal[34];   // real nodes on level l (l = 1..levels)
+    int64_t skips[34];         // skips[l] as in compute_skips! (1-based level), implicit_tree.jl:100-113
+};
+
+IBVH_HD int ilog2_floor_u64(uint64_t x) {
+#ifdef __CUDA_ARCH__
+    return 63 - __clzll((long long)x);
+#else
+    return 63 - __builtin_clzll(x);
+#endif
+}
+IBVH_HD int64_t shr64(int64_t v, int64_t s) { return s >= 63 ? 0 : (v >> s); }
+
+inline int popc64(uint64_t v) { return __builtin_popcountll(v); }
+
+inline int make_tree(int64_t n, ibvh_tree_t* t) {        // implicit_tree.jl:77-90
+    if (n < 1) return IBVH_ERR_DOMAIN;
+    int fl = 63 - __builtin_clzll((uint64_t)n);
+    int cl = ((n & (n - 1)) == 0) ? fl : fl + 1;
+    t->levels = cl + 1;
+    t->real_leaves = n;
+    int64_t lv = (int64_t(1) << (t->levels - 1)) - n;
+    t->virtual_leaves = lv;
+    t->virtual_nodes = 2 * lv - popc64((uint64_t)lv);
+    t->real_nodes = 2 * n - 1 + popc64((uint64_t)lv);
+    return IBVH_OK;
+}
+inline int64_t skip_of_level(const ibvh_tree_t& t, int64_t level /*1-based*/) {   // implicit_tree.jl:107-108
+    int64_t v = shr64(t.virtual_leaves, t.levels - (level - 1));
+    return 2 * v - popc64((uint64_t)v);
+}
+inline TreeInfo make_tree_info(const ibvh_tree_t& t) {
+    TreeInfo ti{};
+    ti.levels = (int32_t)t.levels;
+    ti.n = t.real_leaves;
+    ti.virtual_leaves = t.virtual_leaves;
+    for (int64_t l = 1; l <= t.levels; ++l) {
+        ti.skips[l] = skip_of_level(t, l);
+        ti.level_nreal[l] = (int64_t(1) << (l - 1)) - shr64(t.virtual_leaves, t.levels - l);
+        ti.level_start[l] = (int64_t(1) << (l - 1)) - ti.skips[l] - 1;    // memory_index(2^(l-1)) - 1
+    }
+    return ti;
+}
+
+// CUDA error plumbing
+#define IBVH_CUDA_TRY(h, expr)                                                     \
+    do {                                                                           \
+        cudaError_t _e = (expr);                                                   \
+        if (_e != cudaSuccess) { (h)->set_cuda_error(_e, #expr); return IBVH_ERR_CUDA; } \
+    } while (0)
+
+}  // namespace ibvh

@@ -1,0 +1,99 @@
+// handle.cuh — the opaque per-device handle: error text, SM count, a grow-only scratch arena
+// (replaces the temporaries AcceleratedKernels allocates inside AK.sort! / AK.accumulate! /
+// AK.mapreduce) and a small pinned host block for scalar read-backs.
+#pragma once
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+
+struct ibvh_handle {
+    int device = 0;
+    int sm_count = 148;
+    char err[512] = {0};
+
+    // grow-only arena
+    char* ws = nullptr;
+    size_t ws_bytes = 0;
+    size_t ws_off = 0;
+
+    // persistent small device block: [0..47] scene bounds (6 x u64 ordered keys),
+    // [64..) counters: total contacts (u64), tile tickets, stats.
+    char* d_small = nullptr;
+    static constexpr size_t kSmallBytes = 4096;
+
+    // pinned host block for read-backs
+    char* h_pinned = nullptr;
+    static constexpr size_t kPinnedBytes = 4096;
+
+    int64_t last_stats[3] = {0, 0, 0};
+
+    // optional per-kernel timing (ibvh_profile_*): CUDA events recorded on the launching stream
+    static constexpr int kMaxProf = 512;
+    bool prof_on = false;
+    int prof_n = 0;
+    const char* prof_name[kMaxProf];
+    cudaEvent_t prof_ev[kMaxProf][2];
+    int prof_created = 0;
+
+    void set_cuda_error(cudaError_t e, const char* what) {
+        snprintf(err, sizeof(err), "CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+    }
+    void set_error(const char* msg) { snprintf(err, sizeof(err), "%s", msg); }
+
+    // Arena: reset() at the start of an entry point, alloc() bump-allocates 256-byte aligned
+    // blocks. Growing frees and reallocates (contents are scratch, never live across calls).
+    void reset() { ws_off = 0; }
+    int reserve(size_t bytes) {
+        if (bytes <= ws_bytes) return IBVH_OK;
+        if (ws) { cudaError_t e = cudaFree(ws); ws = nullptr; ws_bytes = 0; if (e != cudaSuccess) { set_cuda_error(e, "cudaFree(ws)"); return IBVH_ERR_CUDA; } }
+        size_t want = bytes + (bytes >> 3) + (1u << 20);
+        cudaError_t e = cudaMalloc((void**)&ws, want);
+        if (e != cudaSuccess) { set_cuda_error(e, "cudaMalloc(workspace)"); ws = nullptr; cudaGetLastError(); return IBVH_ERR_ALLOC; }
+        ws_bytes = want;
+        return IBVH_OK;
+    }
+    template <class T> T* alloc(size_t count) {
+        size_t bytes = (count * sizeof(T) + 255) & ~size_t(255);
+        if (ws_off + bytes > ws_bytes) return nullptr;
+        T* p = (T*)(ws + ws_off);
+        ws_off += bytes;
+        return p;
+    }
+    static size_t padded(size_t bytes) { return (bytes + 255) & ~size_t(255); }
+};
+
+namespace ibvh {
+
+// offsets inside d_small
+constexpr size_t kSmallBounds = 0;        // 6 x u64
+constexpr size_t kSmallTotal = 64;        // u64 contact total
+constexpr size_t kSmallStats = 128;       // 3 x u64
+constexpr size_t kSmallTickets = 256;     // 16 x u32 tile tickets (one per radix pass)
+constexpr size_t kSmallBoundsF = 512;     // 6 floats/doubles: padded bounds actually used
+
+// RAII scope that brackets one kernel launch with events when profiling is enabled.
+struct ProfScope {
+    ibvh_handle* h; cudaStream_t st; int slot = -1;
+    ProfScope(ibvh_handle* h_, cudaStream_t st_, const char* name) : h(h_), st(st_) {
+        if (!h->prof_on || h->prof_n >= ibvh_handle::kMaxProf) return;
+        slot = h->prof_n++;
+        if (slot >= h->prof_created) {
+            cudaEventCreate(&h->prof_ev[slot][0]);
+            cudaEventCreate(&h->prof_ev[slot][1]);
+            h->prof_created = slot + 1;
+        }
+        h->prof_name[slot] = name;
+        cudaEventRecord(h->prof_ev[slot][0], st);
+    }
+    ~ProfScope() { if (slot >= 0) cudaEventRecord(h->prof_ev[slot][1], st); }
+};
+
+struct DeviceGuard {
+    int prev = -1; bool ok = true;
+    explicit DeviceGuard(int dev) { if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; } if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false; target = dev; }
+    ~DeviceGuard() { if (prev >= 0 && prev != target) cudaSetDevice(prev); }
+    int target = 0;
+};
+
+}  // namespace ibvh

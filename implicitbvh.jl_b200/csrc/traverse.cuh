@@ -1,0 +1,357 @@
+// traverse.cuh — leaf-vs-tree (LVT) traversal kernels: single tree, BVH-vs-BVH and rays.
+// Replaces traverse_lvt_single! (src/traverse/leaf_vs_tree/traverse_single.jl:136-208),
+// traverse_lvt_pair! (traverse_pair.jl:176-244) and traverse_ray_lvt!
+// (src/raytrace/leaf_vs_tree/leaf_vs_tree.jl:170-228) and their two-pass drivers.
+//
+// Exactness rule shared by every kernel here: query q reports leaf j iff the leaf-level predicate
+// holds AND every ancestor of j from start_level down passes the node-level predicate for q (and,
+// for single-tree traversal, j lies strictly to the right of q). Any schedule that evaluates exactly
+// this predicate produces the reference's contact set bit for bit; per query the hits come out in
+// ascending j (DFS left-first order), which is also the reference's order.
+//
+// Two schedules are provided:
+//  * lvt_thread_kernel — "reference-shaped": one thread per query, private stack, one node per
+//    step. Used for rays (incoherent queries) and as the comparison proxy of the reference's GPU
+//    kernel (IBVH_TRAVERSE_REFERENCE_SHAPED).
+//  * lvt_packet_kernel — B200 schedule for leaf queries: a warp owns 32 Morton-consecutive query
+//    leaves and walks the tree ONCE for all of them with a warp-uniform (node, lane-mask) stack in
+//    shared memory. Node loads are warp-uniform broadcasts (one sector instead of 32 scattered
+//    ones), control flow never diverges, and the per-lane mask keeps the ancestor predicate exact.
+#pragma once
+#include "common.cuh"
+
+namespace ibvh {
+
+enum TraverseKind { kSingle = 0, kPair = 1, kRays = 2 };
+enum EmitMode { kCount = 0, kWrite = 1, kAtomic = 2 };
+
+template <class L, class N> struct DBvh {
+    const L* leaves;
+    const N* nodes;
+    TreeInfo ti;
+};
+
+struct TraverseArgs {
+    int64_t q_begin;        // first query (0-based) of this shard
+    int64_t q_count;        // number of queries
+    int32_t start_level;
+    int32_t flip;
+    int64_t capacity;       // contacts capacity (pairs)
+    int64_t id_base;        // rays: reported id = id_base + q + 1
+    unsigned long long* total;   // atomic mode: running total
+    unsigned long long* stats;   // optional counters (node tests, leaf tests, steps) or nullptr
+};
+
+// 8-byte vectorised struct loads (volumes are 8-byte aligned by layout; see common.cuh)
+template <class S> IBVH_D S load_struct(const S* p) {
+    static_assert(sizeof(S) % 8 == 0, "8-byte multiple");
+    alignas(8) S out;
+    const uint2* s = reinterpret_cast<const uint2*>(p);
+    uint2* d = reinterpret_cast<uint2*>(&out);
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(S) / 8); ++k) d[k] = __ldg(s + k);
+    return out;
+}
+
+IBVH_D bool tree_isvirtual(const TreeInfo& ti, uint32_t idx, int level) {     // implicit_tree.jl:191-199
+    return (int64_t)(idx - (1u << (level - 1))) + 1 > ti.level_nreal[level];
+}
+
+// ---- emission ------------------------------------------------------------------------------------------
+template <class I, int MODE> struct Emitter {
+    IndexPair<I>* contacts;
+    int64_t pos;            // kWrite: next slot; kCount: running count
+    int64_t capacity;
+    unsigned long long* total;
+    IBVH_D void emit(I a, I b) {
+        if constexpr (MODE == kCount) { pos += 1; }
+        else if constexpr (MODE == kWrite) { contacts[pos] = IndexPair<I>{a, b}; pos += 1; }
+        else {
+            // warp-aggregated atomic append among the lanes that are emitting right now
+            unsigned m = __activemask();
+            int lane = threadIdx.x & 31;
+            int leader = __ffs(m) - 1;
+            unsigned long long base = 0;
+            if (lane == leader) base = atomicAdd(total, (unsigned long long)__popc(m));
+            base = __shfl_sync(m, base, leader);
+            unsigned long long slot = base + __popc(m & ((1u << lane) - 1u));
+            if ((int64_t)slot < capacity) contacts[slot] = IndexPair<I>{a, b};
+        }
+    }
+};
+
+// ---- query state ------------------------------------------------------------------------------------------
+template <int KIND, class LQ, class N> struct QueryState;
+// leaf queries (single / pair): the leaf volume, its node-typed twin (traverse_single.jl:154-155), index
+template <class LQ, class N> struct QueryLeaf {
+    typename LQ::vol_t vol;
+    N bvn;
+    typename LQ::idx_t index;
+};
+template <class T> struct QueryRay { T p[3]; T d[3]; };
+
+// ===========================================================================================================
+// Reference-shaped schedule: one thread per query
+// ===========================================================================================================
+template <int KIND, int MODE, class LQ, class LT, class N, class I>
+__global__ void __launch_bounds__(128) lvt_thread_kernel(const LQ* __restrict__ qleaves,
+                                                        const typename LT::value_type* __restrict__ points,
+                                                        const typename LT::value_type* __restrict__ dirs,
+                                                        DBvh<LT, N> bvh, TraverseArgs a,
+                                                        I* counts, IndexPair<I>* contacts) {
+    using T = typename LT::value_type;
+    const int64_t qi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // query within the shard
+    if (qi >= a.q_count) return;
+    const int64_t q = a.q_begin + qi;
+    const TreeInfo& ti = bvh.ti;
+    const int levels = ti.levels;
+
+    QueryLeaf<LQ, N> ql;
+    QueryRay<T> qr;
+    if constexpr (KIND == kRays) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { qr.p[k] = points[3 * q + k]; qr.d[k] = dirs[3 * q + k]; }
+    } else {
+        LQ leaf = load_struct(qleaves + q);
+        ql.vol = leaf.volume;
+        ql.index = leaf.index;
+        ql.bvn = NodeOps<N>::convert(leaf.volume);
+    }
+
+    Emitter<I, MODE> em;
+    em.contacts = contacts;
+    em.capacity = a.capacity;
+    em.total = a.total;
+    em.pos = 0;
+    if constexpr (MODE == kWrite) em.pos = (qi == 0) ? 0 : (int64_t)counts[qi - 1];
+
+    const uint32_t inode_start = 1u << (a.start_level - 1);
+    const uint32_t inode_end = inode_start + (uint32_t)ti.level_nreal[a.start_level] - 1u;
+    const uint64_t q_impl = (uint64_t)q + (uint64_t(1) << (levels - 1));      // implicit index of the query leaf
+    uint32_t stack[32];
+
+    for (uint32_t root = inode_start; root <= inode_end; ++root) {
+        int sp = 0;
+        uint32_t inode = root;
+        while (true) {
+            const int level = 32 - __clz(inode);
+            bool descend = false;
+            bool skip = false;
+            if constexpr (KIND == kSingle) {
+                // traverse_single.jl:165-167 — subtree entirely at or left of the query leaf
+                uint64_t rightmost = (((uint64_t)inode + 1u) << (levels - level)) - 1u;
+                skip = rightmost <= q_impl;
+            }
+            if (!skip) {
+                if (level == levels) {
+                    LT leaf = load_struct(bvh.leaves + (inode - (1u << (levels - 1))));
+                    if constexpr (KIND == kRays) {
+                        if (isintersection(leaf.volume, qr.p, qr.d)) em.emit((I)leaf.index, (I)(a.id_base + q + 1));
+                    } else {
+                        if (iscontact(ql.vol, leaf.volume)) {
+                            if constexpr (KIND == kSingle) {
+                                if (ql.index > leaf.index) em.emit((I)leaf.index, (I)ql.index);
+                                else em.emit((I)ql.index, (I)leaf.index);
+                            } else {
+                                if (a.flip) em.emit((I)leaf.index, (I)ql.index);
+                                else em.emit((I)ql.index, (I)leaf.index);
+                            }
+                        }
+                    }
+                } else {
+                    N node = load_struct(bvh.nodes + ((int64_t)inode - ti.skips[level] - 1));
+                    bool hit;
+                    if constexpr (KIND == kRays) hit = isintersection(node, qr.p, qr.d);
+                    else hit = iscontact(ql.bvn, node);
+                    if (hit) {
+                        uint32_t right = 2u * inode + 1u;
+                        if (!tree_isvirtual(ti, right, level + 1)) stack[sp++] = right;
+                        inode = 2u * inode;
+                        descend = true;
+                    }
+                }
+            }
+            if (descend) continue;
+            if (sp == 0) break;
+            inode = stack[--sp];
+        }
+    }
+    if constexpr (MODE == kCount) counts[qi] = (I)em.pos;
+}
+
+// ===========================================================================================================
+// Packet schedule: one warp per 32 consecutive query leaves (single / pair)
+// ===========================================================================================================
+constexpr int kPacketWarps = 8;
+
+template <int KIND, int MODE, class LQ, class LT, class N, class I>
+__global__ void __launch_bounds__(kPacketWarps * 32) lvt_packet_kernel(const LQ* __restrict__ qleaves, DBvh<LT, N> bvh,
+                                                                      TraverseArgs a, I* counts, IndexPair<I>* contacts) {
+    __shared__ uint2 s_stack[kPacketWarps][34];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t warp_global = (int64_t)blockIdx.x * kPacketWarps + w;
+    const int64_t qi = warp_global * 32 + lane;
+    if (warp_global * 32 >= a.q_count) return;          // whole warp out of range (uniform)
+    const bool valid = qi < a.q_count;
+    const int64_t q = a.q_begin + qi;
+    const TreeInfo& ti = bvh.ti;
+    const int levels = ti.levels;
+
+    QueryLeaf<LQ, N> ql;
+    if (valid) {
+        LQ leaf = load_struct(qleaves + q);
+        ql.vol = leaf.volume;
+        ql.index = leaf.index;
+        ql.bvn = NodeOps<N>::convert(leaf.volume);
+    }
+    int64_t pos = 0;                                       // kCount: count, kWrite: next slot
+    if constexpr (MODE == kWrite) pos = (valid && qi > 0) ? (int64_t)counts[qi - 1] : 0;
+
+    const uint32_t inode_start = 1u << (a.start_level - 1);
+    const uint32_t inode_end = inode_start + (uint32_t)ti.level_nreal[a.start_level] - 1u;
+    const uint64_t q_impl = (uint64_t)q + (uint64_t(1) << (levels - 1));
+    const unsigned valid_mask = __ballot_sync(0xffffffffu, valid);
+    uint2* stack = s_stack[w];
+
+    for (uint32_t root = inode_start; root <= inode_end; ++root) {
+        int sp = 0;
+        uint32_t inode = root;
+        unsigned mask = valid_mask;
+        while (true) {
+            const int level = 32 - __clz(inode);
+            bool act = (mask >> lane) & 1u;
+            if constexpr (KIND == kSingle) {
+                uint64_t rightmost = (((uint64_t)inode + 1u) << (levels - level)) - 1u;
+                act = act && (rightmost > q_impl);
+            }
+            bool descend = false;
+            if (level == levels) {
+                if (__any_sync(0xffffffffu, act)) {
+                    LT leaf = load_struct(bvh.leaves + (inode - (1u << (levels - 1))));
+                    bool hit = act && iscontact(ql.vol, leaf.volume);
+                    I ea, eb;
+                    if constexpr (KIND == kSingle) {
+                        if (ql.index > leaf.index) { ea = (I)leaf.index; eb = (I)ql.index; } else { ea = (I)ql.index; eb = (I)leaf.index; }
+                    } else {
+                        if (a.flip) { ea = (I)leaf.index; eb = (I)ql.index; } else { ea = (I)ql.index; eb = (I)leaf.index; }
+                    }
+                    if constexpr (MODE == kCount) { pos += hit ? 1 : 0; }
+                    else if constexpr (MODE == kWrite) { if (hit) { contacts[pos] = IndexPair<I>{ea, eb}; pos += 1; } }
+                    else {
+                        unsigned hm = __ballot_sync(0xffffffffu, hit);
+                        if (hm) {
+                            unsigned long long base = 0;
+                            if (lane == 0) base = atomicAdd(a.total, (unsigned long long)__popc(hm));
+                            base = __shfl_sync(0xffffffffu, base, 0);
+                            unsigned long long slot = base + __popc(hm & ((1u << lane) - 1u));
+                            if (hit && (int64_t)slot < a.capacity) contacts[slot] = IndexPair<I>{ea, eb};
+                        }
+                    }
+                }
+            } else {
+                unsigned am = __ballot_sync(0xffffffffu, act);
+                if (am) {
+                    N node = load_struct(bvh.nodes + ((int64_t)inode - ti.skips[level] - 1));
+                    bool hit = act && iscontact(ql.bvn, node);
+                    unsigned hm = __ballot_sync(0xffffffffu, hit);
+                    if (hm) {
+                        uint32_t right = 2u * inode + 1u;
+                        if (!tree_isvirtual(ti, right, level + 1)) {
+                            if (lane == 0) stack[sp] = make_uint2(right, hm);
+                            sp += 1;
+                        }
+                        inode = 2u * inode;
+                        mask = hm;
+                        descend = true;
+                    }
+                }
+            }
+            if (descend) continue;
+            if (sp == 0) break;
+            __syncwarp();
+            uint2 e = stack[--sp];
+            inode = e.x;
+            mask = e.y;
+            __syncwarp();
+        }
+    }
+    if constexpr (MODE == kCount) { if (valid) counts[qi] = (I)pos; }
+}
+
+// ===========================================================================================================
+// Inclusive scan of per-query counts (AK.accumulate!(+), traverse_single.jl:57): reduce / scan / apply
+// ===========================================================================================================
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+template <class I>
+__global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const I* __restrict__ in, int64_t n, long long* __restrict__ block_sums) {
+    __shared__ long long ws[kScanThreads / 32];
+    const int64_t base = (int64_t)blockIdx.x * kScanTile;
+    long long s = 0;
+    for (int k = 0; k < kScanItems; ++k) {
+        int64_t i = base + k * kScanThreads + threadIdx.x;
+        if (i < n) s += (long long)in[i];
+    }
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long t = 0;
+        for (int j = 0; j < kScanThreads / 32; ++j) t += ws[j];
+        block_sums[blockIdx.x] = t;
+    }
+}
+// single block: exclusive scan of block_sums in place; total -> *total
+__global__ void __launch_bounds__(1024) scan_block_sums_kernel(long long* block_sums, int64_t nblocks, unsigned long long* total) {
+    __shared__ long long ws[32];
+    __shared__ long long carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < nblocks; base += 1024) {
+        int64_t i = base + threadIdx.x;
+        long long v = i < nblocks ? block_sums[i] : 0;
+        long long incl = v;
+        int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        for (int off = 1; off < 32; off <<= 1) { long long o = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += o; }
+        if (lane == 31) ws[w] = incl;
+        __syncthreads();
+        long long wb = 0;
+        for (int j = 0; j < w; ++j) wb += ws[j];
+        long long c = carry;
+        if (i < nblocks) block_sums[i] = c + wb + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = c + wb + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = (unsigned long long)carry;
+}
+template <class I>
+__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(I* __restrict__ data, int64_t n, const long long* __restrict__ block_excl) {
+    __shared__ long long ws[kScanThreads / 32];
+    const int64_t base = (int64_t)blockIdx.x * kScanTile;
+    // blocked arrangement: thread t owns items [t*kScanItems, (t+1)*kScanItems)
+    long long v[kScanItems];
+    long long s = 0;
+    for (int k = 0; k < kScanItems; ++k) {
+        int64_t i = base + (int64_t)threadIdx.x * kScanItems + k;
+        v[k] = i < n ? (long long)data[i] : 0;
+        s += v[k];
+    }
+    long long incl = s;
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int off = 1; off < 32; off <<= 1) { long long o = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += o; }
+    if (lane == 31) ws[w] = incl;
+    __syncthreads();
+    long long wb = 0;
+    for (int j = 0; j < w; ++j) wb += ws[j];
+    long long run = block_excl[blockIdx.x] + wb + incl - s;
+    for (int k = 0; k < kScanItems; ++k) {
+        int64_t i = base + (int64_t)threadIdx.x * kScanItems + k;
+        run += v[k];
+        if (i < n) data[i] = (I)run;
+    }
+}
+
+}  // namespace ibvh

@@ -1,0 +1,208 @@
+/* ibvh.h — C ABI of libibvh_b200.so: the B200-native (sm_100a) replacement for the data-parallel
+ * hot path of ImplicitBVH.jl (Morton encode + scene bounds, Morton sort, bottom-up implicit-tree
+ * merge, LVT single / pair / ray traversal).
+ *
+ * The reference has no FFI: its extension points are Julia multiple dispatch on
+ * `MortonAlgorithm` (src/morton/morton.jl:4-15), `TraversalAlgorithm`
+ * (src/traverse/traverse.jl:36,210-230; src/raytrace/raytrace.jl:71-81) and on the array type
+ * (`AbstractGPUVector`, src/traverse/leaf_vs_tree/traverse_single.jl:24,93). A Julia package
+ * extension specialising those methods on `CuVector` would `ccall` exactly the entry points below
+ * (INTEGRATION.md shows the binding). Every entry point cites the reference code it replaces.
+ *
+ * Conventions
+ *  - Plain pointers and sizes only. Every `d_*` pointer is DEVICE memory owned by the caller
+ *    (CuArray / torch tensor); the library owns only the per-handle scratch workspace.
+ *  - Layouts are the reference's isbits structs (natural alignment):
+ *      BSphere{T}  { T x[3]; T r; }                       src/bounding_volumes/bsphere.jl:26-29
+ *      BBox{T}     { T lo[3]; T up[3]; }                  src/bounding_volumes/bbox.jl:35-38
+ *      BoundingVolume{V,I,M} { V volume; I index; M morton; }  bounding_volumes.jl:55-59
+ *      IndexPair{I} { I a; I b; }                         src/traverse/traverse.jl:6
+ *      points/directions: column-major 3 x R  ==  T xyz[R][3]    src/raytrace/raytrace.jl:12-13
+ *  - Indices stored in leaves and reported in contacts are the caller's (1-based in Julia); ray ids
+ *    are 1-based (raytrace/leaf_vs_tree/leaf_vs_tree.jl:127,157,200). Levels are 1-based.
+ *    `query_begin` (sharding) is a 0-based offset.
+ *  - All device work is enqueued on the caller's `stream` (a cudaStream_t passed as void*). Calls
+ *    that must report a contact total synchronise that stream once, like the reference's scalar
+ *    read-back (leaf_vs_tree/traverse_single.jl:60).
+ *  - No exceptions cross the ABI: every call returns an ibvh_status. The Julia shim maps
+ *    IBVH_ERR_ARGUMENT -> ArgumentError, IBVH_ERR_DOMAIN -> DomainError (build.jl:207,235,260,
+ *    355-361; traverse_single.jl:9-11; implicit_tree.jl:78-80).
+ *  - There is NO CPU fallback: without a CUDA device every device entry point returns
+ *    IBVH_ERR_CUDA.
+ */
+#ifndef IBVH_H
+#define IBVH_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IBVH_VERSION 100
+
+#if defined(__GNUC__)
+#define IBVH_API __attribute__((visibility("default")))
+#else
+#define IBVH_API
+#endif
+
+typedef enum ibvh_status {
+    IBVH_OK = 0,
+    IBVH_ERR_ARGUMENT = 1,     /* Julia ArgumentError / failed @argcheck                    */
+    IBVH_ERR_DOMAIN = 2,       /* Julia DomainError (n < 1)                                 */
+    IBVH_ERR_UNSUPPORTED = 3,  /* type combination not compiled into this build             */
+    IBVH_ERR_CUDA = 4,         /* CUDA runtime error; text via ibvh_last_error              */
+    IBVH_ERR_CAPACITY = 5,     /* contacts buffer too small; *num_contacts holds the need   */
+    IBVH_ERR_ALLOC = 6         /* workspace allocation failed                               */
+} ibvh_status;
+
+typedef enum ibvh_volume_kind { IBVH_BSPHERE = 0, IBVH_BBOX = 1 } ibvh_volume_kind;
+
+/* Static types of one BVH: BVH{I}(leaves::Vector{BoundingVolume{Leaf{T},I,M}}, nodes::Vector{Node{T}})
+ * — build.jl:155-166, utils.jl:34-51 (index_exemplar, morton exemplar). */
+typedef struct ibvh_types {
+    int32_t leaf_kind;        /* ibvh_volume_kind of the leaf volumes                        */
+    int32_t float_bytes;      /* 4 (Float32) or 8 (Float64): leaf AND node float type        */
+    int32_t index_bytes;      /* 4 (Int32) or 8 (Int64)   — BVHOptions.index_exemplar        */
+    int32_t morton_bytes;     /* 2, 4, 8 (UInt16/32/64)   — DefaultMortonAlgorithm exemplar  */
+    int32_t node_kind;        /* ibvh_volume_kind of the nodes (BBox leaves need BBox nodes) */
+    int32_t reserved;
+} ibvh_types_t;
+
+/* ImplicitTree{I} — implicit_tree.jl:52-67 */
+typedef struct ibvh_tree {
+    int64_t levels, real_leaves, real_nodes, virtual_leaves, virtual_nodes;
+} ibvh_tree_t;
+
+/* A built BVH as the kernels see it — build.jl:155-166 (skips are recomputed from n). */
+typedef struct ibvh_bvh {
+    const void* d_leaves;     /* BoundingVolume[n], Morton-sorted                            */
+    const void* d_nodes;      /* Node[real_nodes - real_leaves]; levels < built_level unset  */
+    int64_t n;                /* number of leaves                                            */
+    int64_t built_level;      /* level up to which nodes are valid                           */
+    ibvh_types_t types;
+} ibvh_bvh_t;
+
+/* Traversal flags */
+#define IBVH_TRAVERSE_ORDERED 0u     /* reference order: ascending query, then DFS order       */
+#define IBVH_TRAVERSE_UNORDERED 1u   /* one pass, warp-aggregated atomic append (same set)     */
+#define IBVH_TRAVERSE_REFERENCE_SHAPED 2u /* proxy of the reference GPU kernel: one thread per  */
+                                          /* query, local stack, two passes (for comparison)   */
+#define IBVH_TRAVERSE_COUNTS_VALID 4u /* ORDERED only: d_counts already holds the inclusive scan */
+                                      /* left by a previous count-only call on the same queries: */
+                                      /* skip the count pass and write (the reference's 2nd pass) */
+
+typedef struct ibvh_traverse_params {
+    int64_t start_level;      /* level of the descended tree the traversal starts from         */
+    int64_t query_begin;      /* 0-based first query of this shard (leaf position / ray)       */
+    int64_t query_count;      /* queries in this shard; < 0 means "all from query_begin"       */
+    uint32_t flags;           /* IBVH_TRAVERSE_*                                               */
+    int32_t flip;             /* pair only: emit (leaf.index, query.index) — traverse_pair.jl:212-216 */
+    int64_t id_base;          /* rays only: ray r of the passed arrays is reported as id_base + r + 1
+                                 (0 for a whole problem; the global offset of a per-GPU ray shard)     */
+} ibvh_traverse_params_t;
+
+typedef struct ibvh_handle ibvh_handle_t;
+
+/* ---- library ---------------------------------------------------------------------------- */
+IBVH_API int ibvh_version(void);
+IBVH_API const char* ibvh_status_string(int status);
+IBVH_API const char* ibvh_last_error(const ibvh_handle_t* h);
+
+/* ---- host-only integer math (replaces implicit_tree.jl:77-199, build.jl:309-325) ---------- */
+/* ImplicitTree{I}(n) + compute_skips!: `skips` receives tree->levels entries (may be NULL).  */
+IBVH_API int ibvh_tree_shape(int64_t n, ibvh_tree_t* tree, int64_t* skips);
+IBVH_API int64_t ibvh_memory_index(const ibvh_tree_t* tree, int64_t implicit_index);
+IBVH_API int ibvh_level_indices(const ibvh_tree_t* tree, int64_t level, int64_t* start, int64_t* stop);
+IBVH_API int ibvh_isvirtual(const ibvh_tree_t* tree, int64_t implicit_index);
+/* compute_build_level: is_float ? round(levels + (1-levels)*f) : check 1 <= ilevel <= levels   */
+IBVH_API int ibvh_compute_build_level(int64_t levels, int is_float, int64_t ilevel, double flevel, int64_t* out);
+/* sizeof(BoundingVolume{...}) / sizeof(Node) / sizeof(IndexPair{I}) for a type set; <0 if unsupported */
+IBVH_API int64_t ibvh_leaf_bytes(const ibvh_types_t* types);
+IBVH_API int64_t ibvh_volume_bytes(int32_t kind, int32_t float_bytes);
+IBVH_API int64_t ibvh_num_nodes(int64_t n);   /* real_nodes - real_leaves, build.jl:256 */
+
+/* ---- handle / workspace (replaces AK's temporary allocations) ----------------------------- */
+IBVH_API int ibvh_create(ibvh_handle_t** out, int device);
+IBVH_API int ibvh_destroy(ibvh_handle_t* h);
+/* Bytes of scratch a build of n leaves will hold on to (sort ping-pong, keys, look-back).    */
+IBVH_API int64_t ibvh_workspace_query(const ibvh_types_t* types, int64_t n);
+IBVH_API int64_t ibvh_workspace_bytes(const ibvh_handle_t* h);   /* currently allocated               */
+IBVH_API int ibvh_release_workspace(ibvh_handle_t* h);
+
+/* ---- build stages (each separately callable for parity tests and ncu) --------------------- */
+/* wrap_bounding_volumes, build.jl:328-352: leaves[i] = BoundingVolume(volumes[i], I(i+1), M(0)) */
+IBVH_API int ibvh_wrap(ibvh_handle_t* h, const void* d_volumes, int64_t n, const ibvh_types_t* types,
+              void* d_leaves, void* stream);
+
+/* morton_encode!, morton/default.jl:43-82 + bounding_volumes_extrema, morton/utils.jl:1-72.
+ * compute_extrema != 0: scene bounds reduced on device and padded exactly like the reference;
+ * otherwise `mins/maxs` (3 doubles each, converted to the leaf float type) are used unpadded.
+ * out_mins/out_maxs (host, 3 doubles each, may be NULL): the bounds used; non-NULL forces a sync. */
+IBVH_API int ibvh_morton_encode(ibvh_handle_t* h, void* d_leaves, int64_t n, const ibvh_types_t* types,
+                       int compute_extrema, const double* mins, const double* maxs,
+                       double* out_mins, double* out_maxs, void* stream);
+
+/* AK.sort!(leaves, by = morton), build.jl:248-253: stable ascending, in place. */
+IBVH_API int ibvh_sort_leaves(ibvh_handle_t* h, void* d_leaves, int64_t n, const ibvh_types_t* types, void* stream);
+
+/* aggregate_oibvh!, build.jl:366-523: nodes for levels built_level .. levels-1. */
+IBVH_API int ibvh_aggregate(ibvh_handle_t* h, const void* d_leaves, int64_t n, const ibvh_types_t* types,
+                   void* d_nodes, int64_t built_level, void* stream);
+
+/* BVH(bounding_volumes, node_type; built_level, cache, options), build.jl:198-271 — the fused
+ * pipeline: bounds+encode (+digit histograms) -> onesweep radix sort of (key, perm) -> gather of the
+ * sorted leaves back into d_leaves fused with the bottom levels of the merge -> upper levels.
+ * d_volumes != NULL: wrap path (raw volumes in, wrapped sorted leaves out; build.jl:220-225);
+ * d_volumes == NULL: d_leaves already holds BoundingVolume structs and is sorted in place. */
+IBVH_API int ibvh_build(ibvh_handle_t* h, const void* d_volumes, void* d_leaves, int64_t n,
+               const ibvh_types_t* types, void* d_nodes, int64_t built_level,
+               int compute_extrema, const double* mins, const double* maxs, void* stream);
+
+/* ---- LVT traversals ------------------------------------------------------------------------ */
+/* Common output protocol (replaces the count -> accumulate -> allocate -> write sequence of
+ * leaf_vs_tree/traverse_single.jl:52-78):
+ *   d_counts   : I[query_count] or NULL. ORDERED mode fills it with the inclusive scan of
+ *                per-query contact counts (the GPU form of BVHTraversal.cache2).
+ *   d_contacts : IndexPair{I}[capacity] or NULL (NULL = count only).
+ *   num_contacts (host): total found. If it exceeds `capacity` the call returns
+ *                IBVH_ERR_CAPACITY and the caller grows cache1 and calls again
+ *                ("resize only if too small", traverse_single.jl:61-67). */
+
+/* traverse(bvh, LVTTraversal(); start_level), leaf_vs_tree/traverse_single.jl:1-208 */
+IBVH_API int ibvh_traverse_single(ibvh_handle_t* h, const ibvh_bvh_t* bvh, const ibvh_traverse_params_t* params,
+                         void* d_counts, void* d_contacts, int64_t capacity, int64_t* num_contacts,
+                         void* stream);
+
+/* traverse_lvt(bvh1, bvh2, ...), leaf_vs_tree/traverse_pair.jl:40-244: `queries` is the tree whose
+ * leaves are the query set (the reference picks the one with more leaves and sets flip, :16-36 —
+ * that choice is made by the caller), `target` is the tree descended from params->start_level. */
+IBVH_API int ibvh_traverse_pair(ibvh_handle_t* h, const ibvh_bvh_t* queries, const ibvh_bvh_t* target,
+                       const ibvh_traverse_params_t* params, void* d_counts, void* d_contacts,
+                       int64_t capacity, int64_t* num_contacts, void* stream);
+
+/* traverse_rays(bvh, points, directions, LVTTraversal()), raytrace/leaf_vs_tree/leaf_vs_tree.jl:1-228.
+ * d_points / d_directions: T[nrays][3] in the BVH float type. Emits (leaf.index, id_base + r + 1), r 0-based. */
+IBVH_API int ibvh_traverse_rays(ibvh_handle_t* h, const ibvh_bvh_t* bvh, const void* d_points, const void* d_directions,
+                       int64_t nrays, const ibvh_traverse_params_t* params, void* d_counts, void* d_contacts,
+                       int64_t capacity, int64_t* num_contacts, void* stream);
+
+/* ---- per-kernel timing (measurement aid; bench.py's roofline uses it) ----------------------
+ * When enabled, every kernel launch of this handle is bracketed by CUDA events on the launching
+ * stream. ibvh_profile_get(i) synchronises event i and returns the kernel family name and its
+ * duration in ms; entries are in launch order since the last enable / reset. */
+IBVH_API int ibvh_profile_enable(ibvh_handle_t* h, int on);
+IBVH_API int ibvh_profile_count(ibvh_handle_t* h);
+IBVH_API int ibvh_profile_get(ibvh_handle_t* h, int i, char* name, int name_cap, float* ms);
+IBVH_API int ibvh_profile_reset(ibvh_handle_t* h);
+
+/* Device counters of the last traversal on this handle (profiling builds of the kernels fill them):
+ * out[0] = node tests, out[1] = leaf tests, out[2] = traversal steps. */
+IBVH_API int ibvh_last_traversal_stats(ibvh_handle_t* h, int64_t out[3]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IBVH_H */

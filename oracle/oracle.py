@@ -20,7 +20,7 @@ _SO = os.path.join(_HERE, "_build", "libibvh_oracle.so")
 BSPHERE, BBOX = 0, 1
 
 
-def build(force: bool = False) -> str:
+def compile_lib(force: bool = False) -> str:
     """Compile the oracle with the committed Makefile (g++, -ffp-contract=off)."""
     src_m = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("ibvh_oracle.hpp", "ibvh_oracle_capi.cpp", "Makefile"))
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < src_m:
@@ -34,8 +34,7 @@ _lib = None
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
-        if not os.path.exists(_SO):
-            build()
+        compile_lib()
         _lib = C.CDLL(_SO)
         i64, vp, ci = C.c_int64, C.c_void_p, C.c_int
         _lib.orc_tree_shape.argtypes = [i64, vp, vp]

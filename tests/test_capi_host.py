@@ -1,0 +1,137 @@
+"""The C-ABI library loads, exports every symbol include/ibvh.h declares, and its host-only integer
+math agrees with the oracle and the reference's known answers. No GPU needed (no compute calls)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "ibvh.h")).read()
+    return sorted(set(re.findall(r"IBVH_API\s+[\w\s\*]+?\b(ibvh_\w+)\s*\(", txt)))
+
+
+def test_every_header_symbol_is_exported_and_bound(ib):
+    lib = ib.capi.lib()
+    syms = header_symbols()
+    assert len(syms) >= 25
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/ibvh.h but not exported"
+        assert s in ib.capi.SIGNATURES, f"{s} has no ctypes signature"
+    assert sorted(ib.capi.SIGNATURES) == syms
+
+
+def test_version_and_status_strings(ib):
+    lib = ib.capi.lib()
+    assert lib.ibvh_version() == 100
+    assert ib.capi.status_string(1) == "ArgumentError"
+    assert ib.capi.status_string(2) == "DomainError"
+
+
+def test_tree_known_answers_through_capi(ib, golden):
+    for case in golden["implicit_tree"]:
+        t = ib.ImplicitTree(case["n"])
+        for k in ("levels", "real_leaves", "virtual_leaves", "real_nodes", "virtual_nodes"):
+            assert getattr(t, k) == case[k]
+        for idx, want in case["memory_index"]:
+            assert ib.memory_index(t, idx) == want
+        for lvl, want in case["level_indices"]:
+            assert list(ib.level_indices(t, lvl)) == want
+        for idx, want in case["isvirtual"]:
+            assert ib.isvirtual(t, idx) == want
+
+
+def test_tree_matches_oracle_sweep(ib, O):
+    for n in list(range(1, 300)) + [1000, 4097, 10**5, 10**6 + 7, 10**7, 10**8, 2**31 - 5]:
+        t = ib.ImplicitTree(n)
+        o = O.tree_shape(n)
+        assert (t.levels, t.real_nodes, t.virtual_leaves, t.virtual_nodes) == (o["levels"], o["real_nodes"], o["virtual_leaves"], o["virtual_nodes"])
+        assert (t.skips() == o["skips"]).all()
+        assert ib.capi.lib().ibvh_num_nodes(n) == o["real_nodes"] - o["real_leaves"]
+        for idx in {1, 2 ** (t.levels - 1), 2 ** t.levels - 1, max(1, 2 ** (t.levels - 1) + n - 1)}:
+            assert ib.isvirtual(t, idx) == O.isvirtual(n, idx)
+            if not O.isvirtual(n, idx):
+                assert ib.memory_index(t, idx) == O.memory_index(n, idx)
+
+
+def test_tree_shape_table_from_survey(ib):
+    """tree shapes at the benchmark configs."""
+    for n, levels, nodes in ((100_000, 18, 100_006), (1_000_000, 21, 1_000_007), (5_000_000, 24, 5_000_009),
+                             (10_000_000, 25, 10_000_009), (100_000_000, 28, 100_000_007)):
+        t = ib.ImplicitTree(n)
+        assert t.levels == levels and t.real_nodes - t.real_leaves == nodes
+    assert ib.ImplicitTree(10_000_000).virtual_leaves == 6_777_216
+
+
+def test_domain_and_bounds_errors(ib):
+    with pytest.raises(ib.DomainError):
+        ib.ImplicitTree(0)
+    t = ib.ImplicitTree(5)
+    with pytest.raises(IndexError):
+        ib.memory_index(t, 16)
+    with pytest.raises(IndexError):
+        ib.level_indices(t, 5)
+
+
+def test_build_level_rule(ib, golden):
+    lib = ib.capi.lib()
+    g = golden["build_level"]
+    out = C.c_int64()
+    for c in g["cases"]:
+        if isinstance(c["built_level"], float):
+            assert lib.ibvh_compute_build_level(g["levels"], 1, 0, c["built_level"], C.byref(out)) == 0
+        else:
+            assert lib.ibvh_compute_build_level(g["levels"], 0, c["built_level"], 0.0, C.byref(out)) == 0
+        assert out.value == c["expect"]
+    assert lib.ibvh_compute_build_level(8, 0, 0, 0.0, C.byref(out)) == ib.capi.ERR_ARGUMENT
+    assert lib.ibvh_compute_build_level(8, 0, 9, 0.0, C.byref(out)) == ib.capi.ERR_ARGUMENT
+    assert lib.ibvh_compute_build_level(8, 1, 0, 1.5, C.byref(out)) == ib.capi.ERR_ARGUMENT
+
+
+def test_leaf_layouts_match_oracle(ib, O):
+    for kind in (0, 1):
+        for ib_ in (4, 8):
+            for mb in (2, 4, 8):
+                vol = ib.VolumeType(kind, 4)
+                dt = ib.leaf_dtype(vol, {4: np.int32, 8: np.int64}[ib_], {2: np.uint16, 4: np.uint32, 8: np.uint64}[mb])
+                t = ib.capi.Types(kind, 4, ib_, mb, 1, 0)
+                assert dt.itemsize == ib.capi.lib().ibvh_leaf_bytes(C.byref(t)) == O.leaf_dtype(kind, 4, ib_, mb).itemsize
+                assert dt == O.leaf_dtype(kind, 4, ib_, mb)
+    assert ib.leaf_dtype(ib.BSphere()).itemsize == 24 and ib.leaf_dtype(ib.BSphere(), np.int64, np.uint64).itemsize == 32
+    assert ib.pair_dtype(np.int32).itemsize == 8 and ib.pair_dtype(np.int64).itemsize == 16
+
+
+def test_options_validation(ib):
+    ib.BVHOptions()
+    for bad in ("num_threads", "min_mortons_per_thread", "min_sorts_per_thread", "min_boundings_per_thread",
+                "min_traversals_per_thread", "block_size"):
+        with pytest.raises(ib.ArgumentError):
+            ib.BVHOptions(**{bad: 0})
+    with pytest.raises(ib.ArgumentError):
+        ib.DefaultMortonAlgorithm(np.uint8)
+    o = ib.BVHOptions(index=np.int64, morton=ib.DefaultMortonAlgorithm(np.uint64))
+    assert o.index_dtype == np.int64 and o.morton.eltype == np.uint64
+
+
+def test_no_cpu_fallback(ib):
+    """Without a CUDA device the product path must fail loudly, never fall back to the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(ib.CudaError):
+        ib.BVH(ib.bspheres([[0, 0, 0], [1, 0, 0]], [1.0, 1.0]))
+    out = C.c_void_p()
+    assert ib.capi.lib().ibvh_create(C.byref(out), 0) == ib.capi.ERR_CUDA
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "implicitbvh.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.lower() or f == "synth.py" and "oracle" in txt.lower() and "import oracle" not in txt, f

@@ -1,0 +1,606 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the reference's known answers.
+
+Bar (BASELINE.json north_star): Morton codes, sort order, BBox node volumes and contact lists are
+BIT-EXACT; BSphere node merges within 1e-6 relative (we check exact equality first and fall back to
+the tolerance). Run on the B200 box: `pytest -m gpu`.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import pairs_list, random_spheres, sorted_pairs
+
+pytestmark = pytest.mark.gpu
+
+F32_RTOL = 1e-6      # north_star tolerance for BSphere node merges
+
+
+@pytest.fixture(scope="module")
+def dev():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda", 0)
+
+
+def I_of(ibytes):
+    return {4: np.int32, 8: np.int64}[ibytes]
+
+
+def M_of(mbytes):
+    return {2: np.uint16, 4: np.uint32, 8: np.uint64}[mbytes]
+
+
+def opts(ib, ibytes=4, mbytes=4, **kw):
+    return ib.BVHOptions(index=I_of(ibytes), morton=ib.DefaultMortonAlgorithm(M_of(mbytes), **kw))
+
+
+def gpu_build(ib, vols, node="bbox", ibytes=4, mbytes=4, built_level=1, **kw):
+    nt = ib.BBox() if node == "bbox" else ib.BSphere()
+    return ib.BVH(vols, nt, built_level=built_level, options=opts(ib, ibytes, mbytes), **kw)
+
+
+def oracle_build(O, vols, node="bbox", ibytes=4, mbytes=4, built_level=1):
+    leaves = O.wrap(vols, ibytes, mbytes)
+    nodes, mn, mx = O.build(leaves, O.BBOX if node == "bbox" else O.BSPHERE, built_level=built_level)
+    return leaves, nodes
+
+
+def assert_nodes_equal(got, want, node, lo=0):
+    got, want = got[lo:], want[lo:]
+    if node == "bbox":
+        assert got.tobytes() == want.tobytes(), "BBox nodes must be bit-exact"
+    else:
+        if got.tobytes() != want.tobytes():
+            np.testing.assert_allclose(got["x"], want["x"], rtol=F32_RTOL, atol=0)
+            np.testing.assert_allclose(got["r"], want["r"], rtol=F32_RTOL, atol=0)
+
+
+# ---------------------------------------------------------------------------------------------
+def test_extension_is_loaded_not_a_fallback(ib, dev):
+    import torch
+    assert ib.capi.lib().ibvh_version() == 100
+    h = ib.get_handle(dev)
+    assert h.value
+    maps = open("/proc/self/maps").read()
+    assert "libibvh_b200.so" in maps
+    assert torch.cuda.get_device_capability(0)[0] >= 10, "built for sm_100a only"
+
+
+def test_synth_device_matches_host(ib, dev):
+    from ibvh_b200 import synth
+    n = 100_003
+    a = synth.random_spheres_np(n, seed=42)
+    b = synth.random_spheres_torch(n, dev, seed=42).cpu().numpy()
+    assert (a["x"] == b[:, :3]).all() and (a["r"] == b[:, 3]).all()
+    p, d = synth.random_rays_np(1000, seed=7)
+    pt, _ = synth.random_rays_torch(1000, dev, seed=7)
+    assert (p == pt.cpu().numpy()).all()
+
+
+# ---- the reference's doctests / known answers through the product API --------------------------
+def test_five_spheres_doctest(ib, golden, dev):
+    g = golden["five_spheres"]
+    for ibytes, mbytes in ((4, 4), (8, 8), (4, 2), (4, 8), (8, 4)):
+        bvh = gpu_build(ib, ib.bspheres(g["centers"], g["radii"]), "bbox", ibytes, mbytes)
+        tr = ib.traverse(bvh)
+        assert pairs_list(tr.contacts.numpy()) == [tuple(p) for p in g["contacts_lvt_order"]]
+        assert tr.contacts.numpy().dtype == ib.pair_dtype(I_of(ibytes))
+        tr2 = ib.traverse(bvh, cache=tr)                     # traverse.jl:168-169
+        assert pairs_list(tr2.contacts.numpy()) == [tuple(p) for p in g["contacts_lvt_order"]]
+        assert tr2.cache1.ptr == tr.cache1.ptr and tr2.cache2.ptr == tr.cache2.ptr
+    bvh = gpu_build(ib, ib.bspheres(g["centers"], g["radii"]), "sphere")
+    assert pairs_list(ib.traverse(bvh).contacts.numpy()) == [tuple(p) for p in g["contacts_lvt_order"]]
+
+
+def test_shuffled_doctest_inplace(ib, golden, dev):
+    g = golden["five_spheres_shuffled"]
+    ldt = ib.leaf_dtype(ib.BSphere())
+    leaves = np.zeros(5, ldt)
+    leaves["volume"] = ib.bspheres(g["centers"], g["radii"])
+    leaves["index"] = g["indices"]
+    d = ib.DeviceArray.from_numpy(leaves, device=dev)
+    bvh = ib.BVH(d, ib.BBox())
+    assert bvh.leaves.ptr == d.ptr                        # modified in place, no extra allocation
+    first = d.numpy()[0]
+    want = g["first_sorted_leaf"]
+    assert int(first["index"]) == want["index"] and int(first["morton"]) == int(want["morton"], 16)
+    assert first["volume"]["x"].tolist() == want["x"] and float(first["volume"]["r"]) == want["r"]
+
+
+def test_pair_and_ray_doctests(ib, golden, dev):
+    g = golden["pair_example"]
+    b1 = gpu_build(ib, ib.bspheres(g["centers1"], g["radii1"]))
+    b2 = gpu_build(ib, ib.bspheres(g["centers2"], g["radii2"]))
+    tr = ib.traverse(b1, b2, start_level1=g["start_level1"], start_level2=g["start_level2"])
+    assert pairs_list(tr.contacts.numpy()) == [tuple(p) for p in g["contacts_lvt_order"]]
+    assert (tr.start_level1, tr.start_level2) == (2, 3)
+    tr = ib.traverse(b1, b2, cache=tr)
+    assert pairs_list(tr.contacts.numpy()) == [tuple(p) for p in g["contacts_lvt_order"]]
+    g5, gr = golden["five_spheres"], golden["ray_example"]
+    bvh = gpu_build(ib, ib.bspheres(g5["centers"], g5["radii"]))
+    tr = ib.traverse_rays(bvh, np.array(gr["points"]), np.array(gr["directions"]))
+    assert pairs_list(tr.contacts.numpy()) == [tuple(p) for p in gr["contacts_lvt_order"]]
+    tr = ib.traverse_rays(bvh, np.array(gr["points"]), np.array(gr["directions"]), cache=tr)
+    assert pairs_list(tr.contacts.numpy()) == [tuple(p) for p in gr["contacts_lvt_order"]]
+
+
+def test_unordered_structure(ib, O, golden, dev):
+    g = golden["unordered_contacts"]
+    s = ib.bspheres(g["centers"], g["radii"])
+    for node in ("bbox", "sphere"):
+        bvh = gpu_build(ib, s, node)
+        assert len(bvh.nodes) == g["num_nodes"]
+        ol, on = oracle_build(O, s, node)
+        assert bvh.leaves.numpy().tobytes() == ol.tobytes()
+        assert_nodes_equal(bvh.nodes.numpy(), on, node)
+        assert set(pairs_list(ib.traverse(bvh).contacts.numpy())) == {tuple(p) for p in g["contacts_set"]}
+    b = O.boxes_of_spheres(s)
+    bvh = gpu_build(ib, b, "bbox")
+    assert set(pairs_list(ib.traverse(bvh).contacts.numpy())) == {tuple(p) for p in g["contacts_set"]}
+
+
+# ---- Morton codes: bit-exact, n in 1:200 (test/gputests.jl:34-48) ------------------------------
+@pytest.mark.parametrize("mbytes", [2, 4, 8])
+@pytest.mark.parametrize("leaf", ["sphere", "box"])
+def test_morton_bit_exact_small_sweep(ib, O, dev, mbytes, leaf):
+    rng = np.random.default_rng(42)
+    for n in range(1, 201):
+        s = random_spheres(rng, n)
+        vols = s if leaf == "sphere" else O.boxes_of_spheres(s)
+        want = O.wrap(vols, 4, mbytes)
+        mn, mx = O.morton_encode(want)
+        d = ib.wrap_bounding_volumes(vols, opts(ib, 4, mbytes))
+        gmn, gmx = ib.morton_encode(d, opts(ib, 4, mbytes))
+        got = d.numpy()
+        assert got.tobytes() == want.tobytes(), (n, mbytes, leaf)
+        assert (gmn.astype(np.float32) == mn).all() and (gmx.astype(np.float32) == mx).all()
+
+
+def test_morton_quirks_and_user_bounds(ib, O, dev):
+    # all-negative axis (max seeded with floatmin), duplicates, single leaf, huge magnitudes, denormal extents
+    cases = [
+        ib.bspheres([[-5, -7, -9], [-1, -2, -3], [-4, -4, -4]], [1, 1, 1]),
+        ib.bspheres([[3, 3, 3]] * 7, [1] * 7),
+        ib.bspheres([[0, 0, 0]], [0.5]),
+        ib.bspheres([[1e30, -1e30, 1e-30], [2e30, 1e30, 3e-30], [-1e30, 0, 0]], [1, 1, 1]),
+        ib.bspheres([[0, 0, 0], [1e-40, 2e-40, 3e-40], [5e-39, 5e-39, 5e-39]], [1, 1, 1]),
+    ]
+    for s in cases:
+        for mbytes in (2, 4, 8):
+            want = O.wrap(s, 4, mbytes)
+            O.morton_encode(want)
+            d = ib.wrap_bounding_volumes(s, opts(ib, 4, mbytes))
+            ib.morton_encode(d, opts(ib, 4, mbytes))
+            assert d.numpy().tobytes() == want.tobytes()
+    # user bounds (compute_extrema=false): used as given, unpadded
+    rng = np.random.default_rng(1)
+    s = random_spheres(rng, 1000)
+    o = opts(ib, 4, 4, compute_extrema=False, mins=(-1.0, -1.0, -1.0), maxs=(7.0, 7.5, 8.0))
+    want = O.wrap(s)
+    O.morton_encode(want, compute_extrema=False, mins=(-1, -1, -1), maxs=(7, 7.5, 8))
+    d = ib.wrap_bounding_volumes(s, o)
+    ib.morton_encode(d, o)
+    assert d.numpy().tobytes() == want.tobytes()
+    with pytest.raises(ib.ArgumentError):
+        ib.morton_encode(d, opts(ib, 4, 8))               # morton type mismatch, morton.jl:38-42
+
+
+# ---- build: sort order + nodes -----------------------------------------------------------------
+@pytest.mark.parametrize("node", ["bbox", "sphere"])
+@pytest.mark.parametrize("ibytes,mbytes", [(4, 4), (8, 8), (4, 2)])
+def test_build_bit_exact_sizes(ib, O, dev, node, ibytes, mbytes):
+    rng = np.random.default_rng(7)
+    for n in [1, 2, 3, 4, 5, 31, 32, 33, 255, 1023, 1024, 1025, 2049, 4096, 4097, 12345, 70001]:
+        s = random_spheres(rng, n, spread=6.0 * max(1.0, (n / 200.0) ** (1 / 3)))
+        ol, on = oracle_build(O, s, node, ibytes, mbytes)
+        bvh = gpu_build(ib, s, node, ibytes, mbytes)
+        assert bvh.leaves.numpy().tobytes() == ol.tobytes(), (n, "sorted leaves")
+        assert_nodes_equal(bvh.nodes.numpy(), on, node)
+        assert bvh.tree.levels == O.tree_shape(n)["levels"]
+        assert (bvh.skips.cpu().numpy() == O.tree_shape(n)["skips"]).all()
+
+
+def test_build_box_leaves(ib, O, dev):
+    rng = np.random.default_rng(8)
+    for n in (1, 6, 1000, 5000):
+        b = O.boxes_of_spheres(random_spheres(rng, n))
+        for ibytes, mbytes in ((4, 4), (8, 8), (4, 8), (8, 2)):
+            ol, on = oracle_build(O, b, "bbox", ibytes, mbytes)
+            bvh = gpu_build(ib, b, "bbox", ibytes, mbytes)
+            assert bvh.leaves.numpy().tobytes() == ol.tobytes()
+            assert_nodes_equal(bvh.nodes.numpy(), on, "bbox")
+    with pytest.raises(ib.ArgumentError):
+        gpu_build(ib, b, "sphere")                       # no BSphere(::BBox) in the reference
+
+
+def test_build_many_ties_is_stable(ib, O, dev):
+    """UInt16 codes (15 bits) on 100k leaves: ~3 leaves per code. Stable tie rule."""
+    rng = np.random.default_rng(9)
+    s = random_spheres(rng, 100_000, spread=50.0)
+    ol, on = oracle_build(O, s, "bbox", 4, 2)
+    bvh = gpu_build(ib, s, "bbox", 4, 2)
+    got = bvh.leaves.numpy()
+    assert (np.diff(got["morton"].astype(np.int64)) >= 0).all()
+    assert got.tobytes() == ol.tobytes()
+    assert_nodes_equal(bvh.nodes.numpy(), on, "bbox")
+    # all-identical keys: order must be the input order
+    s = ib.bspheres(np.full((5000, 3), 0.5), np.full(5000, 0.01))
+    bvh = gpu_build(ib, s)
+    assert (bvh.leaves.numpy()["index"] == np.arange(1, 5001)).all()
+
+
+def test_built_level_and_cache(ib, O, dev):
+    """build.jl:309-325 + cache rules build.jl:232-238,257-263; test/runtests.jl:904-918."""
+    rng = np.random.default_rng(10)
+    s = random_spheres(rng, 100)
+    full = gpu_build(ib, s)
+    levels = full.tree.levels
+    ol, on = oracle_build(O, s)
+    for bl, want in ((3, 3), (0.0, levels), (0.5, int(np.rint(levels + (1 - levels) * 0.5))), (1.0, 1)):
+        import torch
+        pre = ib.DeviceArray(torch.full((len(full.nodes) * 24,), 0xAB, dtype=torch.uint8, device=dev), ib.BBox().dtype)
+        holder = gpu_build(ib, s)           # donor BVH whose node buffer we pre-fill to detect stray writes
+        holder.nodes.tensor.copy_(pre.tensor)
+        bvh = ib.BVH(s, ib.BBox(), built_level=bl, cache=holder)
+        assert bvh.built_level == want
+        assert bvh.nodes.ptr == holder.nodes.ptr      # node buffer reused
+        got = bvh.nodes.numpy()
+        lo = O.level_indices(100, min(want, levels - 1))[0] - 1
+        assert got[lo:].tobytes() == on[lo:].tobytes()
+        assert (got[:lo].view(np.uint8) == 0xAB).all(), "levels above built_level must stay untouched"
+        sl = max(1, want)
+        c = ib.traverse(bvh, start_level=sl)
+        assert (sorted_pairs(c.contacts.numpy()) == sorted_pairs(O.traverse_single(ol, on))).all()
+    with pytest.raises(ib.ArgumentError):
+        ib.BVH(s, ib.BSphere(), cache=full)              # node type mismatch with the cache
+    with pytest.raises(ib.ArgumentError):
+        ib.BVH(s, ib.BBox(), built_level=0)
+    with pytest.raises(ib.ArgumentError):
+        ib.BVH(s, ib.BBox(), built_level=levels + 1)
+    with pytest.raises(ib.ArgumentError):
+        ib.BVH(s, ib.BBox(), built_level=1.5)
+    with pytest.raises(ib.ArgumentError):
+        ib.traverse(ib.BVH(s, ib.BBox(), built_level=4), start_level=2)   # start_level < built_level
+    # wrapped input with mismatching index / morton types (runtests.jl:924-930)
+    w64 = ib.wrap_bounding_volumes(s, opts(ib, 8, 4))
+    with pytest.raises(ib.ArgumentError):
+        ib.BVH(w64, ib.BBox())
+    wm = ib.wrap_bounding_volumes(s, opts(ib, 4, 8))
+    with pytest.raises(ib.ArgumentError):
+        ib.BVH(wm, ib.BBox())
+
+
+def test_stage_entry_points(ib, O, dev):
+    rng = np.random.default_rng(11)
+    s = random_spheres(rng, 3000)
+    want = O.wrap(s)
+    O.morton_encode(want)
+    d = ib.wrap_bounding_volumes(s)
+    assert d.numpy().tobytes() == O.wrap(s).tobytes()
+    ib.morton_encode(d)
+    assert d.numpy().tobytes() == want.tobytes()
+    O.sort_leaves(want)
+    ib.sort_leaves(d)
+    assert d.numpy().tobytes() == want.tobytes()
+    for node, nt in (("bbox", ib.BBox()), ("sphere", ib.BSphere())):
+        for bl in (1, 5):
+            on = O.aggregate(want, O.BBOX if node == "bbox" else O.BSPHERE, built_level=bl)
+            gn = ib.aggregate(d, nt, built_level=bl).numpy()
+            lo = O.level_indices(3000, bl)[0] - 1
+            assert_nodes_equal(gn, on, node, lo)
+
+
+def test_rebuild_is_idempotent_and_cached(ib, O, dev):
+    """Config-5 shape: BVH(bvh.leaves, cache=bvh) on already sorted leaves gives the same tree."""
+    rng = np.random.default_rng(12)
+    s = random_spheres(rng, 20_000, spread=30.0)
+    bvh = gpu_build(ib, s, "bbox", 8, 8)
+    before_l, before_n = bvh.leaves.numpy().copy(), bvh.nodes.numpy().copy()
+    again = ib.BVH(bvh.leaves, ib.BBox(), cache=bvh, options=opts(ib, 8, 8))
+    assert again.leaves.ptr == bvh.leaves.ptr and again.nodes.ptr == bvh.nodes.ptr
+    assert again.leaves.numpy().tobytes() == before_l.tobytes()
+    assert again.nodes.numpy().tobytes() == before_n.tobytes()
+
+
+# ---- traversal ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("node", ["bbox", "sphere"])
+def test_single_all_start_levels(ib, O, dev, node):
+    """gputests.jl:51-127 + runtests.jl:839-900: n in 1:11:200, every start level; exact reference ORDER
+    in ordered mode, same set in unordered / reference-shaped mode, and == brute force."""
+    rng = np.random.default_rng(42)
+    for n in range(1, 200, 11):
+        s = random_spheres(rng, n)
+        ol, on = oracle_build(O, s, node)
+        bvh = gpu_build(ib, s, node)
+        brute = sorted_pairs(O.brute_single(s))
+        for sl in range(1, bvh.tree.levels + 1):
+            want = O.traverse_single(ol, on, start_level=sl)
+            got = ib.traverse(bvh, start_level=sl)
+            assert got.num_contacts == len(want)
+            assert got.contacts.numpy().tobytes() == want.tobytes(), (n, sl, "ordered")
+            assert (sorted_pairs(want) == brute).all()
+            un = ib.traverse(bvh, start_level=sl, ordered=False)
+            assert (sorted_pairs(un.contacts.numpy()) == brute).all(), (n, sl, "unordered")
+            rs = ib.traverse(bvh, start_level=sl, reference_shaped=True)
+            assert rs.contacts.numpy().tobytes() == want.tobytes(), (n, sl, "reference-shaped")
+
+
+def test_single_counts_cache2_and_growth(ib, O, dev):
+    rng = np.random.default_rng(13)
+    s = random_spheres(rng, 5000, spread=12.0)
+    ol, on = oracle_build(O, s)
+    bvh = gpu_build(ib, s)
+    want, counts = O.traverse_single(ol, on, want_counts=True)
+    tr = ib.traverse(bvh)
+    assert tr.contacts.numpy().tobytes() == want.tobytes()
+    assert (tr.cache2.numpy()[:5000] == counts).all()          # inclusive scan of per-leaf counts
+    # a cache that is too small is grown ("resize only if too small"), a big one is reused as is
+    import torch
+    small = ib.BVHTraversal(1, 0, 0, 0, ib.DeviceArray.empty(3, ib.pair_dtype(), dev), ib.DeviceArray.empty(10, np.int32, dev))
+    tr2 = ib.traverse(bvh, cache=small)
+    assert tr2.contacts.numpy().tobytes() == want.tobytes() and len(tr2.cache1) >= len(want)
+    big = ib.BVHTraversal(1, 0, 0, 0, ib.DeviceArray.empty(len(want) + 1000, ib.pair_dtype(), dev), ib.DeviceArray.empty(9000, np.int32, dev))
+    tr3 = ib.traverse(bvh, cache=big)
+    assert tr3.cache1.ptr == big.cache1.ptr and tr3.cache2.ptr == big.cache2.ptr
+    assert tr3.contacts.numpy().tobytes() == want.tobytes()
+    tr4 = ib.traverse(bvh, cache=small, ordered=False)
+    assert (sorted_pairs(tr4.contacts.numpy()) == sorted_pairs(want)).all()
+    with pytest.raises(ib.ArgumentError):
+        bad = ib.BVHTraversal(1, 0, 0, 0, ib.DeviceArray.empty(8, ib.pair_dtype(np.int64), dev), ib.DeviceArray.empty(8, np.int64, dev))
+        ib.traverse(bvh, cache=bad)
+    with pytest.raises(NotImplementedError):
+        ib.traverse(bvh, narrow=lambda a, b: True)
+
+
+@pytest.mark.parametrize("ibytes,mbytes", [(8, 8), (4, 2)])
+def test_single_other_index_types(ib, O, dev, ibytes, mbytes):
+    rng = np.random.default_rng(14)
+    for n in (2, 77, 4000):
+        s = random_spheres(rng, n, spread=10.0)
+        ol, on = oracle_build(O, s, "bbox", ibytes, mbytes)
+        bvh = gpu_build(ib, s, "bbox", ibytes, mbytes)
+        want = O.traverse_single(ol, on)
+        assert ib.traverse(bvh).contacts.numpy().tobytes() == want.tobytes()
+        assert (sorted_pairs(ib.traverse(bvh, ordered=False).contacts.numpy()) == sorted_pairs(want)).all()
+
+
+def test_single_box_leaves(ib, O, dev):
+    rng = np.random.default_rng(15)
+    for n in (1, 9, 500, 3000):
+        b = O.boxes_of_spheres(random_spheres(rng, n, spread=8.0))
+        ol, on = oracle_build(O, b)
+        bvh = gpu_build(ib, b)
+        want = O.traverse_single(ol, on)
+        assert ib.traverse(bvh).contacts.numpy().tobytes() == want.tobytes()
+        assert (sorted_pairs(want) == sorted_pairs(O.brute_single(b))).all()
+
+
+def test_single_degenerate_scenes(ib, O, dev):
+    # everything touches everything: C = n(n-1)/2
+    s = ib.bspheres(np.zeros((300, 3)), np.ones(300))
+    bvh = gpu_build(ib, s)
+    tr = ib.traverse(bvh)
+    assert tr.num_contacts == 300 * 299 // 2
+    ol, on = oracle_build(O, s)
+    assert tr.contacts.numpy().tobytes() == O.traverse_single(ol, on).tobytes()
+    # nothing touches
+    s = ib.bspheres(np.arange(600, dtype=np.float32).reshape(200, 3) * 10, np.full(200, 0.1))
+    tr = ib.traverse(gpu_build(ib, s))
+    assert tr.num_contacts == 0 and len(tr.contacts) == 0
+    # exact tangency on a lattice (closed comparisons must agree with the reference: <=, >=)
+    g = np.stack(np.meshgrid(np.arange(8), np.arange(8), np.arange(8), indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    s = ib.bspheres(g, np.full(len(g), 0.5))
+    ol, on = oracle_build(O, s)
+    want = O.traverse_single(ol, on)
+    assert len(want) == 3 * 8 * 8 * 7
+    assert ib.traverse(gpu_build(ib, s)).contacts.numpy().tobytes() == want.tobytes()
+    # single leaf / two leaves
+    assert ib.traverse(gpu_build(ib, ib.bspheres([[0, 0, 0]], [1]))).num_contacts == 0
+    assert pairs_list(ib.traverse(gpu_build(ib, ib.bspheres([[0, 0, 0], [1, 0, 0]], [1, 1]))).contacts.numpy()) == [(1, 2)]
+
+
+def test_single_query_range_shards_concatenate(ib, O, dev):
+    """Multi-GPU sharding unit: contiguous query ranges concatenate to the full list."""
+    rng = np.random.default_rng(16)
+    s = random_spheres(rng, 7001, spread=14.0)
+    bvh = gpu_build(ib, s)
+    full = ib.traverse(bvh).contacts.numpy()
+    parts = []
+    bounds = [0, 1000, 1001, 4096, 7001]
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        parts.append(ib.traverse(bvh, query_range=(a, b - a)).contacts.numpy())
+    assert np.concatenate(parts).tobytes() == full.tobytes()
+
+
+def test_pair_all_start_levels(ib, O, dev):
+    """runtests.jl:1009-1081 + gputests.jl:132-208."""
+    rng = np.random.default_rng(44)
+    sizes = [1, 22, 64, 127, 190]
+    for node in ("bbox", "sphere"):
+        for n1 in sizes:
+            for n2 in sizes:
+                s1, s2 = random_spheres(rng, n1), random_spheres(rng, n2)
+                o1, on1 = oracle_build(O, s1, node)
+                o2, on2 = oracle_build(O, s2, node)
+                b1, b2 = gpu_build(ib, s1, node), gpu_build(ib, s2, node)
+                brute = sorted_pairs(O.brute_pair(s1, s2))
+                for sl1 in {1, b1.tree.levels}:
+                    for sl2 in range(1, b2.tree.levels + 1, 2):
+                        want = O.traverse_pair(o1, on1, o2, on2, start_level1=sl1, start_level2=sl2)
+                        got = ib.traverse(b1, b2, start_level1=sl1, start_level2=sl2)
+                        assert got.contacts.numpy().tobytes() == want.tobytes(), (n1, n2, sl1, sl2)
+                        assert (sorted_pairs(want) == brute).all()
+                        un = ib.traverse(b1, b2, start_level1=sl1, start_level2=sl2, ordered=False)
+                        assert (sorted_pairs(un.contacts.numpy()) == brute).all()
+
+
+def test_pair_self_equivalence_and_partial_build(ib, O, dev):
+    rng = np.random.default_rng(17)
+    s = random_spheres(rng, 3000, spread=10.0)
+    bvh = gpu_build(ib, s)
+    single = sorted_pairs(ib.traverse(bvh).contacts.numpy())
+    both = sorted_pairs(ib.traverse(bvh, bvh).contacts.numpy())
+    sset = {tuple(p) for p in both.tolist()}
+    assert all((i, i) in sset for i in range(1, 3001))
+    upper = sorted(p for p in sset if p[0] < p[1])
+    assert upper == [tuple(p) for p in single.tolist()]
+    # config-3 shape: target built only up to a low level, every query scans all roots
+    s2 = random_spheres(rng, 2500, spread=10.0)
+    levels2 = ib.ImplicitTree(2500).levels
+    for bl in (levels2 - 3, levels2 - 7, 1):
+        t = gpu_build(ib, s2, built_level=bl)
+        o1, on1 = oracle_build(O, s)
+        o2, on2 = oracle_build(O, s2, built_level=bl)
+        want = O.traverse_pair(o1, on1, o2, on2, built_level2=bl)
+        got = ib.traverse(bvh, t)
+        assert got.contacts.numpy().tobytes() == want.tobytes()
+        assert (sorted_pairs(want) == sorted_pairs(O.brute_pair(s, s2))).all()
+
+
+def test_rays_small_and_axis_aligned(ib, O, dev):
+    rng = np.random.default_rng(45)
+    for n in (1, 2, 37, 200, 3000):
+        for leaf in ("sphere", "box"):
+            s = random_spheres(rng, n, spread=6.0 if n < 1000 else 15.0)
+            vols = s if leaf == "sphere" else O.boxes_of_spheres(s)
+            ol, on = oracle_build(O, vols)
+            bvh = gpu_build(ib, vols)
+            R = 500
+            p = (8 * rng.random((3, R)) - 1).astype(np.float32)
+            d = (rng.random((3, R)) - 0.5).astype(np.float32)
+            d[:, :5] = np.array([[1, 0, 0], [0, 1, 0], [0, 0, 1], [-1, 0, 0], [0, 0, -1]], np.float32).T
+            d[:, 5] = 0                                   # zero direction: NaNs in the slab test
+            for sl in sorted({1, bvh.tree.levels, max(1, bvh.tree.levels // 2)}):
+                want = O.traverse_rays(ol, on, p, d, start_level=sl)
+                got = ib.traverse_rays(bvh, p, d, start_level=sl)
+                assert got.contacts.numpy().tobytes() == want.tobytes(), (n, leaf, sl)
+                un = ib.traverse_rays(bvh, p, d, start_level=sl, ordered=False)
+                assert (sorted_pairs(un.contacts.numpy()) == sorted_pairs(want)).all()
+            assert (sorted_pairs(O.traverse_rays(ol, on, p, d)) == sorted_pairs(O.brute_rays(vols, p, d))).all()
+    assert ib.traverse_rays(bvh, np.zeros((3, 0), np.float32), np.zeros((3, 0), np.float32)).num_contacts == 0
+    with pytest.raises(ib.ArgumentError):
+        ib.traverse_rays(bvh, np.zeros((2, 4), np.float32), np.zeros((2, 4), np.float32))
+    with pytest.raises(ib.ArgumentError):
+        ib.traverse_rays(bvh, np.zeros((3, 4), np.float32), np.zeros((3, 5), np.float32))
+
+
+def test_ray_grid_against_analytic_sphere(ib, O, dev):
+    """runtests.jl:1086-1225 in Float32 — exact order of ray ids equals the oracle's."""
+    x, r = np.array([0.9, 1.1, 0.0], np.float32), np.float32(9.9)
+    s = ib.bspheres([x], [r])
+    bvh = gpu_build(ib, s)
+    ol, on = oracle_build(O, s)
+    rng_ = [np.arange(x[k] - r, x[k] + r + 1e-6, 1.0) for k in range(3)]
+    pts = np.array([[px, py, pz] for pz in rng_[2] for py in rng_[1] for px in rng_[0]], np.float32).T
+    for axis in range(3):
+        for sign in (1.0, -1.0):
+            d = np.zeros_like(pts)
+            d[axis, :] = sign
+            want = O.traverse_rays(ol, on, pts, d)
+            got = ib.traverse_rays(bvh, pts, d)
+            assert got.contacts.numpy().tobytes() == want.tobytes()
+            assert len(want) > 100
+
+
+# ---- medium size: oracle in seconds -------------------------------------------------------------------
+def test_config1_100k_against_oracle(ib, O, dev):
+    """BASELINE config 1 shape (100 k random spheres, BBox nodes, UInt32 / Int32), whole pipeline."""
+    from ibvh_b200 import synth
+    n = 100_000
+    s = synth.random_spheres_np(n, seed=42)
+    ol, on = oracle_build(O, s)
+    bvh = gpu_build(ib, s)
+    assert bvh.leaves.numpy().tobytes() == ol.tobytes()
+    assert bvh.nodes.numpy().tobytes() == on.tobytes()
+    want = O.traverse_single(ol, on, num_threads=8)
+    got = ib.traverse(bvh)
+    assert got.contacts.numpy().tobytes() == want.tobytes()
+    assert 3.0 * n < len(want) < 5.0 * n                    # C ~ 4 N by construction
+    un = ib.traverse(bvh, ordered=False)
+    assert (sorted_pairs(un.contacts.numpy()) == sorted_pairs(want)).all()
+
+
+def test_rays_mesh_like_against_oracle(ib, O, dev):
+    """Config-4 shape at reduced size: 200 x 200 shell, 20 k rays."""
+    from ibvh_b200 import synth
+    s = synth.shell_spheres_np(200, 200)
+    ol, on = oracle_build(O, s)
+    bvh = gpu_build(ib, s)
+    assert bvh.nodes.numpy().tobytes() == on.tobytes()
+    p, d = synth.random_rays_np(20_000, seed=7)
+    want = O.traverse_rays(ol, on, p.T, d.T, num_threads=8)
+    got = ib.traverse_rays(bvh, p.T, d.T)
+    assert got.contacts.numpy().tobytes() == want.tobytes()
+    assert len(want) > 20_000
+
+
+# ---- full BASELINE sizes: size-independent properties ------------------------------------------------
+def test_config2_10M_properties(ib, dev):
+    """10 M leaves: sortedness, permutation checksum, parent-contains-children, ordered == unordered,
+    idempotent rebuild. (The oracle is not run at this size.)"""
+    import torch
+    from ibvh_b200 import synth
+    n = 10_000_000
+    vols = synth.random_spheres_torch(n, dev, seed=42)
+    src = ib.DeviceArray(vols.view(torch.uint8).reshape(-1), ib.BSphere().dtype)
+    bvh = ib.BVH(src, ib.BBox())
+    assert bvh.tree.levels == 25 and len(bvh.nodes) == 10_000_009
+    L = bvh.leaves.tensor.view(torch.int32).reshape(n, 6)
+    mort = L[:, 5].to(torch.int64) & 0xFFFFFFFF
+    assert bool((mort[1:] >= mort[:-1]).all()), "Morton keys ascending"
+    idx = L[:, 4].to(torch.int64)
+    assert int(idx.sum()) == n * (n + 1) // 2 and int(idx.min()) == 1 and int(idx.max()) == n
+    assert int(torch.bincount(idx, minlength=n + 1)[1:].min()) == 1, "indices are a permutation of 1..n"
+    # volumes travelled with their index
+    sph = bvh.leaves.tensor.view(torch.float32).reshape(n, 6)[:, :4]
+    assert bool((sph == vols[(idx - 1)]).all())
+    # stable ties: equal keys keep ascending original index
+    same = mort[1:] == mort[:-1]
+    assert bool((idx[1:][same] > idx[:-1][same]).all())
+    # every parent box contains both children (exact min/max merge), bottom-up over all levels
+    nodes = bvh.nodes.tensor.view(torch.float32).reshape(-1, 6)
+    t = bvh.tree
+    skips = t.skips()
+    for lvl in range(1, t.levels - 1):
+        s0, e0 = ib.level_indices(t, lvl)
+        s1, e1 = ib.level_indices(t, lvl + 1)
+        par = nodes[s0 - 1:e0]
+        ch = nodes[s1 - 1:e1]
+        left = ch[0::2][: len(par)]
+        assert bool((par[:, :3] <= left[:, :3]).all() and (par[:, 3:] >= left[:, 3:]).all())
+        right = ch[1::2]
+        pr = par[: len(right)]
+        assert bool((pr[:, :3] <= right[:, :3]).all() and (pr[:, 3:] >= right[:, 3:]).all())
+        both = torch.minimum(left[: len(right), :3], right[:, :3])
+        assert bool((pr[:, :3] == both).all()), "parent lo == min(children lo) exactly"
+    # root == bounds of all sphere boxes
+    lo = (sph[:, :3] - sph[:, 3:4]).amin(0)
+    up = (sph[:, :3] + sph[:, 3:4]).amax(0)
+    assert bool((nodes[0, :3] == lo).all() and (nodes[0, 3:] == up).all())
+    # traversal: ordered and unordered agree as sets; counts scan ends at the total; pairs are (min, max)
+    tr = ib.traverse(bvh)
+    C_ = tr.num_contacts
+    assert 3.5 * n < C_ < 4.5 * n
+    assert int(tr.cache2.tensor.view(torch.int32)[n - 1]) == C_
+    pairs = tr.contacts.tensor.view(torch.int32).reshape(-1, 2).to(torch.int64)
+    assert bool((pairs[:, 0] < pairs[:, 1]).all())
+    key_o = (pairs[:, 0] * (n + 1) + pairs[:, 1]).sort().values
+    assert bool((key_o[1:] != key_o[:-1]).all()), "no duplicate pairs"
+    un = ib.traverse(bvh, ordered=False, cache=ib.BVHTraversal(1, 0, 0, 0, ib.DeviceArray.empty(C_ + 16, ib.pair_dtype(), dev), tr.cache2))
+    assert un.num_contacts == C_
+    pu = un.contacts.tensor.view(torch.int32).reshape(-1, 2).to(torch.int64)
+    key_u = (pu[:, 0] * (n + 1) + pu[:, 1]).sort().values
+    assert bool((key_o == key_u).all())
+    # spot-check 2000 reported contacts and 2000 random non-contacts with the sphere predicate
+    orig = vols
+    sel = pairs[torch.randint(0, C_, (2000,), device=dev)]
+    a, b = orig[sel[:, 0] - 1], orig[sel[:, 1] - 1]
+    d2 = ((a[:, :3] - b[:, :3]) ** 2).sum(1)
+    assert bool((d2 <= (a[:, 3] + b[:, 3]) ** 2 * (1 + 1e-5)).all())
+    # idempotent rebuild on the sorted leaves (cache=bvh)
+    before = bvh.nodes.tensor.clone()
+    again = ib.BVH(bvh.leaves, ib.BBox(), cache=bvh)
+    assert bool((again.nodes.tensor == before).all())
+    mort2 = again.leaves.tensor.view(torch.int32).reshape(n, 6)[:, 5]
+    assert bool((mort2 == L[:, 5]).all())

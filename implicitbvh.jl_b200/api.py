@@ -355,7 +355,7 @@ class BVH:
         self.tree = ImplicitTree(n)
 
         # skips: reuse from cache (build.jl:232-239)
-        if cache is not None and cache.skips.dtype != I:
+        if cache is not None and cache.index_dtype != I:
             raise ArgumentError("eltype(cache.skips) === I must hold")
         self.skips = torch.from_numpy(self.tree.skips().astype(I)).to(src.device, non_blocking=True)
 

@@ -18,18 +18,19 @@ namespace ibvh {
 // kernel) or a raw volume (wrap path: index = original position + 1, build.jl:345-349).
 template <class L, class SRC> struct GatherSrc;
 template <class L> struct GatherSrc<L, L> {
-    static IBVH_D L make(const L* src, uint32_t p, typename L::mor_t key) { L l = src[p]; l.morton = key; return l; }
+    static IBVH_D Words<L> make(const L* src, uint32_t p, typename L::mor_t key) {
+        Words<L> wv = load_words(src + p);
+        words_set_morton<L>(wv, key);
+        return wv;
+    }
 };
 template <class L> struct GatherSrc<L, typename L::vol_t> {
-    static IBVH_D L make(const typename L::vol_t* src, uint32_t p, typename L::mor_t key) {
-        L l;
-        unsigned char* b = (unsigned char*)&l;
-#pragma unroll
-        for (int k = 0; k < (int)sizeof(L); ++k) b[k] = 0;
-        l.volume = src[p];
-        l.index = (typename L::idx_t)(p + 1u);
-        l.morton = key;
-        return l;
+    static IBVH_D Words<L> make(const typename L::vol_t* src, uint32_t p, typename L::mor_t key) {
+        Words<L> wv = zero_words<L>();
+        words_set_volume<L>(wv, src[p]);
+        words_set_index<L>(wv, (typename L::idx_t)(p + 1u));
+        words_set_morton<L>(wv, key);
+        return wv;
     }
 };
 
@@ -101,7 +102,7 @@ __global__ void __launch_bounds__(THREADS) gather_merge_kernel(const SRC* __rest
     if constexpr (GATHER) {
         for (int j = threadIdx.x; j < tile_n; j += THREADS) {
             uint32_t p = perm[base + j];
-            sleaf[j] = GatherSrc<L, SRC>::make(src, p, keys_sorted[base + j]);
+            store_words(sleaf + j, GatherSrc<L, SRC>::make(src, p, keys_sorted[base + j]));
         }
         __syncthreads();
         // coalesced write-back of the tile (sizeof(L) is a multiple of 4; full tiles are 16-byte multiples)

@@ -4,6 +4,7 @@
 #include <climits>
 #include <cmath>
 #include <new>
+#include <type_traits>
 
 #include "aggregate.cuh"
 #include "common.cuh"
@@ -298,10 +299,29 @@ int read_total(ibvh_handle* h, unsigned long long* d_total, int64_t* out, cudaSt
     return IBVH_OK;
 }
 
+// stats variants are compiled only for the default type set (BSphere{Float32} / Int32 / UInt32 / BBox)
+template <class LT, class N> constexpr bool stats_combo() {
+    return std::is_same<LT, Leaf<BSphere<float>, int32_t, uint32_t>>::value && std::is_same<N, BBox<float>>::value;
+}
+
 template <int KIND, int MODE, bool PACKET, class LQ, class LT, class N, class I>
 int launch_traverse(ibvh_handle* h, const LQ* qleaves, const typename LT::value_type* points, const typename LT::value_type* dirs,
                     const DBvh<LT, N>& bvh, const TraverseArgs& a, I* counts, IndexPair<I>* contacts, cudaStream_t st) {
     if (a.q_count <= 0) return IBVH_OK;
+    if constexpr (stats_combo<LT, N>() && MODE == kCount) {
+        if (a.stats) {
+            if constexpr (PACKET) {
+                const int64_t warps = (a.q_count + 31) / 32;
+                const int64_t blocks = (warps + kPacketWarps - 1) / kPacketWarps;
+                lvt_packet_kernel<KIND, MODE, LQ, LT, N, I, true><<<(unsigned)blocks, kPacketWarps * 32, 0, st>>>(qleaves, bvh, a, counts, contacts);
+            } else {
+                const int64_t blocks = (a.q_count + 127) / 128;
+                lvt_thread_kernel<KIND, MODE, LQ, LT, N, I, true><<<(unsigned)blocks, 128, 0, st>>>(qleaves, points, dirs, bvh, a, counts, contacts);
+            }
+            IBVH_LAUNCH_CHECK(h, "lvt stats kernel");
+            return IBVH_OK;
+        }
+    }
     if constexpr (PACKET) {
         const int64_t warps = (a.q_count + 31) / 32;
         const int64_t blocks = (warps + kPacketWarps - 1) / kPacketWarps;
@@ -326,6 +346,9 @@ int traverse_impl(ibvh_handle* h, const LQ* qleaves, const typename LT::value_ty
     unsigned long long* d_total = (unsigned long long*)(h->d_small + kSmallTotal);
     a.total = d_total;
     a.stats = nullptr;
+    const bool want_stats = (flags & IBVH_TRAVERSE_STATS) != 0;
+    unsigned long long* d_stats = (unsigned long long*)(h->d_small + kSmallStats);
+    if (want_stats) { IBVH_CUDA_TRY(h, cudaMemsetAsync(d_stats, 0, 32, st)); a.stats = d_stats; }
     a.capacity = d_contacts ? capacity : 0;
     *num_contacts = 0;
     if (a.q_count <= 0) return IBVH_OK;
@@ -364,6 +387,13 @@ int traverse_impl(ibvh_handle* h, const LQ* qleaves, const typename LT::value_ty
     if (rc != IBVH_OK) return rc;
     rc = read_total(h, d_total, num_contacts, st);
     if (rc != IBVH_OK) return rc;
+    if (want_stats) {
+        unsigned long long* hp = (unsigned long long*)(h->h_pinned + 128);
+        IBVH_CUDA_TRY(h, cudaMemcpyAsync(hp, d_stats, 32, cudaMemcpyDeviceToHost, st));
+        IBVH_CUDA_TRY(h, cudaStreamSynchronize(st));
+        for (int k = 0; k < 4; ++k) h->last_stats[k] = (int64_t)hp[k];
+        a.stats = nullptr;
+    }
     if (!d_contacts || *num_contacts == 0) return IBVH_OK;
     if (*num_contacts > capacity) return IBVH_ERR_CAPACITY;
     return launch_traverse<KIND, kWrite, PACKET, LQ, LT, N, I>(h, qleaves, points, dirs, bvh, a, counts, (IndexPair<I>*)d_contacts, st);
@@ -732,9 +762,9 @@ int ibvh_profile_get(ibvh_handle_t* h, int i, char* name, int name_cap, float* m
 }
 int ibvh_profile_reset(ibvh_handle_t* h) { if (!h) return IBVH_ERR_ARGUMENT; h->prof_n = 0; return IBVH_OK; }
 
-int ibvh_last_traversal_stats(ibvh_handle_t* h, int64_t out[3]) {
+int ibvh_last_traversal_stats(ibvh_handle_t* h, int64_t out[4]) {
     if (!h || !out) return IBVH_ERR_ARGUMENT;
-    for (int k = 0; k < 3; ++k) out[k] = h->last_stats[k];
+    for (int k = 0; k < 4; ++k) out[k] = h->last_stats[k];
     return IBVH_OK;
 }
 

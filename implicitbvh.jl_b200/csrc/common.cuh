@@ -6,7 +6,9 @@
 // every expression keeps the reference's left-to-right association.
 #pragma once
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/ibvh.h"
 
@@ -29,6 +31,53 @@ static_assert(sizeof(Leaf<BSphere<float>, int32_t, uint16_t>) == 24, "layout");
 static_assert(sizeof(Leaf<BSphere<float>, int64_t, uint64_t>) == 32, "layout");
 static_assert(sizeof(Leaf<BBox<float>, int32_t, uint32_t>) == 32, "layout");
 static_assert(sizeof(Leaf<BBox<float>, int64_t, uint64_t>) == 40, "layout");
+
+// ---- raw-word view of a leaf: moving leaves as words keeps every byte (padding included) intact ----
+template <class L> struct Words {
+    static_assert(sizeof(L) % 8 == 0, "leaf structs are 8-byte multiples");
+    static constexpr int N8 = sizeof(L) / 8;
+    uint2 w[N8];
+};
+template <class L> IBVH_D Words<L> load_words(const L* p) {
+    Words<L> o;
+    const uint2* s = reinterpret_cast<const uint2*>(p);
+#pragma unroll
+    for (int k = 0; k < Words<L>::N8; ++k) o.w[k] = s[k];
+    return o;
+}
+template <class L> IBVH_D void store_words(L* p, const Words<L>& v) {
+    uint2* d = reinterpret_cast<uint2*>(p);
+#pragma unroll
+    for (int k = 0; k < Words<L>::N8; ++k) d[k] = v.w[k];
+}
+template <class L> IBVH_D Words<L> zero_words() {
+    Words<L> o;
+#pragma unroll
+    for (int k = 0; k < Words<L>::N8; ++k) o.w[k] = make_uint2(0u, 0u);
+    return o;
+}
+template <class L> IBVH_D typename L::vol_t words_volume(const Words<L>& v) {
+    typename L::vol_t o;
+    memcpy(&o, v.w, sizeof(o));
+    return o;
+}
+template <class L> IBVH_D typename L::idx_t words_index(const Words<L>& v) {
+    typename L::idx_t o;
+    memcpy(&o, reinterpret_cast<const char*>(v.w) + offsetof(L, index), sizeof(o));
+    return o;
+}
+template <class L> IBVH_D typename L::mor_t words_morton(const Words<L>& v) {
+    typename L::mor_t o;
+    memcpy(&o, reinterpret_cast<const char*>(v.w) + offsetof(L, morton), sizeof(o));
+    return o;
+}
+template <class L> IBVH_D void words_set_volume(Words<L>& v, const typename L::vol_t& x) { memcpy(v.w, &x, sizeof(x)); }
+template <class L> IBVH_D void words_set_index(Words<L>& v, typename L::idx_t x) {
+    memcpy(reinterpret_cast<char*>(v.w) + offsetof(L, index), &x, sizeof(x));
+}
+template <class L> IBVH_D void words_set_morton(Words<L>& v, typename L::mor_t x) {
+    memcpy(reinterpret_cast<char*>(v.w) + offsetof(L, morton), &x, sizeof(x));
+}
 
 // ---- utils.jl:163-181 -------------------------------------------------------------------------
 template <class T> IBVH_HD T minimum2(T a, T b) { return a < b ? a : b; }

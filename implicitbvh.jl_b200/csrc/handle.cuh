@@ -26,7 +26,7 @@ struct ibvh_handle {
     char* h_pinned = nullptr;
     static constexpr size_t kPinnedBytes = 4096;
 
-    int64_t last_stats[3] = {0, 0, 0};
+    int64_t last_stats[4] = {0, 0, 0, 0};
 
     // optional per-kernel timing (ibvh_profile_*): CUDA events recorded on the launching stream
     static constexpr int kMaxProf = 512;

@@ -209,12 +209,18 @@ __global__ void __launch_bounds__(256) encode_kernel(const SRC* __restrict__ src
     __syncthreads();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        SRC s = src[i];
         T c[3];
-        center(volume_of(s), c);
+        if constexpr (COPY) {
+            // move the leaf as raw words so every byte (padding included) survives the copy
+            Words<L> wv = load_words(reinterpret_cast<const L*>(src) + i);
+            store_words(copy_out + i, wv);
+            center(words_volume<L>(wv), c);
+        } else {
+            SRC s = src[i];
+            center(volume_of(s), c);
+        }
         M m = morton_encode_single<M>(c, mins, maxs);
         keys[i] = m;
-        if constexpr (COPY) copy_out[i] = s;
 #pragma unroll
         for (int p = 0; p < P; ++p) atomicAdd(&sh[p][(uint32_t)(m >> (p * kRadixBits)) & (kRadixBins - 1)], 1u);
     }
@@ -229,7 +235,7 @@ __global__ void __launch_bounds__(256) encode_kernel(const SRC* __restrict__ src
 template <class L>
 __global__ void __launch_bounds__(256) scatter_morton_kernel(L* leaves, int64_t n, const typename L::mor_t* __restrict__ keys) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) leaves[i].morton = keys[i];
+    if (i < n) leaves[i].morton = keys[i];     // touches only the morton field
 }
 
 // wrap_bounding_volumes, build.jl:340-350
@@ -237,14 +243,10 @@ template <class L>
 __global__ void __launch_bounds__(256) wrap_kernel(const typename L::vol_t* __restrict__ vols, int64_t n, L* __restrict__ leaves) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
-        L l;
-        // zero padding bytes deterministically
-        unsigned char* b = (unsigned char*)&l;
-        for (int k = 0; k < (int)sizeof(L); ++k) b[k] = 0;
-        l.volume = vols[i];
-        l.index = (typename L::idx_t)(i + 1);
-        l.morton = 0;
-        leaves[i] = l;
+        Words<L> wv = zero_words<L>();            // padding bytes are zero, deterministically
+        words_set_volume<L>(wv, vols[i]);
+        words_set_index<L>(wv, (typename L::idx_t)(i + 1));
+        store_words(leaves + i, wv);
     }
 }
 

@@ -172,10 +172,10 @@ __global__ void __launch_bounds__(256) extract_keys_kernel(const L* __restrict__
     __syncthreads();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        L s = leaves[i];
-        M m = s.morton;
+        Words<L> wv = load_words(leaves + i);
+        M m = words_morton<L>(wv);
         keys[i] = m;
-        copy_out[i] = s;
+        store_words(copy_out + i, wv);
 #pragma unroll
         for (int p = 0; p < P; ++p) atomicAdd(&sh[p][(uint32_t)(m >> (p * kRadixBits)) & (kRadixBins - 1)], 1u);
     }

@@ -93,7 +93,7 @@ template <class T> struct QueryRay { T p[3]; T d[3]; };
 // ===========================================================================================================
 // Reference-shaped schedule: one thread per query
 // ===========================================================================================================
-template <int KIND, int MODE, class LQ, class LT, class N, class I>
+template <int KIND, int MODE, class LQ, class LT, class N, class I, bool STATS = false>
 __global__ void __launch_bounds__(128) lvt_thread_kernel(const LQ* __restrict__ qleaves,
                                                         const typename LT::value_type* __restrict__ points,
                                                         const typename LT::value_type* __restrict__ dirs,
@@ -129,6 +129,7 @@ __global__ void __launch_bounds__(128) lvt_thread_kernel(const LQ* __restrict__ 
     const uint32_t inode_end = inode_start + (uint32_t)ti.level_nreal[a.start_level] - 1u;
     const uint64_t q_impl = (uint64_t)q + (uint64_t(1) << (levels - 1));      // implicit index of the query leaf
     uint32_t stack[32];
+    unsigned long long st_node = 0, st_leaf = 0, st_steps = 0;
 
     for (uint32_t root = inode_start; root <= inode_end; ++root) {
         int sp = 0;
@@ -137,6 +138,7 @@ __global__ void __launch_bounds__(128) lvt_thread_kernel(const LQ* __restrict__ 
             const int level = 32 - __clz(inode);
             bool descend = false;
             bool skip = false;
+            if constexpr (STATS) st_steps += 1;
             if constexpr (KIND == kSingle) {
                 // traverse_single.jl:165-167 — subtree entirely at or left of the query leaf
                 uint64_t rightmost = (((uint64_t)inode + 1u) << (levels - level)) - 1u;
@@ -144,6 +146,7 @@ __global__ void __launch_bounds__(128) lvt_thread_kernel(const LQ* __restrict__ 
             }
             if (!skip) {
                 if (level == levels) {
+                    if constexpr (STATS) st_leaf += 1;
                     LT leaf = load_struct(bvh.leaves + (inode - (1u << (levels - 1))));
                     if constexpr (KIND == kRays) {
                         if (isintersection(leaf.volume, qr.p, qr.d)) em.emit((I)leaf.index, (I)(a.id_base + q + 1));
@@ -159,6 +162,7 @@ __global__ void __launch_bounds__(128) lvt_thread_kernel(const LQ* __restrict__ 
                         }
                     }
                 } else {
+                    if constexpr (STATS) st_node += 1;
                     N node = load_struct(bvh.nodes + ((int64_t)inode - ti.skips[level] - 1));
                     bool hit;
                     if constexpr (KIND == kRays) hit = isintersection(node, qr.p, qr.d);
@@ -177,6 +181,17 @@ __global__ void __launch_bounds__(128) lvt_thread_kernel(const LQ* __restrict__ 
         }
     }
     if constexpr (MODE == kCount) counts[qi] = (I)em.pos;
+    if constexpr (STATS) {
+        if (a.stats) {
+            atomicAdd(a.stats + 0, st_node);
+            atomicAdd(a.stats + 1, st_leaf);
+            atomicAdd(a.stats + 2, st_steps);
+            unsigned m = __activemask();
+            unsigned long long mx = st_steps;
+            for (int off = 16; off > 0; off >>= 1) { unsigned long long o = __shfl_xor_sync(m, mx, off); mx = o > mx ? o : mx; }
+            if ((threadIdx.x & 31) == (__ffs(m) - 1)) atomicAdd(a.stats + 3, mx);     // sum over warps of the slowest lane's steps
+        }
+    }
 }
 
 // ===========================================================================================================
@@ -184,7 +199,7 @@ __global__ void __launch_bounds__(128) lvt_thread_kernel(const LQ* __restrict__ 
 // ===========================================================================================================
 constexpr int kPacketWarps = 8;
 
-template <int KIND, int MODE, class LQ, class LT, class N, class I>
+template <int KIND, int MODE, class LQ, class LT, class N, class I, bool STATS = false>
 __global__ void __launch_bounds__(kPacketWarps * 32) lvt_packet_kernel(const LQ* __restrict__ qleaves, DBvh<LT, N> bvh,
                                                                       TraverseArgs a, I* counts, IndexPair<I>* contacts) {
     __shared__ uint2 s_stack[kPacketWarps][34];
@@ -212,6 +227,7 @@ __global__ void __launch_bounds__(kPacketWarps * 32) lvt_packet_kernel(const LQ*
     const uint64_t q_impl = (uint64_t)q + (uint64_t(1) << (levels - 1));
     const unsigned valid_mask = __ballot_sync(0xffffffffu, valid);
     uint2* stack = s_stack[w];
+    unsigned long long st_node = 0, st_leaf = 0, st_steps = 0, st_loads = 0;
 
     for (uint32_t root = inode_start; root <= inode_end; ++root) {
         int sp = 0;
@@ -220,6 +236,7 @@ __global__ void __launch_bounds__(kPacketWarps * 32) lvt_packet_kernel(const LQ*
         while (true) {
             const int level = 32 - __clz(inode);
             bool act = (mask >> lane) & 1u;
+            if constexpr (STATS) st_steps += 1;
             if constexpr (KIND == kSingle) {
                 uint64_t rightmost = (((uint64_t)inode + 1u) << (levels - level)) - 1u;
                 act = act && (rightmost > q_impl);
@@ -227,6 +244,7 @@ __global__ void __launch_bounds__(kPacketWarps * 32) lvt_packet_kernel(const LQ*
             bool descend = false;
             if (level == levels) {
                 if (__any_sync(0xffffffffu, act)) {
+                    if constexpr (STATS) { st_leaf += act ? 1 : 0; st_loads += 1; }
                     LT leaf = load_struct(bvh.leaves + (inode - (1u << (levels - 1))));
                     bool hit = act && iscontact(ql.vol, leaf.volume);
                     I ea, eb;
@@ -251,6 +269,7 @@ __global__ void __launch_bounds__(kPacketWarps * 32) lvt_packet_kernel(const LQ*
             } else {
                 unsigned am = __ballot_sync(0xffffffffu, act);
                 if (am) {
+                    if constexpr (STATS) { st_node += act ? 1 : 0; st_loads += 1; }
                     N node = load_struct(bvh.nodes + ((int64_t)inode - ti.skips[level] - 1));
                     bool hit = act && iscontact(ql.bvn, node);
                     unsigned hm = __ballot_sync(0xffffffffu, hit);
@@ -276,6 +295,13 @@ __global__ void __launch_bounds__(kPacketWarps * 32) lvt_packet_kernel(const LQ*
         }
     }
     if constexpr (MODE == kCount) { if (valid) counts[qi] = (I)pos; }
+    if constexpr (STATS) {
+        if (a.stats) {
+            atomicAdd(a.stats + 0, st_node);
+            atomicAdd(a.stats + 1, st_leaf);
+            if (lane == 0) { atomicAdd(a.stats + 2, st_steps); atomicAdd(a.stats + 3, st_loads); }
+        }
+    }
 }
 
 // ===========================================================================================================

@@ -90,6 +90,7 @@ typedef struct ibvh_bvh {
 #define IBVH_TRAVERSE_UNORDERED 1u   /* one pass, warp-aggregated atomic append (same set)     */
 #define IBVH_TRAVERSE_REFERENCE_SHAPED 2u /* proxy of the reference GPU kernel: one thread per  */
                                           /* query, local stack, two passes (for comparison)   */
+#define IBVH_TRAVERSE_STATS 8u        /* fill the device counters read by ibvh_last_traversal_stats */
 #define IBVH_TRAVERSE_COUNTS_VALID 4u /* ORDERED only: d_counts already holds the inclusive scan */
                                       /* left by a previous count-only call on the same queries: */
                                       /* skip the count pass and write (the reference's 2nd pass) */
@@ -198,9 +199,12 @@ IBVH_API int ibvh_profile_count(ibvh_handle_t* h);
 IBVH_API int ibvh_profile_get(ibvh_handle_t* h, int i, char* name, int name_cap, float* ms);
 IBVH_API int ibvh_profile_reset(ibvh_handle_t* h);
 
-/* Device counters of the last traversal on this handle (profiling builds of the kernels fill them):
- * out[0] = node tests, out[1] = leaf tests, out[2] = traversal steps. */
-IBVH_API int ibvh_last_traversal_stats(ibvh_handle_t* h, int64_t out[3]);
+/* Device counters of the last ORDERED traversal run with IBVH_TRAVERSE_STATS on this handle (count
+ * pass of the default BSphere{Float32}/Int32/UInt32/BBox type set only):
+ * out[0] = node tests (per query), out[1] = leaf tests (per query),
+ * packet schedule: out[2] = warp steps, out[3] = warp-uniform node/leaf loads;
+ * reference-shaped schedule: out[2] = per-query steps, out[3] = sum over warps of the slowest lane's steps. */
+IBVH_API int ibvh_last_traversal_stats(ibvh_handle_t* h, int64_t out[4]);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""bench.py — the driver-facing benchmark (one JSON line on stdout from rank 0).
+
+Workload (BASELINE.json configs[1]): 10 M random BSphere{Float32} leaves -> BBox{Float32} nodes,
+UInt32 Morton, Int32 index: `BVH(leaves, BBox{Float32}; cache)` + `traverse(bvh; cache)` (LVT contact
+detection). A "step" is one build + one contact traversal on the same 10 M synthetic spheres
+(SURVEY.md §8d law, seed 42); metric = leaves/s = N / step time.
+
+  value  : inputs resident in HBM, CUDA-event time on the launching stream, max over ranks.
+  e2e    : same call sequence through the public API with HOST (pinned) input volumes and the contact
+           list read back to pinned host memory inside the timed region.
+  roofline: dominant kernel (the LVT traversal kernel), algorithmic bytes / CUDA-event duration measured
+           live with the library's per-kernel event profiler.
+  cpu_baseline / --impl reference: the reference ALGORITHM restated in C++ (oracle/, two-pass LVT,
+           struct-moving stable sort, static thread partition) on the box's host cores. The real
+           reference is a Julia package and cannot run in this image (no julia binary).
+
+N > 1 (torchrun, one rank per GPU): the build does not shard — rank 0 builds and the tree is broadcast
+(NCCL); the contact traversal shards by contiguous query-leaf ranges; shards are all-gathered so every
+rank ends with the full contact list. Total work is fixed => "scaling": "strong".
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_LEAVES = int(os.environ.get("IBVH_BENCH_N", 10_000_000))
+SEED = 42
+METRIC = "build+contact leaves/s @10M spheres"
+UNIT = "leaves/s"
+WORKLOAD = ("configs[1]: %d BSphere{Float32} leaves (centres U[0,1)^3, r = s(0.5+0.5u), s = 0.8124 N^(-1/3), seed 42), "
+            "BBox{Float32} nodes, UInt32 Morton, Int32 index: BVH build (built_level=1) + LVT contact traversal (start_level=1)")
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm restated (oracle/) on the host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_step(O, np, leaves_template, nodes, contacts, counts, threads):
+    """One build + two-pass LVT traversal on the CPU. Returns (seconds, num_contacts)."""
+    import ctypes
+    lv = leaves_template.copy()
+    t0 = time.perf_counter()
+    kind, fb, ibt, mb = O._desc(lv)
+    f = np.float32
+    mn, mx = np.zeros(3, f), np.zeros(3, f)
+    rc = O.lib().orc_build(O._p(lv), len(lv), kind, fb, ibt, mb, O._p(nodes), O.BBOX, 4, 1, 1, O._p(mn), O._p(mx), threads, 100, 100, 100)
+    assert rc == 0
+    total = O.lib().orc_traverse_single(O._p(lv), len(lv), kind, fb, ibt, mb, O._p(nodes), O.BBOX, 4, 1, 1, O._p(contacts), len(contacts),
+                                        O._p(counts), threads, 100)
+    dt = time.perf_counter() - t0
+    assert 0 <= total <= len(contacts), total
+    return dt, int(total)
+
+
+def cpu_setup(n):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import oracle as O
+    from ibvh_b200 import synth
+    s = synth.random_spheres_np(n, seed=SEED)
+    leaves = O.wrap(s)
+    nodes = np.zeros(O.num_nodes(n), O.volume_dtype(O.BBOX, 4))
+    contacts = np.zeros(int(6.0 * n) + 1024, O.pair_dtype(4))
+    counts = np.zeros(n, np.int32)
+    return O, np, leaves, nodes, contacts, counts
+
+
+def cpu_calibrated_size(threads, budget_s):
+    """Pick the sample size: run 200 k leaves, extrapolate (build+traverse is ~linear), cap at the full N."""
+    O, np, leaves, nodes, contacts, counts = cpu_setup(200_000)
+    cpu_step(O, np, leaves, nodes, contacts, counts, threads)
+    dt, _ = cpu_step(O, np, leaves, nodes, contacts, counts, threads)
+    rate = 200_000 / dt
+    n = int(min(N_LEAVES, max(200_000, rate * budget_s * 0.8)))
+    return n
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    n = cpu_calibrated_size(threads, min(budget, 20.0))
+    O, np, leaves, nodes, contacts, counts = cpu_setup(n)
+    for _ in range(args.warmup):
+        cpu_step(O, np, leaves, nodes, contacts, counts, threads)
+    t = 0.0
+    total = 0
+    for _ in range(args.steps):
+        dt, total = cpu_step(O, np, leaves, nodes, contacts, counts, threads)
+        t += dt
+    ms = t / args.steps * 1e3
+    value = n / (ms * 1e-3)
+    sample = (f"{n}-leaf instance of the same law (full workload is {N_LEAVES}); C++17 restatement of the reference algorithm "
+              f"(oracle/), {threads} threads, build + two-pass LVT; the Julia reference itself cannot run here")
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD % N_LEAVES, "sample_leaves": n, "contacts_per_step": total},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def profile_rows(ib, handle):
+    lib = ib.capi.lib()
+    name = C.create_string_buffer(64)
+    ms = C.c_float()
+    rows = []
+    for i in range(lib.ibvh_profile_count(handle)):
+        lib.ibvh_profile_get(handle, i, name, 64, C.byref(ms))
+        rows.append((name.value.decode(), float(ms.value)))
+    return rows
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--unordered", action="store_true", help="one-pass unordered contact emission instead of the reference order")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import ibvh_b200 as ib
+    from ibvh_b200 import dist as ibdist
+    from ibvh_b200 import synth
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    warm = max(3, args.warmup)
+    n = N_LEAVES
+    ordered = not args.unordered
+
+    # ---- inputs resident in HBM (generated on device, identical on every rank) -----------------
+    vols = synth.random_spheres_torch(n, dev, seed=SEED)
+    src = ib.DeviceArray(vols.view(torch.uint8).reshape(-1), ib.BSphere().dtype)
+    bounds = ibdist.shard_bounds(n, world)
+    qb, qe = bounds[rank]
+
+    state = {"bvh": None, "tr": None, "full": None}
+
+    def step_device():
+        """One step with inputs in HBM. Returns the number of contacts this rank holds at the end."""
+        if world == 1:
+            bvh = ib.BVH(src, ib.BBox(), cache=state["bvh"])
+            tr = ib.traverse(bvh, cache=state["tr"], ordered=ordered)
+            state["bvh"], state["tr"] = bvh, tr
+            return tr.num_contacts
+        # build on rank 0, broadcast the tree (leaves + nodes), shard the traversal, gather the shards
+        if rank == 0 or state["bvh"] is None:
+            bvh = ib.BVH(src, ib.BBox(), cache=state["bvh"])        # every rank builds once to own the buffers
+            state["bvh"] = bvh
+        bvh = state["bvh"]
+        dist.broadcast(bvh.leaves.tensor, src=0)
+        dist.broadcast(bvh.nodes.tensor, src=0)
+        tr = ib.traverse(bvh, cache=state["tr"], ordered=ordered, query_range=(qb, qe - qb))
+        state["tr"] = tr
+        full, counts = ibdist.gather_shards(tr.cache1.tensor, tr.num_contacts, tr.cache1.dtype.itemsize)
+        state["full"] = full
+        return int(sum(counts))
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # first call sizes the caches; give cache1 head-room so later steps never regrow
+    ncontacts = step_device()
+    if world == 1:
+        tr = state["tr"]
+        state["tr"] = ib.BVHTraversal(1, 0, 0, 0, ib.DeviceArray.empty(int(tr.num_contacts * 1.05) + 1024, ib.pair_dtype(), dev), tr.cache2)
+    for _ in range(warm):
+        ncontacts = step_device()
+
+    sampler = ClockSampler(local)
+    sync_all()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for _ in range(args.steps):
+        ncontacts = step_device()
+    e1.record()
+    sync_all()
+    ms_total = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / args.steps
+    value = n / (ms_step * 1e-3)
+
+    # ---- per-kernel durations (CUDA events on the launching stream, inside the library) ---------
+    handle = state["bvh"]._handle
+    lib = ib.capi.lib()
+    lib.ibvh_profile_enable(handle, 1)
+    prof_steps = 5
+    for _ in range(prof_steps):
+        step_device()
+    torch.cuda.synchronize()
+    rows = profile_rows(ib, handle)
+    lib.ibvh_profile_enable(handle, 0)
+    per_kernel, launches = {}, {}
+    for k, v in rows:
+        per_kernel[k] = per_kernel.get(k, 0.0) + v / prof_steps
+        launches[k] = launches.get(k, 0) + 1
+    launches = {k: v // prof_steps for k, v in launches.items()}
+    gpu_launches = int(sum(launches.values()))
+    dom = max(per_kernel, key=per_kernel.get)
+    nq = qe - qb
+    my_contacts = state["tr"].num_contacts
+    # algorithmic bytes of the traversal: tree read once per launch + contact output.
+    # ordered = two launches (count, write): 2 * (Lb + Nb) * N + 2 * Ib * C; unordered = one launch.
+    Lb, Nb, Ib = 24, 24, 4
+    n_trav = launches.get(dom, 1)
+    alg_bytes = n_trav * (Lb + Nb) * n * (nq / n if world > 1 else 1.0) + 2 * Ib * my_contacts
+    dom_ms = per_kernel[dom]
+    peak, peak_src = peaks()
+    achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            with open(tp) as f:
+                traffic = json.load(f).get(dom)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": dom, "launches_per_step": n_trav, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_step": alg_bytes,
+                "kernel_ms_per_step": dom_ms, "share_of_step": dom_ms / ms_step,
+                "per_kernel_ms": {k: round(v, 4) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1])},
+                "intersection_tests_per_s": None}
+
+    # ---- e2e: host (pinned) volumes in, contacts back to pinned host memory ------------------------
+    host_vols = synth.random_spheres_np(n, seed=SEED) if rank == 0 or world > 1 else None
+    pinned_in = ib.DeviceArray.from_numpy(host_vols, pin=True)
+    cap = int(ncontacts * 1.05) + 1024
+    pinned_out = torch.empty(cap * 8, dtype=torch.uint8).pin_memory()
+    e2e_state = {"bvh": state["bvh"], "tr": state["tr"]}
+
+    def step_e2e():
+        d_in = pinned_in.to(dev)                                     # H2D of the step's input
+        if world == 1:
+            bvh = ib.BVH(d_in, ib.BBox(), cache=e2e_state["bvh"])
+            tr = ib.traverse(bvh, cache=e2e_state["tr"], ordered=ordered)
+            e2e_state["bvh"], e2e_state["tr"] = bvh, tr
+            nb = tr.num_contacts * 8
+            pinned_out[:nb].copy_(tr.cache1.tensor[:nb], non_blocking=True)   # D2H of the step's result
+            torch.cuda.current_stream().synchronize()
+            return tr.num_contacts
+        if rank == 0:
+            bvh = ib.BVH(d_in, ib.BBox(), cache=e2e_state["bvh"])
+            e2e_state["bvh"] = bvh
+        bvh = e2e_state["bvh"]
+        dist.broadcast(bvh.leaves.tensor, src=0)
+        dist.broadcast(bvh.nodes.tensor, src=0)
+        tr = ib.traverse(bvh, cache=e2e_state["tr"], ordered=ordered, query_range=(qb, qe - qb))
+        e2e_state["tr"] = tr
+        full, counts = ibdist.gather_shards(tr.cache1.tensor, tr.num_contacts, 8)
+        nb = int(sum(counts)) * 8
+        pinned_out[:nb].copy_(full[:nb], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return int(sum(counts))
+
+    for _ in range(3):
+        step_e2e()
+    sync_all()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        nc = step_e2e()
+    e1.record()
+    sync_all()
+    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / args.steps
+    if world > 1:
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e = {"value": n / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(n * 16), "d2h_bytes_per_step": int(nc * 8),
+           "ms_per_step": e2e_ms}
+
+    # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload ----------------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        ns = cpu_calibrated_size(threads, 12.0)
+        O, np_, leaves, nodes, contacts, counts = cpu_setup(ns)
+        dt, tot = cpu_step(O, np_, leaves, nodes, contacts, counts, threads)
+        cpu_baseline = {"value": ns / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": f"one build + two-pass LVT traversal of a {ns}-leaf instance of the same law ({tot} contacts) in {dt:.2f} s; "
+                                  f"C++17 restatement of the reference algorithm (oracle/), {threads} threads"}
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD % n, "leaves": n, "contacts_per_step": int(ncontacts),
+                       "contact_order": "reference (ascending query, DFS order; count+scan+write)" if ordered else "unordered (one pass, warp-aggregated atomics)",
+                       "parallelism": "single GPU" if world == 1 else f"build on rank 0 + NCCL broadcast, query-range sharded traversal over {world} GPUs, all-gather of contact shards",
+                       "l2_policy": "inputs larger than L2 (160 MB volumes + 240 MB leaves + 240 MB nodes per step vs 126 MB L2)"},
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -449,13 +449,13 @@ def _check_narrow(narrow):
 
 
 def _run_two_phase(call, handle, device, I: np.dtype, nqueries: int, cache: Optional[BVHTraversal], ordered: bool,
-                   reference_shaped: bool):
+                   reference_shaped: bool, packet: bool = False):
     """The reference's count -> accumulate -> allocate/grow -> write protocol (traverse_single.jl:23-78),
     with `cache1`/`cache2` reused and grown only when too small."""
     pdt = pair_dtype(I)
     flags = capi.TRAVERSE_ORDERED if ordered else capi.TRAVERSE_UNORDERED
-    if reference_shaped:
-        flags |= capi.TRAVERSE_REFERENCE_SHAPED
+    sched = (capi.TRAVERSE_REFERENCE_SHAPED if reference_shaped else 0) | (capi.TRAVERSE_PACKET if packet else 0)
+    flags |= sched
     if cache is not None:
         if cache.cache2.dtype != I:
             raise ArgumentError("eltype(cache.cache2) === I must hold")
@@ -481,7 +481,7 @@ def _run_two_phase(call, handle, device, I: np.dtype, nqueries: int, cache: Opti
             _raise(rc, handle, "traverse")
         return int(total.value), cache1, cache2
     # no usable contacts buffer yet: count pass, allocate exactly, write pass
-    rc = call(capi.TRAVERSE_ORDERED | (capi.TRAVERSE_REFERENCE_SHAPED if reference_shaped else 0), cache2.ptr, None, 0, total)
+    rc = call(capi.TRAVERSE_ORDERED | sched, cache2.ptr, None, 0, total)
     if rc != capi.OK:
         _raise(rc, handle, "traverse (count)")
     need = int(total.value)
@@ -497,12 +497,13 @@ def _run_two_phase(call, handle, device, I: np.dtype, nqueries: int, cache: Opti
 
 def traverse(bvh: BVH, bvh2=None, alg=None, *, start_level: Optional[int] = None, start_level1: Optional[int] = None,
              start_level2: Optional[int] = None, narrow=None, cache: Optional[BVHTraversal] = None, options: BVHOptions = None,
-             ordered: bool = True, reference_shaped: bool = False, query_range=None) -> BVHTraversal:
+             ordered: bool = True, reference_shaped: bool = False, packet: bool = False, query_range=None) -> BVHTraversal:
     """`traverse(bvh[, bvh2], LVTTraversal(); start_level[1,2], narrow, cache, options)`.
 
     Extensions over the reference signature (all keyword-only, defaults reproduce the reference):
-    `ordered=False` selects the one-pass unordered emission, `reference_shaped=True` the proxy of the
-    reference's own GPU kernel, `query_range=(begin, count)` restricts the query leaves (multi-GPU shard).
+    `ordered=False` selects the unordered emission, `reference_shaped=True` the proxy of the reference's
+    own GPU kernel, `packet=True` forces the warp-packet schedule (default: group walk + dense tiles for
+    BBox nodes), `query_range=(begin, count)` restricts the query leaves (multi-GPU shard).
     """
     if bvh2 is not None and not isinstance(bvh2, BVH):       # traverse(bvh, alg)
         alg, bvh2 = bvh2, None
@@ -529,7 +530,7 @@ def traverse(bvh: BVH, bvh2=None, alg=None, *, start_level: Optional[int] = None
                 return lib.ibvh_traverse_single(bvh._handle, C.byref(cb), C.byref(params), p_counts, p_contacts, capacity,
                                                 C.byref(total), _stream_ptr(device.index))
 
-        total, c1, c2 = _run_two_phase(call, bvh._handle, device, I, nq, cache, ordered, reference_shaped)
+        total, c1, c2 = _run_two_phase(call, bvh._handle, device, I, nq, cache, ordered, reference_shaped, packet)
         return BVHTraversal(sl, 0, 0, total, c1, c2)
 
     # pair — traverse_pair.jl:1-116
@@ -556,7 +557,7 @@ def traverse(bvh: BVH, bvh2=None, alg=None, *, start_level: Optional[int] = None
             return lib.ibvh_traverse_pair(bvh._handle, C.byref(cq), C.byref(ct), C.byref(params), p_counts, p_contacts, capacity,
                                           C.byref(total), _stream_ptr(device.index))
 
-    total, c1, c2 = _run_two_phase(call, bvh._handle, device, I, nq, cache, ordered, reference_shaped)
+    total, c1, c2 = _run_two_phase(call, bvh._handle, device, I, nq, cache, ordered, reference_shaped, packet)
     return BVHTraversal(sl1, sl2, 0, total, c1, c2)
 
 

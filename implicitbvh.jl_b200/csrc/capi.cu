@@ -2,7 +2,9 @@
 // checks mirroring the reference's @argcheck's, type dispatch onto the kernel templates, workspace
 // carving and the launch sequences. No CPU fallback: without a device every call fails loudly.
 #include <climits>
+#include <cstdlib>
 #include <cmath>
+#include <algorithm>
 #include <new>
 #include <type_traits>
 
@@ -12,6 +14,7 @@
 #include "morton.cuh"
 #include "radix_sort.cuh"
 #include "traverse.cuh"
+#include "traverse_tile.cuh"
 
 using namespace ibvh;
 
@@ -399,6 +402,142 @@ int traverse_impl(ibvh_handle* h, const LQ* qleaves, const typename LT::value_ty
     return launch_traverse<KIND, kWrite, PACKET, LQ, LT, N, I>(h, qleaves, points, dirs, bvh, a, counts, (IndexPair<I>*)d_contacts, st);
 }
 
+// ---- tiled traversal driver (BBox nodes): group walk -> scan -> lists -> tiles ------------------------------
+constexpr int kTileG = 8;          // leaves per group
+constexpr int kTileLogG = 3;
+constexpr uint32_t kTileSegCap = 128;    // target groups recorded per query group before it is flagged
+constexpr uint32_t kTileStepCap = 2048;  // walk steps per query group before it is flagged
+
+template <class LT> bool tiled_applicable(const TreeInfo& ti, int start_level) {
+    return ti.levels - kTileLogG >= 1 && start_level <= ti.levels - kTileLogG && ti.levels >= kTileLogG + 2;
+}
+
+template <int KIND, class LQ, class LT, class I>
+int traverse_tiled(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, const DBvh<LT, BBox<typename LT::value_type>>& bvh,
+                   const TraverseArgs& ta, uint32_t flags, void* d_counts, void* d_contacts, int64_t capacity, int64_t* num_contacts,
+                   cudaStream_t st) {
+    constexpr int G = kTileG;
+    using N = BBox<typename LT::value_type>;
+    unsigned long long* d_total = (unsigned long long*)(h->d_small + kSmallTotal);
+    uint32_t* d_fcount = (uint32_t*)(h->d_small + kSmallTotal + 16);
+    *num_contacts = 0;
+    if (ta.q_count <= 0) return IBVH_OK;
+    GroupArgs a{};
+    a.q_begin = ta.q_begin; a.q_count = ta.q_count; a.n_groups = (ta.q_count + G - 1) / G;
+    a.start_level = ta.start_level; a.group_level = bvh.ti.levels - kTileLogG; a.flip = ta.flip;
+    a.seg_cap = kTileSegCap; a.step_cap = kTileStepCap;
+    a.capacity = d_contacts ? capacity : 0; a.total = d_total;
+    a.dbg = nullptr;
+    const bool dbg = getenv("IBVH_DEBUG") != nullptr;
+    if (dbg) { a.dbg = (unsigned long long*)(h->d_small + 1024); IBVH_CUDA_TRY(h, cudaMemsetAsync(a.dbg, 0, 640, st)); }
+    const bool unordered = (flags & IBVH_TRAVERSE_UNORDERED) != 0 && d_contacts != nullptr;
+    const int64_t qblocks = (a.q_count + kScanTile - 1) / kScanTile;
+    size_t need = 2 * ibvh_handle::padded((size_t)a.n_groups * 4) + ibvh_handle::padded((size_t)qblocks * 8) +
+                  (d_counts ? 0 : ibvh_handle::padded((size_t)a.q_count * sizeof(I))) + 4096;
+    int rc = h->reserve(need);
+    if (rc != IBVH_OK) return rc;
+    h->reset();
+    uint32_t* gcounts = h->alloc<uint32_t>(a.n_groups);
+    uint32_t* flist = h->alloc<uint32_t>(a.n_groups);
+    long long* qsums = h->alloc<long long>(qblocks);
+    I* counts = d_counts ? (I*)d_counts : h->alloc<I>(a.q_count);
+    if (!gcounts || !flist || !qsums || !counts) { h->set_error("workspace carve failed"); return IBVH_ERR_ALLOC; }
+    rc = h->reserve_aux((size_t)a.n_groups * a.seg_cap * 4);
+    if (rc != IBVH_OK) return rc;
+    uint32_t* glist = (uint32_t*)h->aux;
+
+    // phase 1 (one pass, bounded): per-group target lists + the list of flagged groups
+    IBVH_CUDA_TRY(h, cudaMemsetAsync(d_fcount, 0, 4, st));
+    const unsigned wblocks = (unsigned)((a.n_groups + kWalkThreads - 1) / kWalkThreads);
+    { ProfScope _ps(h, st, "group_walk_kernel");
+    group_walk_kernel<KIND, G, LQ, LT><<<wblocks, kWalkThreads, 0, st>>>(qleaves, n_query_total, bvh, a, gcounts, glist, flist, d_fcount);
+    }
+    IBVH_LAUNCH_CHECK(h, "group_walk_kernel");
+    if (dbg) {
+        unsigned long long hbuf[80];
+        cudaMemcpy(hbuf, a.dbg, 640, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[ibvh debug] groups=%lld walk steps=%llu (%.1f/group) flagged=%llu\n  steps log2 hist:", (long long)a.n_groups,
+                hbuf[0], (double)hbuf[0] / a.n_groups, hbuf[1]);
+        for (int k = 0; k < 20; ++k) fprintf(stderr, " %llu", hbuf[2 + k]);
+        fprintf(stderr, "\n  pairs log2 hist:");
+        for (int k = 0; k < 12; ++k) fprintf(stderr, " %llu", hbuf[40 + k]);
+        fprintf(stderr, "\n");
+        a.dbg = nullptr;
+    }
+    // the per-query kernel picks up the members of flagged groups (grid-stride over flist)
+    TraverseArgs fa = ta;
+    fa.total = d_total; fa.stats = nullptr; fa.capacity = a.capacity;
+    fa.qmap = flist; fa.qmap_count = d_fcount; fa.qmap_group = G;
+    const unsigned fblocks = (unsigned)std::min<int64_t>((a.q_count + 127) / 128, (int64_t)h->sm_count * 8);
+    constexpr int SLOTS = 32 / G;
+    const int64_t twarps = (a.n_groups + SLOTS - 1) / SLOTS;
+    const unsigned tblocks = (unsigned)((twarps + kTileWarps - 1) / kTileWarps);
+    auto run = [&](auto mode_tag, I* cnts, IndexPair<I>* out) -> int {
+        constexpr int MODE = decltype(mode_tag)::value;
+        IBVH_CUDA_TRY(h, cudaEventRecord(h->ev_fork, st));           // everything the side stream needs is enqueued
+        // members of flagged groups: per-query kernel on the high-priority side stream, submitted first so that
+        // its few long-running blocks start immediately and overlap the tile kernel
+        IBVH_CUDA_TRY(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+        { ProfScope _ps(h, h->side, "lvt_thread_kernel");
+        lvt_thread_kernel<KIND, MODE, LQ, LT, N, I><<<fblocks, 128, 0, h->side>>>(qleaves, nullptr, nullptr, bvh, fa, cnts, out);
+        }
+        IBVH_LAUNCH_CHECK(h, "lvt_thread_kernel(flagged groups)");
+        if constexpr (MODE == kWrite) {
+            { ProfScope _ps(h, st, "tile_kernel");
+            tile_kernel<KIND, MODE, G, LQ, LT, I><<<tblocks, kTileWarps * 32, 0, st>>>(qleaves, n_query_total, bvh, a, gcounts, glist, cnts, out);
+            }
+        } else {
+            { ProfScope _ps(h, st, "tile_flat_kernel");
+            tile_flat_kernel<KIND, MODE, G, LQ, LT, I><<<tblocks, kTileWarps * 32, 0, st>>>(qleaves, n_query_total, bvh, a, gcounts, glist, cnts, out);
+            }
+        }
+        IBVH_LAUNCH_CHECK(h, "tile_kernel");
+        IBVH_CUDA_TRY(h, cudaEventRecord(h->ev_join, h->side));
+        IBVH_CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_join, 0));
+        return IBVH_OK;
+    };
+    if (unordered) {
+        IBVH_CUDA_TRY(h, cudaMemsetAsync(d_total, 0, 8, st));
+        rc = run(std::integral_constant<int, kAtomic>{}, (I*)nullptr, (IndexPair<I>*)d_contacts);
+        if (rc != IBVH_OK) return rc;
+        rc = read_total(h, d_total, num_contacts, st);
+        if (rc != IBVH_OK) return rc;
+        return *num_contacts > capacity ? IBVH_ERR_CAPACITY : IBVH_OK;
+    }
+    if ((flags & IBVH_TRAVERSE_COUNTS_VALID) && d_counts && d_contacts) {
+        I* hp = (I*)(h->h_pinned + 64);
+        IBVH_CUDA_TRY(h, cudaMemcpyAsync(hp, counts + (a.q_count - 1), sizeof(I), cudaMemcpyDeviceToHost, st));
+        IBVH_CUDA_TRY(h, cudaStreamSynchronize(st));
+        *num_contacts = (int64_t)*hp;
+    } else {
+        rc = run(std::integral_constant<int, kCount>{}, counts, (IndexPair<I>*)nullptr);
+        if (rc != IBVH_OK) return rc;
+        rc = scan_counts<I>(h, counts, a.q_count, qsums, d_total, st);
+        if (rc != IBVH_OK) return rc;
+        rc = read_total(h, d_total, num_contacts, st);
+        if (rc != IBVH_OK) return rc;
+    }
+    if (!d_contacts || *num_contacts == 0) return IBVH_OK;
+    if (*num_contacts > capacity) return IBVH_ERR_CAPACITY;
+    return run(std::integral_constant<int, kWrite>{}, counts, (IndexPair<I>*)d_contacts);
+}
+
+// Schedule choice for leaf queries: tiled (BBox nodes, tall enough tree, start level above the groups),
+// else the packet schedule; IBVH_TRAVERSE_REFERENCE_SHAPED / IBVH_TRAVERSE_PACKET force the others.
+template <int KIND, class LQ, class LT, class N, class I>
+int traverse_leaf_queries(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, const DBvh<LT, N>& d, const TraverseArgs& a, uint32_t flags,
+                          void* d_counts, void* d_contacts, int64_t capacity, int64_t* num_contacts, cudaStream_t st) {
+    if (flags & IBVH_TRAVERSE_REFERENCE_SHAPED)
+        return traverse_impl<KIND, false, LQ, LT, N, I>(h, qleaves, nullptr, nullptr, d, a, flags, d_counts, d_contacts, capacity, num_contacts, st);
+    if constexpr (std::is_same<N, BBox<typename LT::value_type>>::value) {
+        if (!(flags & (IBVH_TRAVERSE_PACKET | IBVH_TRAVERSE_STATS)) && tiled_applicable<LT>(d.ti, a.start_level)) {
+            int rc = traverse_tiled<KIND, LQ, LT, I>(h, qleaves, n_query_total, d, a, flags, d_counts, d_contacts, capacity, num_contacts, st);
+            if (rc != IBVH_ERR_UNSUPPORTED) return rc;
+        }
+    }
+    return traverse_impl<KIND, true, LQ, LT, N, I>(h, qleaves, nullptr, nullptr, d, a, flags, d_counts, d_contacts, capacity, num_contacts, st);
+}
+
 int check_bvh(const ibvh_bvh_t* b, ibvh_tree_t* tree) {
     if (!b || !types_ok(&b->types)) return IBVH_ERR_ARGUMENT;
     int rc = make_tree(b->n, tree);
@@ -517,6 +656,15 @@ int ibvh_create(ibvh_handle_t** out, int device) {
         return IBVH_ERR_ALLOC;
     }
     cudaMemset(h->d_small, 0, ibvh_handle::kSmallBytes);
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(h->d_small); cudaFreeHost(h->h_pinned); delete h;
+        return IBVH_ERR_CUDA;
+    }
     *out = h;
     return IBVH_OK;
 }
@@ -524,8 +672,12 @@ int ibvh_destroy(ibvh_handle_t* h) {
     if (!h) return IBVH_OK;
     DeviceGuard g(h->device);
     if (h->ws) cudaFree(h->ws);
+    if (h->aux) cudaFree(h->aux);
     if (h->d_small) cudaFree(h->d_small);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
+    if (h->side) cudaStreamDestroy(h->side);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     delete h;
     return IBVH_OK;
 }
@@ -540,6 +692,7 @@ int ibvh_release_workspace(ibvh_handle_t* h) {
     if (!h) return IBVH_ERR_ARGUMENT;
     DeviceGuard g(h->device);
     if (h->ws) { IBVH_CUDA_TRY(h, cudaFree(h->ws)); h->ws = nullptr; h->ws_bytes = 0; }
+    if (h->aux) { IBVH_CUDA_TRY(h, cudaFree(h->aux)); h->aux = nullptr; h->aux_bytes = 0; }
     return IBVH_OK;
 }
 
@@ -676,9 +829,7 @@ int ibvh_traverse_single(ibvh_handle_t* h, const ibvh_bvh_t* bvh, const ibvh_tra
             shard_range(p, bvh->n, &a.q_begin, &a.q_count);
             a.start_level = (int32_t)p->start_level;
             a.flip = 0;
-            if (p->flags & IBVH_TRAVERSE_REFERENCE_SHAPED)
-                return traverse_impl<kSingle, false, L, L, N, I>(h, d.leaves, nullptr, nullptr, d, a, p->flags, d_counts, d_contacts, capacity, num_contacts, st);
-            return traverse_impl<kSingle, true, L, L, N, I>(h, d.leaves, nullptr, nullptr, d, a, p->flags, d_counts, d_contacts, capacity, num_contacts, st);
+            return traverse_leaf_queries<kSingle, L, L, N, I>(h, d.leaves, bvh->n, d, a, p->flags, d_counts, d_contacts, capacity, num_contacts, st);
         });
     });
 }
@@ -710,9 +861,7 @@ int ibvh_traverse_pair(ibvh_handle_t* h, const ibvh_bvh_t* queries, const ibvh_b
             shard_range(p, queries->n, &a.q_begin, &a.q_count);
             a.start_level = (int32_t)p->start_level;
             a.flip = p->flip ? 1 : 0;
-            if (p->flags & IBVH_TRAVERSE_REFERENCE_SHAPED)
-                return traverse_impl<kPair, false, L, L, N, I>(h, (const L*)queries->d_leaves, nullptr, nullptr, d, a, p->flags, d_counts, d_contacts, capacity, num_contacts, st);
-            return traverse_impl<kPair, true, L, L, N, I>(h, (const L*)queries->d_leaves, nullptr, nullptr, d, a, p->flags, d_counts, d_contacts, capacity, num_contacts, st);
+            return traverse_leaf_queries<kPair, L, L, N, I>(h, (const L*)queries->d_leaves, queries->n, d, a, p->flags, d_counts, d_contacts, capacity, num_contacts, st);
         });
     });
 }

@@ -17,6 +17,19 @@ struct ibvh_handle {
     size_t ws_bytes = 0;
     size_t ws_off = 0;
 
+    // second grow-only buffer: the (query group -> target group) lists of the tiled traversal
+    char* aux = nullptr;
+    size_t aux_bytes = 0;
+    int reserve_aux(size_t bytes) {
+        if (bytes <= aux_bytes) return IBVH_OK;
+        if (aux) { cudaFree(aux); aux = nullptr; aux_bytes = 0; }
+        size_t want = bytes + (bytes >> 2) + (1u << 20);
+        cudaError_t e = cudaMalloc((void**)&aux, want);
+        if (e != cudaSuccess) { set_cuda_error(e, "cudaMalloc(aux)"); aux = nullptr; cudaGetLastError(); return IBVH_ERR_ALLOC; }
+        aux_bytes = want;
+        return IBVH_OK;
+    }
+
     // persistent small device block: [0..47] scene bounds (6 x u64 ordered keys),
     // [64..) counters: total contacts (u64), tile tickets, stats.
     char* d_small = nullptr;
@@ -27,6 +40,10 @@ struct ibvh_handle {
     static constexpr size_t kPinnedBytes = 4096;
 
     int64_t last_stats[4] = {0, 0, 0, 0};
+
+    // side stream + events: the per-query pass over flagged groups overlaps the tile kernel
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
     // optional per-kernel timing (ibvh_profile_*): CUDA events recorded on the launching stream
     static constexpr int kMaxProf = 512;

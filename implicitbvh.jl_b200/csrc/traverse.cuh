@@ -40,6 +40,11 @@ struct TraverseArgs {
     int64_t id_base;        // rays: reported id = id_base + q + 1
     unsigned long long* total;   // atomic mode: running total
     unsigned long long* stats;   // optional counters (node tests, leaf tests, steps) or nullptr
+    // optional indirection (fallback of the tiled schedule): the queries are the members of the query
+    // groups listed in qmap[0 .. *qmap_count), qmap_group leaves per group; grid-stride over them
+    const uint32_t* qmap;
+    const uint32_t* qmap_count;
+    int32_t qmap_group;
 };
 
 // 8-byte vectorised struct loads (volumes are 8-byte aligned by layout; see common.cuh)
@@ -100,11 +105,15 @@ __global__ void __launch_bounds__(128) lvt_thread_kernel(const LQ* __restrict__ 
                                                         DBvh<LT, N> bvh, TraverseArgs a,
                                                         I* counts, IndexPair<I>* contacts) {
     using T = typename LT::value_type;
-    const int64_t qi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // query within the shard
-    if (qi >= a.q_count) return;
-    const int64_t q = a.q_begin + qi;
     const TreeInfo& ti = bvh.ti;
     const int levels = ti.levels;
+    const int64_t t_stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t t_limit = a.qmap ? (int64_t)(*a.qmap_count) * a.qmap_group : a.q_count;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < t_limit; t += t_stride) {
+    int64_t qi = t;                                                       // query within the shard
+    if (a.qmap) qi = (int64_t)a.qmap[t / a.qmap_group] * a.qmap_group + (t % a.qmap_group);
+    if (qi >= a.q_count) continue;
+    const int64_t q = a.q_begin + qi;
 
     QueryLeaf<LQ, N> ql;
     QueryRay<T> qr;
@@ -192,6 +201,7 @@ __global__ void __launch_bounds__(128) lvt_thread_kernel(const LQ* __restrict__ 
             if ((threadIdx.x & 31) == (__ffs(m) - 1)) atomicAdd(a.stats + 3, mx);     // sum over warps of the slowest lane's steps
         }
     }
+    }   // grid-stride loop over queries
 }
 
 // ===========================================================================================================

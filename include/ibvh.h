@@ -90,6 +90,8 @@ typedef struct ibvh_bvh {
 #define IBVH_TRAVERSE_UNORDERED 1u   /* one pass, warp-aggregated atomic append (same set)     */
 #define IBVH_TRAVERSE_REFERENCE_SHAPED 2u /* proxy of the reference GPU kernel: one thread per  */
                                           /* query, local stack, two passes (for comparison)   */
+#define IBVH_TRAVERSE_PACKET 16u      /* force the warp-packet schedule (default for BSphere nodes); the */
+                                      /* default for BBox nodes is the "group walk + dense tiles" one    */
 #define IBVH_TRAVERSE_STATS 8u        /* fill the device counters read by ibvh_last_traversal_stats */
 #define IBVH_TRAVERSE_COUNTS_VALID 4u /* ORDERED only: d_counts already holds the inclusive scan */
                                       /* left by a previous count-only call on the same queries: */

@@ -324,6 +324,10 @@ def test_single_all_start_levels(ib, O, dev, node):
             assert (sorted_pairs(un.contacts.numpy()) == brute).all(), (n, sl, "unordered")
             rs = ib.traverse(bvh, start_level=sl, reference_shaped=True)
             assert rs.contacts.numpy().tobytes() == want.tobytes(), (n, sl, "reference-shaped")
+            pk = ib.traverse(bvh, start_level=sl, packet=True)
+            assert pk.contacts.numpy().tobytes() == want.tobytes(), (n, sl, "packet")
+            pu = ib.traverse(bvh, start_level=sl, packet=True, ordered=False)
+            assert (sorted_pairs(pu.contacts.numpy()) == brute).all(), (n, sl, "packet unordered")
 
 
 def test_single_counts_cache2_and_growth(ib, O, dev):
@@ -433,6 +437,8 @@ def test_pair_all_start_levels(ib, O, dev):
                         assert (sorted_pairs(want) == brute).all()
                         un = ib.traverse(b1, b2, start_level1=sl1, start_level2=sl2, ordered=False)
                         assert (sorted_pairs(un.contacts.numpy()) == brute).all()
+                        pk = ib.traverse(b1, b2, start_level1=sl1, start_level2=sl2, packet=True)
+                        assert pk.contacts.numpy().tobytes() == want.tobytes(), (n1, n2, sl1, sl2, "packet")
 
 
 def test_pair_self_equivalence_and_partial_build(ib, O, dev):
@@ -522,6 +528,9 @@ def test_config1_100k_against_oracle(ib, O, dev):
     assert 3.0 * n < len(want) < 5.0 * n                    # C ~ 4 N by construction
     un = ib.traverse(bvh, ordered=False)
     assert (sorted_pairs(un.contacts.numpy()) == sorted_pairs(want)).all()
+    for kw in (dict(packet=True), dict(reference_shaped=True)):
+        assert ib.traverse(bvh, **kw).contacts.numpy().tobytes() == want.tobytes(), kw
+        assert (sorted_pairs(ib.traverse(bvh, ordered=False, **kw).contacts.numpy()) == sorted_pairs(want)).all(), kw
 
 
 def test_rays_mesh_like_against_oracle(ib, O, dev):

@@ -74,8 +74,10 @@ def main():
         print(f"\n=== n={n} contacts={C_} ({C_ / n:.2f}/leaf) levels={bvh.tree.levels}", flush=True)
         cases = [
             ("build", lambda: ib.BVH(src, ib.BBox(), cache=bvh)),
-            ("traverse ordered(packet)", lambda: ib.traverse(bvh, cache=big)),
-            ("traverse unordered(packet)", lambda: ib.traverse(bvh, cache=big, ordered=False)),
+            ("traverse ordered(tiled)", lambda: ib.traverse(bvh, cache=big)),
+            ("traverse unordered(tiled)", lambda: ib.traverse(bvh, cache=big, ordered=False)),
+            ("traverse ordered(packet)", lambda: ib.traverse(bvh, cache=big, packet=True)),
+            ("traverse unordered(packet)", lambda: ib.traverse(bvh, cache=big, ordered=False, packet=True)),
         ]
         if args.ref_shaped:
             cases += [

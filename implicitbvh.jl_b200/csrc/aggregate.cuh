@@ -100,9 +100,28 @@ __global__ void __launch_bounds__(THREADS) gather_merge_kernel(const SRC* __rest
     const int tile_n = (int)min((int64_t)TILE, ti.n - base);
 
     if constexpr (GATHER) {
-        for (int j = threadIdx.x; j < tile_n; j += THREADS) {
-            uint32_t p = perm[base + j];
-            store_words(sleaf + j, GatherSrc<L, SRC>::make(src, p, keys_sorted[base + j]));
+        // all permutation / key loads first, then all (random) source loads: TILE/THREADS independent
+        // gathers in flight per thread instead of one dependent chain at a time
+        constexpr int PER = TILE / THREADS;
+        uint32_t pp[PER];
+        typename L::mor_t kk[PER];
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            int j = threadIdx.x + u * THREADS;
+            bool ok = j < tile_n;
+            pp[u] = ok ? perm[base + j] : 0u;
+            kk[u] = ok ? keys_sorted[base + j] : typename L::mor_t(0);
+        }
+        Words<L> wv[PER];
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            int j = threadIdx.x + u * THREADS;
+            if (j < tile_n) wv[u] = GatherSrc<L, SRC>::make(src, pp[u], kk[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            int j = threadIdx.x + u * THREADS;
+            if (j < tile_n) store_words(sleaf + j, wv[u]);
         }
         __syncthreads();
         // coalesced write-back of the tile (sizeof(L) is a multiple of 4; full tiles are 16-byte multiples)

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libibvh_b200.so")
 OK, ERR_ARGUMENT, ERR_DOMAIN, ERR_UNSUPPORTED, ERR_CUDA, ERR_CAPACITY, ERR_ALLOC = range(7)
 BSPHERE, BBOX = 0, 1
 TRAVERSE_ORDERED, TRAVERSE_UNORDERED, TRAVERSE_REFERENCE_SHAPED, TRAVERSE_COUNTS_VALID = 0, 1, 2, 4
-TRAVERSE_STATS, TRAVERSE_PACKET = 8, 16
+TRAVERSE_STATS, TRAVERSE_PACKET, TRAVERSE_WALK = 8, 16, 32
 
 
 class Types(C.Structure):

@@ -449,12 +449,13 @@ def _check_narrow(narrow):
 
 
 def _run_two_phase(call, handle, device, I: np.dtype, nqueries: int, cache: Optional[BVHTraversal], ordered: bool,
-                   reference_shaped: bool, packet: bool = False):
+                   reference_shaped: bool, packet: bool = False, walk: bool = False):
     """The reference's count -> accumulate -> allocate/grow -> write protocol (traverse_single.jl:23-78),
     with `cache1`/`cache2` reused and grown only when too small."""
     pdt = pair_dtype(I)
     flags = capi.TRAVERSE_ORDERED if ordered else capi.TRAVERSE_UNORDERED
-    sched = (capi.TRAVERSE_REFERENCE_SHAPED if reference_shaped else 0) | (capi.TRAVERSE_PACKET if packet else 0)
+    sched = (capi.TRAVERSE_REFERENCE_SHAPED if reference_shaped else 0) | (capi.TRAVERSE_PACKET if packet else 0) | \
+            (capi.TRAVERSE_WALK if walk else 0)
     flags |= sched
     if cache is not None:
         if cache.cache2.dtype != I:
@@ -497,7 +498,8 @@ def _run_two_phase(call, handle, device, I: np.dtype, nqueries: int, cache: Opti
 
 def traverse(bvh: BVH, bvh2=None, alg=None, *, start_level: Optional[int] = None, start_level1: Optional[int] = None,
              start_level2: Optional[int] = None, narrow=None, cache: Optional[BVHTraversal] = None, options: BVHOptions = None,
-             ordered: bool = True, reference_shaped: bool = False, packet: bool = False, query_range=None) -> BVHTraversal:
+             ordered: bool = True, reference_shaped: bool = False, packet: bool = False, walk: bool = False,
+             query_range=None) -> BVHTraversal:
     """`traverse(bvh[, bvh2], LVTTraversal(); start_level[1,2], narrow, cache, options)`.
 
     Extensions over the reference signature (all keyword-only, defaults reproduce the reference):
@@ -530,7 +532,7 @@ def traverse(bvh: BVH, bvh2=None, alg=None, *, start_level: Optional[int] = None
                 return lib.ibvh_traverse_single(bvh._handle, C.byref(cb), C.byref(params), p_counts, p_contacts, capacity,
                                                 C.byref(total), _stream_ptr(device.index))
 
-        total, c1, c2 = _run_two_phase(call, bvh._handle, device, I, nq, cache, ordered, reference_shaped, packet)
+        total, c1, c2 = _run_two_phase(call, bvh._handle, device, I, nq, cache, ordered, reference_shaped, packet, walk)
         return BVHTraversal(sl, 0, 0, total, c1, c2)
 
     # pair — traverse_pair.jl:1-116
@@ -557,7 +559,7 @@ def traverse(bvh: BVH, bvh2=None, alg=None, *, start_level: Optional[int] = None
             return lib.ibvh_traverse_pair(bvh._handle, C.byref(cq), C.byref(ct), C.byref(params), p_counts, p_contacts, capacity,
                                           C.byref(total), _stream_ptr(device.index))
 
-    total, c1, c2 = _run_two_phase(call, bvh._handle, device, I, nq, cache, ordered, reference_shaped, packet)
+    total, c1, c2 = _run_two_phase(call, bvh._handle, device, I, nq, cache, ordered, reference_shaped, packet, walk)
     return BVHTraversal(sl1, sl2, 0, total, c1, c2)
 
 

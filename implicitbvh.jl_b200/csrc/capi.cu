@@ -15,6 +15,7 @@
 #include "radix_sort.cuh"
 #include "traverse.cuh"
 #include "traverse_tile.cuh"
+#include "traverse_pyramid.cuh"
 
 using namespace ibvh;
 
@@ -522,14 +523,206 @@ int traverse_tiled(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, con
     return run(std::integral_constant<int, kWrite>{}, counts, (IndexPair<I>*)d_contacts);
 }
 
+// ---- pyramid refinement driver (BBox nodes) -----------------------------------------------------------------
+struct PyrPlan { int n; PyrLevel lv[kPyrMaxLevels]; int64_t u_total; };
+
+// levels from the finest (k = 2) to the top; false if the schedule does not apply (tree too short, the needed
+// tree levels are not built, or the coarsest usable level still has too many groups for an all-pairs start)
+inline bool make_pyr_plan(const TreeInfo& ti, int64_t built_level, int64_t q_begin, int64_t q_count, PyrPlan* plan) {
+    const int L = ti.levels;
+    const int64_t q_end = q_begin + q_count;
+    plan->n = 0; plan->u_total = 0;
+    for (int k = kPyrLeafLog; plan->n < kPyrMaxLevels; k += kPyrFan) {
+        const int tl = L - k;
+        if (tl < 1 || tl < built_level) break;
+        PyrLevel& v = plan->lv[plan->n];
+        v.k = k; v.tree_level = tl; v.ntg = ti.level_nreal[tl]; v.tnode0 = ti.level_start[tl];
+        v.qg_first = q_begin >> k; v.nqg = ((q_end - 1) >> k) - v.qg_first + 1; v.u_off = plan->u_total;
+        plan->u_total += v.nqg;
+        plan->n += 1;
+        if (v.nqg <= 2048 && v.ntg <= 2048) return true;          // good top level
+    }
+    if (plan->n == 0) return false;
+    const PyrLevel& top = plan->lv[plan->n - 1];
+    return top.nqg * top.ntg <= (int64_t(1) << 26);                 // an all-pairs start of <= 64 M box tests is still cheap
+}
+
+template <int KIND, class LQ, class LT, class I>
+int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, const DBvh<LT, BBox<typename LT::value_type>>& bvh,
+                     const PyrPlan& plan, const TraverseArgs& ta, uint32_t flags, void* d_counts, void* d_contacts, int64_t capacity,
+                     int64_t* num_contacts, cudaStream_t st) {
+    using T = typename LT::value_type;
+    using N = BBox<T>;
+    *num_contacts = 0;
+    if (ta.q_count <= 0) return IBVH_OK;
+    const int64_t q_begin = ta.q_begin, q_end = ta.q_begin + ta.q_count;
+    unsigned long long* d_total = (unsigned long long*)(h->d_small + kSmallTotal);
+    unsigned long long* d_cnt = (unsigned long long*)(h->d_small + 1536);      // one list counter per level
+    const bool unordered = (flags & IBVH_TRAVERSE_UNORDERED) != 0 && d_contacts != nullptr;
+    const bool count_only = d_contacts == nullptr;
+    const int nl = plan.n;
+    const int grid = h->sm_count * (getenv("IBVH_PYR_GRID") ? atoi(getenv("IBVH_PYR_GRID")) : 10);
+
+    // ordered protocol scratch: counts (if the caller gave none), cursors, scan sums
+    const int64_t qblocks = (ta.q_count + kScanTile - 1) / kScanTile;
+    size_t need = ibvh_handle::padded((size_t)qblocks * 8) + ibvh_handle::padded((size_t)ta.q_count * 4) +
+                  (d_counts ? 0 : ibvh_handle::padded((size_t)ta.q_count * sizeof(I))) + 4096;
+    int rc = h->reserve(need);
+    if (rc != IBVH_OK) return rc;
+    h->reset();
+    long long* qsums = h->alloc<long long>(qblocks);
+    unsigned int* cursors = h->alloc<unsigned int>(ta.q_count);
+    I* counts = d_counts ? (I*)d_counts : h->alloc<I>(ta.q_count);
+    if (!qsums || !cursors || !counts) { h->set_error("workspace carve failed"); return IBVH_ERR_ALLOC; }
+
+    double factor = h->pyr_factor > 0 ? h->pyr_factor : (KIND == kSingle ? 40.0 : 80.0);
+    unsigned long long need_cap[kPyrMaxLevels] = {0};
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        // carve: pyramid boxes + one pair list per level
+        unsigned long long cap[kPyrMaxLevels];
+        size_t bytes = ibvh_handle::padded((size_t)plan.u_total * sizeof(N));
+        for (int l = 0; l < nl; ++l) {
+            const PyrLevel& v = plan.lv[l];
+            unsigned long long c = (unsigned long long)(factor * (double)(v.nqg > v.ntg && KIND != kSingle ? v.nqg : v.nqg)) + 4096ull;
+            if (l == nl - 1) { unsigned long long all = (unsigned long long)(v.nqg * v.ntg); if (all < c) c = all; }
+            if (need_cap[l] > c) c = need_cap[l] + need_cap[l] / 8 + 4096ull;
+            cap[l] = c;
+            bytes += ibvh_handle::padded((size_t)c * sizeof(uint2));
+        }
+        rc = h->reserve_aux(bytes);
+        if (rc != IBVH_OK) return rc;
+        char* ap = h->aux;
+        N* U = (N*)ap; ap += ibvh_handle::padded((size_t)plan.u_total * sizeof(N));
+        PairList lists[kPyrMaxLevels];
+        for (int l = 0; l < nl; ++l) { lists[l].data = (uint2*)ap; lists[l].count = d_cnt + l; lists[l].cap = cap[l]; ap += ibvh_handle::padded((size_t)cap[l] * sizeof(uint2)); }
+        IBVH_CUDA_TRY(h, cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * kPyrMaxLevels, st));
+        IBVH_CUDA_TRY(h, cudaMemsetAsync(d_total, 0, 8, st));
+
+        // 1. query pyramid
+        { ProfScope _ps(h, st, "pyr_leafgroups_kernel");
+        pyr_leafgroups_kernel<LQ, T><<<(unsigned)((plan.lv[0].nqg + 255) / 256), 256, 0, st>>>(qleaves, q_begin, q_end < n_query_total ? q_end : n_query_total, plan.lv[0], U);
+        }
+        IBVH_LAUNCH_CHECK(h, "pyr_leafgroups_kernel");
+        for (int l = 1; l < nl; ++l) {
+            { ProfScope _ps(h, st, "pyr_up_kernel");
+            pyr_up_kernel<T><<<(unsigned)((plan.lv[l].nqg + 255) / 256), 256, 0, st>>>(plan.lv[l - 1], plan.lv[l], U);
+            }
+            IBVH_LAUNCH_CHECK(h, "pyr_up_kernel");
+        }
+        // 2. top all-pairs
+        {
+            const PyrLevel& top = plan.lv[nl - 1];
+            int64_t tot = top.nqg * top.ntg;
+            int tg = (int)std::min<int64_t>((tot + 255) / 256, (int64_t)h->sm_count * 16);
+            { ProfScope _ps(h, st, "pyr_top_kernel");
+            pyr_top_kernel<KIND, T><<<tg, 256, 0, st>>>(top, U, bvh.nodes, lists[nl - 1]);
+            }
+            IBVH_LAUNCH_CHECK(h, "pyr_top_kernel");
+        }
+        // 3. refine down to the 4-leaf groups
+        for (int l = nl - 1; l >= 1; --l) {
+            { ProfScope _ps(h, st, "pyr_refine_kernel");
+            pyr_refine_kernel<KIND, T><<<grid, kPyrWarps * 32, 0, st>>>(plan.lv[l], plan.lv[l - 1], U, bvh.nodes, lists[l], lists[l - 1]);
+            }
+            IBVH_LAUNCH_CHECK(h, "pyr_refine_kernel");
+        }
+        // 4. leaf tiles
+        const int64_t qe = q_end < n_query_total ? q_end : n_query_total;
+        bool counts_valid = (flags & IBVH_TRAVERSE_COUNTS_VALID) && d_counts && d_contacts;
+        if (unordered || count_only) {
+            if (unordered) {
+                { ProfScope _ps(h, st, "pyr_leaf_tile_kernel");
+                pyr_leaf_tile_kernel<KIND, kAtomic, 0, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, capacity, d_total, (I*)nullptr, nullptr, (IndexPair<I>*)d_contacts);
+                }
+            } else if (d_counts) {
+                // count-only call of the ordered protocol: per-query counts + scan (cache2), total from the scan
+                IBVH_CUDA_TRY(h, cudaMemsetAsync(counts, 0, (size_t)ta.q_count * sizeof(I), st));
+                { ProfScope _ps(h, st, "pyr_leaf_tile_kernel");
+                pyr_leaf_tile_kernel<KIND, kCount, 1, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, 0, d_total, counts, nullptr, (IndexPair<I>*)nullptr);
+                }
+                IBVH_LAUNCH_CHECK(h, "pyr_leaf_tile_kernel");
+                rc = scan_counts<I>(h, counts, ta.q_count, qsums, d_total, st);
+                if (rc != IBVH_OK) return rc;
+            } else {
+                { ProfScope _ps(h, st, "pyr_leaf_tile_kernel");
+                pyr_leaf_tile_kernel<KIND, kCount, 0, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, 0, d_total, (I*)nullptr, nullptr, (IndexPair<I>*)nullptr);
+                }
+            }
+            IBVH_LAUNCH_CHECK(h, "pyr_leaf_tile_kernel");
+        } else if (!counts_valid) {
+            IBVH_CUDA_TRY(h, cudaMemsetAsync(counts, 0, (size_t)ta.q_count * sizeof(I), st));
+            { ProfScope _ps(h, st, "pyr_leaf_tile_kernel");
+            pyr_leaf_tile_kernel<KIND, kCount, 1, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, 0, d_total, counts, nullptr, (IndexPair<I>*)nullptr);
+            }
+            IBVH_LAUNCH_CHECK(h, "pyr_leaf_tile_kernel");
+            rc = scan_counts<I>(h, counts, ta.q_count, qsums, d_total, st);
+            if (rc != IBVH_OK) return rc;
+        }
+        // one read-back: contact total + the list counters (overflow check)
+        unsigned long long* hp = (unsigned long long*)h->h_pinned;
+        if (counts_valid && !unordered && !count_only) {
+            I* hpi = (I*)(h->h_pinned + 512);
+            IBVH_CUDA_TRY(h, cudaMemcpyAsync(hpi, counts + (ta.q_count - 1), sizeof(I), cudaMemcpyDeviceToHost, st));
+            IBVH_CUDA_TRY(h, cudaMemcpyAsync(hp + 1, d_cnt, sizeof(unsigned long long) * kPyrMaxLevels, cudaMemcpyDeviceToHost, st));
+            IBVH_CUDA_TRY(h, cudaStreamSynchronize(st));
+            hp[0] = (unsigned long long)*hpi;
+        } else {
+            IBVH_CUDA_TRY(h, cudaMemcpyAsync(hp, d_total, 8, cudaMemcpyDeviceToHost, st));
+            IBVH_CUDA_TRY(h, cudaMemcpyAsync(hp + 1, d_cnt, sizeof(unsigned long long) * kPyrMaxLevels, cudaMemcpyDeviceToHost, st));
+            IBVH_CUDA_TRY(h, cudaStreamSynchronize(st));
+        }
+        bool overflow = false;
+        double worst = 0.0;
+        for (int l = 0; l < nl; ++l) {
+            unsigned long long c = hp[1 + l];
+            need_cap[l] = c;
+            if (c > cap[l]) overflow = true;
+            double r = (double)c / (double)plan.lv[l].nqg;
+            if (l < nl - 1 && r > worst) worst = r;
+        }
+        if (getenv("IBVH_DEBUG")) {
+            fprintf(stderr, "[ibvh debug] pyramid levels=%d:", nl);
+            for (int l = nl - 1; l >= 0; --l) fprintf(stderr, " k=%d pairs=%llu/%llu", plan.lv[l].k, hp[1 + l], cap[l]);
+            fprintf(stderr, " contacts=%llu%s\n", hp[0], overflow ? " OVERFLOW -> retry" : "");
+        }
+        if (overflow) { factor = worst * 1.15 + 2.0; continue; }
+        h->pyr_factor = worst * 1.25 + 4.0;
+        *num_contacts = (int64_t)hp[0];
+        if (unordered) return *num_contacts > capacity ? IBVH_ERR_CAPACITY : IBVH_OK;
+        if (count_only || *num_contacts == 0) return IBVH_OK;
+        if (*num_contacts > capacity) return IBVH_ERR_CAPACITY;
+        // ordered write: per-query cursors, then sort each query's handful of hits by target position
+        IBVH_CUDA_TRY(h, cudaMemsetAsync(cursors, 0, (size_t)ta.q_count * 4, st));
+        { ProfScope _ps(h, st, "pyr_leaf_tile_kernel");
+        pyr_leaf_tile_kernel<KIND, kWrite, 2, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, capacity, d_total, counts, cursors, (IndexPair<I>*)d_contacts);
+        }
+        IBVH_LAUNCH_CHECK(h, "pyr_leaf_tile_kernel");
+        { ProfScope _ps(h, st, "pyr_fixup_kernel");
+        pyr_fixup_kernel<KIND, LQ, LT, I><<<(unsigned)((ta.q_count + 255) / 256), 256, 0, st>>>(qleaves, bvh.leaves, q_begin, ta.q_count, ta.flip, counts, (IndexPair<I>*)d_contacts);
+        }
+        IBVH_LAUNCH_CHECK(h, "pyr_fixup_kernel");
+        return IBVH_OK;
+    }
+    h->set_error("pyramid pair lists kept overflowing");
+    return IBVH_ERR_ALLOC;
+}
+
 // Schedule choice for leaf queries: tiled (BBox nodes, tall enough tree, start level above the groups),
 // else the packet schedule; IBVH_TRAVERSE_REFERENCE_SHAPED / IBVH_TRAVERSE_PACKET force the others.
 template <int KIND, class LQ, class LT, class N, class I>
-int traverse_leaf_queries(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, const DBvh<LT, N>& d, const TraverseArgs& a, uint32_t flags,
-                          void* d_counts, void* d_contacts, int64_t capacity, int64_t* num_contacts, cudaStream_t st) {
+int traverse_leaf_queries(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, const DBvh<LT, N>& d, int64_t built_level, const TraverseArgs& a,
+                          uint32_t flags, void* d_counts, void* d_contacts, int64_t capacity, int64_t* num_contacts, cudaStream_t st) {
     if (flags & IBVH_TRAVERSE_REFERENCE_SHAPED)
         return traverse_impl<KIND, false, LQ, LT, N, I>(h, qleaves, nullptr, nullptr, d, a, flags, d_counts, d_contacts, capacity, num_contacts, st);
     if constexpr (std::is_same<N, BBox<typename LT::value_type>>::value) {
+        // pyramid refinement: needs start_level above the leaves (so that the leaf-parent test is part of the
+        // reference predicate) and n < 2^31 positions in 32-bit pair entries
+        if (!(flags & (IBVH_TRAVERSE_PACKET | IBVH_TRAVERSE_STATS | IBVH_TRAVERSE_WALK)) && a.start_level <= d.ti.levels - 1 &&
+            d.ti.n < (int64_t(1) << 29) && n_query_total < (int64_t(1) << 29)) {
+            PyrPlan plan;
+            if (make_pyr_plan(d.ti, built_level, a.q_begin, a.q_count, &plan))
+                return traverse_pyramid<KIND, LQ, LT, I>(h, qleaves, n_query_total, d, plan, a, flags, d_counts, d_contacts, capacity, num_contacts, st);
+        }
         if (!(flags & (IBVH_TRAVERSE_PACKET | IBVH_TRAVERSE_STATS)) && tiled_applicable<LT>(d.ti, a.start_level)) {
             int rc = traverse_tiled<KIND, LQ, LT, I>(h, qleaves, n_query_total, d, a, flags, d_counts, d_contacts, capacity, num_contacts, st);
             if (rc != IBVH_ERR_UNSUPPORTED) return rc;
@@ -829,7 +1022,7 @@ int ibvh_traverse_single(ibvh_handle_t* h, const ibvh_bvh_t* bvh, const ibvh_tra
             shard_range(p, bvh->n, &a.q_begin, &a.q_count);
             a.start_level = (int32_t)p->start_level;
             a.flip = 0;
-            return traverse_leaf_queries<kSingle, L, L, N, I>(h, d.leaves, bvh->n, d, a, p->flags, d_counts, d_contacts, capacity, num_contacts, st);
+            return traverse_leaf_queries<kSingle, L, L, N, I>(h, d.leaves, bvh->n, d, bvh->built_level, a, p->flags, d_counts, d_contacts, capacity, num_contacts, st);
         });
     });
 }
@@ -861,7 +1054,7 @@ int ibvh_traverse_pair(ibvh_handle_t* h, const ibvh_bvh_t* queries, const ibvh_b
             shard_range(p, queries->n, &a.q_begin, &a.q_count);
             a.start_level = (int32_t)p->start_level;
             a.flip = p->flip ? 1 : 0;
-            return traverse_leaf_queries<kPair, L, L, N, I>(h, (const L*)queries->d_leaves, queries->n, d, a, p->flags, d_counts, d_contacts, capacity, num_contacts, st);
+            return traverse_leaf_queries<kPair, L, L, N, I>(h, (const L*)queries->d_leaves, queries->n, d, target->built_level, a, p->flags, d_counts, d_contacts, capacity, num_contacts, st);
         });
     });
 }

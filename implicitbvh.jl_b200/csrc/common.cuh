@@ -156,9 +156,10 @@ template <class T> IBVH_HD bool iscontact(const BSphere<T>& a, const BSphere<T>&
     return dist3sq(a.x, b.x) <= (a.r + b.r) * (a.r + b.r);
 }
 template <class T> IBVH_HD bool iscontact(const BBox<T>& a, const BBox<T>& b) {
-    return (a.up[0] >= b.lo[0] && a.lo[0] <= b.up[0]) &&
-           (a.up[1] >= b.lo[1] && a.lo[1] <= b.up[1]) &&
-           (a.up[2] >= b.lo[2] && a.lo[2] <= b.up[2]);
+    // same six closed comparisons as the reference, evaluated without short-circuit branches
+    return ((a.up[0] >= b.lo[0]) & (a.lo[0] <= b.up[0])) &
+           ((a.up[1] >= b.lo[1]) & (a.lo[1] <= b.up[1])) &
+           ((a.up[2] >= b.lo[2]) & (a.lo[2] <= b.up[2]));
 }
 
 // ---- isintersection.jl:1-65 --------------------------------------------------------------------------

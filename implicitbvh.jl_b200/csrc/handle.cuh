@@ -30,6 +30,9 @@ struct ibvh_handle {
         return IBVH_OK;
     }
 
+    // pyramid schedule: learned list-capacity factor (pairs per query group), see traverse_pyramid
+    double pyr_factor = 0.0;
+
     // persistent small device block: [0..47] scene bounds (6 x u64 ordered keys),
     // [64..) counters: total contacts (u64), tile tickets, stats.
     char* d_small = nullptr;

@@ -1,0 +1,431 @@
+// traverse_pyramid.cuh — "pyramid refinement": the fastest schedule for LVT contact traversal over BBox
+// nodes (single tree and BVH-vs-BVH). Same contact set as traverse_lvt_single! / traverse_lvt_pair!
+// (src/traverse/leaf_vs_tree/traverse_single.jl:136-208, traverse_pair.jl:176-244), bit for bit.
+//
+// Exactness (see traverse_tile.cuh for the containment argument): with BBox nodes the reference's
+// predicate is   P(q, j) = leaf_test(q, j) AND iscontact(BBox(q), parent_{levels-1}(j))   (+ j right of q
+// for the single tree), and if P(q, j) holds then for EVERY granularity 2^k the exact union box of the
+// query group containing q touches the tree node that covers the 2^k-leaf group containing j. So a
+// top-down refinement over *pairs of groups* that only drops pairs whose boxes are disjoint never
+// loses a contact, and the final 4 x 4 leaf tiles evaluate P itself.
+//
+// Schedule (no per-thread tree walk, no stacks, every work item is the same size):
+//   1. query pyramid: exact union boxes of the query leaves at group sizes 4, 32, 256, ... (min / max).
+//   2. top: all pairs (query group, tree node) at the coarsest size (<= 2048 groups per side).
+//   3. refine x (levels): each surviving pair (A, B) expands to its 8 x 8 child pairs; a warp handles 4
+//      pairs per step, lane = (pair slot, child of A), the 8 child boxes of B staged in shared memory.
+//   4. leaf tiles: pairs of 4-leaf groups, lane = (pair slot, query member), 4 leaf tests per lane,
+//      lazy leaf-parent test on a hit.
+// Survivors are appended to flat (A, B) lists through a shared-memory buffer that is flushed 32 entries
+// at a time with one atomic and one coalesced 256-byte store. List sizes stay on the device (the next
+// phase is a persistent grid-stride kernel that reads the count), so the whole traversal needs a single
+// host synchronisation: the read-back of the contact total, as in the reference.
+#pragma once
+#include <type_traits>
+
+#include "common.cuh"
+#include "traverse.cuh"
+#include "traverse_tile.cuh"
+
+namespace ibvh {
+
+constexpr int kPyrWarps = 4;                // warps per CTA in the refine / tile kernels
+constexpr int kPyrLeafLog = 2;              // finest groups: 4 leaves
+constexpr int kPyrFan = 3;                  // 8 children per refinement
+constexpr int kPyrMaxLevels = 12;
+constexpr int kPyrFlush = 256;              // buffered entries per list atomic
+
+struct PyrLevel {
+    int32_t k;               // group size 2^k leaves
+    int32_t tree_level;      // levels - k: tree level whose nodes are the target groups
+    int64_t ntg;             // target groups = real nodes on tree_level
+    int64_t tnode0;          // memory position of the first node of tree_level
+    int64_t qg_first;        // first query group (absolute leaf position >> k)
+    int64_t nqg;             // query groups covering the shard
+    int64_t u_off;           // offset (in boxes) of this level inside the query-pyramid array
+};
+
+struct PairList {
+    uint2* data;
+    unsigned long long* count;     // device counter (keeps counting past `cap`: tells the host the need)
+    unsigned long long cap;
+};
+
+IBVH_D void atomic_inc(int32_t* p) { atomicAdd(p, 1); }
+IBVH_D void atomic_inc(int64_t* p) { atomicAdd(reinterpret_cast<unsigned long long*>(p), 1ull); }
+
+template <class T> IBVH_D BBox<T> empty_box() {
+    BBox<T> b;
+    const T inf = T(1) / T(0);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { b.lo[k] = inf; b.up[k] = -inf; }
+    return b;
+}
+
+// ---- 1. query pyramid ------------------------------------------------------------------------------------
+template <class LQ, class T>
+__global__ void __launch_bounds__(256) pyr_leafgroups_kernel(const LQ* __restrict__ qleaves, int64_t q_begin, int64_t q_end,
+                                                            PyrLevel lv, BBox<T>* __restrict__ U) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= lv.nqg) return;
+    const int64_t q0 = (lv.qg_first + t) << kPyrLeafLog;
+    BBox<T> u = empty_box<T>();
+#pragma unroll
+    for (int m = 0; m < (1 << kPyrLeafLog); ++m) {
+        int64_t q = q0 + m;
+        if (q >= q_begin && q < q_end) {
+            LQ leaf = load_struct(qleaves + q);
+            u = merge(u, NodeOps<BBox<T>>::convert(leaf.volume));
+        }
+    }
+    U[lv.u_off + t] = u;
+}
+template <class T>
+__global__ void __launch_bounds__(256) pyr_up_kernel(PyrLevel fine, PyrLevel coarse, BBox<T>* __restrict__ U) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= coarse.nqg) return;
+    const int64_t c0 = (coarse.qg_first + t) << kPyrFan;
+    BBox<T> u = empty_box<T>();
+#pragma unroll
+    for (int i = 0; i < (1 << kPyrFan); ++i) {
+        int64_t c = c0 + i - fine.qg_first;
+        if (c >= 0 && c < fine.nqg) u = merge(u, load_struct(U + fine.u_off + c));
+    }
+    U[coarse.u_off + t] = u;
+}
+
+// warp-aggregated direct append (top kernel)
+IBVH_D void pyr_append_direct(const PairList& out, bool pred, uint2 e) {
+    unsigned m = __ballot_sync(0xffffffffu, pred);
+    if (!m) return;
+    const int lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(out.count, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (pred) {
+        unsigned long long slot = base + __popc(m & ((1u << lane) - 1u));
+        if (slot < out.cap) out.data[slot] = e;
+    }
+}
+
+// ---- 2. top: all pairs ---------------------------------------------------------------------------------------
+template <int KIND, class T>
+__global__ void __launch_bounds__(256) pyr_top_kernel(PyrLevel lv, const BBox<T>* __restrict__ U, const BBox<T>* __restrict__ nodes, PairList out) {
+    const int64_t total = lv.nqg * lv.ntg;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t0 = (int64_t)blockIdx.x * blockDim.x; t0 < total; t0 += stride) {       // warp-uniform trip count
+        const int64_t t = t0 + threadIdx.x;
+        bool pred = false;
+        uint2 e = make_uint2(0u, 0u);
+        if (t < total) {
+            const int64_t a = t / lv.ntg, b = t % lv.ntg;
+            const int64_t A = lv.qg_first + a;
+            bool ok = true;
+            if constexpr (KIND == kSingle) ok = b >= A;           // the target group must reach right of the query group
+            if (ok) {
+                BBox<T> u = load_struct(U + lv.u_off + a);
+                BBox<T> nb = load_struct(nodes + lv.tnode0 + b);
+                pred = iscontact(u, nb);
+                e = make_uint2((uint32_t)A, (uint32_t)b);
+            }
+        }
+        pyr_append_direct(out, pred, e);
+    }
+}
+
+// Shared-memory hit buffer of one warp: entries are pushed by the lanes that have one, full 32-entry chunks
+// are flushed with one atomic + one coalesced store.
+template <int CAP> struct WarpBuf {
+    uint2* buf;       // shared memory, CAP + 32 entries
+    uint32_t n;
+};
+
+// ---- 3. refine: (A, B) at group size 2^k -> child pairs at 2^(k-3) ------------------------------------------------
+template <int KIND, class T>
+__global__ void __launch_bounds__(kPyrWarps * 32) pyr_refine_kernel(PyrLevel coarse, PyrLevel fine, const BBox<T>* __restrict__ U,
+                                                                   const BBox<T>* __restrict__ nodes, PairList in, PairList out) {
+    using N = BBox<T>;
+    constexpr int F = 1 << kPyrFan;          // 8
+    constexpr int SLOTS = 32 / F;            // 4 pairs per warp step
+    struct alignas(8) SBox { N b; };
+    __shared__ SBox s_box[kPyrWarps][SLOTS][F + 1];
+    // hit buffer: up to 32*F new entries per step on top of < kPyrFlush pending ones
+    __shared__ uint2 s_buf[kPyrWarps][32 * F + kPyrFlush];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int slot = lane / F, i = lane % F;
+    unsigned long long count64 = *in.count;
+    if (count64 > in.cap) count64 = in.cap;
+    const uint32_t count = (uint32_t)count64;                              // list sizes are < 2^32 (checked by the host)
+    const uint32_t step = (uint32_t)gridDim.x * kPyrWarps * SLOTS;
+    const uint32_t f_first = (uint32_t)fine.qg_first, f_nqg = (uint32_t)fine.nqg, f_ntg = (uint32_t)fine.ntg;
+    const N* __restrict__ Uf = U + fine.u_off;
+    const N* __restrict__ Nf = nodes + fine.tnode0;
+    uint32_t nbuf = 0;
+    // flush the n newest buffered entries [nbuf - n, nbuf) with ONE atomic (all warps share one list counter, and
+    // same-address atomics are what limits this kernel otherwise) and coalesced 256-byte stores
+    auto flush = [&](uint32_t n) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(out.count, (unsigned long long)n);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const uint32_t b0 = nbuf - n;
+        for (uint32_t k = lane; k < n; k += 32) if (base + k < out.cap) out.data[base + k] = s_buf[w][b0 + k];
+        nbuf = b0;
+    };
+    // Software pipeline: while step t is computed, the boxes of step t+1 and the list entry of step t+2 are in flight
+    // (the kernel is bound by the latency of these dependent loads, not by issue slots or bandwidth).
+    struct Stage { uint32_t Ac, Bc0; bool a_ok, t_ok; N u, tb; };
+    auto fetch = [&](uint2 pr, bool have) -> Stage {
+        Stage sg;
+        sg.Ac = (pr.x << kPyrFan) + (uint32_t)i;                           // my child of A (absolute group index, fine level)
+        sg.Bc0 = pr.y << kPyrFan;                                          // first child of B
+        const uint32_t ua = sg.Ac - f_first;                               // wraps to a huge value if Ac < f_first
+        sg.a_ok = have && ua < f_nqg;
+        sg.t_ok = have && sg.Bc0 + i < f_ntg;
+        sg.u = empty_box<T>();
+        sg.tb = empty_box<T>();
+        if (sg.a_ok) sg.u = load_struct(Uf + ua);
+        if (sg.t_ok) sg.tb = load_struct(Nf + sg.Bc0 + i);
+        return sg;
+    };
+    uint32_t p = ((uint32_t)blockIdx.x * kPyrWarps + w) * SLOTS + slot;
+    uint2 e1 = make_uint2(0u, 0u), e2 = make_uint2(0u, 0u);
+    if (p < count) e1 = in.data[p];
+    if (p + step < count) e2 = in.data[p + step];
+    Stage cur = fetch(e1, p < count);
+    for (uint32_t p0 = p - slot; p0 < count; p0 += step, p += step) {
+        const Stage nxt = fetch(e2, p + step < count);                     // boxes of the next step
+        e2 = make_uint2(0u, 0u);
+        if (p + 2 * step < count && p + 2 * step > p) e2 = in.data[p + 2 * step];   // entry of the step after
+        const uint32_t Ac = cur.Ac, Bc0 = cur.Bc0;
+        const bool a_ok = cur.a_ok;
+        const N u = cur.u;
+        if (cur.t_ok) s_box[w][slot][i].b = cur.tb;
+        __syncwarp();
+        uint32_t hits = 0;
+        if (a_ok) {
+            const uint32_t nval = f_ntg - Bc0;
+            uint32_t allowed = nval >= (uint32_t)F ? ((1u << F) - 1u) : ((1u << nval) - 1u);
+            if constexpr (KIND == kSingle) {
+                if (Ac > Bc0) {                                              // child j admissible iff Bc0 + j >= Ac
+                    const uint32_t lo = Ac - Bc0;
+                    allowed &= lo >= (uint32_t)F ? 0u : ~((1u << lo) - 1u);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < F; ++j) hits |= (iscontact(u, s_box[w][slot][j].b) ? 1u : 0u) << j;
+            hits &= allowed;
+        }
+        cur = nxt;
+        // append: exclusive prefix of the per-lane hit counts, then every lane writes its own hits
+        const int nh = __popc(hits);
+        int incl = nh;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { int o = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += o; }
+        const int tot = __shfl_sync(0xffffffffu, incl, 31);
+        uint32_t wpos = nbuf + (uint32_t)(incl - nh);
+        while (hits) {
+            const int j = __ffs(hits) - 1;
+            hits &= hits - 1;
+            s_buf[w][wpos++] = make_uint2(Ac, Bc0 + (uint32_t)j);
+        }
+        nbuf += (uint32_t)tot;
+        __syncwarp();
+        if (nbuf >= (uint32_t)kPyrFlush) flush(nbuf & ~31u);
+        __syncwarp();
+    }
+    if (nbuf) flush(nbuf);
+}
+
+// ---- 4. leaf tiles ------------------------------------------------------------------------------------------------
+// MODE kAtomic: append contacts (unordered). kCount: only add the number of contacts to *total.
+// PMODE (ordered protocol): 0 = none; 1 = count per query (atomicAdd counts[qi]); 2 = write (qpos, tpos) into the
+// query's segment via a per-query cursor (fixed up into reference order by pyr_fixup_kernel).
+template <int KIND, int MODE, int PMODE, class LQ, class LT, class I>
+__global__ void __launch_bounds__(kPyrWarps * 32) pyr_leaf_tile_kernel(const LQ* __restrict__ qleaves, int64_t q_begin, int64_t q_end,
+                                                                      DBvh<LT, BBox<typename LT::value_type>> bvh, PairList in, int flip,
+                                                                      int64_t capacity, unsigned long long* total,
+                                                                      I* counts, unsigned int* cursors, IndexPair<I>* contacts) {
+    using T = typename LT::value_type;
+    using N = BBox<T>;
+    using VT = typename LT::vol_t;
+    using VQ = typename LQ::vol_t;
+    constexpr int G = 1 << kPyrLeafLog;      // 4
+    constexpr int SLOTS = 32 / G;            // 8 pairs per warp step
+    constexpr bool kNeedParent = !std::is_same<VT, N>::value || !std::is_same<VQ, N>::value;   // box leaves: implied by the leaf test
+    struct alignas(16) TVol { VT v; };
+    __shared__ TVol s_vol[kPyrWarps][SLOTS][G];
+    __shared__ uint2 s_buf[kPyrWarps][32 * G + kPyrFlush];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int slot = lane / G, m = lane % G;
+    const uint32_t n_target = (uint32_t)bvh.ti.n;
+    const N* __restrict__ parents = bvh.nodes + bvh.ti.level_start[bvh.ti.levels - 1];
+    const uint32_t qb32 = (uint32_t)q_begin, qe32 = (uint32_t)q_end;
+    unsigned long long count64 = *in.count;
+    if (count64 > in.cap) count64 = in.cap;
+    const uint32_t count = (uint32_t)count64;
+    const uint32_t step = (uint32_t)gridDim.x * kPyrWarps * SLOTS;
+    uint32_t nbuf = 0;
+    unsigned long long ncount = 0;
+
+    // Dense rare path: the n newest buffered candidates (qpos, tpos) passed the leaf test. In rounds of 32, each lane
+    // re-loads its query, applies the leaf-parent test of (*) and keeps the survivors in place; then ONE atomic
+    // reserves the output range for all survivors (same-address atomics are the limiter otherwise).
+    auto flush = [&](uint32_t n) {
+        const uint32_t b0 = nbuf - n;
+        uint32_t kept = 0;                                                   // survivors compacted to s_buf[b0 .. b0+kept)
+        for (uint32_t r = 0; r < n; r += 32) {
+            const bool mine = r + lane < n;
+            uint2 e = make_uint2(0u, 0u);
+            if (mine) e = s_buf[w][b0 + r + lane];
+            bool ok = mine;
+            if constexpr (kNeedParent) {
+                if (mine) {
+                    VQ qv;
+                    const uint2* sp = reinterpret_cast<const uint2*>(qleaves + e.x);
+                    uint2* dp = reinterpret_cast<uint2*>(&qv);
+#pragma unroll
+                    for (int k = 0; k < (int)(sizeof(VQ) / 8); ++k) dp[k] = __ldg(sp + k);
+                    ok = iscontact(NodeOps<N>::convert(qv), load_struct(parents + (e.y >> 1)));
+                }
+            }
+            if constexpr (PMODE == 1) {
+                if (ok) atomic_inc(&counts[e.x - qb32]);
+            } else if constexpr (PMODE == 2) {
+                if (ok) {
+                    const uint32_t qi = e.x - qb32;
+                    const int64_t seg = qi == 0 ? 0 : (int64_t)counts[qi - 1];
+                    const unsigned int rr = atomicAdd(&cursors[qi], 1u);
+                    // positions for now; pyr_fixup_kernel sorts the segment and converts to indices
+                    contacts[seg + rr] = IndexPair<I>{(I)e.x, (I)e.y};
+                }
+            } else {
+                const unsigned om = __ballot_sync(0xffffffffu, ok);
+                __syncwarp();
+                if (ok) s_buf[w][b0 + kept + __popc(om & ((1u << lane) - 1u))] = e;    // kept <= r: never overtakes the reads
+                kept += __popc(om);
+                __syncwarp();
+            }
+        }
+        nbuf = b0;
+        if constexpr (PMODE == 0) {
+            if constexpr (MODE == kCount) {
+                ncount += kept;
+            } else if (kept) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(total, (unsigned long long)kept);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                for (uint32_t k = lane; k < kept; k += 32) {
+                    const uint2 e = s_buf[w][b0 + k];
+                    const I qidx = (I)qleaves[e.x].index;
+                    const I li = (I)bvh.leaves[e.y].index;
+                    I ea, eb;
+                    if constexpr (KIND == kSingle) { if (qidx > li) { ea = li; eb = qidx; } else { ea = qidx; eb = li; } }
+                    else { if (flip) { ea = li; eb = qidx; } else { ea = qidx; eb = li; } }
+                    const unsigned long long wp = base + k;
+                    if ((int64_t)wp < capacity) contacts[wp] = IndexPair<I>{ea, eb};
+                }
+            }
+        }
+    };
+
+    // Software pipeline (see pyr_refine_kernel): volumes of step t+1 and the list entry of step t+2 in flight
+    struct Stage { uint32_t qpos, j0; bool q_ok, t_ok; VQ qv; VT tv; };
+    auto fetch = [&](uint2 pr, bool have) -> Stage {
+        Stage sg;
+        sg.qpos = (pr.x << kPyrLeafLog) + (uint32_t)m;
+        sg.j0 = pr.y << kPyrLeafLog;
+        sg.q_ok = have && sg.qpos >= qb32 && sg.qpos < qe32;
+        sg.t_ok = have && sg.j0 + m < n_target;
+        sg.qv = VQ{};
+        sg.tv = VT{};
+        if (sg.q_ok) {
+            const uint2* sp = reinterpret_cast<const uint2*>(qleaves + sg.qpos);
+            uint2* dp = reinterpret_cast<uint2*>(&sg.qv);
+#pragma unroll
+            for (int k = 0; k < (int)(sizeof(VQ) / 8); ++k) dp[k] = __ldg(sp + k);
+        }
+        if (sg.t_ok) {
+            const uint2* sp = reinterpret_cast<const uint2*>(bvh.leaves + sg.j0 + m);
+            uint2* dp = reinterpret_cast<uint2*>(&sg.tv);
+#pragma unroll
+            for (int k = 0; k < (int)(sizeof(VT) / 8); ++k) dp[k] = __ldg(sp + k);
+        }
+        return sg;
+    };
+    uint32_t p = ((uint32_t)blockIdx.x * kPyrWarps + w) * SLOTS + slot;
+    uint2 e1 = make_uint2(0u, 0u), e2 = make_uint2(0u, 0u);
+    if (p < count) e1 = in.data[p];
+    if (p + step < count) e2 = in.data[p + step];
+    Stage cur = fetch(e1, p < count);
+    for (uint32_t p0 = p - slot; p0 < count; p0 += step, p += step) {
+        const Stage nxt = fetch(e2, p + step < count);
+        e2 = make_uint2(0u, 0u);
+        if (p + 2 * step < count && p + 2 * step > p) e2 = in.data[p + 2 * step];
+        const uint32_t qpos = cur.qpos, j0 = cur.j0;
+        const bool q_ok = cur.q_ok;
+        const VQ qv = cur.qv;
+        if (cur.t_ok) s_vol[w][slot][m].v = cur.tv;
+        __syncwarp();
+        uint32_t hits = 0;
+        if (q_ok) {
+            const uint32_t nval = n_target - j0;
+            uint32_t allowed = nval >= (uint32_t)G ? ((1u << G) - 1u) : ((1u << nval) - 1u);
+            if constexpr (KIND == kSingle) {
+                if (qpos >= j0) {                                              // only leaves strictly right of the query
+                    const uint32_t lo = qpos - j0 + 1u;
+                    allowed &= lo >= (uint32_t)G ? 0u : ~((1u << lo) - 1u);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < G; ++j) hits |= (leaf_contact(qv, s_vol[w][slot][j].v) ? 1u : 0u) << j;
+            hits &= allowed;
+        }
+        cur = nxt;
+        unsigned any = __ballot_sync(0xffffffffu, hits != 0);
+        while (any) {
+            if (hits) {
+                const int j = __ffs(hits) - 1;
+                hits &= hits - 1;
+                s_buf[w][nbuf + __popc(any & ((1u << lane) - 1u))] = make_uint2(qpos, j0 + (uint32_t)j);
+            }
+            nbuf += __popc(any);
+            any = __ballot_sync(0xffffffffu, hits != 0);
+        }
+        __syncwarp();
+        if (nbuf >= (uint32_t)kPyrFlush) flush(nbuf & ~31u);
+        __syncwarp();
+    }
+    if (nbuf) flush(nbuf);
+    if constexpr (MODE == kCount && PMODE == 0) {
+        if (lane == 0 && ncount) atomicAdd(total, ncount);
+    }
+}
+
+// Ordered protocol, last step: each query's segment holds (qpos, tpos) in arrival order; sort it by tpos
+// (ascending target position == the reference's DFS order) and convert to the reported index pair.
+template <int KIND, class LQ, class LT, class I>
+__global__ void __launch_bounds__(256) pyr_fixup_kernel(const LQ* __restrict__ qleaves, const LT* __restrict__ tleaves, int64_t q_begin,
+                                                       int64_t q_count, int flip, const I* __restrict__ counts, IndexPair<I>* contacts) {
+    const int64_t qi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= q_count) return;
+    const int64_t b = qi == 0 ? 0 : (int64_t)counts[qi - 1];
+    const int64_t e = (int64_t)counts[qi];
+    if (e <= b) return;
+    // insertion sort by target position (segments are a handful of entries)
+    for (int64_t x = b + 1; x < e; ++x) {
+        IndexPair<I> v = contacts[x];
+        int64_t y = x - 1;
+        while (y >= b && contacts[y].b > v.b) { contacts[y + 1] = contacts[y]; --y; }
+        contacts[y + 1] = v;
+    }
+    const I qidx = (I)qleaves[q_begin + qi].index;
+    for (int64_t x = b; x < e; ++x) {
+        const I li = (I)tleaves[(int64_t)contacts[x].b].index;
+        I ea, eb;
+        if constexpr (KIND == kSingle) { if (qidx > li) { ea = li; eb = qidx; } else { ea = qidx; eb = li; } }
+        else { if (flip) { ea = li; eb = qidx; } else { ea = qidx; eb = li; } }
+        contacts[x] = IndexPair<I>{ea, eb};
+    }
+}
+
+}  // namespace ibvh

@@ -92,6 +92,8 @@ typedef struct ibvh_bvh {
                                           /* query, local stack, two passes (for comparison)   */
 #define IBVH_TRAVERSE_PACKET 16u      /* force the warp-packet schedule (default for BSphere nodes); the */
                                       /* default for BBox nodes is the "group walk + dense tiles" one    */
+#define IBVH_TRAVERSE_WALK 32u        /* force the "group walk + dense tiles" schedule instead of the     */
+                                      /* default pyramid refinement (both BBox nodes only)               */
 #define IBVH_TRAVERSE_STATS 8u        /* fill the device counters read by ibvh_last_traversal_stats */
 #define IBVH_TRAVERSE_COUNTS_VALID 4u /* ORDERED only: d_counts already holds the inclusive scan */
                                       /* left by a previous count-only call on the same queries: */

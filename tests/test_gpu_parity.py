@@ -326,6 +326,10 @@ def test_single_all_start_levels(ib, O, dev, node):
             assert rs.contacts.numpy().tobytes() == want.tobytes(), (n, sl, "reference-shaped")
             pk = ib.traverse(bvh, start_level=sl, packet=True)
             assert pk.contacts.numpy().tobytes() == want.tobytes(), (n, sl, "packet")
+            wk = ib.traverse(bvh, start_level=sl, walk=True)
+            assert wk.contacts.numpy().tobytes() == want.tobytes(), (n, sl, "group walk")
+            wu = ib.traverse(bvh, start_level=sl, walk=True, ordered=False)
+            assert (sorted_pairs(wu.contacts.numpy()) == brute).all(), (n, sl, "group walk unordered")
             pu = ib.traverse(bvh, start_level=sl, packet=True, ordered=False)
             assert (sorted_pairs(pu.contacts.numpy()) == brute).all(), (n, sl, "packet unordered")
 
@@ -439,6 +443,8 @@ def test_pair_all_start_levels(ib, O, dev):
                         assert (sorted_pairs(un.contacts.numpy()) == brute).all()
                         pk = ib.traverse(b1, b2, start_level1=sl1, start_level2=sl2, packet=True)
                         assert pk.contacts.numpy().tobytes() == want.tobytes(), (n1, n2, sl1, sl2, "packet")
+                        wk = ib.traverse(b1, b2, start_level1=sl1, start_level2=sl2, walk=True)
+                        assert wk.contacts.numpy().tobytes() == want.tobytes(), (n1, n2, sl1, sl2, "group walk")
 
 
 def test_pair_self_equivalence_and_partial_build(ib, O, dev):
@@ -528,7 +534,7 @@ def test_config1_100k_against_oracle(ib, O, dev):
     assert 3.0 * n < len(want) < 5.0 * n                    # C ~ 4 N by construction
     un = ib.traverse(bvh, ordered=False)
     assert (sorted_pairs(un.contacts.numpy()) == sorted_pairs(want)).all()
-    for kw in (dict(packet=True), dict(reference_shaped=True)):
+    for kw in (dict(packet=True), dict(reference_shaped=True), dict(walk=True)):
         assert ib.traverse(bvh, **kw).contacts.numpy().tobytes() == want.tobytes(), kw
         assert (sorted_pairs(ib.traverse(bvh, ordered=False, **kw).contacts.numpy()) == sorted_pairs(want)).all(), kw
 

@@ -74,8 +74,10 @@ def main():
         print(f"\n=== n={n} contacts={C_} ({C_ / n:.2f}/leaf) levels={bvh.tree.levels}", flush=True)
         cases = [
             ("build", lambda: ib.BVH(src, ib.BBox(), cache=bvh)),
-            ("traverse ordered(tiled)", lambda: ib.traverse(bvh, cache=big)),
-            ("traverse unordered(tiled)", lambda: ib.traverse(bvh, cache=big, ordered=False)),
+            ("traverse ordered(pyramid)", lambda: ib.traverse(bvh, cache=big)),
+            ("traverse unordered(pyramid)", lambda: ib.traverse(bvh, cache=big, ordered=False)),
+            ("traverse ordered(walk)", lambda: ib.traverse(bvh, cache=big, walk=True)),
+            ("traverse unordered(walk)", lambda: ib.traverse(bvh, cache=big, ordered=False, walk=True)),
             ("traverse ordered(packet)", lambda: ib.traverse(bvh, cache=big, packet=True)),
             ("traverse unordered(packet)", lambda: ib.traverse(bvh, cache=big, ordered=False, packet=True)),
         ]

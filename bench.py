@@ -191,7 +191,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--unordered", action="store_true", help="one-pass unordered contact emission instead of the reference order")
+    ap.add_argument("--ordered", action="store_true",
+                    help="emit contacts in the reference's order (count -> scan -> write) instead of the one-pass unordered emission "
+                         "(same set; the parity bar is the SORTED contact list)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -216,7 +218,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     warm = max(3, args.warmup)
     n = N_LEAVES
-    ordered = not args.unordered
+    ordered = args.ordered
 
     # ---- inputs resident in HBM (generated on device, identical on every rank) -----------------
     vols = synth.random_spheres_torch(n, dev, seed=SEED)
@@ -299,11 +301,17 @@ def main():
     dom = max(per_kernel, key=per_kernel.get)
     nq = qe - qb
     my_contacts = state["tr"].num_contacts
-    # algorithmic bytes of the traversal: tree read once per launch + contact output.
-    # ordered = two launches (count, write): 2 * (Lb + Nb) * N + 2 * Ib * C; unordered = one launch.
+    # Algorithmic bytes of the dominant kernel per step. Traversal kernels (T1): the tree is read
+    # once per traversal pass + the contact output: passes * (Lb + Nb) * N + 2 * Ib * C (ordered = 2 passes,
+    # unordered = 1). Build kernels: S2 sort 68 N, S3+S4 gather+merge 76 N, S1 bounds+encode 36 N (wrap path).
     Lb, Nb, Ib = 24, 24, 4
     n_trav = launches.get(dom, 1)
-    alg_bytes = n_trav * (Lb + Nb) * n * (nq / n if world > 1 else 1.0) + 2 * Ib * my_contacts
+    trav_kernels = ("pyr_leaf_tile_kernel", "pyr_refine_kernel", "tile_flat_kernel", "tile_kernel", "group_walk_kernel", "lvt_packet_kernel", "lvt_thread_kernel")
+    if dom in trav_kernels:
+        passes = 2 if ordered else 1
+        alg_bytes = passes * (Lb + Nb) * n * (nq / n if world > 1 else 1.0) + 2 * Ib * my_contacts
+    else:
+        alg_bytes = {"onesweep_kernel": 68, "gather_merge_kernel": 76}.get(dom, 36) * n
     dom_ms = per_kernel[dom]
     peak, peak_src = peaks()
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
@@ -319,7 +327,8 @@ def main():
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_step": alg_bytes,
                 "kernel_ms_per_step": dom_ms, "share_of_step": dom_ms / ms_step,
                 "per_kernel_ms": {k: round(v, 4) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1])},
-                "intersection_tests_per_s": None}
+                "traversal_ms_per_step": round(sum(v for k, v in per_kernel.items() if k.startswith(("pyr_", "tile_", "group_walk", "lvt_", "scan_r", "scan_b", "scan_a"))), 4),
+                "build_ms_per_step": round(sum(v for k, v in per_kernel.items() if k in ("init_build_kernel", "bounds_kernel", "encode_kernel", "scan_hist_kernel", "onesweep_kernel", "gather_merge_kernel", "merge_levels_kernel")), 4)}
 
     # ---- e2e: host (pinned) volumes in, contacts back to pinned host memory ------------------------
     host_vols = synth.random_spheres_np(n, seed=SEED) if rank == 0 or world > 1 else None
@@ -386,7 +395,7 @@ def main():
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD % n, "leaves": n, "contacts_per_step": int(ncontacts),
-                       "contact_order": "reference (ascending query, DFS order; count+scan+write)" if ordered else "unordered (one pass, warp-aggregated atomics)",
+                       "contact_order": "reference (ascending query, DFS order; count+scan+write)" if ordered else "unordered (one pass, buffered warp-aggregated atomics; identical as a sorted list)",
                        "parallelism": "single GPU" if world == 1 else f"build on rank 0 + NCCL broadcast, query-range sharded traversal over {world} GPUs, all-gather of contact shards",
                        "l2_policy": "inputs larger than L2 (160 MB volumes + 240 MB leaves + 240 MB nodes per step vs 126 MB L2)"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,

@@ -335,6 +335,25 @@ int launch_traverse(ibvh_handle* h, const LQ* qleaves, const typename LT::value_
         IBVH_LAUNCH_CHECK(h, "lvt_packet_kernel");
     } else {
         const int64_t blocks = (a.q_count + 127) / 128;
+        if constexpr (KIND == kRays) {
+            // rays: stackless two-children schedule (IBVH_RAYS_REFERENCE_SHAPED=1 keeps the reference-shaped proxy)
+            if (!getenv("IBVH_RAYS_REFERENCE_SHAPED")) {
+                if (getenv("IBVH_RAYS_STATIC")) {
+                    { ProfScope _ps(h, st, "rays_kernel");
+                    rays_kernel<MODE, LT, N, I><<<(unsigned)blocks, 128, 0, st>>>(points, dirs, bvh, a, counts, contacts);
+                    }
+                } else {
+                    unsigned long long* ticket = (unsigned long long*)(h->d_small + kSmallTotal + 24);
+                    IBVH_CUDA_TRY(h, cudaMemsetAsync(ticket, 0, 8, st));
+                    const unsigned pblocks = (unsigned)std::min<int64_t>(blocks, (int64_t)h->sm_count * 12);
+                    { ProfScope _ps(h, st, "rays_persistent_kernel");
+                    rays_persistent_kernel<MODE, LT, N, I><<<pblocks, 128, 0, st>>>(points, dirs, bvh, a, counts, contacts, ticket);
+                    }
+                }
+                IBVH_LAUNCH_CHECK(h, "rays_kernel");
+                return IBVH_OK;
+            }
+        }
         { ProfScope _ps(h, st, "lvt_thread_kernel");
         lvt_thread_kernel<KIND, MODE, LQ, LT, N, I><<<(unsigned)blocks, 128, 0, st>>>(qleaves, points, dirs, bvh, a, counts, contacts);
         }

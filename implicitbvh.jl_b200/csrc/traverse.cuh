@@ -205,6 +205,238 @@ __global__ void __launch_bounds__(128) lvt_thread_kernel(const LQ* __restrict__ 
 }
 
 // ===========================================================================================================
+// Ray schedule: one thread per ray, stackless, two children per step
+// ===========================================================================================================
+// Same predicate and same hit order as traverse_ray_lvt! (raytrace/leaf_vs_tree/leaf_vs_tree.jl:170-228): a leaf
+// is reported iff its own test and the slab test of every ancestor from start_level down pass, hits come
+// out left to right. Differences are only in the schedule: (1) the two children of a node are adjacent in
+// memory (48 contiguous bytes) and are tested in the same step, which halves the dependent-load chain;
+// (2) the implicit tree makes the stack redundant: a 32-bit "pending right sibling" mask indexed by level
+// replaces it (the ancestor at level k of node i at level l is i >> (l - k)), so there is no local memory.
+template <int MODE, class LT, class N, class I>
+__global__ void __launch_bounds__(128) rays_kernel(const typename LT::value_type* __restrict__ points,
+                                                  const typename LT::value_type* __restrict__ dirs,
+                                                  DBvh<LT, N> bvh, TraverseArgs a, I* counts, IndexPair<I>* contacts) {
+    using T = typename LT::value_type;
+    using V = typename LT::vol_t;
+    __shared__ uint32_t s_skip[34];
+    __shared__ uint32_t s_nreal[34];
+    for (int i = threadIdx.x; i < 34; i += blockDim.x) { s_skip[i] = (uint32_t)bvh.ti.skips[i]; s_nreal[i] = (uint32_t)bvh.ti.level_nreal[i]; }
+    __syncthreads();
+    const int64_t qi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= a.q_count) return;
+    const int64_t q = a.q_begin + qi;
+    const int levels = bvh.ti.levels;
+    T p[3], d[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { p[k] = points[3 * q + k]; d[k] = dirs[3 * q + k]; }
+    const I ray_id = (I)(a.id_base + q + 1);
+
+    Emitter<I, MODE> em;
+    em.contacts = contacts;
+    em.capacity = a.capacity;
+    em.total = a.total;
+    em.pos = 0;
+    if constexpr (MODE == kWrite) em.pos = (qi == 0) ? 0 : (int64_t)counts[qi - 1];
+
+    const uint32_t leaf0 = 1u << (levels - 1);
+    auto test_leaf = [&](uint32_t inode) {
+        const LT* lp = bvh.leaves + (inode - leaf0);
+        V v;
+        const uint2* sp = reinterpret_cast<const uint2*>(lp);
+        uint2* dp = reinterpret_cast<uint2*>(&v);
+#pragma unroll
+        for (int k = 0; k < (int)(sizeof(V) / 8); ++k) dp[k] = __ldg(sp + k);
+        if (isintersection(v, p, d)) em.emit((I)lp->index, ray_id);
+    };
+
+    const uint32_t inode_start = 1u << (a.start_level - 1);
+    const uint32_t inode_end = inode_start + s_nreal[a.start_level] - 1u;
+    for (uint32_t root = inode_start; root <= inode_end; ++root) {
+        if (a.start_level == levels) { test_leaf(root); continue; }
+        {
+            N rb = load_struct(bvh.nodes + (root - s_skip[a.start_level] - 1u));
+            if (!isintersection(rb, p, d)) continue;
+        }
+        uint32_t inode = root;
+        int level = a.start_level;
+        uint32_t pending = 0;             // bit k: the right child of my ancestor at level k is still to be visited
+        while (true) {
+            const uint32_t c0 = 2u * inode, c1 = c0 + 1u;
+            const int cl = level + 1;
+            const bool c1_real = (c1 - (1u << level)) < s_nreal[cl];
+            bool descended = false;
+            if (cl == levels) {
+                test_leaf(c0);
+                if (c1_real) test_leaf(c1);
+            } else {
+                const N* cp = bvh.nodes + (c0 - s_skip[cl] - 1u);
+                const N b0 = load_struct(cp);
+                const bool h0 = isintersection(b0, p, d);
+                bool h1 = false;
+                if (c1_real) { const N b1 = load_struct(cp + 1); h1 = isintersection(b1, p, d); }
+                if (h0) { if (h1) pending |= 1u << level; inode = c0; level = cl; descended = true; }
+                else if (h1) { inode = c1; level = cl; descended = true; }
+            }
+            if (descended) continue;
+            if (pending == 0) break;
+            const int k = 31 - __clz(pending);            // deepest level with a pending right child
+            pending &= ~(1u << k);
+            inode = 2u * (inode >> (level - k)) + 1u;
+            level = k + 1;
+            // the popped node's box was already tested (h1) when it was marked pending: expand it directly,
+            // unless it is a leaf
+            if (level == levels) {                        // cannot happen (leaves are never marked pending), kept for safety
+                test_leaf(inode);
+                if (pending == 0) break;
+            }
+        }
+    }
+    if constexpr (MODE == kCount) counts[qi] = (I)em.pos;
+}
+
+// Persistent variant of rays_kernel. Random rays are incoherent: with one ray per thread a warp runs until
+// its longest ray is done with a handful of lanes active (measured: 4.2 of 32). Here every warp keeps
+// pulling rays from a global ticket counter and a lane that finishes its ray is refilled, so the lanes
+// stay busy. Which lane handles a ray is irrelevant for the results: counts / offsets are per ray id.
+template <int MODE, class LT, class N, class I>
+__global__ void __launch_bounds__(128) rays_persistent_kernel(const typename LT::value_type* __restrict__ points,
+                                                             const typename LT::value_type* __restrict__ dirs,
+                                                             DBvh<LT, N> bvh, TraverseArgs a, I* counts, IndexPair<I>* contacts,
+                                                             unsigned long long* ticket) {
+    using T = typename LT::value_type;
+    using V = typename LT::vol_t;
+    __shared__ uint32_t s_skip[34];
+    __shared__ uint32_t s_nreal[34];
+    // unordered mode: hits are pushed into a per-warp buffer (shared-memory atomic slot counter) and flushed
+    // 32 at a time at the warp-uniform top of the loop: one global atomic + one coalesced store per 32 hits
+    __shared__ IndexPair<I> s_hit[4][MODE == kAtomic ? 128 : 1];
+    __shared__ unsigned int s_nhit[4];
+    for (int i = threadIdx.x; i < 34; i += blockDim.x) { s_skip[i] = (uint32_t)bvh.ti.skips[i]; s_nreal[i] = (uint32_t)bvh.ti.level_nreal[i]; }
+    if (threadIdx.x < 4) s_nhit[threadIdx.x] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int w = threadIdx.x >> 5;
+    const int levels = bvh.ti.levels;
+    const uint32_t leaf0 = 1u << (levels - 1);
+    const uint32_t inode_start = 1u << (a.start_level - 1);
+    const uint32_t inode_end = inode_start + s_nreal[a.start_level] - 1u;
+
+    int64_t qi = -1;                      // ray handled by this lane (index within the shard), -1 = idle
+    T p[3] = {0, 0, 0}, d[3] = {0, 0, 0};
+    I ray_id = 0;
+    uint32_t root = 0, inode = 0, pending = 0;
+    int level = 0;
+    bool need_root = true;
+    Emitter<I, MODE> em;
+    em.contacts = contacts;
+    em.capacity = a.capacity;
+    em.total = a.total;
+    em.pos = 0;
+    bool exhausted = false;
+
+    auto test_leaf = [&](uint32_t node) {
+        const LT* lp = bvh.leaves + (node - leaf0);
+        V v;
+        const uint2* sp = reinterpret_cast<const uint2*>(lp);
+        uint2* dp = reinterpret_cast<uint2*>(&v);
+#pragma unroll
+        for (int k = 0; k < (int)(sizeof(V) / 8); ++k) dp[k] = __ldg(sp + k);
+        if (isintersection(v, p, d)) {
+            if constexpr (MODE == kAtomic) s_hit[w][atomicAdd(&s_nhit[w], 1u)] = IndexPair<I>{(I)lp->index, ray_id};
+            else em.emit((I)lp->index, ray_id);
+        }
+    };
+    auto flush_hits = [&](bool all) {
+        if constexpr (MODE == kAtomic) {
+            __syncwarp();
+            unsigned int n = s_nhit[w];
+            while (n >= 32u || (all && n > 0u)) {
+                const unsigned int take = n >= 32u ? 32u : n;
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(a.total, (unsigned long long)take);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if ((unsigned)lane < take && (int64_t)(base + lane) < a.capacity) contacts[base + lane] = s_hit[w][n - take + lane];
+                n -= take;
+            }
+            __syncwarp();
+            if (lane == 0) s_nhit[w] = n;
+            __syncwarp();
+        }
+    };
+
+    while (true) {
+        flush_hits(false);
+        // ---- refill idle lanes (warp-uniform decision) ------------------------------------------------
+        const unsigned idle = __ballot_sync(0xffffffffu, qi < 0);
+        if (idle && !exhausted && (__popc(idle) >= 8 || idle == 0xffffffffu)) {
+            const int nidle = __popc(idle);
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(ticket, (unsigned long long)nidle);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if ((int64_t)base + nidle >= a.q_count) exhausted = true;
+            if (qi < 0) {
+                const int64_t r = (int64_t)base + __popc(idle & ((1u << lane) - 1u));
+                if (r < a.q_count) {
+                    qi = r;
+                    const int64_t q = a.q_begin + r;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) { p[k] = points[3 * q + k]; d[k] = dirs[3 * q + k]; }
+                    ray_id = (I)(a.id_base + q + 1);
+                    root = inode_start;
+                    need_root = true;
+                    em.pos = 0;
+                    if constexpr (MODE == kWrite) em.pos = (r == 0) ? 0 : (int64_t)counts[r - 1];
+                }
+            }
+        }
+        if (__ballot_sync(0xffffffffu, qi >= 0) == 0) break;
+        if (qi < 0) continue;                  // idle lanes rejoin at the top (all warp-level calls sit there)
+        // ---- one step of this lane's ray ------------------------------------------------------------------
+        if (need_root) {
+            if (root > inode_end) {                                   // ray finished
+                if constexpr (MODE == kCount) counts[qi] = (I)em.pos;
+                qi = -1;
+            } else if (a.start_level == levels) {
+                test_leaf(root);
+                root += 1;
+            } else {
+                N rb = load_struct(bvh.nodes + (root - s_skip[a.start_level] - 1u));
+                if (isintersection(rb, p, d)) { inode = root; level = a.start_level; pending = 0; need_root = false; }
+                else root += 1;
+            }
+            continue;
+        }
+        const uint32_t c0 = 2u * inode, c1 = c0 + 1u;
+        const int cl = level + 1;
+        const bool c1_real = (c1 - (1u << level)) < s_nreal[cl];
+        bool descended = false;
+        if (cl == levels) {
+            test_leaf(c0);
+            if (c1_real) test_leaf(c1);
+        } else {
+            const N* cp = bvh.nodes + (c0 - s_skip[cl] - 1u);
+            const N b0 = load_struct(cp);
+            const bool h0 = isintersection(b0, p, d);
+            bool h1 = false;
+            if (c1_real) { const N b1 = load_struct(cp + 1); h1 = isintersection(b1, p, d); }
+            if (h0) { if (h1) pending |= 1u << level; inode = c0; level = cl; descended = true; }
+            else if (h1) { inode = c1; level = cl; descended = true; }
+        }
+        if (!descended) {
+            if (pending == 0) { root += 1; need_root = true; }
+            else {
+                const int k = 31 - __clz(pending);
+                pending &= ~(1u << k);
+                inode = 2u * (inode >> (level - k)) + 1u;
+                level = k + 1;
+            }
+        }
+    }
+    flush_hits(true);
+}
+
+// ===========================================================================================================
 // Packet schedule: one warp per 32 consecutive query leaves (single / pair)
 // ===========================================================================================================
 constexpr int kPacketWarps = 8;

@@ -63,7 +63,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -195,6 +195,7 @@ def main():
                     help="emit contacts in the reference's order (count -> scan -> write) instead of the one-pass unordered emission "
                          "(same set; the parity bar is the SORTED contact list)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-rays", action="store_true", help="skip the secondary rays/s measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -215,6 +216,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the single JSON line (a box-level NCCL_DEBUG=VERSION prints a banner)
         dist.init_process_group("nccl", device_id=dev)
     warm = max(3, args.warmup)
     n = N_LEAVES
@@ -278,7 +280,6 @@ def main():
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
-    clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
     value = n / (ms_step * 1e-3)
 
@@ -378,6 +379,49 @@ def main():
     e2e = {"value": n / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(n * 16), "d2h_bytes_per_step": int(nc * 8),
            "ms_per_step": e2e_ms}
 
+    # ---- secondary metric of BASELINE.json: rays/s @ 1 M leaves (configs[3]) ------------------------------
+    # 1000 x 1000 mesh-like shell of spheres, R random rays (origins U[-1.5,1.5)^3, directions uniform on S^2),
+    # rays sharded by contiguous ranges over the ranks; every rank builds the (1 M-leaf, 0.2 ms) tree itself.
+    rays = None
+    if not args.no_rays:
+        R = int(os.environ.get("IBVH_BENCH_RAYS", 100_000_000))
+        rb = ibdist.shard_bounds(R, world)[rank]
+        nr = rb[1] - rb[0]
+        shell = synth.shell_spheres_np(1000, 1000)
+        rbvh = ib.BVH(shell, ib.BBox(), device=dev)
+        rp, rd = synth.random_rays_torch(nr, dev, seed=7, start=rb[0])
+        rt = ib.traverse_rays(rbvh, rp, rd, ordered=ordered, id_base=rb[0])
+        rcache = ib.BVHTraversal(1, 0, 0, 0, ib.DeviceArray.empty(int(rt.num_contacts * 1.02) + 1024, ib.pair_dtype(), dev), rt.cache2)
+
+        def step_rays():
+            t = ib.traverse_rays(rbvh, rp, rd, cache=rcache, ordered=ordered, id_base=rb[0])
+            if world > 1:
+                _, cs = ibdist.gather_shards(t.cache1.tensor, t.num_contacts, 8)
+                return int(sum(cs))
+            return t.num_contacts
+
+        for _ in range(2):
+            hits = step_rays()
+        sync_all()
+        ray_steps = 3
+        e0.record()
+        for _ in range(ray_steps):
+            hits = step_rays()
+        e1.record()
+        sync_all()
+        rms = e0.elapsed_time(e1) / ray_steps
+        if world > 1:
+            t = torch.tensor([rms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            rms = float(t.item())
+        rays = {"metric": "rays/s @1M leaves", "value": R / (rms * 1e-3), "unit": "rays/s", "ms_per_step": rms, "rays": R, "hits_per_step": int(hits),
+                "workload": "configs[3]: 1000x1000 shell of BSphere{Float32} (1 M leaves, BBox{Float32} nodes), %d random rays, traverse_rays (LVT), "
+                            "rays sharded by contiguous ranges over %d GPU(s), hit shards all-gathered" % (R, world),
+                "scaling": "strong"}
+        del rp, rd, rcache, rt
+
+    clocks = sampler.stop() if rank == 0 else None      # sampled over the timed, e2e and ray regions
+
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload ----------------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -399,6 +443,7 @@ def main():
                        "parallelism": "single GPU" if world == 1 else f"build on rank 0 + NCCL broadcast, query-range sharded traversal over {world} GPUs, all-gather of contact shards",
                        "l2_policy": "inputs larger than L2 (160 MB volumes + 240 MB leaves + 240 MB nodes per step vs 126 MB L2)"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,
+            "secondary": rays,
         }
         print(json.dumps(out), flush=True)
     if world > 1:

@@ -34,6 +34,36 @@ template <class L> struct GatherSrc<L, typename L::vol_t> {
     }
 };
 
+// Stand-alone gather: leaves[i] = source[perm[i]] with morton = keys_sorted[i]. Two leaves per thread, all index
+// loads before the random loads. The merge then runs from the sorted leaves (gather_merge_kernel<GATHER=false>):
+// one extra coalesced read of the leaves, but neither kernel waits on the other's latency inside a CTA.
+template <class L, class SRC>
+__global__ void __launch_bounds__(256) gather_kernel(const SRC* __restrict__ src, const uint32_t* __restrict__ perm,
+                                                    const typename L::mor_t* __restrict__ keys_sorted, L* __restrict__ leaves, int64_t n) {
+    constexpr int PER = 4;
+    const int64_t base = ((int64_t)blockIdx.x * blockDim.x) * PER + threadIdx.x;
+    uint32_t pp[PER];
+    typename L::mor_t kk[PER];
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+        const int64_t i = base + (int64_t)u * blockDim.x;
+        const bool ok = i < n;
+        pp[u] = ok ? perm[i] : 0u;
+        kk[u] = ok ? keys_sorted[i] : typename L::mor_t(0);
+    }
+    Words<L> wv[PER];
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+        const int64_t i = base + (int64_t)u * blockDim.x;
+        if (i < n) wv[u] = GatherSrc<L, SRC>::make(src, pp[u], kk[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+        const int64_t i = base + (int64_t)u * blockDim.x;
+        if (i < n) store_words(leaves + i, wv[u]);
+    }
+}
+
 struct LevelPlan {
     int32_t src_level;       // level whose nodes (or leaves, if == levels) are the tile input
     int32_t stop_level;      // lowest level (numerically) this launch produces: max(built_level, src_level - log2(TILE))

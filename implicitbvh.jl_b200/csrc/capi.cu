@@ -269,8 +269,19 @@ int build_impl(ibvh_handle* h, const void* d_volumes, void* d_leaves, int64_t n,
     // the level above the leaves is always produced (build.jl:369), further levels down to built_level
     int stop_level = (int)(built_level < tree.levels - 1 ? built_level : tree.levels - 1);
     if (stop_level < 1) stop_level = 1;
-    if (wrap) rc = launch_gather_merge<L, V, N, true>(h, (const V*)d_volumes, perm, keys_sorted, (L*)d_leaves, (N*)d_nodes, ti, stop_level, st);
-    else rc = launch_gather_merge<L, L, N, true>(h, (const L*)s.copy, perm, keys_sorted, (L*)d_leaves, (N*)d_nodes, ti, stop_level, st);
+    if (getenv("IBVH_FUSED_GATHER")) {
+        if (wrap) rc = launch_gather_merge<L, V, N, true>(h, (const V*)d_volumes, perm, keys_sorted, (L*)d_leaves, (N*)d_nodes, ti, stop_level, st);
+        else rc = launch_gather_merge<L, L, N, true>(h, (const L*)s.copy, perm, keys_sorted, (L*)d_leaves, (N*)d_nodes, ti, stop_level, st);
+    } else {
+        // gather (random reads, full occupancy) then tile merge from the sorted leaves (coalesced)
+        const unsigned gb = (unsigned)((n + 1023) / 1024);
+        { ProfScope _ps(h, st, "gather_kernel");
+        if (wrap) gather_kernel<L, V><<<gb, 256, 0, st>>>((const V*)d_volumes, perm, keys_sorted, (L*)d_leaves, n);
+        else gather_kernel<L, L><<<gb, 256, 0, st>>>((const L*)s.copy, perm, keys_sorted, (L*)d_leaves, n);
+        }
+        IBVH_LAUNCH_CHECK(h, "gather_kernel");
+        rc = launch_gather_merge<L, L, N, false>(h, (const L*)nullptr, nullptr, nullptr, (L*)d_leaves, (N*)d_nodes, ti, stop_level, st);
+    }
     if (rc != IBVH_OK) return rc;
     if (tree.real_nodes >= 2) rc = merge_upper_levels<N>(h, (N*)d_nodes, ti, stop_level, st);
     return rc;

@@ -362,22 +362,90 @@ def main():
         torch.cuda.current_stream().synchronize()
         return int(sum(counts))
 
-    for _ in range(3):
-        step_e2e()
-    sync_all()
-    t0 = time.perf_counter()
-    e0.record()
-    for _ in range(args.steps):
-        nc = step_e2e()
-    e1.record()
-    sync_all()
-    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / args.steps
+    def run_e2e_pipelined(k_steps):
+        """Single GPU: the same per-step work (H2D of the step's volumes -> BVH -> traverse -> D2H of the step's
+        contact list), software-pipelined over three streams with double buffers so that the copies of
+        neighbouring steps overlap the kernels (PCIe is full duplex). Every step's input still comes from pinned
+        host memory and every step's contacts still land in pinned host memory inside the timed region."""
+        s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        main = torch.cuda.current_stream(dev)
+        d_in = [ib.DeviceArray.empty(n, pinned_in.dtype, dev) for _ in range(2)]
+        caches = [ib.BVHTraversal(1, 0, 0, 0, ib.DeviceArray.empty(cap, ib.pair_dtype(), dev), ib.DeviceArray.empty(n, np.int32, dev)) for _ in range(2)]
+        outs = [pinned_out, torch.empty(cap * 8, dtype=torch.uint8).pin_memory()]
+        in_ready = [torch.cuda.Event() for _ in range(2)]
+        comp_done = [torch.cuda.Event() for _ in range(2)]
+        out_done = [torch.cuda.Event() for _ in range(2)]
+        bvh_prev = e2e_state["bvh"]
+
+        def h2d(k):
+            b = k % 2
+            with torch.cuda.stream(s_in):
+                s_in.wait_event(comp_done[b])                 # step k-2 no longer reads d_in[b]
+                d_in[b].tensor.copy_(pinned_in.tensor, non_blocking=True)
+                in_ready[b].record(s_in)
+
+        for ev in comp_done + out_done:
+            ev.record(main)
+        h2d(0)
+        last = 0
+        for k in range(k_steps):
+            b = k % 2
+            if k + 1 < k_steps:
+                h2d(k + 1)                                     # next step's input travels while this step computes
+            main.wait_event(in_ready[b])
+            main.wait_event(out_done[b])                       # step k-2's contacts have left caches[b]
+            bvh = ib.BVH(d_in[b], ib.BBox(), cache=bvh_prev)
+            tr = ib.traverse(bvh, cache=caches[b], ordered=ordered)
+            caches[b] = tr
+            bvh_prev = bvh
+            comp_done[b].record(main)
+            nb = tr.num_contacts * 8
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(comp_done[b])
+                outs[b][:nb].copy_(tr.cache1.tensor[:nb], non_blocking=True)
+                out_done[b].record(s_out)
+            last = tr.num_contacts
+        s_out.synchronize(); s_in.synchronize(); main.synchronize()
+        return last
+
+    if world == 1:
+        run_e2e_pipelined(3)
+        sync_all()
+        t0 = time.perf_counter()
+        e0.record()
+        nc = run_e2e_pipelined(args.steps)
+        e1.record()
+        sync_all()
+        e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / args.steps
+        # also the strictly sequential figure (no overlap between steps), for reference
+        for _ in range(2):
+            step_e2e()
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(max(3, args.steps // 4)):
+            step_e2e()
+        sync_all()
+        e2e_seq_ms = (time.perf_counter() - t0) * 1e3 / max(3, args.steps // 4)
+    else:
+        for _ in range(3):
+            step_e2e()
+        sync_all()
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(args.steps):
+            nc = step_e2e()
+        e1.record()
+        sync_all()
+        e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / args.steps
+        e2e_seq_ms = e2e_ms
     if world > 1:
         t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
     e2e = {"value": n / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(n * 16), "d2h_bytes_per_step": int(nc * 8),
-           "ms_per_step": e2e_ms}
+           "ms_per_step": e2e_ms, "sequential_ms_per_step": e2e_seq_ms,
+           "note": "public API (BVH + traverse) from pinned host volumes to pinned host contacts; single GPU: copies of neighbouring steps overlap "
+                   "the kernels (3 streams, double buffers); sequential_ms_per_step is the same without any overlap"}
 
     # ---- secondary metric of BASELINE.json: rays/s @ 1 M leaves (configs[3]) ------------------------------
     # 1000 x 1000 mesh-like shell of spheres, R random rays (origins U[-1.5,1.5)^3, directions uniform on S^2),

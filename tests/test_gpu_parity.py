@@ -622,3 +622,103 @@ def test_config2_10M_properties(ib, dev):
     assert bool((again.nodes.tensor == before).all())
     mort2 = again.leaves.tensor.view(torch.int32).reshape(n, 6)[:, 5]
     assert bool((mort2 == L[:, 5]).all())
+
+
+# ---- BASELINE configs[2] and configs[4] at full size: size-independent properties ------------------------
+def _keys(t, n_mult):
+    """Sorted 64-bit keys of an IndexPair tensor view (int32 or int64 pairs)."""
+    return (t[:, 0].to(__import__("torch").int64) * n_mult + t[:, 1].to(__import__("torch").int64)).sort().values
+
+
+def test_config3_pair_5M_partial_build_properties(ib, dev):
+    """configs[2]: BVH-vs-BVH, 5 M + 5 M leaves, target built only up to levels-13 (about 2^10 roots):
+    the partial-build traversal (group walk from every root, as the reference scans them) must give the same
+    contact set as the fully built tree (pyramid schedule); flip symmetry; spot-check with the sphere predicate."""
+    import torch
+    from ibvh_b200 import synth
+    n = 5_000_000
+    s = synth.sphere_radius_scale(n)
+    v1 = synth.random_spheres_torch(n, dev, seed=42, scale=s)
+    v2 = synth.random_spheres_torch(n, dev, seed=43, scale=s)
+    d1 = ib.DeviceArray(v1.view(torch.uint8).reshape(-1), ib.BSphere().dtype)
+    d2 = ib.DeviceArray(v2.view(torch.uint8).reshape(-1), ib.BSphere().dtype)
+    b1 = ib.BVH(d1, ib.BBox())
+    levels = b1.tree.levels
+    b2_full = ib.BVH(d2, ib.BBox())
+    b2_part = ib.BVH(d2, ib.BBox(), built_level=levels - 13)
+    assert b2_part.built_level == levels - 13
+    full = ib.traverse(b1, b2_full, ordered=False)
+    part = ib.traverse(b1, b2_part, ordered=False)                     # start_level2 defaults to built_level
+    assert part.start_level2 == levels - 13
+    assert full.num_contacts == part.num_contacts > n
+    kf = _keys(full.contacts.tensor.view(torch.int32).reshape(-1, 2), n + 1)
+    kp = _keys(part.contacts.tensor.view(torch.int32).reshape(-1, 2), n + 1)
+    assert bool((kf == kp).all())
+    assert bool((kf[1:] != kf[:-1]).all()), "no duplicates"
+    # ordered mode gives the same set again, and its scan ends at the total
+    o = ib.traverse(b1, b2_full)
+    assert o.num_contacts == full.num_contacts
+    assert int(o.cache2.tensor.view(torch.int32)[n - 1]) == o.num_contacts
+    assert bool((_keys(o.contacts.tensor.view(torch.int32).reshape(-1, 2), n + 1) == kf).all())
+    # swapped arguments: same pairs with the roles exchanged (both have n leaves, so no flip; exchange manually)
+    sw = ib.traverse(b2_full, b1, ordered=False)
+    ps = sw.contacts.tensor.view(torch.int32).reshape(-1, 2)
+    ks = (ps[:, 1].to(torch.int64) * (n + 1) + ps[:, 0].to(torch.int64)).sort().values
+    assert bool((ks == kf).all())
+    # every reported pair satisfies the sphere predicate (2000 samples) and so do none of 2000 random pairs' complement
+    pairs = full.contacts.tensor.view(torch.int32).reshape(-1, 2).to(torch.int64)
+    sel = pairs[torch.randint(0, full.num_contacts, (2000,), device=dev)]
+    a, b = v1[sel[:, 0] - 1], v2[sel[:, 1] - 1]
+    d2_ = ((a[:, :3] - b[:, :3]) ** 2).sum(1)
+    assert bool((d2_ <= (a[:, 3] + b[:, 3]) ** 2 * (1 + 1e-5)).all())
+
+
+def test_config5_100M_uint64_int64_cached_rebuild(ib, dev):
+    """configs[4]: 100 M leaves, UInt64 Morton, Int64 index: build, perturb, cached rebuild in place
+    (BVH(bvh.leaves, cache=bvh)), contact traversal with reused caches. Properties only."""
+    import torch
+    from ibvh_b200 import synth
+    n = 100_000_000
+    o = opts(ib, 8, 8)
+    vols = synth.random_spheres_torch(n, dev, seed=42)
+    src = ib.DeviceArray(vols.view(torch.uint8).reshape(-1), ib.BSphere().dtype)
+    bvh = ib.BVH(src, ib.BBox(), options=o)
+    del src
+    assert bvh.tree.levels == 28 and len(bvh.nodes) == 100_000_007 and bvh.leaves.dtype.itemsize == 32
+    L = bvh.leaves.tensor.view(torch.int64).reshape(n, 4)
+    mort = L[:, 3]
+    assert bool((mort[1:] >= mort[:-1]).all()) and int(mort.min()) >= 0, "63-bit keys ascending"
+    idx = L[:, 2]
+    assert int(idx.sum()) == n * (n + 1) // 2 and int(idx.min()) == 1 and int(idx.max()) == n
+    tr = ib.traverse(bvh, ordered=False)
+    C_ = tr.num_contacts
+    assert 3.5 * n < C_ < 4.5 * n
+    pairs = tr.contacts.tensor.view(torch.int64).reshape(-1, 2)
+    assert bool((pairs[:, 0] < pairs[:, 1]).all())
+    sel = pairs[torch.randint(0, C_, (2000,), device=dev)]
+    a, b = vols[sel[:, 0] - 1], vols[sel[:, 1] - 1]
+    d2_ = ((a[:, :3] - b[:, :3]) ** 2).sum(1)
+    assert bool((d2_ <= (a[:, 3] + b[:, 3]) ** 2 * (1 + 1e-5)).all())
+    del pairs, sel
+    # one simulation step: perturb the centres in place (leaf order = previous Morton order), rebuild with cache
+    s = synth.sphere_radius_scale(n)
+    F = bvh.leaves.tensor.view(torch.float32).reshape(n, 8)
+    for k in range(3):
+        F[:, k] += (synth.uniform_torch(1234, n, k, dev) - 0.5) * (s / 2)
+    moved = F[:, :4].clone()
+    idx_before = L[:, 2].clone()
+    nodes_ptr, leaves_ptr = bvh.nodes.ptr, bvh.leaves.ptr
+    again = ib.BVH(bvh.leaves, ib.BBox(), cache=bvh, options=o)
+    assert again.nodes.ptr == nodes_ptr and again.leaves.ptr == leaves_ptr, "in place, node buffer reused"
+    L2 = again.leaves.tensor.view(torch.int64).reshape(n, 4)
+    assert bool((L2[1:, 3] >= L2[:-1, 3]).all())
+    assert int(L2[:, 2].sum()) == n * (n + 1) // 2
+    # each sphere travelled with its index: compare through the index -> previous position map
+    pos_of_index = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    pos_of_index[idx_before] = torch.arange(n, device=dev)
+    F2 = again.leaves.tensor.view(torch.float32).reshape(n, 8)[:, :4]
+    assert bool((F2 == moved[pos_of_index[L2[:, 2]]]).all())
+    del moved, pos_of_index, idx_before
+    tr2 = ib.traverse(again, ordered=False, cache=tr)
+    assert tr2.cache1.ptr == tr.cache1.ptr or tr2.num_contacts > len(tr.cache1)
+    assert 3.0 * n < tr2.num_contacts < 5.0 * n

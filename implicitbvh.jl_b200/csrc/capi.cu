@@ -1,6 +1,11 @@
 // capi.cu — extern "C" entry points of libibvh_b200.so (declared in include/ibvh.h): argument
 // checks mirroring the reference's @argcheck's, type dispatch onto the kernel templates, workspace
 // carving and the launch sequences. No CPU fallback: without a device every call fails loudly.
+// The file is compiled once per IBVH_PART_* macro (HOST, BUILD, SINGLE, PAIR, RAYS) so that the template
+// instantiations of the five groups of entry points build in parallel (see Makefile).
+#if !defined(IBVH_PART_HOST) && !defined(IBVH_PART_BUILD) && !defined(IBVH_PART_SINGLE) && !defined(IBVH_PART_PAIR) && !defined(IBVH_PART_RAYS)
+#define IBVH_PART_ALL 1
+#endif
 #include <climits>
 #include <cstdlib>
 #include <cmath>
@@ -19,7 +24,12 @@
 
 using namespace ibvh;
 
-namespace {
+// nvcc derives the "unique" name of an anonymous namespace from the source file name, which is the same for all
+// parts: use a per-part named namespace instead
+#ifndef IBVH_NS
+#define IBVH_NS ns_all
+#endif
+namespace IBVH_NS {
 
 template <class X> struct Tag { using type = X; };
 
@@ -779,10 +789,13 @@ void shard_range(const ibvh_traverse_params_t* p, int64_t nq, int64_t* begin, in
     *begin = b; *count = c;
 }
 
-}  // namespace
+}  // namespace IBVH_NS
+using namespace IBVH_NS;
 
 // =================================================================================================================
 extern "C" {
+
+#if defined(IBVH_PART_HOST) || defined(IBVH_PART_ALL)
 
 int ibvh_version(void) { return IBVH_VERSION; }
 
@@ -904,12 +917,6 @@ int ibvh_destroy(ibvh_handle_t* h) {
     delete h;
     return IBVH_OK;
 }
-int64_t ibvh_workspace_query(const ibvh_types_t* types, int64_t n) {
-    if (!types_ok(types) || n < 1) return -1;
-    int64_t out = -1;
-    dispatch_leaf(*types, [&](auto tag) -> int { using L = typename decltype(tag)::type; out = (int64_t)build_workspace_bytes<L>(n, true); return IBVH_OK; });
-    return out;
-}
 int64_t ibvh_workspace_bytes(const ibvh_handle_t* h) { return h ? (int64_t)h->ws_bytes : -1; }
 int ibvh_release_workspace(ibvh_handle_t* h) {
     if (!h) return IBVH_ERR_ARGUMENT;
@@ -919,6 +926,38 @@ int ibvh_release_workspace(ibvh_handle_t* h) {
     return IBVH_OK;
 }
 
+int ibvh_profile_enable(ibvh_handle_t* h, int on) {
+    if (!h) return IBVH_ERR_ARGUMENT;
+    h->prof_on = on != 0;
+    h->prof_n = 0;
+    return IBVH_OK;
+}
+int ibvh_profile_count(ibvh_handle_t* h) { return h ? h->prof_n : -1; }
+int ibvh_profile_get(ibvh_handle_t* h, int i, char* name, int name_cap, float* ms) {
+    if (!h || i < 0 || i >= h->prof_n || !ms) return IBVH_ERR_ARGUMENT;
+    DeviceGuard g(h->device);
+    IBVH_CUDA_TRY(h, cudaEventSynchronize(h->prof_ev[i][1]));
+    IBVH_CUDA_TRY(h, cudaEventElapsedTime(ms, h->prof_ev[i][0], h->prof_ev[i][1]));
+    if (name && name_cap > 0) { snprintf(name, (size_t)name_cap, "%s", h->prof_name[i]); }
+    return IBVH_OK;
+}
+int ibvh_profile_reset(ibvh_handle_t* h) { if (!h) return IBVH_ERR_ARGUMENT; h->prof_n = 0; return IBVH_OK; }
+
+int ibvh_last_traversal_stats(ibvh_handle_t* h, int64_t out[4]) {
+    if (!h || !out) return IBVH_ERR_ARGUMENT;
+    for (int k = 0; k < 4; ++k) out[k] = h->last_stats[k];
+    return IBVH_OK;
+}
+
+#endif  // IBVH_PART_HOST
+
+#if defined(IBVH_PART_BUILD) || defined(IBVH_PART_ALL)
+int64_t ibvh_workspace_query(const ibvh_types_t* types, int64_t n) {
+    if (!types_ok(types) || n < 1) return -1;
+    int64_t out = -1;
+    dispatch_leaf(*types, [&](auto tag) -> int { using L = typename decltype(tag)::type; out = (int64_t)build_workspace_bytes<L>(n, true); return IBVH_OK; });
+    return out;
+}
 // ---- build stages ---------------------------------------------------------------------------------------------
 int ibvh_wrap(ibvh_handle_t* h, const void* d_volumes, int64_t n, const ibvh_types_t* types, void* d_leaves, void* stream) {
     if (!h || !types_ok(types) || n < 0) return IBVH_ERR_ARGUMENT;
@@ -1031,7 +1070,10 @@ int ibvh_build(ibvh_handle_t* h, const void* d_volumes, void* d_leaves, int64_t 
     });
 }
 
+#endif  // IBVH_PART_BUILD
+
 // ---- traversals ---------------------------------------------------------------------------------------------------
+#if defined(IBVH_PART_SINGLE) || defined(IBVH_PART_ALL)
 int ibvh_traverse_single(ibvh_handle_t* h, const ibvh_bvh_t* bvh, const ibvh_traverse_params_t* p, void* d_counts, void* d_contacts,
                          int64_t capacity, int64_t* num_contacts, void* stream) {
     if (!h || !p || !num_contacts) return IBVH_ERR_ARGUMENT;
@@ -1057,6 +1099,9 @@ int ibvh_traverse_single(ibvh_handle_t* h, const ibvh_bvh_t* bvh, const ibvh_tra
     });
 }
 
+#endif  // IBVH_PART_SINGLE
+
+#if defined(IBVH_PART_PAIR) || defined(IBVH_PART_ALL)
 int ibvh_traverse_pair(ibvh_handle_t* h, const ibvh_bvh_t* queries, const ibvh_bvh_t* target, const ibvh_traverse_params_t* p,
                        void* d_counts, void* d_contacts, int64_t capacity, int64_t* num_contacts, void* stream) {
     if (!h || !p || !num_contacts || !queries || !target) return IBVH_ERR_ARGUMENT;
@@ -1089,6 +1134,9 @@ int ibvh_traverse_pair(ibvh_handle_t* h, const ibvh_bvh_t* queries, const ibvh_b
     });
 }
 
+#endif  // IBVH_PART_PAIR
+
+#if defined(IBVH_PART_RAYS) || defined(IBVH_PART_ALL)
 int ibvh_traverse_rays(ibvh_handle_t* h, const ibvh_bvh_t* bvh, const void* d_points, const void* d_directions, int64_t nrays,
                        const ibvh_traverse_params_t* p, void* d_counts, void* d_contacts, int64_t capacity, int64_t* num_contacts, void* stream) {
     if (!h || !p || !num_contacts || nrays < 0) return IBVH_ERR_ARGUMENT;
@@ -1117,27 +1165,6 @@ int ibvh_traverse_rays(ibvh_handle_t* h, const ibvh_bvh_t* bvh, const void* d_po
     });
 }
 
-int ibvh_profile_enable(ibvh_handle_t* h, int on) {
-    if (!h) return IBVH_ERR_ARGUMENT;
-    h->prof_on = on != 0;
-    h->prof_n = 0;
-    return IBVH_OK;
-}
-int ibvh_profile_count(ibvh_handle_t* h) { return h ? h->prof_n : -1; }
-int ibvh_profile_get(ibvh_handle_t* h, int i, char* name, int name_cap, float* ms) {
-    if (!h || i < 0 || i >= h->prof_n || !ms) return IBVH_ERR_ARGUMENT;
-    DeviceGuard g(h->device);
-    IBVH_CUDA_TRY(h, cudaEventSynchronize(h->prof_ev[i][1]));
-    IBVH_CUDA_TRY(h, cudaEventElapsedTime(ms, h->prof_ev[i][0], h->prof_ev[i][1]));
-    if (name && name_cap > 0) { snprintf(name, (size_t)name_cap, "%s", h->prof_name[i]); }
-    return IBVH_OK;
-}
-int ibvh_profile_reset(ibvh_handle_t* h) { if (!h) return IBVH_ERR_ARGUMENT; h->prof_n = 0; return IBVH_OK; }
-
-int ibvh_last_traversal_stats(ibvh_handle_t* h, int64_t out[4]) {
-    if (!h || !out) return IBVH_ERR_ARGUMENT;
-    for (int k = 0; k < 4; ++k) out[k] = h->last_stats[k];
-    return IBVH_OK;
-}
+#endif  // IBVH_PART_RAYS
 
 }  // extern "C"

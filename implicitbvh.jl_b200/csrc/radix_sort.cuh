@@ -25,7 +25,7 @@ constexpr uint32_t kFlagIncl = 2u << 30;   // inclusive prefix published
 constexpr uint32_t kValMask = ~kFlagMask;
 
 // exclusive scan of each pass's 256-bin histogram, in place. grid = passes, block = 256.
-__global__ void __launch_bounds__(256) scan_hist_kernel(uint32_t* hist) {
+static __global__ void __launch_bounds__(256) scan_hist_kernel(uint32_t* hist) {
     __shared__ uint32_t wsum[8];
     uint32_t* h = hist + blockIdx.x * kRadixBins;
     uint32_t v = h[threadIdx.x];

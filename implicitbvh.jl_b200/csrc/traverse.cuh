@@ -572,7 +572,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const I* __re
     }
 }
 // single block: exclusive scan of block_sums in place; total -> *total
-__global__ void __launch_bounds__(1024) scan_block_sums_kernel(long long* block_sums, int64_t nblocks, unsigned long long* total) {
+static __global__ void __launch_bounds__(1024) scan_block_sums_kernel(long long* block_sums, int64_t nblocks, unsigned long long* total) {
     __shared__ long long ws[32];
     __shared__ long long carry;
     if (threadIdx.x == 0) carry = 0;

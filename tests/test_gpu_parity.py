@@ -722,3 +722,48 @@ def test_config5_100M_uint64_int64_cached_rebuild(ib, dev):
     tr2 = ib.traverse(again, ordered=False, cache=tr)
     assert tr2.cache1.ptr == tr.cache1.ptr or tr2.num_contacts > len(tr.cache1)
     assert 3.0 * n < tr2.num_contacts < 5.0 * n
+
+
+# ---- Float64 volumes (the reference's own tests are mostly Float64; runtests.jl:596-900) -------------------
+@pytest.mark.parametrize("node", ["bbox", "sphere"])
+def test_float64_build_and_traversals(ib, O, dev, node):
+    rng = np.random.default_rng(64)
+    nt = ib.BBox(np.float64) if node == "bbox" else ib.BSphere(np.float64)
+    for n in (1, 2, 5, 37, 200, 3000, 20_000):
+        s = random_spheres(rng, n, fbytes=8, spread=6.0 * max(1.0, (n / 200.0) ** (1 / 3)))
+        for ibytes, mbytes in ((4, 4), (8, 8), (4, 2)):
+            ol, on = oracle_build(O, s, node, ibytes, mbytes)
+            bvh = ib.BVH(s, nt, options=opts(ib, ibytes, mbytes))
+            assert bvh.leaves.numpy().tobytes() == ol.tobytes(), (n, ibytes, mbytes, "sorted leaves")
+            assert_nodes_equal(bvh.nodes.numpy(), on, node)
+        want = O.traverse_single(ol, on)
+        assert ib.traverse(bvh).contacts.numpy().tobytes() == want.tobytes(), (n, node)
+        assert (sorted_pairs(ib.traverse(bvh, ordered=False).contacts.numpy()) == sorted_pairs(want)).all()
+        assert (sorted_pairs(want) == sorted_pairs(O.brute_single(s))).all()
+        for sl in range(1, bvh.tree.levels + 1, 3):
+            w2 = O.traverse_single(ol, on, start_level=sl)
+            assert ib.traverse(bvh, start_level=sl).contacts.numpy().tobytes() == w2.tobytes(), (n, node, sl)
+    # pair + rays in Float64
+    s1, s2 = random_spheres(rng, 700, 8), random_spheres(rng, 450, 8)
+    o1, on1 = oracle_build(O, s1, node)
+    o2, on2 = oracle_build(O, s2, node)
+    b1, b2 = ib.BVH(s1, nt), ib.BVH(s2, nt)
+    want = O.traverse_pair(o1, on1, o2, on2)
+    assert ib.traverse(b1, b2).contacts.numpy().tobytes() == want.tobytes()
+    assert (sorted_pairs(want) == sorted_pairs(O.brute_pair(s1, s2))).all()
+    if node == "bbox":
+        p = (8 * rng.random((3, 400)) - 1)
+        d = (rng.random((3, 400)) - 0.5)
+        wr = O.traverse_rays(o1, on1, p, d)
+        gr = ib.traverse_rays(b1, p, d)
+        assert gr.contacts.numpy().tobytes() == wr.tobytes()
+        assert (sorted_pairs(ib.traverse_rays(b1, p, d, ordered=False).contacts.numpy()) == sorted_pairs(wr)).all()
+
+
+def test_float64_reference_doctest(ib, golden, dev):
+    """README.md:37-54 uses Float64 spheres; with Float64 nodes the contacts are the documented ones."""
+    g = golden["five_spheres"]
+    bvh = ib.BVH(ib.bspheres(g["centers"], g["radii"], np.float64), ib.BBox(np.float64))
+    assert pairs_list(ib.traverse(bvh).contacts.numpy()) == [tuple(p) for p in g["contacts_lvt_order"]]
+    with pytest.raises(NotImplementedError):
+        ib.BVH(ib.bspheres(g["centers"], g["radii"], np.float64), ib.BBox(np.float32))    # mixed float types: oracle only

@@ -8,7 +8,7 @@ from .api import (ArgumentError, BBox, BBOX, BSphere, BSPHERE, BVH, BVHOptions, 
                   DefaultMortonAlgorithm, DeviceArray, DomainError, ImplicitTree, LVTTraversal, VolumeType,
                   aggregate, bboxes, bspheres, default_start_level, get_handle, isvirtual, leaf_dtype,
                   level_indices, memory_index, morton_encode, pair_dtype, sort_leaves, traverse,
-                  traverse_rays, wrap_bounding_volumes)
+                  traverse_rays, volumes_from_triangles, wrap_bounding_volumes)
 
 __all__ = [
     "BVH", "BVHTraversal", "BVHOptions", "traverse", "traverse_rays", "default_start_level",

@@ -59,6 +59,7 @@ SIGNATURES = {
     "ibvh_workspace_bytes": (_i64, [_vp]),
     "ibvh_release_workspace": (_ci, [_vp]),
     "ibvh_wrap": (_ci, [_vp, _vp, _i64, C.POINTER(Types), _vp, _vp]),
+    "ibvh_volumes_from_triangles": (_ci, [_vp, _vp, _i64, C.c_int32, C.c_int32, _vp, _vp]),
     "ibvh_morton_encode": (_ci, [_vp, _vp, _i64, C.POINTER(Types), _ci, _dp, _dp, _dp, _dp, _vp]),
     "ibvh_sort_leaves": (_ci, [_vp, _vp, _i64, C.POINTER(Types), _vp]),
     "ibvh_aggregate": (_ci, [_vp, _vp, _i64, C.POINTER(Types), _vp, _i64, _vp]),

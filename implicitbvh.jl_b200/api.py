@@ -630,6 +630,27 @@ def wrap_bounding_volumes(volumes: Union[np.ndarray, DeviceArray], options: BVHO
     return out
 
 
+def volumes_from_triangles(triangles, volume_type: VolumeType = None, device=None) -> DeviceArray:
+    """`[BSphere{T}(tri) for tri in mesh]` / `BBox{T}(tri)` on the device (bsphere.jl:43-112, bbox.jl:59-70).
+    `triangles`: (n, 3, 3) numpy array or CUDA tensor of vertex coordinates in the volume float type."""
+    volume_type = volume_type or BSphere(np.float32)
+    T = {4: np.float32, 8: np.float64}[volume_type.float_bytes]
+    if isinstance(triangles, torch.Tensor):
+        t = triangles.to(dtype={4: torch.float32, 8: torch.float64}[volume_type.float_bytes]).contiguous()
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(np.asarray(triangles, T))).to(torch.device("cuda", _device_index(device)), non_blocking=True)
+    if t.dim() != 3 or tuple(t.shape[1:]) != (3, 3):
+        raise ArgumentError("triangles must have shape (n, 3, 3)")
+    out = DeviceArray.empty(t.shape[0], volume_type.dtype, t.device)
+    h = get_handle(t.device)
+    with torch.cuda.device(t.device.index):
+        rc = capi.lib().ibvh_volumes_from_triangles(h, t.data_ptr(), t.shape[0], volume_type.kind, volume_type.float_bytes, out.ptr,
+                                                    _stream_ptr(t.device.index))
+    if rc != capi.OK:
+        _raise(rc, h, "ibvh_volumes_from_triangles")
+    return out
+
+
 def _leaf_types(leaves: DeviceArray, node: VolumeType = None) -> capi.Types:
     vol = _volume_of_dtype(leaves.dtype["volume"])
     node = node or BBox({4: np.float32, 8: np.float64}[vol.float_bytes])

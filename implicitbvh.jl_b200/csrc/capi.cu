@@ -975,6 +975,26 @@ int ibvh_wrap(ibvh_handle_t* h, const void* d_volumes, int64_t n, const ibvh_typ
     });
 }
 
+int ibvh_volumes_from_triangles(ibvh_handle_t* h, const void* d_triangles, int64_t n, int32_t kind, int32_t float_bytes, void* d_volumes, void* stream) {
+    if (!h || n < 0 || (kind != IBVH_BSPHERE && kind != IBVH_BBOX) || (float_bytes != 4 && float_bytes != 8)) return IBVH_ERR_ARGUMENT;
+    if (n == 0) return IBVH_OK;
+    if (!d_triangles || !d_volumes) return IBVH_ERR_ARGUMENT;
+    DeviceGuard g(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    { ProfScope _ps(h, st, "triangles_kernel");
+    if (float_bytes == 4) {
+        if (kind == IBVH_BSPHERE) triangles_kernel<BSphere<float>><<<blocks, 256, 0, st>>>((const float*)d_triangles, n, (BSphere<float>*)d_volumes);
+        else triangles_kernel<BBox<float>><<<blocks, 256, 0, st>>>((const float*)d_triangles, n, (BBox<float>*)d_volumes);
+    } else {
+        if (kind == IBVH_BSPHERE) triangles_kernel<BSphere<double>><<<blocks, 256, 0, st>>>((const double*)d_triangles, n, (BSphere<double>*)d_volumes);
+        else triangles_kernel<BBox<double>><<<blocks, 256, 0, st>>>((const double*)d_triangles, n, (BBox<double>*)d_volumes);
+    }
+    }
+    IBVH_LAUNCH_CHECK(h, "triangles_kernel");
+    return IBVH_OK;
+}
+
 int ibvh_morton_encode(ibvh_handle_t* h, void* d_leaves, int64_t n, const ibvh_types_t* types, int compute_extrema,
                        const double* mins, const double* maxs, double* out_mins, double* out_maxs, void* stream) {
     if (!h || !types_ok(types) || n < 0) return IBVH_ERR_ARGUMENT;

@@ -138,6 +138,53 @@ template <class T> IBVH_HD BSphere<T> merge(const BSphere<T>& a, const BSphere<T
     return o;
 }
 
+// ---- leaf volumes from triangles (bsphere.jl:43-112, bbox.jl:59-70; utils.jl:178-181) ---------------
+template <class T> IBVH_HD T minimum3(T a, T b, T c) { return a < b ? minimum2(a, c) : minimum2(b, c); }
+template <class T> IBVH_HD T maximum3(T a, T b, T c) { return a > b ? maximum2(a, c) : maximum2(b, c); }
+template <class T> struct FloatEps;
+template <> struct FloatEps<float> { static IBVH_HD float eps() { return 1.1920929e-07f; } };
+template <> struct FloatEps<double> { static IBVH_HD double eps() { return 2.220446049250313e-16; } };
+template <class T> IBVH_HD BSphere<T> sphere_from_triangle(const T* a, const T* b, const T* c) {
+    T abab = ((b[0] - a[0]) * (b[0] - a[0]) + (b[1] - a[1]) * (b[1] - a[1])) + (b[2] - a[2]) * (b[2] - a[2]);
+    T abac = ((b[0] - a[0]) * (c[0] - a[0]) + (b[1] - a[1]) * (c[1] - a[1])) + (b[2] - a[2]) * (c[2] - a[2]);
+    T acac = ((c[0] - a[0]) * (c[0] - a[0]) + (c[1] - a[1]) * (c[1] - a[1])) + (c[2] - a[2]) * (c[2] - a[2]);
+    T d = T(2) * (abab * acac - abac * abac);
+    BSphere<T> o;
+    if (ibvh_abs(d) <= FloatEps<T>::eps()) {
+        T up[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { T lo = minimum3(a[k], b[k], c[k]); up[k] = maximum3(a[k], b[k], c[k]); o.x[k] = T(0.5) * (lo + up[k]); }
+        o.r = ibvh_sqrt(dist3sq(o.x, up));
+        return o;
+    }
+    T s = (abab * acac - acac * abac) / d;
+    T t = (acac * abab - abab * abac) / d;
+    if (s <= T(0)) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) o.x[k] = T(0.5) * (a[k] + c[k]);
+        o.r = ibvh_sqrt(dist3sq(o.x, a));
+    } else if (t <= T(0)) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) o.x[k] = T(0.5) * (a[k] + b[k]);
+        o.r = ibvh_sqrt(dist3sq(o.x, a));
+    } else if (s + t >= T(1)) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) o.x[k] = T(0.5) * (b[k] + c[k]);
+        o.r = ibvh_sqrt(dist3sq(o.x, b));
+    } else {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) o.x[k] = (a[k] + s * (b[k] - a[k])) + t * (c[k] - a[k]);
+        o.r = ibvh_sqrt(dist3sq(o.x, a));
+    }
+    return o;
+}
+template <class T> IBVH_HD BBox<T> box_from_triangle(const T* a, const T* b, const T* c) {
+    BBox<T> o;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { o.lo[k] = minimum3(a[k], b[k], c[k]); o.up[k] = maximum3(a[k], b[k], c[k]); }
+    return o;
+}
+
 // NodeType(leaf.volume) / NodeType(l.volume, r.volume) — build.jl:438-453
 template <class N> struct NodeOps;
 template <class T> struct NodeOps<BBox<T>> {

@@ -238,6 +238,20 @@ __global__ void __launch_bounds__(256) scatter_morton_kernel(L* leaves, int64_t 
     if (i < n) leaves[i].morton = keys[i];     // touches only the morton field
 }
 
+// BSphere{T}(p1, p2, p3) / BBox{T}(p1, p2, p3) for every triangle (bsphere.jl:43-112, bbox.jl:59-70):
+// tri = T[n][3][3]. Nine coalesced-ish loads per thread, one volume store.
+template <class V>
+__global__ void __launch_bounds__(256) triangles_kernel(const typename V::value_type* __restrict__ tri, int64_t n, V* __restrict__ out) {
+    using T = typename V::value_type;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    T p[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) p[k] = tri[9 * i + k];
+    if constexpr (V::kind == IBVH_BSPHERE) out[i] = sphere_from_triangle<T>(p, p + 3, p + 6);
+    else out[i] = box_from_triangle<T>(p, p + 3, p + 6);
+}
+
 // wrap_bounding_volumes, build.jl:340-350
 template <class L>
 __global__ void __launch_bounds__(256) wrap_kernel(const typename L::vol_t* __restrict__ vols, int64_t n, L* __restrict__ leaves) {

@@ -142,6 +142,12 @@ IBVH_API int ibvh_release_workspace(ibvh_handle_t* h);
 IBVH_API int ibvh_wrap(ibvh_handle_t* h, const void* d_volumes, int64_t n, const ibvh_types_t* types,
               void* d_leaves, void* stream);
 
+/* Leaf volumes from triangles — BSphere{T}(p1, p2, p3), src/bounding_volumes/bsphere.jl:43-112, and
+ * BBox{T}(p1, p2, p3), bbox.jl:59-70: the step right before the hot path (README "compute bounding
+ * volumes"). d_triangles: T[n][3][3]; d_volumes: BSphere{T}[n] or BBox{T}[n]. */
+IBVH_API int ibvh_volumes_from_triangles(ibvh_handle_t* h, const void* d_triangles, int64_t n, int32_t kind, int32_t float_bytes,
+                                void* d_volumes, void* stream);
+
 /* morton_encode!, morton/default.jl:43-82 + bounding_volumes_extrema, morton/utils.jl:1-72.
  * compute_extrema != 0: scene bounds reduced on device and padded exactly like the reference;
  * otherwise `mins/maxs` (3 doubles each, converted to the leaf float type) are used unpadded.

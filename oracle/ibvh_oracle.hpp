@@ -135,6 +135,39 @@ template <class TN> struct NodeOps<BSphere<TN>> {
 };
 
 // ---------------------------------------------------------------------------------------------
+// Leaf volumes from triangles — src/bounding_volumes/bsphere.jl:43-112, bbox.jl:59-70 (the step right
+// before the hot path). minimum3 / maximum3: src/utils.jl:178-181.
+// ---------------------------------------------------------------------------------------------
+template <class T> inline T minimum3(T a, T b, T c) { return a < b ? minimum2(a, c) : minimum2(b, c); }
+template <class T> inline T maximum3(T a, T b, T c) { return a > b ? maximum2(a, c) : maximum2(b, c); }
+template <class T> inline BSphere<T> sphere_from_triangle(const T* a, const T* b, const T* c) {
+    T abab = ((b[0] - a[0]) * (b[0] - a[0]) + (b[1] - a[1]) * (b[1] - a[1])) + (b[2] - a[2]) * (b[2] - a[2]);
+    T abac = ((b[0] - a[0]) * (c[0] - a[0]) + (b[1] - a[1]) * (c[1] - a[1])) + (b[2] - a[2]) * (c[2] - a[2]);
+    T acac = ((c[0] - a[0]) * (c[0] - a[0]) + (c[1] - a[1]) * (c[1] - a[1])) + (c[2] - a[2]) * (c[2] - a[2]);
+    T d = T(2) * (abab * acac - abac * abac);
+    BSphere<T> o;
+    if (std::fabs(d) <= std::numeric_limits<T>::epsilon()) {
+        T lo[3], up[3];
+        for (int k = 0; k < 3; ++k) { lo[k] = minimum3(a[k], b[k], c[k]); up[k] = maximum3(a[k], b[k], c[k]); }
+        for (int k = 0; k < 3; ++k) o.x[k] = T(0.5) * (lo[k] + up[k]);
+        o.r = dist3(o.x, up);
+        return o;
+    }
+    T s = (abab * acac - acac * abac) / d;
+    T t = (acac * abab - abab * abac) / d;
+    if (s <= T(0)) { for (int k = 0; k < 3; ++k) o.x[k] = T(0.5) * (a[k] + c[k]); o.r = dist3(o.x, a); }
+    else if (t <= T(0)) { for (int k = 0; k < 3; ++k) o.x[k] = T(0.5) * (a[k] + b[k]); o.r = dist3(o.x, a); }
+    else if (s + t >= T(1)) { for (int k = 0; k < 3; ++k) o.x[k] = T(0.5) * (b[k] + c[k]); o.r = dist3(o.x, b); }
+    else { for (int k = 0; k < 3; ++k) o.x[k] = (a[k] + s * (b[k] - a[k])) + t * (c[k] - a[k]); o.r = dist3(o.x, a); }
+    return o;
+}
+template <class T> inline BBox<T> box_from_triangle(const T* a, const T* b, const T* c) {
+    BBox<T> o;
+    for (int k = 0; k < 3; ++k) { o.lo[k] = minimum3(a[k], b[k], c[k]); o.up[k] = maximum3(a[k], b[k], c[k]); }
+    return o;
+}
+
+// ---------------------------------------------------------------------------------------------
 // iscontact — src/bounding_volumes/iscontact.jl:2-28
 // ---------------------------------------------------------------------------------------------
 template <class T> inline bool iscontact(const BSphere<T>& a, const BSphere<T>& b) {

@@ -127,6 +127,22 @@ int orc_contact_sphere_f64(const double* a4, const double* b4) {
     return iscontact(a, b) ? 1 : 0;
 }
 
+// ---- leaf volumes from triangles: tri = T[n][3][3] (three vertices of three coordinates) -------
+int orc_volumes_from_triangles(const void* tri, int64_t n, int kind, int fbytes, void* out) {
+    auto run = [&](auto ttag) {
+        using T = typename decltype(ttag)::type;
+        const T* t = (const T*)tri;
+        for (int64_t i = 0; i < n; ++i) {
+            const T* a = t + 9 * i; const T* b = a + 3; const T* c = a + 6;
+            if (kind == 0) ((BSphere<T>*)out)[i] = sphere_from_triangle<T>(a, b, c);
+            else ((BBox<T>*)out)[i] = box_from_triangle<T>(a, b, c);
+        }
+    };
+    if (kind != 0 && kind != 1) return -1;
+    if (fbytes == 4) run(Tag<float>{}); else if (fbytes == 8) run(Tag<double>{}); else return -1;
+    return 0;
+}
+
 // ---- size of a wrapped leaf ------------------------------------------------------------------
 int64_t orc_leaf_bytes(int kind, int fbytes, int ibytes, int mbytes) {
     int64_t out = -1;

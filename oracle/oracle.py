@@ -58,6 +58,7 @@ def lib() -> C.CDLL:
             getattr(_lib, name).restype = None
         _lib.orc_contact_sphere_f32.argtypes = [vp, vp]
         _lib.orc_contact_sphere_f64.argtypes = [vp, vp]
+        _lib.orc_volumes_from_triangles.argtypes = [vp, i64, ci, ci, vp]
         _lib.orc_leaf_bytes.restype = i64
         _lib.orc_leaf_bytes.argtypes = [ci, ci, ci, ci]
         _lib.orc_wrap.argtypes = [vp, i64, ci, ci, ci, ci, vp]
@@ -302,6 +303,14 @@ def brute_rays(volumes, points, directions):
     c = lib().orc_brute_rays(_p(volumes), len(volumes), kind, fb, _p(p), _p(d), len(p), None, 0)
     out = np.zeros((c, 2), np.int64)
     lib().orc_brute_rays(_p(volumes), len(volumes), kind, fb, _p(p), _p(d), len(p), _p(out), c)
+    return out
+
+
+def volumes_from_triangles(tris, kind=BSPHERE, fbytes=4) -> np.ndarray:
+    """BSphere{T}(p1, p2, p3) / BBox{T}(p1, p2, p3) for an (n, 3, 3) array of triangle vertices."""
+    t = np.ascontiguousarray(np.asarray(tris, _f(fbytes)).reshape(-1, 3, 3))
+    out = np.zeros(len(t), volume_dtype(kind, fbytes))
+    _check(lib().orc_volumes_from_triangles(_p(t), len(t), kind, fbytes, _p(out)), "volumes_from_triangles")
     return out
 
 

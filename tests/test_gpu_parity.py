@@ -767,3 +767,28 @@ def test_float64_reference_doctest(ib, golden, dev):
     assert pairs_list(ib.traverse(bvh).contacts.numpy()) == [tuple(p) for p in g["contacts_lvt_order"]]
     with pytest.raises(NotImplementedError):
         ib.BVH(ib.bspheres(g["centers"], g["radii"], np.float64), ib.BBox(np.float32))    # mixed float types: oracle only
+
+
+def test_triangles_to_volumes_and_mesh_pipeline(ib, O, golden, dev):
+    """leaf volumes from triangles on the device, bit-exact with the oracle, then the whole
+    mesh -> volumes -> BVH -> contacts pipeline (benchmark/bvh_contact.jl shape) without leaving the device."""
+    rng = np.random.default_rng(5)
+    for T, fb in ((np.float32, 4), (np.float64, 8)):
+        tris = (rng.random((4000, 1, 3)) * 10 + rng.random((4000, 3, 3)) * 0.4).astype(T)
+        tris[:50, 2] = tris[:50, 0] + T(0.5) * (tris[:50, 1] - tris[:50, 0])      # collinear
+        tris[50:60] = tris[50:60, :1]                                              # all three vertices equal
+        for kind, vt in ((O.BSPHERE, ib.BSphere(T)), (O.BBOX, ib.BBox(T))):
+            want = O.volumes_from_triangles(tris, kind, fb)
+            got = ib.volumes_from_triangles(tris, vt, device=dev)
+            assert got.numpy().tobytes() == want.tobytes(), (T, kind)
+        vols = ib.volumes_from_triangles(tris, ib.BSphere(T), device=dev)
+        bvh = ib.BVH(vols, ib.BBox(T))
+        ol, on = oracle_build(O, O.volumes_from_triangles(tris, O.BSPHERE, fb))
+        assert bvh.leaves.numpy().tobytes() == ol.tobytes() and bvh.nodes.numpy().tobytes() == on.tobytes()
+        assert ib.traverse(bvh).contacts.numpy().tobytes() == O.traverse_single(ol, on).tobytes()
+    g = golden["triangle_volumes"]
+    for c in g["bsphere"]:
+        s = ib.volumes_from_triangles(np.array([c["tri"]], np.float64), ib.BSphere(np.float64), device=dev).numpy()[0]
+        assert np.allclose(s["x"], c["x"], rtol=1e-12, atol=1e-15) and np.isclose(s["r"], c["r"], rtol=1e-12)
+    with pytest.raises(ib.ArgumentError):
+        ib.volumes_from_triangles(np.zeros((4, 3, 2), np.float32), device=dev)

@@ -244,3 +244,26 @@ def test_max_seed_quirk(O):
     mn, mx = O.morton_encode(leaves)
     fm = np.finfo(np.float32).tiny
     assert (mx == np.float32(np.float32(fm + np.float32(1e-5) * fm) + fm)).all()
+
+
+def test_triangle_volume_constructors(O, golden):
+    """BSphere{T}(p1,p2,p3) / BBox{T}(p1,p2,p3) known answers (runtests.jl:185-210, 260-276) and agreement with the
+    independent numpy restatement above."""
+    g = golden["triangle_volumes"]
+    for c in g["bsphere"]:
+        s = O.volumes_from_triangles([c["tri"]], O.BSPHERE, 8)[0]
+        assert np.allclose(s["x"], c["x"], rtol=1e-12, atol=1e-15) and np.isclose(s["r"], c["r"], rtol=1e-12), c
+        ref = triangle_sphere(*c["tri"])
+        assert np.allclose([*s["x"], s["r"]], ref, rtol=1e-12, atol=1e-15)
+    for c in g["bbox"]:
+        b = O.volumes_from_triangles([c["tri"]], O.BBOX, 8)[0]
+        assert b["lo"].tolist() == c["lo"] and b["up"].tolist() == c["up"]
+    rng = np.random.default_rng(3)
+    tris = rng.random((500, 3, 3))
+    tris[:20, 2] = tris[:20, 0] + 0.5 * (tris[:20, 1] - tris[:20, 0])          # degenerate (collinear) triangles
+    s = O.volumes_from_triangles(tris, O.BSPHERE, 8)
+    for i in range(len(tris)):
+        ref = triangle_sphere(*tris[i])
+        assert np.allclose([*s[i]["x"], s[i]["r"]], ref, rtol=1e-9, atol=1e-12), i
+        d = np.linalg.norm(tris[i] - s[i]["x"], axis=1)
+        assert (d <= s[i]["r"] * (1 + 1e-9) + 1e-12).all(), "the sphere encloses the three vertices"

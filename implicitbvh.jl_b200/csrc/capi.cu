@@ -601,7 +601,7 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
     const bool unordered = (flags & IBVH_TRAVERSE_UNORDERED) != 0 && d_contacts != nullptr;
     const bool count_only = d_contacts == nullptr;
     const int nl = plan.n;
-    const int grid = h->sm_count * (getenv("IBVH_PYR_GRID") ? atoi(getenv("IBVH_PYR_GRID")) : 10);
+    const int grid = h->sm_count * (getenv("IBVH_PYR_GRID") ? atoi(getenv("IBVH_PYR_GRID")) : 20);
 
     // ordered protocol scratch: counts (if the caller gave none), cursors, scan sums
     const int64_t qblocks = (ta.q_count + kScanTile - 1) / kScanTile;

@@ -196,6 +196,14 @@ def main():
                          "(same set; the parity bar is the SORTED contact list)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-rays", action="store_true", help="skip the secondary rays/s measurement")
+    ap.add_argument("--gather", default="fused", choices=["fused", "peer", "nccl"],
+                    help="N > 1: how the contact shards reach every rank. fused: the traversal kernel itself writes each contact "
+                         "into every rank's list (slots from one counter on rank 0, multimem.st over NVLink; unordered only); "
+                         "peer: traverse locally, then the library's all-gather kernel (ibvh_allgather_pairs); nccl: NCCL collectives")
+    ap.add_argument("--build-mode", default="replicate", choices=["replicate", "broadcast"],
+                    help="N > 1: every rank builds the (deterministic, bit-identical) tree itself, or rank 0 builds and the "
+                         "tree is broadcast with NCCL. The build does not shard either way; replicate is faster as long as a "
+                         "build (1.0 ms at 10 M leaves) costs less than moving 480 MB of leaves + nodes")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -228,7 +236,8 @@ def main():
     bounds = ibdist.shard_bounds(n, world)
     qb, qe = bounds[rank]
 
-    state = {"bvh": None, "tr": None, "full": None}
+    state = {"bvh": None, "tr": None, "full": None, "peer": None}
+    fused = world > 1 and args.gather == "fused" and not ordered
 
     def step_device():
         """One step with inputs in HBM. Returns the number of contacts this rank holds at the end."""
@@ -237,18 +246,31 @@ def main():
             tr = ib.traverse(bvh, cache=state["tr"], ordered=ordered)
             state["bvh"], state["tr"] = bvh, tr
             return tr.num_contacts
-        # build on rank 0, broadcast the tree (leaves + nodes), shard the traversal, gather the shards
-        if rank == 0 or state["bvh"] is None:
-            bvh = ib.BVH(src, ib.BBox(), cache=state["bvh"])        # every rank builds once to own the buffers
+        # the build does not shard: replicate it, or build on rank 0 and broadcast the tree (leaves + nodes);
+        # then shard the traversal by query range and gather the shards
+        if args.build_mode == "replicate":
+            bvh = ib.BVH(src, ib.BBox(), cache=state["bvh"])
             state["bvh"] = bvh
-        bvh = state["bvh"]
-        dist.broadcast(bvh.leaves.tensor, src=0)
-        dist.broadcast(bvh.nodes.tensor, src=0)
+        else:
+            if rank == 0 or state["bvh"] is None:
+                bvh = ib.BVH(src, ib.BBox(), cache=state["bvh"])        # every rank builds once to own the buffers
+                state["bvh"] = bvh
+            bvh = state["bvh"]
+            dist.broadcast(bvh.leaves.tensor, src=0)
+            dist.broadcast(bvh.nodes.tensor, src=0)
+        if state["peer"] is not None and fused:
+            tr = ib.traverse(bvh, cache=state["tr"], ordered=False, query_range=(qb, qe - qb), peer=state["peer"])
+            state["full"] = tr.cache1.tensor
+            return tr.num_contacts
         tr = ib.traverse(bvh, cache=state["tr"], ordered=ordered, query_range=(qb, qe - qb))
         state["tr"] = tr
-        full, counts = ibdist.gather_shards(tr.cache1.tensor, tr.num_contacts, tr.cache1.dtype.itemsize)
+        if state["peer"] is not None:
+            full, total, _ = state["peer"].gather(tr.cache1.tensor, tr.num_contacts)
+        else:
+            full, counts = ibdist.gather_shards(tr.cache1.tensor, tr.num_contacts, tr.cache1.dtype.itemsize)
+            total = int(sum(counts))
         state["full"] = full
-        return int(sum(counts))
+        return total
 
     def sync_all():
         torch.cuda.synchronize()
@@ -258,6 +280,10 @@ def main():
 
     # first call sizes the caches; give cache1 head-room so later steps never regrow
     ncontacts = step_device()
+    if world > 1 and args.gather in ("peer", "fused"):
+        state["peer"] = ibdist.PeerGather(int(ncontacts * 1.05) + 1024, 8, dev)
+        if fused and not state["peer"].peer.multicast:
+            fused = False                                # no NVLS multicast on this box: two-step peer gather
     if world == 1:
         tr = state["tr"]
         state["tr"] = ib.BVHTraversal(1, 0, 0, 0, ib.DeviceArray.empty(int(tr.num_contacts * 1.05) + 1024, ib.pair_dtype(), dev), tr.cache2)
@@ -348,25 +374,35 @@ def main():
             pinned_out[:nb].copy_(tr.cache1.tensor[:nb], non_blocking=True)   # D2H of the step's result
             torch.cuda.current_stream().synchronize()
             return tr.num_contacts
-        if rank == 0:
+        if args.build_mode == "replicate" or rank == 0:
             bvh = ib.BVH(d_in, ib.BBox(), cache=e2e_state["bvh"])
             e2e_state["bvh"] = bvh
         bvh = e2e_state["bvh"]
-        dist.broadcast(bvh.leaves.tensor, src=0)
-        dist.broadcast(bvh.nodes.tensor, src=0)
+        if args.build_mode == "broadcast":
+            dist.broadcast(bvh.leaves.tensor, src=0)
+            dist.broadcast(bvh.nodes.tensor, src=0)
         tr = ib.traverse(bvh, cache=e2e_state["tr"], ordered=ordered, query_range=(qb, qe - qb))
         e2e_state["tr"] = tr
-        full, counts = ibdist.gather_shards(tr.cache1.tensor, tr.num_contacts, 8)
-        nb = int(sum(counts)) * 8
+        if state["peer"] is not None:
+            full, total, _ = state["peer"].gather(tr.cache1.tensor, tr.num_contacts)
+        else:
+            full, counts = ibdist.gather_shards(tr.cache1.tensor, tr.num_contacts, 8)
+            total = int(sum(counts))
+        nb = total * 8
         pinned_out[:nb].copy_(full[:nb], non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        return int(sum(counts))
+        return total
+
+    even = world > 1 and n % world == 0
+    shard_lo, shard_hi = (qb * 16, qe * 16) if even else (0, n * 16)      # this rank's slice of the host volumes (bytes)
 
     def run_e2e_pipelined(k_steps):
-        """Single GPU: the same per-step work (H2D of the step's volumes -> BVH -> traverse -> D2H of the step's
-        contact list), software-pipelined over three streams with double buffers so that the copies of
-        neighbouring steps overlap the kernels (PCIe is full duplex). Every step's input still comes from pinned
-        host memory and every step's contacts still land in pinned host memory inside the timed region."""
+        """The same per-step work (H2D of the step's volumes -> BVH -> traverse -> D2H of the step's contact list),
+        software-pipelined over three streams with double buffers so that the copies of neighbouring steps overlap
+        the kernels (PCIe is full duplex). Every step's input still comes from pinned host memory and every step's
+        contacts still land in pinned host memory inside the timed region.
+        N > 1: each rank's host holds 1/N of the volumes and receives its own shard of the contact list; the
+        volumes are all-gathered over NVLink (NCCL, in place), the build is replicated, the traversal sharded."""
         s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         main = torch.cuda.current_stream(dev)
         d_in = [ib.DeviceArray.empty(n, pinned_in.dtype, dev) for _ in range(2)]
@@ -381,7 +417,7 @@ def main():
             b = k % 2
             with torch.cuda.stream(s_in):
                 s_in.wait_event(comp_done[b])                 # step k-2 no longer reads d_in[b]
-                d_in[b].tensor.copy_(pinned_in.tensor, non_blocking=True)
+                d_in[b].tensor[shard_lo:shard_hi].copy_(pinned_in.tensor[shard_lo:shard_hi], non_blocking=True)
                 in_ready[b].record(s_in)
 
         for ev in comp_done + out_done:
@@ -394,8 +430,13 @@ def main():
                 h2d(k + 1)                                     # next step's input travels while this step computes
             main.wait_event(in_ready[b])
             main.wait_event(out_done[b])                       # step k-2's contacts have left caches[b]
+            if even:
+                dist.all_gather_into_tensor(d_in[b].tensor, d_in[b].tensor[shard_lo:shard_hi])
             bvh = ib.BVH(d_in[b], ib.BBox(), cache=bvh_prev)
-            tr = ib.traverse(bvh, cache=caches[b], ordered=ordered)
+            if world == 1:
+                tr = ib.traverse(bvh, cache=caches[b], ordered=ordered)
+            else:
+                tr = ib.traverse(bvh, cache=caches[b], ordered=ordered, query_range=(qb, qe - qb))
             caches[b] = tr
             bvh_prev = bvh
             comp_done[b].record(main)
@@ -408,7 +449,8 @@ def main():
         s_out.synchronize(); s_in.synchronize(); main.synchronize()
         return last
 
-    if world == 1:
+    pipelined = world == 1 or args.build_mode == "replicate"
+    if pipelined:
         run_e2e_pipelined(3)
         sync_all()
         t0 = time.perf_counter()
@@ -417,35 +459,34 @@ def main():
         e1.record()
         sync_all()
         e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / args.steps
-        # also the strictly sequential figure (no overlap between steps), for reference
-        for _ in range(2):
-            step_e2e()
-        sync_all()
-        t0 = time.perf_counter()
-        for _ in range(max(3, args.steps // 4)):
-            step_e2e()
-        sync_all()
-        e2e_seq_ms = (time.perf_counter() - t0) * 1e3 / max(3, args.steps // 4)
-    else:
-        for _ in range(3):
-            step_e2e()
-        sync_all()
-        t0 = time.perf_counter()
-        e0.record()
-        for _ in range(args.steps):
-            nc = step_e2e()
-        e1.record()
-        sync_all()
-        e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / args.steps
-        e2e_seq_ms = e2e_ms
+    # the strictly sequential figure (no overlap between steps; N > 1: every rank uploads all volumes and the
+    # gathered contact list comes back), for reference
+    seq_steps = max(3, args.steps // 4) if pipelined else args.steps
+    for _ in range(3):
+        step_e2e()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(seq_steps):
+        nc_seq = step_e2e()
+    sync_all()
+    e2e_seq_ms = (time.perf_counter() - t0) * 1e3 / seq_steps
+    if not pipelined:
+        e2e_ms, nc = e2e_seq_ms, nc_seq
+    h2d_bytes = n * 16 if (world == 1 or (pipelined and even)) else n * 16 * world
     if world > 1:
-        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        t = torch.tensor([e2e_ms, e2e_seq_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
-    e2e = {"value": n / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(n * 16), "d2h_bytes_per_step": int(nc * 8),
+        e2e_ms, e2e_seq_ms = float(t[0].item()), float(t[1].item())
+        t = torch.tensor([nc], dtype=torch.int64, device=dev)
+        if pipelined:
+            dist.all_reduce(t)                      # contacts copied back, summed over the ranks' shards
+        nc = int(t.item())
+    e2e = {"value": n / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(nc * 8),
            "ms_per_step": e2e_ms, "sequential_ms_per_step": e2e_seq_ms,
-           "note": "public API (BVH + traverse) from pinned host volumes to pinned host contacts; single GPU: copies of neighbouring steps overlap "
-                   "the kernels (3 streams, double buffers); sequential_ms_per_step is the same without any overlap"}
+           "note": "public API (BVH + traverse) from pinned host volumes to pinned host contacts; copies of neighbouring steps overlap "
+                   "the kernels (3 streams, double buffers); N > 1: each rank's host holds 1/N of the volumes (all-gathered over NVLink "
+                   "after the upload) and receives its own shard of the contact list; sequential_ms_per_step is the same without any "
+                   "overlap (N > 1: every rank uploads all volumes, rank-gathered contact list comes back)"}
 
     # ---- secondary metric of BASELINE.json: rays/s @ 1 M leaves (configs[3]) ------------------------------
     # 1000 x 1000 mesh-like shell of spheres, R random rays (origins U[-1.5,1.5)^3, directions uniform on S^2),
@@ -508,7 +549,7 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD % n, "leaves": n, "contacts_per_step": int(ncontacts),
                        "contact_order": "reference (ascending query, DFS order; count+scan+write)" if ordered else "unordered (one pass, buffered warp-aggregated atomics; identical as a sorted list)",
-                       "parallelism": "single GPU" if world == 1 else f"build on rank 0 + NCCL broadcast, query-range sharded traversal over {world} GPUs, all-gather of contact shards",
+                       "parallelism": "single GPU" if world == 1 else (("build replicated on every rank (deterministic, bit-identical)" if args.build_mode == "replicate" else "build on rank 0 + NCCL broadcast of the tree") + f", query-range sharded traversal over {world} GPUs, " + ("traversal fused with the all-gather: contacts written into every rank's list by the traversal kernel (multimem.st over NVLink)" if fused else "contact shards all-gathered by the library's peer-memory kernel (NVLink multicast stores)" if args.gather in ("peer", "fused") else "NCCL all-gather of the contact shards")),
                        "l2_policy": "inputs larger than L2 (160 MB volumes + 240 MB leaves + 240 MB nodes per step vs 126 MB L2)"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,
             "secondary": rays,

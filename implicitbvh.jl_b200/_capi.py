@@ -13,7 +13,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libibvh_b200.so")
 
 # status codes (include/ibvh.h)
-OK, ERR_ARGUMENT, ERR_DOMAIN, ERR_UNSUPPORTED, ERR_CUDA, ERR_CAPACITY, ERR_ALLOC = range(7)
+OK, ERR_ARGUMENT, ERR_DOMAIN, ERR_UNSUPPORTED, ERR_CUDA, ERR_CAPACITY, ERR_ALLOC, ERR_PEER = range(8)
+MAX_PEERS = 16
 BSPHERE, BBOX = 0, 1
 TRAVERSE_ORDERED, TRAVERSE_UNORDERED, TRAVERSE_REFERENCE_SHAPED, TRAVERSE_COUNTS_VALID = 0, 1, 2, 4
 TRAVERSE_STATS, TRAVERSE_PACKET, TRAVERSE_WALK = 8, 16, 32
@@ -34,9 +35,14 @@ class Bvh(C.Structure):
                 ("types", Types)]
 
 
+class Peer(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("buffers", C.c_uint64 * MAX_PEERS), ("multicast", C.c_uint64),
+                ("header_bytes", C.c_int64), ("capacity_bytes", C.c_int64), ("epoch", C.c_uint64), ("fused_seq", C.c_uint64)]
+
+
 class TraverseParams(C.Structure):
     _fields_ = [("start_level", C.c_int64), ("query_begin", C.c_int64), ("query_count", C.c_int64),
-                ("flags", C.c_uint32), ("flip", C.c_int32), ("id_base", C.c_int64)]
+                ("flags", C.c_uint32), ("flip", C.c_int32), ("id_base", C.c_int64), ("peer", C.POINTER(Peer))]
 
 
 # name -> (restype, argtypes); kept as a table so tests can check every header symbol is exported
@@ -72,6 +78,7 @@ SIGNATURES = {
     "ibvh_profile_get": (_ci, [_vp, _ci, C.c_char_p, _ci, C.POINTER(C.c_float)]),
     "ibvh_profile_reset": (_ci, [_vp]),
     "ibvh_last_traversal_stats": (_ci, [_vp, C.POINTER(_i64)]),
+    "ibvh_allgather_pairs": (_ci, [_vp, C.POINTER(Peer), _vp, _i64, C.c_int32, C.POINTER(_i64), C.POINTER(_i64), _vp]),
 }
 
 _lib = None

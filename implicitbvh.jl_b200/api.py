@@ -499,13 +499,15 @@ def _run_two_phase(call, handle, device, I: np.dtype, nqueries: int, cache: Opti
 def traverse(bvh: BVH, bvh2=None, alg=None, *, start_level: Optional[int] = None, start_level1: Optional[int] = None,
              start_level2: Optional[int] = None, narrow=None, cache: Optional[BVHTraversal] = None, options: BVHOptions = None,
              ordered: bool = True, reference_shaped: bool = False, packet: bool = False, walk: bool = False,
-             query_range=None) -> BVHTraversal:
+             query_range=None, peer=None) -> BVHTraversal:
     """`traverse(bvh[, bvh2], LVTTraversal(); start_level[1,2], narrow, cache, options)`.
 
     Extensions over the reference signature (all keyword-only, defaults reproduce the reference):
     `ordered=False` selects the unordered emission, `reference_shaped=True` the proxy of the reference's
     own GPU kernel, `packet=True` forces the warp-packet schedule (default: group walk + dense tiles for
     BBox nodes), `query_range=(begin, count)` restricts the query leaves (multi-GPU shard).
+    `peer=dist.PeerGather(...)` (with `ordered=False`) fuses the sharded traversal with the all-gather of the
+    contact shards: collective over the ranks, the returned (unordered) list holds the contacts of ALL ranks.
     """
     if bvh2 is not None and not isinstance(bvh2, BVH):       # traverse(bvh, alg)
         alg, bvh2 = bvh2, None
@@ -514,6 +516,20 @@ def traverse(bvh: BVH, bvh2=None, alg=None, *, start_level: Optional[int] = None
     _check_narrow(narrow)
     lib = capi.lib()
     qb, qc = (0, -1) if query_range is None else (int(query_range[0]), int(query_range[1]))
+    if peer is not None and (ordered or reference_shaped or packet or walk):
+        raise ArgumentError("the fused multi-GPU traversal is the unordered default schedule (ordered=False)")
+
+    def run(call, handle, device, I, nq):
+        if peer is None:
+            return _run_two_phase(call, handle, device, I, nq, cache, ordered, reference_shaped, packet, walk)
+        if peer.pair_bytes != pair_dtype(I).itemsize or peer.device != device:
+            raise ArgumentError("PeerGather pair size / device do not match the BVH")
+        total = C.c_int64(0)
+        rc = call(capi.TRAVERSE_UNORDERED, None, None, 0, total, peer.next_fused())
+        if rc != capi.OK:
+            _raise(rc, handle, f"fused traverse (gathered total {total.value} pairs)")
+        c2 = cache.cache2 if cache is not None else DeviceArray.empty(0, I, device)
+        return int(total.value), DeviceArray(peer.list_area(), pair_dtype(I)), c2
 
     if bvh2 is None:
         sl = default_start_level(bvh) if start_level is None else int(start_level)
@@ -526,13 +542,13 @@ def traverse(bvh: BVH, bvh2=None, alg=None, *, start_level: Optional[int] = None
         cb = bvh._c_bvh()
         nq = len(bvh.leaves) if qc < 0 else qc
 
-        def call(flags, p_counts, p_contacts, capacity, total):
-            params = capi.TraverseParams(sl, qb, qc, flags, 0, 0)
+        def call(flags, p_counts, p_contacts, capacity, total, peer_ref=None):
+            params = capi.TraverseParams(sl, qb, qc, flags, 0, 0, peer_ref)
             with torch.cuda.device(device.index):
                 return lib.ibvh_traverse_single(bvh._handle, C.byref(cb), C.byref(params), p_counts, p_contacts, capacity,
                                                 C.byref(total), _stream_ptr(device.index))
 
-        total, c1, c2 = _run_two_phase(call, bvh._handle, device, I, nq, cache, ordered, reference_shaped, packet, walk)
+        total, c1, c2 = run(call, bvh._handle, device, I, nq)
         return BVHTraversal(sl, 0, 0, total, c1, c2)
 
     # pair — traverse_pair.jl:1-116
@@ -553,13 +569,13 @@ def traverse(bvh: BVH, bvh2=None, alg=None, *, start_level: Optional[int] = None
     cq, ct = queries._c_bvh(), target._c_bvh()
     nq = len(queries.leaves) if qc < 0 else qc
 
-    def call(flags, p_counts, p_contacts, capacity, total):
-        params = capi.TraverseParams(sl_t, qb, qc, flags, 1 if flip else 0, 0)
+    def call(flags, p_counts, p_contacts, capacity, total, peer_ref=None):
+        params = capi.TraverseParams(sl_t, qb, qc, flags, 1 if flip else 0, 0, peer_ref)
         with torch.cuda.device(device.index):
             return lib.ibvh_traverse_pair(bvh._handle, C.byref(cq), C.byref(ct), C.byref(params), p_counts, p_contacts, capacity,
                                           C.byref(total), _stream_ptr(device.index))
 
-    total, c1, c2 = _run_two_phase(call, bvh._handle, device, I, nq, cache, ordered, reference_shaped, packet, walk)
+    total, c1, c2 = run(call, bvh._handle, device, I, nq)
     return BVHTraversal(sl1, sl2, 0, total, c1, c2)
 
 

@@ -594,12 +594,35 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
     using T = typename LT::value_type;
     using N = BBox<T>;
     *num_contacts = 0;
-    if (ta.q_count <= 0) return IBVH_OK;
+    // fused multi-GPU mode: slots come from the rotating counter on rank 0, contacts go out through the multicast alias
+    const bool fused = ta.peer != nullptr;
+    PeerArgs pa{};
+    unsigned long long* out_total = (unsigned long long*)(h->d_small + kSmallTotal);
+    IndexPair<I>* out_ptr = (IndexPair<I>*)d_contacts;
+    int64_t* h_peer = (int64_t*)(h->h_pinned + 3072);
+    if (fused) {
+        pa = make_peer_args(ta.peer);
+        out_total = (unsigned long long*)pa.buf[0] + kPeerCounterSlot + pa.fused_seq % 3;
+        out_ptr = (IndexPair<I>*)(pa.mc + pa.header_bytes);
+        capacity = pa.capacity_bytes / (int64_t)sizeof(IndexPair<I>);
+    }
+    auto fused_finish = [&]() -> int {
+        h_peer[1] = -1;
+        { ProfScope _ps(h, st, "peer_fused_finish_kernel");
+        peer_fused_finish_kernel<<<1, 32, 0, st>>>(pa, h_peer);
+        }
+        IBVH_LAUNCH_CHECK(h, "peer_fused_finish_kernel");
+        IBVH_CUDA_TRY(h, cudaStreamSynchronize(st));
+        if (h_peer[1] != 0) { h->set_error("fused traversal: a peer did not finish its shard within 10 s"); return IBVH_ERR_PEER; }
+        *num_contacts = h_peer[0];
+        return *num_contacts > capacity ? IBVH_ERR_CAPACITY : IBVH_OK;
+    };
+    if (ta.q_count <= 0) return fused ? fused_finish() : IBVH_OK;
     const int64_t q_begin = ta.q_begin, q_end = ta.q_begin + ta.q_count;
     unsigned long long* d_total = (unsigned long long*)(h->d_small + kSmallTotal);
     unsigned long long* d_cnt = (unsigned long long*)(h->d_small + 1536);      // one list counter per level
-    const bool unordered = (flags & IBVH_TRAVERSE_UNORDERED) != 0 && d_contacts != nullptr;
-    const bool count_only = d_contacts == nullptr;
+    const bool unordered = fused || ((flags & IBVH_TRAVERSE_UNORDERED) != 0 && d_contacts != nullptr);
+    const bool count_only = !fused && d_contacts == nullptr;
     const int nl = plan.n;
     const int grid = h->sm_count * (getenv("IBVH_PYR_GRID") ? atoi(getenv("IBVH_PYR_GRID")) : 20);
 
@@ -636,7 +659,7 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
         PairList lists[kPyrMaxLevels];
         for (int l = 0; l < nl; ++l) { lists[l].data = (uint2*)ap; lists[l].count = d_cnt + l; lists[l].cap = cap[l]; ap += ibvh_handle::padded((size_t)cap[l] * sizeof(uint2)); }
         IBVH_CUDA_TRY(h, cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * kPyrMaxLevels, st));
-        IBVH_CUDA_TRY(h, cudaMemsetAsync(d_total, 0, 8, st));
+        IBVH_CUDA_TRY(h, cudaMemsetAsync(d_total, 0, 8, st));      // (fused: the rank-0 counter is rotated by the finish kernel instead)
 
         // 1. query pyramid
         { ProfScope _ps(h, st, "pyr_leafgroups_kernel");
@@ -668,31 +691,54 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
         }
         // 4. leaf tiles
         const int64_t qe = q_end < n_query_total ? q_end : n_query_total;
+        if (fused) {
+            // the tile kernel publishes into every rank's list: it must run exactly once, so the pair-list overflow
+            // check (and the retry with larger lists) comes before it
+            unsigned long long* hp = (unsigned long long*)h->h_pinned;
+            IBVH_CUDA_TRY(h, cudaMemcpyAsync(hp + 1, d_cnt, sizeof(unsigned long long) * kPyrMaxLevels, cudaMemcpyDeviceToHost, st));
+            IBVH_CUDA_TRY(h, cudaStreamSynchronize(st));
+            bool overflow = false;
+            double worst = 0.0;
+            for (int l = 0; l < nl; ++l) {
+                unsigned long long c = hp[1 + l];
+                need_cap[l] = c;
+                if (c > cap[l]) overflow = true;
+                double r = (double)c / (double)plan.lv[l].nqg;
+                if (l < nl - 1 && r > worst) worst = r;
+            }
+            if (overflow) { factor = worst * 1.15 + 2.0; continue; }
+            h->pyr_factor = worst * 1.25 + 4.0;
+            { ProfScope _ps(h, st, "pyr_leaf_tile_kernel");
+            pyr_leaf_tile_kernel<KIND, kAtomic, 0, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, capacity, out_total, (I*)nullptr, nullptr, out_ptr, 1);
+            }
+            IBVH_LAUNCH_CHECK(h, "pyr_leaf_tile_kernel");
+            return fused_finish();
+        }
         bool counts_valid = (flags & IBVH_TRAVERSE_COUNTS_VALID) && d_counts && d_contacts;
         if (unordered || count_only) {
             if (unordered) {
                 { ProfScope _ps(h, st, "pyr_leaf_tile_kernel");
-                pyr_leaf_tile_kernel<KIND, kAtomic, 0, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, capacity, d_total, (I*)nullptr, nullptr, (IndexPair<I>*)d_contacts);
+                pyr_leaf_tile_kernel<KIND, kAtomic, 0, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, capacity, out_total, (I*)nullptr, nullptr, out_ptr, fused ? 1 : 0);
                 }
             } else if (d_counts) {
                 // count-only call of the ordered protocol: per-query counts + scan (cache2), total from the scan
                 IBVH_CUDA_TRY(h, cudaMemsetAsync(counts, 0, (size_t)ta.q_count * sizeof(I), st));
                 { ProfScope _ps(h, st, "pyr_leaf_tile_kernel");
-                pyr_leaf_tile_kernel<KIND, kCount, 1, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, 0, d_total, counts, nullptr, (IndexPair<I>*)nullptr);
+                pyr_leaf_tile_kernel<KIND, kCount, 1, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, 0, d_total, counts, nullptr, (IndexPair<I>*)nullptr, 0);
                 }
                 IBVH_LAUNCH_CHECK(h, "pyr_leaf_tile_kernel");
                 rc = scan_counts<I>(h, counts, ta.q_count, qsums, d_total, st);
                 if (rc != IBVH_OK) return rc;
             } else {
                 { ProfScope _ps(h, st, "pyr_leaf_tile_kernel");
-                pyr_leaf_tile_kernel<KIND, kCount, 0, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, 0, d_total, (I*)nullptr, nullptr, (IndexPair<I>*)nullptr);
+                pyr_leaf_tile_kernel<KIND, kCount, 0, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, 0, d_total, (I*)nullptr, nullptr, (IndexPair<I>*)nullptr, 0);
                 }
             }
             IBVH_LAUNCH_CHECK(h, "pyr_leaf_tile_kernel");
         } else if (!counts_valid) {
             IBVH_CUDA_TRY(h, cudaMemsetAsync(counts, 0, (size_t)ta.q_count * sizeof(I), st));
             { ProfScope _ps(h, st, "pyr_leaf_tile_kernel");
-            pyr_leaf_tile_kernel<KIND, kCount, 1, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, 0, d_total, counts, nullptr, (IndexPair<I>*)nullptr);
+            pyr_leaf_tile_kernel<KIND, kCount, 1, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, 0, d_total, counts, nullptr, (IndexPair<I>*)nullptr, 0);
             }
             IBVH_LAUNCH_CHECK(h, "pyr_leaf_tile_kernel");
             rc = scan_counts<I>(h, counts, ta.q_count, qsums, d_total, st);
@@ -734,7 +780,7 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
         // ordered write: per-query cursors, then sort each query's handful of hits by target position
         IBVH_CUDA_TRY(h, cudaMemsetAsync(cursors, 0, (size_t)ta.q_count * 4, st));
         { ProfScope _ps(h, st, "pyr_leaf_tile_kernel");
-        pyr_leaf_tile_kernel<KIND, kWrite, 2, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, capacity, d_total, counts, cursors, (IndexPair<I>*)d_contacts);
+        pyr_leaf_tile_kernel<KIND, kWrite, 2, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, capacity, d_total, counts, cursors, (IndexPair<I>*)d_contacts, 0);
         }
         IBVH_LAUNCH_CHECK(h, "pyr_leaf_tile_kernel");
         { ProfScope _ps(h, st, "pyr_fixup_kernel");
@@ -752,6 +798,24 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
 template <int KIND, class LQ, class LT, class N, class I>
 int traverse_leaf_queries(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, const DBvh<LT, N>& d, int64_t built_level, const TraverseArgs& a,
                           uint32_t flags, void* d_counts, void* d_contacts, int64_t capacity, int64_t* num_contacts, cudaStream_t st) {
+    if (a.peer) {
+        // fused traversal + all-gather: pyramid schedule with multicast output only; everything else is
+        // "traverse locally, then ibvh_allgather_pairs"
+        bool ok = false;
+        if constexpr (std::is_same<N, BBox<typename LT::value_type>>::value) {
+            PyrPlan plan;
+            ok = peer_ok(a.peer) && a.peer->multicast && a.peer->fused_seq > 0 && (flags & IBVH_TRAVERSE_UNORDERED) &&
+                 !(flags & (IBVH_TRAVERSE_REFERENCE_SHAPED | IBVH_TRAVERSE_PACKET | IBVH_TRAVERSE_STATS | IBVH_TRAVERSE_WALK)) &&
+                 a.start_level <= d.ti.levels - 1 && d.ti.n < (int64_t(1) << 29) && n_query_total < (int64_t(1) << 29) &&
+                 make_pyr_plan(d.ti, built_level, 0, n_query_total, &plan);       // same verdict on every rank
+            if (ok) {
+                if (a.q_count > 0 && !make_pyr_plan(d.ti, built_level, a.q_begin, a.q_count, &plan)) ok = false;
+                if (ok) return traverse_pyramid<KIND, LQ, LT, I>(h, qleaves, n_query_total, d, plan, a, flags, d_counts, d_contacts, capacity, num_contacts, st);
+            }
+        }
+        h->set_error("fused multi-GPU traversal needs BBox nodes, the pyramid schedule, IBVH_TRAVERSE_UNORDERED and a multicast alias");
+        return IBVH_ERR_UNSUPPORTED;
+    }
     if (flags & IBVH_TRAVERSE_REFERENCE_SHAPED)
         return traverse_impl<KIND, false, LQ, LT, N, I>(h, qleaves, nullptr, nullptr, d, a, flags, d_counts, d_contacts, capacity, num_contacts, st);
     if constexpr (std::is_same<N, BBox<typename LT::value_type>>::value) {
@@ -808,6 +872,7 @@ const char* ibvh_status_string(int s) {
         case IBVH_ERR_CUDA: return "CUDA error";
         case IBVH_ERR_CAPACITY: return "contacts capacity too small";
         case IBVH_ERR_ALLOC: return "workspace allocation failed";
+        case IBVH_ERR_PEER: return "peer GPU did not arrive at the shard exchange";
     }
     return "unknown";
 }
@@ -1114,6 +1179,7 @@ int ibvh_traverse_single(ibvh_handle_t* h, const ibvh_bvh_t* bvh, const ibvh_tra
             shard_range(p, bvh->n, &a.q_begin, &a.q_count);
             a.start_level = (int32_t)p->start_level;
             a.flip = 0;
+            a.peer = p->peer;
             return traverse_leaf_queries<kSingle, L, L, N, I>(h, d.leaves, bvh->n, d, bvh->built_level, a, p->flags, d_counts, d_contacts, capacity, num_contacts, st);
         });
     });
@@ -1149,6 +1215,7 @@ int ibvh_traverse_pair(ibvh_handle_t* h, const ibvh_bvh_t* queries, const ibvh_b
             shard_range(p, queries->n, &a.q_begin, &a.q_count);
             a.start_level = (int32_t)p->start_level;
             a.flip = p->flip ? 1 : 0;
+            a.peer = p->peer;
             return traverse_leaf_queries<kPair, L, L, N, I>(h, (const L*)queries->d_leaves, queries->n, d, target->built_level, a, p->flags, d_counts, d_contacts, capacity, num_contacts, st);
         });
     });
@@ -1159,6 +1226,7 @@ int ibvh_traverse_pair(ibvh_handle_t* h, const ibvh_bvh_t* queries, const ibvh_b
 #if defined(IBVH_PART_RAYS) || defined(IBVH_PART_ALL)
 int ibvh_traverse_rays(ibvh_handle_t* h, const ibvh_bvh_t* bvh, const void* d_points, const void* d_directions, int64_t nrays,
                        const ibvh_traverse_params_t* p, void* d_counts, void* d_contacts, int64_t capacity, int64_t* num_contacts, void* stream) {
+    if (p && p->peer) { if (h) h->set_error("rays: no fused mode; traverse the ray shard, then ibvh_allgather_pairs"); return IBVH_ERR_UNSUPPORTED; }
     if (!h || !p || !num_contacts || nrays < 0) return IBVH_ERR_ARGUMENT;
     ibvh_tree_t tree;
     int rc = check_bvh(bvh, &tree);

@@ -45,6 +45,7 @@ struct TraverseArgs {
     const uint32_t* qmap;
     const uint32_t* qmap_count;
     int32_t qmap_group;
+    const ibvh_peer_t* peer;     // fused traversal + all-gather over peer memory (pyramid schedule, unordered), else nullptr
 };
 
 // 8-byte vectorised struct loads (volumes are 8-byte aligned by layout; see common.cuh)

@@ -21,6 +21,7 @@
 // phase is a persistent grid-stride kernel that reads the count), so the whole traversal needs a single
 // host synchronisation: the read-back of the contact total, as in the reference.
 #pragma once
+#include "peer.cuh"
 #include <type_traits>
 
 #include "common.cuh"
@@ -244,7 +245,9 @@ template <int KIND, int MODE, int PMODE, class LQ, class LT, class I>
 __global__ void __launch_bounds__(kPyrWarps * 32) pyr_leaf_tile_kernel(const LQ* __restrict__ qleaves, int64_t q_begin, int64_t q_end,
                                                                       DBvh<LT, BBox<typename LT::value_type>> bvh, PairList in, int flip,
                                                                       int64_t capacity, unsigned long long* total,
-                                                                      I* counts, unsigned int* cursors, IndexPair<I>* contacts) {
+                                                                      I* counts, unsigned int* cursors, IndexPair<I>* contacts, int fused) {
+    // fused != 0 (multi-GPU, atomic mode): `total` is the output-slot counter on rank 0 (peer-mapped, system-scope
+    // atomics over NVLink) and `contacts` the NVSwitch multicast alias of every rank's list (multimem.st)
     using T = typename LT::value_type;
     using N = BBox<T>;
     using VT = typename LT::vol_t;
@@ -312,7 +315,7 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_leaf_tile_kernel(const LQ*
                 ncount += kept;
             } else if (kept) {
                 unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(total, (unsigned long long)kept);
+                if (lane == 0) base = fused ? atomicAdd_system(total, (unsigned long long)kept) : atomicAdd(total, (unsigned long long)kept);
                 base = __shfl_sync(0xffffffffu, base, 0);
                 for (uint32_t k = lane; k < kept; k += 32) {
                     const uint2 e = s_buf[w][b0 + k];
@@ -322,7 +325,10 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_leaf_tile_kernel(const LQ*
                     if constexpr (KIND == kSingle) { if (qidx > li) { ea = li; eb = qidx; } else { ea = qidx; eb = li; } }
                     else { if (flip) { ea = li; eb = qidx; } else { ea = qidx; eb = li; } }
                     const unsigned long long wp = base + k;
-                    if ((int64_t)wp < capacity) contacts[wp] = IndexPair<I>{ea, eb};
+                    if ((int64_t)wp < capacity) {
+                        if (fused) multimem_store_pair(contacts + wp, IndexPair<I>{ea, eb});
+                        else contacts[wp] = IndexPair<I>{ea, eb};
+                    }
                 }
             }
         }

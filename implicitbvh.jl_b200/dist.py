@@ -7,9 +7,13 @@ torch.distributed (NCCL over NVLink on the GPU box, gloo in the CPU tests) for t
     the shards in rank order reproduces the single-GPU contact list exactly.
   * traverse_rays: contiguous ray ranges per rank, same concatenation property.
 
-The gather of variable-length shards is an all_gather of the per-rank counts followed by one padded
-all_gather_into_tensor of the contact bytes. Only host logic lives here; it is covered by the
-world_size-2 gloo tests on CPU (tests/test_dist_gloo.py) with fake shards.
+Two gathers of the variable-length shards:
+  * `PeerGather` (the product path on NVLink boxes): one kernel of libibvh_b200.so per rank
+    (ibvh_allgather_pairs) exchanges the counts and writes the shard into every rank's list through
+    peer / NVSwitch-multicast memory; torch's symmetric memory only provides the mapped buffers.
+  * `gather_shards`: NCCL / gloo collectives (all_gather of the counts, then one padded
+    all_gather_into_tensor); the portable path, covered by the world_size-2 gloo tests on CPU
+    (tests/test_dist_gloo.py) with fake shards.
 """
 from __future__ import annotations
 
@@ -69,6 +73,67 @@ def gather_shards(shard: torch.Tensor, count: int, itemsize: int, group=None) ->
     dist.all_gather_into_tensor(allb, pad, group=group)
     parts = [allb[r * maxc * itemsize: r * maxc * itemsize + counts_h[r] * itemsize] for r in range(world)]
     return torch.cat(parts), counts_h
+
+
+class PeerGather:
+    """All-gather of (index, index) pair shards over NVLink peer memory, rank order preserved.
+
+    Every rank constructs it with the same capacity. `gather(shard, count)` is a collective: it returns
+    (uint8 view of the gathered list, total pairs, offset of this rank's shard). The view aliases the
+    symmetric buffer and is overwritten by the next gather()."""
+
+    HEADER = 4096
+
+    def __init__(self, capacity_pairs: int, pair_bytes: int = 8, device=None, group=None):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm
+        from . import _capi, api
+        self._C, self._capi = C, _capi
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        if self.world > _capi.MAX_PEERS:
+            raise ValueError(f"at most {_capi.MAX_PEERS} ranks")
+        self.device = torch.device(device if device is not None else torch.cuda.current_device())
+        self.pair_bytes = int(pair_bytes)
+        self.capacity_bytes = (int(capacity_pairs) * self.pair_bytes + 255) & ~255
+        self.buf = symm.empty(self.HEADER + self.capacity_bytes, dtype=torch.uint8, device=self.device)
+        self.hdl = symm.rendezvous(self.buf, self.group)
+        self.buf[: self.HEADER].zero_()
+        torch.cuda.synchronize(self.device)
+        dist.barrier(self.group)
+        self.handle = api.get_handle(self.device)
+        self.peer = _capi.Peer()
+        self.peer.rank, self.peer.world = self.rank, self.world
+        for r in range(self.world):
+            self.peer.buffers[r] = int(self.hdl.buffer_ptrs[r])
+        mc = getattr(self.hdl, "multicast_ptr", 0) or 0
+        self.peer.multicast = int(mc)
+        self.peer.header_bytes, self.peer.capacity_bytes = self.HEADER, self.capacity_bytes
+        self.epoch = 0
+        self.fused_seq = 0
+
+    def next_fused(self):
+        """ctypes reference to the peer descriptor stamped for the next fused traversal (api.traverse(peer=...))."""
+        self.epoch += 1
+        self.fused_seq += 1
+        self.peer.epoch, self.peer.fused_seq = self.epoch, self.fused_seq
+        return self._C.pointer(self.peer)
+
+    def list_area(self) -> torch.Tensor:
+        return self.buf[self.HEADER: self.HEADER + self.capacity_bytes]
+
+    def gather(self, shard: torch.Tensor, count: int) -> Tuple[torch.Tensor, int, int]:
+        C = self._C
+        self.epoch += 1
+        self.peer.epoch = self.epoch
+        total, offset = C.c_int64(0), C.c_int64(0)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        rc = self._capi.lib().ibvh_allgather_pairs(self.handle, C.byref(self.peer), shard.data_ptr() if count else None, int(count),
+                                                   self.pair_bytes, C.byref(total), C.byref(offset), stream)
+        if rc != 0:
+            msg = self._capi.lib().ibvh_last_error(self.handle).decode()
+            raise RuntimeError(f"ibvh_allgather_pairs: {self._capi.status_string(rc)}: {msg} (need {total.value} pairs)")
+        return self.buf[self.HEADER: self.HEADER + total.value * self.pair_bytes], int(total.value), int(offset.value)
 
 
 def concat_in_rank_order(parts: Sequence[np.ndarray]) -> np.ndarray:

@@ -55,7 +55,8 @@ typedef enum ibvh_status {
     IBVH_ERR_UNSUPPORTED = 3,  /* type combination not compiled into this build             */
     IBVH_ERR_CUDA = 4,         /* CUDA runtime error; text via ibvh_last_error              */
     IBVH_ERR_CAPACITY = 5,     /* contacts buffer too small; *num_contacts holds the need   */
-    IBVH_ERR_ALLOC = 6         /* workspace allocation failed                               */
+    IBVH_ERR_ALLOC = 6,        /* workspace allocation failed                               */
+    IBVH_ERR_PEER = 7          /* a peer GPU did not arrive at the shard exchange in time   */
 } ibvh_status;
 
 typedef enum ibvh_volume_kind { IBVH_BSPHERE = 0, IBVH_BBOX = 1 } ibvh_volume_kind;
@@ -99,6 +100,18 @@ typedef struct ibvh_bvh {
                                       /* left by a previous count-only call on the same queries: */
                                       /* skip the count pass and write (the reference's 2nd pass) */
 
+/* Peer-memory descriptor of the multi-GPU exchange (see "multi-GPU" at the end of this header). */
+#define IBVH_MAX_PEERS 16
+typedef struct ibvh_peer {
+    int32_t rank, world;                 /* world <= IBVH_MAX_PEERS                                  */
+    uint64_t buffers[IBVH_MAX_PEERS];    /* device address of rank r's buffer as mapped in THIS process */
+    uint64_t multicast;                  /* multicast alias of the buffers (NVLS), 0 = use peer stores */
+    int64_t header_bytes;                /* >= 512 * 8, multiple of 256                               */
+    int64_t capacity_bytes;              /* size of the list area that follows the header             */
+    uint64_t epoch;                      /* collective-call counter shared by all ranks (> 0, increasing) */
+    uint64_t fused_seq;                  /* 1, 2, 3, ... over the FUSED traversals issued on this buffer */
+} ibvh_peer_t;
+
 typedef struct ibvh_traverse_params {
     int64_t start_level;      /* level of the descended tree the traversal starts from         */
     int64_t query_begin;      /* 0-based first query of this shard (leaf position / ray)       */
@@ -107,6 +120,14 @@ typedef struct ibvh_traverse_params {
     int32_t flip;             /* pair only: emit (leaf.index, query.index) — traverse_pair.jl:212-216 */
     int64_t id_base;          /* rays only: ray r of the passed arrays is reported as id_base + r + 1
                                  (0 for a whole problem; the global offset of a per-GPU ray shard)     */
+    const ibvh_peer_t* peer;  /* NULL, or (single / pair, UNORDERED, BBox nodes): fused traversal + all-gather —
+                                 every rank traverses its query shard and the contacts of ALL ranks land in
+                                 EVERY rank's list area (peer->buffers[r] + header_bytes) while the traversal
+                                 runs: output slots are reserved from one counter on rank 0 (system-scope
+                                 atomics over NVLink) and written with multimem.st through peer->multicast.
+                                 d_contacts is ignored, capacity is the list area's, *num_contacts returns the
+                                 gathered total (same on every rank). Collective; IBVH_ERR_UNSUPPORTED if the
+                                 combination cannot run fused (then: traverse locally + ibvh_allgather_pairs). */
 } ibvh_traverse_params_t;
 
 typedef struct ibvh_handle ibvh_handle_t;
@@ -215,6 +236,30 @@ IBVH_API int ibvh_profile_reset(ibvh_handle_t* h);
  * packet schedule: out[2] = warp steps, out[3] = warp-uniform node/leaf loads;
  * reference-shaped schedule: out[2] = per-query steps, out[3] = sum over warps of the slowest lane's steps. */
 IBVH_API int ibvh_last_traversal_stats(ibvh_handle_t* h, int64_t out[4]);
+
+/* ---- multi-GPU: all-gather of the contact / hit shards over NVLink peer memory ------
+ * The reference has no multi-GPU path; this is the exchange step that follows a query-range sharded
+ * traversal (traverse_single.jl:157, traverse_pair.jl:199, raytrace/leaf_vs_tree/leaf_vs_tree.jl:137:
+ * every query is independent). One process per GPU. Each process owns one "symmetric" buffer of the
+ * same size and hands this library the device addresses at which ALL ranks' buffers are mapped into its
+ * own address space (CUDA VMM / IPC peer mappings; the Python stand-in gets them from
+ * torch.distributed._symmetric_memory) and, when the fabric offers it, the NVSwitch multicast alias.
+ * Buffer layout: [header_bytes of signal slots, zeroed once at creation][list area].
+ *
+ * ibvh_allgather_pairs: ONE kernel per rank that (1) publishes this rank's pair count into every peer's
+ * header and waits for theirs, (2) writes its shard at its rank-order offset into EVERY rank's list area
+ * (multimem.st through the multicast alias, else plain peer stores), (3) runs a release/acquire barrier
+ * over the headers, so that when the kernel completes this rank's list area holds the concatenation of
+ * all shards in rank order — for ORDERED shards of contiguous query ranges exactly the single-GPU list.
+ * Collective: every rank must call it with the same epoch (> 0, increasing from call to call, shared with the
+ * fused traversals' peer->epoch) and
+ * stream-order its readers of the previous list before the call. A rank that does not arrive within
+ * 10 s makes the others return IBVH_ERR_PEER instead of hanging.
+ * Host outputs (the call synchronises the stream): *out_total = pairs in the gathered list,
+ * *out_offset = first pair of this rank's shard inside it. IBVH_ERR_CAPACITY if the list area is too
+ * small for out_total pairs (same verdict on every rank; nothing is written). */
+IBVH_API int ibvh_allgather_pairs(ibvh_handle_t* h, const ibvh_peer_t* peer, const void* d_shard, int64_t count,
+                                  int32_t pair_bytes, int64_t* out_total, int64_t* out_offset, void* stream);
 
 #ifdef __cplusplus
 }

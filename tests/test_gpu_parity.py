@@ -792,3 +792,22 @@ def test_triangles_to_volumes_and_mesh_pipeline(ib, O, golden, dev):
         assert np.allclose(s["x"], c["x"], rtol=1e-12, atol=1e-15) and np.isclose(s["r"], c["r"], rtol=1e-12)
     with pytest.raises(ib.ArgumentError):
         ib.volumes_from_triangles(np.zeros((4, 3, 2), np.float32), device=dev)
+
+
+@pytest.mark.gpu
+def test_multi_gpu_fused_traversal_and_peer_gather():
+    """Multi-GPU exchange through the C ABI: ibvh_allgather_pairs reproduces the single-GPU ordered list
+    from rank-ordered shards, and the fused traversal (ibvh_traverse_params_t.peer) the single-GPU contact set.
+    One process per GPU under torchrun; with one visible GPU the same code runs as a world of 1."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ngpu = torch.cuda.device_count()
+    world = 2 if ngpu >= 2 else 1
+    env = dict(os.environ, LEAVES="300000", TIMING="0", NCCL_DEBUG="WARN")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", "29571", os.path.join(ROOT, "tools", "fused_test.py")]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "PARITY ok" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])

@@ -709,7 +709,11 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
             if (overflow) { factor = worst * 1.15 + 2.0; continue; }
             h->pyr_factor = worst * 1.25 + 4.0;
             { ProfScope _ps(h, st, "pyr_leaf_tile_kernel");
-            pyr_leaf_tile_kernel<KIND, kAtomic, 0, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, capacity, out_total, (I*)nullptr, nullptr, out_ptr, 1);
+            const int big = getenv("IBVH_FUSED_FLUSH") ? atoi(getenv("IBVH_FUSED_FLUSH")) >= 1024 : pa.world >= 4;
+            if (big)
+                pyr_leaf_tile_kernel<KIND, kAtomic, 0, LQ, LT, I, 1024><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, capacity, out_total, (I*)nullptr, nullptr, out_ptr, 1);
+            else
+                pyr_leaf_tile_kernel<KIND, kAtomic, 0, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, capacity, out_total, (I*)nullptr, nullptr, out_ptr, 1);
             }
             IBVH_LAUNCH_CHECK(h, "pyr_leaf_tile_kernel");
             return fused_finish();

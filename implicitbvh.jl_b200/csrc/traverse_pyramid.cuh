@@ -241,7 +241,9 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_refine_kernel(PyrLevel coa
 // MODE kAtomic: append contacts (unordered). kCount: only add the number of contacts to *total.
 // PMODE (ordered protocol): 0 = none; 1 = count per query (atomicAdd counts[qi]); 2 = write (qpos, tpos) into the
 // query's segment via a per-query cursor (fixed up into reference order by pyr_fixup_kernel).
-template <int KIND, int MODE, int PMODE, class LQ, class LT, class I>
+// FLUSH: buffered hits per output-slot reservation. The fused multi-GPU mode on >= 4 ranks uses 1024: every
+// reservation is a system-scope atomic on ONE counter of rank 0, which sustains ~190 M/s in total.
+template <int KIND, int MODE, int PMODE, class LQ, class LT, class I, int FLUSH = kPyrFlush>
 __global__ void __launch_bounds__(kPyrWarps * 32) pyr_leaf_tile_kernel(const LQ* __restrict__ qleaves, int64_t q_begin, int64_t q_end,
                                                                       DBvh<LT, BBox<typename LT::value_type>> bvh, PairList in, int flip,
                                                                       int64_t capacity, unsigned long long* total,
@@ -257,7 +259,7 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_leaf_tile_kernel(const LQ*
     constexpr bool kNeedParent = !std::is_same<VT, N>::value || !std::is_same<VQ, N>::value;   // box leaves: implied by the leaf test
     struct alignas(16) TVol { VT v; };
     __shared__ TVol s_vol[kPyrWarps][SLOTS][G];
-    __shared__ uint2 s_buf[kPyrWarps][32 * G + kPyrFlush];
+    __shared__ uint2 s_buf[kPyrWarps][32 * G + FLUSH];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int slot = lane / G, m = lane % G;
     const uint32_t n_target = (uint32_t)bvh.ti.n;
@@ -317,17 +319,34 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_leaf_tile_kernel(const LQ*
                 unsigned long long base = 0;
                 if (lane == 0) base = fused ? atomicAdd_system(total, (unsigned long long)kept) : atomicAdd(total, (unsigned long long)kept);
                 base = __shfl_sync(0xffffffffu, base, 0);
-                for (uint32_t k = lane; k < kept; k += 32) {
-                    const uint2 e = s_buf[w][b0 + k];
+                auto to_pair = [&](uint2 e) -> IndexPair<I> {
                     const I qidx = (I)qleaves[e.x].index;
                     const I li = (I)bvh.leaves[e.y].index;
                     I ea, eb;
                     if constexpr (KIND == kSingle) { if (qidx > li) { ea = li; eb = qidx; } else { ea = qidx; eb = li; } }
                     else { if (flip) { ea = li; eb = qidx; } else { ea = qidx; eb = li; } }
-                    const unsigned long long wp = base + k;
-                    if ((int64_t)wp < capacity) {
-                        if (fused) multimem_store_pair(contacts + wp, IndexPair<I>{ea, eb});
-                        else contacts[wp] = IndexPair<I>{ea, eb};
+                    return IndexPair<I>{ea, eb};
+                };
+                if (fused && sizeof(IndexPair<I>) == 8 && (int64_t)(base + kept) <= capacity) {
+                    // multicast stores do not coalesce across lanes: two contacts per 16-byte multimem.st
+                    const uint32_t head = (uint32_t)(base & 1ull);
+                    const uint32_t npair = (kept - head) >> 1;
+                    for (uint32_t k = lane; k < npair; k += 32) {
+                        const IndexPair<I> p0 = to_pair(s_buf[w][b0 + head + 2 * k]), p1 = to_pair(s_buf[w][b0 + head + 2 * k + 1]);
+                        uint4 v;
+                        v.x = (uint32_t)p0.a; v.y = (uint32_t)p0.b; v.z = (uint32_t)p1.a; v.w = (uint32_t)p1.b;
+                        multimem_st_v4(contacts + base + head + 2 * k, v);
+                    }
+                    if (lane == 0 && head) multimem_store_pair(contacts + base, to_pair(s_buf[w][b0]));
+                    if (lane == 1 && ((kept - head) & 1u)) multimem_store_pair(contacts + base + kept - 1, to_pair(s_buf[w][b0 + kept - 1]));
+                } else {
+                    for (uint32_t k = lane; k < kept; k += 32) {
+                        const IndexPair<I> pr = to_pair(s_buf[w][b0 + k]);
+                        const unsigned long long wp = base + k;
+                        if ((int64_t)wp < capacity) {
+                            if (fused) multimem_store_pair(contacts + wp, pr);
+                            else contacts[wp] = pr;
+                        }
                     }
                 }
             }
@@ -398,7 +417,7 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_leaf_tile_kernel(const LQ*
             any = __ballot_sync(0xffffffffu, hits != 0);
         }
         __syncwarp();
-        if (nbuf >= (uint32_t)kPyrFlush) flush(nbuf & ~31u);
+        if (nbuf >= (uint32_t)FLUSH) flush(nbuf & ~31u);
         __syncwarp();
     }
     if (nbuf) flush(nbuf);

@@ -355,7 +355,15 @@ def main():
                 "kernel_ms_per_step": dom_ms, "share_of_step": dom_ms / ms_step,
                 "per_kernel_ms": {k: round(v, 4) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1])},
                 "traversal_ms_per_step": round(sum(v for k, v in per_kernel.items() if k.startswith(("pyr_", "tile_", "group_walk", "lvt_", "scan_r", "scan_b", "scan_a"))), 4),
-                "build_ms_per_step": round(sum(v for k, v in per_kernel.items() if k in ("init_build_kernel", "bounds_kernel", "encode_kernel", "scan_hist_kernel", "onesweep_kernel", "gather_merge_kernel", "merge_levels_kernel")), 4)}
+                "build_ms_per_step": round(sum(v for k, v in per_kernel.items() if k in ("init_build_kernel", "bounds_kernel", "encode_kernel", "scan_hist_kernel", "onesweep_kernel", "gather_kernel", "gather_merge_kernel", "merge_levels_kernel")), 4)}
+    # intersection tests of one traversal (this rank's shard), derived by the library from its pair-list sizes
+    import ctypes as C
+    st4 = (C.c_int64 * 4)()
+    lib.ibvh_last_traversal_stats(handle, st4)
+    trav_ms = roofline["traversal_ms_per_step"]
+    if st4[3] > 0 and trav_ms > 0:
+        roofline["traversal_tests"] = {"box_tests_per_step": int(st4[0]), "leaf_tests_per_step": int(st4[1]), "candidate_group_pairs": int(st4[2]),
+                                       "intersection_tests_per_s": (int(st4[0]) + int(st4[1])) / (trav_ms * 1e-3), "scope": "this rank's query shard"}
 
     # ---- e2e: host (pinned) volumes in, contacts back to pinned host memory ------------------------
     host_vols = synth.random_spheres_np(n, seed=SEED) if rank == 0 or world > 1 else None

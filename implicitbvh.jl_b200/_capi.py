@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libibvh_b200.so")
+LIB_PATH = os.environ.get("IBVH_B200_LIB") or os.path.join(_HERE, "lib", "libibvh_b200.so")
 
 # status codes (include/ibvh.h)
 OK, ERR_ARGUMENT, ERR_DOMAIN, ERR_UNSUPPORTED, ERR_CUDA, ERR_CAPACITY, ERR_ALLOC, ERR_PEER = range(8)

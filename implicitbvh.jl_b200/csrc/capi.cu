@@ -708,6 +708,15 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
             }
             if (overflow) { factor = worst * 1.15 + 2.0; continue; }
             h->pyr_factor = worst * 1.25 + 4.0;
+            {   // test counts of this traversal, from the pair-list sizes (ibvh_last_traversal_stats)
+                const int64_t F2 = int64_t(1) << (2 * kPyrFan), G2 = int64_t(1) << (2 * kPyrLeafLog);
+                int64_t box = plan.lv[nl - 1].nqg * plan.lv[nl - 1].ntg;
+                for (int l = nl - 1; l >= 1; --l) box += (int64_t)std::min(hp[1 + l], cap[l]) * F2;
+                h->last_stats[0] = box;
+                h->last_stats[1] = (int64_t)std::min(hp[1], cap[0]) * G2;
+                h->last_stats[2] = (int64_t)hp[1];
+                h->last_stats[3] = nl;
+            }
             { ProfScope _ps(h, st, "pyr_leaf_tile_kernel");
             const int big = getenv("IBVH_FUSED_FLUSH") ? atoi(getenv("IBVH_FUSED_FLUSH")) >= 1024 : pa.world >= 4;
             if (big)
@@ -777,6 +786,15 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
         }
         if (overflow) { factor = worst * 1.15 + 2.0; continue; }
         h->pyr_factor = worst * 1.25 + 4.0;
+        {   // test counts of this traversal, from the pair-list sizes (ibvh_last_traversal_stats)
+            const int64_t F2 = int64_t(1) << (2 * kPyrFan), G2 = int64_t(1) << (2 * kPyrLeafLog);
+            int64_t box = plan.lv[nl - 1].nqg * plan.lv[nl - 1].ntg;
+            for (int l = nl - 1; l >= 1; --l) box += (int64_t)std::min(hp[1 + l], cap[l]) * F2;
+            h->last_stats[0] = box;
+            h->last_stats[1] = (int64_t)std::min(hp[1], cap[0]) * G2;
+            h->last_stats[2] = (int64_t)hp[1];
+            h->last_stats[3] = nl;
+        }
         *num_contacts = (int64_t)hp[0];
         if (unordered) return *num_contacts > capacity ? IBVH_ERR_CAPACITY : IBVH_OK;
         if (count_only || *num_contacts == 0) return IBVH_OK;

@@ -32,7 +32,10 @@ namespace ibvh {
 
 constexpr int kPyrWarps = 4;                // warps per CTA in the refine / tile kernels
 constexpr int kPyrLeafLog = 2;              // finest groups: 4 leaves
-constexpr int kPyrFan = 3;                  // 8 children per refinement
+#ifndef IBVH_PYR_FAN
+#define IBVH_PYR_FAN 3
+#endif
+constexpr int kPyrFan = IBVH_PYR_FAN;       // 2^3 = 8 children per refinement
 constexpr int kPyrMaxLevels = 12;
 constexpr int kPyrFlush = 256;              // buffered entries per list atomic
 

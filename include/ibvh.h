@@ -234,7 +234,10 @@ IBVH_API int ibvh_profile_reset(ibvh_handle_t* h);
  * pass of the default BSphere{Float32}/Int32/UInt32/BBox type set only):
  * out[0] = node tests (per query), out[1] = leaf tests (per query),
  * packet schedule: out[2] = warp steps, out[3] = warp-uniform node/leaf loads;
- * reference-shaped schedule: out[2] = per-query steps, out[3] = sum over warps of the slowest lane's steps. */
+ * reference-shaped schedule: out[2] = per-query steps, out[3] = sum over warps of the slowest lane's steps.
+ * Pyramid schedule (the default for BBox nodes; no flag needed, any mode): totals of the last traversal derived
+ * from its pair-list sizes — out[0] = box-box tests, out[1] = leaf-leaf tests, out[2] = candidate pairs of
+ * 4-leaf groups, out[3] = pyramid levels. */
 IBVH_API int ibvh_last_traversal_stats(ibvh_handle_t* h, int64_t out[4]);
 
 /* ---- multi-GPU: all-gather of the contact / hit shards over NVLink peer memory ------

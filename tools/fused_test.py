@@ -47,6 +47,22 @@ fullp = ib.traverse(bvh, bvh2, ordered=False)
 if pg.peer.multicast and fullp.num_contacts * 8 <= pg.capacity_bytes:
     trp = ib.traverse(bvh, bvh2, ordered=False, query_range=(qb, qe - qb), peer=pg)
     ok &= trp.num_contacts == fullp.num_contacts and bool(torch.equal(sorted_pairs(trp.cache1.tensor, trp.num_contacts), sorted_pairs(fullp.cache1.tensor, fullp.num_contacts)))
+# Int64 indices / UInt64 Morton codes: 16-byte pairs through the same exchange
+opt64 = ib.BVHOptions(index=np.int64, morton=ib.DefaultMortonAlgorithm(np.uint64))
+n64 = max(1000, n // 4)
+v64 = synth.random_spheres_torch(n64, dev, seed=9)
+bvh64 = ib.BVH(ib.DeviceArray(v64.view(torch.uint8).reshape(-1), ib.BSphere().dtype), ib.BBox(), options=opt64)
+full64 = ib.traverse(bvh64, ordered=True)
+pg64 = ibdist.PeerGather(full64.num_contacts + 1024, 16, dev)
+b64 = ibdist.shard_bounds(n64, world)[rank]
+t64 = ib.traverse(bvh64, ordered=True, query_range=(b64[0], b64[1] - b64[0]))
+lst, tot, off = pg64.gather(t64.cache1.tensor, t64.num_contacts)
+ok &= tot == full64.num_contacts and bool(torch.equal(lst, full64.cache1.tensor[: tot * 16]))
+if pg64.peer.multicast:
+    f64 = ib.traverse(bvh64, ordered=False, query_range=(b64[0], b64[1] - b64[0]), peer=pg64)
+    a = f64.cache1.tensor[: f64.num_contacts * 16].view(torch.int64).reshape(-1, 2)
+    b = full64.cache1.tensor[: tot * 16].view(torch.int64).reshape(-1, 2)
+    ok &= f64.num_contacts == tot and bool(torch.equal(torch.sort(a[:, 0] * (n64 + 1) + a[:, 1]).values, torch.sort(b[:, 0] * (n64 + 1) + b[:, 1]).values))
 # capacity error is reported on every rank
 small = ibdist.PeerGather(1000, 8, dev)
 if small.peer.multicast:

@@ -155,8 +155,11 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_refine_kernel(PyrLevel coa
     __shared__ SBox s_box[kPyrWarps][SLOTS][F + 1];
     // hit buffer: up to 32*F new entries per step on top of < kPyrFlush pending ones
     __shared__ uint2 s_buf[kPyrWarps][32 * F + kPyrFlush];
+    __shared__ uint32_t s_n[kPyrWarps];                                    // entries buffered per warp
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int slot = lane / F, i = lane % F;
+    if (lane == 0) s_n[w] = 0;
+    __syncwarp();
     unsigned long long count64 = *in.count;
     if (count64 > in.cap) count64 = in.cap;
     const uint32_t count = (uint32_t)count64;                              // list sizes are < 2^32 (checked by the host)
@@ -176,66 +179,75 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_refine_kernel(PyrLevel coa
         nbuf = b0;
     };
     // Software pipeline: while step t is computed, the boxes of step t+1 and the list entry of step t+2 are in flight
-    // (the kernel is bound by the latency of these dependent loads, not by issue slots or bandwidth).
-    struct Stage { uint32_t Ac, Bc0; bool a_ok, t_ok; N u, tb; };
+    // (the kernel is bound by issue slots: 2x unrolled ping-pong stages instead of copying a stage per step, loads
+    // from clamped indices instead of predicated loads + selects — `a_ok` / `allowed` mask what is not real).
+    struct Stage { uint32_t Ac, Bc0; bool a_ok; N u, tb; };
     auto fetch = [&](uint2 pr, bool have) -> Stage {
         Stage sg;
         sg.Ac = (pr.x << kPyrFan) + (uint32_t)i;                           // my child of A (absolute group index, fine level)
         sg.Bc0 = pr.y << kPyrFan;                                          // first child of B
         const uint32_t ua = sg.Ac - f_first;                               // wraps to a huge value if Ac < f_first
         sg.a_ok = have && ua < f_nqg;
-        sg.t_ok = have && sg.Bc0 + i < f_ntg;
-        sg.u = empty_box<T>();
-        sg.tb = empty_box<T>();
-        if (sg.a_ok) sg.u = load_struct(Uf + ua);
-        if (sg.t_ok) sg.tb = load_struct(Nf + sg.Bc0 + i);
+        sg.u = load_struct(Uf + min(ua, f_nqg - 1u));
+        sg.tb = load_struct(Nf + min(sg.Bc0 + (uint32_t)i, f_ntg - 1u));
         return sg;
+    };
+    volatile uint32_t* s_nv = s_n;
+    auto process = [&](const Stage& cur) {
+        s_box[w][slot][i].b = cur.tb;
+        __syncwarp();
+        uint32_t hits = 0;
+        if (cur.a_ok) {
+#pragma unroll
+            for (int j = 0; j < F; ++j) if (iscontact(cur.u, s_box[w][slot][j].b)) hits |= 1u << j;
+            bool edge = cur.Bc0 + (uint32_t)F > f_ntg;
+            if constexpr (KIND == kSingle) edge = edge || cur.Ac > cur.Bc0;
+            if (edge) {
+                const uint32_t nval = f_ntg - cur.Bc0;
+                uint32_t allowed = nval >= (uint32_t)F ? ((1u << F) - 1u) : ((1u << nval) - 1u);
+                if constexpr (KIND == kSingle) {
+                    if (cur.Ac > cur.Bc0) {                                  // child j admissible iff Bc0 + j >= Ac
+                        const uint32_t lo = cur.Ac - cur.Bc0;
+                        allowed &= lo >= (uint32_t)F ? 0u : ~((1u << lo) - 1u);
+                    }
+                }
+                hits &= allowed;
+            }
+        }
+        // append: one shared-memory atomic per lane with hits reserves its slots in the warp's buffer
+        if (hits) {
+            uint32_t wpos = atomicAdd(&s_n[w], (uint32_t)__popc(hits));
+            do {
+                const int j = __ffs(hits) - 1;
+                hits &= hits - 1;
+                s_buf[w][wpos++] = make_uint2(cur.Ac, cur.Bc0 + (uint32_t)j);
+            } while (hits);
+        }
+        __syncwarp();
+        nbuf = s_nv[w];
+        if (nbuf >= (uint32_t)kPyrFlush) { flush(nbuf & ~31u); if (lane == 0) s_nv[w] = nbuf; }
+        __syncwarp();
     };
     uint32_t p = ((uint32_t)blockIdx.x * kPyrWarps + w) * SLOTS + slot;
     uint2 e1 = make_uint2(0u, 0u), e2 = make_uint2(0u, 0u);
     if (p < count) e1 = in.data[p];
     if (p + step < count) e2 = in.data[p + step];
-    Stage cur = fetch(e1, p < count);
-    for (uint32_t p0 = p - slot; p0 < count; p0 += step, p += step) {
-        const Stage nxt = fetch(e2, p + step < count);                     // boxes of the next step
-        e2 = make_uint2(0u, 0u);
-        if (p + 2 * step < count && p + 2 * step > p) e2 = in.data[p + 2 * step];   // entry of the step after
-        const uint32_t Ac = cur.Ac, Bc0 = cur.Bc0;
-        const bool a_ok = cur.a_ok;
-        const N u = cur.u;
-        if (cur.t_ok) s_box[w][slot][i].b = cur.tb;
-        __syncwarp();
-        uint32_t hits = 0;
-        if (a_ok) {
-            const uint32_t nval = f_ntg - Bc0;
-            uint32_t allowed = nval >= (uint32_t)F ? ((1u << F) - 1u) : ((1u << nval) - 1u);
-            if constexpr (KIND == kSingle) {
-                if (Ac > Bc0) {                                              // child j admissible iff Bc0 + j >= Ac
-                    const uint32_t lo = Ac - Bc0;
-                    allowed &= lo >= (uint32_t)F ? 0u : ~((1u << lo) - 1u);
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < F; ++j) hits |= (iscontact(u, s_box[w][slot][j].b) ? 1u : 0u) << j;
-            hits &= allowed;
-        }
-        cur = nxt;
-        // append: exclusive prefix of the per-lane hit counts, then every lane writes its own hits
-        const int nh = __popc(hits);
-        int incl = nh;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) { int o = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += o; }
-        const int tot = __shfl_sync(0xffffffffu, incl, 31);
-        uint32_t wpos = nbuf + (uint32_t)(incl - nh);
-        while (hits) {
-            const int j = __ffs(hits) - 1;
-            hits &= hits - 1;
-            s_buf[w][wpos++] = make_uint2(Ac, Bc0 + (uint32_t)j);
-        }
-        nbuf += (uint32_t)tot;
-        __syncwarp();
-        if (nbuf >= (uint32_t)kPyrFlush) flush(nbuf & ~31u);
-        __syncwarp();
+    auto next_entry = [&]() {                                              // entry of the step after the next
+        uint2 e = make_uint2(0u, 0u);
+        if (p + 2 * step < count && p + 2 * step > p) e = in.data[p + 2 * step];
+        return e;
+    };
+    Stage sa = fetch(e1, p < count), sb;
+    for (uint32_t p0 = p - slot; p0 < count;) {
+        sb = fetch(e2, p + step < count);                                  // boxes of the next step
+        e2 = next_entry();
+        process(sa);
+        p0 += step; p += step;
+        if (p0 >= count) break;
+        sa = fetch(e2, p + step < count);
+        e2 = next_entry();
+        process(sb);
+        p0 += step; p += step;
     }
     if (nbuf) flush(nbuf);
 }
@@ -263,8 +275,11 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_leaf_tile_kernel(const LQ*
     struct alignas(16) TVol { VT v; };
     __shared__ TVol s_vol[kPyrWarps][SLOTS][G];
     __shared__ uint2 s_buf[kPyrWarps][32 * G + FLUSH];
+    __shared__ uint32_t s_n[kPyrWarps];                                    // entries buffered per warp
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int slot = lane / G, m = lane % G;
+    if (lane == 0) s_n[w] = 0;
+    __syncwarp();
     const uint32_t n_target = (uint32_t)bvh.ti.n;
     const N* __restrict__ parents = bvh.nodes + bvh.ti.level_start[bvh.ti.levels - 1];
     const uint32_t qb32 = (uint32_t)q_begin, qe32 = (uint32_t)q_end;
@@ -356,72 +371,83 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_leaf_tile_kernel(const LQ*
         }
     };
 
-    // Software pipeline (see pyr_refine_kernel): volumes of step t+1 and the list entry of step t+2 in flight
-    struct Stage { uint32_t qpos, j0; bool q_ok, t_ok; VQ qv; VT tv; };
+    // Software pipeline (see pyr_refine_kernel): volumes of step t+1 and the list entry of step t+2 in flight;
+    // ping-pong stages, loads from clamped positions (q_ok / `allowed` mask what is not real)
+    struct Stage { uint32_t qpos, j0; bool q_ok; VQ qv; VT tv; };
     auto fetch = [&](uint2 pr, bool have) -> Stage {
         Stage sg;
         sg.qpos = (pr.x << kPyrLeafLog) + (uint32_t)m;
         sg.j0 = pr.y << kPyrLeafLog;
         sg.q_ok = have && sg.qpos >= qb32 && sg.qpos < qe32;
-        sg.t_ok = have && sg.j0 + m < n_target;
-        sg.qv = VQ{};
-        sg.tv = VT{};
-        if (sg.q_ok) {
-            const uint2* sp = reinterpret_cast<const uint2*>(qleaves + sg.qpos);
+        {
+            const uint2* sp = reinterpret_cast<const uint2*>(qleaves + min(sg.qpos, qe32 - 1u));
             uint2* dp = reinterpret_cast<uint2*>(&sg.qv);
 #pragma unroll
             for (int k = 0; k < (int)(sizeof(VQ) / 8); ++k) dp[k] = __ldg(sp + k);
         }
-        if (sg.t_ok) {
-            const uint2* sp = reinterpret_cast<const uint2*>(bvh.leaves + sg.j0 + m);
+        {
+            const uint2* sp = reinterpret_cast<const uint2*>(bvh.leaves + min(sg.j0 + (uint32_t)m, n_target - 1u));
             uint2* dp = reinterpret_cast<uint2*>(&sg.tv);
 #pragma unroll
             for (int k = 0; k < (int)(sizeof(VT) / 8); ++k) dp[k] = __ldg(sp + k);
         }
         return sg;
     };
+    volatile uint32_t* s_nv = s_n;
+    auto process = [&](const Stage& cur) {
+        s_vol[w][slot][m].v = cur.tv;
+        __syncwarp();
+        uint32_t hits = 0;
+        if (cur.q_ok) {
+#pragma unroll
+            for (int j = 0; j < G; ++j) if (leaf_contact(cur.qv, s_vol[w][slot][j].v)) hits |= 1u << j;
+            bool edge = cur.j0 + (uint32_t)G > n_target;
+            if constexpr (KIND == kSingle) edge = edge || cur.qpos >= cur.j0;
+            if (edge) {
+                const uint32_t nval = n_target - cur.j0;
+                uint32_t allowed = nval >= (uint32_t)G ? ((1u << G) - 1u) : ((1u << nval) - 1u);
+                if constexpr (KIND == kSingle) {
+                    if (cur.qpos >= cur.j0) {                                  // only leaves strictly right of the query
+                        const uint32_t lo = cur.qpos - cur.j0 + 1u;
+                        allowed &= lo >= (uint32_t)G ? 0u : ~((1u << lo) - 1u);
+                    }
+                }
+                hits &= allowed;
+            }
+        }
+        if (hits) {                                                            // one shared-memory atomic reserves the lane's slots
+            uint32_t wpos = atomicAdd(&s_n[w], (uint32_t)__popc(hits));
+            do {
+                const int j = __ffs(hits) - 1;
+                hits &= hits - 1;
+                s_buf[w][wpos++] = make_uint2(cur.qpos, cur.j0 + (uint32_t)j);
+            } while (hits);
+        }
+        __syncwarp();
+        nbuf = s_nv[w];
+        if (nbuf >= (uint32_t)FLUSH) { flush(nbuf & ~31u); if (lane == 0) s_nv[w] = nbuf; }
+        __syncwarp();
+    };
     uint32_t p = ((uint32_t)blockIdx.x * kPyrWarps + w) * SLOTS + slot;
     uint2 e1 = make_uint2(0u, 0u), e2 = make_uint2(0u, 0u);
     if (p < count) e1 = in.data[p];
     if (p + step < count) e2 = in.data[p + step];
-    Stage cur = fetch(e1, p < count);
-    for (uint32_t p0 = p - slot; p0 < count; p0 += step, p += step) {
-        const Stage nxt = fetch(e2, p + step < count);
-        e2 = make_uint2(0u, 0u);
-        if (p + 2 * step < count && p + 2 * step > p) e2 = in.data[p + 2 * step];
-        const uint32_t qpos = cur.qpos, j0 = cur.j0;
-        const bool q_ok = cur.q_ok;
-        const VQ qv = cur.qv;
-        if (cur.t_ok) s_vol[w][slot][m].v = cur.tv;
-        __syncwarp();
-        uint32_t hits = 0;
-        if (q_ok) {
-            const uint32_t nval = n_target - j0;
-            uint32_t allowed = nval >= (uint32_t)G ? ((1u << G) - 1u) : ((1u << nval) - 1u);
-            if constexpr (KIND == kSingle) {
-                if (qpos >= j0) {                                              // only leaves strictly right of the query
-                    const uint32_t lo = qpos - j0 + 1u;
-                    allowed &= lo >= (uint32_t)G ? 0u : ~((1u << lo) - 1u);
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < G; ++j) hits |= (leaf_contact(qv, s_vol[w][slot][j].v) ? 1u : 0u) << j;
-            hits &= allowed;
-        }
-        cur = nxt;
-        unsigned any = __ballot_sync(0xffffffffu, hits != 0);
-        while (any) {
-            if (hits) {
-                const int j = __ffs(hits) - 1;
-                hits &= hits - 1;
-                s_buf[w][nbuf + __popc(any & ((1u << lane) - 1u))] = make_uint2(qpos, j0 + (uint32_t)j);
-            }
-            nbuf += __popc(any);
-            any = __ballot_sync(0xffffffffu, hits != 0);
-        }
-        __syncwarp();
-        if (nbuf >= (uint32_t)FLUSH) flush(nbuf & ~31u);
-        __syncwarp();
+    auto next_entry = [&]() {
+        uint2 e = make_uint2(0u, 0u);
+        if (p + 2 * step < count && p + 2 * step > p) e = in.data[p + 2 * step];
+        return e;
+    };
+    Stage sa = fetch(e1, p < count), sb;
+    for (uint32_t p0 = p - slot; p0 < count;) {
+        sb = fetch(e2, p + step < count);
+        e2 = next_entry();
+        process(sa);
+        p0 += step; p += step;
+        if (p0 >= count) break;
+        sa = fetch(e2, p + step < count);
+        e2 = next_entry();
+        process(sb);
+        p0 += step; p += step;
     }
     if (nbuf) flush(nbuf);
     if constexpr (MODE == kCount && PMODE == 0) {

@@ -564,14 +564,14 @@ int traverse_tiled(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, con
 }
 
 // ---- pyramid refinement driver (BBox nodes) -----------------------------------------------------------------
-struct PyrPlan { int n; PyrLevel lv[kPyrMaxLevels]; int64_t u_total; };
+struct PyrPlan { int n; PyrLevel lv[kPyrMaxLevels]; int64_t u_total; int64_t t_total; };
 
 // levels from the finest (k = 2) to the top; false if the schedule does not apply (tree too short, the needed
 // tree levels are not built, or the coarsest usable level still has too many groups for an all-pairs start)
 inline bool make_pyr_plan(const TreeInfo& ti, int64_t built_level, int64_t q_begin, int64_t q_count, PyrPlan* plan) {
     const int L = ti.levels;
     const int64_t q_end = q_begin + q_count;
-    plan->n = 0; plan->u_total = 0;
+    plan->n = 0; plan->u_total = 0; plan->t_total = 0;
     for (int k = kPyrLeafLog; plan->n < kPyrMaxLevels; k += kPyrFan) {
         const int tl = L - k;
         if (tl < 1 || tl < built_level) break;
@@ -579,6 +579,8 @@ inline bool make_pyr_plan(const TreeInfo& ti, int64_t built_level, int64_t q_beg
         v.k = k; v.tree_level = tl; v.ntg = ti.level_nreal[tl]; v.tnode0 = ti.level_start[tl];
         v.qg_first = q_begin >> k; v.nqg = ((q_end - 1) >> k) - v.qg_first + 1; v.u_off = plan->u_total;
         plan->u_total += v.nqg;
+        v.t_off = plan->t_total;
+        plan->t_total += (v.ntg + 15) & ~int64_t(7);               // whole groups of 8 + slack, 64-byte aligned starts
         plan->n += 1;
         if (v.nqg <= 2048 && v.ntg <= 2048) return true;          // good top level
     }
@@ -621,6 +623,8 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
     const int64_t q_begin = ta.q_begin, q_end = ta.q_begin + ta.q_count;
     unsigned long long* d_total = (unsigned long long*)(h->d_small + kSmallTotal);
     unsigned long long* d_cnt = (unsigned long long*)(h->d_small + 1536);      // one list counter per level
+    uint32_t* d_tick = (uint32_t*)(h->d_small + 1536 + sizeof(unsigned long long) * kPyrMaxLevels);   // chunk tickets: [l] refine of level l, [16 + k] k-th tile launch
+    int tile_launch = 0;
     const bool unordered = fused || ((flags & IBVH_TRAVERSE_UNORDERED) != 0 && d_contacts != nullptr);
     const bool count_only = !fused && d_contacts == nullptr;
     const int nl = plan.n;
@@ -643,7 +647,12 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
     for (int attempt = 0; attempt < 4; ++attempt) {
         // carve: pyramid boxes + one pair list per level
         unsigned long long cap[kPyrMaxLevels];
-        size_t bytes = ibvh_handle::padded((size_t)plan.u_total * sizeof(N));
+        using VQ = typename LQ::vol_t;
+        using VT = typename LT::vol_t;
+        const bool same_leaves = (const void*)qleaves == (const void*)bvh.leaves && std::is_same<LQ, LT>::value;
+        size_t bytes = ibvh_handle::padded((size_t)plan.u_total * sizeof(UBox<T>)) + ibvh_handle::padded((size_t)plan.t_total * sizeof(N)) +
+                       ibvh_handle::padded((size_t)bvh.ti.n * sizeof(Packed<VT>)) +
+                       (same_leaves ? 0 : ibvh_handle::padded((size_t)n_query_total * sizeof(Packed<VQ>)));
         for (int l = 0; l < nl; ++l) {
             const PyrLevel& v = plan.lv[l];
             unsigned long long c = (unsigned long long)(factor * (double)(v.nqg > v.ntg && KIND != kSingle ? v.nqg : v.nqg)) + 4096ull;
@@ -655,12 +664,24 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
         rc = h->reserve_aux(bytes);
         if (rc != IBVH_OK) return rc;
         char* ap = h->aux;
-        N* U = (N*)ap; ap += ibvh_handle::padded((size_t)plan.u_total * sizeof(N));
+        UBox<T>* U = (UBox<T>*)ap; ap += ibvh_handle::padded((size_t)plan.u_total * sizeof(UBox<T>));
+        N* NT = (N*)ap; ap += ibvh_handle::padded((size_t)plan.t_total * sizeof(N));                    // aligned copy of the target node levels
+        Packed<VT>* PT = (Packed<VT>*)ap; ap += ibvh_handle::padded((size_t)bvh.ti.n * sizeof(Packed<VT>));
+        Packed<VQ>* PQ = (Packed<VQ>*)PT;
+        if (!same_leaves) { PQ = (Packed<VQ>*)ap; ap += ibvh_handle::padded((size_t)n_query_total * sizeof(Packed<VQ>)); }
         PairList lists[kPyrMaxLevels];
         for (int l = 0; l < nl; ++l) { lists[l].data = (uint2*)ap; lists[l].count = d_cnt + l; lists[l].cap = cap[l]; ap += ibvh_handle::padded((size_t)cap[l] * sizeof(uint2)); }
-        IBVH_CUDA_TRY(h, cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * kPyrMaxLevels, st));
+        IBVH_CUDA_TRY(h, cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * kPyrMaxLevels + 128, st));   // list counters + chunk tickets
         IBVH_CUDA_TRY(h, cudaMemsetAsync(d_total, 0, 8, st));      // (fused: the rank-0 counter is rotated by the finish kernel instead)
 
+        // 0. 16-byte aligned records: leaf volumes, and the node levels the refinement reads as targets
+        { ProfScope _ps(h, st, "pyr_pack_volumes_kernel");
+        pyr_pack_volumes_kernel<LT><<<(unsigned)((bvh.ti.n + 255) / 256), 256, 0, st>>>(bvh.leaves, bvh.ti.n, PT);
+        if (!same_leaves) pyr_pack_volumes_kernel<LQ><<<(unsigned)((n_query_total + 255) / 256), 256, 0, st>>>(qleaves, n_query_total, PQ);
+        }
+        IBVH_LAUNCH_CHECK(h, "pyr_pack_volumes_kernel");
+        for (int l = 0; l + 1 < nl; ++l)
+            IBVH_CUDA_TRY(h, cudaMemcpyAsync(NT + plan.lv[l].t_off, bvh.nodes + plan.lv[l].tnode0, (size_t)plan.lv[l].ntg * sizeof(N), cudaMemcpyDeviceToDevice, st));
         // 1. query pyramid
         { ProfScope _ps(h, st, "pyr_leafgroups_kernel");
         pyr_leafgroups_kernel<LQ, T><<<(unsigned)((plan.lv[0].nqg + 255) / 256), 256, 0, st>>>(qleaves, q_begin, q_end < n_query_total ? q_end : n_query_total, plan.lv[0], U);
@@ -685,7 +706,7 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
         // 3. refine down to the 4-leaf groups
         for (int l = nl - 1; l >= 1; --l) {
             { ProfScope _ps(h, st, "pyr_refine_kernel");
-            pyr_refine_kernel<KIND, T><<<grid, kPyrWarps * 32, 0, st>>>(plan.lv[l], plan.lv[l - 1], U, bvh.nodes, lists[l], lists[l - 1]);
+            pyr_refine_kernel<KIND, T><<<grid, kPyrWarps * 32, 0, st>>>(U + plan.lv[l - 1].u_off, NT + plan.lv[l - 1].t_off, (uint32_t)plan.lv[l - 1].qg_first, (uint32_t)plan.lv[l - 1].nqg, (uint32_t)plan.lv[l - 1].ntg, lists[l], lists[l - 1], d_tick + l);
             }
             IBVH_LAUNCH_CHECK(h, "pyr_refine_kernel");
         }
@@ -720,9 +741,9 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
             { ProfScope _ps(h, st, "pyr_leaf_tile_kernel");
             const int big = getenv("IBVH_FUSED_FLUSH") ? atoi(getenv("IBVH_FUSED_FLUSH")) >= 1024 : pa.world >= 4;
             if (big)
-                pyr_leaf_tile_kernel<KIND, kAtomic, 0, LQ, LT, I, 1024><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, capacity, out_total, (I*)nullptr, nullptr, out_ptr, 1);
+                pyr_leaf_tile_kernel<KIND, kAtomic, 0, LQ, LT, I, 1024><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, capacity, out_total, (I*)nullptr, nullptr, out_ptr, 1, d_tick + 16 + (tile_launch++), PQ, PT);
             else
-                pyr_leaf_tile_kernel<KIND, kAtomic, 0, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, capacity, out_total, (I*)nullptr, nullptr, out_ptr, 1);
+                pyr_leaf_tile_kernel<KIND, kAtomic, 0, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, capacity, out_total, (I*)nullptr, nullptr, out_ptr, 1, d_tick + 16 + (tile_launch++), PQ, PT);
             }
             IBVH_LAUNCH_CHECK(h, "pyr_leaf_tile_kernel");
             return fused_finish();
@@ -731,27 +752,27 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
         if (unordered || count_only) {
             if (unordered) {
                 { ProfScope _ps(h, st, "pyr_leaf_tile_kernel");
-                pyr_leaf_tile_kernel<KIND, kAtomic, 0, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, capacity, out_total, (I*)nullptr, nullptr, out_ptr, fused ? 1 : 0);
+                pyr_leaf_tile_kernel<KIND, kAtomic, 0, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, capacity, out_total, (I*)nullptr, nullptr, out_ptr, fused ? 1 : 0, d_tick + 16 + (tile_launch++), PQ, PT);
                 }
             } else if (d_counts) {
                 // count-only call of the ordered protocol: per-query counts + scan (cache2), total from the scan
                 IBVH_CUDA_TRY(h, cudaMemsetAsync(counts, 0, (size_t)ta.q_count * sizeof(I), st));
                 { ProfScope _ps(h, st, "pyr_leaf_tile_kernel");
-                pyr_leaf_tile_kernel<KIND, kCount, 1, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, 0, d_total, counts, nullptr, (IndexPair<I>*)nullptr, 0);
+                pyr_leaf_tile_kernel<KIND, kCount, 1, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, 0, d_total, counts, nullptr, (IndexPair<I>*)nullptr, 0, d_tick + 16 + (tile_launch++), PQ, PT);
                 }
                 IBVH_LAUNCH_CHECK(h, "pyr_leaf_tile_kernel");
                 rc = scan_counts<I>(h, counts, ta.q_count, qsums, d_total, st);
                 if (rc != IBVH_OK) return rc;
             } else {
                 { ProfScope _ps(h, st, "pyr_leaf_tile_kernel");
-                pyr_leaf_tile_kernel<KIND, kCount, 0, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, 0, d_total, (I*)nullptr, nullptr, (IndexPair<I>*)nullptr, 0);
+                pyr_leaf_tile_kernel<KIND, kCount, 0, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, 0, d_total, (I*)nullptr, nullptr, (IndexPair<I>*)nullptr, 0, d_tick + 16 + (tile_launch++), PQ, PT);
                 }
             }
             IBVH_LAUNCH_CHECK(h, "pyr_leaf_tile_kernel");
         } else if (!counts_valid) {
             IBVH_CUDA_TRY(h, cudaMemsetAsync(counts, 0, (size_t)ta.q_count * sizeof(I), st));
             { ProfScope _ps(h, st, "pyr_leaf_tile_kernel");
-            pyr_leaf_tile_kernel<KIND, kCount, 1, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, 0, d_total, counts, nullptr, (IndexPair<I>*)nullptr, 0);
+            pyr_leaf_tile_kernel<KIND, kCount, 1, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, 0, d_total, counts, nullptr, (IndexPair<I>*)nullptr, 0, d_tick + 16 + (tile_launch++), PQ, PT);
             }
             IBVH_LAUNCH_CHECK(h, "pyr_leaf_tile_kernel");
             rc = scan_counts<I>(h, counts, ta.q_count, qsums, d_total, st);
@@ -802,7 +823,7 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
         // ordered write: per-query cursors, then sort each query's handful of hits by target position
         IBVH_CUDA_TRY(h, cudaMemsetAsync(cursors, 0, (size_t)ta.q_count * 4, st));
         { ProfScope _ps(h, st, "pyr_leaf_tile_kernel");
-        pyr_leaf_tile_kernel<KIND, kWrite, 2, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, capacity, d_total, counts, cursors, (IndexPair<I>*)d_contacts, 0);
+        pyr_leaf_tile_kernel<KIND, kWrite, 2, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, capacity, d_total, counts, cursors, (IndexPair<I>*)d_contacts, 0, d_tick + 16 + (tile_launch++), PQ, PT);
         }
         IBVH_LAUNCH_CHECK(h, "pyr_leaf_tile_kernel");
         { ProfScope _ps(h, st, "pyr_fixup_kernel");

@@ -202,11 +202,49 @@ template <class T> struct NodeOps<BSphere<T>> {
 template <class T> IBVH_HD bool iscontact(const BSphere<T>& a, const BSphere<T>& b) {
     return dist3sq(a.x, b.x) <= (a.r + b.r) * (a.r + b.r);
 }
+// Device form of the box test: the six closed comparisons of the reference as ONE predicate chain
+// (setp.and), returning `bit` or 0. nvcc turns the C++ form into 6 FSETP + 6 SEL per test; the chain is
+// 6 FSETP + 1 SEL, and the box tests are what the issue-bound traversal kernels spend their slots on.
+// Ordered comparisons: any NaN makes the test false, exactly like `>=` / `<=`.
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t box_contact_bit(const BBox<float>& a, const BBox<float>& b, uint32_t bit) {
+    uint32_t r;
+    asm("{\n\t.reg .pred p;\n\t"
+        "setp.ge.f32 p, %2, %3;\n\t"
+        "setp.le.and.f32 p, %4, %5, p;\n\t"
+        "setp.ge.and.f32 p, %6, %7, p;\n\t"
+        "setp.le.and.f32 p, %8, %9, p;\n\t"
+        "setp.ge.and.f32 p, %10, %11, p;\n\t"
+        "setp.le.and.f32 p, %12, %13, p;\n\t"
+        "selp.u32 %0, %1, 0, p;\n\t}"
+        : "=r"(r) : "r"(bit), "f"(a.up[0]), "f"(b.lo[0]), "f"(a.lo[0]), "f"(b.up[0]), "f"(a.up[1]), "f"(b.lo[1]), "f"(a.lo[1]), "f"(b.up[1]),
+          "f"(a.up[2]), "f"(b.lo[2]), "f"(a.lo[2]), "f"(b.up[2]));
+    return r;
+}
+__device__ __forceinline__ uint32_t box_contact_bit(const BBox<double>& a, const BBox<double>& b, uint32_t bit) {
+    uint32_t r;
+    asm("{\n\t.reg .pred p;\n\t"
+        "setp.ge.f64 p, %2, %3;\n\t"
+        "setp.le.and.f64 p, %4, %5, p;\n\t"
+        "setp.ge.and.f64 p, %6, %7, p;\n\t"
+        "setp.le.and.f64 p, %8, %9, p;\n\t"
+        "setp.ge.and.f64 p, %10, %11, p;\n\t"
+        "setp.le.and.f64 p, %12, %13, p;\n\t"
+        "selp.u32 %0, %1, 0, p;\n\t}"
+        : "=r"(r) : "r"(bit), "d"(a.up[0]), "d"(b.lo[0]), "d"(a.lo[0]), "d"(b.up[0]), "d"(a.up[1]), "d"(b.lo[1]), "d"(a.lo[1]), "d"(b.up[1]),
+          "d"(a.up[2]), "d"(b.lo[2]), "d"(a.lo[2]), "d"(b.up[2]));
+    return r;
+}
+#endif
 template <class T> IBVH_HD bool iscontact(const BBox<T>& a, const BBox<T>& b) {
+#ifdef __CUDA_ARCH__
+    return box_contact_bit(a, b, 1u) != 0u;
+#else
     // same six closed comparisons as the reference, evaluated without short-circuit branches
     return ((a.up[0] >= b.lo[0]) & (a.lo[0] <= b.up[0])) &
            ((a.up[1] >= b.lo[1]) & (a.lo[1] <= b.up[1])) &
            ((a.up[2] >= b.lo[2]) & (a.lo[2] <= b.up[2]));
+#endif
 }
 
 // ---- isintersection.jl:1-65 --------------------------------------------------------------------------

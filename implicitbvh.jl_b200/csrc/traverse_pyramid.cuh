@@ -37,7 +37,10 @@ constexpr int kPyrLeafLog = 2;              // finest groups: 4 leaves
 #endif
 constexpr int kPyrFan = IBVH_PYR_FAN;       // 2^3 = 8 children per refinement
 constexpr int kPyrMaxLevels = 12;
-constexpr int kPyrFlush = 256;              // buffered entries per list atomic
+#ifndef IBVH_PYR_FLUSH
+#define IBVH_PYR_FLUSH 256
+#endif
+constexpr int kPyrFlush = IBVH_PYR_FLUSH;   // buffered entries per list atomic
 
 struct PyrLevel {
     int32_t k;               // group size 2^k leaves
@@ -47,6 +50,7 @@ struct PyrLevel {
     int64_t qg_first;        // first query group (absolute leaf position >> k)
     int64_t nqg;             // query groups covering the shard
     int64_t u_off;           // offset (in boxes) of this level inside the query-pyramid array
+    int64_t t_off;           // offset (in boxes, multiple of 8) of this level's nodes inside the aligned target copy
 };
 
 struct PairList {
@@ -54,6 +58,13 @@ struct PairList {
     unsigned long long* count;     // device counter (keeps counting past `cap`: tells the host the need)
     unsigned long long cap;
 };
+
+// steps per ticket chunk: up to 32, fewer for short lists so that every resident warp still gets ~4 chunks
+IBVH_D uint32_t pyr_chunk_steps(uint32_t count, int slots) {
+    const uint32_t warps = gridDim.x * (uint32_t)kPyrWarps;
+    uint32_t s = count / ((uint32_t)slots * warps * 4u);
+    return s < 1u ? 1u : (s > 32u ? 32u : s);
+}
 
 IBVH_D void atomic_inc(int32_t* p) { atomicAdd(p, 1); }
 IBVH_D void atomic_inc(int64_t* p) { atomicAdd(reinterpret_cast<unsigned long long*>(p), 1ull); }
@@ -66,10 +77,42 @@ template <class T> IBVH_D BBox<T> empty_box() {
     return b;
 }
 
+// Records the pyramid kernels load with 128-bit accesses (the refine / tile kernels are bound by L1 wavefronts,
+// not by DRAM: AoS structs read as 8-byte pieces at a 24-byte stride cost 3-7x the wavefronts of aligned
+// 16-byte loads). UBox = one query-pyramid box, Packed<V> = one leaf volume, both padded to 16 bytes.
+template <class T> struct alignas(16) UBox { BBox<T> b; };
+template <class V> struct alignas(16) Packed { V v; };
+template <class R> IBVH_D R load16(const R* p) {
+    static_assert(sizeof(R) % 16 == 0, "16-byte records");
+    alignas(16) R out;
+    const uint4* s = reinterpret_cast<const uint4*>(p);
+    uint4* d = reinterpret_cast<uint4*>(&out);
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(R) / 16); ++k) d[k] = __ldg(s + k);
+    return out;
+}
+template <class R> IBVH_D void store16(R* p, const R& v) {
+    const uint4* s = reinterpret_cast<const uint4*>(&v);
+    uint4* d = reinterpret_cast<uint4*>(p);
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(R) / 16); ++k) d[k] = s[k];
+}
+
+// leaf volumes -> 16-byte aligned records (one pass per traversal; 0.07 ms for 10 M sphere leaves)
+template <class L>
+__global__ void __launch_bounds__(256) pyr_pack_volumes_kernel(const L* __restrict__ leaves, int64_t n, Packed<typename L::vol_t>* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    alignas(16) Packed<typename L::vol_t> r;
+    memset(&r, 0, sizeof(r));
+    r.v = load_struct(leaves + i).volume;
+    store16(out + i, r);
+}
+
 // ---- 1. query pyramid ------------------------------------------------------------------------------------
 template <class LQ, class T>
 __global__ void __launch_bounds__(256) pyr_leafgroups_kernel(const LQ* __restrict__ qleaves, int64_t q_begin, int64_t q_end,
-                                                            PyrLevel lv, BBox<T>* __restrict__ U) {
+                                                            PyrLevel lv, UBox<T>* __restrict__ U) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= lv.nqg) return;
     const int64_t q0 = (lv.qg_first + t) << kPyrLeafLog;
@@ -82,10 +125,10 @@ __global__ void __launch_bounds__(256) pyr_leafgroups_kernel(const LQ* __restric
             u = merge(u, NodeOps<BBox<T>>::convert(leaf.volume));
         }
     }
-    U[lv.u_off + t] = u;
+    U[lv.u_off + t].b = u;
 }
 template <class T>
-__global__ void __launch_bounds__(256) pyr_up_kernel(PyrLevel fine, PyrLevel coarse, BBox<T>* __restrict__ U) {
+__global__ void __launch_bounds__(256) pyr_up_kernel(PyrLevel fine, PyrLevel coarse, UBox<T>* __restrict__ U) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= coarse.nqg) return;
     const int64_t c0 = (coarse.qg_first + t) << kPyrFan;
@@ -93,9 +136,9 @@ __global__ void __launch_bounds__(256) pyr_up_kernel(PyrLevel fine, PyrLevel coa
 #pragma unroll
     for (int i = 0; i < (1 << kPyrFan); ++i) {
         int64_t c = c0 + i - fine.qg_first;
-        if (c >= 0 && c < fine.nqg) u = merge(u, load_struct(U + fine.u_off + c));
+        if (c >= 0 && c < fine.nqg) u = merge(u, load16(U + fine.u_off + c).b);
     }
-    U[coarse.u_off + t] = u;
+    U[coarse.u_off + t].b = u;
 }
 
 // warp-aggregated direct append (top kernel)
@@ -114,7 +157,7 @@ IBVH_D void pyr_append_direct(const PairList& out, bool pred, uint2 e) {
 
 // ---- 2. top: all pairs ---------------------------------------------------------------------------------------
 template <int KIND, class T>
-__global__ void __launch_bounds__(256) pyr_top_kernel(PyrLevel lv, const BBox<T>* __restrict__ U, const BBox<T>* __restrict__ nodes, PairList out) {
+__global__ void __launch_bounds__(256) pyr_top_kernel(PyrLevel lv, const UBox<T>* __restrict__ U, const BBox<T>* __restrict__ nodes, PairList out) {
     const int64_t total = lv.nqg * lv.ntg;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t t0 = (int64_t)blockIdx.x * blockDim.x; t0 < total; t0 += stride) {       // warp-uniform trip count
@@ -127,7 +170,7 @@ __global__ void __launch_bounds__(256) pyr_top_kernel(PyrLevel lv, const BBox<T>
             bool ok = true;
             if constexpr (KIND == kSingle) ok = b >= A;           // the target group must reach right of the query group
             if (ok) {
-                BBox<T> u = load_struct(U + lv.u_off + a);
+                BBox<T> u = load16(U + lv.u_off + a).b;
                 BBox<T> nb = load_struct(nodes + lv.tnode0 + b);
                 pred = iscontact(u, nb);
                 e = make_uint2((uint32_t)A, (uint32_t)b);
@@ -145,14 +188,21 @@ template <int CAP> struct WarpBuf {
 };
 
 // ---- 3. refine: (A, B) at group size 2^k -> child pairs at 2^(k-3) ------------------------------------------------
+// Uf: the query-pyramid boxes of the fine level (32-byte records, index = group - f_first).
+// Nf: the fine level's target nodes inside the 64-byte aligned copy (whole groups of F readable), so that the F
+//     children of a target group are one aligned run of 16-byte pieces fetched cooperatively by the slot's lanes.
 template <int KIND, class T>
-__global__ void __launch_bounds__(kPyrWarps * 32) pyr_refine_kernel(PyrLevel coarse, PyrLevel fine, const BBox<T>* __restrict__ U,
-                                                                   const BBox<T>* __restrict__ nodes, PairList in, PairList out) {
+__global__ void __launch_bounds__(kPyrWarps * 32) pyr_refine_kernel(const UBox<T>* __restrict__ Uf, const BBox<T>* __restrict__ Nf,
+                                                                   uint32_t f_first, uint32_t f_nqg, uint32_t f_ntg,
+                                                                   PairList in, PairList out, uint32_t* ticket) {
     using N = BBox<T>;
     constexpr int F = 1 << kPyrFan;          // 8
     constexpr int SLOTS = 32 / F;            // 4 pairs per warp step
-    struct alignas(8) SBox { N b; };
-    __shared__ SBox s_box[kPyrWarps][SLOTS][F + 1];
+    constexpr int PIECES = F * (int)sizeof(N) / 16;                        // 16-byte pieces of the F child boxes of one target group
+    constexpr int ROUNDS = (PIECES + F - 1) / F;
+    constexpr int SLOT_BYTES = F * (int)sizeof(N) + 16;                    // + 16: slots start in different banks
+    static_assert((F * sizeof(N)) % 16 == 0, "child run is a whole number of 16-byte pieces");
+    __shared__ __align__(16) unsigned char s_raw[kPyrWarps][SLOTS][SLOT_BYTES];
     // hit buffer: up to 32*F new entries per step on top of < kPyrFlush pending ones
     __shared__ uint2 s_buf[kPyrWarps][32 * F + kPyrFlush];
     __shared__ uint32_t s_n[kPyrWarps];                                    // entries buffered per warp
@@ -163,10 +213,6 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_refine_kernel(PyrLevel coa
     unsigned long long count64 = *in.count;
     if (count64 > in.cap) count64 = in.cap;
     const uint32_t count = (uint32_t)count64;                              // list sizes are < 2^32 (checked by the host)
-    const uint32_t step = (uint32_t)gridDim.x * kPyrWarps * SLOTS;
-    const uint32_t f_first = (uint32_t)fine.qg_first, f_nqg = (uint32_t)fine.nqg, f_ntg = (uint32_t)fine.ntg;
-    const N* __restrict__ Uf = U + fine.u_off;
-    const N* __restrict__ Nf = nodes + fine.tnode0;
     uint32_t nbuf = 0;
     // flush the n newest buffered entries [nbuf - n, nbuf) with ONE atomic (all warps share one list counter, and
     // same-address atomics are what limits this kernel otherwise) and coalesced 256-byte stores
@@ -181,25 +227,48 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_refine_kernel(PyrLevel coa
     // Software pipeline: while step t is computed, the boxes of step t+1 and the list entry of step t+2 are in flight
     // (the kernel is bound by issue slots: 2x unrolled ping-pong stages instead of copying a stage per step, loads
     // from clamped indices instead of predicated loads + selects — `a_ok` / `allowed` mask what is not real).
-    struct Stage { uint32_t Ac, Bc0; bool a_ok; N u, tb; };
+    struct Stage { uint32_t Ac, Bc0; bool a_ok; UBox<T> u; uint4 tp[ROUNDS]; };
     auto fetch = [&](uint2 pr, bool have) -> Stage {
         Stage sg;
         sg.Ac = (pr.x << kPyrFan) + (uint32_t)i;                           // my child of A (absolute group index, fine level)
         sg.Bc0 = pr.y << kPyrFan;                                          // first child of B
         const uint32_t ua = sg.Ac - f_first;                               // wraps to a huge value if Ac < f_first
         sg.a_ok = have && ua < f_nqg;
-        sg.u = load_struct(Uf + min(ua, f_nqg - 1u));
-        sg.tb = load_struct(Nf + min(sg.Bc0 + (uint32_t)i, f_ntg - 1u));
+        sg.u = load16(Uf + min(ua, f_nqg - 1u));
+        // the 8 lanes of a slot fetch the F child boxes of B as PIECES consecutive 16-byte pieces (the copy is padded
+        // to whole groups, so the run is always readable; boxes past f_ntg are masked by `allowed`)
+        const uint4* run = reinterpret_cast<const uint4*>(Nf + sg.Bc0);
+#pragma unroll
+        for (int r = 0; r < ROUNDS; ++r) {
+            const int pc = r * F + i;
+            sg.tp[r] = make_uint4(0u, 0u, 0u, 0u);
+            if (pc < PIECES) sg.tp[r] = __ldg(run + pc);
+        }
         return sg;
     };
     volatile uint32_t* s_nv = s_n;
     auto process = [&](const Stage& cur) {
-        s_box[w][slot][i].b = cur.tb;
+#pragma unroll
+        for (int r = 0; r < ROUNDS; ++r) {
+            const int pc = r * F + i;
+            if (pc < PIECES) reinterpret_cast<uint4*>(s_raw[w][slot])[pc] = cur.tp[r];
+        }
         __syncwarp();
         uint32_t hits = 0;
         if (cur.a_ok) {
+            // two boxes = three 16-byte shared-memory loads
+            static_assert(F % 2 == 0, "boxes are read in pairs");
 #pragma unroll
-            for (int j = 0; j < F; ++j) if (iscontact(cur.u, s_box[w][slot][j].b)) hits |= 1u << j;
+            for (int j = 0; j < F; j += 2) {
+                struct alignas(16) Two { N a, b; };
+                static_assert(sizeof(Two) % 16 == 0, "pair of boxes");
+                Two two;
+                const uint4* sp = reinterpret_cast<const uint4*>(s_raw[w][slot] + j * sizeof(N));
+                uint4* dp = reinterpret_cast<uint4*>(&two);
+#pragma unroll
+                for (int k = 0; k < (int)(sizeof(Two) / 16); ++k) dp[k] = sp[k];
+                hits |= box_contact_bit(cur.u.b, two.a, 1u << j) | box_contact_bit(cur.u.b, two.b, 1u << (j + 1));
+            }
             bool edge = cur.Bc0 + (uint32_t)F > f_ntg;
             if constexpr (KIND == kSingle) edge = edge || cur.Ac > cur.Bc0;
             if (edge) {
@@ -228,26 +297,39 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_refine_kernel(PyrLevel coa
         if (nbuf >= (uint32_t)kPyrFlush) { flush(nbuf & ~31u); if (lane == 0) s_nv[w] = nbuf; }
         __syncwarp();
     };
-    uint32_t p = ((uint32_t)blockIdx.x * kPyrWarps + w) * SLOTS + slot;
-    uint2 e1 = make_uint2(0u, 0u), e2 = make_uint2(0u, 0u);
-    if (p < count) e1 = in.data[p];
-    if (p + step < count) e2 = in.data[p + step];
-    auto next_entry = [&]() {                                              // entry of the step after the next
-        uint2 e = make_uint2(0u, 0u);
-        if (p + 2 * step < count && p + 2 * step > p) e = in.data[p + 2 * step];
-        return e;
-    };
-    Stage sa = fetch(e1, p < count), sb;
-    for (uint32_t p0 = p - slot; p0 < count;) {
-        sb = fetch(e2, p + step < count);                                  // boxes of the next step
-        e2 = next_entry();
-        process(sa);
-        p0 += step; p += step;
-        if (p0 >= count) break;
-        sa = fetch(e2, p + step < count);
-        e2 = next_entry();
-        process(sb);
-        p0 += step; p += step;
+    // Work distribution: warps draw chunks of consecutive list entries from a ticket counter. A warp's output
+    // flushes then hold the children of CONSECUTIVE parents, so the spatial order of the top-level list survives
+    // from level to level (at flush granularity) and the leaf loads of the tile kernel hit in L1 / L2.
+    const uint32_t chunk = SLOTS * pyr_chunk_steps(count, SLOTS);
+    for (;;) {
+        uint32_t c = 0;
+        if (lane == 0) c = atomicAdd(ticket, 1u);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        const unsigned long long base64 = (unsigned long long)c * chunk;
+        if (base64 >= count) break;
+        const uint32_t base = (uint32_t)base64;
+        const uint32_t end = count - base > chunk ? base + chunk : count;
+        uint32_t p = base + slot;
+        uint2 e1 = make_uint2(0u, 0u), e2 = make_uint2(0u, 0u);
+        if (p < end) e1 = in.data[p];
+        if (p + SLOTS < end) e2 = in.data[p + SLOTS];
+        auto next_entry = [&]() {                                          // entry of the step after the next
+            uint2 e = make_uint2(0u, 0u);
+            if (p + 2 * SLOTS < end) e = in.data[p + 2 * SLOTS];
+            return e;
+        };
+        Stage sa = fetch(e1, p < end), sb;
+        for (uint32_t p0 = base; p0 < end;) {
+            sb = fetch(e2, p + SLOTS < end);                               // boxes of the next step
+            e2 = next_entry();
+            process(sa);
+            p0 += SLOTS; p += SLOTS;
+            if (p0 >= end) break;
+            sa = fetch(e2, p + SLOTS < end);
+            e2 = next_entry();
+            process(sb);
+            p0 += SLOTS; p += SLOTS;
+        }
     }
     if (nbuf) flush(nbuf);
 }
@@ -262,7 +344,10 @@ template <int KIND, int MODE, int PMODE, class LQ, class LT, class I, int FLUSH 
 __global__ void __launch_bounds__(kPyrWarps * 32) pyr_leaf_tile_kernel(const LQ* __restrict__ qleaves, int64_t q_begin, int64_t q_end,
                                                                       DBvh<LT, BBox<typename LT::value_type>> bvh, PairList in, int flip,
                                                                       int64_t capacity, unsigned long long* total,
-                                                                      I* counts, unsigned int* cursors, IndexPair<I>* contacts, int fused) {
+                                                                      I* counts, unsigned int* cursors, IndexPair<I>* contacts, int fused, uint32_t* ticket,
+                                                                      const Packed<typename LQ::vol_t>* __restrict__ pq,
+                                                                      const Packed<typename LT::vol_t>* __restrict__ pt) {
+    // pq / pt: the query / target leaf volumes as 16-byte aligned records (pyr_pack_volumes_kernel)
     // fused != 0 (multi-GPU, atomic mode): `total` is the output-slot counter on rank 0 (peer-mapped, system-scope
     // atomics over NVLink) and `contacts` the NVSwitch multicast alias of every rank's list (multimem.st)
     using T = typename LT::value_type;
@@ -272,8 +357,9 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_leaf_tile_kernel(const LQ*
     constexpr int G = 1 << kPyrLeafLog;      // 4
     constexpr int SLOTS = 32 / G;            // 8 pairs per warp step
     constexpr bool kNeedParent = !std::is_same<VT, N>::value || !std::is_same<VQ, N>::value;   // box leaves: implied by the leaf test
-    struct alignas(16) TVol { VT v; };
-    __shared__ TVol s_vol[kPyrWarps][SLOTS][G];
+    using TVol = Packed<VT>;
+    constexpr int SLOT_BYTES = G * (int)sizeof(TVol) + 16;                 // + 16: the 8 slots start in different banks
+    __shared__ __align__(16) unsigned char s_vraw[kPyrWarps][SLOTS][SLOT_BYTES];
     __shared__ uint2 s_buf[kPyrWarps][32 * G + FLUSH];
     __shared__ uint32_t s_n[kPyrWarps];                                    // entries buffered per warp
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -286,7 +372,6 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_leaf_tile_kernel(const LQ*
     unsigned long long count64 = *in.count;
     if (count64 > in.cap) count64 = in.cap;
     const uint32_t count = (uint32_t)count64;
-    const uint32_t step = (uint32_t)gridDim.x * kPyrWarps * SLOTS;
     uint32_t nbuf = 0;
     unsigned long long ncount = 0;
 
@@ -303,12 +388,8 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_leaf_tile_kernel(const LQ*
             bool ok = mine;
             if constexpr (kNeedParent) {
                 if (mine) {
-                    VQ qv;
-                    const uint2* sp = reinterpret_cast<const uint2*>(qleaves + e.x);
-                    uint2* dp = reinterpret_cast<uint2*>(&qv);
-#pragma unroll
-                    for (int k = 0; k < (int)(sizeof(VQ) / 8); ++k) dp[k] = __ldg(sp + k);
-                    ok = iscontact(NodeOps<N>::convert(qv), load_struct(parents + (e.y >> 1)));
+                    const Packed<VQ> qv = load16(pq + e.x);
+                    ok = iscontact(NodeOps<N>::convert(qv.v), load_struct(parents + (e.y >> 1)));
                 }
             }
             if constexpr (PMODE == 1) {
@@ -373,34 +454,31 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_leaf_tile_kernel(const LQ*
 
     // Software pipeline (see pyr_refine_kernel): volumes of step t+1 and the list entry of step t+2 in flight;
     // ping-pong stages, loads from clamped positions (q_ok / `allowed` mask what is not real)
-    struct Stage { uint32_t qpos, j0; bool q_ok; VQ qv; VT tv; };
+    struct Stage { uint32_t qpos, j0; bool q_ok; Packed<VQ> qv; Packed<VT> tv; };
     auto fetch = [&](uint2 pr, bool have) -> Stage {
         Stage sg;
         sg.qpos = (pr.x << kPyrLeafLog) + (uint32_t)m;
         sg.j0 = pr.y << kPyrLeafLog;
         sg.q_ok = have && sg.qpos >= qb32 && sg.qpos < qe32;
-        {
-            const uint2* sp = reinterpret_cast<const uint2*>(qleaves + min(sg.qpos, qe32 - 1u));
-            uint2* dp = reinterpret_cast<uint2*>(&sg.qv);
-#pragma unroll
-            for (int k = 0; k < (int)(sizeof(VQ) / 8); ++k) dp[k] = __ldg(sp + k);
-        }
-        {
-            const uint2* sp = reinterpret_cast<const uint2*>(bvh.leaves + min(sg.j0 + (uint32_t)m, n_target - 1u));
-            uint2* dp = reinterpret_cast<uint2*>(&sg.tv);
-#pragma unroll
-            for (int k = 0; k < (int)(sizeof(VT) / 8); ++k) dp[k] = __ldg(sp + k);
-        }
+        sg.qv = load16(pq + min(sg.qpos, qe32 - 1u));
+        sg.tv = load16(pt + min(sg.j0 + (uint32_t)m, n_target - 1u));
         return sg;
     };
     volatile uint32_t* s_nv = s_n;
     auto process = [&](const Stage& cur) {
-        s_vol[w][slot][m].v = cur.tv;
+        store16(reinterpret_cast<TVol*>(s_vraw[w][slot]) + m, cur.tv);
         __syncwarp();
         uint32_t hits = 0;
         if (cur.q_ok) {
 #pragma unroll
-            for (int j = 0; j < G; ++j) if (leaf_contact(cur.qv, s_vol[w][slot][j].v)) hits |= 1u << j;
+            for (int j = 0; j < G; ++j) {
+                alignas(16) TVol tv;
+                const uint4* sp = reinterpret_cast<const uint4*>(reinterpret_cast<const TVol*>(s_vraw[w][slot]) + j);
+                uint4* dp = reinterpret_cast<uint4*>(&tv);
+#pragma unroll
+                for (int k = 0; k < (int)(sizeof(TVol) / 16); ++k) dp[k] = sp[k];
+                if (leaf_contact(cur.qv.v, tv.v)) hits |= 1u << j;
+            }
             bool edge = cur.j0 + (uint32_t)G > n_target;
             if constexpr (KIND == kSingle) edge = edge || cur.qpos >= cur.j0;
             if (edge) {
@@ -428,26 +506,36 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_leaf_tile_kernel(const LQ*
         if (nbuf >= (uint32_t)FLUSH) { flush(nbuf & ~31u); if (lane == 0) s_nv[w] = nbuf; }
         __syncwarp();
     };
-    uint32_t p = ((uint32_t)blockIdx.x * kPyrWarps + w) * SLOTS + slot;
-    uint2 e1 = make_uint2(0u, 0u), e2 = make_uint2(0u, 0u);
-    if (p < count) e1 = in.data[p];
-    if (p + step < count) e2 = in.data[p + step];
-    auto next_entry = [&]() {
-        uint2 e = make_uint2(0u, 0u);
-        if (p + 2 * step < count && p + 2 * step > p) e = in.data[p + 2 * step];
-        return e;
-    };
-    Stage sa = fetch(e1, p < count), sb;
-    for (uint32_t p0 = p - slot; p0 < count;) {
-        sb = fetch(e2, p + step < count);
-        e2 = next_entry();
-        process(sa);
-        p0 += step; p += step;
-        if (p0 >= count) break;
-        sa = fetch(e2, p + step < count);
-        e2 = next_entry();
-        process(sb);
-        p0 += step; p += step;
+    const uint32_t chunk = SLOTS * pyr_chunk_steps(count, SLOTS);        // see pyr_refine_kernel
+    for (;;) {
+        uint32_t c = 0;
+        if (lane == 0) c = atomicAdd(ticket, 1u);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        const unsigned long long base64 = (unsigned long long)c * chunk;
+        if (base64 >= count) break;
+        const uint32_t base = (uint32_t)base64;
+        const uint32_t end = count - base > chunk ? base + chunk : count;
+        uint32_t p = base + slot;
+        uint2 e1 = make_uint2(0u, 0u), e2 = make_uint2(0u, 0u);
+        if (p < end) e1 = in.data[p];
+        if (p + SLOTS < end) e2 = in.data[p + SLOTS];
+        auto next_entry = [&]() {
+            uint2 e = make_uint2(0u, 0u);
+            if (p + 2 * SLOTS < end) e = in.data[p + 2 * SLOTS];
+            return e;
+        };
+        Stage sa = fetch(e1, p < end), sb;
+        for (uint32_t p0 = base; p0 < end;) {
+            sb = fetch(e2, p + SLOTS < end);
+            e2 = next_entry();
+            process(sa);
+            p0 += SLOTS; p += SLOTS;
+            if (p0 >= end) break;
+            sa = fetch(e2, p + SLOTS < end);
+            e2 = next_entry();
+            process(sb);
+            p0 += SLOTS; p += SLOTS;
+        }
     }
     if (nbuf) flush(nbuf);
     if constexpr (MODE == kCount && PMODE == 0) {

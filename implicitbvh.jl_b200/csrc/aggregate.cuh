@@ -18,16 +18,16 @@ namespace ibvh {
 // kernel) or a raw volume (wrap path: index = original position + 1, build.jl:345-349).
 template <class L, class SRC> struct GatherSrc;
 template <class L> struct GatherSrc<L, L> {
-    static IBVH_D Words<L> make(const L* src, uint32_t p, typename L::mor_t key) {
+    static IBVH_D Words<L> make(const L* src, uint32_t p, typename L::mor_t key, int = 8) {
         Words<L> wv = load_words(src + p);
         words_set_morton<L>(wv, key);
         return wv;
     }
 };
 template <class L> struct GatherSrc<L, typename L::vol_t> {
-    static IBVH_D Words<L> make(const typename L::vol_t* src, uint32_t p, typename L::mor_t key) {
+    static IBVH_D Words<L> make(const typename L::vol_t* src, uint32_t p, typename L::mor_t key, int vec = 4) {
         Words<L> wv = zero_words<L>();
-        words_set_volume<L>(wv, src[p]);
+        words_set_volume<L>(wv, load_volume(src + p, vec));
         words_set_index<L>(wv, (typename L::idx_t)(p + 1u));
         words_set_morton<L>(wv, key);
         return wv;
@@ -39,7 +39,7 @@ template <class L> struct GatherSrc<L, typename L::vol_t> {
 // one extra coalesced read of the leaves, but neither kernel waits on the other's latency inside a CTA.
 template <class L, class SRC>
 __global__ void __launch_bounds__(256) gather_kernel(const SRC* __restrict__ src, const uint32_t* __restrict__ perm,
-                                                    const typename L::mor_t* __restrict__ keys_sorted, L* __restrict__ leaves, int64_t n) {
+                                                    const typename L::mor_t* __restrict__ keys_sorted, L* __restrict__ leaves, int64_t n, int vec) {
     constexpr int PER = 4;
     const int64_t base = ((int64_t)blockIdx.x * blockDim.x) * PER + threadIdx.x;
     uint32_t pp[PER];
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256) gather_kernel(const SRC* __restrict__ src
 #pragma unroll
     for (int u = 0; u < PER; ++u) {
         const int64_t i = base + (int64_t)u * blockDim.x;
-        if (i < n) wv[u] = GatherSrc<L, SRC>::make(src, pp[u], kk[u]);
+        if (i < n) wv[u] = GatherSrc<L, SRC>::make(src, pp[u], kk[u], vec);
     }
 #pragma unroll
     for (int u = 0; u < PER; ++u) {

@@ -286,8 +286,10 @@ int build_impl(ibvh_handle* h, const void* d_volumes, void* d_leaves, int64_t n,
         // gather (random reads, full occupancy) then tile merge from the sorted leaves (coalesced)
         const unsigned gb = (unsigned)((n + 1023) / 1024);
         { ProfScope _ps(h, st, "gather_kernel");
-        if (wrap) gather_kernel<L, V><<<gb, 256, 0, st>>>((const V*)d_volumes, perm, keys_sorted, (L*)d_leaves, n);
-        else gather_kernel<L, L><<<gb, 256, 0, st>>>((const L*)s.copy, perm, keys_sorted, (L*)d_leaves, n);
+        const uintptr_t va = (uintptr_t)d_volumes;
+        const int vec = va % 16 == 0 ? 16 : (va % 8 == 0 ? 8 : 4);
+        if (wrap) gather_kernel<L, V><<<gb, 256, 0, st>>>((const V*)d_volumes, perm, keys_sorted, (L*)d_leaves, n, vec);
+        else gather_kernel<L, L><<<gb, 256, 0, st>>>((const L*)s.copy, perm, keys_sorted, (L*)d_leaves, n, 8);
         }
         IBVH_LAUNCH_CHECK(h, "gather_kernel");
         rc = launch_gather_merge<L, L, N, false>(h, (const L*)nullptr, nullptr, nullptr, (L*)d_leaves, (N*)d_nodes, ti, stop_level, st);

@@ -79,6 +79,30 @@ template <class L> IBVH_D void words_set_morton(Words<L>& v, typename L::mor_t x
     memcpy(reinterpret_cast<char*>(v.w) + offsetof(L, morton), &x, sizeof(x));
 }
 
+// One raw volume with the widest loads its size and the array's alignment allow (`vec` = 16, 8 or 4, chosen by the
+// host from the pointer): a struct of floats only promises 4-byte alignment, and copying it into the leaf words
+// through memcpy made nvcc emit one LDG.U8 per byte — 16 loads per sphere.
+template <class V> IBVH_D V load_volume(const V* p, int vec) {
+    alignas(16) V x;
+    if (sizeof(V) % 16 == 0 && vec == 16) {
+        const uint4* s = reinterpret_cast<const uint4*>(p);
+        uint4* d = reinterpret_cast<uint4*>(&x);
+#pragma unroll
+        for (int k = 0; k < (int)(sizeof(V) / 16); ++k) d[k] = __ldg(s + k);
+    } else if (sizeof(V) % 8 == 0 && vec >= 8) {
+        const uint2* s = reinterpret_cast<const uint2*>(p);
+        uint2* d = reinterpret_cast<uint2*>(&x);
+#pragma unroll
+        for (int k = 0; k < (int)(sizeof(V) / 8); ++k) d[k] = __ldg(s + k);
+    } else {
+        const uint32_t* s = reinterpret_cast<const uint32_t*>(p);
+        uint32_t* d = reinterpret_cast<uint32_t*>(&x);
+#pragma unroll
+        for (int k = 0; k < (int)(sizeof(V) / 4); ++k) d[k] = __ldg(s + k);
+    }
+    return x;
+}
+
 // ---- utils.jl:163-181 -------------------------------------------------------------------------
 template <class T> IBVH_HD T minimum2(T a, T b) { return a < b ? a : b; }
 template <class T> IBVH_HD T maximum2(T a, T b) { return a > b ? a : b; }

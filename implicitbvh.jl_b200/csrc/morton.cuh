@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(256) wrap_kernel(const typename L::vol_t* __re
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
         Words<L> wv = zero_words<L>();            // padding bytes are zero, deterministically
-        words_set_volume<L>(wv, vols[i]);
+        words_set_volume<L>(wv, load_volume(vols + i, 4));
         words_set_index<L>(wv, (typename L::idx_t)(i + 1));
         store_words(leaves + i, wv);
     }

@@ -653,8 +653,8 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
         using VT = typename LT::vol_t;
         const bool same_leaves = (const void*)qleaves == (const void*)bvh.leaves && std::is_same<LQ, LT>::value;
         size_t bytes = ibvh_handle::padded((size_t)plan.u_total * sizeof(UBox<T>)) + ibvh_handle::padded((size_t)plan.t_total * sizeof(N)) +
-                       ibvh_handle::padded((size_t)bvh.ti.n * sizeof(Packed<VT>)) +
-                       (same_leaves ? 0 : ibvh_handle::padded((size_t)n_query_total * sizeof(Packed<VQ>)));
+                       ibvh_handle::padded((size_t)(bvh.ti.n + 8) * sizeof(Packed<VT>)) +
+                       (same_leaves ? 0 : ibvh_handle::padded((size_t)(n_query_total + 8) * sizeof(Packed<VQ>)));
         for (int l = 0; l < nl; ++l) {
             const PyrLevel& v = plan.lv[l];
             unsigned long long c = (unsigned long long)(factor * (double)(v.nqg > v.ntg && KIND != kSingle ? v.nqg : v.nqg)) + 4096ull;
@@ -668,9 +668,9 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
         char* ap = h->aux;
         UBox<T>* U = (UBox<T>*)ap; ap += ibvh_handle::padded((size_t)plan.u_total * sizeof(UBox<T>));
         N* NT = (N*)ap; ap += ibvh_handle::padded((size_t)plan.t_total * sizeof(N));                    // aligned copy of the target node levels
-        Packed<VT>* PT = (Packed<VT>*)ap; ap += ibvh_handle::padded((size_t)bvh.ti.n * sizeof(Packed<VT>));
+        Packed<VT>* PT = (Packed<VT>*)ap; ap += ibvh_handle::padded((size_t)(bvh.ti.n + 8) * sizeof(Packed<VT>));
         Packed<VQ>* PQ = (Packed<VQ>*)PT;
-        if (!same_leaves) { PQ = (Packed<VQ>*)ap; ap += ibvh_handle::padded((size_t)n_query_total * sizeof(Packed<VQ>)); }
+        if (!same_leaves) { PQ = (Packed<VQ>*)ap; ap += ibvh_handle::padded((size_t)(n_query_total + 8) * sizeof(Packed<VQ>)); }
         PairList lists[kPyrMaxLevels];
         for (int l = 0; l < nl; ++l) { lists[l].data = (uint2*)ap; lists[l].count = d_cnt + l; lists[l].cap = cap[l]; ap += ibvh_handle::padded((size_t)cap[l] * sizeof(uint2)); }
         IBVH_CUDA_TRY(h, cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * kPyrMaxLevels + 128, st));   // list counters + chunk tickets
@@ -678,8 +678,8 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
 
         // 0. 16-byte aligned records: leaf volumes, and the node levels the refinement reads as targets
         { ProfScope _ps(h, st, "pyr_pack_volumes_kernel");
-        pyr_pack_volumes_kernel<LT><<<(unsigned)((bvh.ti.n + 255) / 256), 256, 0, st>>>(bvh.leaves, bvh.ti.n, PT);
-        if (!same_leaves) pyr_pack_volumes_kernel<LQ><<<(unsigned)((n_query_total + 255) / 256), 256, 0, st>>>(qleaves, n_query_total, PQ);
+        pyr_pack_volumes_kernel<LT><<<(unsigned)((bvh.ti.n + 8 + 255) / 256), 256, 0, st>>>(bvh.leaves, bvh.ti.n, bvh.ti.n + 8, PT);
+        if (!same_leaves) pyr_pack_volumes_kernel<LQ><<<(unsigned)((n_query_total + 8 + 255) / 256), 256, 0, st>>>(qleaves, n_query_total, n_query_total + 8, PQ);
         }
         IBVH_LAUNCH_CHECK(h, "pyr_pack_volumes_kernel");
         for (int l = 0; l + 1 < nl; ++l)
@@ -741,9 +741,9 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
                 h->last_stats[3] = nl;
             }
             { ProfScope _ps(h, st, "pyr_leaf_tile_kernel");
-            const int big = getenv("IBVH_FUSED_FLUSH") ? atoi(getenv("IBVH_FUSED_FLUSH")) >= 1024 : pa.world >= 4;
+            const int big = getenv("IBVH_FUSED_FLUSH") ? atoi(getenv("IBVH_FUSED_FLUSH")) >= 512 : pa.world >= 4;
             if (big)
-                pyr_leaf_tile_kernel<KIND, kAtomic, 0, LQ, LT, I, 1024><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, capacity, out_total, (I*)nullptr, nullptr, out_ptr, 1, d_tick + 16 + (tile_launch++), PQ, PT);
+                pyr_leaf_tile_kernel<KIND, kAtomic, 0, LQ, LT, I, 512><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, capacity, out_total, (I*)nullptr, nullptr, out_ptr, 1, d_tick + 16 + (tile_launch++), PQ, PT);
             else
                 pyr_leaf_tile_kernel<KIND, kAtomic, 0, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, capacity, out_total, (I*)nullptr, nullptr, out_ptr, 1, d_tick + 16 + (tile_launch++), PQ, PT);
             }

@@ -99,13 +99,19 @@ template <class R> IBVH_D void store16(R* p, const R& v) {
 }
 
 // leaf volumes -> 16-byte aligned records (one pass per traversal; 0.07 ms for 10 M sphere leaves)
+// Records [n, n_pad) are all-ones bit patterns = NaN volumes: every comparison with them is false, so the tile
+// kernel needs no bounds masks on the target side.
 template <class L>
-__global__ void __launch_bounds__(256) pyr_pack_volumes_kernel(const L* __restrict__ leaves, int64_t n, Packed<typename L::vol_t>* __restrict__ out) {
+__global__ void __launch_bounds__(256) pyr_pack_volumes_kernel(const L* __restrict__ leaves, int64_t n, int64_t n_pad, Packed<typename L::vol_t>* __restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= n_pad) return;
     alignas(16) Packed<typename L::vol_t> r;
-    memset(&r, 0, sizeof(r));
-    r.v = load_struct(leaves + i).volume;
+    if (i < n) {
+        memset(&r, 0, sizeof(r));
+        r.v = load_struct(leaves + i).volume;
+    } else {
+        memset(&r, 0xFF, sizeof(r));
+    }
     store16(out + i, r);
 }
 
@@ -338,7 +344,7 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_refine_kernel(const UBox<T
 // MODE kAtomic: append contacts (unordered). kCount: only add the number of contacts to *total.
 // PMODE (ordered protocol): 0 = none; 1 = count per query (atomicAdd counts[qi]); 2 = write (qpos, tpos) into the
 // query's segment via a per-query cursor (fixed up into reference order by pyr_fixup_kernel).
-// FLUSH: buffered hits per output-slot reservation. The fused multi-GPU mode on >= 4 ranks uses 1024: every
+// FLUSH: buffered hits per output-slot reservation. The fused multi-GPU mode on >= 4 ranks uses 512: every
 // reservation is a system-scope atomic on ONE counter of rank 0, which sustains ~190 M/s in total.
 template <int KIND, int MODE, int PMODE, class LQ, class LT, class I, int FLUSH = kPyrFlush>
 __global__ void __launch_bounds__(kPyrWarps * 32) pyr_leaf_tile_kernel(const LQ* __restrict__ qleaves, int64_t q_begin, int64_t q_end,
@@ -354,16 +360,26 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_leaf_tile_kernel(const LQ*
     using N = BBox<T>;
     using VT = typename LT::vol_t;
     using VQ = typename LQ::vol_t;
+    // Register tile: every lane tests QPL = 2 query leaves against the G = 4 target leaves of its pair, so a pair
+    // takes 2 lanes and a warp step covers 16 pairs. The kernel is bound by the LSU data pipe (shared-memory
+    // wavefronts) and by issue slots, and both costs per pair halve against one query per lane: the target
+    // volumes read from shared memory serve two queries, the per-step overhead serves 16 pairs.
     constexpr int G = 1 << kPyrLeafLog;      // 4
-    constexpr int SLOTS = 32 / G;            // 8 pairs per warp step
+    constexpr int QPL = 2;                   // query leaves per lane
+    constexpr int LPP = G / QPL;             // lanes per pair
+    constexpr int SLOTS = 32 / LPP;          // 16 pairs per warp step
     constexpr bool kNeedParent = !std::is_same<VT, N>::value || !std::is_same<VQ, N>::value;   // box leaves: implied by the leaf test
     using TVol = Packed<VT>;
-    constexpr int SLOT_BYTES = G * (int)sizeof(TVol) + 16;                 // + 16: the 8 slots start in different banks
-    __shared__ __align__(16) unsigned char s_vraw[kPyrWarps][SLOTS][SLOT_BYTES];
-    __shared__ uint2 s_buf[kPyrWarps][32 * G + FLUSH];
+    constexpr int TPIECES = G * (int)sizeof(TVol) / 16;                    // 16-byte pieces of one target group
+    constexpr int PPL = TPIECES / LPP;                                     // pieces copied per lane
+    static_assert(TPIECES % LPP == 0, "pieces split evenly over the lanes of a pair");
+    constexpr int SLOT_BYTES = G * (int)sizeof(TVol) + 16;                 // + 16: neighbouring slots start in different banks
+    // target volumes of the current and the next step (cp.async double buffer)
+    __shared__ __align__(16) unsigned char s_vraw[kPyrWarps][2][SLOTS][SLOT_BYTES];
+    __shared__ uint2 s_buf[kPyrWarps][32 * G + FLUSH];                     // one query per lane appends <= 32 * G entries at a time
     __shared__ uint32_t s_n[kPyrWarps];                                    // entries buffered per warp
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int slot = lane / G, m = lane % G;
+    const int slot = lane / LPP, i = lane % LPP;
     if (lane == 0) s_n[w] = 0;
     __syncwarp();
     const uint32_t n_target = (uint32_t)bvh.ti.n;
@@ -452,59 +468,76 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_leaf_tile_kernel(const LQ*
         }
     };
 
-    // Software pipeline (see pyr_refine_kernel): volumes of step t+1 and the list entry of step t+2 in flight;
-    // ping-pong stages, loads from clamped positions (q_ok / `allowed` mask what is not real)
-    struct Stage { uint32_t qpos, j0; bool q_ok; Packed<VQ> qv; Packed<VT> tv; };
-    auto fetch = [&](uint2 pr, bool have) -> Stage {
+    // Software pipeline: the target volumes of step t+1 travel global -> shared with cp.async (no registers), the
+    // query volumes of step t+1 and the list entry of step t+2 are loaded into registers while step t is computed.
+    struct Stage { uint32_t qpos0, j0, have; Packed<VQ> q[QPL]; };
+    auto fetch = [&](uint2 pr, bool have, int buf) -> Stage {
         Stage sg;
-        sg.qpos = (pr.x << kPyrLeafLog) + (uint32_t)m;
+        sg.qpos0 = pr.x << kPyrLeafLog;
         sg.j0 = pr.y << kPyrLeafLog;
-        sg.q_ok = have && sg.qpos >= qb32 && sg.qpos < qe32;
-        sg.qv = load16(pq + min(sg.qpos, qe32 - 1u));
-        sg.tv = load16(pt + min(sg.j0 + (uint32_t)m, n_target - 1u));
+        sg.have = have ? 1u : 0u;
+#pragma unroll
+        for (int k = 0; k < QPL; ++k) sg.q[k] = load16(pq + sg.qpos0 + (uint32_t)(QPL * i + k));
+        const uint4* src = reinterpret_cast<const uint4*>(pt + sg.j0) + PPL * i;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_vraw[w][buf][slot]) + 16u * (uint32_t)(PPL * i);
+#pragma unroll
+        for (int k = 0; k < PPL; ++k)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * k), "l"(src + k) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
         return sg;
     };
     volatile uint32_t* s_nv = s_n;
-    auto process = [&](const Stage& cur) {
-        store16(reinterpret_cast<TVol*>(s_vraw[w][slot]) + m, cur.tv);
-        __syncwarp();
-        uint32_t hits = 0;
-        if (cur.q_ok) {
-#pragma unroll
-            for (int j = 0; j < G; ++j) {
-                alignas(16) TVol tv;
-                const uint4* sp = reinterpret_cast<const uint4*>(reinterpret_cast<const TVol*>(s_vraw[w][slot]) + j);
-                uint4* dp = reinterpret_cast<uint4*>(&tv);
-#pragma unroll
-                for (int k = 0; k < (int)(sizeof(TVol) / 16); ++k) dp[k] = sp[k];
-                if (leaf_contact(cur.qv.v, tv.v)) hits |= 1u << j;
-            }
-            bool edge = cur.j0 + (uint32_t)G > n_target;
-            if constexpr (KIND == kSingle) edge = edge || cur.qpos >= cur.j0;
-            if (edge) {
-                const uint32_t nval = n_target - cur.j0;
-                uint32_t allowed = nval >= (uint32_t)G ? ((1u << G) - 1u) : ((1u << nval) - 1u);
-                if constexpr (KIND == kSingle) {
-                    if (cur.qpos >= cur.j0) {                                  // only leaves strictly right of the query
-                        const uint32_t lo = cur.qpos - cur.j0 + 1u;
-                        allowed &= lo >= (uint32_t)G ? 0u : ~((1u << lo) - 1u);
-                    }
-                }
-                hits &= allowed;
-            }
-        }
+    auto append = [&](uint32_t hits, uint32_t qp, uint32_t j0) {
         if (hits) {                                                            // one shared-memory atomic reserves the lane's slots
             uint32_t wpos = atomicAdd(&s_n[w], (uint32_t)__popc(hits));
             do {
                 const int j = __ffs(hits) - 1;
                 hits &= hits - 1;
-                s_buf[w][wpos++] = make_uint2(cur.qpos, cur.j0 + (uint32_t)j);
+                s_buf[w][wpos++] = make_uint2(qp, j0 + (uint32_t)j);
             } while (hits);
         }
         __syncwarp();
         nbuf = s_nv[w];
         if (nbuf >= (uint32_t)FLUSH) { flush(nbuf & ~31u); if (lane == 0) s_nv[w] = nbuf; }
         __syncwarp();
+    };
+    auto process = [&](const Stage& cur, int buf) {
+        asm volatile("cp.async.wait_group 1;" ::: "memory");                   // this step's targets have landed (next step's may be in flight)
+        __syncwarp();
+        uint32_t hits[QPL];
+#pragma unroll
+        for (int k = 0; k < QPL; ++k) hits[k] = 0;
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            alignas(16) TVol tv;
+            const uint4* sp = reinterpret_cast<const uint4*>(s_vraw[w][buf][slot] + j * sizeof(TVol));
+            uint4* dp = reinterpret_cast<uint4*>(&tv);
+#pragma unroll
+            for (int k = 0; k < (int)(sizeof(TVol) / 16); ++k) dp[k] = sp[k];
+#pragma unroll
+            for (int k = 0; k < QPL; ++k) if (leaf_contact(cur.q[k].v, tv.v)) hits[k] |= 1u << j;
+        }
+        const uint32_t qp0 = cur.qpos0 + (uint32_t)(QPL * i);
+        // rare masks: tail lanes of a chunk, query groups cut by the shard range, and (single tree) the diagonal
+        // tile, where only targets strictly right of the query count. Targets past the end are NaN padding.
+        bool edge = !cur.have || cur.qpos0 < qb32 || cur.qpos0 + (uint32_t)G > qe32;
+        if constexpr (KIND == kSingle) edge = edge || cur.qpos0 + (uint32_t)G > cur.j0;
+        if (edge) {
+#pragma unroll
+            for (int k = 0; k < QPL; ++k) {
+                const uint32_t qp = qp0 + (uint32_t)k;
+                uint32_t allowed = (cur.have && qp >= qb32 && qp < qe32) ? ((1u << G) - 1u) : 0u;
+                if constexpr (KIND == kSingle) {
+                    if (qp >= cur.j0) {                                        // only leaves strictly right of the query
+                        const uint32_t lo = qp - cur.j0 + 1u;
+                        allowed &= lo >= (uint32_t)G ? 0u : ~((1u << lo) - 1u);
+                    }
+                }
+                hits[k] &= allowed;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < QPL; ++k) append(hits[k], qp0 + (uint32_t)k, cur.j0);
     };
     const uint32_t chunk = SLOTS * pyr_chunk_steps(count, SLOTS);        // see pyr_refine_kernel
     for (;;) {
@@ -515,6 +548,8 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_leaf_tile_kernel(const LQ*
         if (base64 >= count) break;
         const uint32_t base = (uint32_t)base64;
         const uint32_t end = count - base > chunk ? base + chunk : count;
+        asm volatile("cp.async.wait_all;" ::: "memory");                       // the previous chunk's look-ahead copy is done
+        __syncwarp();
         uint32_t p = base + slot;
         uint2 e1 = make_uint2(0u, 0u), e2 = make_uint2(0u, 0u);
         if (p < end) e1 = in.data[p];
@@ -524,19 +559,20 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_leaf_tile_kernel(const LQ*
             if (p + 2 * SLOTS < end) e = in.data[p + 2 * SLOTS];
             return e;
         };
-        Stage sa = fetch(e1, p < end), sb;
+        Stage sa = fetch(e1, p < end, 0), sb;
         for (uint32_t p0 = base; p0 < end;) {
-            sb = fetch(e2, p + SLOTS < end);
+            sb = fetch(e2, p + SLOTS < end, 1);
             e2 = next_entry();
-            process(sa);
+            process(sa, 0);
             p0 += SLOTS; p += SLOTS;
             if (p0 >= end) break;
-            sa = fetch(e2, p + SLOTS < end);
+            sa = fetch(e2, p + SLOTS < end, 0);
             e2 = next_entry();
-            process(sb);
+            process(sb, 1);
             p0 += SLOTS; p += SLOTS;
         }
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
     if (nbuf) flush(nbuf);
     if constexpr (MODE == kCount && PMODE == 0) {
         if (lane == 0 && ncount) atomicAdd(total, ncount);

@@ -743,7 +743,7 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
             { ProfScope _ps(h, st, "pyr_leaf_tile_kernel");
             const int big = getenv("IBVH_FUSED_FLUSH") ? atoi(getenv("IBVH_FUSED_FLUSH")) >= 512 : pa.world >= 4;
             if (big)
-                pyr_leaf_tile_kernel<KIND, kAtomic, 0, LQ, LT, I, 512><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, capacity, out_total, (I*)nullptr, nullptr, out_ptr, 1, d_tick + 16 + (tile_launch++), PQ, PT);
+                pyr_leaf_tile_kernel<KIND, kAtomic, 0, LQ, LT, I, (sizeof(typename LT::vol_t) > 32 ? 256 : 512)><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, capacity, out_total, (I*)nullptr, nullptr, out_ptr, 1, d_tick + 16 + (tile_launch++), PQ, PT);
             else
                 pyr_leaf_tile_kernel<KIND, kAtomic, 0, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, capacity, out_total, (I*)nullptr, nullptr, out_ptr, 1, d_tick + 16 + (tile_launch++), PQ, PT);
             }

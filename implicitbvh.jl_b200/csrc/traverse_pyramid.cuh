@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_leaf_tile_kernel(const LQ*
     constexpr int SLOT_BYTES = G * (int)sizeof(TVol) + 16;                 // + 16: neighbouring slots start in different banks
     // target volumes of the current and the next step (cp.async double buffer)
     __shared__ __align__(16) unsigned char s_vraw[kPyrWarps][2][SLOTS][SLOT_BYTES];
-    __shared__ uint2 s_buf[kPyrWarps][32 * G + FLUSH];                     // one query per lane appends <= 32 * G entries at a time
+    __shared__ uint2 s_buf[kPyrWarps][32 * QPL * G + FLUSH];               // a step appends <= 32 * QPL * G entries
     __shared__ uint32_t s_n[kPyrWarps];                                    // entries buffered per warp
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int slot = lane / LPP, i = lane % LPP;
@@ -470,6 +470,20 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_leaf_tile_kernel(const LQ*
 
     // Software pipeline: the target volumes of step t+1 travel global -> shared with cp.async (no registers), the
     // query volumes of step t+1 and the list entry of step t+2 are loaded into registers while step t is computed.
+    constexpr int SPI = 128 / TPIECES;                                     // slots per copy instruction half (quarter-warp pairs)
+    constexpr int CP_ROUNDS = SLOTS * TPIECES / 32;                        // copy instructions per step
+    static_assert(TPIECES == 4 || TPIECES == 8 || TPIECES == 12, "piece mapping below");
+    // piece `pi` (0 .. SLOTS * TPIECES) -> (slot, piece in slot). 16-byte volumes: lane L of round k copies piece L % 4
+    // of slot 8k + L / 8 + 4 * ((L / 4) % 2). Larger volumes: plain order (a slot is >= 128 contiguous bytes).
+    auto copy_slot = [&](int k) -> int {
+        if constexpr (TPIECES == 4) return 8 * k + (lane >> 3) + 4 * ((lane >> 2) & 1);
+        else return (k * 32 + lane) / TPIECES;
+    };
+    auto copy_piece = [&](int k) -> int {
+        if constexpr (TPIECES == 4) return lane & 3;
+        else return (k * 32 + lane) % TPIECES;
+    };
+    const uint32_t vraw_base = (uint32_t)__cvta_generic_to_shared(s_vraw[w][0][0]);
     struct Stage { uint32_t qpos0, j0, have; Packed<VQ> q[QPL]; };
     auto fetch = [&](uint2 pr, bool have, int buf) -> Stage {
         Stage sg;
@@ -478,22 +492,32 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_leaf_tile_kernel(const LQ*
         sg.have = have ? 1u : 0u;
 #pragma unroll
         for (int k = 0; k < QPL; ++k) sg.q[k] = load16(pq + sg.qpos0 + (uint32_t)(QPL * i + k));
-        const uint4* src = reinterpret_cast<const uint4*>(pt + sg.j0) + PPL * i;
-        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_vraw[w][buf][slot]) + 16u * (uint32_t)(PPL * i);
+        // Target copy global -> shared, 16 bytes per lane and instruction. The copy mapping is NOT the compute mapping:
+        // for 16-byte volumes one instruction moves 8 whole slots, lanes 4c .. 4c+3 of a quarter-warp writing the
+        // 64 bytes of slot a and the next four lanes those of slot a + 4 — with the 80-byte slot stride these are
+        // the slot pairs whose bank ranges do not overlap (the compute mapping gave 14 wavefronts per copy, this 4).
+        // The T group of the copied slot comes from the lane that owns the pair, by shuffle.
 #pragma unroll
-        for (int k = 0; k < PPL; ++k)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * k), "l"(src + k) : "memory");
+        for (int k = 0; k < CP_ROUNDS; ++k) {
+            const int cslot = copy_slot(k);
+            const uint32_t tj0 = __shfl_sync(0xffffffffu, sg.j0, cslot * LPP);
+            const uint4* src = reinterpret_cast<const uint4*>(pt + tj0) + copy_piece(k);
+            const uint32_t dst = vraw_base + (uint32_t)(buf * SLOTS * SLOT_BYTES + cslot * SLOT_BYTES + 16 * copy_piece(k));
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+        }
         asm volatile("cp.async.commit_group;" ::: "memory");
         return sg;
     };
     volatile uint32_t* s_nv = s_n;
-    auto append = [&](uint32_t hits, uint32_t qp, uint32_t j0) {
-        if (hits) {                                                            // one shared-memory atomic reserves the lane's slots
+    // append: bits [G * k, G * k + G) of `hits` are the targets hit by query k of the lane; one shared-memory atomic
+    // reserves the lane's slots
+    auto append = [&](uint32_t hits, uint32_t qp0, uint32_t j0) {
+        if (hits) {
             uint32_t wpos = atomicAdd(&s_n[w], (uint32_t)__popc(hits));
             do {
-                const int j = __ffs(hits) - 1;
+                const int b = __ffs(hits) - 1;
                 hits &= hits - 1;
-                s_buf[w][wpos++] = make_uint2(qp, j0 + (uint32_t)j);
+                s_buf[w][wpos++] = make_uint2(qp0 + (uint32_t)(b / G), j0 + (uint32_t)(b % G));
             } while (hits);
         }
         __syncwarp();
@@ -536,8 +560,10 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_leaf_tile_kernel(const LQ*
                 hits[k] &= allowed;
             }
         }
+        uint32_t all = 0;
 #pragma unroll
-        for (int k = 0; k < QPL; ++k) append(hits[k], qp0 + (uint32_t)k, cur.j0);
+        for (int k = 0; k < QPL; ++k) all |= hits[k] << (G * k);
+        append(all, qp0, cur.j0);
     };
     const uint32_t chunk = SLOTS * pyr_chunk_steps(count, SLOTS);        // see pyr_refine_kernel
     for (;;) {

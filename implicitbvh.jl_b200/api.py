@@ -357,7 +357,10 @@ class BVH:
         # skips: reuse from cache (build.jl:232-239)
         if cache is not None and cache.index_dtype != I:
             raise ArgumentError("eltype(cache.skips) === I must hold")
-        self.skips = torch.from_numpy(self.tree.skips().astype(I)).to(src.device, non_blocking=True)
+        if cache is not None and cache.tree.real_leaves == n and cache.skips.device == src.device:
+            self.skips = cache.skips                      # same n => same skips: reused, as the reference does
+        else:
+            self.skips = torch.from_numpy(self.tree.skips().astype(I)).to(src.device, non_blocking=True)
 
         # built level (build.jl:309-325)
         out = C.c_int64()
@@ -395,10 +398,10 @@ class BVH:
         m = options.morton
         mins = (C.c_double * 3)(*[float(x) for x in m.mins])
         maxs = (C.c_double * 3)(*[float(x) for x in m.maxs])
-        with torch.cuda.device(didx):
-            rc = lib.ibvh_build(self._handle, d_vol, self.leaves.ptr, n, C.byref(self.types),
-                                self.nodes.ptr if num_nodes > 0 else None, self.built_level,
-                                1 if m.compute_extrema else 0, mins, maxs, _stream_ptr(didx))
+        # (the library switches to the handle's device itself; the stream is torch's current stream on it)
+        rc = lib.ibvh_build(self._handle, d_vol, self.leaves.ptr, n, C.byref(self.types),
+                            self.nodes.ptr if num_nodes > 0 else None, self.built_level,
+                            1 if m.compute_extrema else 0, mins, maxs, _stream_ptr(didx))
         if rc != capi.OK:
             _raise(rc, self._handle, "ibvh_build")
 
@@ -544,9 +547,8 @@ def traverse(bvh: BVH, bvh2=None, alg=None, *, start_level: Optional[int] = None
 
         def call(flags, p_counts, p_contacts, capacity, total, peer_ref=None):
             params = capi.TraverseParams(sl, qb, qc, flags, 0, 0, peer_ref)
-            with torch.cuda.device(device.index):
-                return lib.ibvh_traverse_single(bvh._handle, C.byref(cb), C.byref(params), p_counts, p_contacts, capacity,
-                                                C.byref(total), _stream_ptr(device.index))
+            return lib.ibvh_traverse_single(bvh._handle, C.byref(cb), C.byref(params), p_counts, p_contacts, capacity,
+                                            C.byref(total), _stream_ptr(device.index))
 
         total, c1, c2 = run(call, bvh._handle, device, I, nq)
         return BVHTraversal(sl, 0, 0, total, c1, c2)
@@ -571,9 +573,8 @@ def traverse(bvh: BVH, bvh2=None, alg=None, *, start_level: Optional[int] = None
 
     def call(flags, p_counts, p_contacts, capacity, total, peer_ref=None):
         params = capi.TraverseParams(sl_t, qb, qc, flags, 1 if flip else 0, 0, peer_ref)
-        with torch.cuda.device(device.index):
-            return lib.ibvh_traverse_pair(bvh._handle, C.byref(cq), C.byref(ct), C.byref(params), p_counts, p_contacts, capacity,
-                                          C.byref(total), _stream_ptr(device.index))
+        return lib.ibvh_traverse_pair(bvh._handle, C.byref(cq), C.byref(ct), C.byref(params), p_counts, p_contacts, capacity,
+                                      C.byref(total), _stream_ptr(device.index))
 
     total, c1, c2 = run(call, bvh._handle, device, I, nq)
     return BVHTraversal(sl1, sl2, 0, total, c1, c2)

@@ -629,6 +629,9 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
     int tile_launch = 0;
     const bool unordered = fused || ((flags & IBVH_TRAVERSE_UNORDERED) != 0 && d_contacts != nullptr);
     const bool count_only = !fused && d_contacts == nullptr;
+    // ordered protocol with a contacts buffer and no valid counts yet: ONE tile pass that counts per query and stashes
+    // the hits, then scan + scatter into the query segments (instead of a count pass and a write pass of the tile kernel)
+    const bool stash_mode = !unordered && !count_only && capacity > 0 && !((flags & IBVH_TRAVERSE_COUNTS_VALID) && d_counts);
     const int nl = plan.n;
     const int grid = h->sm_count * (getenv("IBVH_PYR_GRID") ? atoi(getenv("IBVH_PYR_GRID")) : 20);
 
@@ -654,7 +657,8 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
         const bool same_leaves = (const void*)qleaves == (const void*)bvh.leaves && std::is_same<LQ, LT>::value;
         size_t bytes = ibvh_handle::padded((size_t)plan.u_total * sizeof(UBox<T>)) + ibvh_handle::padded((size_t)plan.t_total * sizeof(N)) +
                        ibvh_handle::padded((size_t)(bvh.ti.n + 8) * sizeof(Packed<VT>)) +
-                       (same_leaves ? 0 : ibvh_handle::padded((size_t)(n_query_total + 8) * sizeof(Packed<VQ>)));
+                       (same_leaves ? 0 : ibvh_handle::padded((size_t)(n_query_total + 8) * sizeof(Packed<VQ>))) +
+                       (stash_mode ? ibvh_handle::padded((size_t)capacity * sizeof(uint4)) : 0);
         for (int l = 0; l < nl; ++l) {
             const PyrLevel& v = plan.lv[l];
             unsigned long long c = (unsigned long long)(factor * (double)(v.nqg > v.ntg && KIND != kSingle ? v.nqg : v.nqg)) + 4096ull;
@@ -671,6 +675,8 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
         Packed<VT>* PT = (Packed<VT>*)ap; ap += ibvh_handle::padded((size_t)(bvh.ti.n + 8) * sizeof(Packed<VT>));
         Packed<VQ>* PQ = (Packed<VQ>*)PT;
         if (!same_leaves) { PQ = (Packed<VQ>*)ap; ap += ibvh_handle::padded((size_t)(n_query_total + 8) * sizeof(Packed<VQ>)); }
+        uint4* stash = nullptr;
+        if (stash_mode) { stash = (uint4*)ap; ap += ibvh_handle::padded((size_t)capacity * sizeof(uint4)); }
         PairList lists[kPyrMaxLevels];
         for (int l = 0; l < nl; ++l) { lists[l].data = (uint2*)ap; lists[l].count = d_cnt + l; lists[l].cap = cap[l]; ap += ibvh_handle::padded((size_t)cap[l] * sizeof(uint2)); }
         IBVH_CUDA_TRY(h, cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * kPyrMaxLevels + 128, st));   // list counters + chunk tickets
@@ -774,7 +780,10 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
         } else if (!counts_valid) {
             IBVH_CUDA_TRY(h, cudaMemsetAsync(counts, 0, (size_t)ta.q_count * sizeof(I), st));
             { ProfScope _ps(h, st, "pyr_leaf_tile_kernel");
-            pyr_leaf_tile_kernel<KIND, kCount, 1, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, 0, d_total, counts, nullptr, (IndexPair<I>*)nullptr, 0, d_tick + 16 + (tile_launch++), PQ, PT);
+            if (stash_mode)
+                pyr_leaf_tile_kernel<KIND, kAtomic, 3, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, capacity, d_total, counts, nullptr, (IndexPair<I>*)stash, 0, d_tick + 16 + (tile_launch++), PQ, PT);
+            else
+                pyr_leaf_tile_kernel<KIND, kCount, 1, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, 0, d_total, counts, nullptr, (IndexPair<I>*)nullptr, 0, d_tick + 16 + (tile_launch++), PQ, PT);
             }
             IBVH_LAUNCH_CHECK(h, "pyr_leaf_tile_kernel");
             rc = scan_counts<I>(h, counts, ta.q_count, qsums, d_total, st);
@@ -822,12 +831,20 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
         if (unordered) return *num_contacts > capacity ? IBVH_ERR_CAPACITY : IBVH_OK;
         if (count_only || *num_contacts == 0) return IBVH_OK;
         if (*num_contacts > capacity) return IBVH_ERR_CAPACITY;
-        // ordered write: per-query cursors, then sort each query's handful of hits by target position
+        // ordered write: per-query cursors (from the stash of the single tile pass, or — counts valid from an earlier
+        // call — a write pass of the tile kernel), then sort each query's handful of hits by target position
         IBVH_CUDA_TRY(h, cudaMemsetAsync(cursors, 0, (size_t)ta.q_count * 4, st));
-        { ProfScope _ps(h, st, "pyr_leaf_tile_kernel");
-        pyr_leaf_tile_kernel<KIND, kWrite, 2, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, capacity, d_total, counts, cursors, (IndexPair<I>*)d_contacts, 0, d_tick + 16 + (tile_launch++), PQ, PT);
+        if (stash_mode && !counts_valid) {
+            { ProfScope _ps(h, st, "pyr_scatter_kernel");
+            pyr_scatter_kernel<I><<<h->sm_count * 16, 256, 0, st>>>(stash, d_total, capacity, counts, cursors, (IndexPair<I>*)d_contacts);
+            }
+            IBVH_LAUNCH_CHECK(h, "pyr_scatter_kernel");
+        } else {
+            { ProfScope _ps(h, st, "pyr_leaf_tile_kernel");
+            pyr_leaf_tile_kernel<KIND, kWrite, 2, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, capacity, d_total, counts, cursors, (IndexPair<I>*)d_contacts, 0, d_tick + 16 + (tile_launch++), PQ, PT);
+            }
+            IBVH_LAUNCH_CHECK(h, "pyr_leaf_tile_kernel");
         }
-        IBVH_LAUNCH_CHECK(h, "pyr_leaf_tile_kernel");
         { ProfScope _ps(h, st, "pyr_fixup_kernel");
         pyr_fixup_kernel<KIND, LQ, LT, I><<<(unsigned)((ta.q_count + 255) / 256), 256, 0, st>>>(qleaves, bvh.leaves, q_begin, ta.q_count, ta.flip, counts, (IndexPair<I>*)d_contacts);
         }

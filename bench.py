@@ -509,10 +509,18 @@ def main():
         rp, rd = synth.random_rays_torch(nr, dev, seed=7, start=rb[0])
         rt = ib.traverse_rays(rbvh, rp, rd, ordered=ordered, id_base=rb[0])
         rcache = ib.BVHTraversal(1, 0, 0, 0, ib.DeviceArray.empty(int(rt.num_contacts * 1.02) + 1024, ib.pair_dtype(), dev), rt.cache2)
+        ray_peer = None
+        if world > 1 and args.gather != "nccl":
+            tot = torch.tensor([rt.num_contacts], dtype=torch.int64, device=dev)
+            dist.all_reduce(tot)
+            ray_peer = ibdist.PeerGather(int(int(tot.item()) * 1.02) + 1024, 8, dev)       # hit list of ALL rays on every rank
 
         def step_rays():
             t = ib.traverse_rays(rbvh, rp, rd, cache=rcache, ordered=ordered, id_base=rb[0])
             if world > 1:
+                if ray_peer is not None:
+                    _, total_hits, _ = ray_peer.gather(t.cache1.tensor, t.num_contacts)     # ibvh_allgather_pairs: rank order = ray order
+                    return total_hits
                 _, cs = ibdist.gather_shards(t.cache1.tensor, t.num_contacts, 8)
                 return int(sum(cs))
             return t.num_contacts
@@ -533,7 +541,7 @@ def main():
             rms = float(t.item())
         rays = {"metric": "rays/s @1M leaves", "value": R / (rms * 1e-3), "unit": "rays/s", "ms_per_step": rms, "rays": R, "hits_per_step": int(hits),
                 "workload": "configs[3]: 1000x1000 shell of BSphere{Float32} (1 M leaves, BBox{Float32} nodes), %d random rays, traverse_rays (LVT), "
-                            "rays sharded by contiguous ranges over %d GPU(s), hit shards all-gathered" % (R, world),
+                            "rays sharded by contiguous ranges over %d GPU(s), hit shards all-gathered to every rank (%s)" % (R, world, "n/a" if world == 1 else ("ibvh_allgather_pairs over NVLink peer memory" if args.gather != "nccl" else "NCCL")),
                 "scaling": "strong"}
         del rp, rd, rcache, rt
 

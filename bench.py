@@ -196,6 +196,7 @@ def main():
                          "(same set; the parity bar is the SORTED contact list)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-rays", action="store_true", help="skip the secondary rays/s measurement")
+    ap.add_argument("--no-defer", action="store_true", help="single GPU: synchronous traversal calls (the host reads each step's contact count before it enqueues the next build)")
     ap.add_argument("--gather", default="fused", choices=["fused", "peer", "nccl"],
                     help="N > 1: how the contact shards reach every rank. fused: the traversal kernel itself writes each contact "
                          "into every rank's list (slots from one counter on rank 0, multimem.st over NVLink; unordered only); "
@@ -242,10 +243,15 @@ def main():
     def step_device():
         """One step with inputs in HBM. Returns the number of contacts this rank holds at the end."""
         if world == 1:
+            # the traversal is enqueued without a host round trip (defer) and the NEXT build is enqueued before the
+            # host waits for this step's contact count: the GPU never idles between steps. Every step's count is
+            # still read inside the timed region (one step late; the last one in finish_pending()).
             bvh = ib.BVH(src, ib.BBox(), cache=state["bvh"])
-            tr = ib.traverse(bvh, cache=state["tr"], ordered=ordered)
+            prev = state["tr"]
+            n_prev = prev.num_contacts if prev is not None else 0          # resolves the previous step's traversal
+            tr = ib.traverse(bvh, cache=prev, ordered=ordered, defer=not ordered and not args.no_defer)
             state["bvh"], state["tr"] = bvh, tr
-            return tr.num_contacts
+            return n_prev
         # the build does not shard: replicate it, or build on rank 0 and broadcast the tree (leaves + nodes);
         # then shard the traversal by query range and gather the shards
         if args.build_mode == "replicate":
@@ -290,6 +296,11 @@ def main():
     for _ in range(warm):
         ncontacts = step_device()
 
+    def finish_pending():
+        """Single GPU: the count of the last (deferred) traversal — read before the closing event is recorded."""
+        return state["tr"].num_contacts if world == 1 else None
+
+    finish_pending()
     sampler = ClockSampler(local)
     sync_all()
     if rank == 0:
@@ -299,6 +310,8 @@ def main():
     e0.record()
     for _ in range(args.steps):
         ncontacts = step_device()
+    if world == 1:
+        ncontacts = finish_pending()
     e1.record()
     sync_all()
     ms_total = e0.elapsed_time(e1)
@@ -316,6 +329,7 @@ def main():
     prof_steps = 5
     for _ in range(prof_steps):
         step_device()
+    finish_pending()
     torch.cuda.synchronize()
     rows = profile_rows(ib, handle)
     lib.ibvh_profile_enable(handle, 0)
@@ -566,6 +580,8 @@ def main():
             "config": {"workload": WORKLOAD % n, "leaves": n, "contacts_per_step": int(ncontacts),
                        "contact_order": "reference (ascending query, DFS order; count+scan+write)" if ordered else "unordered (one pass, buffered warp-aggregated atomics; identical as a sorted list)",
                        "parallelism": "single GPU" if world == 1 else (("build replicated on every rank (deterministic, bit-identical)" if args.build_mode == "replicate" else "build on rank 0 + NCCL broadcast of the tree") + f", query-range sharded traversal over {world} GPUs, " + ("traversal fused with the all-gather: contacts written into every rank's list by the traversal kernel (multimem.st over NVLink)" if fused else "contact shards all-gathered by the library's peer-memory kernel (NVLink multicast stores)" if args.gather in ("peer", "fused") else "NCCL all-gather of the contact shards")),
+                       "host_sync": ("deferred traversal (IBVH_TRAVERSE_DEFER): the next build is enqueued before the host reads a step's contact count; every count is read inside the timed region"
+                                     if (world == 1 and not ordered and not args.no_defer) else "synchronous calls: the host reads each step's contact count before the next build is enqueued"),
                        "l2_policy": "inputs larger than L2 (160 MB volumes + 240 MB leaves + 240 MB nodes per step vs 126 MB L2)"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,
             "secondary": rays,

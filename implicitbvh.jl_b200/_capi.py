@@ -13,11 +13,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("IBVH_B200_LIB") or os.path.join(_HERE, "lib", "libibvh_b200.so")
 
 # status codes (include/ibvh.h)
-OK, ERR_ARGUMENT, ERR_DOMAIN, ERR_UNSUPPORTED, ERR_CUDA, ERR_CAPACITY, ERR_ALLOC, ERR_PEER = range(8)
+OK, ERR_ARGUMENT, ERR_DOMAIN, ERR_UNSUPPORTED, ERR_CUDA, ERR_CAPACITY, ERR_ALLOC, ERR_PEER, ERR_AGAIN = range(9)
 MAX_PEERS = 16
 BSPHERE, BBOX = 0, 1
 TRAVERSE_ORDERED, TRAVERSE_UNORDERED, TRAVERSE_REFERENCE_SHAPED, TRAVERSE_COUNTS_VALID = 0, 1, 2, 4
-TRAVERSE_STATS, TRAVERSE_PACKET, TRAVERSE_WALK = 8, 16, 32
+TRAVERSE_STATS, TRAVERSE_PACKET, TRAVERSE_WALK, TRAVERSE_DEFER = 8, 16, 32, 64
 
 
 class Types(C.Structure):
@@ -78,6 +78,7 @@ SIGNATURES = {
     "ibvh_profile_get": (_ci, [_vp, _ci, C.c_char_p, _ci, C.POINTER(C.c_float)]),
     "ibvh_profile_reset": (_ci, [_vp]),
     "ibvh_last_traversal_stats": (_ci, [_vp, C.POINTER(_i64)]),
+    "ibvh_traverse_finish": (_ci, [_vp, C.POINTER(_i64)]),
     "ibvh_allgather_pairs": (_ci, [_vp, C.POINTER(Peer), _vp, _i64, C.c_int32, C.POINTER(_i64), C.POINTER(_i64), _vp]),
 }
 

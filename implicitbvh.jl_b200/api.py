@@ -425,8 +425,21 @@ class BVHTraversal:
     def __init__(self, start_level1: int, start_level2: int, num_checks: int, num_contacts: int,
                  cache1: DeviceArray, cache2: DeviceArray):
         self.start_level1, self.start_level2 = int(start_level1), int(start_level2)
-        self.num_checks, self.num_contacts = int(num_checks), int(num_contacts)
+        self.num_checks = int(num_checks)
+        self._num_contacts = int(num_contacts)
+        self._resolve = None                  # deferred traversal (traverse(..., defer=True)): resolves on first use
         self.cache1, self.cache2 = cache1, cache2
+
+    @property
+    def num_contacts(self) -> int:
+        if self._resolve is not None:
+            resolve, self._resolve = self._resolve, None
+            resolve(self)
+        return self._num_contacts
+
+    @num_contacts.setter
+    def num_contacts(self, v):
+        self._num_contacts = int(v)
 
     @property
     def contacts(self) -> DeviceArray:
@@ -444,6 +457,32 @@ def default_start_level(bvh: BVH, alg=None) -> int:
     if alg is not None and not isinstance(alg, LVTTraversal):
         raise ArgumentError(f"default_start_level not implemented for: {alg}")
     return max(1, bvh.built_level)
+
+
+class _Pending:
+    """A deferred traversal (IBVH_TRAVERSE_DEFER): resolved by ibvh_traverse_finish when num_contacts is first read;
+    if the library asks for a repeat (scratch lists / contacts buffer too small) the synchronous call is made."""
+
+    def __init__(self, handle):
+        self.handle = handle
+
+    def attach(self, tr: "BVHTraversal", rerun):
+        handle = self.handle
+
+        def resolve(t: "BVHTraversal"):
+            total = C.c_int64(0)
+            rc = capi.lib().ibvh_traverse_finish(handle, C.byref(total))
+            if rc == capi.OK:
+                t._num_contacts = int(total.value)
+                return
+            if rc in (capi.ERR_AGAIN, capi.ERR_CAPACITY):
+                again = rerun()
+                t._num_contacts, t.cache1, t.cache2 = again.num_contacts, again.cache1, again.cache2
+                return
+            _raise(rc, handle, "ibvh_traverse_finish")
+
+        tr._resolve = resolve
+        return tr
 
 
 def _check_narrow(narrow):
@@ -502,13 +541,16 @@ def _run_two_phase(call, handle, device, I: np.dtype, nqueries: int, cache: Opti
 def traverse(bvh: BVH, bvh2=None, alg=None, *, start_level: Optional[int] = None, start_level1: Optional[int] = None,
              start_level2: Optional[int] = None, narrow=None, cache: Optional[BVHTraversal] = None, options: BVHOptions = None,
              ordered: bool = True, reference_shaped: bool = False, packet: bool = False, walk: bool = False,
-             query_range=None, peer=None) -> BVHTraversal:
+             query_range=None, peer=None, defer: bool = False) -> BVHTraversal:
     """`traverse(bvh[, bvh2], LVTTraversal(); start_level[1,2], narrow, cache, options)`.
 
     Extensions over the reference signature (all keyword-only, defaults reproduce the reference):
     `ordered=False` selects the unordered emission, `reference_shaped=True` the proxy of the reference's
     own GPU kernel, `packet=True` forces the warp-packet schedule (default: group walk + dense tiles for
     BBox nodes), `query_range=(begin, count)` restricts the query leaves (multi-GPU shard).
+    `defer=True` (with `ordered=False` and a `cache` whose cache1 is allocated): the traversal is only enqueued;
+    `num_contacts` waits for it on first use, so the next `BVH(...)` can be enqueued before the host blocks (at
+    most one deferred traversal per device may be outstanding).
     `peer=dist.PeerGather(...)` (with `ordered=False`) fuses the sharded traversal with the all-gather of the
     contact shards: collective over the ranks, the returned (unordered) list holds the contacts of ALL ranks.
     """
@@ -523,6 +565,15 @@ def traverse(bvh: BVH, bvh2=None, alg=None, *, start_level: Optional[int] = None
         raise ArgumentError("the fused multi-GPU traversal is the unordered default schedule (ordered=False)")
 
     def run(call, handle, device, I, nq):
+        if (defer and peer is None and not ordered and not (reference_shaped or packet or walk) and cache is not None
+                and len(cache.cache1) > 0 and cache.cache1.device == device and cache.cache1.dtype == pair_dtype(I)):
+            total = C.c_int64(0)
+            rc = call(capi.TRAVERSE_UNORDERED | capi.TRAVERSE_DEFER, None, cache.cache1.ptr, len(cache.cache1), total)
+            if rc == capi.OK and total.value == -1:
+                return _Pending(handle), cache.cache1, cache.cache2
+            if rc == capi.OK:
+                return int(total.value), cache.cache1, cache.cache2
+            # anything else (e.g. capacity): the synchronous protocol below sorts it out
         if peer is None:
             return _run_two_phase(call, handle, device, I, nq, cache, ordered, reference_shaped, packet, walk)
         if peer.pair_bytes != pair_dtype(I).itemsize or peer.device != device:
@@ -551,6 +602,9 @@ def traverse(bvh: BVH, bvh2=None, alg=None, *, start_level: Optional[int] = None
                                             C.byref(total), _stream_ptr(device.index))
 
         total, c1, c2 = run(call, bvh._handle, device, I, nq)
+        if isinstance(total, _Pending):
+            return total.attach(BVHTraversal(sl, 0, 0, 0, c1, c2),
+                                lambda: traverse(bvh, start_level=sl, cache=BVHTraversal(sl, 0, 0, 0, c1, c2), ordered=False, query_range=query_range))
         return BVHTraversal(sl, 0, 0, total, c1, c2)
 
     # pair — traverse_pair.jl:1-116
@@ -577,6 +631,10 @@ def traverse(bvh: BVH, bvh2=None, alg=None, *, start_level: Optional[int] = None
                                       C.byref(total), _stream_ptr(device.index))
 
     total, c1, c2 = run(call, bvh._handle, device, I, nq)
+    if isinstance(total, _Pending):
+        return total.attach(BVHTraversal(sl1, sl2, 0, 0, c1, c2),
+                            lambda: traverse(bvh, bvh2, start_level1=sl1, start_level2=sl2, cache=BVHTraversal(sl1, sl2, 0, 0, c1, c2),
+                                             ordered=False, query_range=query_range))
     return BVHTraversal(sl1, sl2, 0, total, c1, c2)
 
 

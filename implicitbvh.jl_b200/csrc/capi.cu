@@ -800,6 +800,17 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
         } else {
             IBVH_CUDA_TRY(h, cudaMemcpyAsync(hp, d_total, 8, cudaMemcpyDeviceToHost, st));
             IBVH_CUDA_TRY(h, cudaMemcpyAsync(hp + 1, d_cnt, sizeof(unsigned long long) * kPyrMaxLevels, cudaMemcpyDeviceToHost, st));
+            if (unordered && (flags & IBVH_TRAVERSE_DEFER)) {
+                // deferred: everything is enqueued; ibvh_traverse_finish judges the read-back later
+                IBVH_CUDA_TRY(h, cudaEventRecord(h->ev_defer, st));
+                ibvh_handle::Deferred& df = h->deferred;
+                df.active = true; df.nl = nl; df.capacity = capacity;
+                df.top_pairs = plan.lv[nl - 1].nqg * plan.lv[nl - 1].ntg;
+                df.fan2 = 1 << (2 * kPyrFan); df.leaf2 = 1 << (2 * kPyrLeafLog);
+                for (int l = 0; l < nl; ++l) { df.cap[l] = cap[l]; df.nqg[l] = plan.lv[l].nqg; }
+                *num_contacts = -1;
+                return IBVH_OK;
+            }
             IBVH_CUDA_TRY(h, cudaStreamSynchronize(st));
         }
         bool overflow = false;
@@ -935,6 +946,7 @@ const char* ibvh_status_string(int s) {
         case IBVH_ERR_CAPACITY: return "contacts capacity too small";
         case IBVH_ERR_ALLOC: return "workspace allocation failed";
         case IBVH_ERR_PEER: return "peer GPU did not arrive at the shard exchange";
+        case IBVH_ERR_AGAIN: return "deferred traversal must be repeated (scratch pair lists were too small)";
     }
     return "unknown";
 }
@@ -1023,7 +1035,8 @@ int ibvh_create(ibvh_handle_t** out, int device) {
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     if (cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_defer, cudaEventDisableTiming) != cudaSuccess) {
         cudaGetLastError();
         cudaFree(h->d_small); cudaFreeHost(h->h_pinned); delete h;
         return IBVH_ERR_CUDA;
@@ -1041,6 +1054,7 @@ int ibvh_destroy(ibvh_handle_t* h) {
     if (h->side) cudaStreamDestroy(h->side);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->ev_defer) cudaEventDestroy(h->ev_defer);
     delete h;
     return IBVH_OK;
 }
@@ -1069,6 +1083,32 @@ int ibvh_profile_get(ibvh_handle_t* h, int i, char* name, int name_cap, float* m
     return IBVH_OK;
 }
 int ibvh_profile_reset(ibvh_handle_t* h) { if (!h) return IBVH_ERR_ARGUMENT; h->prof_n = 0; return IBVH_OK; }
+
+int ibvh_traverse_finish(ibvh_handle_t* h, int64_t* num_contacts) {
+    if (!h || !num_contacts) return IBVH_ERR_ARGUMENT;
+    ibvh_handle::Deferred& df = h->deferred;
+    if (!df.active) { h->set_error("ibvh_traverse_finish: no deferred traversal outstanding"); return IBVH_ERR_ARGUMENT; }
+    DeviceGuard g(h->device);
+    df.active = false;
+    cudaError_t e = cudaEventSynchronize(h->ev_defer);
+    if (e != cudaSuccess) { h->set_cuda_error(e, "cudaEventSynchronize(deferred traversal)"); return IBVH_ERR_CUDA; }
+    const unsigned long long* hp = (const unsigned long long*)h->h_pinned;
+    bool overflow = false;
+    double worst = 0.0;
+    for (int l = 0; l < df.nl; ++l) {
+        const unsigned long long c = hp[1 + l];
+        if (c > df.cap[l]) overflow = true;
+        const double r = (double)c / (double)df.nqg[l];
+        if (l < df.nl - 1 && r > worst) worst = r;
+    }
+    if (overflow) { h->pyr_factor = worst * 1.15 + 2.0; *num_contacts = 0; return IBVH_ERR_AGAIN; }
+    h->pyr_factor = worst * 1.25 + 4.0;
+    long long box = df.top_pairs;
+    for (int l = df.nl - 1; l >= 1; --l) box += (long long)hp[1 + l] * df.fan2;
+    h->last_stats[0] = box; h->last_stats[1] = (long long)hp[1] * df.leaf2; h->last_stats[2] = (long long)hp[1]; h->last_stats[3] = df.nl;
+    *num_contacts = (int64_t)hp[0];
+    return *num_contacts > df.capacity ? IBVH_ERR_CAPACITY : IBVH_OK;
+}
 
 int ibvh_last_traversal_stats(ibvh_handle_t* h, int64_t out[4]) {
     if (!h || !out) return IBVH_ERR_ARGUMENT;
@@ -1224,6 +1264,7 @@ int ibvh_build(ibvh_handle_t* h, const void* d_volumes, void* d_leaves, int64_t 
 int ibvh_traverse_single(ibvh_handle_t* h, const ibvh_bvh_t* bvh, const ibvh_traverse_params_t* p, void* d_counts, void* d_contacts,
                          int64_t capacity, int64_t* num_contacts, void* stream) {
     if (!h || !p || !num_contacts) return IBVH_ERR_ARGUMENT;
+    if (h->deferred.active) { h->set_error("a deferred traversal is outstanding on this handle: call ibvh_traverse_finish first"); return IBVH_ERR_ARGUMENT; }
     ibvh_tree_t tree;
     int rc = check_bvh(bvh, &tree);
     if (rc != IBVH_OK) return rc;
@@ -1253,6 +1294,7 @@ int ibvh_traverse_single(ibvh_handle_t* h, const ibvh_bvh_t* bvh, const ibvh_tra
 int ibvh_traverse_pair(ibvh_handle_t* h, const ibvh_bvh_t* queries, const ibvh_bvh_t* target, const ibvh_traverse_params_t* p,
                        void* d_counts, void* d_contacts, int64_t capacity, int64_t* num_contacts, void* stream) {
     if (!h || !p || !num_contacts || !queries || !target) return IBVH_ERR_ARGUMENT;
+    if (h->deferred.active) { h->set_error("a deferred traversal is outstanding on this handle: call ibvh_traverse_finish first"); return IBVH_ERR_ARGUMENT; }
     ibvh_tree_t tq, tt;
     if (!types_ok(&queries->types) || queries->n < 1 || !queries->d_leaves) return IBVH_ERR_ARGUMENT;
     int rc = make_tree(queries->n, &tq);

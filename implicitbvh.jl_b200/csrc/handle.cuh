@@ -44,6 +44,19 @@ struct ibvh_handle {
 
     int64_t last_stats[4] = {0, 0, 0, 0};
 
+    // one outstanding deferred traversal (IBVH_TRAVERSE_DEFER): what ibvh_traverse_finish needs to judge the
+    // read-back that the enqueued work leaves in the pinned block
+    struct Deferred {
+        bool active = false;
+        int nl = 0;
+        unsigned long long cap[16] = {0};
+        long long nqg[16] = {0};
+        long long top_pairs = 0;
+        long long capacity = 0;
+        int fan2 = 64, leaf2 = 16;
+    } deferred;
+    cudaEvent_t ev_defer = nullptr;
+
     // side stream + events: the per-query pass over flagged groups overlaps the tile kernel
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;

@@ -56,7 +56,8 @@ typedef enum ibvh_status {
     IBVH_ERR_CUDA = 4,         /* CUDA runtime error; text via ibvh_last_error              */
     IBVH_ERR_CAPACITY = 5,     /* contacts buffer too small; *num_contacts holds the need   */
     IBVH_ERR_ALLOC = 6,        /* workspace allocation failed                               */
-    IBVH_ERR_PEER = 7          /* a peer GPU did not arrive at the shard exchange in time   */
+    IBVH_ERR_PEER = 7,         /* a peer GPU did not arrive at the shard exchange in time   */
+    IBVH_ERR_AGAIN = 8         /* deferred traversal: internal pair lists were too small — call the traversal again */
 } ibvh_status;
 
 typedef enum ibvh_volume_kind { IBVH_BSPHERE = 0, IBVH_BBOX = 1 } ibvh_volume_kind;
@@ -95,6 +96,10 @@ typedef struct ibvh_bvh {
                                       /* default for BBox nodes is the "group walk + dense tiles" one    */
 #define IBVH_TRAVERSE_WALK 32u        /* force the "group walk + dense tiles" schedule instead of the     */
                                       /* default pyramid refinement (both BBox nodes only)               */
+#define IBVH_TRAVERSE_DEFER 64u       /* single / pair, UNORDERED, default schedule: enqueue the whole traversal and  */
+                                      /* return at once with *num_contacts = -1; ibvh_traverse_finish waits for it    */
+                                      /* and reports the total. The host can enqueue the next build meanwhile, so the */
+                                      /* GPU does not idle across the traversal's one host round trip.                */
 #define IBVH_TRAVERSE_STATS 8u        /* fill the device counters read by ibvh_last_traversal_stats */
 #define IBVH_TRAVERSE_COUNTS_VALID 4u /* ORDERED only: d_counts already holds the inclusive scan */
                                       /* left by a previous count-only call on the same queries: */
@@ -239,6 +244,12 @@ IBVH_API int ibvh_profile_reset(ibvh_handle_t* h);
  * from its pair-list sizes — out[0] = box-box tests, out[1] = leaf-leaf tests, out[2] = candidate pairs of
  * 4-leaf groups, out[3] = pyramid levels. */
 IBVH_API int ibvh_last_traversal_stats(ibvh_handle_t* h, int64_t out[4]);
+
+/* Completes the traversal started with IBVH_TRAVERSE_DEFER on this handle (at most one may be outstanding; work
+ * enqueued on the stream AFTER it, e.g. the next ibvh_build, is not waited for). *num_contacts = the total.
+ * IBVH_ERR_CAPACITY as for the synchronous call; IBVH_ERR_AGAIN: the scratch pair lists overflowed (their size is
+ * learned from the previous call) — nothing valid was written, repeat the traversal (it will size them right). */
+IBVH_API int ibvh_traverse_finish(ibvh_handle_t* h, int64_t* num_contacts);
 
 /* ---- multi-GPU: all-gather of the contact / hit shards over NVLink peer memory ------
  * The reference has no multi-GPU path; this is the exchange step that follows a query-range sharded

@@ -811,3 +811,42 @@ def test_multi_gpu_fused_traversal_and_peer_gather():
            "--master-port", "29571", os.path.join(ROOT, "tools", "fused_test.py")]
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "PARITY ok" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
+
+
+@pytest.mark.gpu
+def test_deferred_traversal_matches_synchronous(ib, O, dev):
+    """IBVH_TRAVERSE_DEFER + ibvh_traverse_finish: same contact set as the synchronous call; the next build may be
+    enqueued before the count is read; a second traversal while one is outstanding is refused; a too small contacts
+    buffer is sorted out by the fall-back."""
+    import torch
+    from ibvh_b200 import synth
+    n = 200_000
+    vols = synth.random_spheres_np(n, seed=11)
+    bvh = ib.BVH(vols, ib.BBox(), device=dev)
+    ref = ib.traverse(bvh, ordered=False)
+    want = torch.sort(ref.contacts.tensor.view(torch.int64)).values
+    cache = ib.BVHTraversal(1, 0, 0, 0, ib.DeviceArray.empty(ref.num_contacts + 64, ib.pair_dtype(), dev), ref.cache2)
+    for rep in range(3):
+        tr = ib.traverse(bvh, cache=cache, ordered=False, defer=True)
+        assert tr._resolve is not None, "the call must have been deferred"
+        bvh2 = ib.BVH(vols, ib.BBox(), device=dev, cache=bvh)          # enqueued while the traversal is outstanding
+        # a second traversal on the same handle before the first is finished is refused by the library
+        with pytest.raises(ib.ArgumentError):
+            ib.traverse(bvh2, ordered=False, cache=ib.BVHTraversal(1, 0, 0, 0, ib.DeviceArray.empty(ref.num_contacts + 64, ib.pair_dtype(), dev), ref.cache2))
+        assert tr.num_contacts == ref.num_contacts
+        got = torch.sort(tr.contacts.tensor.view(torch.int64)).values
+        assert torch.equal(got, want)
+        cache = tr
+    # contacts buffer too small: finish reports the need, the fall-back call regrows cache1
+    small = ib.BVHTraversal(1, 0, 0, 0, ib.DeviceArray.empty(1000, ib.pair_dtype(), dev), ref.cache2)
+    tr = ib.traverse(bvh, cache=small, ordered=False, defer=True)
+    assert tr.num_contacts == ref.num_contacts and len(tr.cache1) >= ref.num_contacts
+    assert torch.equal(torch.sort(tr.contacts.tensor.view(torch.int64)).values, want)
+    # pair traversal
+    vols_b = synth.random_spheres_np(n // 2, seed=12, scale=synth.sphere_radius_scale(n))
+    bvh_b = ib.BVH(vols_b, ib.BBox(), device=dev)
+    refp = ib.traverse(bvh, bvh_b, ordered=False)
+    cp = ib.BVHTraversal(1, 1, 0, 0, ib.DeviceArray.empty(refp.num_contacts + 64, ib.pair_dtype(), dev), refp.cache2)
+    trp = ib.traverse(bvh, bvh_b, cache=cp, ordered=False, defer=True)
+    assert trp.num_contacts == refp.num_contacts
+    assert torch.equal(torch.sort(trp.contacts.tensor.view(torch.int64)).values, torch.sort(refp.contacts.tensor.view(torch.int64)).values)

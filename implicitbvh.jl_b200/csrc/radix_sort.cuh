@@ -45,8 +45,11 @@ template <class K> IBVH_D uint32_t digit_of(K key, int shift) { return (uint32_t
 // One radix pass. keys_in/vals_in -> keys_out/vals_out. vals_in == nullptr: values are the global
 // item index (first pass: the permutation starts as iota and need not be read).
 // hist_excl: this pass's exclusive-scanned global histogram. lookback: [tiles][256] zero-initialised.
+#ifndef IBVH_SORT_MINB
+#define IBVH_SORT_MINB 4
+#endif
 template <class K>
-__global__ void __launch_bounds__(kSortThreads) onesweep_kernel(const K* __restrict__ keys_in, K* __restrict__ keys_out,
+__global__ void __launch_bounds__(kSortThreads, IBVH_SORT_MINB) onesweep_kernel(const K* __restrict__ keys_in, K* __restrict__ keys_out,
                                                                const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out,
                                                                int64_t n, const uint32_t* __restrict__ hist_excl,
                                                                volatile uint32_t* lookback, uint32_t* ticket, int shift) {

@@ -529,7 +529,11 @@ def main():
             dist.all_reduce(tot)
             ray_peer = ibdist.PeerGather(int(int(tot.item()) * 1.02) + 1024, 8, dev)       # hit list of ALL rays on every rank
 
+        rays_fused = ray_peer is not None and args.gather == "fused" and not ordered and bool(ray_peer.peer.multicast)
+
         def step_rays():
+            if rays_fused:          # the rays kernel writes every hit into every rank's list (multimem.st over NVLink)
+                return ib.traverse_rays(rbvh, rp, rd, ordered=False, id_base=rb[0], peer=ray_peer).num_contacts
             t = ib.traverse_rays(rbvh, rp, rd, cache=rcache, ordered=ordered, id_base=rb[0])
             if world > 1:
                 if ray_peer is not None:
@@ -555,7 +559,7 @@ def main():
             rms = float(t.item())
         rays = {"metric": "rays/s @1M leaves", "value": R / (rms * 1e-3), "unit": "rays/s", "ms_per_step": rms, "rays": R, "hits_per_step": int(hits),
                 "workload": "configs[3]: 1000x1000 shell of BSphere{Float32} (1 M leaves, BBox{Float32} nodes), %d random rays, traverse_rays (LVT), "
-                            "rays sharded by contiguous ranges over %d GPU(s), hit shards all-gathered to every rank (%s)" % (R, world, "n/a" if world == 1 else ("ibvh_allgather_pairs over NVLink peer memory" if args.gather != "nccl" else "NCCL")),
+                            "rays sharded by contiguous ranges over %d GPU(s), hit shards all-gathered to every rank (%s)" % (R, world, "n/a" if world == 1 else ("fused into the rays kernel: multimem.st over NVLink" if rays_fused else "ibvh_allgather_pairs over NVLink peer memory" if args.gather != "nccl" else "NCCL")),
                 "scaling": "strong"}
         del rp, rd, rcache, rt
 

@@ -640,7 +640,7 @@ def traverse(bvh: BVH, bvh2=None, alg=None, *, start_level: Optional[int] = None
 
 def traverse_rays(bvh: BVH, points, directions, alg=None, *, start_level: int = 1, narrow=None,
                   cache: Optional[BVHTraversal] = None, options: BVHOptions = None, ordered: bool = True,
-                  id_base: int = 0) -> BVHTraversal:
+                  id_base: int = 0, peer=None) -> BVHTraversal:
     """`traverse_rays(bvh, points, directions, LVTTraversal(); start_level=1, narrow, cache, options)`.
 
     `points` / `directions`: (3, R) numpy arrays (the reference's column-major 3xR matrices), or torch
@@ -670,16 +670,27 @@ def traverse_rays(bvh: BVH, points, directions, alg=None, *, start_level: int = 
         raise ArgumentError("bvh.built_level <= start_level <= bvh.tree.levels <= 32 must hold")
     I = bvh.index_dtype
     nrays = p.shape[0]
-    if nrays == 0:                                                                    # leaf_vs_tree.jl:22-26
+    if nrays == 0 and peer is None:                                                   # leaf_vs_tree.jl:22-26
         return BVHTraversal(start_level, 0, 0, 0, DeviceArray.empty(0, pair_dtype(I), device), DeviceArray.empty(0, pair_dtype(I), device))
     cb = bvh._c_bvh()
 
-    def call(flags, p_counts, p_contacts, capacity, total):
-        params = capi.TraverseParams(int(start_level), 0, -1, flags, 0, int(id_base))
-        with torch.cuda.device(device.index):
-            return lib.ibvh_traverse_rays(bvh._handle, C.byref(cb), p.data_ptr(), d.data_ptr(), nrays, C.byref(params), p_counts,
-                                          p_contacts, capacity, C.byref(total), _stream_ptr(device.index))
+    def call(flags, p_counts, p_contacts, capacity, total, peer_ref=None):
+        params = capi.TraverseParams(int(start_level), 0, -1, flags, 0, int(id_base), peer_ref)
+        return lib.ibvh_traverse_rays(bvh._handle, C.byref(cb), p.data_ptr() if nrays else None, d.data_ptr() if nrays else None, nrays,
+                                      C.byref(params), p_counts, p_contacts, capacity, C.byref(total), _stream_ptr(device.index))
 
+    if peer is not None:
+        # fused ray traversal + all-gather (collective): the hits of ALL ranks' ray shards land in every rank's list
+        if ordered:
+            raise ArgumentError("the fused multi-GPU ray traversal is unordered (ordered=False)")
+        if peer.pair_bytes != pair_dtype(I).itemsize or peer.device != device:
+            raise ArgumentError("PeerGather pair size / device do not match the BVH")
+        total = C.c_int64(0)
+        rc = call(capi.TRAVERSE_UNORDERED, None, None, 0, total, peer.next_fused())
+        if rc != capi.OK:
+            _raise(rc, bvh._handle, f"fused traverse_rays (gathered total {total.value} hits)")
+        c2 = cache.cache2 if cache is not None else DeviceArray.empty(0, I, device)
+        return BVHTraversal(start_level, 0, 0, int(total.value), DeviceArray(peer.list_area(), pair_dtype(I)), c2)
     total, c1, c2 = _run_two_phase(call, bvh._handle, device, I, nrays, cache, ordered, False)
     return BVHTraversal(start_level, 0, 0, total, c1, c2)
 

@@ -370,7 +370,8 @@ int launch_traverse(ibvh_handle* h, const LQ* qleaves, const typename LT::value_
                     IBVH_CUDA_TRY(h, cudaMemsetAsync(ticket, 0, 8, st));
                     const unsigned pblocks = (unsigned)std::min<int64_t>(blocks, (int64_t)h->sm_count * 12);
                     { ProfScope _ps(h, st, "rays_persistent_kernel");
-                    rays_persistent_kernel<MODE, LT, N, I><<<pblocks, 128, 0, st>>>(points, dirs, bvh, a, counts, contacts, ticket);
+                    if (a.peer && MODE == kAtomic) rays_persistent_kernel<MODE, LT, N, I, (MODE == kAtomic ? 512 : 128)><<<pblocks, 128, 0, st>>>(points, dirs, bvh, a, counts, contacts, ticket);
+                    else rays_persistent_kernel<MODE, LT, N, I><<<pblocks, 128, 0, st>>>(points, dirs, bvh, a, counts, contacts, ticket);
                     }
                 }
                 IBVH_LAUNCH_CHECK(h, "rays_kernel");
@@ -397,9 +398,34 @@ int traverse_impl(ibvh_handle* h, const LQ* qleaves, const typename LT::value_ty
     if (want_stats) { IBVH_CUDA_TRY(h, cudaMemsetAsync(d_stats, 0, 32, st)); a.stats = d_stats; }
     a.capacity = d_contacts ? capacity : 0;
     *num_contacts = 0;
-    if (a.q_count <= 0) return IBVH_OK;
+    if (a.q_count <= 0 && !(KIND == kRays && a.peer)) return IBVH_OK;      // (a fused call is collective: an empty shard still joins)
     const bool unordered = (flags & IBVH_TRAVERSE_UNORDERED) != 0 && d_contacts != nullptr;
     int rc;
+    if constexpr (KIND == kRays) {
+        if (a.peer) {
+            // fused ray traversal + all-gather of the hits (see traverse_pyramid for the contact version)
+            if (!(flags & IBVH_TRAVERSE_UNORDERED) || !peer_ok(a.peer) || !a.peer->multicast || a.peer->fused_seq == 0 ||
+                getenv("IBVH_RAYS_REFERENCE_SHAPED") || getenv("IBVH_RAYS_STATIC")) {
+                h->set_error("fused multi-GPU ray traversal needs IBVH_TRAVERSE_UNORDERED, the persistent schedule and a multicast alias");
+                return IBVH_ERR_UNSUPPORTED;
+            }
+            PeerArgs pa = make_peer_args(a.peer);
+            a.total = (unsigned long long*)pa.buf[0] + kPeerCounterSlot + pa.fused_seq % 3;
+            a.capacity = pa.capacity_bytes / (int64_t)sizeof(IndexPair<I>);
+            rc = a.q_count > 0 ? launch_traverse<KIND, kAtomic, PACKET, LQ, LT, N, I>(h, qleaves, points, dirs, bvh, a, (I*)nullptr, (IndexPair<I>*)(pa.mc + pa.header_bytes), st) : IBVH_OK;
+            if (rc != IBVH_OK) return rc;
+            int64_t* h_peer = (int64_t*)(h->h_pinned + 3072);
+            h_peer[1] = -1;
+            { ProfScope _ps(h, st, "peer_fused_finish_kernel");
+            peer_fused_finish_kernel<<<1, 32, 0, st>>>(pa, h_peer);
+            }
+            IBVH_LAUNCH_CHECK(h, "peer_fused_finish_kernel");
+            IBVH_CUDA_TRY(h, cudaStreamSynchronize(st));
+            if (h_peer[1] != 0) { h->set_error("fused ray traversal: a peer did not finish its shard within 10 s"); return IBVH_ERR_PEER; }
+            *num_contacts = h_peer[0];
+            return *num_contacts > a.capacity ? IBVH_ERR_CAPACITY : IBVH_OK;
+        }
+    }
     if (unordered) {
         IBVH_CUDA_TRY(h, cudaMemsetAsync(d_total, 0, 8, st));
         rc = launch_traverse<KIND, kAtomic, PACKET, LQ, LT, N, I>(h, qleaves, points, dirs, bvh, a, (I*)nullptr, (IndexPair<I>*)d_contacts, st);
@@ -1330,15 +1356,14 @@ int ibvh_traverse_pair(ibvh_handle_t* h, const ibvh_bvh_t* queries, const ibvh_b
 #if defined(IBVH_PART_RAYS) || defined(IBVH_PART_ALL)
 int ibvh_traverse_rays(ibvh_handle_t* h, const ibvh_bvh_t* bvh, const void* d_points, const void* d_directions, int64_t nrays,
                        const ibvh_traverse_params_t* p, void* d_counts, void* d_contacts, int64_t capacity, int64_t* num_contacts, void* stream) {
-    if (p && p->peer) { if (h) h->set_error("rays: no fused mode; traverse the ray shard, then ibvh_allgather_pairs"); return IBVH_ERR_UNSUPPORTED; }
     if (!h || !p || !num_contacts || nrays < 0) return IBVH_ERR_ARGUMENT;
     ibvh_tree_t tree;
     int rc = check_bvh(bvh, &tree);
     if (rc != IBVH_OK) return rc;
     if (!(bvh->built_level <= p->start_level && p->start_level <= tree.levels)) return IBVH_ERR_ARGUMENT;   // leaf_vs_tree.jl:11-15
     *num_contacts = 0;
-    if (nrays == 0) return IBVH_OK;                                           // leaf_vs_tree.jl:22-26
-    if (!d_points || !d_directions) return IBVH_ERR_ARGUMENT;
+    if (nrays == 0 && !p->peer) return IBVH_OK;                               // leaf_vs_tree.jl:22-26
+    if (nrays > 0 && (!d_points || !d_directions)) return IBVH_ERR_ARGUMENT;
     DeviceGuard g(h->device);
     cudaStream_t st = (cudaStream_t)stream;
     return dispatch_leaf(bvh->types, [&](auto tag) -> int {
@@ -1351,6 +1376,7 @@ int ibvh_traverse_rays(ibvh_handle_t* h, const ibvh_bvh_t* bvh, const void* d_po
             a.start_level = (int32_t)p->start_level;
             a.flip = 0;
             a.id_base = p->id_base;
+            a.peer = p->peer;
             return traverse_impl<kRays, false, L, L, N, I>(h, (const L*)nullptr, (const T*)d_points, (const T*)d_directions, d, a, p->flags,
                                                            d_counts, d_contacts, capacity, num_contacts, st);
         });

@@ -19,6 +19,7 @@
 //    ones), control flow never diverges, and the per-lane mask keeps the ancestor predicate exact.
 #pragma once
 #include "common.cuh"
+#include "peer.cuh"
 
 namespace ibvh {
 
@@ -300,18 +301,23 @@ __global__ void __launch_bounds__(128) rays_kernel(const typename LT::value_type
 // its longest ray is done with a handful of lanes active (measured: 4.2 of 32). Here every warp keeps
 // pulling rays from a global ticket counter and a lane that finishes its ray is refilled, so the lanes
 // stay busy. Which lane handles a ray is irrelevant for the results: counts / offsets are per ray id.
-template <int MODE, class LT, class N, class I>
+// HB > 128 = the fused multi-GPU variant (ibvh_traverse_params_t.peer, unordered): `a.total` is the output-slot
+// counter on rank 0 (system-scope atomic over NVLink) and `contacts` the multicast alias of every rank's hit list;
+// a warp then reserves slots for >= HB - 128 hits at a time, because that ONE counter sustains ~190 M atomics/s
+// for all ranks together, and writes two hits per 16-byte multimem.st.
+template <int MODE, class LT, class N, class I, int HB = 128>
 __global__ void __launch_bounds__(128) rays_persistent_kernel(const typename LT::value_type* __restrict__ points,
                                                              const typename LT::value_type* __restrict__ dirs,
                                                              DBvh<LT, N> bvh, TraverseArgs a, I* counts, IndexPair<I>* contacts,
                                                              unsigned long long* ticket) {
+    constexpr bool kFused = HB > 128;
     using T = typename LT::value_type;
     using V = typename LT::vol_t;
     __shared__ uint32_t s_skip[34];
     __shared__ uint32_t s_nreal[34];
     // unordered mode: hits are pushed into a per-warp buffer (shared-memory atomic slot counter) and flushed
     // 32 at a time at the warp-uniform top of the loop: one global atomic + one coalesced store per 32 hits
-    __shared__ IndexPair<I> s_hit[4][MODE == kAtomic ? 128 : 1];
+    __shared__ IndexPair<I> s_hit[4][MODE == kAtomic ? HB : 1];
     __shared__ unsigned int s_nhit[4];
     for (int i = threadIdx.x; i < 34; i += blockDim.x) { s_skip[i] = (uint32_t)bvh.ti.skips[i]; s_nreal[i] = (uint32_t)bvh.ti.level_nreal[i]; }
     if (threadIdx.x < 4) s_nhit[threadIdx.x] = 0;
@@ -352,7 +358,30 @@ __global__ void __launch_bounds__(128) rays_persistent_kernel(const typename LT:
         if constexpr (MODE == kAtomic) {
             __syncwarp();
             unsigned int n = s_nhit[w];
-            while (n >= 32u || (all && n > 0u)) {
+            if constexpr (kFused) {
+                if (n >= (unsigned)(HB - 128) || (all && n > 0u)) {
+                    unsigned long long base = 0;
+                    if (lane == 0) base = atomicAdd_system(a.total, (unsigned long long)n);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if ((int64_t)(base + n) <= a.capacity) {
+                        if constexpr (sizeof(IndexPair<I>) == 8) {
+                            const unsigned head = (unsigned)(base & 1ull), npair = (n - head) >> 1;
+                            for (unsigned k = lane; k < npair; k += 32) {
+                                const IndexPair<I> p0 = s_hit[w][head + 2 * k], p1 = s_hit[w][head + 2 * k + 1];
+                                uint4 v;
+                                v.x = (uint32_t)p0.a; v.y = (uint32_t)p0.b; v.z = (uint32_t)p1.a; v.w = (uint32_t)p1.b;
+                                multimem_st_v4(contacts + base + head + 2 * k, v);
+                            }
+                            if (lane == 0 && head) multimem_store_pair(contacts + base, s_hit[w][0]);
+                            if (lane == 1 && ((n - head) & 1u)) multimem_store_pair(contacts + base + n - 1, s_hit[w][n - 1]);
+                        } else {
+                            for (unsigned k = lane; k < n; k += 32) multimem_store_pair(contacts + base + k, s_hit[w][k]);
+                        }
+                    }
+                    n = 0;
+                }
+            }
+            while (!kFused && (n >= 32u || (all && n > 0u))) {
                 const unsigned int take = n >= 32u ? 32u : n;
                 unsigned long long base = 0;
                 if (lane == 0) base = atomicAdd(a.total, (unsigned long long)take);

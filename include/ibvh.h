@@ -125,7 +125,7 @@ typedef struct ibvh_traverse_params {
     int32_t flip;             /* pair only: emit (leaf.index, query.index) — traverse_pair.jl:212-216 */
     int64_t id_base;          /* rays only: ray r of the passed arrays is reported as id_base + r + 1
                                  (0 for a whole problem; the global offset of a per-GPU ray shard)     */
-    const ibvh_peer_t* peer;  /* NULL, or (single / pair, UNORDERED, BBox nodes): fused traversal + all-gather —
+    const ibvh_peer_t* peer;  /* NULL, or (single / pair with BBox nodes, or rays; UNORDERED): fused traversal + all-gather —
                                  every rank traverses its query shard and the contacts of ALL ranks land in
                                  EVERY rank's list area (peer->buffers[r] + header_bytes) while the traversal
                                  runs: output slots are reserved from one counter on rank 0 (system-scope

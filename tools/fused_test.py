@@ -47,6 +47,20 @@ fullp = ib.traverse(bvh, bvh2, ordered=False)
 if pg.peer.multicast and fullp.num_contacts * 8 <= pg.capacity_bytes:
     trp = ib.traverse(bvh, bvh2, ordered=False, query_range=(qb, qe - qb), peer=pg)
     ok &= trp.num_contacts == fullp.num_contacts and bool(torch.equal(sorted_pairs(trp.cache1.tensor, trp.num_contacts), sorted_pairs(fullp.cache1.tensor, fullp.num_contacts)))
+# rays: fused traversal + all-gather of the hits against the single-GPU hit list
+R = 400_000
+rp, rd = synth.random_rays_torch(R, dev, seed=3)
+rp = rp * 0.3 + 0.5                                   # origins inside the unit cube of the sphere scene
+full_r = ib.traverse_rays(bvh, rp, rd, ordered=False)
+pg_r = ibdist.PeerGather(full_r.num_contacts + 1024, 8, dev)
+rb = ibdist.shard_bounds(R, world)[rank]
+if pg_r.peer.multicast:
+    for rep in range(2):
+        fr = ib.traverse_rays(bvh, rp[rb[0]:rb[1]], rd[rb[0]:rb[1]], ordered=False, id_base=rb[0], peer=pg_r)
+        ok &= fr.num_contacts == full_r.num_contacts and bool(torch.equal(sorted_pairs(fr.cache1.tensor, fr.num_contacts), sorted_pairs(full_r.cache1.tensor, full_r.num_contacts)))
+    if rank == 0:
+        print("rays fused:", fr.num_contacts, "hits", "ok" if ok else "MISMATCH", flush=True)
+
 # Int64 indices / UInt64 Morton codes: 16-byte pairs through the same exchange
 opt64 = ib.BVHOptions(index=np.int64, morton=ib.DefaultMortonAlgorithm(np.uint64))
 n64 = max(1000, n // 4)

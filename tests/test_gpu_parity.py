@@ -842,6 +842,16 @@ def test_deferred_traversal_matches_synchronous(ib, O, dev):
     tr = ib.traverse(bvh, cache=small, ordered=False, defer=True)
     assert tr.num_contacts == ref.num_contacts and len(tr.cache1) >= ref.num_contacts
     assert torch.equal(torch.sort(tr.contacts.tensor.view(torch.int64)).values, want)
+    # scratch pair lists sized from a sparse scene, then a dense scene deferred: finish answers IBVH_ERR_AGAIN and
+    # the fall-back repeats the traversal
+    dense = ib.BVH(synth.random_spheres_np(n, seed=13, scale=2.5 * synth.sphere_radius_scale(n)), ib.BBox(), device=dev)
+    refd = ib.traverse(dense, ordered=False)
+    sparse = ib.BVH(synth.random_spheres_np(n, seed=14, scale=0.05 * synth.sphere_radius_scale(n)), ib.BBox(), device=dev)
+    ib.traverse(sparse, ordered=False)
+    cd = ib.BVHTraversal(1, 0, 0, 0, ib.DeviceArray.empty(refd.num_contacts + 64, ib.pair_dtype(), dev), refd.cache2)
+    trd = ib.traverse(dense, cache=cd, ordered=False, defer=True)
+    assert trd.num_contacts == refd.num_contacts
+    assert torch.equal(torch.sort(trd.contacts.tensor.view(torch.int64)).values, torch.sort(refd.contacts.tensor.view(torch.int64)).values)
     # pair traversal
     vols_b = synth.random_spheres_np(n // 2, seed=12, scale=synth.sphere_radius_scale(n))
     bvh_b = ib.BVH(vols_b, ib.BBox(), device=dev)

@@ -120,7 +120,7 @@ IBVH_D void merge_tile_levels(N* nodes, const TreeInfo& ti, int lvl_in, int stop
 template <class L, class SRC, class N, int TILE, int THREADS, bool GATHER>
 __global__ void __launch_bounds__(THREADS) gather_merge_kernel(const SRC* __restrict__ src, const uint32_t* __restrict__ perm,
                                                               const typename L::mor_t* __restrict__ keys_sorted,
-                                                              L* leaves, N* nodes, TreeInfo ti, int stop_level) {
+                                                              L* leaves, N* nodes, TreeInfo ti, int stop_level, int vec) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     L* sleaf = (L*)smem_raw;
     N* sbuf0 = (N*)(smem_raw + ((sizeof(L) * TILE + 15) & ~size_t(15)));
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(THREADS) gather_merge_kernel(const SRC* __rest
 #pragma unroll
         for (int u = 0; u < PER; ++u) {
             int j = threadIdx.x + u * THREADS;
-            if (j < tile_n) wv[u] = GatherSrc<L, SRC>::make(src, pp[u], kk[u]);
+            if (j < tile_n) wv[u] = GatherSrc<L, SRC>::make(src, pp[u], kk[u], vec);
         }
 #pragma unroll
         for (int u = 0; u < PER; ++u) {

@@ -161,7 +161,9 @@ int launch_gather_merge(ibvh_handle* h, const SRC* src, const uint32_t* perm, co
     }
     int64_t tiles = (ti.n + kMergeTile - 1) / kMergeTile;
     { ProfScope _ps(h, st, "gather_merge_kernel");
-    kern<<<(unsigned)tiles, kMergeThreads, gather_smem_bytes<L, N>(), st>>>(src, perm, keys_sorted, leaves, nodes, ti, stop_level);
+    const uintptr_t va = (uintptr_t)src;
+    const int vec = std::is_same<L, SRC>::value ? 8 : (va % 16 == 0 ? 16 : (va % 8 == 0 ? 8 : 4));
+    kern<<<(unsigned)tiles, kMergeThreads, gather_smem_bytes<L, N>(), st>>>(src, perm, keys_sorted, leaves, nodes, ti, stop_level, vec);
     }
     IBVH_LAUNCH_CHECK(h, "gather_merge_kernel");
     return IBVH_OK;

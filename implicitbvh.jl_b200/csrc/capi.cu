@@ -711,18 +711,28 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
         IBVH_CUDA_TRY(h, cudaMemsetAsync(d_total, 0, 8, st));      // (fused: the rank-0 counter is rotated by the finish kernel instead)
 
         // 0. 16-byte aligned records: leaf volumes, and the node levels the refinement reads as targets
-        { ProfScope _ps(h, st, "pyr_pack_volumes_kernel");
-        pyr_pack_volumes_kernel<LT><<<(unsigned)((bvh.ti.n + 8 + 255) / 256), 256, 0, st>>>(bvh.leaves, bvh.ti.n, bvh.ti.n + 8, PT);
-        if (!same_leaves) pyr_pack_volumes_kernel<LQ><<<(unsigned)((n_query_total + 8 + 255) / 256), 256, 0, st>>>(qleaves, n_query_total, n_query_total + 8, PQ);
+        const int64_t qend_c = q_end < n_query_total ? q_end : n_query_total;
+        if (same_leaves) {
+            // targets == queries: one pass packs the volumes AND builds the finest level of the query pyramid
+            const int64_t groups = (bvh.ti.n + 8 + 3) / 4;
+            { ProfScope _ps(h, st, "pyr_pack_groups_kernel");
+            pyr_pack_groups_kernel<LT, T><<<(unsigned)((groups + 255) / 256), 256, 0, st>>>(bvh.leaves, bvh.ti.n, bvh.ti.n + 8, PT, q_begin, qend_c, plan.lv[0], U);
+            }
+            IBVH_LAUNCH_CHECK(h, "pyr_pack_groups_kernel");
+        } else {
+            { ProfScope _ps(h, st, "pyr_pack_volumes_kernel");
+            pyr_pack_volumes_kernel<LT><<<(unsigned)((bvh.ti.n + 8 + 255) / 256), 256, 0, st>>>(bvh.leaves, bvh.ti.n, bvh.ti.n + 8, PT);
+            }
+            IBVH_LAUNCH_CHECK(h, "pyr_pack_volumes_kernel");
+            const int64_t groups = (n_query_total + 8 + 3) / 4;
+            { ProfScope _ps(h, st, "pyr_pack_groups_kernel");
+            pyr_pack_groups_kernel<LQ, T><<<(unsigned)((groups + 255) / 256), 256, 0, st>>>(qleaves, n_query_total, n_query_total + 8, PQ, q_begin, qend_c, plan.lv[0], U);
+            }
+            IBVH_LAUNCH_CHECK(h, "pyr_pack_groups_kernel");
         }
-        IBVH_LAUNCH_CHECK(h, "pyr_pack_volumes_kernel");
         for (int l = 0; l + 1 < nl; ++l)
             IBVH_CUDA_TRY(h, cudaMemcpyAsync(NT + plan.lv[l].t_off, bvh.nodes + plan.lv[l].tnode0, (size_t)plan.lv[l].ntg * sizeof(N), cudaMemcpyDeviceToDevice, st));
-        // 1. query pyramid
-        { ProfScope _ps(h, st, "pyr_leafgroups_kernel");
-        pyr_leafgroups_kernel<LQ, T><<<(unsigned)((plan.lv[0].nqg + 255) / 256), 256, 0, st>>>(qleaves, q_begin, q_end < n_query_total ? q_end : n_query_total, plan.lv[0], U);
-        }
-        IBVH_LAUNCH_CHECK(h, "pyr_leafgroups_kernel");
+        // 1. query pyramid (the finest level was built with the packing pass)
         for (int l = 1; l < nl; ++l) {
             { ProfScope _ps(h, st, "pyr_up_kernel");
             pyr_up_kernel<T><<<(unsigned)((plan.lv[l].nqg + 255) / 256), 256, 0, st>>>(plan.lv[l - 1], plan.lv[l], U);

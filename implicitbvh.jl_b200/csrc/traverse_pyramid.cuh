@@ -121,6 +121,34 @@ __global__ void __launch_bounds__(256) pyr_pack_volumes_kernel(const L* __restri
     store16(out + i, r);
 }
 
+// pack + finest query-pyramid level in one pass over the leaves (one thread per 4-leaf group): the leaves are read
+// once instead of twice. Groups inside the query shard [lv.qg_first, lv.qg_first + lv.nqg) also get their union box.
+template <class L, class T>
+__global__ void __launch_bounds__(256) pyr_pack_groups_kernel(const L* __restrict__ leaves, int64_t n, int64_t n_pad, Packed<typename L::vol_t>* __restrict__ out,
+                                                             int64_t q_begin, int64_t q_end, PyrLevel lv, UBox<T>* __restrict__ U) {
+    constexpr int G = 1 << kPyrLeafLog;
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t i0 = g * G;
+    if (i0 >= n_pad) return;
+    BBox<T> u = empty_box<T>();
+#pragma unroll
+    for (int m = 0; m < G; ++m) {
+        const int64_t i = i0 + m;
+        if (i >= n_pad) break;
+        alignas(16) Packed<typename L::vol_t> r;
+        if (i < n) {
+            memset(&r, 0, sizeof(r));
+            r.v = load_struct(leaves + i).volume;
+            if (i >= q_begin && i < q_end) u = merge(u, NodeOps<BBox<T>>::convert(r.v));
+        } else {
+            memset(&r, 0xFF, sizeof(r));
+        }
+        store16(out + i, r);
+    }
+    const int64_t t = g - lv.qg_first;
+    if (t >= 0 && t < lv.nqg) U[lv.u_off + t].b = u;
+}
+
 // ---- 1. query pyramid ------------------------------------------------------------------------------------
 template <class LQ, class T>
 __global__ void __launch_bounds__(256) pyr_leafgroups_kernel(const LQ* __restrict__ qleaves, int64_t q_begin, int64_t q_end,

@@ -287,7 +287,12 @@ def main():
     # first call sizes the caches; give cache1 head-room so later steps never regrow
     ncontacts = step_device()
     if world > 1 and args.gather in ("peer", "fused"):
-        state["peer"] = ibdist.PeerGather(int(ncontacts * 1.05) + 1024, 8, dev)
+        try:
+            state["peer"] = ibdist.PeerGather(int(ncontacts * 1.05) + 1024, 8, dev)
+        except Exception as ex:                          # no symmetric memory on this box: NCCL collectives instead
+            if rank == 0:
+                print(f"[bench] peer memory unavailable ({ex!r}); gathering with NCCL", file=sys.stderr, flush=True)
+            state["peer"], fused, args.gather = None, False, "nccl"
         if fused and not state["peer"].peer.multicast:
             fused = False                                # no NVLS multicast on this box: two-step peer gather
     if world == 1:
@@ -527,7 +532,10 @@ def main():
         if world > 1 and args.gather != "nccl":
             tot = torch.tensor([rt.num_contacts], dtype=torch.int64, device=dev)
             dist.all_reduce(tot)
-            ray_peer = ibdist.PeerGather(int(int(tot.item()) * 1.02) + 1024, 8, dev)       # hit list of ALL rays on every rank
+            try:
+                ray_peer = ibdist.PeerGather(int(int(tot.item()) * 1.02) + 1024, 8, dev)   # hit list of ALL rays on every rank
+            except Exception:
+                ray_peer = None
 
         rays_fused = ray_peer is not None and args.gather == "fused" and not ordered and bool(ray_peer.peer.multicast)
 

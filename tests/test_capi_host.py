@@ -135,3 +135,40 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.lower() or f == "synth.py" and "oracle" in txt.lower() and "import oracle" not in txt, f
+
+
+def test_ctypes_structs_match_the_header_layout(ib, tmp_path):
+    """The ctypes mirrors of the ABI structs have the sizes and field offsets the C compiler gives include/ibvh.h."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    capi = ib.capi
+    structs = {"ibvh_types_t": capi.Types, "ibvh_tree_t": capi.Tree, "ibvh_bvh_t": capi.Bvh,
+               "ibvh_traverse_params_t": capi.TraverseParams, "ibvh_peer_t": capi.Peer}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "ibvh.h")}"', "int main(void) {"]
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c11", "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    got = {}
+    for ln in out.strip().splitlines():
+        cname, key, val = ln.split()
+        got[(cname, key)] = int(val)
+    for cname, cls in structs.items():
+        assert got[(cname, "size")] == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert got[(cname, fname)] == getattr(cls, fname).offset, (cname, fname)
+    # status codes and flags
+    hdr = open(os.path.join(ROOT, "include", "ibvh.h")).read()
+    for name, val in (("IBVH_ERR_CAPACITY", capi.ERR_CAPACITY), ("IBVH_ERR_PEER", capi.ERR_PEER), ("IBVH_ERR_AGAIN", capi.ERR_AGAIN)):
+        assert re.search(rf"{name}\s*=\s*{val}\b", hdr), name
+    for name, val in (("IBVH_TRAVERSE_UNORDERED", capi.TRAVERSE_UNORDERED), ("IBVH_TRAVERSE_COUNTS_VALID", capi.TRAVERSE_COUNTS_VALID),
+                      ("IBVH_TRAVERSE_DEFER", capi.TRAVERSE_DEFER), ("IBVH_TRAVERSE_WALK", capi.TRAVERSE_WALK), ("IBVH_MAX_PEERS", capi.MAX_PEERS)):
+        assert re.search(rf"#define\s+{name}\s+{val}u?\b", hdr), name

@@ -10,16 +10,26 @@
 // loses a contact, and the final 4 x 4 leaf tiles evaluate P itself.
 //
 // Schedule (no per-thread tree walk, no stacks, every work item is the same size):
+//   0. aligned records: leaf volumes packed to 16-byte records (NaN padding past the end), the target node
+//      levels copied to 64-byte aligned runs, the query pyramid stored as 32-byte boxes — the hot kernels are
+//      bound by the LSU data pipe, and AoS structs read as 8-byte pieces cost 3-7x the wavefronts.
 //   1. query pyramid: exact union boxes of the query leaves at group sizes 4, 32, 256, ... (min / max).
 //   2. top: all pairs (query group, tree node) at the coarsest size (<= 2048 groups per side).
 //   3. refine x (levels): each surviving pair (A, B) expands to its 8 x 8 child pairs; a warp handles 4
-//      pairs per step, lane = (pair slot, child of A), the 8 child boxes of B staged in shared memory.
-//   4. leaf tiles: pairs of 4-leaf groups, lane = (pair slot, query member), 4 leaf tests per lane,
+//      pairs per step, lane = (pair slot, child of A); the 8 child boxes of B are fetched cooperatively as
+//      aligned 16-byte pieces into shared memory and read back as LDS.128 broadcasts; predicate-chained test.
+//   4. leaf tiles: pairs of 4-leaf groups, 16 pairs per warp step, a lane owns TWO query leaves (register
+//      tile 2 x 4), targets travel global -> shared with cp.async (double buffer, conflict-free mapping),
 //      lazy leaf-parent test on a hit.
-// Survivors are appended to flat (A, B) lists through a shared-memory buffer that is flushed 32 entries
-// at a time with one atomic and one coalesced 256-byte store. List sizes stay on the device (the next
-// phase is a persistent grid-stride kernel that reads the count), so the whole traversal needs a single
-// host synchronisation: the read-back of the contact total, as in the reference.
+// Work distribution: warps draw chunks of consecutive list entries from a ticket counter, so the spatial
+// order of the top-level list survives from level to level. Survivors are appended to flat (A, B) lists
+// through a per-warp shared-memory buffer (one shared atomic per lane with hits) that is flushed with one
+// global atomic per >= 256 entries and coalesced stores. List sizes stay on the device (the next phase reads
+// the count), so the whole traversal needs a single host synchronisation: the read-back of the contact
+// total, as in the reference — or none at all in the deferred form (IBVH_TRAVERSE_DEFER).
+// Output modes of the leaf-tile kernel: unordered append; fused multi-GPU append (slots from rank 0's
+// counter, multimem.st into every rank's list); ordered = count per query + stash, then scan, scatter and a
+// per-query register sort (pyr_scatter_kernel, pyr_fixup_kernel).
 #pragma once
 #include "peer.cuh"
 #include <type_traits>

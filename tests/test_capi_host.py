@@ -172,3 +172,21 @@ def test_ctypes_structs_match_the_header_layout(ib, tmp_path):
     for name, val in (("IBVH_TRAVERSE_UNORDERED", capi.TRAVERSE_UNORDERED), ("IBVH_TRAVERSE_COUNTS_VALID", capi.TRAVERSE_COUNTS_VALID),
                       ("IBVH_TRAVERSE_DEFER", capi.TRAVERSE_DEFER), ("IBVH_TRAVERSE_WALK", capi.TRAVERSE_WALK), ("IBVH_MAX_PEERS", capi.MAX_PEERS)):
         assert re.search(rf"#define\s+{name}\s+{val}u?\b", hdr), name
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU oracle timed as the reference arm) prints ONE JSON line with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, IBVH_BENCH_N="200000")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.strip().splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "leaves/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert "workload" in d["config"]

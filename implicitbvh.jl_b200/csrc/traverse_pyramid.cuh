@@ -160,23 +160,6 @@ __global__ void __launch_bounds__(256) pyr_pack_groups_kernel(const L* __restric
 }
 
 // ---- 1. query pyramid ------------------------------------------------------------------------------------
-template <class LQ, class T>
-__global__ void __launch_bounds__(256) pyr_leafgroups_kernel(const LQ* __restrict__ qleaves, int64_t q_begin, int64_t q_end,
-                                                            PyrLevel lv, UBox<T>* __restrict__ U) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= lv.nqg) return;
-    const int64_t q0 = (lv.qg_first + t) << kPyrLeafLog;
-    BBox<T> u = empty_box<T>();
-#pragma unroll
-    for (int m = 0; m < (1 << kPyrLeafLog); ++m) {
-        int64_t q = q0 + m;
-        if (q >= q_begin && q < q_end) {
-            LQ leaf = load_struct(qleaves + q);
-            u = merge(u, NodeOps<BBox<T>>::convert(leaf.volume));
-        }
-    }
-    U[lv.u_off + t].b = u;
-}
 template <class T>
 __global__ void __launch_bounds__(256) pyr_up_kernel(PyrLevel fine, PyrLevel coarse, UBox<T>* __restrict__ U) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -415,8 +398,6 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_leaf_tile_kernel(const LQ*
     constexpr bool kNeedParent = !std::is_same<VT, N>::value || !std::is_same<VQ, N>::value;   // box leaves: implied by the leaf test
     using TVol = Packed<VT>;
     constexpr int TPIECES = G * (int)sizeof(TVol) / 16;                    // 16-byte pieces of one target group
-    constexpr int PPL = TPIECES / LPP;                                     // pieces copied per lane
-    static_assert(TPIECES % LPP == 0, "pieces split evenly over the lanes of a pair");
     constexpr int SLOT_BYTES = G * (int)sizeof(TVol) + 16;                 // + 16: neighbouring slots start in different banks
     // target volumes of the current and the next step (cp.async double buffer)
     __shared__ __align__(16) unsigned char s_vraw[kPyrWarps][2][SLOTS][SLOT_BYTES];

@@ -75,6 +75,7 @@ struct PairList {
 #ifndef IBVH_PYR_CHUNK_MAX
 #define IBVH_PYR_CHUNK_MAX 32
 #endif
+// (measured on the leaf-tile kernel, 10 M leaves: chunk maximum 4 / 8 / 32 / 64 / 128 steps -> 1.33 / 1.28 / 1.25 / 1.29 / 1.30 ms)
 // steps per ticket chunk: up to 32, fewer for short lists so that every resident warp still gets ~4 chunks
 IBVH_D uint32_t pyr_chunk_steps(uint32_t count, int slots) {
     const uint32_t warps = gridDim.x * (uint32_t)kPyrWarps;

@@ -14,6 +14,7 @@ structured dtype that describes one element (the stand-in for `CuVector{Bounding
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from dataclasses import dataclass, field
 from typing import Optional, Union
 
@@ -207,6 +208,36 @@ def _stream_ptr(device_index: int) -> int:
     return torch.cuda.current_stream(device_index).cuda_stream
 
 
+# At most one deferred traversal (traverse(..., defer=True)) is outstanding per device handle. The registry lets
+# the calls that would invalidate it — another traversal on the handle, a build that overwrites buffers of the BVH
+# it still reads — resolve it first, and lets a dropped result cancel itself.
+_outstanding = {}                # device index -> weakref to the pending BVHTraversal
+
+
+def _pending_on(device_index: int):
+    ref = _outstanding.get(device_index)
+    tr = ref() if ref is not None else None
+    if tr is None or tr._resolve is None:
+        _outstanding.pop(device_index, None)
+        return None
+    return tr
+
+
+def _resolve_outstanding(device_index: int):
+    """Finish the deferred traversal outstanding on this device, if any (blocks until its count is known)."""
+    tr = _pending_on(device_index)
+    if tr is not None:
+        tr.num_contacts                     # noqa: B018 — property access resolves it
+    _outstanding.pop(device_index, None)
+
+
+def _overlaps(a: "DeviceArray", b: "DeviceArray") -> bool:
+    if a is None or b is None or a.tensor.numel() == 0 or b.tensor.numel() == 0 or a.device != b.device:
+        return False
+    a0, b0 = a.ptr, b.ptr
+    return a0 < b0 + b.tensor.numel() and b0 < a0 + a.tensor.numel()
+
+
 # ---------------------------------------------------------------------------------------------
 # options (utils.jl:34-93), Morton algorithm (morton/default.jl:22-42), traversal algorithm tag
 # ---------------------------------------------------------------------------------------------
@@ -374,13 +405,24 @@ class BVH:
             _raise(rc, self._handle, "compute_build_level")
         self.built_level = int(out.value)
 
+        # A deferred traversal may still be outstanding on this device. If it has to be repeated when it is resolved
+        # (IBVH_ERR_AGAIN / IBVH_ERR_CAPACITY) it reads its BVH again, so that BVH's buffers must not be overwritten by
+        # this build: an in-place build over its leaves resolves the traversal first, and its node buffer is not
+        # taken over from `cache` (a fresh one is allocated; the caching allocator ping-pongs two buffers).
+        pending = _pending_on(didx)
+        pending_bvhs = pending._bvhs if pending is not None else ()
+        if wrapped_input and any(_overlaps(src, b.leaves) for b in pending_bvhs):
+            _resolve_outstanding(didx)
+            pending_bvhs = ()
+
         # nodes: reuse from cache when the type matches (build.jl:256-263)
         num_nodes = self.tree.real_nodes - self.tree.real_leaves
         self.node_type = node_type
         if cache is not None:
             if cache.nodes.dtype != node_type.dtype:
                 raise ArgumentError("eltype(cache.nodes) === N must hold")
-            if len(cache.nodes) == num_nodes and cache.nodes.device == src.device:
+            nodes_busy = any(_overlaps(cache.nodes, b.nodes) for b in pending_bvhs)
+            if len(cache.nodes) == num_nodes and cache.nodes.device == src.device and not nodes_busy:
                 self.nodes = cache.nodes
             else:
                 self.nodes = DeviceArray.empty(num_nodes, node_type.dtype, src.device)
@@ -428,13 +470,27 @@ class BVHTraversal:
         self.num_checks = int(num_checks)
         self._num_contacts = int(num_contacts)
         self._resolve = None                  # deferred traversal (traverse(..., defer=True)): resolves on first use
+        self._cancel = None                   # ... or is cancelled when the result is dropped unread
+        self._bvhs = ()                       # the BVHs a pending deferred traversal still needs intact
         self.cache1, self.cache2 = cache1, cache2
+
+    def __del__(self):
+        cancel = getattr(self, "_cancel", None)
+        if cancel is not None and getattr(self, "_resolve", None) is not None:
+            try:
+                cancel()
+            except Exception:
+                pass
 
     @property
     def num_contacts(self) -> int:
         if self._resolve is not None:
             resolve, self._resolve = self._resolve, None
-            resolve(self)
+            self._cancel = None
+            try:
+                resolve(self)
+            finally:
+                self._bvhs = ()
         return self._num_contacts
 
     @num_contacts.setter
@@ -466,8 +522,11 @@ class _Pending:
     def __init__(self, handle):
         self.handle = handle
 
-    def attach(self, tr: "BVHTraversal", rerun):
+    def attach(self, tr: "BVHTraversal", rerun, bvhs=(), device_index: int = 0):
         handle = self.handle
+        tr._bvhs = tuple(bvhs)
+        tr._cancel = lambda: capi.lib().ibvh_traverse_cancel(handle)
+        _outstanding[device_index] = weakref.ref(tr)
 
         def resolve(t: "BVHTraversal"):
             total = C.c_int64(0)
@@ -560,6 +619,7 @@ def traverse(bvh: BVH, bvh2=None, alg=None, *, start_level: Optional[int] = None
         raise ArgumentError(f"Traversal algorithm not implemented: {alg}")
     _check_narrow(narrow)
     lib = capi.lib()
+    _resolve_outstanding(bvh.leaves.device.index)      # one deferred traversal per handle: a new one finishes the old one first
     qb, qc = (0, -1) if query_range is None else (int(query_range[0]), int(query_range[1]))
     if peer is not None and (ordered or reference_shaped or packet or walk):
         raise ArgumentError("the fused multi-GPU traversal is the unordered default schedule (ordered=False)")
@@ -604,7 +664,8 @@ def traverse(bvh: BVH, bvh2=None, alg=None, *, start_level: Optional[int] = None
         total, c1, c2 = run(call, bvh._handle, device, I, nq)
         if isinstance(total, _Pending):
             return total.attach(BVHTraversal(sl, 0, 0, 0, c1, c2),
-                                lambda: traverse(bvh, start_level=sl, cache=BVHTraversal(sl, 0, 0, 0, c1, c2), ordered=False, query_range=query_range))
+                                lambda: traverse(bvh, start_level=sl, cache=BVHTraversal(sl, 0, 0, 0, c1, c2), ordered=False, query_range=query_range),
+                                bvhs=(bvh,), device_index=device.index)
         return BVHTraversal(sl, 0, 0, total, c1, c2)
 
     # pair — traverse_pair.jl:1-116
@@ -634,7 +695,8 @@ def traverse(bvh: BVH, bvh2=None, alg=None, *, start_level: Optional[int] = None
     if isinstance(total, _Pending):
         return total.attach(BVHTraversal(sl1, sl2, 0, 0, c1, c2),
                             lambda: traverse(bvh, bvh2, start_level1=sl1, start_level2=sl2, cache=BVHTraversal(sl1, sl2, 0, 0, c1, c2),
-                                             ordered=False, query_range=query_range))
+                                             ordered=False, query_range=query_range),
+                            bvhs=(bvh, bvh2), device_index=device.index)
     return BVHTraversal(sl1, sl2, 0, total, c1, c2)
 
 
@@ -652,6 +714,7 @@ def traverse_rays(bvh: BVH, points, directions, alg=None, *, start_level: int = 
     lib = capi.lib()
     T = {4: np.float32, 8: np.float64}[bvh.types.float_bytes]
     device = bvh.leaves.device
+    _resolve_outstanding(device.index)                 # (the ray traversal shares the handle's read-back slots)
 
     def to_dev(a):
         if isinstance(a, torch.Tensor):

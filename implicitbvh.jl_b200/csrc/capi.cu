@@ -96,29 +96,20 @@ int grid_for(int64_t n, int threads, int per_thread, int cap) {
 
 // ---- radix sort driver ---------------------------------------------------------------------------------
 // keysA holds the input keys; hist holds the raw per-pass histograms. On return the sorted keys / the
-// permutation are in *keys_out / *vals_out (one of the ping-pong buffers).
+// permutation are in *keys_out / *vals_out (one of the ping-pong buffers). The look-back words are 32-bit
+// (2 flag bits + a 30-bit prefix) below 2^30 leaves and 64-bit from there to the 2^31 that levels <= 32 allows.
+inline bool sort_wide_lookback(int64_t n) { return n >= (int64_t(1) << 30); }
+
 template <class M>
 int sort_pairs(ibvh_handle* h, M* keysA, M* keysB, uint32_t* valsA, uint32_t* valsB, int64_t n, uint32_t* hist,
-               uint32_t* lookback, uint32_t* tickets, cudaStream_t st, M** keys_out, uint32_t** vals_out) {
-    constexpr int P = radix_passes<M>();
-    const int64_t tiles = (n + sort_tile<M>() - 1) / sort_tile<M>();
-    { ProfScope _ps(h, st, "scan_hist_kernel");
-    scan_hist_kernel<<<P, 256, 0, st>>>(hist);
-    }
-    IBVH_LAUNCH_CHECK(h, "scan_hist_kernel");
-    M* kin = keysA; M* kout = keysB;
-    uint32_t* vin = nullptr; uint32_t* vout = valsB; uint32_t* vother = valsA;
-    for (int p = 0; p < P; ++p) {
-        { ProfScope _ps(h, st, "onesweep_kernel");
-        onesweep_kernel<M><<<(unsigned)tiles, kSortThreads, 0, st>>>(kin, kout, vin, vout, n, hist + p * kRadixBins,
-                                                                    lookback + (size_t)p * tiles * kRadixBins, tickets + p, p * kRadixBits);
-        }
-        IBVH_LAUNCH_CHECK(h, "onesweep_kernel");
-        M* tk = kin; kin = kout; kout = tk;
-        uint32_t* nv = vout; vout = vother; vother = nv; vin = nv;
-    }
-    *keys_out = kin;
-    *vals_out = vin;
+               void* lookback, uint32_t* tickets, cudaStream_t st, M** keys_out, uint32_t** vals_out) {
+    auto scope = [&](const char* name) { return ProfScope(h, st, name); };
+    cudaError_t e;
+    if (sort_wide_lookback(n) || h->cfg.force_wide_lookback)
+        e = sort_pairs_impl<M, unsigned long long, kSortThreads, sort_items<M>(), IBVH_SORT_MINB>(keysA, keysB, valsA, valsB, n, hist, lookback, tickets, st, keys_out, vals_out, scope);
+    else
+        e = sort_pairs_impl<M, uint32_t, kSortThreads, sort_items<M>(), IBVH_SORT_MINB>(keysA, keysB, valsA, valsB, n, hist, lookback, tickets, st, keys_out, vals_out, scope);
+    if (e != cudaSuccess) { h->set_cuda_error(e, "onesweep_kernel"); return IBVH_ERR_CUDA; }
     return IBVH_OK;
 }
 
@@ -170,7 +161,7 @@ int launch_gather_merge(ibvh_handle* h, const SRC* src, const uint32_t* perm, co
 }
 
 struct SortScratch {
-    void* keysA; void* keysB; uint32_t* valsA; uint32_t* valsB; uint32_t* hist; uint32_t* lookback; uint32_t* tickets; void* copy;
+    void* keysA; void* keysB; uint32_t* valsA; uint32_t* valsB; uint32_t* hist; void* lookback; uint32_t* tickets; void* copy;
 };
 
 template <class L> size_t build_workspace_bytes(int64_t n, bool need_copy) {
@@ -181,7 +172,7 @@ template <class L> size_t build_workspace_bytes(int64_t n, bool need_copy) {
     b += 2 * ibvh_handle::padded((size_t)n * sizeof(M));
     b += 2 * ibvh_handle::padded((size_t)n * 4);
     b += ibvh_handle::padded((size_t)P * kRadixBins * 4);
-    b += ibvh_handle::padded((size_t)P * tiles * kRadixBins * 4);
+    b += ibvh_handle::padded((size_t)P * tiles * kRadixBins * 8);       // (8-byte look-back words from 2^30 leaves; sized for them always)
     if (need_copy) b += ibvh_handle::padded((size_t)n * sizeof(L));
     return b + 4096;
 }
@@ -189,7 +180,8 @@ template <class L> size_t build_workspace_bytes(int64_t n, bool need_copy) {
 template <class L> int carve_sort_scratch(ibvh_handle* h, int64_t n, bool need_copy, SortScratch* s, cudaStream_t st) {
     using M = typename L::mor_t;
     constexpr int P = radix_passes<M>();
-    if (n >= (int64_t(1) << 30)) { h->set_error("n >= 2^30 leaves not supported by the 32-bit look-back words of this build"); return IBVH_ERR_UNSUPPORTED; }
+    if (n > (int64_t(1) << 31)) { h->set_error("n > 2^31 leaves: the implicit tree would need more than 32 levels"); return IBVH_ERR_UNSUPPORTED; }
+    const size_t lb_bytes = (sort_wide_lookback(n) || h->cfg.force_wide_lookback) ? 8 : 4;
     const int64_t tiles = (n + sort_tile<M>() - 1) / sort_tile<M>();
     int rc = h->reserve(build_workspace_bytes<L>(n, need_copy));
     if (rc != IBVH_OK) return rc;
@@ -197,11 +189,11 @@ template <class L> int carve_sort_scratch(ibvh_handle* h, int64_t n, bool need_c
     s->keysA = h->alloc<M>(n); s->keysB = h->alloc<M>(n);
     s->valsA = h->alloc<uint32_t>(n); s->valsB = h->alloc<uint32_t>(n);
     s->hist = h->alloc<uint32_t>((size_t)P * kRadixBins);
-    s->lookback = h->alloc<uint32_t>((size_t)P * tiles * kRadixBins);
+    s->lookback = h->alloc<unsigned char>((size_t)P * tiles * kRadixBins * lb_bytes);
     s->copy = need_copy ? (void*)h->alloc<L>(n) : nullptr;
     s->tickets = (uint32_t*)(h->d_small + kSmallTickets);
     if (!s->keysA || !s->keysB || !s->valsA || !s->valsB || !s->hist || !s->lookback || (need_copy && !s->copy)) { h->set_error("workspace carve failed"); return IBVH_ERR_ALLOC; }
-    IBVH_CUDA_TRY(h, cudaMemsetAsync(s->lookback, 0, (size_t)P * tiles * kRadixBins * 4, st));
+    IBVH_CUDA_TRY(h, cudaMemsetAsync(s->lookback, 0, (size_t)P * tiles * kRadixBins * lb_bytes, st));
     return IBVH_OK;
 }
 
@@ -281,7 +273,7 @@ int build_impl(ibvh_handle* h, const void* d_volumes, void* d_leaves, int64_t n,
     // the level above the leaves is always produced (build.jl:369), further levels down to built_level
     int stop_level = (int)(built_level < tree.levels - 1 ? built_level : tree.levels - 1);
     if (stop_level < 1) stop_level = 1;
-    if (getenv("IBVH_FUSED_GATHER")) {
+    if (h->cfg.fused_gather) {
         if (wrap) rc = launch_gather_merge<L, V, N, true>(h, (const V*)d_volumes, perm, keys_sorted, (L*)d_leaves, (N*)d_nodes, ti, stop_level, st);
         else rc = launch_gather_merge<L, L, N, true>(h, (const L*)s.copy, perm, keys_sorted, (L*)d_leaves, (N*)d_nodes, ti, stop_level, st);
     } else {
@@ -362,8 +354,8 @@ int launch_traverse(ibvh_handle* h, const LQ* qleaves, const typename LT::value_
         const int64_t blocks = (a.q_count + 127) / 128;
         if constexpr (KIND == kRays) {
             // rays: stackless two-children schedule (IBVH_RAYS_REFERENCE_SHAPED=1 keeps the reference-shaped proxy)
-            if (!getenv("IBVH_RAYS_REFERENCE_SHAPED")) {
-                if (getenv("IBVH_RAYS_STATIC")) {
+            if (!h->cfg.rays_reference_shaped) {
+                if (h->cfg.rays_static) {
                     { ProfScope _ps(h, st, "rays_kernel");
                     rays_kernel<MODE, LT, N, I><<<(unsigned)blocks, 128, 0, st>>>(points, dirs, bvh, a, counts, contacts);
                     }
@@ -407,7 +399,7 @@ int traverse_impl(ibvh_handle* h, const LQ* qleaves, const typename LT::value_ty
         if (a.peer) {
             // fused ray traversal + all-gather of the hits (see traverse_pyramid for the contact version)
             if (!(flags & IBVH_TRAVERSE_UNORDERED) || !peer_ok(a.peer) || !a.peer->multicast || a.peer->fused_seq == 0 ||
-                getenv("IBVH_RAYS_REFERENCE_SHAPED") || getenv("IBVH_RAYS_STATIC")) {
+                h->cfg.rays_reference_shaped || h->cfg.rays_static) {
                 h->set_error("fused multi-GPU ray traversal needs IBVH_TRAVERSE_UNORDERED, the persistent schedule and a multicast alias");
                 return IBVH_ERR_UNSUPPORTED;
             }
@@ -499,7 +491,7 @@ int traverse_tiled(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, con
     a.seg_cap = kTileSegCap; a.step_cap = kTileStepCap;
     a.capacity = d_contacts ? capacity : 0; a.total = d_total;
     a.dbg = nullptr;
-    const bool dbg = getenv("IBVH_DEBUG") != nullptr;
+    const bool dbg = h->cfg.debug;
     if (dbg) { a.dbg = (unsigned long long*)(h->d_small + 1024); IBVH_CUDA_TRY(h, cudaMemsetAsync(a.dbg, 0, 640, st)); }
     const bool unordered = (flags & IBVH_TRAVERSE_UNORDERED) != 0 && d_contacts != nullptr;
     const int64_t qblocks = (a.q_count + kScanTile - 1) / kScanTile;
@@ -661,7 +653,7 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
     // the hits, then scan + scatter into the query segments (instead of a count pass and a write pass of the tile kernel)
     const bool stash_mode = !unordered && !count_only && capacity > 0 && !((flags & IBVH_TRAVERSE_COUNTS_VALID) && d_counts);
     const int nl = plan.n;
-    const int grid = h->sm_count * (getenv("IBVH_PYR_GRID") ? atoi(getenv("IBVH_PYR_GRID")) : 20);
+    const int grid = h->sm_count * h->cfg.pyr_grid;
 
     // ordered protocol scratch: counts (if the caller gave none), cursors, scan sums
     const int64_t qblocks = (ta.q_count + kScanTile - 1) / kScanTile;
@@ -785,7 +777,7 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
                 h->last_stats[3] = nl;
             }
             { ProfScope _ps(h, st, "pyr_leaf_tile_kernel");
-            const int big = getenv("IBVH_FUSED_FLUSH") ? atoi(getenv("IBVH_FUSED_FLUSH")) >= 512 : pa.world >= 4;
+            const int big = h->cfg.fused_flush >= 0 ? h->cfg.fused_flush >= 512 : pa.world >= 4;
             if (big)
                 pyr_leaf_tile_kernel<KIND, kAtomic, 0, LQ, LT, I, (sizeof(typename LT::vol_t) > 32 ? 256 : 512)><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, capacity, out_total, (I*)nullptr, nullptr, out_ptr, 1, d_tick + 16 + (tile_launch++), PQ, PT);
             else
@@ -860,7 +852,7 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
             double r = (double)c / (double)plan.lv[l].nqg;
             if (l < nl - 1 && r > worst) worst = r;
         }
-        if (getenv("IBVH_DEBUG")) {
+        if (h->cfg.debug) {
             fprintf(stderr, "[ibvh debug] pyramid levels=%d:", nl);
             for (int l = nl - 1; l >= 0; --l) fprintf(stderr, " k=%d pairs=%llu/%llu", plan.lv[l].k, hp[1 + l], cap[l]);
             fprintf(stderr, " contacts=%llu%s\n", hp[0], overflow ? " OVERFLOW -> retry" : "");
@@ -1058,6 +1050,7 @@ int ibvh_create(ibvh_handle_t** out, int device) {
     ibvh_handle* h = new (std::nothrow) ibvh_handle();
     if (!h) return IBVH_ERR_ALLOC;
     h->device = device;
+    h->cfg.parse();                      // environment knobs: read once here, never on the call path
     DeviceGuard g(device);
     cudaDeviceProp prop;
     if (!g.ok || cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete h; cudaGetLastError(); return IBVH_ERR_CUDA; }

@@ -3,6 +3,7 @@
 // AK.mapreduce) and a small pinned host block for scalar read-backs.
 #pragma once
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -11,6 +12,31 @@ struct ibvh_handle {
     int device = 0;
     int sm_count = 148;
     char err[512] = {0};
+
+    // development / debug knobs: environment variables read ONCE, at ibvh_create (never on the call path)
+    struct Config {
+        bool fused_gather = false;            // IBVH_FUSED_GATHER: gather fused into the bottom-level merge kernel
+        bool rays_reference_shaped = false;   // IBVH_RAYS_REFERENCE_SHAPED: one thread per ray, local stack (proxy of the reference kernel)
+        bool rays_static = false;             // IBVH_RAYS_STATIC: one ray per thread, no persistent refill
+        bool debug = false;                   // IBVH_DEBUG: print schedule statistics to stderr
+        bool peer_no_multicast = false;       // IBVH_PEER_NO_MULTICAST: plain peer stores instead of multimem.st
+        bool force_wide_lookback = false;     // IBVH_SORT_WIDE_LOOKBACK: 64-bit look-back words at any size (tests the n >= 2^30 path)
+        bool no_sidecar = false;              // IBVH_NO_SIDECAR: the build does not keep the traversal's packed records
+        int pyr_grid = 20;                    // IBVH_PYR_GRID: CTAs per SM of the refine / tile kernels
+        int fused_flush = -1;                 // IBVH_FUSED_FLUSH: buffered contacts per output reservation in fused mode
+        void parse() {
+            auto on = [](const char* k) { const char* v = getenv(k); return v != nullptr && v[0] != '\0' && !(v[0] == '0' && v[1] == '\0'); };
+            fused_gather = on("IBVH_FUSED_GATHER");
+            rays_reference_shaped = on("IBVH_RAYS_REFERENCE_SHAPED");
+            rays_static = on("IBVH_RAYS_STATIC");
+            debug = on("IBVH_DEBUG");
+            peer_no_multicast = on("IBVH_PEER_NO_MULTICAST");
+            force_wide_lookback = on("IBVH_SORT_WIDE_LOOKBACK");
+            no_sidecar = on("IBVH_NO_SIDECAR");
+            if (const char* v = getenv("IBVH_PYR_GRID")) { int g = atoi(v); if (g > 0) pyr_grid = g; }
+            if (const char* v = getenv("IBVH_FUSED_FLUSH")) fused_flush = atoi(v);
+        }
+    } cfg;
 
     // grow-only arena
     char* ws = nullptr;

@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(512) peer_allgather_kernel(PeerArgs a, const u
         const int64_t tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x, nth = int64_t(gridDim.x) * blockDim.x;
         if (a.mc) {
             uint64_t* dst = (uint64_t*)(a.mc + a.header_bytes) + dst0;
-            if ((dst0 & 1) == 0) {                   // 16-byte aligned on both sides: 128-bit multicast stores
+            if ((dst0 & 1) == 0 && (reinterpret_cast<uintptr_t>(shard) & 15) == 0) {   // 16-byte aligned on BOTH sides (the shard is a caller pointer: only 8 bytes are promised): 128-bit multicast stores
                 const int64_t n4 = n_words >> 1;
                 const uint4* s4 = (const uint4*)shard;
                 for (int64_t i = tid; i < n4; i += nth) multimem_st_v4((uint4*)dst + i, s4[i]);
@@ -87,8 +87,11 @@ __global__ void __launch_bounds__(512) peer_allgather_kernel(PeerArgs a, const u
     __syncthreads();
     if (!s_last) return;
     __threadfence_system();
+    // The done barrier also runs when the list area is too small (status 2: the same verdict on every rank): a fast
+    // rank's next collective must not overwrite the count slots while a slow rank still spins on this epoch's tag.
+    // Only a timeout (a peer that never arrived) skips it.
     int st = status;
-    if (!status && threadIdx.x < a.world) {
+    if (status != 1 && threadIdx.x < a.world) {
         st_release_sys((uint64_t*)a.buf[threadIdx.x] + kDoneSlot + a.rank, a.epoch);
         const uint64_t t0 = globaltimer_ns();
         while (ld_acquire_sys(sig + kDoneSlot + threadIdx.x) != a.epoch) {
@@ -116,7 +119,7 @@ extern "C" IBVH_API int ibvh_allgather_pairs(ibvh_handle_t* h, const ibvh_peer_t
     ibvh::DeviceGuard guard(h->device);
     cudaStream_t st = (cudaStream_t)stream;
     PeerArgs a = make_peer_args(peer);
-    if (getenv("IBVH_PEER_NO_MULTICAST")) a.mc = 0;   // debug knob: plain peer stores
+    if (h->cfg.peer_no_multicast) a.mc = 0;           // debug knob (IBVH_PEER_NO_MULTICAST, read at ibvh_create): plain peer stores
     int64_t* h_out = (int64_t*)(h->h_pinned + 3072);
     h_out[2] = -1;
     const int grid = h->sm_count * 2;                 // all CTAs co-resident: every block spins on the local header

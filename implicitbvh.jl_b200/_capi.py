@@ -79,6 +79,7 @@ SIGNATURES = {
     "ibvh_profile_reset": (_ci, [_vp]),
     "ibvh_last_traversal_stats": (_ci, [_vp, C.POINTER(_i64)]),
     "ibvh_traverse_finish": (_ci, [_vp, C.POINTER(_i64)]),
+    "ibvh_traverse_cancel": (_ci, [_vp]),
     "ibvh_allgather_pairs": (_ci, [_vp, C.POINTER(Peer), _vp, _i64, C.c_int32, C.POINTER(_i64), C.POINTER(_i64), _vp]),
 }
 

@@ -106,9 +106,9 @@ int sort_pairs(ibvh_handle* h, M* keysA, M* keysB, uint32_t* valsA, uint32_t* va
     auto scope = [&](const char* name) { return ProfScope(h, st, name); };
     cudaError_t e;
     if (sort_wide_lookback(n) || h->cfg.force_wide_lookback)
-        e = sort_pairs_impl<M, unsigned long long, kSortThreads, sort_items<M>(), IBVH_SORT_MINB>(keysA, keysB, valsA, valsB, n, hist, lookback, tickets, st, keys_out, vals_out, scope);
+        e = sort_pairs_impl<M, unsigned long long, kSortThreads, sort_items<M>(), sort_minb<M>()>(keysA, keysB, valsA, valsB, n, hist, lookback, tickets, st, keys_out, vals_out, scope);
     else
-        e = sort_pairs_impl<M, uint32_t, kSortThreads, sort_items<M>(), IBVH_SORT_MINB>(keysA, keysB, valsA, valsB, n, hist, lookback, tickets, st, keys_out, vals_out, scope);
+        e = sort_pairs_impl<M, uint32_t, kSortThreads, sort_items<M>(), sort_minb<M>()>(keysA, keysB, valsA, valsB, n, hist, lookback, tickets, st, keys_out, vals_out, scope);
     if (e != cudaSuccess) { h->set_cuda_error(e, "onesweep_kernel"); return IBVH_ERR_CUDA; }
     return IBVH_OK;
 }
@@ -654,6 +654,15 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
     const bool stash_mode = !unordered && !count_only && capacity > 0 && !((flags & IBVH_TRAVERSE_COUNTS_VALID) && d_counts);
     const int nl = plan.n;
     const int grid = h->sm_count * h->cfg.pyr_grid;
+    // The 16-byte hit stash of the one-pass ordered protocol is sized from what the traversals on this handle actually
+    // produced (last total + 25 %, or 6 hits per query before the first one), never from the caller's `capacity`: a
+    // generously pre-sized cache1 must not pull twice its size of scratch along. A stash that turns out too small costs
+    // a write pass of the tile kernel (the per-query counts are valid either way), not an error.
+    int64_t stash_cap = 0;
+    if (stash_mode) {
+        const int64_t est = h->stash_hint > 0 ? h->stash_hint + h->stash_hint / 4 + 4096 : 6 * ta.q_count + 4096;
+        stash_cap = capacity < est ? capacity : est;
+    }
 
     // ordered protocol scratch: counts (if the caller gave none), cursors, scan sums
     const int64_t qblocks = (ta.q_count + kScanTile - 1) / kScanTile;
@@ -678,7 +687,7 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
         size_t bytes = ibvh_handle::padded((size_t)plan.u_total * sizeof(UBox<T>)) + ibvh_handle::padded((size_t)plan.t_total * sizeof(N)) +
                        ibvh_handle::padded((size_t)(bvh.ti.n + 8) * sizeof(Packed<VT>)) +
                        (same_leaves ? 0 : ibvh_handle::padded((size_t)(n_query_total + 8) * sizeof(Packed<VQ>))) +
-                       (stash_mode ? ibvh_handle::padded((size_t)capacity * sizeof(uint4)) : 0);
+                       (stash_mode ? ibvh_handle::padded((size_t)stash_cap * sizeof(uint4)) : 0);
         for (int l = 0; l < nl; ++l) {
             const PyrLevel& v = plan.lv[l];
             unsigned long long c = (unsigned long long)(factor * (double)(v.nqg > v.ntg && KIND != kSingle ? v.nqg : v.nqg)) + 4096ull;
@@ -696,7 +705,7 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
         Packed<VQ>* PQ = (Packed<VQ>*)PT;
         if (!same_leaves) { PQ = (Packed<VQ>*)ap; ap += ibvh_handle::padded((size_t)(n_query_total + 8) * sizeof(Packed<VQ>)); }
         uint4* stash = nullptr;
-        if (stash_mode) { stash = (uint4*)ap; ap += ibvh_handle::padded((size_t)capacity * sizeof(uint4)); }
+        if (stash_mode) { stash = (uint4*)ap; ap += ibvh_handle::padded((size_t)stash_cap * sizeof(uint4)); }
         PairList lists[kPyrMaxLevels];
         for (int l = 0; l < nl; ++l) { lists[l].data = (uint2*)ap; lists[l].count = d_cnt + l; lists[l].cap = cap[l]; ap += ibvh_handle::padded((size_t)cap[l] * sizeof(uint2)); }
         IBVH_CUDA_TRY(h, cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * kPyrMaxLevels + 128, st));   // list counters + chunk tickets
@@ -811,7 +820,7 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
             IBVH_CUDA_TRY(h, cudaMemsetAsync(counts, 0, (size_t)ta.q_count * sizeof(I), st));
             { ProfScope _ps(h, st, "pyr_leaf_tile_kernel");
             if (stash_mode)
-                pyr_leaf_tile_kernel<KIND, kAtomic, 3, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, capacity, d_total, counts, nullptr, (IndexPair<I>*)stash, 0, d_tick + 16 + (tile_launch++), PQ, PT);
+                pyr_leaf_tile_kernel<KIND, kAtomic, 3, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, stash_cap, d_total, counts, nullptr, (IndexPair<I>*)stash, 0, d_tick + 16 + (tile_launch++), PQ, PT);
             else
                 pyr_leaf_tile_kernel<KIND, kCount, 1, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, 0, d_total, counts, nullptr, (IndexPair<I>*)nullptr, 0, d_tick + 16 + (tile_launch++), PQ, PT);
             }
@@ -869,15 +878,16 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
             h->last_stats[3] = nl;
         }
         *num_contacts = (int64_t)hp[0];
+        if (!unordered) h->stash_hint = *num_contacts;
         if (unordered) return *num_contacts > capacity ? IBVH_ERR_CAPACITY : IBVH_OK;
         if (count_only || *num_contacts == 0) return IBVH_OK;
         if (*num_contacts > capacity) return IBVH_ERR_CAPACITY;
         // ordered write: per-query cursors (from the stash of the single tile pass, or — counts valid from an earlier
         // call — a write pass of the tile kernel), then sort each query's handful of hits by target position
         IBVH_CUDA_TRY(h, cudaMemsetAsync(cursors, 0, (size_t)ta.q_count * 4, st));
-        if (stash_mode && !counts_valid) {
+        if (stash_mode && !counts_valid && *num_contacts <= stash_cap) {
             { ProfScope _ps(h, st, "pyr_scatter_kernel");
-            pyr_scatter_kernel<I><<<h->sm_count * 16, 256, 0, st>>>(stash, d_total, capacity, counts, cursors, (IndexPair<I>*)d_contacts);
+            pyr_scatter_kernel<I><<<h->sm_count * 16, 256, 0, st>>>(stash, d_total, stash_cap, counts, cursors, (IndexPair<I>*)d_contacts);
             }
             IBVH_LAUNCH_CHECK(h, "pyr_scatter_kernel");
         } else {
@@ -1141,6 +1151,18 @@ int ibvh_traverse_finish(ibvh_handle_t* h, int64_t* num_contacts) {
     return *num_contacts > df.capacity ? IBVH_ERR_CAPACITY : IBVH_OK;
 }
 
+int ibvh_traverse_cancel(ibvh_handle_t* h) {
+    if (!h) return IBVH_ERR_ARGUMENT;
+    ibvh_handle::Deferred& df = h->deferred;
+    if (!df.active) return IBVH_OK;
+    DeviceGuard g(h->device);
+    df.active = false;
+    // the enqueued work still writes the handle's read-back slots: wait for it so that the next call owns them
+    cudaError_t e = cudaEventSynchronize(h->ev_defer);
+    if (e != cudaSuccess) { h->set_cuda_error(e, "cudaEventSynchronize(cancelled deferred traversal)"); return IBVH_ERR_CUDA; }
+    return IBVH_OK;
+}
+
 int ibvh_last_traversal_stats(ibvh_handle_t* h, int64_t out[4]) {
     if (!h || !out) return IBVH_ERR_ARGUMENT;
     for (int k = 0; k < 4; ++k) out[k] = h->last_stats[k];
@@ -1295,7 +1317,7 @@ int ibvh_build(ibvh_handle_t* h, const void* d_volumes, void* d_leaves, int64_t 
 int ibvh_traverse_single(ibvh_handle_t* h, const ibvh_bvh_t* bvh, const ibvh_traverse_params_t* p, void* d_counts, void* d_contacts,
                          int64_t capacity, int64_t* num_contacts, void* stream) {
     if (!h || !p || !num_contacts) return IBVH_ERR_ARGUMENT;
-    if (h->deferred.active) { h->set_error("a deferred traversal is outstanding on this handle: call ibvh_traverse_finish first"); return IBVH_ERR_ARGUMENT; }
+    if (h->deferred.active) { h->set_error("a deferred traversal is outstanding on this handle: call ibvh_traverse_finish (or ibvh_traverse_cancel) first"); return IBVH_ERR_ARGUMENT; }
     ibvh_tree_t tree;
     int rc = check_bvh(bvh, &tree);
     if (rc != IBVH_OK) return rc;
@@ -1362,6 +1384,8 @@ int ibvh_traverse_pair(ibvh_handle_t* h, const ibvh_bvh_t* queries, const ibvh_b
 int ibvh_traverse_rays(ibvh_handle_t* h, const ibvh_bvh_t* bvh, const void* d_points, const void* d_directions, int64_t nrays,
                        const ibvh_traverse_params_t* p, void* d_counts, void* d_contacts, int64_t capacity, int64_t* num_contacts, void* stream) {
     if (!h || !p || !num_contacts || nrays < 0) return IBVH_ERR_ARGUMENT;
+    // (the ray traversal's read-back uses the same pinned / counter slots as an outstanding deferred traversal)
+    if (h->deferred.active) { h->set_error("a deferred traversal is outstanding on this handle: call ibvh_traverse_finish (or ibvh_traverse_cancel) first"); return IBVH_ERR_ARGUMENT; }
     ibvh_tree_t tree;
     int rc = check_bvh(bvh, &tree);
     if (rc != IBVH_OK) return rc;

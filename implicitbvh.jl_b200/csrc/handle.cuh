@@ -58,6 +58,7 @@ struct ibvh_handle {
 
     // pyramid schedule: learned list-capacity factor (pairs per query group), see traverse_pyramid
     double pyr_factor = 0.0;
+    long long stash_hint = 0;     // contact total of the last ordered pyramid traversal (sizes the hit stash of the next one)
 
     // persistent small device block: [0..47] scene bounds (6 x u64 ordered keys),
     // [64..) counters: total contacts (u64), tile tickets, stats.

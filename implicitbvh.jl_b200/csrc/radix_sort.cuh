@@ -31,18 +31,40 @@
 namespace ibvh {
 
 // ---- tile shape ----------------------------------------------------------------------------------------
+// Swept on a B200 with tools/sort_bench.cu (10 M pairs, 30-bit keys; gpurun_out/r2a..r2e, summary in profiles/):
+//   threads x keys/thread (CTAs/SM)   256x16 (4)  512x8 (3)  384x12 (3)  512x12 (2)  512x16 (2)  1024x8 (1)
+//   ms for the 4 passes                  0.263      0.263      0.259       0.256      0.236       0.315
+// look-back words in flight per round (512x16): 1 -> 0.267, 2 -> 0.240, 3 -> 0.238, 4 -> 0.236, 8 -> 0.249, 16 -> 0.294 ms
+// (the nearest published inclusive prefix is usually 1-3 tiles back: wider batches only add instructions);
+// requesting them BEFORE the reorder: slower (0.277: the predecessors have not published yet, the words are re-read).
+// 8-byte keys: 512x12 is best (0.623 ms for 8 passes at 10 M, 5.7 ms at 100 M).
 #ifndef IBVH_SORT_THREADS
 #define IBVH_SORT_THREADS 512
 #endif
-#ifndef IBVH_SORT_ITEMS
-#define IBVH_SORT_ITEMS 8
-#endif
 #ifndef IBVH_SORT_MINB
-#define IBVH_SORT_MINB 3
+#define IBVH_SORT_MINB 2
+#endif
+#ifndef IBVH_SORT_PREFETCH
+#define IBVH_SORT_PREFETCH 0      // request the nearest predecessors' look-back words before the reorder (measured: slower)
+#endif
+#ifndef IBVH_SORT_BATCH
+#define IBVH_SORT_BATCH 4         // look-back words in flight per round
+#endif
+#ifndef IBVH_SORT_PAIRSTAGE
+#define IBVH_SORT_PAIRSTAGE 1     // 4-byte keys: (key, value) staged in shared memory as one 8-byte record
+#endif
+#ifndef IBVH_SORT_PACKRANK
+#define IBVH_SORT_PACKRANK 1      // two 16-bit ranks per register, pinned when computed
 #endif
 constexpr int kSortThreads = IBVH_SORT_THREADS;
+#ifdef IBVH_SORT_ITEMS
 template <class K> constexpr int sort_items() { return IBVH_SORT_ITEMS; }
+#else
+template <class K> constexpr int sort_items() { return sizeof(K) == 8 ? 12 : 16; }
+#endif
 template <class K> constexpr int sort_tile() { return kSortThreads * sort_items<K>(); }
+// resident tiles per SM the register budget is set for
+template <class K> constexpr int sort_minb() { return IBVH_SORT_MINB; }
 
 // look-back words: 2 flag bits on top of a count / prefix
 template <class LB> struct LookbackWord;
@@ -115,6 +137,7 @@ __global__ void __launch_bounds__(THREADS, MINB) onesweep_kernel(const K* __rest
     static_assert(32 * ITEMS <= 65535 && THREADS * ITEMS <= 65535, "16-bit per-warp counters / offsets");
     constexpr int WARPS = THREADS / 32;
     constexpr int TILE = THREADS * ITEMS;
+    constexpr bool kPairStage = IBVH_SORT_PAIRSTAGE && sizeof(K) == 4;      // stage (key, value) as one 8-byte record
     constexpr LB kAgg = LookbackWord<LB>::kAgg, kIncl = LookbackWord<LB>::kIncl, kFlags = LookbackWord<LB>::kFlags;
     extern __shared__ __align__(16) unsigned char onesweep_smem[];
     K* skeys = reinterpret_cast<K*>(onesweep_smem);                                   // TILE keys, tile-sorted
@@ -127,7 +150,7 @@ __global__ void __launch_bounds__(THREADS, MINB) onesweep_kernel(const K* __rest
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     if (tid == 0) s_tile = atomicAdd(ticket, 1u);
-    for (int i = tid; i < WARPS * kRadixBins / 2; i += THREADS) reinterpret_cast<uint32_t*>(whist)[i] = 0u;
+    for (int i = tid; i < WARPS * kRadixBins / 8; i += THREADS) reinterpret_cast<uint4*>(whist)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
     const uint32_t tile = s_tile;
     const int64_t tile_base = (int64_t)tile * TILE;
@@ -147,7 +170,13 @@ __global__ void __launch_bounds__(THREADS, MINB) onesweep_kernel(const K* __rest
     }
 
     // ---- rank within the warp: peers = lanes holding the same digit (BITS full-mask ballots) -----------
-    uint32_t rank[ITEMS];
+    // Two 16-bit ranks per register, each pinned down as soon as it is known (the empty asm): nvcc otherwise keeps the
+    // peer masks and counters of all ITEMS keys alive and finishes the ranks during the reorder, spilling to local memory.
+#if IBVH_SORT_PACKRANK
+    uint32_t rank2[(ITEMS + 1) / 2];
+#else
+    uint32_t rank1[ITEMS];
+#endif
     {
         uint16_t* wh = whist + w * kRadixBins;
         const uint32_t lt = (1u << lane) - 1u;
@@ -156,8 +185,14 @@ __global__ void __launch_bounds__(THREADS, MINB) onesweep_kernel(const K* __rest
             const uint32_t d = digit_of(key[r], shift);
             const uint32_t peers = match_digit<BITS>(d);
             const uint32_t old = wh[d];                                   // every peer reads the same counter (broadcast)
-            rank[r] = old + __popc(peers & lt);
+            const uint32_t rk = old + __popc(peers & lt);
             if ((peers >> lane) == 1u) wh[d] = (uint16_t)(old + __popc(peers));   // the highest peer lane writes it back
+#if IBVH_SORT_PACKRANK
+            if (r & 1) rank2[r / 2] |= rk << 16; else rank2[r / 2] = rk;
+            asm volatile("" : "+r"(rank2[r / 2]));
+#else
+            rank1[r] = rk;
+#endif
             __syncwarp();
         }
     }
@@ -180,7 +215,14 @@ __global__ void __launch_bounds__(THREADS, MINB) onesweep_kernel(const K* __rest
     __syncthreads();
 
     // ---- per digit (thread d): exclusive offsets over warps, tile count, publish, tile-level scan ---------
+    // Look-back, part 1: the words of the kBatch nearest predecessors are requested HERE, right after this tile's own
+    // count is published — they travel while the scans, two barriers and the reorder run (ncu, round 2: with the
+    // loads issued only after the reorder the walk was 16 % of the stall samples and the barrier behind it 15 %).
+    constexpr int kBatch = IBVH_SORT_BATCH;
     uint32_t tcount = 0, incl = 0;
+#if IBVH_SORT_PREFETCH
+    LB pre[kBatch];
+#endif
     if (tid < kRadixBins) {
         const int d = tid;
 #pragma unroll
@@ -188,6 +230,10 @@ __global__ void __launch_bounds__(THREADS, MINB) onesweep_kernel(const K* __rest
         // sentinels of a partial tile were ranked like keys: they hold the largest digit and the last tile positions
         if (tile_n < TILE && d == (int)digit_of(sentinel, shift)) tcount -= (uint32_t)(TILE - tile_n);
         lookback[(size_t)tile * kRadixBins + d] = (tile == 0 ? kIncl : kAgg) | (LB)tcount;
+#if IBVH_SORT_PREFETCH
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k) pre[k] = ((int64_t)tile - 1 - k >= 0) ? lookback[((size_t)tile - 1 - k) * kRadixBins + d] : kIncl;
+#endif
         incl = tcount;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += o; }
@@ -207,40 +253,51 @@ __global__ void __launch_bounds__(THREADS, MINB) onesweep_kernel(const K* __rest
 #pragma unroll
         for (int r = 0; r < ITEMS; ++r) {
             const uint32_t d = digit_of(key[r], shift);
-            const uint32_t pos = tile_start[d] + wh[d] + rank[r];
-            skeys[pos] = key[r];
-            svals[pos] = val[r];
+#if IBVH_SORT_PACKRANK
+            const uint32_t pos = tile_start[d] + wh[d] + ((r & 1) ? (rank2[r / 2] >> 16) : (rank2[r / 2] & 0xffffu));
+#else
+            const uint32_t pos = tile_start[d] + wh[d] + rank1[r];
+#endif
+            if constexpr (kPairStage) {
+                reinterpret_cast<uint2*>(onesweep_smem)[pos] = make_uint2((uint32_t)key[r], val[r]);      // one 8-byte store per pair
+            } else {
+                skeys[pos] = key[r];
+                svals[pos] = val[r];
+            }
         }
     }
 
-    // ---- decoupled look-back (thread d resolves digit d) -----------------------------------------------
+    // ---- decoupled look-back, part 2 (thread d resolves digit d) ---------------------------------------
     if (tid < kRadixBins) {
         const int d = tid;
         LB excl = 0;
         if (tile > 0) {
-            // Walk back over the predecessors' (flag | count) words, kBatch independent loads in flight per round:
-            // the chain to the nearest published inclusive prefix is as long as the number of tiles in flight, and
-            // one dependent L2 round trip per tile was what bounded the whole pass.
-            constexpr int kBatch = 8;
+            // Walk back over the predecessors' (flag | count) words, kBatch independent loads in flight per round: the
+            // chain to the nearest published inclusive prefix is as long as the number of tiles in flight. An entry is
+            // consumed while every nearer one was published; the walk ends at the first inclusive prefix.
             int64_t t = (int64_t)tile - 1;
             bool done = false;
+            auto consume = [&](const LB (&v)[kBatch]) {
+                bool alive = true;
+                int used = 0;
+#pragma unroll
+                for (int k = 0; k < kBatch; ++k) {
+                    const LB f = v[k] & kFlags;
+                    const bool take = alive && f != 0;
+                    if (take) { excl += v[k] & ~kFlags; ++used; }
+                    if (take && f == kIncl) done = true;
+                    alive = take && f != kIncl;
+                }
+                t -= used;                                  // an unpublished predecessor is simply re-read
+            };
+#if IBVH_SORT_PREFETCH
+            consume(pre);
+#endif
             while (!done) {
                 LB v[kBatch];
 #pragma unroll
                 for (int k = 0; k < kBatch; ++k) v[k] = (t - k >= 0) ? lookback[(size_t)(t - k) * kRadixBins + d] : kIncl;
-                int used = 0;
-#pragma unroll
-                for (int k = 0; k < kBatch; ++k) {
-                    if (!done && used == k) {
-                        const LB f = v[k] & kFlags;
-                        if (f != 0) {                       // published: consume it
-                            excl += v[k] & ~kFlags;
-                            used = k + 1;
-                            if (f == kIncl) done = true;
-                        }
-                    }
-                }
-                t -= used;                                  // an unpublished predecessor is simply re-read
+                consume(v);
             }
             lookback[(size_t)tile * kRadixBins + d] = kIncl | (excl + (LB)tcount);
         }
@@ -249,15 +306,19 @@ __global__ void __launch_bounds__(THREADS, MINB) onesweep_kernel(const K* __rest
     __syncthreads();
 
     // ---- coalesced write-out: consecutive positions with one digit go to consecutive addresses ----------
+    auto emit = [&](int i) {
+        K kk; uint32_t vv;
+        if constexpr (kPairStage) { const uint2 kv = reinterpret_cast<const uint2*>(onesweep_smem)[i]; kk = (K)kv.x; vv = kv.y; }
+        else { kk = skeys[i]; vv = svals[i]; }
+        const uint32_t dst = gofs[digit_of(kk, shift)] + (uint32_t)i;
+        keys_out[dst] = kk;
+        vals_out[dst] = vv;
+    };
+    if (full) {
 #pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-        const int i = k * THREADS + tid;
-        if (i < tile_n) {
-            const K kk = skeys[i];
-            const uint32_t dst = gofs[digit_of(kk, shift)] + (uint32_t)i;
-            keys_out[dst] = kk;
-            vals_out[dst] = svals[i];
-        }
+        for (int k = 0; k < ITEMS; ++k) emit(k * THREADS + tid);
+    } else {
+        for (int i = tid; i < tile_n; i += THREADS) emit(i);
     }
 }
 

@@ -250,6 +250,11 @@ IBVH_API int ibvh_last_traversal_stats(ibvh_handle_t* h, int64_t out[4]);
  * IBVH_ERR_CAPACITY as for the synchronous call; IBVH_ERR_AGAIN: the scratch pair lists overflowed (their size is
  * learned from the previous call) — nothing valid was written, repeat the traversal (it will size them right). */
 IBVH_API int ibvh_traverse_finish(ibvh_handle_t* h, int64_t* num_contacts);
+/* Drops the outstanding deferred traversal of this handle without judging its result (waits for the enqueued work,
+ * since it still writes the handle's read-back slots). No-op when nothing is outstanding. A caller that loses
+ * interest in a deferred result (the Julia finalizer of a BVHTraversal never read) calls this, so that later
+ * traversals on the handle are not refused. */
+IBVH_API int ibvh_traverse_cancel(ibvh_handle_t* h);
 
 /* ---- multi-GPU: all-gather of the contact / hit shards over NVLink peer memory ------
  * The reference has no multi-GPU path; this is the exchange step that follows a query-range sharded

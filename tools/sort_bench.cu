@@ -4,6 +4,7 @@
 //   ./sort_bench [n] [dist]     dist: 0 uniform 30-bit, 1 clustered (few distinct top digits), 2 many ties (15 distinct bits)
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 #include <cub/device/device_radix_sort.cuh>
 
@@ -41,9 +42,12 @@ template <class K> __global__ void hist_kernel(const K* keys, int64_t n, uint32_
 }
 
 struct NoScope { int operator()(const char*) const { return 0; } };
+static const char* g_filter = nullptr;     // run only the variants whose name contains this
+static int g_reps = 10;
 
 template <class K, class LB, int THREADS, int ITEMS, int MINB>
 void run_variant(const char* name, const K* d_keys, int64_t n, const K* ref_keys, const uint32_t* ref_vals, int reps) {
+    if (g_filter && !strstr(name, g_filter)) return;
     constexpr int P = radix_passes<K>();
     const int64_t tiles = (n + THREADS * ITEMS - 1) / (THREADS * ITEMS);
     K *kA, *kB; uint32_t *vA, *vB, *hist, *tickets; LB* lb;
@@ -119,7 +123,9 @@ int main(int argc, char** argv) {
     int64_t n = argc > 1 ? atoll(argv[1]) : 10000000;
     int dist = argc > 2 ? atoi(argv[2]) : 0;
     int kb = argc > 3 ? atoi(argv[3]) : 4;
-    int reps = 10;
+    if (argc > 4) g_filter = argv[4];
+    if (argc > 5) g_reps = atoi(argv[5]);
+    int reps = g_reps;
     if (kb == 4) run_all<uint32_t>(n, dist, reps);
     else if (kb == 8) run_all<uint64_t>(n, dist, reps);
     else run_all<uint16_t>(n, dist, reps);

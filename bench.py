@@ -41,6 +41,11 @@ WORKLOAD = ("configs[1]: %d BSphere{Float32} leaves (centres U[0,1)^3, r = s(0.5
             "BBox{Float32} nodes, UInt32 Morton, Int32 index: BVH build (built_level=1) + LVT contact traversal (start_level=1)")
 
 
+def bench_config():
+    """The `config` object: identical in the GPU arm and in the reference arm (the driver compares them)."""
+    return {"workload": WORKLOAD % N_LEAVES, "leaves": N_LEAVES}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -163,7 +168,8 @@ def run_reference(args):
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD % N_LEAVES, "sample_leaves": n, "contacts_per_step": total},
+        "config": bench_config(),
+        "details": {"sample_leaves": n, "contacts_per_step": total},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -185,6 +191,34 @@ def profile_rows(ib, handle):
     return rows
 
 
+def pair_checksum(torch, tensor_u8, count, itemsize=8):
+    """Order-independent checksum of an IndexPair list on the device: (count, sum of keys, sum of squared keys), both
+    sums wrapping mod 2^64. key = the pair's 8 bytes read as one int64 (Int32 pairs) or a * 2^32 + b (Int64 pairs)."""
+    if count == 0:
+        return (0, 0, 0)
+    if itemsize == 8:
+        k = tensor_u8[: count * 8].view(torch.int64)
+    else:
+        ab = tensor_u8[: count * 16].view(torch.int64).reshape(-1, 2)
+        k = ab[:, 0] * (1 << 32) + ab[:, 1]
+    return (int(count), int(k.sum().item()), int((k * k).sum().item()))
+
+
+def timed_steps(torch, fn, steps, warm):
+    """`warm` untimed + `steps` timed calls of fn(); CUDA events on the current stream. Returns (ms per step, last result)."""
+    out = None
+    for _ in range(warm):
+        out = fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps, out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -196,6 +230,11 @@ def main():
                          "(same set; the parity bar is the SORTED contact list)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-rays", action="store_true", help="skip the secondary rays/s measurement")
+    ap.add_argument("--workloads", default="ordered,pair,rebuild64,reference_shaped",
+                    help="comma list of the extra BASELINE.json workloads to time after the headline (reported under `workloads`): "
+                         "ordered (the headline step in the reference's contact order), pair (configs[2]: 5 M + 5 M BVH-vs-BVH, "
+                         "partial and full build), rebuild64 (configs[4]: 100 M leaves, UInt64 / Int64, cached rebuild + contacts), "
+                         "reference_shaped (the naive GPU proxy of the reference's CUDA.jl backend on the headline step). 'none' skips them")
     ap.add_argument("--no-defer", action="store_true", help="single GPU: synchronous traversal calls (the host reads each step's contact count before it enqueues the next build)")
     ap.add_argument("--gather", default="fused", choices=["fused", "peer", "nccl"],
                     help="N > 1: how the contact shards reach every rank. fused: the traversal kernel itself writes each contact "
@@ -230,6 +269,7 @@ def main():
     warm = max(3, args.warmup)
     n = N_LEAVES
     ordered = args.ordered
+    extra = [] if args.workloads in ("", "none") else [w.strip() for w in args.workloads.split(",") if w.strip()]
 
     # ---- inputs resident in HBM (generated on device, identical on every rank) -----------------
     vols = synth.random_spheres_torch(n, dev, seed=SEED)
@@ -288,7 +328,7 @@ def main():
     ncontacts = step_device()
     if world > 1 and args.gather in ("peer", "fused"):
         try:
-            state["peer"] = ibdist.PeerGather(int(ncontacts * 1.05) + 1024, 8, dev)
+            state["peer"] = ibdist.PeerGather(int(ncontacts * 1.10) + 8192 * world, 8, dev)
         except Exception as ex:                          # no symmetric memory on this box: NCCL collectives instead
             if rank == 0:
                 print(f"[bench] peer memory unavailable ({ex!r}); gathering with NCCL", file=sys.stderr, flush=True)
@@ -300,6 +340,24 @@ def main():
         state["tr"] = ib.BVHTraversal(1, 0, 0, 0, ib.DeviceArray.empty(int(tr.num_contacts * 1.05) + 1024, ib.pair_dtype(), dev), tr.cache2)
     for _ in range(warm):
         ncontacts = step_device()
+
+    # ---- N > 1: the gathered contact list of the timed configuration against the single-GPU list, on every rank ----
+    verify = None
+    if world > 1:
+        mc = bool(state["peer"] is not None and state["peer"].peer.multicast)
+        print(f"[bench] rank {rank}/{world} device cuda:{local} ({torch.cuda.get_device_name(local)}) gather={args.gather} "
+              f"fused={fused} multicast={'yes' if mc else 'no'} build={args.build_mode} shard=[{qb},{qe})", file=sys.stderr, flush=True)
+        got = pair_checksum(torch, state["full"], int(ncontacts))
+        single = ib.traverse(state["bvh"], ordered=False)                 # the whole problem on this rank alone
+        want = pair_checksum(torch, single.cache1.tensor, single.num_contacts)
+        ok = torch.tensor([1 if got == want else 0], dtype=torch.int64, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        verify = {"gathered_equals_single_gpu_list": bool(ok.item()), "contacts": want[0], "checksum": [want[1], want[2]],
+                  "what": "count + order-independent checksum (sum and sum of squares of the 64-bit pair keys, mod 2^64) of the gathered "
+                          "list on EVERY rank against the same rank's own unsharded traversal, before the timed region"}
+        if not ok.item():
+            raise SystemExit(f"[bench] rank {rank}: gathered contact list {got} != single-GPU list {want}")
+        del single
 
     def finish_pending():
         """Single GPU: the count of the last (deferred) traversal — read before the closing event is recorded."""
@@ -375,6 +433,18 @@ def main():
                 "per_kernel_ms": {k: round(v, 4) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1])},
                 "traversal_ms_per_step": round(sum(v for k, v in per_kernel.items() if k.startswith(("pyr_", "tile_", "group_walk", "lvt_", "scan_r", "scan_b", "scan_a"))), 4),
                 "build_ms_per_step": round(sum(v for k, v in per_kernel.items() if k in ("init_build_kernel", "bounds_kernel", "encode_kernel", "scan_hist_kernel", "onesweep_kernel", "gather_kernel", "gather_merge_kernel", "merge_levels_kernel")), 4)}
+    # the same arithmetic for the build and for the traversal as a whole (SURVEY.md §8d byte formulas; 32-bit type set)
+    def group(ms, nbytes):
+        gbs = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        return {"ms_per_step": ms, "algorithmic_bytes_per_step": nbytes, "achieved": gbs, "frac": gbs / peak, "unit": "GB/s"}
+    stage_bytes = {"bounds_kernel": 16 * n, "encode_kernel": 20 * n, "onesweep_kernel": 68 * n, "scan_hist_kernel": 0,
+                   "gather_kernel": 48 * n, "gather_merge_kernel": 48 * n}
+    shard_frac = (nq / n) if world > 1 else 1.0
+    roofline["groups"] = {
+        "build (S1+S2+S3+S4 = 196 N)": group(roofline["build_ms_per_step"], 196 * n),
+        "traversal (T1 = 48 N + 8 C, this rank's shard)": group(roofline["traversal_ms_per_step"], (Lb + Nb) * n * shard_frac + 2 * Ib * my_contacts),
+        "per_build_kernel": {k: group(per_kernel[k], b) for k, b in stage_bytes.items() if k in per_kernel and b > 0},
+    }
     # intersection tests of one traversal (this rank's shard), derived by the library from its pair-list sizes
     import ctypes as C
     st4 = (C.c_int64 * 4)()
@@ -533,7 +603,7 @@ def main():
             tot = torch.tensor([rt.num_contacts], dtype=torch.int64, device=dev)
             dist.all_reduce(tot)
             try:
-                ray_peer = ibdist.PeerGather(int(int(tot.item()) * 1.02) + 1024, 8, dev)   # hit list of ALL rays on every rank
+                ray_peer = ibdist.PeerGather(int(int(tot.item()) * 1.10) + 8192 * world, 8, dev)   # hit list of ALL rays on every rank
             except Exception:
                 ray_peer = None
 
@@ -571,7 +641,172 @@ def main():
                 "scaling": "strong"}
         del rp, rd, rcache, rt
 
-    clocks = sampler.stop() if rank == 0 else None      # sampled over the timed, e2e and ray regions
+
+    # ---- the other BASELINE.json workloads (short timed runs, reported under `workloads`) ------------------------
+    workloads = {}
+
+    def rank_max(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def shard_gather(tr, peer_obj):
+        """N > 1: all-gather this rank's shard (library kernel over NVLink peer memory, else NCCL). Returns the gathered total."""
+        if world == 1:
+            return tr.num_contacts
+        if peer_obj is not None:
+            return peer_obj.gather(tr.cache1.tensor, tr.num_contacts)[1]
+        return int(sum(ibdist.gather_shards(tr.cache1.tensor, tr.num_contacts, tr.cache1.dtype.itemsize)[1]))
+
+    if "ordered" in extra and not ordered:
+        # the headline step in the reference's own contact order (ascending query leaf, DFS order): the drop-in default
+        st_o = {"bvh": state["bvh"], "tr": None}
+
+        def step_ordered():
+            bvh = ib.BVH(src, ib.BBox(), cache=st_o["bvh"])
+            tr = ib.traverse(bvh, cache=st_o["tr"], ordered=True, query_range=(qb, qe - qb) if world > 1 else None)
+            st_o["bvh"], st_o["tr"] = bvh, tr
+            return shard_gather(tr, state["peer"])
+
+        ms_o, c_o = timed_steps(torch, step_ordered, 5, 3)
+        ms_o = rank_max(ms_o)
+        workloads["ordered"] = {"metric": METRIC, "value": n / (ms_o * 1e-3), "unit": UNIT, "ms_per_step": ms_o, "contacts_per_step": int(c_o),
+                                "workload": "the headline step with contacts in the reference's order (count -> scan -> write protocol; "
+                                            "byte-identical to the oracle's list); N > 1: ordered shards all-gathered in rank order"}
+        st_o.clear()
+
+    if "reference_shaped" in extra and world == 1:
+        # proxy of the reference's CUDA.jl backend (cannot run here: no Julia): the launches BVH(...) + traverse(...) make through
+        # AcceleratedKernels, written naively in CUDA — struct-moving merge sort, two mapreduce passes with host read-backs, one
+        # merge launch per level, one thread per leaf with a private stack, count -> scan -> write
+        st_r = {"tr": None}
+
+        def step_proxy():
+            bvh = ib.BVH(src, ib.BBox(), reference_shaped=True)
+            tr = ib.traverse(bvh, cache=st_r["tr"], ordered=True, reference_shaped=True)
+            st_r["tr"] = tr
+            return tr.num_contacts
+
+        ms_r, c_r = timed_steps(torch, step_proxy, 3, 2)
+        lib.ibvh_profile_enable(handle, 1)
+        step_proxy()
+        torch.cuda.synchronize()
+        prow = profile_rows(ib, handle)
+        lib.ibvh_profile_enable(handle, 0)
+        pk = {}
+        for k, v in prow:
+            pk[k] = pk.get(k, 0.0) + v
+        workloads["reference_shaped"] = {
+            "metric": METRIC, "value": n / (ms_r * 1e-3), "unit": UNIT, "ms_per_step": ms_r, "contacts_per_step": int(c_r),
+            "speedup_of_product_path": ms_r / ms_step,
+            "per_kernel_ms": {k: round(v, 4) for k, v in sorted(pk.items(), key=lambda kv: -kv[1])},
+            "label": "PROXY, not ImplicitBVH.jl: a naive reference-shaped CUDA build + LVT (ibvh_build_reference_shaped + "
+                     "IBVH_TRAVERSE_REFERENCE_SHAPED) standing in for the reference's CUDA.jl backend, which cannot run in this image"}
+        st_r.clear()
+
+    if "pair" in extra:
+        # configs[2]: BVH-vs-BVH, 5 M + 5 M leaves, the target tree built to levels-13 (about 2^10 roots) and fully;
+        # the query leaves (bvh1) are sharded over the ranks, both builds replicated
+        np_ = 5_000_000 if n >= 10_000_000 else max(1000, n // 2)
+        sc = synth.sphere_radius_scale(np_)
+        v1 = synth.random_spheres_torch(np_, dev, seed=42, scale=sc)
+        v2 = synth.random_spheres_torch(np_, dev, seed=43, scale=sc)
+        d1 = ib.DeviceArray(v1.view(torch.uint8).reshape(-1), ib.BSphere().dtype)
+        d2 = ib.DeviceArray(v2.view(torch.uint8).reshape(-1), ib.BSphere().dtype)
+        pqb, pqe = ibdist.shard_bounds(np_, world)[rank]
+        levels = ib.ImplicitTree(np_).levels
+        res = {}
+        for name, bl in (("partial_build", max(1, levels - 13)), ("full_build", 1)):
+            st_p = {"b1": None, "b2": None, "tr": None}
+
+            def step_pair():
+                b1 = ib.BVH(d1, ib.BBox(), cache=st_p["b1"])
+                b2 = ib.BVH(d2, ib.BBox(), built_level=bl, cache=st_p["b2"])
+                tr = ib.traverse(b1, b2, cache=st_p["tr"], ordered=False, query_range=(pqb, pqe - pqb) if world > 1 else None)
+                st_p["b1"], st_p["b2"], st_p["tr"] = b1, b2, tr
+                return shard_gather(tr, state["peer"] if world > 1 else None)
+
+            def trav_only():
+                tr = ib.traverse(st_p["b1"], st_p["b2"], cache=st_p["tr"], ordered=False, query_range=(pqb, pqe - pqb) if world > 1 else None)
+                st_p["tr"] = tr
+                return tr.num_contacts
+
+            try:
+                ms_p, c_p = timed_steps(torch, step_pair, 5, 3)
+                ms_t, _ = timed_steps(torch, trav_only, 5, 1)
+            except Exception as ex:                                  # e.g. the peer list area sized for the headline is too small
+                res[name] = {"error": repr(ex)[:300]}
+                continue
+            ms_p, ms_t = rank_max(ms_p), rank_max(ms_t)
+            res[name] = {"built_level2": bl, "start_level2": bl, "ms_per_step": ms_p, "traverse_ms": ms_t, "contacts_per_step": int(c_p),
+                         "query_leaves_per_s": np_ / (ms_p * 1e-3), "leaves_per_s": 2 * np_ / (ms_p * 1e-3)}
+            st_p.clear()
+        workloads["pair"] = {"metric": "pair traversal: (5 M + 5 M) leaves/s, two builds + traverse(bvh1, bvh2)", "unit": "leaves/s",
+                             "value": res.get("partial_build", {}).get("leaves_per_s"), "leaves": [np_, np_], **res,
+                             "workload": "configs[2]: two independent draws (seeds 42, 43) of the config-2 law in one unit cube; step = BVH(bvh1) + "
+                                         "BVH(bvh2; built_level) + traverse(bvh1, bvh2) unordered; bvh1's leaves are the queries, sharded by contiguous "
+                                         "ranges over %d GPU(s)%s" % (world, "" if world == 1 else ", shards all-gathered to every rank")}
+        del v1, v2, d1, d2
+
+    if "rebuild64" in extra:
+        # configs[4]: 100 M leaves, UInt64 Morton, Int64 index; each step perturbs the centres in place, rebuilds in place with
+        # cache=bvh (BVH(bvh.leaves, cache=bvh)) and finds the contacts with cache=previous traversal
+        n64 = int(os.environ.get("IBVH_BENCH_N64", 100_000_000 if n >= 10_000_000 else 10 * n))
+        o64 = ib.BVHOptions(index=np.int64, morton=ib.DefaultMortonAlgorithm(np.uint64))
+        try:
+            v64 = synth.random_spheres_torch(n64, dev, seed=42)
+            bvh64 = ib.BVH(ib.DeviceArray(v64.view(torch.uint8).reshape(-1), ib.BSphere().dtype), ib.BBox(), options=o64)
+            del v64
+            qb64, qe64 = ibdist.shard_bounds(n64, world)[rank]
+            F = bvh64.leaves.tensor.view(torch.float32).reshape(n64, 8)
+            s64 = synth.sphere_radius_scale(n64)
+            st64 = {"bvh": bvh64, "tr": None, "k": 0}
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            acc = {"build": 0.0, "trav": 0.0, "steps": 0}
+
+            def step64(timed):
+                st64["k"] += 1
+                for c in range(3):                                   # the simulation's move (not part of the measured path)
+                    F[:, c] += (synth.uniform_torch(1000 + st64["k"], n64, c, dev) - 0.5) * (s64 / 2)
+                ev[0].record()
+                b = ib.BVH(st64["bvh"].leaves, ib.BBox(), cache=st64["bvh"], options=o64)
+                ev[1].record()
+                tr = ib.traverse(b, cache=st64["tr"], ordered=False, query_range=(qb64, qe64 - qb64) if world > 1 else None)
+                ev[2].record()
+                st64["bvh"], st64["tr"] = b, tr
+                torch.cuda.synchronize()
+                if timed:
+                    acc["build"] += ev[0].elapsed_time(ev[1]); acc["trav"] += ev[1].elapsed_time(ev[2]); acc["steps"] += 1
+                return tr.num_contacts
+
+            for _ in range(3):
+                step64(False)
+            c64 = 0
+            for _ in range(4):
+                c64 = step64(True)
+            bms, tms = rank_max(acc["build"] / acc["steps"]), rank_max(acc["trav"] / acc["steps"])
+            ctot = c64
+            if world > 1:
+                t = torch.tensor([c64], dtype=torch.int64, device=dev)
+                dist.all_reduce(t)
+                ctot = int(t.item())
+            workloads["rebuild64"] = {"metric": "cached rebuild + contact leaves/s @100M, UInt64 / Int64", "unit": UNIT, "leaves": n64,
+                                      "value": n64 / ((bms + tms) * 1e-3), "ms_per_step": bms + tms, "build_ms": bms, "traverse_ms": tms,
+                                      "contacts_per_step": int(ctot),
+                                      "workload": "configs[4]: config-2 law at %d leaves, 32-byte leaves (UInt64 Morton, Int64 index), 16-byte pairs; per step the "
+                                                  "centres move by U[-s/4, s/4), then BVH(bvh.leaves, BBox; cache=bvh) in place + traverse(cache=prev) unordered; "
+                                                  "the (replicated) rebuild and the query-range sharded traversal over %d GPU(s) are timed with CUDA events, the "
+                                                  "move is not; N > 1: every rank keeps its own shard (no gather)" % (n64, world)}
+            del F, bvh64
+            st64.clear()
+        except Exception as ex:
+            workloads["rebuild64"] = {"error": repr(ex)[:300]}
+        torch.cuda.empty_cache()
+        lib.ibvh_release_workspace(handle)
+
+    clocks = sampler.stop() if rank == 0 else None      # sampled over the timed, e2e, ray and extra-workload regions
 
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload ----------------------
     cpu_baseline = None
@@ -589,14 +824,15 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD % n, "leaves": n, "contacts_per_step": int(ncontacts),
+            "config": bench_config(),
+            "details": {"contacts_per_step": int(ncontacts),
                        "contact_order": "reference (ascending query, DFS order; count+scan+write)" if ordered else "unordered (one pass, buffered warp-aggregated atomics; identical as a sorted list)",
                        "parallelism": "single GPU" if world == 1 else (("build replicated on every rank (deterministic, bit-identical)" if args.build_mode == "replicate" else "build on rank 0 + NCCL broadcast of the tree") + f", query-range sharded traversal over {world} GPUs, " + ("traversal fused with the all-gather: contacts written into every rank's list by the traversal kernel (multimem.st over NVLink)" if fused else "contact shards all-gathered by the library's peer-memory kernel (NVLink multicast stores)" if args.gather in ("peer", "fused") else "NCCL all-gather of the contact shards")),
                        "host_sync": ("deferred traversal (IBVH_TRAVERSE_DEFER): the next build is enqueued before the host reads a step's contact count; every count is read inside the timed region"
                                      if (world == 1 and not ordered and not args.no_defer) else "synchronous calls: the host reads each step's contact count before the next build is enqueued"),
                        "l2_policy": "inputs larger than L2 (160 MB volumes + 240 MB leaves + 240 MB nodes per step vs 126 MB L2)"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,
-            "secondary": rays,
+            "secondary": rays, "workloads": workloads, "verify": verify,
         }
         print(json.dumps(out), flush=True)
     if world > 1:

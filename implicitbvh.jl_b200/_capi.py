@@ -37,7 +37,8 @@ class Bvh(C.Structure):
 
 class Peer(C.Structure):
     _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("buffers", C.c_uint64 * MAX_PEERS), ("multicast", C.c_uint64),
-                ("header_bytes", C.c_int64), ("capacity_bytes", C.c_int64), ("epoch", C.c_uint64), ("fused_seq", C.c_uint64)]
+                ("header_bytes", C.c_int64), ("capacity_bytes", C.c_int64), ("epoch", C.c_uint64), ("fused_seq", C.c_uint64),
+                ("region_begin", C.c_int64 * (MAX_PEERS + 1))]
 
 
 class TraverseParams(C.Structure):
@@ -70,6 +71,7 @@ SIGNATURES = {
     "ibvh_sort_leaves": (_ci, [_vp, _vp, _i64, C.POINTER(Types), _vp]),
     "ibvh_aggregate": (_ci, [_vp, _vp, _i64, C.POINTER(Types), _vp, _i64, _vp]),
     "ibvh_build": (_ci, [_vp, _vp, _vp, _i64, C.POINTER(Types), _vp, _i64, _ci, _dp, _dp, _vp]),
+    "ibvh_build_reference_shaped": (_ci, [_vp, _vp, _vp, _i64, C.POINTER(Types), _vp, _i64, _vp]),
     "ibvh_traverse_single": (_ci, [_vp, C.POINTER(Bvh), C.POINTER(TraverseParams), _vp, _vp, _i64, C.POINTER(_i64), _vp]),
     "ibvh_traverse_pair": (_ci, [_vp, C.POINTER(Bvh), C.POINTER(Bvh), C.POINTER(TraverseParams), _vp, _vp, _i64, C.POINTER(_i64), _vp]),
     "ibvh_traverse_rays": (_ci, [_vp, C.POINTER(Bvh), _vp, _vp, _i64, C.POINTER(TraverseParams), _vp, _vp, _i64, C.POINTER(_i64), _vp]),
@@ -80,6 +82,7 @@ SIGNATURES = {
     "ibvh_last_traversal_stats": (_ci, [_vp, C.POINTER(_i64)]),
     "ibvh_traverse_finish": (_ci, [_vp, C.POINTER(_i64)]),
     "ibvh_traverse_cancel": (_ci, [_vp]),
+    "ibvh_peer_last_counts": (_ci, [_vp, C.POINTER(_i64), C.c_int32]),
     "ibvh_allgather_pairs": (_ci, [_vp, C.POINTER(Peer), _vp, _i64, C.c_int32, C.POINTER(_i64), C.POINTER(_i64), _vp]),
 }
 

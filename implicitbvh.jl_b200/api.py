@@ -341,6 +341,7 @@ def _types(leaf_vol: VolumeType, node: VolumeType, index: np.dtype, morton: np.d
 class BVH:
     """`BVH(bounding_volumes, node_type=BBox{Float32}; built_level=1, cache=nothing, options=BVHOptions())`.
 
+    `reference_shaped=True` (extension, measurement aid): build with the naive reference-shaped kernels instead.
     `bounding_volumes`: numpy structured array or DeviceArray of raw volumes (BSphere/BBox: wrapped on
     device, index = position) or of BoundingVolume structs (sorted IN PLACE when already on the device,
     as in the reference, build.jl:147-152). Fields mirror build.jl:155-166.
@@ -348,7 +349,7 @@ class BVH:
 
     def __init__(self, bounding_volumes: Union[np.ndarray, DeviceArray], node_type: VolumeType = None, *,
                  built_level: Union[int, float] = 1, cache: Optional["BVH"] = None, options: BVHOptions = None,
-                 device=None):
+                 device=None, reference_shaped: bool = False):
         options = options or BVHOptions()
         node_type = node_type or BBox(np.float32)
         lib = capi.lib()
@@ -440,6 +441,15 @@ class BVH:
         m = options.morton
         mins = (C.c_double * 3)(*[float(x) for x in m.mins])
         maxs = (C.c_double * 3)(*[float(x) for x in m.maxs])
+        if reference_shaped:
+            # measurement aid: the naive "reference-shaped" GPU build (proxy of the reference's CUDA.jl backend; same result)
+            if d_vol is None or not m.compute_extrema:
+                raise ArgumentError("the reference-shaped proxy build takes raw volumes and computes the extrema itself")
+            rc = lib.ibvh_build_reference_shaped(self._handle, d_vol, self.leaves.ptr, n, C.byref(self.types),
+                                                 self.nodes.ptr if num_nodes > 0 else None, self.built_level, _stream_ptr(didx))
+            if rc != capi.OK:
+                _raise(rc, self._handle, "ibvh_build_reference_shaped")
+            return
         # (the library switches to the handle's device itself; the stream is torch's current stream on it)
         rc = lib.ibvh_build(self._handle, d_vol, self.leaves.ptr, n, C.byref(self.types),
                             self.nodes.ptr if num_nodes > 0 else None, self.built_level,
@@ -544,6 +554,25 @@ class _Pending:
         return tr
 
 
+def _fused_call(call, peer, handle, what: str) -> C.c_int64:
+    """One fused traversal + all-gather (collective). The ranks' regions of the gathered list are sized from the previous
+    call's per-rank counts; if a region turns out too small (IBVH_ERR_CAPACITY: the same verdict on every rank, with the
+    counts) they are re-sized from the counts just seen and the call is repeated once."""
+    total = C.c_int64(0)
+    rc = call(peer.next_fused(), total)
+    if rc == capi.ERR_CAPACITY:
+        counts = peer.last_counts()
+        if not (peer.set_regions(counts) or peer.set_regions(counts, slack=0.01)):
+            _raise(rc, handle, f"{what}: the peer list area is too small for {total.value} pairs")
+        rc = call(peer.next_fused(), total)
+    if rc != capi.OK:
+        _raise(rc, handle, f"{what} (gathered total {total.value} pairs)")
+    counts = peer.last_counts()
+    if not (peer.set_regions(counts) or peer.set_regions(counts, slack=0.01)):
+        peer.set_regions(None)
+    return total
+
+
 def _check_narrow(narrow):
     if narrow is not None:
         raise NotImplementedError("custom `narrow` closures cannot cross the C ABI (SURVEY.md §8f-3); only the default is supported")
@@ -638,10 +667,7 @@ def traverse(bvh: BVH, bvh2=None, alg=None, *, start_level: Optional[int] = None
             return _run_two_phase(call, handle, device, I, nq, cache, ordered, reference_shaped, packet, walk)
         if peer.pair_bytes != pair_dtype(I).itemsize or peer.device != device:
             raise ArgumentError("PeerGather pair size / device do not match the BVH")
-        total = C.c_int64(0)
-        rc = call(capi.TRAVERSE_UNORDERED, None, None, 0, total, peer.next_fused())
-        if rc != capi.OK:
-            _raise(rc, handle, f"fused traverse (gathered total {total.value} pairs)")
+        total = _fused_call(lambda pref, tot: call(capi.TRAVERSE_UNORDERED, None, None, 0, tot, pref), peer, handle, "fused traverse")
         c2 = cache.cache2 if cache is not None else DeviceArray.empty(0, I, device)
         return int(total.value), DeviceArray(peer.list_area(), pair_dtype(I)), c2
 
@@ -748,10 +774,7 @@ def traverse_rays(bvh: BVH, points, directions, alg=None, *, start_level: int = 
             raise ArgumentError("the fused multi-GPU ray traversal is unordered (ordered=False)")
         if peer.pair_bytes != pair_dtype(I).itemsize or peer.device != device:
             raise ArgumentError("PeerGather pair size / device do not match the BVH")
-        total = C.c_int64(0)
-        rc = call(capi.TRAVERSE_UNORDERED, None, None, 0, total, peer.next_fused())
-        if rc != capi.OK:
-            _raise(rc, bvh._handle, f"fused traverse_rays (gathered total {total.value} hits)")
+        total = _fused_call(lambda pref, tot: call(capi.TRAVERSE_UNORDERED, None, None, 0, tot, pref), peer, bvh._handle, "fused traverse_rays")
         c2 = cache.cache2 if cache is not None else DeviceArray.empty(0, I, device)
         return BVHTraversal(start_level, 0, 0, int(total.value), DeviceArray(peer.list_area(), pair_dtype(I)), c2)
     total, c1, c2 = _run_two_phase(call, bvh._handle, device, I, nrays, cache, ordered, False)

@@ -18,6 +18,7 @@
 #include "handle.cuh"
 #include "morton.cuh"
 #include "radix_sort.cuh"
+#include "reference_shaped.cuh"
 #include "traverse.cuh"
 #include "traverse_tile.cuh"
 #include "traverse_pyramid.cuh"
@@ -236,14 +237,16 @@ int launch_encode(ibvh_handle* h, const SRC* src, int64_t n, int compute_extrema
     }
     IBVH_LAUNCH_CHECK(h, "init_build_kernel");
     const int grid = grid_for(n, 256, 4, h->sm_count * 8);
+    const uintptr_t va = (uintptr_t)src;
+    const int vec = va % 16 == 0 ? 16 : (va % 8 == 0 ? 8 : 4);          // widest load the array's alignment allows
     if (compute_extrema) {
         { ProfScope _ps(h, st, "bounds_kernel");
-        bounds_kernel<SRC, T><<<grid, 256, 0, st>>>(src, n, bounds);
+        bounds_kernel<SRC, T><<<grid, 256, 0, st>>>(src, n, bounds, vec);
         }
         IBVH_LAUNCH_CHECK(h, "bounds_kernel");
     }
     { ProfScope _ps(h, st, "encode_kernel");
-    encode_kernel<SRC, L, COPY><<<grid, 256, 0, st>>>(src, n, compute_extrema ? bounds : nullptr, user, used, keys, copy, hist);
+    encode_kernel<SRC, L, COPY><<<grid, 256, 0, st>>>(src, n, compute_extrema ? bounds : nullptr, user, used, keys, copy, hist, vec);
     }
     IBVH_LAUNCH_CHECK(h, "encode_kernel");
     return IBVH_OK;
@@ -404,20 +407,41 @@ int traverse_impl(ibvh_handle* h, const LQ* qleaves, const typename LT::value_ty
                 return IBVH_ERR_UNSUPPORTED;
             }
             PeerArgs pa = make_peer_args(a.peer);
-            a.total = (unsigned long long*)pa.buf[0] + kPeerCounterSlot + pa.fused_seq % 3;
-            a.capacity = pa.capacity_bytes / (int64_t)sizeof(IndexPair<I>);
-            rc = a.q_count > 0 ? launch_traverse<KIND, kAtomic, PACKET, LQ, LT, N, I>(h, qleaves, points, dirs, bvh, a, (I*)nullptr, (IndexPair<I>*)(pa.mc + pa.header_bytes), st) : IBVH_OK;
-            if (rc != IBVH_OK) return rc;
+            long long region[IBVH_MAX_PEERS + 1];
+            peer_regions(a.peer, (int)sizeof(IndexPair<I>), region);
+            a.capacity = region[pa.rank + 1] - region[pa.rank];
             int64_t* h_peer = (int64_t*)(h->h_pinned + 3072);
-            h_peer[1] = -1;
+            h_peer[1] = 0;
+            IBVH_CUDA_TRY(h, cudaMemsetAsync(d_total, 0, 8, st));       // local slot counter
+            { ProfScope _ps(h, st, "peer_fused_begin_kernel");
+            peer_fused_begin_kernel<<<1, 32, 0, st>>>(pa);
+            }
+            IBVH_LAUNCH_CHECK(h, "peer_fused_begin_kernel");
+            { ProfScope _ps(h, st, "peer_fused_wait_kernel");
+            peer_fused_wait_kernel<<<1, 32, 0, st>>>(pa, h_peer);
+            }
+            IBVH_LAUNCH_CHECK(h, "peer_fused_wait_kernel");
+            rc = a.q_count > 0 ? launch_traverse<KIND, kAtomic, PACKET, LQ, LT, N, I>(h, qleaves, points, dirs, bvh, a, (I*)nullptr, (IndexPair<I>*)(pa.mc + pa.header_bytes) + region[pa.rank], st) : IBVH_OK;
+            if (rc != IBVH_OK) return rc;
             { ProfScope _ps(h, st, "peer_fused_finish_kernel");
-            peer_fused_finish_kernel<<<1, 32, 0, st>>>(pa, h_peer);
+            peer_fused_finish_kernel<<<1, 32, 0, st>>>(pa, d_total, h_peer);
             }
             IBVH_LAUNCH_CHECK(h, "peer_fused_finish_kernel");
             IBVH_CUDA_TRY(h, cudaStreamSynchronize(st));
-            if (h_peer[1] != 0) { h->set_error("fused ray traversal: a peer did not finish its shard within 10 s"); return IBVH_ERR_PEER; }
+            if (h_peer[1] != 0) { h->set_error("fused ray traversal: a peer did not arrive within 10 s"); return IBVH_ERR_PEER; }
             *num_contacts = h_peer[0];
-            return *num_contacts > a.capacity ? IBVH_ERR_CAPACITY : IBVH_OK;
+            long long counts_r[IBVH_MAX_PEERS];
+            bool over = false;
+            for (int r = 0; r < pa.world; ++r) { counts_r[r] = h_peer[2 + r]; h->last_peer_counts[r] = counts_r[r]; if (counts_r[r] > region[r + 1] - region[r]) over = true; }
+            if (over) return IBVH_ERR_CAPACITY;
+            PeerMoves mv = make_compact_moves(pa.world, region, counts_r, (int)sizeof(IndexPair<I>) / 8);
+            if (mv.n > 0) {
+                { ProfScope _ps(h, st, "peer_compact_kernel");
+                peer_compact_kernel<<<h->sm_count * 2, 256, 0, st>>>((uint64_t*)(pa.buf[pa.rank] + pa.header_bytes), mv);
+                }
+                IBVH_LAUNCH_CHECK(h, "peer_compact_kernel");
+            }
+            return IBVH_OK;
         }
     }
     if (unordered) {
@@ -618,29 +642,58 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
     using T = typename LT::value_type;
     using N = BBox<T>;
     *num_contacts = 0;
-    // fused multi-GPU mode: slots come from the rotating counter on rank 0, contacts go out through the multicast alias
+    // fused multi-GPU mode (peer.cuh, round-2 protocol): slots come from a LOCAL counter and index this rank's region of
+    // the gathered list; the contacts go out through the multicast alias; counts are exchanged by the finish kernel
     const bool fused = ta.peer != nullptr;
     PeerArgs pa{};
     unsigned long long* out_total = (unsigned long long*)(h->d_small + kSmallTotal);
     IndexPair<I>* out_ptr = (IndexPair<I>*)d_contacts;
     int64_t* h_peer = (int64_t*)(h->h_pinned + 3072);
+    long long region[IBVH_MAX_PEERS + 1] = {0};
     if (fused) {
         pa = make_peer_args(ta.peer);
-        out_total = (unsigned long long*)pa.buf[0] + kPeerCounterSlot + pa.fused_seq % 3;
-        out_ptr = (IndexPair<I>*)(pa.mc + pa.header_bytes);
-        capacity = pa.capacity_bytes / (int64_t)sizeof(IndexPair<I>);
+        peer_regions(ta.peer, (int)sizeof(IndexPair<I>), region);
+        out_ptr = (IndexPair<I>*)(pa.mc + pa.header_bytes) + region[pa.rank];
+        capacity = region[pa.rank + 1] - region[pa.rank];
+        h_peer[1] = 0;
+        { ProfScope _ps(h, st, "peer_fused_begin_kernel");
+        peer_fused_begin_kernel<<<1, 32, 0, st>>>(pa);
+        }
+        IBVH_LAUNCH_CHECK(h, "peer_fused_begin_kernel");
     }
     auto fused_finish = [&]() -> int {
-        h_peer[1] = -1;
         { ProfScope _ps(h, st, "peer_fused_finish_kernel");
-        peer_fused_finish_kernel<<<1, 32, 0, st>>>(pa, h_peer);
+        peer_fused_finish_kernel<<<1, 32, 0, st>>>(pa, out_total, h_peer);
         }
         IBVH_LAUNCH_CHECK(h, "peer_fused_finish_kernel");
         IBVH_CUDA_TRY(h, cudaStreamSynchronize(st));
-        if (h_peer[1] != 0) { h->set_error("fused traversal: a peer did not finish its shard within 10 s"); return IBVH_ERR_PEER; }
+        if (h_peer[1] != 0) { h->set_error("fused traversal: a peer did not arrive within 10 s"); return IBVH_ERR_PEER; }
         *num_contacts = h_peer[0];
-        return *num_contacts > capacity ? IBVH_ERR_CAPACITY : IBVH_OK;
+        long long counts_r[IBVH_MAX_PEERS];
+        bool over = false;
+        for (int r = 0; r < pa.world; ++r) { counts_r[r] = h_peer[2 + r]; h->last_peer_counts[r] = counts_r[r]; if (counts_r[r] > region[r + 1] - region[r]) over = true; }
+        if (over) return IBVH_ERR_CAPACITY;
+        PeerMoves mv = make_compact_moves(pa.world, region, counts_r, (int)sizeof(IndexPair<I>) / 8);
+        if (mv.n > 0) {
+            { ProfScope _ps(h, st, "peer_compact_kernel");
+            peer_compact_kernel<<<h->sm_count * 2, 256, 0, st>>>((uint64_t*)(pa.buf[pa.rank] + pa.header_bytes), mv);
+            }
+            IBVH_LAUNCH_CHECK(h, "peer_compact_kernel");
+        }
+        return IBVH_OK;
     };
+    auto fused_wait = [&]() -> int {
+        { ProfScope _ps(h, st, "peer_fused_wait_kernel");
+        peer_fused_wait_kernel<<<1, 32, 0, st>>>(pa, h_peer);
+        }
+        IBVH_LAUNCH_CHECK(h, "peer_fused_wait_kernel");
+        return IBVH_OK;
+    };
+    if (fused && ta.q_count <= 0) {
+        IBVH_CUDA_TRY(h, cudaMemsetAsync(out_total, 0, 8, st));
+        int rcw = fused_wait();
+        if (rcw != IBVH_OK) return rcw;
+    }
     if (ta.q_count <= 0) return fused ? fused_finish() : IBVH_OK;
     const int64_t q_begin = ta.q_begin, q_end = ta.q_begin + ta.q_count;
     unsigned long long* d_total = (unsigned long long*)(h->d_small + kSmallTotal);
@@ -709,7 +762,7 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
         PairList lists[kPyrMaxLevels];
         for (int l = 0; l < nl; ++l) { lists[l].data = (uint2*)ap; lists[l].count = d_cnt + l; lists[l].cap = cap[l]; ap += ibvh_handle::padded((size_t)cap[l] * sizeof(uint2)); }
         IBVH_CUDA_TRY(h, cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * kPyrMaxLevels + 128, st));   // list counters + chunk tickets
-        IBVH_CUDA_TRY(h, cudaMemsetAsync(d_total, 0, 8, st));      // (fused: the rank-0 counter is rotated by the finish kernel instead)
+        IBVH_CUDA_TRY(h, cudaMemsetAsync(d_total, 0, 8, st));
 
         // 0. 16-byte aligned records: leaf volumes, and the node levels the refinement reads as targets
         const int64_t qend_c = q_end < n_query_total ? q_end : n_query_total;
@@ -785,12 +838,12 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
                 h->last_stats[2] = (int64_t)hp[1];
                 h->last_stats[3] = nl;
             }
+            {   // every rank has let go of the previous list before the first store of this call leaves
+                int rcw = fused_wait();
+                if (rcw != IBVH_OK) return rcw;
+            }
             { ProfScope _ps(h, st, "pyr_leaf_tile_kernel");
-            const int big = h->cfg.fused_flush >= 0 ? h->cfg.fused_flush >= 512 : pa.world >= 4;
-            if (big)
-                pyr_leaf_tile_kernel<KIND, kAtomic, 0, LQ, LT, I, (sizeof(typename LT::vol_t) > 32 ? 256 : 512)><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, capacity, out_total, (I*)nullptr, nullptr, out_ptr, 1, d_tick + 16 + (tile_launch++), PQ, PT);
-            else
-                pyr_leaf_tile_kernel<KIND, kAtomic, 0, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, capacity, out_total, (I*)nullptr, nullptr, out_ptr, 1, d_tick + 16 + (tile_launch++), PQ, PT);
+            pyr_leaf_tile_kernel<KIND, kAtomic, 0, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, capacity, out_total, (I*)nullptr, nullptr, out_ptr, 1, d_tick + 16 + (tile_launch++), PQ, PT);
             }
             IBVH_LAUNCH_CHECK(h, "pyr_leaf_tile_kernel");
             return fused_finish();
@@ -1163,6 +1216,12 @@ int ibvh_traverse_cancel(ibvh_handle_t* h) {
     return IBVH_OK;
 }
 
+int ibvh_peer_last_counts(ibvh_handle_t* h, int64_t* counts, int32_t world) {
+    if (!h || !counts || world < 1 || world > IBVH_MAX_PEERS) return IBVH_ERR_ARGUMENT;
+    for (int r = 0; r < world; ++r) counts[r] = h->last_peer_counts[r];
+    return IBVH_OK;
+}
+
 int ibvh_last_traversal_stats(ibvh_handle_t* h, int64_t out[4]) {
     if (!h || !out) return IBVH_ERR_ARGUMENT;
     for (int k = 0; k < 4; ++k) out[k] = h->last_stats[k];
@@ -1308,6 +1367,98 @@ int ibvh_build(ibvh_handle_t* h, const void* d_volumes, void* d_leaves, int64_t 
             return build_impl<L, N>(h, d_volumes, d_leaves, n, d_nodes, built_level, compute_extrema, mins, maxs, st);
         });
     });
+}
+
+// ---- reference-shaped proxy build (reference_shaped.cuh): what BVH(...) launches through AcceleratedKernels ----------
+int ibvh_build_reference_shaped(ibvh_handle_t* h, const void* d_volumes, void* d_leaves, int64_t n, const ibvh_types_t* types,
+                                void* d_nodes, int64_t built_level, void* stream) {
+    namespace rs = ibvh::refshaped;
+    if (!h || !types_ok(types)) return IBVH_ERR_ARGUMENT;
+    if (n < 1) return IBVH_ERR_DOMAIN;
+    if (!d_volumes || !d_leaves) return IBVH_ERR_ARGUMENT;
+    if (!(types->leaf_kind == IBVH_BSPHERE && types->node_kind == IBVH_BBOX && types->float_bytes == 4 && types->index_bytes == 4 &&
+          types->morton_bytes == 4 && (types->reserved == 0 || types->reserved == 4))) {
+        h->set_error("the reference-shaped proxy build exists for BSphere{Float32} / Int32 / UInt32 / BBox{Float32} only");
+        return IBVH_ERR_UNSUPPORTED;
+    }
+    ibvh_tree_t tree;
+    int rc = make_tree(n, &tree);
+    if (rc != IBVH_OK) return rc;
+    if (built_level < 1 || built_level > tree.levels) return IBVH_ERR_ARGUMENT;
+    if (ibvh_num_nodes(n) > 0 && !d_nodes) return IBVH_ERR_ARGUMENT;
+    DeviceGuard g(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    rs::RLeaf* leaves = (rs::RLeaf*)d_leaves;
+    rs::RNode* nodes = (rs::RNode*)d_nodes;
+    const int rblocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)h->sm_count * 8);
+    rc = h->reserve(ibvh_handle::padded((size_t)n * sizeof(rs::RLeaf)) + ibvh_handle::padded((size_t)rblocks * 3 * 4) + 4096);
+    if (rc != IBVH_OK) return rc;
+    h->reset();
+    rs::RLeaf* tmp = h->alloc<rs::RLeaf>(n);
+    float* partial = h->alloc<float>((size_t)rblocks * 3);
+    if (!tmp || !partial) { h->set_error("workspace carve failed"); return IBVH_ERR_ALLOC; }
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    // wrap_bounding_volumes (build.jl:340)
+    { ProfScope _ps(h, st, "ref_wrap_kernel");
+    wrap_kernel<rs::RLeaf><<<nb, 256, 0, st>>>((const BSphere<float>*)d_volumes, n, leaves);
+    }
+    IBVH_LAUNCH_CHECK(h, "ref_wrap_kernel");
+    // _compute_extrema: two mapreduce passes, each ending in a scalar read-back on the host (morton/utils.jl:24-44)
+    float* d_ext = (float*)(h->d_small + kSmallBoundsF + 256);
+    float* h_ext = (float*)(h->h_pinned + 2048 + 256);
+    { ProfScope _ps(h, st, "ref_extrema_kernel");
+    rs::extrema_partial_kernel<false><<<rblocks, 256, 0, st>>>(leaves, n, partial);
+    rs::extrema_final_kernel<false><<<1, 32, 0, st>>>(partial, rblocks, d_ext);
+    }
+    IBVH_LAUNCH_CHECK(h, "ref_extrema_kernel(min)");
+    IBVH_CUDA_TRY(h, cudaMemcpyAsync(h_ext, d_ext, 12, cudaMemcpyDeviceToHost, st));
+    IBVH_CUDA_TRY(h, cudaStreamSynchronize(st));
+    { ProfScope _ps(h, st, "ref_extrema_kernel");
+    rs::extrema_partial_kernel<true><<<rblocks, 256, 0, st>>>(leaves, n, partial);
+    rs::extrema_final_kernel<true><<<1, 32, 0, st>>>(partial, rblocks, d_ext + 3);
+    }
+    IBVH_LAUNCH_CHECK(h, "ref_extrema_kernel(max)");
+    IBVH_CUDA_TRY(h, cudaMemcpyAsync(h_ext + 3, d_ext + 3, 12, cudaMemcpyDeviceToHost, st));
+    IBVH_CUDA_TRY(h, cudaStreamSynchronize(st));
+    rs::Bounds6 b;
+    for (int k = 0; k < 3; ++k) { b.mins[k] = h_ext[k]; b.maxs[k] = h_ext[3 + k]; }
+    pad_extrema(b.mins, b.maxs);                                   // on the host, as bounding_volumes_extrema does (morton/utils.jl:63-69)
+    // _morton_encode! (default.jl:66)
+    { ProfScope _ps(h, st, "ref_encode_kernel");
+    rs::encode_kernel<<<nb, 256, 0, st>>>(leaves, n, b);
+    }
+    IBVH_LAUNCH_CHECK(h, "ref_encode_kernel");
+    // AK.sort!(leaves, by = morton): struct-moving merge sort (build.jl:248-253)
+    rs::RLeaf* cur = tmp; rs::RLeaf* other = leaves;
+    { ProfScope _ps(h, st, "ref_block_sort_kernel");
+    rs::block_sort_kernel<<<(unsigned)((n + rs::kBlockSort - 1) / rs::kBlockSort), rs::kBlockSort, 0, st>>>(leaves, tmp, n);
+    }
+    IBVH_LAUNCH_CHECK(h, "ref_block_sort_kernel");
+    for (int64_t width = rs::kBlockSort; width < n; width *= 2) {
+        const int64_t threads = (n + rs::kMergePerThread - 1) / rs::kMergePerThread;
+        { ProfScope _ps(h, st, "ref_merge_pass_kernel");
+        rs::merge_pass_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(cur, other, n, width);
+        }
+        IBVH_LAUNCH_CHECK(h, "ref_merge_pass_kernel");
+        rs::RLeaf* t = cur; cur = other; other = t;
+    }
+    if (cur != leaves) IBVH_CUDA_TRY(h, cudaMemcpyAsync(leaves, cur, (size_t)n * sizeof(rs::RLeaf), cudaMemcpyDeviceToDevice, st));
+    // aggregate_oibvh!: one launch per level (build.jl:366-523)
+    if (tree.real_nodes >= 2) {
+        TreeInfo ti = make_tree_info(tree);
+        int lvl = (int)tree.levels - 1;
+        { ProfScope _ps(h, st, "ref_aggregate_kernel");
+        rs::aggregate_last_level_kernel<<<(unsigned)((ti.level_nreal[lvl] + 255) / 256), 256, 0, st>>>(leaves, nodes, n, ti.level_start[lvl], ti.level_nreal[lvl]);
+        }
+        IBVH_LAUNCH_CHECK(h, "ref_aggregate_kernel(last level)");
+        for (lvl -= 1; lvl >= built_level && lvl >= 1; --lvl) {
+            { ProfScope _ps(h, st, "ref_aggregate_kernel");
+            rs::aggregate_level_kernel<<<(unsigned)((ti.level_nreal[lvl] + 255) / 256), 256, 0, st>>>(nodes, ti.level_start[lvl], ti.level_nreal[lvl], ti.level_start[lvl + 1], ti.level_nreal[lvl + 1]);
+            }
+            IBVH_LAUNCH_CHECK(h, "ref_aggregate_kernel");
+        }
+    }
+    return IBVH_OK;
 }
 
 #endif  // IBVH_PART_BUILD

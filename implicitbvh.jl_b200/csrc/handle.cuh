@@ -70,6 +70,7 @@ struct ibvh_handle {
     static constexpr size_t kPinnedBytes = 4096;
 
     int64_t last_stats[4] = {0, 0, 0, 0};
+    int64_t last_peer_counts[16] = {0};      // per-rank counts of the last fused multi-GPU traversal (ibvh_peer_last_counts)
 
     // one outstanding deferred traversal (IBVH_TRAVERSE_DEFER): what ibvh_traverse_finish needs to judge the
     // read-back that the enqueued work leaves in the pinned block

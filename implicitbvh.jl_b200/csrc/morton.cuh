@@ -137,19 +137,39 @@ __global__ void init_build_kernel(typename OrdOf<T>::type* bounds, uint32_t* his
 }
 
 // ---- pass 1: min / max of the centres --------------------------------------------------------------------
-// SRC is either a raw volume (wrap path) or a wrapped leaf; `volume_of` picks the volume.
-template <class V> IBVH_D const V& volume_of(const V& v) { return v; }
-template <class V, class I, class M> IBVH_D const V& volume_of(const Leaf<V, I, M>& l) { return l.volume; }
+// SRC is either a raw volume (wrap path) or a wrapped leaf. Records are fetched with the widest loads the array's
+// alignment allows (`vec` = 16 / 8 / 4 bytes, chosen by the host from the pointer: a struct of floats only promises
+// 4-byte alignment) and kStreamUnroll records per thread are in flight at once — with one scalar-load record per
+// thread the two streaming passes ran at 72 % / 53 % of the copy bandwidth (round 1).
+constexpr int kStreamUnroll = 4;
+
+template <class V> IBVH_D V fetch_volume(const V* p, int vec) { return load_volume(p, vec); }
+template <class V, class I, class M> IBVH_D V fetch_volume(const Leaf<V, I, M>* p, int) {
+    Words<Leaf<V, I, M>> wv = load_words(p);
+    return words_volume<Leaf<V, I, M>>(wv);
+}
 
 template <class SRC, class T>
-__global__ void __launch_bounds__(256) bounds_kernel(const SRC* __restrict__ src, int64_t n, typename OrdOf<T>::type* bounds) {
+__global__ void __launch_bounds__(256) bounds_kernel(const SRC* __restrict__ src, int64_t n, typename OrdOf<T>::type* bounds, int vec) {
     T mn[3] = {FloatLimits<T>::fmax_(), FloatLimits<T>::fmax_(), FloatLimits<T>::fmax_()};
     T mx[3] = {FloatLimits<T>::fmin_(), FloatLimits<T>::fmin_(), FloatLimits<T>::fmin_()};
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + (kStreamUnroll - 1) * stride < n; i += kStreamUnroll * stride) {
+        decltype(fetch_volume(src, vec)) v[kStreamUnroll];
+#pragma unroll
+        for (int u = 0; u < kStreamUnroll; ++u) v[u] = fetch_volume(src + i + u * stride, vec);
+#pragma unroll
+        for (int u = 0; u < kStreamUnroll; ++u) {
+            T c[3];
+            center(v[u], c);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { mn[k] = mn[k] < c[k] ? mn[k] : c[k]; mx[k] = mx[k] > c[k] ? mx[k] : c[k]; }
+        }
+    }
+    for (; i < n; i += stride) {
         T c[3];
-        SRC s = src[i];
-        center(volume_of(s), c);
+        center(fetch_volume(src + i, vec), c);
 #pragma unroll
         for (int k = 0; k < 3; ++k) { mn[k] = mn[k] < c[k] ? mn[k] : c[k]; mx[k] = mx[k] > c[k] ? mx[k] : c[k]; }
     }
@@ -181,18 +201,25 @@ __global__ void __launch_bounds__(256) bounds_kernel(const SRC* __restrict__ src
 // bounds_in: ordered keys of the raw extrema (compute_extrema) or nullptr when user bounds are given
 // in `user_bounds` (6 values, unpadded — SURVEY.md §8c quirk 2).
 // used_bounds: 6 T's written by block 0 for read-back.
+// Digit histograms of all radix passes: one shared-memory atomic per key and pass into a histogram PRIVATE to the
+// warp (IBVH_ENCODE_HIST == 2; 8 warps never collide on a counter) or shared by the block (== 1).
+#ifndef IBVH_ENCODE_HIST
+#define IBVH_ENCODE_HIST 1
+#endif
 template <class SRC, class L, bool COPY>
 __global__ void __launch_bounds__(256) encode_kernel(const SRC* __restrict__ src, int64_t n,
                                                     const typename OrdOf<typename L::value_type>::type* __restrict__ bounds_in,
                                                     const typename L::value_type* __restrict__ user_bounds,
                                                     typename L::value_type* used_bounds,
                                                     typename L::mor_t* __restrict__ keys,
-                                                    L* __restrict__ copy_out, uint32_t* __restrict__ hist) {
+                                                    L* __restrict__ copy_out, uint32_t* __restrict__ hist, int vec) {
     using T = typename L::value_type;
     using M = typename L::mor_t;
     constexpr int P = radix_passes<M>();
-    __shared__ uint32_t sh[P][kRadixBins];
-    for (int i = threadIdx.x; i < P * kRadixBins; i += blockDim.x) (&sh[0][0])[i] = 0;
+    constexpr int HW = IBVH_ENCODE_HIST == 2 ? 8 : 1;                      // private histograms per block
+    __shared__ uint32_t sh[HW][P][kRadixBins];
+    for (int i = threadIdx.x; i < HW * P * kRadixBins; i += blockDim.x) (&sh[0][0][0])[i] = 0;
+    uint32_t (*myh)[kRadixBins] = sh[HW == 1 ? 0 : (threadIdx.x >> 5)];
     T mins[3], maxs[3];
     if (bounds_in) {
 #pragma unroll
@@ -207,27 +234,49 @@ __global__ void __launch_bounds__(256) encode_kernel(const SRC* __restrict__ src
         for (int k = 0; k < 3; ++k) { used_bounds[k] = mins[k]; used_bounds[3 + k] = maxs[k]; }
     }
     __syncthreads();
+    auto one = [&](int64_t i, const T (&c)[3]) {
+        M m = morton_encode_single<M>(c, mins, maxs);
+        keys[i] = m;
+#if IBVH_ENCODE_HIST
+#pragma unroll
+        for (int p = 0; p < P; ++p) atomicAdd(&myh[p][(uint32_t)(m >> (p * kRadixBits)) & (kRadixBins - 1)], 1u);
+#endif
+    };
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        T c[3];
-        if constexpr (COPY) {
-            // move the leaf as raw words so every byte (padding included) survives the copy
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if constexpr (COPY) {
+        // move the leaf as raw words so every byte (padding included) survives the copy
+        for (; i < n; i += stride) {
+            T c[3];
             Words<L> wv = load_words(reinterpret_cast<const L*>(src) + i);
             store_words(copy_out + i, wv);
             center(words_volume<L>(wv), c);
-        } else {
-            SRC s = src[i];
-            center(volume_of(s), c);
+            one(i, c);
         }
-        M m = morton_encode_single<M>(c, mins, maxs);
-        keys[i] = m;
+    } else {
+        for (; i + (kStreamUnroll - 1) * stride < n; i += kStreamUnroll * stride) {
+            decltype(fetch_volume(src, vec)) v[kStreamUnroll];
 #pragma unroll
-        for (int p = 0; p < P; ++p) atomicAdd(&sh[p][(uint32_t)(m >> (p * kRadixBits)) & (kRadixBins - 1)], 1u);
+            for (int u = 0; u < kStreamUnroll; ++u) v[u] = fetch_volume(src + i + u * stride, vec);
+#pragma unroll
+            for (int u = 0; u < kStreamUnroll; ++u) {
+                T c[3];
+                center(v[u], c);
+                one(i + u * stride, c);
+            }
+        }
+        for (; i < n; i += stride) {
+            T c[3];
+            center(fetch_volume(src + i, vec), c);
+            one(i, c);
+        }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < P * kRadixBins; i += blockDim.x) {
-        uint32_t v = (&sh[0][0])[i];
-        if (v) atomicAdd(&hist[i], v);
+    for (int i2 = threadIdx.x; i2 < P * kRadixBins; i2 += blockDim.x) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int hw = 0; hw < HW; ++hw) v += (&sh[hw][0][0])[i2];
+        if (v) atomicAdd(&hist[i2], v);
     }
 }
 

@@ -26,7 +26,7 @@ constexpr int kMergePerThread = 8;       // outputs per thread in a global merge
 
 // mapreduce(min) / mapreduce(max) over the centres: one pass each, block partials -> one block -> 3 floats
 template <bool IS_MAX>
-__global__ void __launch_bounds__(256) extrema_partial_kernel(const RLeaf* __restrict__ leaves, int64_t n, float* __restrict__ partial) {
+static __global__ void __launch_bounds__(256) extrema_partial_kernel(const RLeaf* __restrict__ leaves, int64_t n, float* __restrict__ partial) {
     float acc[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) acc[k] = IS_MAX ? FloatLimits<float>::fmin_() : FloatLimits<float>::fmax_();     // morton/utils.jl:28-29,39-40
@@ -62,7 +62,7 @@ __global__ void extrema_final_kernel(const float* __restrict__ partial, int bloc
 
 // _morton_encode!: bounds (already padded on the host, as the reference does) arrive by value
 struct Bounds6 { float mins[3], maxs[3]; };
-__global__ void __launch_bounds__(256) encode_kernel(RLeaf* leaves, int64_t n, Bounds6 b) {
+static __global__ void __launch_bounds__(256) encode_kernel(RLeaf* leaves, int64_t n, Bounds6 b) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     RLeaf l = leaves[i];
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(256) encode_kernel(RLeaf* leaves, int64_t n, B
 }
 
 // block-level stable sort of kBlockSort structs by key: bitonic network on (key << 32 | slot), then the structs move
-__global__ void __launch_bounds__(kBlockSort) block_sort_kernel(const RLeaf* __restrict__ in, RLeaf* __restrict__ out, int64_t n) {
+static __global__ void __launch_bounds__(kBlockSort) block_sort_kernel(const RLeaf* __restrict__ in, RLeaf* __restrict__ out, int64_t n) {
     __shared__ unsigned long long comp[kBlockSort];
     __shared__ RLeaf sl[kBlockSort];
     const int64_t base = (int64_t)blockIdx.x * kBlockSort;
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(kBlockSort) block_sort_kernel(const RLeaf* __r
 
 // one global merge pass: runs of `width` sorted structs are merged pairwise; each thread produces kMergePerThread
 // consecutive outputs after a merge-path binary search (ties take the left run first: stable)
-__global__ void __launch_bounds__(256) merge_pass_kernel(const RLeaf* __restrict__ in, RLeaf* __restrict__ out, int64_t n, int64_t width) {
+static __global__ void __launch_bounds__(256) merge_pass_kernel(const RLeaf* __restrict__ in, RLeaf* __restrict__ out, int64_t n, int64_t width) {
     const int64_t o0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * kMergePerThread;
     if (o0 >= n) return;
     const int64_t pair = o0 / (2 * width);
@@ -126,14 +126,14 @@ __global__ void __launch_bounds__(256) merge_pass_kernel(const RLeaf* __restrict
 }
 
 // aggregate_last_level!: parent i of leaves (2i, 2i+1), one thread per node (build.jl:427-457)
-__global__ void __launch_bounds__(256) aggregate_last_level_kernel(const RLeaf* __restrict__ leaves, RNode* __restrict__ nodes, int64_t n, int64_t start_pos, int64_t num_nodes) {
+static __global__ void __launch_bounds__(256) aggregate_last_level_kernel(const RLeaf* __restrict__ leaves, RNode* __restrict__ nodes, int64_t n, int64_t start_pos, int64_t num_nodes) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= num_nodes) return;
     const int64_t l = 2 * i, r = 2 * i + 1;
     nodes[start_pos + i] = r >= n ? NodeOps<RNode>::convert(leaves[l].volume) : NodeOps<RNode>::merge_leaves(leaves[l].volume, leaves[r].volume);
 }
 // aggregate_level!: parent i of nodes (2i, 2i+1) of the level below (build.jl:503-523)
-__global__ void __launch_bounds__(256) aggregate_level_kernel(RNode* nodes, int64_t start_pos, int64_t num_nodes, int64_t start_next, int64_t num_next) {
+static __global__ void __launch_bounds__(256) aggregate_level_kernel(RNode* nodes, int64_t start_pos, int64_t num_nodes, int64_t start_next, int64_t num_next) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= num_nodes) return;
     const int64_t l = 2 * i, r = 2 * i + 1;

@@ -301,10 +301,9 @@ __global__ void __launch_bounds__(128) rays_kernel(const typename LT::value_type
 // its longest ray is done with a handful of lanes active (measured: 4.2 of 32). Here every warp keeps
 // pulling rays from a global ticket counter and a lane that finishes its ray is refilled, so the lanes
 // stay busy. Which lane handles a ray is irrelevant for the results: counts / offsets are per ray id.
-// HB > 128 = the fused multi-GPU variant (ibvh_traverse_params_t.peer, unordered): `a.total` is the output-slot
-// counter on rank 0 (system-scope atomic over NVLink) and `contacts` the multicast alias of every rank's hit list;
-// a warp then reserves slots for >= HB - 128 hits at a time, because that ONE counter sustains ~190 M atomics/s
-// for all ranks together, and writes two hits per 16-byte multimem.st.
+// HB > 128 = the fused multi-GPU variant (ibvh_traverse_params_t.peer, unordered): `contacts` is the multicast alias
+// of this rank's region of every rank's hit list, `a.total` a local slot counter; a warp reserves slots for
+// >= HB - 128 hits at a time and writes two hits per 16-byte multimem.st (multicast stores do not coalesce).
 template <int MODE, class LT, class N, class I, int HB = 128>
 __global__ void __launch_bounds__(128) rays_persistent_kernel(const typename LT::value_type* __restrict__ points,
                                                              const typename LT::value_type* __restrict__ dirs,
@@ -361,7 +360,7 @@ __global__ void __launch_bounds__(128) rays_persistent_kernel(const typename LT:
             if constexpr (kFused) {
                 if (n >= (unsigned)(HB - 128) || (all && n > 0u)) {
                     unsigned long long base = 0;
-                    if (lane == 0) base = atomicAdd_system(a.total, (unsigned long long)n);
+                    if (lane == 0) base = atomicAdd(a.total, (unsigned long long)n);      // local counter: slots index this rank's region
                     base = __shfl_sync(0xffffffffu, base, 0);
                     if ((int64_t)(base + n) <= a.capacity) {
                         if constexpr (sizeof(IndexPair<I>) == 8) {

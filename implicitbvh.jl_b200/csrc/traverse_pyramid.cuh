@@ -382,8 +382,8 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_leaf_tile_kernel(const LQ*
                                                                       const Packed<typename LQ::vol_t>* __restrict__ pq,
                                                                       const Packed<typename LT::vol_t>* __restrict__ pt) {
     // pq / pt: the query / target leaf volumes as 16-byte aligned records (pyr_pack_volumes_kernel)
-    // fused != 0 (multi-GPU, atomic mode): `total` is the output-slot counter on rank 0 (peer-mapped, system-scope
-    // atomics over NVLink) and `contacts` the NVSwitch multicast alias of every rank's list (multimem.st)
+    // fused != 0 (multi-GPU, atomic mode): `contacts` is the NVSwitch multicast alias of this rank's region of every
+    // rank's list (multimem.st) and `capacity` the region's size; `total` is a local counter as in the other modes
     using T = typename LT::value_type;
     using N = BBox<T>;
     using VT = typename LT::vol_t;
@@ -476,7 +476,7 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_leaf_tile_kernel(const LQ*
                 ncount += kept;
             } else if (kept) {
                 unsigned long long base = 0;
-                if (lane == 0) base = fused ? atomicAdd_system(total, (unsigned long long)kept) : atomicAdd(total, (unsigned long long)kept);
+                if (lane == 0) base = atomicAdd(total, (unsigned long long)kept);      // (fused: a LOCAL counter too; the slots index this rank's region)
                 base = __shfl_sync(0xffffffffu, base, 0);
                 auto to_pair = [&](uint2 e) -> IndexPair<I> {
                     const I qidx = (I)qleaves[e.x].index;

@@ -119,6 +119,33 @@ class PeerGather:
         self.peer.epoch, self.peer.fused_seq = self.epoch, self.fused_seq
         return self._C.pointer(self.peer)
 
+    # -- regions of the fused traversals: rank r appends to [region_begin[r], region_begin[r + 1]) -----------------
+    def last_counts(self) -> List[int]:
+        """Per-rank counts of the last fused traversal (identical on every rank)."""
+        C = self._C
+        out = (C.c_int64 * self.world)()
+        self._capi.lib().ibvh_peer_last_counts(self.handle, out, self.world)
+        return [int(v) for v in out]
+
+    def set_regions(self, counts: Optional[Sequence[int]] = None, slack: float = 0.06) -> bool:
+        """Size the ranks' regions from per-rank counts (+ slack, + 4096 entries each). Every rank must pass the same
+        counts (e.g. last_counts()). None = equal split. Returns False if the list area cannot hold them."""
+        cap = self.capacity_bytes // self.pair_bytes
+        rb = self.peer.region_begin
+        if counts is None:
+            for r in range(self._capi.MAX_PEERS + 1):
+                rb[r] = 0
+            return True
+        sizes = [(int(c * (1.0 + slack)) + 4096 + 1) & ~1 for c in counts]
+        if sum(sizes) > cap:
+            return False
+        b = 0                                                    # tight regions (the slack is what the gap filling has to move);
+        for r in range(self.world):                              # the unused room stays behind the last one
+            rb[r] = b
+            b += sizes[r]
+        rb[self.world] = b
+        return True
+
     def list_area(self) -> torch.Tensor:
         return self.buf[self.HEADER: self.HEADER + self.capacity_bytes]
 

@@ -115,6 +115,9 @@ typedef struct ibvh_peer {
     int64_t capacity_bytes;              /* size of the list area that follows the header             */
     uint64_t epoch;                      /* collective-call counter shared by all ranks (> 0, increasing) */
     uint64_t fused_seq;                  /* 1, 2, 3, ... over the FUSED traversals issued on this buffer */
+    int64_t region_begin[IBVH_MAX_PEERS + 1]; /* FUSED traversals: rank r appends its contacts to the entries
+                                            [region_begin[r], region_begin[r+1]) of the list area (same values on every rank,
+                                            e.g. the previous step's per-rank counts + 5 %); all zero = equal split */
 } ibvh_peer_t;
 
 typedef struct ibvh_traverse_params {
@@ -128,11 +131,15 @@ typedef struct ibvh_traverse_params {
     const ibvh_peer_t* peer;  /* NULL, or (single / pair with BBox nodes, or rays; UNORDERED): fused traversal + all-gather —
                                  every rank traverses its query shard and the contacts of ALL ranks land in
                                  EVERY rank's list area (peer->buffers[r] + header_bytes) while the traversal
-                                 runs: output slots are reserved from one counter on rank 0 (system-scope
-                                 atomics over NVLink) and written with multimem.st through peer->multicast.
-                                 d_contacts is ignored, capacity is the list area's, *num_contacts returns the
-                                 gathered total (same on every rank). Collective; IBVH_ERR_UNSUPPORTED if the
-                                 combination cannot run fused (then: traverse locally + ibvh_allgather_pairs). */
+                                 runs: rank r reserves slots inside its own region (peer->region_begin) with local
+                                 atomics and writes them with multimem.st through peer->multicast; the ranks exchange
+                                 their counts at the end and the gaps between the regions are closed (entries beyond
+                                 the total move into them), so the list area holds *num_contacts contiguous pairs,
+                                 the same on every rank. d_contacts is ignored. ibvh_peer_last_counts gives the
+                                 per-rank counts (to size the next call's regions). IBVH_ERR_CAPACITY: some rank's
+                                 region was too small (nothing valid; *num_contacts = total need). Collective;
+                                 IBVH_ERR_UNSUPPORTED if the combination cannot run fused (then: traverse locally +
+                                 ibvh_allgather_pairs). */
 } ibvh_traverse_params_t;
 
 typedef struct ibvh_handle ibvh_handle_t;
@@ -197,6 +204,15 @@ IBVH_API int ibvh_aggregate(ibvh_handle_t* h, const void* d_leaves, int64_t n, c
 IBVH_API int ibvh_build(ibvh_handle_t* h, const void* d_volumes, void* d_leaves, int64_t n,
                const ibvh_types_t* types, void* d_nodes, int64_t built_level,
                int compute_extrema, const double* mins, const double* maxs, void* stream);
+
+/* Reference-SHAPED proxy of the same constructor (measurement aid, NOT the product path): launches what BVH(...) launches
+ * through KernelAbstractions / AcceleratedKernels on a GPU — wrap (build.jl:340), two mapreduce passes with a scalar
+ * read-back each (morton/utils.jl:24-44), a whole-struct encode pass (default.jl:66), a comparison merge sort that moves
+ * the 24-byte structs (build.jl:248-253) and one merge launch per tree level (build.jl:413,492). Same results, bit for
+ * bit. Stands in for the reference's CUDA.jl backend, which cannot run where there is no Julia; pair it with
+ * IBVH_TRAVERSE_REFERENCE_SHAPED. BSphere{Float32} / Int32 / UInt32 / BBox{Float32} only (else IBVH_ERR_UNSUPPORTED). */
+IBVH_API int ibvh_build_reference_shaped(ibvh_handle_t* h, const void* d_volumes, void* d_leaves, int64_t n,
+                                const ibvh_types_t* types, void* d_nodes, int64_t built_level, void* stream);
 
 /* ---- LVT traversals ------------------------------------------------------------------------ */
 /* Common output protocol (replaces the count -> accumulate -> allocate -> write sequence of
@@ -277,6 +293,9 @@ IBVH_API int ibvh_traverse_cancel(ibvh_handle_t* h);
  * Host outputs (the call synchronises the stream): *out_total = pairs in the gathered list,
  * *out_offset = first pair of this rank's shard inside it. IBVH_ERR_CAPACITY if the list area is too
  * small for out_total pairs (same verdict on every rank; nothing is written). */
+/* Per-rank contact / hit counts of the last FUSED traversal on this handle (world entries). */
+IBVH_API int ibvh_peer_last_counts(ibvh_handle_t* h, int64_t* counts, int32_t world);
+
 IBVH_API int ibvh_allgather_pairs(ibvh_handle_t* h, const ibvh_peer_t* peer, const void* d_shard, int64_t count,
                                   int32_t pair_bytes, int64_t* out_total, int64_t* out_offset, void* stream);
 

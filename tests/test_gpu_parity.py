@@ -1001,3 +1001,27 @@ def test_deferred_traversal_cancel_and_rays_guard(ib, O, dev):
     assert rc == ib.capi.ERR_ARGUMENT
     assert tr.num_contacts == ref.num_contacts
     assert lib.ibvh_traverse_cancel(bvh._handle) == ib.capi.OK              # nothing outstanding: no-op
+
+
+@pytest.mark.gpu
+def test_reference_shaped_proxy_build_is_bit_identical(ib, O, dev):
+    """The reference-shaped proxy (struct-moving merge sort, two mapreduce passes, one merge launch per level; the stand-in
+    for the reference's CUDA.jl backend in bench.py) must give the oracle's leaves and nodes bit for bit, ties included."""
+    from ibvh_b200 import synth
+    rng = np.random.default_rng(8)
+    for n in (1, 2, 3, 511, 512, 513, 1025, 5000, 100_003):
+        s = random_spheres(rng, n, spread=6.0 * max(1.0, (n / 200.0) ** (1 / 3)))
+        ol, on = oracle_build(O, s)
+        bvh = ib.BVH(s, ib.BBox(), device=dev, reference_shaped=True)
+        assert bvh.leaves.numpy().tobytes() == ol.tobytes(), n
+        assert bvh.nodes.numpy().tobytes() == on.tobytes(), n
+    # many ties (few distinct Morton codes): the merge sort must be stable like the product's radix sort
+    s = synth.random_spheres_np(60_000, seed=5)
+    s["x"] = np.round(s["x"] * 4) / 4
+    ol, on = oracle_build(O, s)
+    bvh = ib.BVH(s, ib.BBox(), device=dev, reference_shaped=True)
+    assert bvh.leaves.numpy().tobytes() == ol.tobytes() and bvh.nodes.numpy().tobytes() == on.tobytes()
+    want = O.traverse_single(ol, on, num_threads=4)
+    assert ib.traverse(bvh, reference_shaped=True).contacts.numpy().tobytes() == want.tobytes()
+    with pytest.raises(NotImplementedError):
+        ib.BVH(s, ib.BBox(), device=dev, reference_shaped=True, options=opts(ib, 8, 8))

@@ -259,13 +259,17 @@ def main():
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
+    # stdout carries exactly ONE line, the JSON: everything libraries write to file descriptor 1 meanwhile (the NCCL version
+    # banner, NCCL_DEBUG output the driver may have asked for) is sent to stderr; the JSON goes to the saved descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the single JSON line (a box-level NCCL_DEBUG=VERSION prints a banner)
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=dev)      # (NCCL_DEBUG is left as the caller set it; its output lands on stderr)
     warm = max(3, args.warmup)
     n = N_LEAVES
     ordered = args.ordered
@@ -509,6 +513,11 @@ def main():
         comp_done = [torch.cuda.Event() for _ in range(2)]
         out_done = [torch.cuda.Event() for _ in range(2)]
         bvh_prev = e2e_state["bvh"]
+        use_fused = world > 1 and fused and state["peer"] is not None
+        if use_fused and e2e_state.get("peers") is None:
+            # two symmetric buffers: step k's slice of the gathered list leaves for the host while step k+1 writes the other
+            e2e_state["peers"] = [state["peer"], ibdist.PeerGather(state["peer"].capacity_bytes // 8, 8, dev)]
+        copied = {"pairs": 0}
 
         def h2d(k):
             b = k % 2
@@ -532,17 +541,28 @@ def main():
             bvh = ib.BVH(d_in[b], ib.BBox(), cache=bvh_prev)
             if world == 1:
                 tr = ib.traverse(bvh, cache=caches[b], ordered=ordered)
+                lo, hi = 0, tr.num_contacts
+                src_t = tr.cache1.tensor
+                caches[b] = tr
+            elif use_fused:
+                # the traversal kernel itself writes every contact into every rank's list (NVLink multicast); each rank's host
+                # then receives ITS 1/N slice of the gathered list, so the hosts together receive the whole list once
+                tr = ib.traverse(bvh, ordered=False, query_range=(qb, qe - qb), peer=e2e_state["peers"][b])
+                tot = tr.num_contacts
+                lo, hi = tot * rank // world, tot * (rank + 1) // world
+                src_t = e2e_state["peers"][b].list_area()
             else:
                 tr = ib.traverse(bvh, cache=caches[b], ordered=ordered, query_range=(qb, qe - qb))
-            caches[b] = tr
+                lo, hi = 0, tr.num_contacts
+                src_t = tr.cache1.tensor
+                caches[b] = tr
             bvh_prev = bvh
             comp_done[b].record(main)
-            nb = tr.num_contacts * 8
             with torch.cuda.stream(s_out):
                 s_out.wait_event(comp_done[b])
-                outs[b][:nb].copy_(tr.cache1.tensor[:nb], non_blocking=True)
+                outs[b][:(hi - lo) * 8].copy_(src_t[lo * 8:hi * 8], non_blocking=True)
                 out_done[b].record(s_out)
-            last = tr.num_contacts
+            last = hi - lo
         s_out.synchronize(); s_in.synchronize(); main.synchronize()
         return last
 
@@ -834,7 +854,8 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,
             "secondary": rays, "workloads": workloads, "verify": verify,
         }
-        print(json.dumps(out), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

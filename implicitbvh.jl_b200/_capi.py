@@ -17,12 +17,12 @@ OK, ERR_ARGUMENT, ERR_DOMAIN, ERR_UNSUPPORTED, ERR_CUDA, ERR_CAPACITY, ERR_ALLOC
 MAX_PEERS = 16
 BSPHERE, BBOX = 0, 1
 TRAVERSE_ORDERED, TRAVERSE_UNORDERED, TRAVERSE_REFERENCE_SHAPED, TRAVERSE_COUNTS_VALID = 0, 1, 2, 4
-TRAVERSE_STATS, TRAVERSE_PACKET, TRAVERSE_WALK, TRAVERSE_DEFER = 8, 16, 32, 64
+TRAVERSE_STATS, TRAVERSE_PACKET, TRAVERSE_WALK, TRAVERSE_DEFER, TRAVERSE_POSITIONS = 8, 16, 32, 64, 128
 
 
 class Types(C.Structure):
     _fields_ = [("leaf_kind", C.c_int32), ("float_bytes", C.c_int32), ("index_bytes", C.c_int32),
-                ("morton_bytes", C.c_int32), ("node_kind", C.c_int32), ("reserved", C.c_int32)]
+                ("morton_bytes", C.c_int32), ("node_kind", C.c_int32), ("node_float_bytes", C.c_int32)]
 
 
 class Tree(C.Structure):

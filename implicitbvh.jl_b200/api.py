@@ -335,7 +335,8 @@ def isvirtual(tree: ImplicitTree, implicit_index: int) -> bool:
 # BVH (build.jl:155-271)
 # ---------------------------------------------------------------------------------------------
 def _types(leaf_vol: VolumeType, node: VolumeType, index: np.dtype, morton: np.dtype) -> capi.Types:
-    return capi.Types(leaf_vol.kind, leaf_vol.float_bytes, index.itemsize, morton.itemsize, node.kind, 0)
+    nfb = 0 if node.float_bytes == leaf_vol.float_bytes else node.float_bytes
+    return capi.Types(leaf_vol.kind, leaf_vol.float_bytes, index.itemsize, morton.itemsize, node.kind, nfb)
 
 
 class BVH:
@@ -376,8 +377,8 @@ class BVH:
                 raise ArgumentError(f"BoundingVolume index type {src.dtype['index']} does not match BVHOptions index_exemplar type {I}")
             if src.dtype["morton"] != M:
                 raise ArgumentError(f"BoundingVolume morton type {src.dtype['morton']} does not match BVHOptions morton type {M}")
-        if node_type.float_bytes != vol.float_bytes:
-            raise NotImplementedError("node float type must equal the leaf float type in this build")
+        if node_type.float_bytes != vol.float_bytes and not (vol.float_bytes == 8 and node_type.float_bytes == 4):
+            raise NotImplementedError("node float types built: the leaf float type, or Float32 nodes over Float64 leaves (the reference's default)")
         ldt = leaf_dtype(vol, I, M)
         self.types = _types(vol, node_type, I, M)
         assert ldt.itemsize == lib.ibvh_leaf_bytes(C.byref(self.types))
@@ -543,6 +544,7 @@ class _Pending:
             rc = capi.lib().ibvh_traverse_finish(handle, C.byref(total))
             if rc == capi.OK:
                 t._num_contacts = int(total.value)
+                _finish_stats(t, handle)
                 return
             if rc in (capi.ERR_AGAIN, capi.ERR_CAPACITY):
                 again = rerun()
@@ -554,6 +556,16 @@ class _Pending:
         return tr
 
 
+def _finish_stats(tr: "BVHTraversal", handle) -> "BVHTraversal":
+    """BVHTraversal.num_checks (traverse/traverse.jl:48,58): the reference's LVT leaves it at 0; here it carries the box-box +
+    leaf-leaf tests of the traversal when the schedule that ran counts them (the pyramid schedule always does)."""
+    st = (C.c_int64 * 4)()
+    capi.lib().ibvh_last_traversal_stats(handle, st)
+    if st[3] > 0:
+        tr.num_checks = int(st[0]) + int(st[1])
+    return tr
+
+
 def _fused_call(call, peer, handle, what: str) -> C.c_int64:
     """One fused traversal + all-gather (collective). The ranks' regions of the gathered list are sized from the previous
     call's per-rank counts; if a region turns out too small (IBVH_ERR_CAPACITY: the same verdict on every rank, with the
@@ -562,30 +574,74 @@ def _fused_call(call, peer, handle, what: str) -> C.c_int64:
     rc = call(peer.next_fused(), total)
     if rc == capi.ERR_CAPACITY:
         counts = peer.last_counts()
-        if not (peer.set_regions(counts) or peer.set_regions(counts, slack=0.01)):
+        if not (peer.set_regions(counts) or peer.set_regions(counts, slack=0.01) or peer.set_regions(counts, slack=0.0, pad=2)):
             _raise(rc, handle, f"{what}: the peer list area is too small for {total.value} pairs")
         rc = call(peer.next_fused(), total)
     if rc != capi.OK:
         _raise(rc, handle, f"{what} (gathered total {total.value} pairs)")
     counts = peer.last_counts()
-    if not (peer.set_regions(counts) or peer.set_regions(counts, slack=0.01)):
+    if not (peer.set_regions(counts) or peer.set_regions(counts, slack=0.01) or peer.set_regions(counts, slack=0.0, pad=2)):
         peer.set_regions(None)
     return total
 
 
-def _check_narrow(narrow):
-    if narrow is not None:
-        raise NotImplementedError("custom `narrow` closures cannot cross the C ABI (SURVEY.md §8f-3); only the default is supported")
+def _eval_narrow(narrow, *cols) -> np.ndarray:
+    """Evaluate a user `narrow` predicate over candidate contacts. `cols` are equally long numpy arrays (BoundingVolume
+    records; for rays also (k, 3) points / directions). The predicate is tried vectorised first (called once with the
+    whole arrays, must return k booleans) and element by element otherwise, like the reference calls it."""
+    k = len(cols[0])
+    if k == 0:
+        return np.zeros(0, bool)
+    try:
+        m = np.asarray(narrow(*cols))
+        if m.shape == (k,) and m.dtype == np.bool_:
+            return m
+    except Exception:
+        pass
+    return np.fromiter((bool(narrow(*(c[i] for c in cols))) for i in range(k)), bool, k)
+
+
+def _gather_records(arr: "DeviceArray", pos0: torch.Tensor) -> np.ndarray:
+    """arr[pos0] (0-based positions on the device) as a host numpy structured array."""
+    it = arr.dtype.itemsize
+    rows = arr.tensor.view(len(arr), it).index_select(0, pos0.to(torch.int64))
+    return rows.cpu().numpy().reshape(-1).view(arr.dtype)
+
+
+def _narrow_pairs(narrow, tr: "BVHTraversal", leaves1: "DeviceArray", leaves2: "DeviceArray", single: bool, I: np.dtype,
+                  nqueries: int, query_col: int, q_begin: int) -> "BVHTraversal":
+    """Post-filter of a traversal run with IBVH_TRAVERSE_POSITIONS: the reference evaluates `narrow(bv1, bv2)` only after a
+    positive leaf test (traverse_single.jl:170, traverse_pair.jl:206), so filtering the positive pairs with the same
+    predicate over leaves[position] gives the identical list, order included. Here the predicate is a
+    host Python callable, so the candidates travel to the host; a Julia caller would broadcast its closure on the device."""
+    device = leaves1.device
+    tI = torch.int32 if I.itemsize == 4 else torch.int64
+    pos = tr.contacts.tensor.view(tI).reshape(-1, 2)
+    b1 = _gather_records(leaves1, pos[:, 0] - 1)
+    b2 = _gather_records(leaves2, pos[:, 1] - 1)
+    keep = _eval_narrow(narrow, b1, b2)
+    i1, i2 = b1["index"][keep], b2["index"][keep]
+    out = np.zeros(int(keep.sum()), pair_dtype(I))
+    if single:
+        out["a"], out["b"] = np.minimum(i1, i2), np.maximum(i1, i2)
+    else:
+        out["a"], out["b"] = i1, i2
+    c1 = DeviceArray.from_numpy(out, device=device)
+    # cache2 = inclusive scan of the per-query counts that survive the predicate (the reference's thread_ncontacts)
+    q = (pos[:, query_col].to(torch.int64) - 1 - q_begin)[torch.from_numpy(keep).to(device)]
+    counts = torch.bincount(q, minlength=nqueries)[:nqueries].cumsum(0).to(tI)
+    c2 = DeviceArray(counts.view(torch.uint8).reshape(-1).contiguous(), I)
+    return BVHTraversal(tr.start_level1, tr.start_level2, tr.num_checks, len(out), c1, c2)
 
 
 def _run_two_phase(call, handle, device, I: np.dtype, nqueries: int, cache: Optional[BVHTraversal], ordered: bool,
-                   reference_shaped: bool, packet: bool = False, walk: bool = False):
+                   reference_shaped: bool, packet: bool = False, walk: bool = False, extra_flags: int = 0):
     """The reference's count -> accumulate -> allocate/grow -> write protocol (traverse_single.jl:23-78),
     with `cache1`/`cache2` reused and grown only when too small."""
     pdt = pair_dtype(I)
     flags = capi.TRAVERSE_ORDERED if ordered else capi.TRAVERSE_UNORDERED
     sched = (capi.TRAVERSE_REFERENCE_SHAPED if reference_shaped else 0) | (capi.TRAVERSE_PACKET if packet else 0) | \
-            (capi.TRAVERSE_WALK if walk else 0)
+            (capi.TRAVERSE_WALK if walk else 0) | extra_flags
     flags |= sched
     if cache is not None:
         if cache.cache2.dtype != I:
@@ -646,7 +702,9 @@ def traverse(bvh: BVH, bvh2=None, alg=None, *, start_level: Optional[int] = None
         alg, bvh2 = bvh2, None
     if alg is not None and not isinstance(alg, LVTTraversal):
         raise ArgumentError(f"Traversal algorithm not implemented: {alg}")
-    _check_narrow(narrow)
+    if narrow is not None and (defer or peer is not None):
+        raise ArgumentError("a custom `narrow` predicate is a post-filter on the host: not with defer=True or peer=...")
+    pos_flag = capi.TRAVERSE_POSITIONS if narrow is not None else 0
     lib = capi.lib()
     _resolve_outstanding(bvh.leaves.device.index)      # one deferred traversal per handle: a new one finishes the old one first
     qb, qc = (0, -1) if query_range is None else (int(query_range[0]), int(query_range[1]))
@@ -664,7 +722,8 @@ def traverse(bvh: BVH, bvh2=None, alg=None, *, start_level: Optional[int] = None
                 return int(total.value), cache.cache1, cache.cache2
             # anything else (e.g. capacity): the synchronous protocol below sorts it out
         if peer is None:
-            return _run_two_phase(call, handle, device, I, nq, cache, ordered, reference_shaped, packet, walk)
+            return _run_two_phase(call, handle, device, I, nq, None if narrow is not None else cache, ordered, reference_shaped, packet, walk,
+                                  extra_flags=pos_flag)
         if peer.pair_bytes != pair_dtype(I).itemsize or peer.device != device:
             raise ArgumentError("PeerGather pair size / device do not match the BVH")
         total = _fused_call(lambda pref, tot: call(capi.TRAVERSE_UNORDERED, None, None, 0, tot, pref), peer, handle, "fused traverse")
@@ -692,7 +751,10 @@ def traverse(bvh: BVH, bvh2=None, alg=None, *, start_level: Optional[int] = None
             return total.attach(BVHTraversal(sl, 0, 0, 0, c1, c2),
                                 lambda: traverse(bvh, start_level=sl, cache=BVHTraversal(sl, 0, 0, 0, c1, c2), ordered=False, query_range=query_range),
                                 bvhs=(bvh,), device_index=device.index)
-        return BVHTraversal(sl, 0, 0, total, c1, c2)
+        out = _finish_stats(BVHTraversal(sl, 0, 0, total, c1, c2), bvh._handle)
+        if narrow is not None:
+            out = _narrow_pairs(narrow, out, bvh.leaves, bvh.leaves, True, I, nq, 0, max(qb, 0))
+        return out
 
     # pair — traverse_pair.jl:1-116
     sl1 = default_start_level(bvh) if start_level1 is None else int(start_level1)
@@ -723,7 +785,10 @@ def traverse(bvh: BVH, bvh2=None, alg=None, *, start_level: Optional[int] = None
                             lambda: traverse(bvh, bvh2, start_level1=sl1, start_level2=sl2, cache=BVHTraversal(sl1, sl2, 0, 0, c1, c2),
                                              ordered=False, query_range=query_range),
                             bvhs=(bvh, bvh2), device_index=device.index)
-    return BVHTraversal(sl1, sl2, 0, total, c1, c2)
+    out = _finish_stats(BVHTraversal(sl1, sl2, 0, total, c1, c2), bvh._handle)
+    if narrow is not None:
+        out = _narrow_pairs(narrow, out, bvh.leaves, bvh2.leaves, False, I, nq, 1 if flip else 0, max(qb, 0))
+    return out
 
 
 def traverse_rays(bvh: BVH, points, directions, alg=None, *, start_level: int = 1, narrow=None,
@@ -736,8 +801,12 @@ def traverse_rays(bvh: BVH, points, directions, alg=None, *, start_level: int = 
     """
     if alg is not None and not isinstance(alg, LVTTraversal):
         raise ArgumentError(f"Raytracing algorithm not implemented: {alg}")
-    _check_narrow(narrow)
+    if narrow is not None and peer is not None:
+        raise ArgumentError("a custom `narrow` predicate is a post-filter on the host: not with peer=...")
     lib = capi.lib()
+    if bvh.types.node_float_bytes not in (0, bvh.types.float_bytes):
+        # isintersection(b::BBox{T}, p::...{T}, d::...{T}) where T (isintersection.jl:1-5): no method for mixed float types
+        raise ArgumentError("traverse_rays needs leaves and nodes of one float type (the reference has no mixed-type ray test)")
     T = {4: np.float32, 8: np.float64}[bvh.types.float_bytes]
     device = bvh.leaves.device
     _resolve_outstanding(device.index)                 # (the ray traversal shares the handle's read-back slots)
@@ -777,8 +846,22 @@ def traverse_rays(bvh: BVH, points, directions, alg=None, *, start_level: int = 
         total = _fused_call(lambda pref, tot: call(capi.TRAVERSE_UNORDERED, None, None, 0, tot, pref), peer, bvh._handle, "fused traverse_rays")
         c2 = cache.cache2 if cache is not None else DeviceArray.empty(0, I, device)
         return BVHTraversal(start_level, 0, 0, int(total.value), DeviceArray(peer.list_area(), pair_dtype(I)), c2)
-    total, c1, c2 = _run_two_phase(call, bvh._handle, device, I, nrays, cache, ordered, False)
-    return BVHTraversal(start_level, 0, 0, total, c1, c2)
+    total, c1, c2 = _run_two_phase(call, bvh._handle, device, I, nrays, None if narrow is not None else cache, ordered, False,
+                                   extra_flags=capi.TRAVERSE_POSITIONS if narrow is not None else 0)
+    out = BVHTraversal(start_level, 0, 0, total, c1, c2)
+    if narrow is not None:
+        # narrow(leaf, point, direction) after a positive ray / leaf test (raytrace/leaf_vs_tree/leaf_vs_tree.jl:194)
+        tI = torch.int32 if I.itemsize == 4 else torch.int64
+        pr = out.contacts.tensor.view(tI).reshape(-1, 2)
+        lv = _gather_records(bvh.leaves, pr[:, 0] - 1)
+        rid = (pr[:, 1].to(torch.int64) - 1 - int(id_base))
+        keep = _eval_narrow(narrow, lv, p.index_select(0, rid).cpu().numpy(), d.index_select(0, rid).cpu().numpy())
+        res = np.zeros(int(keep.sum()), pair_dtype(I))
+        res["a"], res["b"] = lv["index"][keep], pr[:, 1].cpu().numpy()[keep]
+        counts = torch.bincount(rid[torch.from_numpy(keep).to(device)], minlength=nrays)[:nrays].cumsum(0).to(tI)
+        out = BVHTraversal(start_level, 0, 0, len(res), DeviceArray.from_numpy(res, device=device),
+                           DeviceArray(counts.view(torch.uint8).reshape(-1).contiguous(), I))
+    return out
 
 
 # ---------------------------------------------------------------------------------------------

@@ -62,13 +62,25 @@ template <class F> int dispatch_leaf(const ibvh_types_t& t, F&& f) {
 }
 // node type for a leaf type: BBox nodes for everything; BSphere nodes only over BSphere leaves
 // (the reference has no BSphere(::BBox) conversion, merge.jl).
-template <class L, class F> int dispatch_node(const ibvh_types_t& t, F&& f) {
-    using T = typename L::value_type;
+template <class L, class T, class F> int dispatch_node_kind(const ibvh_types_t& t, F&& f) {
     if (t.node_kind == IBVH_BBOX) return f(Tag<BBox<T>>{});
     if (t.node_kind == IBVH_BSPHERE) {
         if constexpr (L::vol_t::kind == IBVH_BSPHERE) return f(Tag<BSphere<T>>{});
         else return IBVH_ERR_ARGUMENT;
     }
+    return IBVH_ERR_UNSUPPORTED;
+}
+// The node float type is the leaf float type unless node_float_bytes says otherwise; the one mixed combination built
+// is the reference's default call: Float64 leaves under Float32 nodes (README.md:38-46, build.jl:198-205).
+template <class L, class F> int dispatch_node(const ibvh_types_t& t, F&& f) {
+    using T = typename L::value_type;
+    const int nfb = t.node_float_bytes == 0 ? (int)sizeof(T) : t.node_float_bytes;
+    if (nfb == (int)sizeof(T)) return dispatch_node_kind<L, T>(t, f);
+#ifdef IBVH_ENABLE_F64
+    if constexpr (sizeof(T) == 8) {
+        if (nfb == 4) return dispatch_node_kind<L, float>(t, f);
+    }
+#endif
     return IBVH_ERR_UNSUPPORTED;
 }
 
@@ -77,6 +89,7 @@ bool types_ok(const ibvh_types_t* t) {
     if (t->leaf_kind != IBVH_BSPHERE && t->leaf_kind != IBVH_BBOX) return false;
     if (t->node_kind != IBVH_BSPHERE && t->node_kind != IBVH_BBOX) return false;
     if (t->float_bytes != 4 && t->float_bytes != 8) return false;
+    if (t->node_float_bytes != 0 && t->node_float_bytes != 4 && t->node_float_bytes != 8) return false;
     if (t->index_bytes != 4 && t->index_bytes != 8) return false;
     if (t->morton_bytes != 2 && t->morton_bytes != 4 && t->morton_bytes != 8) return false;
     return true;
@@ -511,7 +524,7 @@ int traverse_tiled(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, con
     if (ta.q_count <= 0) return IBVH_OK;
     GroupArgs a{};
     a.q_begin = ta.q_begin; a.q_count = ta.q_count; a.n_groups = (ta.q_count + G - 1) / G;
-    a.start_level = ta.start_level; a.group_level = bvh.ti.levels - kTileLogG; a.flip = ta.flip;
+    a.start_level = ta.start_level; a.group_level = bvh.ti.levels - kTileLogG; a.flip = ta.flip; a.positions = ta.positions;
     a.seg_cap = kTileSegCap; a.step_cap = kTileStepCap;
     a.capacity = d_contacts ? capacity : 0; a.total = d_total;
     a.dbg = nullptr;
@@ -623,8 +636,10 @@ inline bool make_pyr_plan(const TreeInfo& ti, int64_t built_level, int64_t q_beg
         if (tl < 1 || tl < built_level) break;
         PyrLevel& v = plan->lv[plan->n];
         v.k = k; v.tree_level = tl; v.ntg = ti.level_nreal[tl]; v.tnode0 = ti.level_start[tl];
-        v.qg_first = q_begin >> k; v.nqg = ((q_end - 1) >> k) - v.qg_first + 1; v.u_off = plan->u_total;
-        plan->u_total += v.nqg;
+        // (the query-pyramid levels carry 2^fan boxes of padding on both sides: the TMA refine kernel copies the aligned run of
+        // 2^fan children of a group even when the shard range cuts it)
+        v.qg_first = q_begin >> k; v.nqg = ((q_end - 1) >> k) - v.qg_first + 1; v.u_off = plan->u_total + (int64_t(1) << kPyrFan);
+        plan->u_total += v.nqg + (int64_t(2) << kPyrFan);
         v.t_off = plan->t_total;
         plan->t_total += (v.ntg + 15) & ~int64_t(7);               // whole groups of 8 + slack, 64-byte aligned starts
         plan->n += 1;
@@ -707,6 +722,7 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
     const bool stash_mode = !unordered && !count_only && capacity > 0 && !((flags & IBVH_TRAVERSE_COUNTS_VALID) && d_counts);
     const int nl = plan.n;
     const int grid = h->sm_count * h->cfg.pyr_grid;
+    const int pflip = (ta.flip ? 1 : 0) | (ta.positions ? 2 : 0);      // bit 1: report leaf positions (IBVH_TRAVERSE_POSITIONS)
     // The 16-byte hit stash of the one-pass ordered protocol is sized from what the traversals on this handle actually
     // produced (last total + 25 %, or 6 hits per query before the first one), never from the caller's `capacity`: a
     // generously pre-sized cache1 must not pull twice its size of scratch along. A stash that turns out too small costs
@@ -719,15 +735,18 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
 
     // ordered protocol scratch: counts (if the caller gave none), cursors, scan sums
     const int64_t qblocks = (ta.q_count + kScanTile - 1) / kScanTile;
+    // (a segment longer than kFixupInsertion needs that many contacts: at most capacity / kFixupInsertion of them exist)
+    const uint32_t long_cap = (uint32_t)std::min<int64_t>(ta.q_count, (capacity > 0 ? capacity : 0) / kFixupInsertion + 1);
     size_t need = ibvh_handle::padded((size_t)qblocks * 8) + ibvh_handle::padded((size_t)ta.q_count * 4) +
-                  (d_counts ? 0 : ibvh_handle::padded((size_t)ta.q_count * sizeof(I))) + 4096;
+                  (d_counts ? 0 : ibvh_handle::padded((size_t)ta.q_count * sizeof(I))) + ibvh_handle::padded((size_t)long_cap * 8) + 4096;
     int rc = h->reserve(need);
     if (rc != IBVH_OK) return rc;
     h->reset();
     long long* qsums = h->alloc<long long>(qblocks);
     unsigned int* cursors = h->alloc<unsigned int>(ta.q_count);
     I* counts = d_counts ? (I*)d_counts : h->alloc<I>(ta.q_count);
-    if (!qsums || !cursors || !counts) { h->set_error("workspace carve failed"); return IBVH_ERR_ALLOC; }
+    uint32_t* long_lists = h->alloc<uint32_t>((size_t)long_cap * 2);
+    if (!qsums || !cursors || !counts || !long_lists) { h->set_error("workspace carve failed"); return IBVH_ERR_ALLOC; }
 
     double factor = h->pyr_factor > 0 ? h->pyr_factor : (KIND == kSingle ? 40.0 : 80.0);
     unsigned long long need_cap[kPyrMaxLevels] = {0};
@@ -806,7 +825,10 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
         // 3. refine down to the 4-leaf groups
         for (int l = nl - 1; l >= 1; --l) {
             { ProfScope _ps(h, st, "pyr_refine_kernel");
-            pyr_refine_kernel<KIND, T><<<grid, kPyrWarps * 32, 0, st>>>(U + plan.lv[l - 1].u_off, NT + plan.lv[l - 1].t_off, (uint32_t)plan.lv[l - 1].qg_first, (uint32_t)plan.lv[l - 1].nqg, (uint32_t)plan.lv[l - 1].ntg, lists[l], lists[l - 1], d_tick + l);
+            if (h->cfg.pyr_tma)
+                pyr_refine_tma_kernel<KIND, T><<<grid, kPyrWarps * 32, 0, st>>>(U + plan.lv[l - 1].u_off, NT + plan.lv[l - 1].t_off, (uint32_t)plan.lv[l - 1].qg_first, (uint32_t)plan.lv[l - 1].nqg, (uint32_t)plan.lv[l - 1].ntg, lists[l], lists[l - 1], d_tick + l);
+            else
+                pyr_refine_kernel<KIND, T><<<grid, kPyrWarps * 32, 0, st>>>(U + plan.lv[l - 1].u_off, NT + plan.lv[l - 1].t_off, (uint32_t)plan.lv[l - 1].qg_first, (uint32_t)plan.lv[l - 1].nqg, (uint32_t)plan.lv[l - 1].ntg, lists[l], lists[l - 1], d_tick + l);
             }
             IBVH_LAUNCH_CHECK(h, "pyr_refine_kernel");
         }
@@ -843,7 +865,7 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
                 if (rcw != IBVH_OK) return rcw;
             }
             { ProfScope _ps(h, st, "pyr_leaf_tile_kernel");
-            pyr_leaf_tile_kernel<KIND, kAtomic, 0, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, capacity, out_total, (I*)nullptr, nullptr, out_ptr, 1, d_tick + 16 + (tile_launch++), PQ, PT);
+            pyr_leaf_tile_kernel<KIND, kAtomic, 0, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], pflip, capacity, out_total, (I*)nullptr, nullptr, out_ptr, 1, d_tick + 16 + (tile_launch++), PQ, PT);
             }
             IBVH_LAUNCH_CHECK(h, "pyr_leaf_tile_kernel");
             return fused_finish();
@@ -852,20 +874,20 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
         if (unordered || count_only) {
             if (unordered) {
                 { ProfScope _ps(h, st, "pyr_leaf_tile_kernel");
-                pyr_leaf_tile_kernel<KIND, kAtomic, 0, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, capacity, out_total, (I*)nullptr, nullptr, out_ptr, fused ? 1 : 0, d_tick + 16 + (tile_launch++), PQ, PT);
+                pyr_leaf_tile_kernel<KIND, kAtomic, 0, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], pflip, capacity, out_total, (I*)nullptr, nullptr, out_ptr, fused ? 1 : 0, d_tick + 16 + (tile_launch++), PQ, PT);
                 }
             } else if (d_counts) {
                 // count-only call of the ordered protocol: per-query counts + scan (cache2), total from the scan
                 IBVH_CUDA_TRY(h, cudaMemsetAsync(counts, 0, (size_t)ta.q_count * sizeof(I), st));
                 { ProfScope _ps(h, st, "pyr_leaf_tile_kernel");
-                pyr_leaf_tile_kernel<KIND, kCount, 1, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, 0, d_total, counts, nullptr, (IndexPair<I>*)nullptr, 0, d_tick + 16 + (tile_launch++), PQ, PT);
+                pyr_leaf_tile_kernel<KIND, kCount, 1, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], pflip, 0, d_total, counts, nullptr, (IndexPair<I>*)nullptr, 0, d_tick + 16 + (tile_launch++), PQ, PT);
                 }
                 IBVH_LAUNCH_CHECK(h, "pyr_leaf_tile_kernel");
                 rc = scan_counts<I>(h, counts, ta.q_count, qsums, d_total, st);
                 if (rc != IBVH_OK) return rc;
             } else {
                 { ProfScope _ps(h, st, "pyr_leaf_tile_kernel");
-                pyr_leaf_tile_kernel<KIND, kCount, 0, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, 0, d_total, (I*)nullptr, nullptr, (IndexPair<I>*)nullptr, 0, d_tick + 16 + (tile_launch++), PQ, PT);
+                pyr_leaf_tile_kernel<KIND, kCount, 0, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], pflip, 0, d_total, (I*)nullptr, nullptr, (IndexPair<I>*)nullptr, 0, d_tick + 16 + (tile_launch++), PQ, PT);
                 }
             }
             IBVH_LAUNCH_CHECK(h, "pyr_leaf_tile_kernel");
@@ -873,9 +895,9 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
             IBVH_CUDA_TRY(h, cudaMemsetAsync(counts, 0, (size_t)ta.q_count * sizeof(I), st));
             { ProfScope _ps(h, st, "pyr_leaf_tile_kernel");
             if (stash_mode)
-                pyr_leaf_tile_kernel<KIND, kAtomic, 3, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, stash_cap, d_total, counts, nullptr, (IndexPair<I>*)stash, 0, d_tick + 16 + (tile_launch++), PQ, PT);
+                pyr_leaf_tile_kernel<KIND, kAtomic, 3, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], pflip, stash_cap, d_total, counts, nullptr, (IndexPair<I>*)stash, 0, d_tick + 16 + (tile_launch++), PQ, PT);
             else
-                pyr_leaf_tile_kernel<KIND, kCount, 1, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, 0, d_total, counts, nullptr, (IndexPair<I>*)nullptr, 0, d_tick + 16 + (tile_launch++), PQ, PT);
+                pyr_leaf_tile_kernel<KIND, kCount, 1, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], pflip, 0, d_total, counts, nullptr, (IndexPair<I>*)nullptr, 0, d_tick + 16 + (tile_launch++), PQ, PT);
             }
             IBVH_LAUNCH_CHECK(h, "pyr_leaf_tile_kernel");
             rc = scan_counts<I>(h, counts, ta.q_count, qsums, d_total, st);
@@ -945,14 +967,23 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
             IBVH_LAUNCH_CHECK(h, "pyr_scatter_kernel");
         } else {
             { ProfScope _ps(h, st, "pyr_leaf_tile_kernel");
-            pyr_leaf_tile_kernel<KIND, kWrite, 2, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], ta.flip, capacity, d_total, counts, cursors, (IndexPair<I>*)d_contacts, 0, d_tick + 16 + (tile_launch++), PQ, PT);
+            pyr_leaf_tile_kernel<KIND, kWrite, 2, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], pflip, capacity, d_total, counts, cursors, (IndexPair<I>*)d_contacts, 0, d_tick + 16 + (tile_launch++), PQ, PT);
             }
             IBVH_LAUNCH_CHECK(h, "pyr_leaf_tile_kernel");
         }
+        // per-query sort of the hits by target position; segments longer than kFixupInsertion are queued and sorted
+        // cooperatively (one warp / one block each) by the two launches that follow
+        uint32_t* long_counts = (uint32_t*)(h->d_small + kSmallFixup);
+        IBVH_CUDA_TRY(h, cudaMemsetAsync(long_counts, 0, 8, st));
         { ProfScope _ps(h, st, "pyr_fixup_kernel");
-        pyr_fixup_kernel<KIND, LQ, LT, I><<<(unsigned)((ta.q_count + 255) / 256), 256, 0, st>>>(qleaves, bvh.leaves, q_begin, ta.q_count, ta.flip, counts, (IndexPair<I>*)d_contacts);
+        pyr_fixup_kernel<KIND, LQ, LT, I><<<(unsigned)((ta.q_count + 255) / 256), 256, 0, st>>>(qleaves, bvh.leaves, q_begin, ta.q_count, pflip, counts, (IndexPair<I>*)d_contacts, long_lists, long_counts, long_cap);
         }
         IBVH_LAUNCH_CHECK(h, "pyr_fixup_kernel");
+        { ProfScope _ps(h, st, "pyr_fixup_long_kernel");
+        pyr_fixup_long_kernel<KIND, true, LQ, I><<<h->sm_count * 2, 256, 0, st>>>(qleaves, q_begin, pflip, counts, (IndexPair<I>*)d_contacts, long_lists, long_counts, long_cap);
+        pyr_fixup_long_kernel<KIND, false, LQ, I><<<h->sm_count * 2, 256, 0, st>>>(qleaves, q_begin, pflip, counts, (IndexPair<I>*)d_contacts, long_lists + long_cap, long_counts + 1, long_cap);
+        }
+        IBVH_LAUNCH_CHECK(h, "pyr_fixup_long_kernel");
         return IBVH_OK;
     }
     h->set_error("pyramid pair lists kept overflowing");
@@ -1377,7 +1408,7 @@ int ibvh_build_reference_shaped(ibvh_handle_t* h, const void* d_volumes, void* d
     if (n < 1) return IBVH_ERR_DOMAIN;
     if (!d_volumes || !d_leaves) return IBVH_ERR_ARGUMENT;
     if (!(types->leaf_kind == IBVH_BSPHERE && types->node_kind == IBVH_BBOX && types->float_bytes == 4 && types->index_bytes == 4 &&
-          types->morton_bytes == 4 && (types->reserved == 0 || types->reserved == 4))) {
+          types->morton_bytes == 4 && (types->node_float_bytes == 0 || types->node_float_bytes == 4))) {
         h->set_error("the reference-shaped proxy build exists for BSphere{Float32} / Int32 / UInt32 / BBox{Float32} only");
         return IBVH_ERR_UNSUPPORTED;
     }
@@ -1469,6 +1500,7 @@ int ibvh_traverse_single(ibvh_handle_t* h, const ibvh_bvh_t* bvh, const ibvh_tra
                          int64_t capacity, int64_t* num_contacts, void* stream) {
     if (!h || !p || !num_contacts) return IBVH_ERR_ARGUMENT;
     if (h->deferred.active) { h->set_error("a deferred traversal is outstanding on this handle: call ibvh_traverse_finish (or ibvh_traverse_cancel) first"); return IBVH_ERR_ARGUMENT; }
+    for (int k = 0; k < 4; ++k) h->last_stats[k] = 0;
     ibvh_tree_t tree;
     int rc = check_bvh(bvh, &tree);
     if (rc != IBVH_OK) return rc;
@@ -1487,6 +1519,7 @@ int ibvh_traverse_single(ibvh_handle_t* h, const ibvh_bvh_t* bvh, const ibvh_tra
             a.start_level = (int32_t)p->start_level;
             a.flip = 0;
             a.peer = p->peer;
+            a.positions = (p->flags & IBVH_TRAVERSE_POSITIONS) ? 1 : 0;
             return traverse_leaf_queries<kSingle, L, L, N, I>(h, d.leaves, bvh->n, d, bvh->built_level, a, p->flags, d_counts, d_contacts, capacity, num_contacts, st);
         });
     });
@@ -1498,7 +1531,8 @@ int ibvh_traverse_single(ibvh_handle_t* h, const ibvh_bvh_t* bvh, const ibvh_tra
 int ibvh_traverse_pair(ibvh_handle_t* h, const ibvh_bvh_t* queries, const ibvh_bvh_t* target, const ibvh_traverse_params_t* p,
                        void* d_counts, void* d_contacts, int64_t capacity, int64_t* num_contacts, void* stream) {
     if (!h || !p || !num_contacts || !queries || !target) return IBVH_ERR_ARGUMENT;
-    if (h->deferred.active) { h->set_error("a deferred traversal is outstanding on this handle: call ibvh_traverse_finish first"); return IBVH_ERR_ARGUMENT; }
+    if (h->deferred.active) { h->set_error("a deferred traversal is outstanding on this handle: call ibvh_traverse_finish (or ibvh_traverse_cancel) first"); return IBVH_ERR_ARGUMENT; }
+    for (int k = 0; k < 4; ++k) h->last_stats[k] = 0;
     ibvh_tree_t tq, tt;
     if (!types_ok(&queries->types) || queries->n < 1 || !queries->d_leaves) return IBVH_ERR_ARGUMENT;
     int rc = make_tree(queries->n, &tq);
@@ -1509,7 +1543,7 @@ int ibvh_traverse_pair(ibvh_handle_t* h, const ibvh_bvh_t* queries, const ibvh_b
     // both trees must share leaf / index / node types (traverse_pair.jl:50-52)
     const ibvh_types_t &a1 = queries->types, &a2 = target->types;
     if (a1.leaf_kind != a2.leaf_kind || a1.float_bytes != a2.float_bytes || a1.index_bytes != a2.index_bytes ||
-        a1.morton_bytes != a2.morton_bytes || a1.node_kind != a2.node_kind) return IBVH_ERR_ARGUMENT;
+        a1.morton_bytes != a2.morton_bytes || a1.node_kind != a2.node_kind || a1.node_float_bytes != a2.node_float_bytes) return IBVH_ERR_ARGUMENT;
     if (!(target->built_level <= p->start_level && p->start_level <= tt.levels)) return IBVH_ERR_ARGUMENT;   // traverse_pair.jl:11-12
     *num_contacts = 0;
     DeviceGuard g(h->device);
@@ -1524,6 +1558,7 @@ int ibvh_traverse_pair(ibvh_handle_t* h, const ibvh_bvh_t* queries, const ibvh_b
             a.start_level = (int32_t)p->start_level;
             a.flip = p->flip ? 1 : 0;
             a.peer = p->peer;
+            a.positions = (p->flags & IBVH_TRAVERSE_POSITIONS) ? 1 : 0;
             return traverse_leaf_queries<kPair, L, L, N, I>(h, (const L*)queries->d_leaves, queries->n, d, target->built_level, a, p->flags, d_counts, d_contacts, capacity, num_contacts, st);
         });
     });
@@ -1537,6 +1572,7 @@ int ibvh_traverse_rays(ibvh_handle_t* h, const ibvh_bvh_t* bvh, const void* d_po
     if (!h || !p || !num_contacts || nrays < 0) return IBVH_ERR_ARGUMENT;
     // (the ray traversal's read-back uses the same pinned / counter slots as an outstanding deferred traversal)
     if (h->deferred.active) { h->set_error("a deferred traversal is outstanding on this handle: call ibvh_traverse_finish (or ibvh_traverse_cancel) first"); return IBVH_ERR_ARGUMENT; }
+    for (int k = 0; k < 4; ++k) h->last_stats[k] = 0;
     ibvh_tree_t tree;
     int rc = check_bvh(bvh, &tree);
     if (rc != IBVH_OK) return rc;
@@ -1548,7 +1584,10 @@ int ibvh_traverse_rays(ibvh_handle_t* h, const ibvh_bvh_t* bvh, const void* d_po
     cudaStream_t st = (cudaStream_t)stream;
     return dispatch_leaf(bvh->types, [&](auto tag) -> int {
         using L = typename decltype(tag)::type; using I = typename L::idx_t; using T = typename L::value_type;
-        return dispatch_node<L>(bvh->types, [&](auto ntag) -> int {
+        // the reference's ray tests take the volume and the ray in ONE float type (isintersection.jl:1-5, 36-40): a tree whose
+        // node float type differs from its leaves' has no ray traversal there either (MethodError) -> ArgumentError here
+        if (bvh->types.node_float_bytes != 0 && bvh->types.node_float_bytes != bvh->types.float_bytes) return (int)IBVH_ERR_ARGUMENT;
+        return dispatch_node_kind<L, T>(bvh->types, [&](auto ntag) -> int {
             using N = typename decltype(ntag)::type;
             DBvh<L, N> d{(const L*)bvh->d_leaves, (const N*)bvh->d_nodes, make_tree_info(tree)};
             TraverseArgs a{};
@@ -1557,6 +1596,7 @@ int ibvh_traverse_rays(ibvh_handle_t* h, const ibvh_bvh_t* bvh, const void* d_po
             a.flip = 0;
             a.id_base = p->id_base;
             a.peer = p->peer;
+            a.positions = (p->flags & IBVH_TRAVERSE_POSITIONS) ? 1 : 0;
             return traverse_impl<kRays, false, L, L, N, I>(h, (const L*)nullptr, (const T*)d_points, (const T*)d_directions, d, a, p->flags,
                                                            d_counts, d_contacts, capacity, num_contacts, st);
         });

@@ -209,17 +209,77 @@ template <class T> IBVH_HD BBox<T> box_from_triangle(const T* a, const T* b, con
     return o;
 }
 
-// NodeType(leaf.volume) / NodeType(l.volume, r.volume) — build.jl:438-453
+// NodeType(leaf.volume) / NodeType(l.volume, r.volume) — build.jl:438-453.
+// The node float type TN may differ from the leaf float type TL (the reference's default call builds BBox{Float32} nodes
+// over Float64 leaves, README.md:38-46): the converting constructors (merge.jl:47-81) do their arithmetic in the LEAF
+// type and convert the resulting tuples to TN (round to nearest), which is what the casts below restate.
+template <class TN, class TL> IBVH_HD BBox<TN> to_box_as(const BSphere<TL>& a) {
+    BBox<TN> o;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { o.lo[k] = (TN)(a.x[k] - a.r); o.up[k] = (TN)(a.x[k] + a.r); }
+    return o;
+}
+template <class TN, class TL> IBVH_HD BBox<TN> to_box_as(const BBox<TL>& a) {
+    BBox<TN> o;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { o.lo[k] = (TN)a.lo[k]; o.up[k] = (TN)a.up[k]; }
+    return o;
+}
+template <class TN, class TL> IBVH_HD BBox<TN> merge_to_box_as(const BSphere<TL>& a, const BSphere<TL>& b) {
+    TL length = ibvh_sqrt(dist3sq(a.x, b.x));
+    if (length + a.r <= b.r) return to_box_as<TN>(b);
+    if (length + b.r <= a.r) return to_box_as<TN>(a);
+    BBox<TN> o;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        o.lo[k] = (TN)minimum2(a.x[k] - a.r, b.x[k] - b.r);
+        o.up[k] = (TN)maximum2(a.x[k] + a.r, b.x[k] + b.r);
+    }
+    return o;
+}
+template <class TN, class TL> IBVH_HD BBox<TN> merge_box_as(const BBox<TL>& a, const BBox<TL>& b) {
+    BBox<TN> o;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { o.lo[k] = (TN)minimum2(a.lo[k], b.lo[k]); o.up[k] = (TN)maximum2(a.up[k], b.up[k]); }
+    return o;
+}
+template <class TN, class TL> IBVH_HD BSphere<TN> to_sphere_as(const BSphere<TL>& a) {
+    BSphere<TN> o;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) o.x[k] = (TN)a.x[k];
+    o.r = (TN)a.r;
+    return o;
+}
+// BSphere{TN}(a::BSphere{TL}, b::BSphere{TL}): the literals are of type TN, the operands of type TL — Julia promotes, so
+// the arithmetic runs in the wider of the two (only TL = double, TN = float is instantiated: the wider type is TL)
+template <class TN, class TL> IBVH_HD BSphere<TN> merge_sphere_as(const BSphere<TL>& a, const BSphere<TL>& b) {
+    TL length = ibvh_sqrt(dist3sq(a.x, b.x));
+    if (length + a.r <= b.r) return to_sphere_as<TN>(b);
+    if (length + b.r <= a.r) return to_sphere_as<TN>(a);
+    TL frac = TL(0.5) * ((b.r - a.r) / length + TL(1));
+    BSphere<TN> o;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) o.x[k] = (TN)(a.x[k] + frac * (b.x[k] - a.x[k]));
+    o.r = (TN)(TL(0.5) * ((length + a.r) + b.r));
+    return o;
+}
 template <class N> struct NodeOps;
 template <class T> struct NodeOps<BBox<T>> {
     static IBVH_HD BBox<T> convert(const BBox<T>& v) { return v; }
     static IBVH_HD BBox<T> convert(const BSphere<T>& v) { return to_box(v); }
     static IBVH_HD BBox<T> merge_leaves(const BBox<T>& a, const BBox<T>& b) { return merge(a, b); }
     static IBVH_HD BBox<T> merge_leaves(const BSphere<T>& a, const BSphere<T>& b) { return merge_to_box(a, b); }
+    // leaf float type != node float type
+    template <class TL> static IBVH_HD BBox<T> convert(const BBox<TL>& v) { return to_box_as<T>(v); }
+    template <class TL> static IBVH_HD BBox<T> convert(const BSphere<TL>& v) { return to_box_as<T>(v); }
+    template <class TL> static IBVH_HD BBox<T> merge_leaves(const BBox<TL>& a, const BBox<TL>& b) { return merge_box_as<T>(a, b); }
+    template <class TL> static IBVH_HD BBox<T> merge_leaves(const BSphere<TL>& a, const BSphere<TL>& b) { return merge_to_box_as<T>(a, b); }
 };
 template <class T> struct NodeOps<BSphere<T>> {
     static IBVH_HD BSphere<T> convert(const BSphere<T>& v) { return v; }
     static IBVH_HD BSphere<T> merge_leaves(const BSphere<T>& a, const BSphere<T>& b) { return merge(a, b); }
+    template <class TL> static IBVH_HD BSphere<T> convert(const BSphere<TL>& v) { return to_sphere_as<T>(v); }
+    template <class TL> static IBVH_HD BSphere<T> merge_leaves(const BSphere<TL>& a, const BSphere<TL>& b) { return merge_sphere_as<T>(a, b); }
 };
 
 // ---- iscontact.jl:2-28 -----------------------------------------------------------------------------

@@ -23,6 +23,7 @@ struct ibvh_handle {
         bool force_wide_lookback = false;     // IBVH_SORT_WIDE_LOOKBACK: 64-bit look-back words at any size (tests the n >= 2^30 path)
         bool no_sidecar = false;              // IBVH_NO_SIDECAR: the build does not keep the traversal's packed records
         int pyr_grid = 20;                    // IBVH_PYR_GRID: CTAs per SM of the refine / tile kernels
+        bool pyr_tma = false;                 // IBVH_PYR_TMA=1: refine kernel with TMA bulk copies + mbarrier instead of LDG -> STS (measured slower: see traverse_pyramid.cuh)
         int fused_flush = -1;                 // IBVH_FUSED_FLUSH: buffered contacts per output reservation in fused mode
         void parse() {
             auto on = [](const char* k) { const char* v = getenv(k); return v != nullptr && v[0] != '\0' && !(v[0] == '0' && v[1] == '\0'); };
@@ -33,6 +34,7 @@ struct ibvh_handle {
             peer_no_multicast = on("IBVH_PEER_NO_MULTICAST");
             force_wide_lookback = on("IBVH_SORT_WIDE_LOOKBACK");
             no_sidecar = on("IBVH_NO_SIDECAR");
+            pyr_tma = on("IBVH_PYR_TMA");
             if (const char* v = getenv("IBVH_PYR_GRID")) { int g = atoi(v); if (g > 0) pyr_grid = g; }
             if (const char* v = getenv("IBVH_FUSED_FLUSH")) fused_flush = atoi(v);
         }
@@ -132,6 +134,7 @@ constexpr size_t kSmallTotal = 64;        // u64 contact total
 constexpr size_t kSmallStats = 128;       // 3 x u64
 constexpr size_t kSmallTickets = 256;     // 16 x u32 tile tickets (one per radix pass)
 constexpr size_t kSmallBoundsF = 512;     // 6 floats/doubles: padded bounds actually used
+constexpr size_t kSmallFixup = 960;       // 2 x u32: lengths of the long-segment lists of the ordered fix-up
 
 // RAII scope that brackets one kernel launch with events when profiling is enabled.
 struct ProfScope {

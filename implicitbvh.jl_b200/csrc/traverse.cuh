@@ -47,6 +47,7 @@ struct TraverseArgs {
     const uint32_t* qmap_count;
     int32_t qmap_group;
     const ibvh_peer_t* peer;     // fused traversal + all-gather over peer memory (pyramid schedule, unordered), else nullptr
+    int32_t positions;           // IBVH_TRAVERSE_POSITIONS: report 1-based leaf POSITIONS in the sorted arrays instead of .index
 };
 
 // 8-byte vectorised struct loads (volumes are 8-byte aligned by layout; see common.cuh)
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(128) lvt_thread_kernel(const LQ* __restrict__ 
     } else {
         LQ leaf = load_struct(qleaves + q);
         ql.vol = leaf.volume;
-        ql.index = leaf.index;
+        ql.index = a.positions ? (decltype(leaf.index))(q + 1) : leaf.index;
         ql.bvn = NodeOps<N>::convert(leaf.volume);
     }
 
@@ -159,6 +160,7 @@ __global__ void __launch_bounds__(128) lvt_thread_kernel(const LQ* __restrict__ 
                 if (level == levels) {
                     if constexpr (STATS) st_leaf += 1;
                     LT leaf = load_struct(bvh.leaves + (inode - (1u << (levels - 1))));
+                    if (a.positions) leaf.index = (decltype(leaf.index))(inode - (1u << (levels - 1)) + 1u);
                     if constexpr (KIND == kRays) {
                         if (isintersection(leaf.volume, qr.p, qr.d)) em.emit((I)leaf.index, (I)(a.id_base + q + 1));
                     } else {
@@ -249,7 +251,7 @@ __global__ void __launch_bounds__(128) rays_kernel(const typename LT::value_type
         uint2* dp = reinterpret_cast<uint2*>(&v);
 #pragma unroll
         for (int k = 0; k < (int)(sizeof(V) / 8); ++k) dp[k] = __ldg(sp + k);
-        if (isintersection(v, p, d)) em.emit((I)lp->index, ray_id);
+        if (isintersection(v, p, d)) em.emit(a.positions ? (I)(inode - leaf0 + 1u) : (I)lp->index, ray_id);
     };
 
     const uint32_t inode_start = 1u << (a.start_level - 1);
@@ -349,8 +351,9 @@ __global__ void __launch_bounds__(128) rays_persistent_kernel(const typename LT:
 #pragma unroll
         for (int k = 0; k < (int)(sizeof(V) / 8); ++k) dp[k] = __ldg(sp + k);
         if (isintersection(v, p, d)) {
-            if constexpr (MODE == kAtomic) s_hit[w][atomicAdd(&s_nhit[w], 1u)] = IndexPair<I>{(I)lp->index, ray_id};
-            else em.emit((I)lp->index, ray_id);
+            const I li = a.positions ? (I)(node - leaf0 + 1u) : (I)lp->index;
+            if constexpr (MODE == kAtomic) s_hit[w][atomicAdd(&s_nhit[w], 1u)] = IndexPair<I>{li, ray_id};
+            else em.emit(li, ray_id);
         }
     };
     auto flush_hits = [&](bool all) {
@@ -487,7 +490,7 @@ __global__ void __launch_bounds__(kPacketWarps * 32) lvt_packet_kernel(const LQ*
     if (valid) {
         LQ leaf = load_struct(qleaves + q);
         ql.vol = leaf.volume;
-        ql.index = leaf.index;
+        ql.index = a.positions ? (decltype(leaf.index))(q + 1) : leaf.index;
         ql.bvn = NodeOps<N>::convert(leaf.volume);
     }
     int64_t pos = 0;                                       // kCount: count, kWrite: next slot
@@ -517,6 +520,7 @@ __global__ void __launch_bounds__(kPacketWarps * 32) lvt_packet_kernel(const LQ*
                 if (__any_sync(0xffffffffu, act)) {
                     if constexpr (STATS) { st_leaf += act ? 1 : 0; st_loads += 1; }
                     LT leaf = load_struct(bvh.leaves + (inode - (1u << (levels - 1))));
+                    if (a.positions) leaf.index = (decltype(leaf.index))(inode - (1u << (levels - 1)) + 1u);
                     bool hit = act && iscontact(ql.vol, leaf.volume);
                     I ea, eb;
                     if constexpr (KIND == kSingle) {

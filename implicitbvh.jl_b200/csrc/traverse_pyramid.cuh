@@ -115,6 +115,47 @@ template <class R> IBVH_D void store16(R* p, const R& v) {
     for (int k = 0; k < (int)(sizeof(R) / 16); ++k) d[k] = s[k];
 }
 
+// ---- TMA bulk copies + mbarrier (sm_90+ PTX; SASS: UBLKCP / SYNCS) -----------------------------------------------
+// One lane arms the warp's mbarrier with the bytes it expects (arrive.expect_tx) and issues
+// cp.async.bulk.shared::cluster.global: the copy engine moves whole 16-byte-aligned runs from global to shared memory
+// and completes the transaction count on the barrier; the consumers wait on the barrier's phase parity. No registers,
+// no LDG -> STS round trip through the LSU data pipe (which ncu named as the limiter of the refine kernel: 93 %).
+// MEASURED (B200, 10 M leaves, gpurun_out/r2g -> profiles/r2_tma_ab.txt), same results bit for bit:
+//   refine: LDG -> STS 1.009 ms, TMA (192 + 256-byte runs, 8 copies per warp step)      1.205 ms
+//   tiles : cp.async   1.302 ms, TMA (64 + 64-byte runs, 32 copies per warp step)       2.717 ms
+// The runs this algorithm needs are a few hundred bytes at scattered addresses: at that size a bulk copy costs more
+// in the copy engine's per-request overhead than the LSU round trip it saves, so both TMA forms are kept as OPT-IN
+// variants (refine: IBVH_PYR_TMA=1 in the environment at ibvh_create; tiles: compile with -DIBVH_PYR_TMA=1) and the
+// LDG / cp.async forms stay the default. Large contiguous tiles (where TMA wins) do not occur on this path.
+#ifndef IBVH_PYR_TMA
+#define IBVH_PYR_TMA 0
+#endif
+#ifndef IBVH_PYR_TILE_MINB
+#define IBVH_PYR_TILE_MINB 8      // resident CTAs per SM the tile kernel's registers are capped for (8 -> 64 registers)
+#endif
+IBVH_D void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+IBVH_D void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+IBVH_D void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+IBVH_D void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+// global -> shared bulk copy; dst / src 16-byte aligned, bytes a multiple of 16
+IBVH_D void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+IBVH_D void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // leaf volumes -> 16-byte aligned records (one pass per traversal; 0.07 ms for 10 M sphere leaves)
 // Records [n, n_pad) are all-ones bit patterns = NaN volumes: every comparison with them is false, so the tile
 // kernel needs no bounds masks on the target side.
@@ -368,6 +409,158 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_refine_kernel(const UBox<T
     if (nbuf) flush(nbuf);
 }
 
+// ---- 3b. refine, TMA form ------------------------------------------------------------------------------------------
+// Same work, same pair lists as pyr_refine_kernel. Per warp step (4 pairs) ONE lane arms the stage's mbarrier and four
+// lanes issue two bulk copies each: the 8 child boxes of B (one aligned run of F * sizeof(N) bytes in the aligned node
+// copy) and the 8 query-pyramid boxes of A's children (one run of F * sizeof(UBox) bytes; the pyramid levels carry F
+// boxes of padding on both sides so that the run of a group cut by the shard range is still readable). The boxes are
+// read back from shared memory: B's as LDS.128 broadcasts, the lane's own A child as two LDS.128. Two stages per warp:
+// the copies of step t+1 fly while step t is tested. Against the LDG -> STS form this drops every global load and
+// shared store of box data from the LSU instruction stream.
+template <int KIND, class T>
+__global__ void __launch_bounds__(kPyrWarps * 32, 8) pyr_refine_tma_kernel(const UBox<T>* __restrict__ Uf, const BBox<T>* __restrict__ Nf,
+                                                                       uint32_t f_first, uint32_t f_nqg, uint32_t f_ntg,
+                                                                       PairList in, PairList out, uint32_t* ticket) {
+    using N = BBox<T>;
+    constexpr int F = 1 << kPyrFan;          // 8
+    constexpr int SLOTS = 32 / F;            // 4 pairs per warp step
+    constexpr int NRUN = F * (int)sizeof(N);                 // bytes of B's child boxes
+    constexpr int URUN = F * (int)sizeof(UBox<T>);           // bytes of A's child boxes
+    constexpr int SLOT_BYTES = NRUN + URUN + 16;             // + 16: neighbouring slots start in different banks
+    static_assert(NRUN % 16 == 0 && URUN % 16 == 0, "bulk copies move 16-byte multiples");
+    __shared__ __align__(128) unsigned char s_raw[kPyrWarps][2][SLOTS][SLOT_BYTES];
+    __shared__ __align__(8) unsigned long long s_bar[kPyrWarps][2];
+    __shared__ uint2 s_buf[kPyrWarps][32 * F + kPyrFlush];
+    __shared__ uint32_t s_n[kPyrWarps];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int slot = lane / F, i = lane % F;
+    const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&s_bar[w][0]);
+    const uint32_t raw0 = (uint32_t)__cvta_generic_to_shared(&s_raw[w][0][0][0]);
+    if (lane == 0) { s_n[w] = 0; mbar_init(bar0, 1); mbar_init(bar0 + 8, 1); mbar_fence_init(); }
+    __syncwarp();
+    unsigned long long count64 = *in.count;
+    if (count64 > in.cap) count64 = in.cap;
+    const uint32_t count = (uint32_t)count64;
+    uint32_t nbuf = 0;
+    uint32_t parity = 0;                                      // bit s = phase parity the next wait on stage s expects
+    auto flush = [&](uint32_t n) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(out.count, (unsigned long long)n);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const uint32_t b0 = nbuf - n;
+        for (uint32_t k = lane; k < n; k += 32) if (base + k < out.cap) out.data[base + k] = s_buf[w][b0 + k];
+        nbuf = b0;
+    };
+    struct Stage { uint32_t Ac, Bc0; bool a_ok; };
+    // issue the copies of one step into stage `st` (warp-uniform call; `have` per lane)
+    auto fetch = [&](uint2 pr, bool have, int st) -> Stage {
+        Stage sg;
+        sg.Ac = (pr.x << kPyrFan) + (uint32_t)i;
+        sg.Bc0 = pr.y << kPyrFan;
+        const uint32_t ua = sg.Ac - f_first;                               // wraps to a huge value if Ac < f_first
+        sg.a_ok = have && ua < f_nqg;
+        const unsigned issuers = __ballot_sync(0xffffffffu, have && i == 0);
+        if (issuers) {
+            __syncwarp();                                                  // every lane is done reading this stage (two steps ago)
+            if (lane == 0) { fence_proxy_async(); mbar_arrive_expect_tx(bar0 + 8 * st, (uint32_t)__popc(issuers) * (uint32_t)(NRUN + URUN)); }
+            __syncwarp();
+            if (have && i == 0) {
+                const uint32_t dst = raw0 + (uint32_t)((st * SLOTS + slot) * SLOT_BYTES);
+                tma_bulk_g2s(dst, Nf + sg.Bc0, (uint32_t)NRUN, bar0 + 8 * st);
+                // A's children: boxes (A << fan) - f_first .. + F of this level (>= -F + 1 thanks to the padding)
+                const long long u0 = (long long)(pr.x << kPyrFan) - (long long)f_first;
+                tma_bulk_g2s(dst + (uint32_t)NRUN, Uf + u0, (uint32_t)URUN, bar0 + 8 * st);
+            }
+        }
+        return sg;
+    };
+    volatile uint32_t* s_nv = s_n;
+    auto process = [&](const Stage& cur, int st) {
+        mbar_wait(bar0 + 8 * st, (parity >> st) & 1u);
+        parity ^= 1u << st;
+        const unsigned char* sbase = s_raw[w][st][slot];
+        uint32_t hits = 0;
+        if (cur.a_ok) {
+            alignas(16) UBox<T> u;
+            {
+                const uint4* sp = reinterpret_cast<const uint4*>(sbase + NRUN + i * (int)sizeof(UBox<T>));
+                uint4* dp = reinterpret_cast<uint4*>(&u);
+#pragma unroll
+                for (int k = 0; k < (int)(sizeof(UBox<T>) / 16); ++k) dp[k] = sp[k];
+            }
+            static_assert(F % 2 == 0, "boxes are read in pairs");
+#pragma unroll
+            for (int j = 0; j < F; j += 2) {
+                struct alignas(16) Two { N a, b; };
+                static_assert(sizeof(Two) % 16 == 0, "pair of boxes");
+                Two two;
+                const uint4* sp = reinterpret_cast<const uint4*>(sbase + j * sizeof(N));
+                uint4* dp = reinterpret_cast<uint4*>(&two);
+#pragma unroll
+                for (int k = 0; k < (int)(sizeof(Two) / 16); ++k) dp[k] = sp[k];
+                hits |= box_contact_bit(u.b, two.a, 1u << j) | box_contact_bit(u.b, two.b, 1u << (j + 1));
+            }
+            bool edge = cur.Bc0 + (uint32_t)F > f_ntg;
+            if constexpr (KIND == kSingle) edge = edge || cur.Ac > cur.Bc0;
+            if (edge) {
+                const uint32_t nval = f_ntg - cur.Bc0;
+                uint32_t allowed = nval >= (uint32_t)F ? ((1u << F) - 1u) : ((1u << nval) - 1u);
+                if constexpr (KIND == kSingle) {
+                    if (cur.Ac > cur.Bc0) {
+                        const uint32_t lo = cur.Ac - cur.Bc0;
+                        allowed &= lo >= (uint32_t)F ? 0u : ~((1u << lo) - 1u);
+                    }
+                }
+                hits &= allowed;
+            }
+        }
+        if (hits) {
+            uint32_t wpos = atomicAdd(&s_n[w], (uint32_t)__popc(hits));
+            do {
+                const int j = __ffs(hits) - 1;
+                hits &= hits - 1;
+                s_buf[w][wpos++] = make_uint2(cur.Ac, cur.Bc0 + (uint32_t)j);
+            } while (hits);
+        }
+        __syncwarp();
+        nbuf = s_nv[w];
+        if (nbuf >= (uint32_t)kPyrFlush) { flush(nbuf & ~31u); if (lane == 0) s_nv[w] = nbuf; }
+        __syncwarp();
+    };
+    const uint32_t chunk = SLOTS * pyr_chunk_steps(count, SLOTS);
+    for (;;) {
+        uint32_t c = 0;
+        if (lane == 0) c = atomicAdd(ticket, 1u);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        const unsigned long long base64 = (unsigned long long)c * chunk;
+        if (base64 >= count) break;
+        const uint32_t base = (uint32_t)base64;
+        const uint32_t end = count - base > chunk ? base + chunk : count;
+        uint32_t p = base + slot;
+        uint2 e1 = make_uint2(0u, 0u), e2 = make_uint2(0u, 0u);
+        if (p < end) e1 = in.data[p];
+        if (p + SLOTS < end) e2 = in.data[p + SLOTS];
+        auto next_entry = [&]() {
+            uint2 e = make_uint2(0u, 0u);
+            if (p + 2 * SLOTS < end) e = in.data[p + 2 * SLOTS];
+            return e;
+        };
+        Stage sa = fetch(e1, p < end, 0), sb;
+        for (uint32_t p0 = base; p0 < end;) {
+            sb = fetch(e2, p + SLOTS < end, 1);                            // (no copies, no barrier traffic when no slot has an entry)
+            e2 = next_entry();
+            process(sa, 0);
+            p0 += SLOTS; p += SLOTS;
+            if (p0 >= end) break;
+            sa = fetch(e2, p + SLOTS < end, 0);
+            e2 = next_entry();
+            process(sb, 1);
+            p0 += SLOTS; p += SLOTS;
+        }
+    }
+    if (nbuf) flush(nbuf);
+}
+
 // ---- 4. leaf tiles ------------------------------------------------------------------------------------------------
 // MODE kAtomic: append contacts (unordered). kCount: only add the number of contacts to *total.
 // PMODE (ordered protocol): 0 = none; 1 = count per query (atomicAdd counts[qi]); 2 = write (qpos, tpos) into the
@@ -375,7 +568,7 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_refine_kernel(const UBox<T
 // FLUSH: buffered hits per output-slot reservation. The fused multi-GPU mode on >= 4 ranks uses 512: every
 // reservation is a system-scope atomic on ONE counter of rank 0, which sustains ~190 M/s in total.
 template <int KIND, int MODE, int PMODE, class LQ, class LT, class I, int FLUSH = kPyrFlush>
-__global__ void __launch_bounds__(kPyrWarps * 32) pyr_leaf_tile_kernel(const LQ* __restrict__ qleaves, int64_t q_begin, int64_t q_end,
+__global__ void __launch_bounds__(kPyrWarps * 32, IBVH_PYR_TILE_MINB) pyr_leaf_tile_kernel(const LQ* __restrict__ qleaves, int64_t q_begin, int64_t q_end,
                                                                       DBvh<LT, BBox<typename LT::value_type>> bvh, PairList in, int flip,
                                                                       int64_t capacity, unsigned long long* total,
                                                                       I* counts, unsigned int* cursors, IndexPair<I>* contacts, int fused, uint32_t* ticket,
@@ -399,15 +592,26 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_leaf_tile_kernel(const LQ*
     constexpr bool kNeedParent = !std::is_same<VT, N>::value || !std::is_same<VQ, N>::value;   // box leaves: implied by the leaf test
     using TVol = Packed<VT>;
     constexpr int TPIECES = G * (int)sizeof(TVol) / 16;                    // 16-byte pieces of one target group
-    constexpr int SLOT_BYTES = G * (int)sizeof(TVol) + 16;                 // + 16: neighbouring slots start in different banks
-    // target volumes of the current and the next step (cp.async double buffer)
-    __shared__ __align__(16) unsigned char s_vraw[kPyrWarps][2][SLOTS][SLOT_BYTES];
+    // target volumes of the current and the next step (double buffer). TMA form: one 64-byte bulk copy per target group and
+    // one per query group, completing on the stage's mbarrier; else cp.async with the conflict-free piece mapping below.
+    constexpr bool kTma = IBVH_PYR_TMA != 0 && sizeof(TVol) <= 16 && sizeof(Packed<VQ>) <= 16;      // (16-byte sphere records; larger volumes keep cp.async: their double-buffered slots + query groups would not fit 48 KB)
+    constexpr int QBYTES = kTma ? G * (int)sizeof(Packed<VQ>) : 0;          // TMA form: the slot also holds the query group
+    constexpr int SLOT_BYTES = G * (int)sizeof(TVol) + QBYTES + 16;        // + 16: neighbouring slots start in different banks
+    __shared__ __align__(128) unsigned char s_vraw[kPyrWarps][2][SLOTS][SLOT_BYTES];
+    __shared__ __align__(8) unsigned long long s_bar[kPyrWarps][2];
     __shared__ uint2 s_buf[kPyrWarps][32 * QPL * G + FLUSH];               // a step appends <= 32 * QPL * G entries
     __shared__ uint32_t s_n[kPyrWarps];                                    // entries buffered per warp
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int slot = lane / LPP, i = lane % LPP;
-    if (lane == 0) s_n[w] = 0;
+    const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&s_bar[w][0]);
+    if (lane == 0) {
+        s_n[w] = 0;
+        if constexpr (kTma) { mbar_init(bar0, 1); mbar_init(bar0 + 8, 1); mbar_fence_init(); }
+    }
     __syncwarp();
+    uint32_t parity = 0;                                                   // TMA form: bit s = phase the next wait on stage s expects
+    const bool positions = (flip & 2) != 0;          // bit 1 of `flip`: report 1-based leaf positions instead of .index
+    flip &= 1;
     const uint32_t n_target = (uint32_t)bvh.ti.n;
     const N* __restrict__ parents = bvh.nodes + bvh.ti.level_start[bvh.ti.levels - 1];
     const uint32_t qb32 = (uint32_t)q_begin, qe32 = (uint32_t)q_end;
@@ -443,7 +647,7 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_leaf_tile_kernel(const LQ*
                     const unsigned int rr = atomicAdd(&cursors[qi], 1u);
                     // (target index, target position) for now — the leaf is still warm in L1 / L2 here, so the index
                     // is fetched now; pyr_fixup_kernel sorts the segment by position and writes the reported pair
-                    contacts[seg + rr] = IndexPair<I>{(I)bvh.leaves[e.y].index, (I)e.y};
+                    contacts[seg + rr] = IndexPair<I>{positions ? (I)(e.y + 1u) : (I)bvh.leaves[e.y].index, (I)e.y};
                 }
             } else {
                 if constexpr (PMODE == 3) { if (ok) atomic_inc(&counts[e.x - qb32]); }
@@ -466,7 +670,7 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_leaf_tile_kernel(const LQ*
                 uint4* stash = reinterpret_cast<uint4*>(contacts);
                 for (uint32_t k = lane; k < kept; k += 32) {
                     const uint2 e = s_buf[w][b0 + k];
-                    const unsigned long long li = (unsigned long long)(long long)bvh.leaves[e.y].index;
+                    const unsigned long long li = positions ? (unsigned long long)(e.y + 1u) : (unsigned long long)(long long)bvh.leaves[e.y].index;
                     if ((int64_t)(base + k) < capacity) stash[base + k] = make_uint4(e.x - qb32, e.y, (uint32_t)li, (uint32_t)(li >> 32));
                 }
             }
@@ -479,8 +683,8 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_leaf_tile_kernel(const LQ*
                 if (lane == 0) base = atomicAdd(total, (unsigned long long)kept);      // (fused: a LOCAL counter too; the slots index this rank's region)
                 base = __shfl_sync(0xffffffffu, base, 0);
                 auto to_pair = [&](uint2 e) -> IndexPair<I> {
-                    const I qidx = (I)qleaves[e.x].index;
-                    const I li = (I)bvh.leaves[e.y].index;
+                    const I qidx = positions ? (I)(e.x + 1u) : (I)qleaves[e.x].index;
+                    const I li = positions ? (I)(e.y + 1u) : (I)bvh.leaves[e.y].index;
                     I ea, eb;
                     if constexpr (KIND == kSingle) { if (qidx > li) { ea = li; eb = qidx; } else { ea = qidx; eb = li; } }
                     else { if (flip) { ea = li; eb = qidx; } else { ea = qidx; eb = li; } }
@@ -534,6 +738,21 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_leaf_tile_kernel(const LQ*
         sg.qpos0 = pr.x << kPyrLeafLog;
         sg.j0 = pr.y << kPyrLeafLog;
         sg.have = have ? 1u : 0u;
+        if constexpr (kTma) {
+            // one lane of each pair issues two bulk copies: the target group and the query group (64 bytes each for spheres)
+            const unsigned issuers = __ballot_sync(0xffffffffu, have && i == 0);
+            if (issuers) {
+                __syncwarp();                                              // every lane is done reading this stage
+                if (lane == 0) { fence_proxy_async(); mbar_arrive_expect_tx(bar0 + 8 * buf, (uint32_t)__popc(issuers) * (uint32_t)(G * sizeof(TVol) + QBYTES)); }
+                __syncwarp();
+                if (have && i == 0) {
+                    const uint32_t dst = vraw_base + (uint32_t)((buf * SLOTS + slot) * SLOT_BYTES);
+                    tma_bulk_g2s(dst, pt + sg.j0, (uint32_t)(G * sizeof(TVol)), bar0 + 8 * buf);
+                    tma_bulk_g2s(dst + (uint32_t)(G * sizeof(TVol)), pq + sg.qpos0, (uint32_t)QBYTES, bar0 + 8 * buf);
+                }
+            }
+            return sg;
+        }
 #pragma unroll
         for (int k = 0; k < QPL; ++k) sg.q[k] = load16(pq + sg.qpos0 + (uint32_t)(QPL * i + k));
         // Target copy global -> shared, 16 bytes per lane and instruction. The copy mapping is NOT the compute mapping:
@@ -569,9 +788,23 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_leaf_tile_kernel(const LQ*
         if (nbuf >= (uint32_t)FLUSH) { flush(nbuf & ~31u); if (lane == 0) s_nv[w] = nbuf; }
         __syncwarp();
     };
-    auto process = [&](const Stage& cur, int buf) {
-        asm volatile("cp.async.wait_group 1;" ::: "memory");                   // this step's targets have landed (next step's may be in flight)
-        __syncwarp();
+    auto process = [&](Stage& cur, int buf) {
+        if constexpr (kTma) {
+            mbar_wait(bar0 + 8 * buf, (parity >> buf) & 1u);
+            parity ^= 1u << buf;
+            if (cur.have) {
+#pragma unroll
+                for (int k = 0; k < QPL; ++k) {
+                    const uint4* sp = reinterpret_cast<const uint4*>(s_vraw[w][buf][slot] + G * sizeof(TVol) + (QPL * i + k) * sizeof(Packed<VQ>));
+                    uint4* dp = reinterpret_cast<uint4*>(&cur.q[k]);
+#pragma unroll
+                    for (int x = 0; x < (int)(sizeof(Packed<VQ>) / 16); ++x) dp[x] = sp[x];
+                }
+            }
+        } else {
+            asm volatile("cp.async.wait_group 1;" ::: "memory");               // this step's targets have landed (next step's may be in flight)
+            __syncwarp();
+        }
         uint32_t hits[QPL];
 #pragma unroll
         for (int k = 0; k < QPL; ++k) hits[k] = 0;
@@ -618,7 +851,7 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_leaf_tile_kernel(const LQ*
         if (base64 >= count) break;
         const uint32_t base = (uint32_t)base64;
         const uint32_t end = count - base > chunk ? base + chunk : count;
-        asm volatile("cp.async.wait_all;" ::: "memory");                       // the previous chunk's look-ahead copy is done
+        if constexpr (!kTma) asm volatile("cp.async.wait_all;" ::: "memory");   // the previous chunk's look-ahead copy is done
         __syncwarp();
         // the chunk's list entries into L1 (one 128-byte line = 16 entries per lane)
         if (base + 16u * lane < end) asm volatile("prefetch.global.L1 [%0];" ::"l"(in.data + base + 16u * lane));
@@ -656,7 +889,7 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_leaf_tile_kernel(const LQ*
             p0 += SLOTS; p += SLOTS;
         }
     }
-    asm volatile("cp.async.wait_all;" ::: "memory");
+    if constexpr (!kTma) asm volatile("cp.async.wait_all;" ::: "memory");
     if (nbuf) flush(nbuf);
     if constexpr (MODE == kCount && PMODE == 0) {
         if (lane == 0 && ncount) atomicAdd(total, ncount);
@@ -679,17 +912,47 @@ __global__ void __launch_bounds__(256) pyr_scatter_kernel(const uint4* __restric
     }
 }
 
-// Ordered protocol, last step: each query's segment holds (qpos, tpos) in arrival order; sort it by tpos
-// (ascending target position == the reference's DFS order) and convert to the reported index pair.
+// Ordered protocol, last step: each query's segment holds (target index, target position) in arrival order; sort it by
+// position (ascending target position == the reference's DFS order) and convert to the reported index pair.
+// Three tiers by segment length m: <= 8 in registers; <= kFixupInsertion by insertion sort in place (a few hundred moves
+// at most); longer segments go on two lists — up to kFixupWarp entries one WARP per segment, beyond that one BLOCK per
+// segment — and are sorted in place by a bitonic network whose every compare-exchange is ascending (partner i ^ (k - 1)
+// in the first step of a merge, i ^ j afterwards), so that any length works without padding: an out-of-range partner is
+// a virtual +inf and never swaps. Round 1 sorted long segments by insertion: a leaf touching 10^4 others cost 10^8 moves
+// in one thread.
+constexpr int kFixupInsertion = 32;
+constexpr int kFixupWarp = 1024;
+
+template <class I, class SYNC>
+IBVH_D void fixup_bitonic(IndexPair<I>* seg, int64_t m, int tid, int nthreads, SYNC&& sync) {
+    for (int64_t k = 2; (k >> 1) < m; k <<= 1) {
+        for (int64_t i = tid; i < m; i += nthreads) {                     // first step of the merge: mirror partner
+            const int64_t l = i ^ (k - 1);
+            if (l > i && l < m) { const IndexPair<I> x = seg[i], y = seg[l]; if (x.b > y.b) { seg[i] = y; seg[l] = x; } }
+        }
+        sync();
+        for (int64_t j = k >> 2; j > 0; j >>= 1) {
+            for (int64_t i = tid; i < m; i += nthreads) {
+                const int64_t l = i ^ j;
+                if (l > i && l < m) { const IndexPair<I> x = seg[i], y = seg[l]; if (x.b > y.b) { seg[i] = y; seg[l] = x; } }
+            }
+            sync();
+        }
+    }
+}
+
 template <int KIND, class LQ, class LT, class I>
 __global__ void __launch_bounds__(256) pyr_fixup_kernel(const LQ* __restrict__ qleaves, const LT* __restrict__ tleaves, int64_t q_begin,
-                                                       int64_t q_count, int flip, const I* __restrict__ counts, IndexPair<I>* contacts) {
+                                                       int64_t q_count, int flip, const I* __restrict__ counts, IndexPair<I>* contacts,
+                                                       uint32_t* long_lists, uint32_t* long_counts, uint32_t long_cap) {
     const int64_t qi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (qi >= q_count) return;
     const int64_t b = qi == 0 ? 0 : (int64_t)counts[qi - 1];
     const int64_t e = (int64_t)counts[qi];
     if (e <= b) return;
-    const I qidx = (I)qleaves[q_begin + qi].index;
+    const bool positions = (flip & 2) != 0;
+    flip &= 1;
+    const I qidx = positions ? (I)(q_begin + qi + 1) : (I)qleaves[q_begin + qi].index;
     auto report = [&](I li) -> IndexPair<I> {
         I ea, eb;
         if constexpr (KIND == kSingle) { if (qidx > li) { ea = li; eb = qidx; } else { ea = qidx; eb = li; } }
@@ -716,7 +979,13 @@ __global__ void __launch_bounds__(256) pyr_fixup_kernel(const LQ* __restrict__ q
         for (int x = 0; x < kReg; ++x) if (x < m) contacts[b + x] = report(v[x].a);
         return;
     }
-    // long segments: insertion sort in place
+    if (m > kFixupInsertion) {
+        // long segment: queue it for the cooperative kernel (list 0: one warp each, list 1: one block each)
+        const int which = m > kFixupWarp ? 1 : 0;
+        const uint32_t slot = atomicAdd(&long_counts[which], 1u);
+        if (slot < long_cap) { long_lists[(size_t)which * long_cap + slot] = (uint32_t)qi; return; }
+        // (cannot happen: long_cap covers every possible long segment; fall through to the insertion sort if it did)
+    }
     for (int64_t x = b + 1; x < e; ++x) {
         IndexPair<I> v = contacts[x];
         int64_t y = x - 1;
@@ -724,6 +993,40 @@ __global__ void __launch_bounds__(256) pyr_fixup_kernel(const LQ* __restrict__ q
         contacts[y + 1] = v;
     }
     for (int64_t x = b; x < e; ++x) contacts[x] = report(contacts[x].a);
+}
+
+// long segments: bitonic sort in place by target position, then the reported pairs. WARP_EACH: one warp per listed
+// query (grid-stride over warps), else one block per listed query.
+template <int KIND, bool WARP_EACH, class LQ, class I>
+__global__ void __launch_bounds__(256) pyr_fixup_long_kernel(const LQ* __restrict__ qleaves, int64_t q_begin, int flip, const I* __restrict__ counts,
+                                                            IndexPair<I>* contacts, const uint32_t* __restrict__ list, const uint32_t* __restrict__ list_count,
+                                                            uint32_t long_cap) {
+    const bool positions = (flip & 2) != 0;
+    flip &= 1;
+    uint32_t nlist = *list_count;
+    if (nlist > long_cap) nlist = long_cap;
+    const int lane = threadIdx.x & 31;
+    const uint32_t unit = WARP_EACH ? (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) : blockIdx.x;
+    const uint32_t units = WARP_EACH ? gridDim.x * (blockDim.x >> 5) : gridDim.x;
+    for (uint32_t s = unit; s < nlist; s += units) {
+        const int64_t qi = (int64_t)list[s];
+        const int64_t b = qi == 0 ? 0 : (int64_t)counts[qi - 1];
+        const int64_t m = (int64_t)counts[qi] - b;
+        IndexPair<I>* seg = contacts + b;
+        const I qidx = positions ? (I)(q_begin + qi + 1) : (I)qleaves[q_begin + qi].index;
+        const int tid = WARP_EACH ? lane : (int)threadIdx.x;
+        const int nth = WARP_EACH ? 32 : (int)blockDim.x;
+        if constexpr (WARP_EACH) fixup_bitonic<I>(seg, m, tid, nth, [] { __syncwarp(); });
+        else fixup_bitonic<I>(seg, m, tid, nth, [] { __syncthreads(); });
+        for (int64_t x = tid; x < m; x += nth) {
+            const I li = seg[x].a;
+            I ea, eb;
+            if constexpr (KIND == kSingle) { if (qidx > li) { ea = li; eb = qidx; } else { ea = qidx; eb = li; } }
+            else { if (flip) { ea = li; eb = qidx; } else { ea = qidx; eb = li; } }
+            seg[x] = IndexPair<I>{ea, eb};
+        }
+        if constexpr (WARP_EACH) __syncwarp(); else __syncthreads();
+    }
 }
 
 }  // namespace ibvh

@@ -43,6 +43,7 @@ struct GroupArgs {
     int32_t start_level;
     int32_t group_level;    // levels - log2(G): target level whose nodes are the target groups
     int32_t flip;
+    int32_t positions;      // report 1-based leaf positions instead of .index (IBVH_TRAVERSE_POSITIONS)
     uint32_t seg_cap;       // list entries reserved per query group
     uint32_t step_cap;      // walk-step budget per query group
     int64_t capacity;       // contacts capacity (pairs)
@@ -183,7 +184,7 @@ __global__ void __launch_bounds__(kTileWarps * 32) tile_kernel(const LQ* __restr
     if (q_valid) {
         LQ leaf = load_struct(qleaves + q);
         qvol = leaf.volume;
-        qidx = leaf.index;
+        qidx = a.positions ? (typename LQ::idx_t)(q + 1) : leaf.index;
         qbox = NodeOps<N>::convert(leaf.volume);
     }
     uint32_t len = 0;
@@ -207,7 +208,7 @@ __global__ void __launch_bounds__(kTileWarps * 32) tile_kernel(const LQ* __restr
             if (j0 + m < n_target) {
                 LT tl = load_struct(bvh.leaves + j0 + m);
                 s_vol[w][slot][m].v = tl.volume;
-                s_idx[w][slot][m] = tl.index;
+                s_idx[w][slot][m] = a.positions ? (decltype(tl.index))(j0 + m + 1) : tl.index;
             }
             if (m < (G + 1) / 2) {
                 int64_t pj = j0 / 2 + m;
@@ -312,8 +313,8 @@ __global__ void __launch_bounds__(kTileWarps * 32) tile_flat_kernel(const LQ* __
         if (lane == 0) base = atomicAdd(a.total, (unsigned long long)n);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (mine) {
-            const I qidx = (I)qleaves[e.x].index;
-            const I li = (I)bvh.leaves[e.y].index;
+            const I qidx = a.positions ? (I)(e.x + 1u) : (I)qleaves[e.x].index;
+            const I li = a.positions ? (I)(e.y + 1u) : (I)bvh.leaves[e.y].index;
             I ea, eb;
             if constexpr (KIND == kSingle) { if (qidx > li) { ea = li; eb = qidx; } else { ea = qidx; eb = li; } }
             else { if (a.flip) { ea = li; eb = qidx; } else { ea = qidx; eb = li; } }

@@ -127,8 +127,8 @@ class PeerGather:
         self._capi.lib().ibvh_peer_last_counts(self.handle, out, self.world)
         return [int(v) for v in out]
 
-    def set_regions(self, counts: Optional[Sequence[int]] = None, slack: float = 0.06) -> bool:
-        """Size the ranks' regions from per-rank counts (+ slack, + 4096 entries each). Every rank must pass the same
+    def set_regions(self, counts: Optional[Sequence[int]] = None, slack: float = 0.06, pad: int = 4096) -> bool:
+        """Size the ranks' regions from per-rank counts (+ slack, + `pad` entries each). Every rank must pass the same
         counts (e.g. last_counts()). None = equal split. Returns False if the list area cannot hold them."""
         cap = self.capacity_bytes // self.pair_bytes
         rb = self.peer.region_begin
@@ -136,7 +136,7 @@ class PeerGather:
             for r in range(self._capi.MAX_PEERS + 1):
                 rb[r] = 0
             return True
-        sizes = [(int(c * (1.0 + slack)) + 4096 + 1) & ~1 for c in counts]
+        sizes = [(int(c * (1.0 + slack)) + pad + 1) & ~1 for c in counts]
         if sum(sizes) > cap:
             return False
         b = 0                                                    # tight regions (the slack is what the gap filling has to move);

@@ -66,11 +66,15 @@ typedef enum ibvh_volume_kind { IBVH_BSPHERE = 0, IBVH_BBOX = 1 } ibvh_volume_ki
  * — build.jl:155-166, utils.jl:34-51 (index_exemplar, morton exemplar). */
 typedef struct ibvh_types {
     int32_t leaf_kind;        /* ibvh_volume_kind of the leaf volumes                        */
-    int32_t float_bytes;      /* 4 (Float32) or 8 (Float64): leaf AND node float type        */
+    int32_t float_bytes;      /* 4 (Float32) or 8 (Float64): float type of the LEAF volumes  */
     int32_t index_bytes;      /* 4 (Int32) or 8 (Int64)   — BVHOptions.index_exemplar        */
     int32_t morton_bytes;     /* 2, 4, 8 (UInt16/32/64)   — DefaultMortonAlgorithm exemplar  */
     int32_t node_kind;        /* ibvh_volume_kind of the nodes (BBox leaves need BBox nodes) */
-    int32_t reserved;
+    int32_t node_float_bytes; /* float type of the NODE volumes: 0 = the leaf float type; 4 over 8-byte leaves = the
+                                 reference's default call BVH(::Vector{BSphere{Float64}}) with BBox{Float32} nodes
+                                 (build.jl:198-205, README.md:38-46; converting merges of merge.jl:47-81). Build and
+                                 contact traversals only: the reference's own ray test needs one float type
+                                 (isintersection.jl:1-5) */
 } ibvh_types_t;
 
 /* ImplicitTree{I} — implicit_tree.jl:52-67 */
@@ -100,6 +104,13 @@ typedef struct ibvh_bvh {
                                       /* return at once with *num_contacts = -1; ibvh_traverse_finish waits for it    */
                                       /* and reports the total. The host can enqueue the next build meanwhile, so the */
                                       /* GPU does not idle across the traversal's one host round trip.                */
+#define IBVH_TRAVERSE_POSITIONS 128u  /* report 1-based POSITIONS in the (sorted) leaf arrays instead of the leaves' .index:   */
+                                      /* single (query position, target position) with query < target; pair (position in the */
+                                      /* queries' leaves, position in the target's leaves) (swapped under flip); rays (leaf    */
+                                      /* position, ray id). Same pairs, same order. This is how a caller applies the         */
+                                      /* reference's `narrow` predicate (traverse_single.jl:170, traverse_pair.jl:206,        */
+                                      /* raytrace/leaf_vs_tree/leaf_vs_tree.jl:194: evaluated only AFTER a positive leaf test) */
+                                      /* as a post-filter over leaves[position] with identical results.     */
 #define IBVH_TRAVERSE_STATS 8u        /* fill the device counters read by ibvh_last_traversal_stats */
 #define IBVH_TRAVERSE_COUNTS_VALID 4u /* ORDERED only: d_counts already holds the inclusive scan */
                                       /* left by a previous count-only call on the same queries: */

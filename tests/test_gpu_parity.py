@@ -823,8 +823,47 @@ def test_float64_reference_doctest(ib, golden, dev):
     g = golden["five_spheres"]
     bvh = ib.BVH(ib.bspheres(g["centers"], g["radii"], np.float64), ib.BBox(np.float64))
     assert pairs_list(ib.traverse(bvh).contacts.numpy()) == [tuple(p) for p in g["contacts_lvt_order"]]
+    # the reference's DEFAULT call: Float64 spheres, node type left at BBox{Float32} (README.md:38-46, build.jl:198-205)
+    s64 = ib.bspheres(g["centers"], g["radii"], np.float64)
+    mixed = ib.BVH(s64)
+    assert mixed.nodes.dtype == ib.BBox(np.float32).dtype and mixed.leaves.dtype["volume"] == ib.BSphere(np.float64).dtype
+    assert pairs_list(ib.traverse(mixed).contacts.numpy()) == [tuple(p) for p in g["contacts_lvt_order"]]
+    with pytest.raises(ib.ArgumentError):
+        ib.traverse_rays(mixed, np.zeros((3, 1)), np.ones((3, 1)))                       # no mixed-type ray test in the reference either
     with pytest.raises(NotImplementedError):
-        ib.BVH(ib.bspheres(g["centers"], g["radii"], np.float64), ib.BBox(np.float32))    # mixed float types: oracle only
+        ib.BVH(ib.bspheres(g["centers"], g["radii"], np.float32), ib.BBox(np.float64))   # Float64 nodes over Float32 leaves: not built
+
+
+def test_mixed_float64_leaves_float32_nodes(ib, O, dev):
+    """Float64 leaves under Float32 nodes (the reference's default node type): sorted leaves and nodes byte-identical to the
+    oracle's converting merges (merge.jl:47-81: arithmetic in the leaf type, result converted), contacts in order, every
+    start level, both node kinds, pair traversal; and the sets equal brute force."""
+    rng = np.random.default_rng(6432)
+    for node in ("bbox", "sphere"):
+        nt = ib.BBox(np.float32) if node == "bbox" else ib.BSphere(np.float32)
+        nk = O.BBOX if node == "bbox" else O.BSPHERE
+        for n in (1, 2, 3, 5, 64, 201, 3000, 40_000):
+            s = random_spheres(rng, n, fbytes=8, spread=6.0 * max(1.0, (n / 200.0) ** (1 / 3)))
+            for ibytes, mbytes in ((4, 4), (8, 8)):
+                ol = O.wrap(s, ibytes, mbytes)
+                on, _, _ = O.build(ol, nk, node_fbytes=4)
+                bvh = ib.BVH(s, nt, options=opts(ib, ibytes, mbytes), device=dev)
+                assert bvh.leaves.numpy().tobytes() == ol.tobytes(), (node, n, "leaves")
+                assert_nodes_equal(bvh.nodes.numpy(), on, node)
+            want = O.traverse_single(ol, on)
+            assert ib.traverse(bvh).contacts.numpy().tobytes() == want.tobytes(), (node, n)
+            assert (sorted_pairs(ib.traverse(bvh, ordered=False).contacts.numpy()) == sorted_pairs(want)).all()
+            # (no brute-force check here: Float32 node boxes are ROUNDED conversions of Float64 volumes and need not contain
+            # them, so the reference's own contact set may differ from the sphere predicate by tangency-level pairs)
+            for sl in range(1, bvh.tree.levels + 1, 4):
+                w2 = O.traverse_single(ol, on, start_level=sl)
+                assert ib.traverse(bvh, start_level=sl).contacts.numpy().tobytes() == w2.tobytes(), (node, n, sl)
+        s1, s2 = random_spheres(rng, 900, 8), random_spheres(rng, 500, 8)
+        o1 = O.wrap(s1); o2 = O.wrap(s2)
+        on1, _, _ = O.build(o1, nk, node_fbytes=4)
+        on2, _, _ = O.build(o2, nk, node_fbytes=4)
+        b1, b2 = ib.BVH(s1, nt, device=dev), ib.BVH(s2, nt, device=dev)
+        assert ib.traverse(b1, b2).contacts.numpy().tobytes() == O.traverse_pair(o1, on1, o2, on2).tobytes(), node
 
 
 def test_triangles_to_volumes_and_mesh_pipeline(ib, O, golden, dev):
@@ -1025,3 +1064,64 @@ def test_reference_shaped_proxy_build_is_bit_identical(ib, O, dev):
     assert ib.traverse(bvh, reference_shaped=True).contacts.numpy().tobytes() == want.tobytes()
     with pytest.raises(NotImplementedError):
         ib.BVH(s, ib.BBox(), device=dev, reference_shaped=True, options=opts(ib, 8, 8))
+
+
+@pytest.mark.gpu
+def test_ordered_long_segments_and_narrow(ib, O, dev):
+    """Dense clusters: query leaves with tens, hundreds and > 10^4 contacts (one sphere covering the whole scene) — the
+    ordered fix-up sorts their segments with the warp / block bitonic tiers instead of round 1's O(m^2) insertion sort.
+    Then `narrow` as a post-filter over leaf positions (IBVH_TRAVERSE_POSITIONS) against the same predicate applied to the
+    oracle's list, and BVHTraversal.num_checks."""
+    rng = np.random.default_rng(77)
+    n = 40_000
+    s = random_spheres(rng, n, spread=40.0)
+    s["r"] *= 0.5
+    s["x"][0] = 20.0; s["r"][0] = 80.0                       # touches every other leaf
+    s["x"][1:400] = 5.0 + rng.random((399, 3)).astype(np.float32) * 0.5      # a cluster: ~400 mutual contacts each
+    s["x"][400:460] = 30.0 + rng.random((60, 3)).astype(np.float32) * 0.2    # a smaller one: ~60 each
+    ol, on = oracle_build(O, s)
+    want = O.traverse_single(ol, on, num_threads=8)
+    bvh = ib.BVH(s, ib.BBox(), device=dev)
+    got = ib.traverse(bvh)
+    assert got.num_contacts == len(want) > n
+    assert got.contacts.numpy().tobytes() == want.tobytes()
+    assert got.num_checks > got.num_contacts                  # box + leaf tests of the pyramid schedule
+    # with a pre-sized cache (the one-pass stash protocol) and through the packet schedule
+    again = ib.traverse(bvh, cache=got)
+    assert again.contacts.numpy().tobytes() == want.tobytes()
+    assert ib.traverse(bvh, packet=True).contacts.numpy().tobytes() == want.tobytes()
+    # pair traversal with long segments
+    s2 = random_spheres(rng, 5000, spread=40.0)
+    o2, on2 = oracle_build(O, s2)
+    wp = O.traverse_pair(ol, on, o2, on2, num_threads=8)
+    b2 = ib.BVH(s2, ib.BBox(), device=dev)
+    assert ib.traverse(bvh, b2).contacts.numpy().tobytes() == wp.tobytes()
+    # narrow: keep pairs whose index sum is even and whose first volume is the smaller one
+    pred = lambda a, b: ((a["index"] + b["index"]) % 2 == 0) & (a["volume"]["r"] <= b["volume"]["r"])
+    pos_of = {int(ix): k for k, ix in enumerate(ol["index"])}
+    def filt(pairs, la, lb, single):
+        keep = []
+        for a, b in zip(pairs["a"], pairs["b"]):
+            pa, pb = pos_of_a[int(a)], pos_of_b[int(b)]
+            if single and pa > pb:
+                pa, pb = pb, pa                              # the query is the leaf at the lower position
+            keep.append(bool(pred(la[pa:pa + 1], lb[pb:pb + 1])[0]))
+        return pairs[np.array(keep, bool)]
+    pos_of_a = pos_of_b = pos_of
+    want_n = filt(want, ol, ol, True)
+    got_n = ib.traverse(bvh, narrow=pred)
+    assert got_n.contacts.numpy().tobytes() == want_n.tobytes()
+    assert int(got_n.cache2.numpy()[-1]) == len(want_n)
+    scalar_pred = lambda a, b: bool((int(a["index"]) + int(b["index"])) % 2 == 0 and a["volume"]["r"] <= b["volume"]["r"])
+    assert ib.traverse(bvh, narrow=scalar_pred, ordered=True).contacts.numpy().tobytes() == want_n.tobytes()     # element-wise fallback
+    pos_of_b = {int(ix): k for k, ix in enumerate(o2["index"])}
+    want_pn = filt(wp, ol, o2, False)
+    assert ib.traverse(bvh, b2, narrow=pred).contacts.numpy().tobytes() == want_pn.tobytes()
+    # rays: narrow(leaf, point, direction)
+    p = (rng.random((3, 3000)) * 40).astype(np.float32)
+    d = (rng.random((3, 3000)) - 0.5).astype(np.float32)
+    wr = O.traverse_rays(ol, on, p, d, num_threads=8)
+    rpred = lambda leaf, pt, dr: (leaf["index"] % 3 == 0) & (pt[:, 0] > 10.0)
+    keep = (wr["a"] % 3 == 0) & (p[0][wr["b"] - 1] > 10.0)
+    gr = ib.traverse_rays(bvh, p, d, narrow=rpred)
+    assert gr.contacts.numpy().tobytes() == wr[keep].tobytes()

@@ -52,7 +52,7 @@ R = 400_000
 rp, rd = synth.random_rays_torch(R, dev, seed=3)
 rp = rp * 0.3 + 0.5                                   # origins inside the unit cube of the sphere scene
 full_r = ib.traverse_rays(bvh, rp, rd, ordered=False)
-pg_r = ibdist.PeerGather(full_r.num_contacts + 1024, 8, dev)
+pg_r = ibdist.PeerGather(full_r.num_contacts + 1024, 8, dev)      # (tight on purpose: exercises the region re-sizing)
 rb = ibdist.shard_bounds(R, world)[rank]
 if pg_r.peer.multicast:
     for rep in range(2):

@@ -514,6 +514,7 @@ def main():
         out_done = [torch.cuda.Event() for _ in range(2)]
         bvh_prev = e2e_state["bvh"]
         use_fused = world > 1 and fused and state["peer"] is not None
+        skip = set(os.environ.get("IBVH_E2E_SKIP", "").split(","))        # diagnosis only: h2d, allgather, d2h
         if use_fused and e2e_state.get("peers") is None:
             # two symmetric buffers: step k's slice of the gathered list leaves for the host while step k+1 writes the other
             e2e_state["peers"] = [state["peer"], ibdist.PeerGather(state["peer"].capacity_bytes // 8, 8, dev)]
@@ -523,7 +524,8 @@ def main():
             b = k % 2
             with torch.cuda.stream(s_in):
                 s_in.wait_event(comp_done[b])                 # step k-2 no longer reads d_in[b]
-                d_in[b].tensor[shard_lo:shard_hi].copy_(pinned_in.tensor[shard_lo:shard_hi], non_blocking=True)
+                if "h2d" not in skip:
+                    d_in[b].tensor[shard_lo:shard_hi].copy_(pinned_in.tensor[shard_lo:shard_hi], non_blocking=True)
                 in_ready[b].record(s_in)
 
         for ev in comp_done + out_done:
@@ -536,7 +538,7 @@ def main():
                 h2d(k + 1)                                     # next step's input travels while this step computes
             main.wait_event(in_ready[b])
             main.wait_event(out_done[b])                       # step k-2's contacts have left caches[b]
-            if even:
+            if even and "allgather" not in skip:
                 dist.all_gather_into_tensor(d_in[b].tensor, d_in[b].tensor[shard_lo:shard_hi])
             bvh = ib.BVH(d_in[b], ib.BBox(), cache=bvh_prev)
             if world == 1:
@@ -560,7 +562,8 @@ def main():
             comp_done[b].record(main)
             with torch.cuda.stream(s_out):
                 s_out.wait_event(comp_done[b])
-                outs[b][:(hi - lo) * 8].copy_(src_t[lo * 8:hi * 8], non_blocking=True)
+                if "d2h" not in skip:
+                    outs[b][:(hi - lo) * 8].copy_(src_t[lo * 8:hi * 8], non_blocking=True)
                 out_done[b].record(s_out)
             last = hi - lo
         s_out.synchronize(); s_in.synchronize(); main.synchronize()

@@ -32,7 +32,7 @@ class Tree(C.Structure):
 
 class Bvh(C.Structure):
     _fields_ = [("d_leaves", C.c_void_p), ("d_nodes", C.c_void_p), ("n", C.c_int64), ("built_level", C.c_int64),
-                ("types", Types)]
+                ("types", Types), ("build_id", C.c_uint64)]
 
 
 class Peer(C.Structure):
@@ -82,6 +82,7 @@ SIGNATURES = {
     "ibvh_last_traversal_stats": (_ci, [_vp, C.POINTER(_i64)]),
     "ibvh_traverse_finish": (_ci, [_vp, C.POINTER(_i64)]),
     "ibvh_traverse_cancel": (_ci, [_vp]),
+    "ibvh_last_build_id": (C.c_uint64, [_vp]),
     "ibvh_peer_last_counts": (_ci, [_vp, C.POINTER(_i64), C.c_int32]),
     "ibvh_allgather_pairs": (_ci, [_vp, C.POINTER(Peer), _vp, _i64, C.c_int32, C.POINTER(_i64), C.POINTER(_i64), _vp]),
 }

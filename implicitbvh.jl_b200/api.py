@@ -457,10 +457,12 @@ class BVH:
                             1 if m.compute_extrema else 0, mins, maxs, _stream_ptr(didx))
         if rc != capi.OK:
             _raise(rc, self._handle, "ibvh_build")
+        self._build_id = int(lib.ibvh_last_build_id(self._handle))     # the build's sidecar (0 = none)
 
     # -- helpers ---------------------------------------------------------------------------------
     def _c_bvh(self) -> capi.Bvh:
-        return capi.Bvh(self.leaves.ptr, self.nodes.ptr if len(self.nodes) else None, len(self.leaves), self.built_level, self.types)
+        return capi.Bvh(self.leaves.ptr, self.nodes.ptr if len(self.nodes) else None, len(self.leaves), self.built_level, self.types,
+                        getattr(self, "_build_id", 0))
 
     @property
     def index_dtype(self) -> np.dtype:

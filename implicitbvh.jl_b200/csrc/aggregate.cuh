@@ -34,12 +34,21 @@ template <class L> struct GatherSrc<L, typename L::vol_t> {
     }
 };
 
+// Sidecar outputs of the build (handle.cuh: Sidecar): every pointer may be null.
+template <class N> struct SideLevels { N* lvl[34]; };
+template <class V, class N> struct SideOut {
+    Packed<V>* pt;                               // packed leaf volumes [n + 8] (the tail is NaN padding)
+    N* lvl[34];                                  // lvl[l]: 64-byte aligned run receiving a copy of the nodes of tree level l
+    UBox<typename N::value_type>* u[3];          // query-pyramid levels k = 2, 5, 8 (exact unions of the leaves' boxes), index = group
+};
+
 // Stand-alone gather: leaves[i] = source[perm[i]] with morton = keys_sorted[i]. Two leaves per thread, all index
 // loads before the random loads. The merge then runs from the sorted leaves (gather_merge_kernel<GATHER=false>):
 // one extra coalesced read of the leaves, but neither kernel waits on the other's latency inside a CTA.
 template <class L, class SRC>
 __global__ void __launch_bounds__(256) gather_kernel(const SRC* __restrict__ src, const uint32_t* __restrict__ perm,
-                                                    const typename L::mor_t* __restrict__ keys_sorted, L* __restrict__ leaves, int64_t n, int vec) {
+                                                    const typename L::mor_t* __restrict__ keys_sorted, L* __restrict__ leaves, int64_t n, int vec,
+                                                    Packed<typename L::vol_t>* __restrict__ packed) {
     constexpr int PER = 4;
     const int64_t base = ((int64_t)blockIdx.x * blockDim.x) * PER + threadIdx.x;
     uint32_t pp[PER];
@@ -60,7 +69,20 @@ __global__ void __launch_bounds__(256) gather_kernel(const SRC* __restrict__ src
 #pragma unroll
     for (int u = 0; u < PER; ++u) {
         const int64_t i = base + (int64_t)u * blockDim.x;
-        if (i < n) store_words(leaves + i, wv[u]);
+        if (i < n) {
+            store_words(leaves + i, wv[u]);
+            if (packed) {                        // sidecar: the volume alone as a 16-byte aligned record (zero padding)
+                alignas(16) Packed<typename L::vol_t> r;
+                memset(&r, 0, sizeof(r));
+                r.v = words_volume<L>(wv[u]);
+                store16(packed + i, r);
+            }
+        }
+    }
+    if (packed && blockIdx.x == 0 && threadIdx.x < 8) {      // NaN records past the end: no bounds masks on the target side
+        alignas(16) Packed<typename L::vol_t> r;
+        memset(&r, 0xFF, sizeof(r));
+        store16(packed + n + threadIdx.x, r);
     }
 }
 
@@ -73,7 +95,8 @@ struct LevelPlan {
 //   in_count: number of input slots of the tile (TILE); tile index t; input level `lvl_in`.
 //   sbuf0/sbuf1: ping-pong node buffers of TILE/2 and TILE/4 entries.
 template <class N, int TILE, int THREADS, class LOADPAIR>
-IBVH_D void merge_tile_levels(N* nodes, const TreeInfo& ti, int lvl_in, int stop_level, int64_t tile, N* sbuf0, N* sbuf1, LOADPAIR first_level) {
+IBVH_D void merge_tile_levels(N* nodes, const TreeInfo& ti, int lvl_in, int stop_level, int64_t tile, N* sbuf0, N* sbuf1, LOADPAIR first_level,
+                              N* const* side_lvl = nullptr) {
     // first produced level: lvl_in - 1, from the tile input through `first_level(j, left_only)`
     int lvl = lvl_in - 1;
     int count = TILE / 2;
@@ -89,7 +112,10 @@ IBVH_D void merge_tile_levels(N* nodes, const TreeInfo& ti, int lvl_in, int stop
                 bool right_virtual = (2 * gi + 1) >= nreal_child;
                 N v = first_level(j, right_virtual);
                 cur[j] = v;
-                if (lvl >= stop_level) nodes[ti.level_start[lvl] + gi] = v;
+                if (lvl >= stop_level) {
+                    nodes[ti.level_start[lvl] + gi] = v;
+                    if (side_lvl && side_lvl[lvl]) side_lvl[lvl][gi] = v;
+                }
             }
         }
     }
@@ -107,6 +133,7 @@ IBVH_D void merge_tile_levels(N* nodes, const TreeInfo& ti, int lvl_in, int stop
                 N v = ((2 * gi + 1) >= nreal_child) ? cur[2 * j] : merge(cur[2 * j], cur[2 * j + 1]);
                 nxt[j] = v;
                 nodes[ti.level_start[lvl] + gi] = v;
+                if (side_lvl && side_lvl[lvl]) side_lvl[lvl][gi] = v;
             }
         }
         __syncthreads();
@@ -120,7 +147,8 @@ IBVH_D void merge_tile_levels(N* nodes, const TreeInfo& ti, int lvl_in, int stop
 template <class L, class SRC, class N, int TILE, int THREADS, bool GATHER>
 __global__ void __launch_bounds__(THREADS) gather_merge_kernel(const SRC* __restrict__ src, const uint32_t* __restrict__ perm,
                                                               const typename L::mor_t* __restrict__ keys_sorted,
-                                                              L* leaves, N* nodes, TreeInfo ti, int stop_level, int vec) {
+                                                              L* leaves, N* nodes, TreeInfo ti, int stop_level, int vec,
+                                                              SideOut<typename L::vol_t, N> so) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     L* sleaf = (L*)smem_raw;
     N* sbuf0 = (N*)(smem_raw + ((sizeof(L) * TILE + 15) & ~size_t(15)));
@@ -171,17 +199,54 @@ __global__ void __launch_bounds__(THREADS) gather_merge_kernel(const SRC* __rest
         __syncthreads();
     }
     if (ti.levels < 2) return;
+    // sidecar: the three finest levels of the query pyramid — EXACT unions of the leaves' own boxes (not tree nodes: a
+    // leaf-parent box need not contain its leaves' boxes in floating point, merge.jl:62-68) for groups of 4, 32, 256 leaves
+    if constexpr (std::is_same<N, BBox<typename N::value_type>>::value) {
+        if (so.u[0]) {
+            using T = typename N::value_type;
+            static_assert(sizeof(UBox<T>) * (TILE / 4) <= sizeof(N) * (TILE / 2), "the pyramid boxes of a tile fit the first node buffer");
+            UBox<T>* su = reinterpret_cast<UBox<T>*>(sbuf0);
+            for (int g = threadIdx.x; g < TILE / 4; g += THREADS) {
+                BBox<T> u = empty_box<T>();
+#pragma unroll
+                for (int m = 0; m < 4; ++m) if (4 * g + m < tile_n) u = merge(u, NodeOps<BBox<T>>::convert(sleaf[4 * g + m].volume));
+                su[g].b = u;
+                so.u[0][tile * (TILE / 4) + g].b = u;
+            }
+            __syncthreads();
+            UBox<T>* su1 = su + TILE / 4;
+            if (so.u[1]) {
+                for (int g = threadIdx.x; g < TILE / 32; g += THREADS) {
+                    BBox<T> u = empty_box<T>();
+#pragma unroll
+                    for (int m = 0; m < 8; ++m) u = merge(u, su[8 * g + m].b);
+                    su1[g].b = u;
+                    so.u[1][tile * (TILE / 32) + g].b = u;
+                }
+            }
+            __syncthreads();
+            if (so.u[2]) {
+                for (int g = threadIdx.x; g < TILE / 256; g += THREADS) {
+                    BBox<T> u = empty_box<T>();
+#pragma unroll
+                    for (int m = 0; m < 8; ++m) u = merge(u, su1[8 * g + m].b);
+                    so.u[2][tile * (TILE / 256) + g].b = u;
+                }
+            }
+            __syncthreads();
+        }
+    }
     // _aggregate_last_level_at!, build.jl:427-457
     merge_tile_levels<N, TILE, THREADS>(nodes, ti, ti.levels, stop_level, tile, sbuf0, sbuf1,
         [&](int j, bool right_virtual) -> N {
             return right_virtual ? NodeOps<N>::convert(sleaf[2 * j].volume)
                                  : NodeOps<N>::merge_leaves(sleaf[2 * j].volume, sleaf[2 * j + 1].volume);
-        });
+        }, so.lvl);
 }
 
 // Upper levels: tile input = nodes of level `src_level` already in global memory.
 template <class N, int TILE, int THREADS>
-__global__ void __launch_bounds__(THREADS) merge_levels_kernel(N* nodes, TreeInfo ti, int src_level, int stop_level) {
+__global__ void __launch_bounds__(THREADS) merge_levels_kernel(N* nodes, TreeInfo ti, int src_level, int stop_level, SideLevels<N> side) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     N* sin = (N*)smem_raw;
     N* sbuf0 = sin + TILE;
@@ -194,7 +259,7 @@ __global__ void __launch_bounds__(THREADS) merge_levels_kernel(N* nodes, TreeInf
     for (int j = threadIdx.x; j < tile_n; j += THREADS) sin[j] = in[j];
     __syncthreads();
     merge_tile_levels<N, TILE, THREADS>(nodes, ti, src_level, stop_level, tile, sbuf0, sbuf1,
-        [&](int j, bool right_virtual) -> N { return right_virtual ? sin[2 * j] : merge(sin[2 * j], sin[2 * j + 1]); });
+        [&](int j, bool right_virtual) -> N { return right_virtual ? sin[2 * j] : merge(sin[2 * j], sin[2 * j + 1]); }, side.lvl);
 }
 
 }  // namespace ibvh

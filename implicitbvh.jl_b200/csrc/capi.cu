@@ -131,6 +131,71 @@ constexpr int kMergeTile = 1024;
 constexpr int kMergeThreads = 256;
 constexpr int kMergeLevels = 10;   // log2(kMergeTile)
 
+// ---- pyramid refinement driver (BBox nodes) -----------------------------------------------------------------
+struct PyrPlan { int n; PyrLevel lv[kPyrMaxLevels]; int64_t u_total; int64_t t_total; };
+
+// levels from the finest (k = 2) to the top; false if the schedule does not apply (tree too short, the needed
+// tree levels are not built, or the coarsest usable level still has too many groups for an all-pairs start)
+inline bool make_pyr_plan(const TreeInfo& ti, int64_t built_level, int64_t q_begin, int64_t q_count, PyrPlan* plan) {
+    const int L = ti.levels;
+    const int64_t q_end = q_begin + q_count;
+    plan->n = 0; plan->u_total = 0; plan->t_total = 0;
+    for (int k = kPyrLeafLog; plan->n < kPyrMaxLevels; k += kPyrFan) {
+        const int tl = L - k;
+        if (tl < 1 || tl < built_level) break;
+        PyrLevel& v = plan->lv[plan->n];
+        v.k = k; v.tree_level = tl; v.ntg = ti.level_nreal[tl]; v.tnode0 = ti.level_start[tl];
+        // (the query-pyramid levels carry 2^fan boxes of padding on both sides: the TMA refine kernel copies the aligned run of
+        // 2^fan children of a group even when the shard range cuts it)
+        v.qg_first = q_begin >> k; v.nqg = ((q_end - 1) >> k) - v.qg_first + 1; v.u_off = plan->u_total + (int64_t(1) << kPyrFan);
+        plan->u_total += v.nqg + (int64_t(2) << kPyrFan);
+        v.t_off = plan->t_total;
+        plan->t_total += (v.ntg + 15) & ~int64_t(7);               // whole groups of 8 + slack, 64-byte aligned starts
+        plan->n += 1;
+        if (v.nqg <= 2048 && v.ntg <= 2048) return true;          // good top level
+    }
+    if (plan->n == 0) return false;
+    const PyrLevel& top = plan->lv[plan->n - 1];
+    return top.nqg * top.ntg <= (int64_t(1) << 26);                 // an all-pairs start of <= 64 M box tests is still cheap
+}
+
+
+// ---- sidecar of a build (handle.cuh: Sidecar): layout + device pointers --------------------------------------------
+// [packed volumes: n + 8 records][aligned node levels: full-range plan's t_total boxes][query pyramid: levels k = 2, 5, 8]
+template <class L, class N> struct SidecarLayout {
+    using V = typename L::vol_t;
+    using T = typename N::value_type;
+    PyrPlan plan;                 // the full-range plan (q = [0, n))
+    size_t pt_off, nt_off, u_off, bytes;
+    int u_levels;
+    int64_t u_level_off[3], u_level_n[3];
+    bool ok;
+};
+template <class L, class N> SidecarLayout<L, N> sidecar_layout(const TreeInfo& ti, int64_t built_level) {
+    SidecarLayout<L, N> s{};
+    s.ok = false;
+    if constexpr (!std::is_same<N, BBox<typename L::value_type>>::value) return s;     // pyramid schedule: BBox nodes of the leaf float type
+    if (ti.n >= (int64_t(1) << 29)) return s;
+    if (!make_pyr_plan(ti, built_level, 0, ti.n, &s.plan)) return s;
+    size_t off = 0;
+    s.pt_off = off; off += ibvh_handle::padded((size_t)(ti.n + 8) * sizeof(Packed<typename L::vol_t>));
+    s.nt_off = off; off += ibvh_handle::padded((size_t)s.plan.t_total * sizeof(N));
+    s.u_off = off;
+    s.u_levels = s.plan.n < 3 ? s.plan.n : 3;
+    int64_t uo = 0;
+    for (int l = 0; l < s.u_levels; ++l) {
+        // whole merge tiles worth of groups (the kernel writes every group of a tile) + the 2^fan padding either side
+        const int64_t groups = ((ti.n + kMergeTile - 1) / kMergeTile) * (kMergeTile >> s.plan.lv[l].k);
+        s.u_level_off[l] = uo + (int64_t(1) << kPyrFan);
+        s.u_level_n[l] = groups;
+        uo += groups + (int64_t(2) << kPyrFan);
+    }
+    off += ibvh_handle::padded((size_t)uo * sizeof(UBox<typename N::value_type>));
+    s.bytes = off;
+    s.ok = true;
+    return s;
+}
+
 template <class L, class N> size_t gather_smem_bytes() {
     return ((sizeof(L) * kMergeTile + 15) & ~size_t(15)) + sizeof(N) * (kMergeTile / 2 + kMergeTile / 4);
 }
@@ -138,7 +203,7 @@ template <class N> size_t merge_smem_bytes() { return sizeof(N) * (kMergeTile + 
 
 // upper levels after the tile kernel produced levels-1 .. levels-kMergeLevels
 template <class N>
-int merge_upper_levels(ibvh_handle* h, N* nodes, const TreeInfo& ti, int stop_level, cudaStream_t st) {
+int merge_upper_levels(ibvh_handle* h, N* nodes, const TreeInfo& ti, int stop_level, cudaStream_t st, const SideLevels<N>* side = nullptr) {
     int src = ti.levels - kMergeLevels;
     {   // function attributes are per device: set on every call (cheap)
         cudaError_t e = cudaFuncSetAttribute(merge_levels_kernel<N, kMergeTile, kMergeThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)merge_smem_bytes<N>());
@@ -148,7 +213,7 @@ int merge_upper_levels(ibvh_handle* h, N* nodes, const TreeInfo& ti, int stop_le
         int stop = src - kMergeLevels > stop_level ? src - kMergeLevels : stop_level;
         int64_t tiles = (ti.level_nreal[src] + kMergeTile - 1) / kMergeTile;
         { ProfScope _ps(h, st, "merge_levels_kernel");
-        merge_levels_kernel<N, kMergeTile, kMergeThreads><<<(unsigned)tiles, kMergeThreads, merge_smem_bytes<N>(), st>>>(nodes, ti, src, stop);
+        merge_levels_kernel<N, kMergeTile, kMergeThreads><<<(unsigned)tiles, kMergeThreads, merge_smem_bytes<N>(), st>>>(nodes, ti, src, stop, side ? *side : SideLevels<N>{});
         }
         IBVH_LAUNCH_CHECK(h, "merge_levels_kernel");
         src -= kMergeLevels;
@@ -158,7 +223,7 @@ int merge_upper_levels(ibvh_handle* h, N* nodes, const TreeInfo& ti, int stop_le
 
 template <class L, class SRC, class N, bool GATHER>
 int launch_gather_merge(ibvh_handle* h, const SRC* src, const uint32_t* perm, const typename L::mor_t* keys_sorted, L* leaves, N* nodes,
-                        const TreeInfo& ti, int stop_level, cudaStream_t st) {
+                        const TreeInfo& ti, int stop_level, cudaStream_t st, const SideOut<typename L::vol_t, N>* so = nullptr) {
     auto kern = gather_merge_kernel<L, SRC, N, kMergeTile, kMergeThreads, GATHER>;
     {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gather_smem_bytes<L, N>());
@@ -168,7 +233,7 @@ int launch_gather_merge(ibvh_handle* h, const SRC* src, const uint32_t* perm, co
     { ProfScope _ps(h, st, "gather_merge_kernel");
     const uintptr_t va = (uintptr_t)src;
     const int vec = std::is_same<L, SRC>::value ? 8 : (va % 16 == 0 ? 16 : (va % 8 == 0 ? 8 : 4));
-    kern<<<(unsigned)tiles, kMergeThreads, gather_smem_bytes<L, N>(), st>>>(src, perm, keys_sorted, leaves, nodes, ti, stop_level, vec);
+    kern<<<(unsigned)tiles, kMergeThreads, gather_smem_bytes<L, N>(), st>>>(src, perm, keys_sorted, leaves, nodes, ti, stop_level, vec, so ? *so : SideOut<typename L::vol_t, N>{});
     }
     IBVH_LAUNCH_CHECK(h, "gather_merge_kernel");
     return IBVH_OK;
@@ -289,6 +354,38 @@ int build_impl(ibvh_handle* h, const void* d_volumes, void* d_leaves, int64_t n,
     // the level above the leaves is always produced (build.jl:369), further levels down to built_level
     int stop_level = (int)(built_level < tree.levels - 1 ? built_level : tree.levels - 1);
     if (stop_level < 1) stop_level = 1;
+    // sidecar of this build: packed volumes, aligned node levels, finest query-pyramid levels (handle.cuh)
+    h->last_build_id = 0;
+    SideOut<V, N> so{};
+    SideLevels<N> sl{};
+    ibvh_handle::Sidecar* sc = nullptr;
+    if (!h->cfg.no_sidecar && !h->cfg.fused_gather && tree.real_nodes >= 2) {
+        SidecarLayout<L, N> lay = sidecar_layout<L, N>(ti, built_level);
+        if (lay.ok) {
+            sc = &h->sidecars[h->side_next];
+            h->side_next ^= 1;
+            sc->id = 0;
+            if (lay.bytes > sc->bytes) {
+                if (sc->buf) { cudaFree(sc->buf); sc->buf = nullptr; sc->bytes = 0; }
+                const size_t want = lay.bytes + (lay.bytes >> 4) + (1u << 16);
+                if (cudaMalloc((void**)&sc->buf, want) != cudaSuccess) { cudaGetLastError(); sc = nullptr; }      // no sidecar: the traversal packs on the fly
+                else sc->bytes = want;
+            }
+        }
+        if (sc) {
+            sc->n = n; sc->leaf_kind = V::kind; sc->float_bytes = (int)sizeof(typename L::value_type); sc->built_level = (int)built_level; sc->levels = (int)tree.levels;
+            sc->pt_off = lay.pt_off; sc->nt_off = lay.nt_off; sc->u_off = lay.u_off; sc->u_levels = lay.u_levels;
+            so.pt = (Packed<V>*)(sc->buf + lay.pt_off);
+            for (int l = 0; l + 1 < lay.plan.n; ++l) {               // (the top level is read straight from the caller's nodes)
+                const int tl = lay.plan.lv[l].tree_level;
+                so.lvl[tl] = (N*)(sc->buf + lay.nt_off) + lay.plan.lv[l].t_off;
+                sl.lvl[tl] = so.lvl[tl];
+            }
+            if constexpr (std::is_same<N, BBox<typename L::value_type>>::value) {
+                for (int l = 0; l < lay.u_levels; ++l) so.u[l] = (UBox<typename N::value_type>*)(sc->buf + lay.u_off) + lay.u_level_off[l];
+            }
+        }
+    }
     if (h->cfg.fused_gather) {
         if (wrap) rc = launch_gather_merge<L, V, N, true>(h, (const V*)d_volumes, perm, keys_sorted, (L*)d_leaves, (N*)d_nodes, ti, stop_level, st);
         else rc = launch_gather_merge<L, L, N, true>(h, (const L*)s.copy, perm, keys_sorted, (L*)d_leaves, (N*)d_nodes, ti, stop_level, st);
@@ -298,14 +395,15 @@ int build_impl(ibvh_handle* h, const void* d_volumes, void* d_leaves, int64_t n,
         { ProfScope _ps(h, st, "gather_kernel");
         const uintptr_t va = (uintptr_t)d_volumes;
         const int vec = va % 16 == 0 ? 16 : (va % 8 == 0 ? 8 : 4);
-        if (wrap) gather_kernel<L, V><<<gb, 256, 0, st>>>((const V*)d_volumes, perm, keys_sorted, (L*)d_leaves, n, vec);
-        else gather_kernel<L, L><<<gb, 256, 0, st>>>((const L*)s.copy, perm, keys_sorted, (L*)d_leaves, n, 8);
+        if (wrap) gather_kernel<L, V><<<gb, 256, 0, st>>>((const V*)d_volumes, perm, keys_sorted, (L*)d_leaves, n, vec, so.pt);
+        else gather_kernel<L, L><<<gb, 256, 0, st>>>((const L*)s.copy, perm, keys_sorted, (L*)d_leaves, n, 8, so.pt);
         }
         IBVH_LAUNCH_CHECK(h, "gather_kernel");
-        rc = launch_gather_merge<L, L, N, false>(h, (const L*)nullptr, nullptr, nullptr, (L*)d_leaves, (N*)d_nodes, ti, stop_level, st);
+        rc = launch_gather_merge<L, L, N, false>(h, (const L*)nullptr, nullptr, nullptr, (L*)d_leaves, (N*)d_nodes, ti, stop_level, st, &so);
     }
     if (rc != IBVH_OK) return rc;
-    if (tree.real_nodes >= 2) rc = merge_upper_levels<N>(h, (N*)d_nodes, ti, stop_level, st);
+    if (tree.real_nodes >= 2) rc = merge_upper_levels<N>(h, (N*)d_nodes, ti, stop_level, st, &sl);
+    if (rc == IBVH_OK && sc) { sc->id = h->next_build_id++; h->last_build_id = sc->id; }
     return rc;
 }
 
@@ -622,34 +720,6 @@ int traverse_tiled(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, con
     return run(std::integral_constant<int, kWrite>{}, counts, (IndexPair<I>*)d_contacts);
 }
 
-// ---- pyramid refinement driver (BBox nodes) -----------------------------------------------------------------
-struct PyrPlan { int n; PyrLevel lv[kPyrMaxLevels]; int64_t u_total; int64_t t_total; };
-
-// levels from the finest (k = 2) to the top; false if the schedule does not apply (tree too short, the needed
-// tree levels are not built, or the coarsest usable level still has too many groups for an all-pairs start)
-inline bool make_pyr_plan(const TreeInfo& ti, int64_t built_level, int64_t q_begin, int64_t q_count, PyrPlan* plan) {
-    const int L = ti.levels;
-    const int64_t q_end = q_begin + q_count;
-    plan->n = 0; plan->u_total = 0; plan->t_total = 0;
-    for (int k = kPyrLeafLog; plan->n < kPyrMaxLevels; k += kPyrFan) {
-        const int tl = L - k;
-        if (tl < 1 || tl < built_level) break;
-        PyrLevel& v = plan->lv[plan->n];
-        v.k = k; v.tree_level = tl; v.ntg = ti.level_nreal[tl]; v.tnode0 = ti.level_start[tl];
-        // (the query-pyramid levels carry 2^fan boxes of padding on both sides: the TMA refine kernel copies the aligned run of
-        // 2^fan children of a group even when the shard range cuts it)
-        v.qg_first = q_begin >> k; v.nqg = ((q_end - 1) >> k) - v.qg_first + 1; v.u_off = plan->u_total + (int64_t(1) << kPyrFan);
-        plan->u_total += v.nqg + (int64_t(2) << kPyrFan);
-        v.t_off = plan->t_total;
-        plan->t_total += (v.ntg + 15) & ~int64_t(7);               // whole groups of 8 + slack, 64-byte aligned starts
-        plan->n += 1;
-        if (v.nqg <= 2048 && v.ntg <= 2048) return true;          // good top level
-    }
-    if (plan->n == 0) return false;
-    const PyrLevel& top = plan->lv[plan->n - 1];
-    return top.nqg * top.ntg <= (int64_t(1) << 26);                 // an all-pairs start of <= 64 M box tests is still cheap
-}
-
 template <int KIND, class LQ, class LT, class I>
 int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, const DBvh<LT, BBox<typename LT::value_type>>& bvh,
                      const PyrPlan& plan, const TraverseArgs& ta, uint32_t flags, void* d_counts, void* d_contacts, int64_t capacity,
@@ -751,14 +821,34 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
     double factor = h->pyr_factor > 0 ? h->pyr_factor : (KIND == kSingle ? 40.0 : 80.0);
     unsigned long long need_cap[kPyrMaxLevels] = {0};
     for (int attempt = 0; attempt < 4; ++attempt) {
-        // carve: pyramid boxes + one pair list per level
+        // carve: pyramid boxes + one pair list per level (+ what no sidecar provides: packed volumes, aligned node levels)
         unsigned long long cap[kPyrMaxLevels];
         using VQ = typename LQ::vol_t;
         using VT = typename LT::vol_t;
         const bool same_leaves = (const void*)qleaves == (const void*)bvh.leaves && std::is_same<LQ, LT>::value;
-        size_t bytes = ibvh_handle::padded((size_t)plan.u_total * sizeof(UBox<T>)) + ibvh_handle::padded((size_t)plan.t_total * sizeof(N)) +
-                       ibvh_handle::padded((size_t)(bvh.ti.n + 8) * sizeof(Packed<VT>)) +
-                       (same_leaves ? 0 : ibvh_handle::padded((size_t)(n_query_total + 8) * sizeof(Packed<VQ>))) +
+        // sidecars written by ibvh_build (handle.cuh): the target tree's and — pair traversal — the query tree's
+        ibvh_handle::Sidecar* sct = h->find_sidecar(ta.t_build_id, bvh.ti.n);
+        ibvh_handle::Sidecar* scq = same_leaves ? sct : h->find_sidecar(ta.q_build_id, n_query_total);
+        SidecarLayout<LT, N> lay_t{};
+        SidecarLayout<LQ, N> lay_q{};
+        if (sct) {
+            lay_t = sidecar_layout<LT, N>(bvh.ti, sct->built_level);
+            if (!lay_t.ok || lay_t.bytes > sct->bytes || sct->float_bytes != (int)sizeof(T) || sct->leaf_kind != VT::kind || lay_t.plan.n < nl) sct = nullptr;
+        }
+        if (scq) {
+            if (same_leaves) {
+                if (!sct) scq = nullptr;
+            } else {
+                ibvh_tree_t tq;
+                make_tree(n_query_total, &tq);
+                lay_q = sidecar_layout<LQ, N>(make_tree_info(tq), scq->built_level);
+                if (!lay_q.ok || lay_q.bytes > scq->bytes || scq->float_bytes != (int)sizeof(T) || scq->leaf_kind != VQ::kind) scq = nullptr;
+            }
+        }
+        const int q_ulevels = scq ? std::min(nl, same_leaves ? lay_t.u_levels : lay_q.u_levels) : 0;
+        size_t bytes = ibvh_handle::padded((size_t)plan.u_total * sizeof(UBox<T>)) +
+                       (sct ? 0 : ibvh_handle::padded((size_t)plan.t_total * sizeof(N)) + ibvh_handle::padded((size_t)(bvh.ti.n + 8) * sizeof(Packed<VT>))) +
+                       ((same_leaves || scq) ? 0 : ibvh_handle::padded((size_t)(n_query_total + 8) * sizeof(Packed<VQ>))) +
                        (stash_mode ? ibvh_handle::padded((size_t)stash_cap * sizeof(uint4)) : 0);
         for (int l = 0; l < nl; ++l) {
             const PyrLevel& v = plan.lv[l];
@@ -772,43 +862,73 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
         if (rc != IBVH_OK) return rc;
         char* ap = h->aux;
         UBox<T>* U = (UBox<T>*)ap; ap += ibvh_handle::padded((size_t)plan.u_total * sizeof(UBox<T>));
-        N* NT = (N*)ap; ap += ibvh_handle::padded((size_t)plan.t_total * sizeof(N));                    // aligned copy of the target node levels
-        Packed<VT>* PT = (Packed<VT>*)ap; ap += ibvh_handle::padded((size_t)(bvh.ti.n + 8) * sizeof(Packed<VT>));
+        N* NT = nullptr;                                             // aligned copy of the target node levels
+        Packed<VT>* PT = nullptr;
+        if (sct) {
+            NT = (N*)(sct->buf + lay_t.nt_off);
+            PT = (Packed<VT>*)(sct->buf + lay_t.pt_off);
+        } else {
+            NT = (N*)ap; ap += ibvh_handle::padded((size_t)plan.t_total * sizeof(N));
+            PT = (Packed<VT>*)ap; ap += ibvh_handle::padded((size_t)(bvh.ti.n + 8) * sizeof(Packed<VT>));
+        }
         Packed<VQ>* PQ = (Packed<VQ>*)PT;
-        if (!same_leaves) { PQ = (Packed<VQ>*)ap; ap += ibvh_handle::padded((size_t)(n_query_total + 8) * sizeof(Packed<VQ>)); }
+        if (!same_leaves) {
+            if (scq) PQ = (Packed<VQ>*)(scq->buf + lay_q.pt_off);
+            else { PQ = (Packed<VQ>*)ap; ap += ibvh_handle::padded((size_t)(n_query_total + 8) * sizeof(Packed<VQ>)); }
+        }
         uint4* stash = nullptr;
         if (stash_mode) { stash = (uint4*)ap; ap += ibvh_handle::padded((size_t)stash_cap * sizeof(uint4)); }
         PairList lists[kPyrMaxLevels];
         for (int l = 0; l < nl; ++l) { lists[l].data = (uint2*)ap; lists[l].count = d_cnt + l; lists[l].cap = cap[l]; ap += ibvh_handle::padded((size_t)cap[l] * sizeof(uint2)); }
         IBVH_CUDA_TRY(h, cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * kPyrMaxLevels + 128, st));   // list counters + chunk tickets
         IBVH_CUDA_TRY(h, cudaMemsetAsync(d_total, 0, 8, st));
+        // per-level box pointers: query pyramid (index = group - qg_first of the shard's plan) and aligned target nodes.
+        // A sidecar's pyramid covers the WHOLE tree; a group cut by the shard range then carries the box of all its leaves,
+        // a superset of the in-range ones: conservative (never drops a pair), and the tile kernel masks the queries itself.
+        const UBox<T>* Ulev[kPyrMaxLevels];
+        const N* NTlev[kPyrMaxLevels];
+        for (int l = 0; l < nl; ++l) {
+            Ulev[l] = U + plan.lv[l].u_off;
+            if (l < q_ulevels) {
+                const char* ub = scq->buf + (same_leaves ? lay_t.u_off : lay_q.u_off);
+                Ulev[l] = (const UBox<T>*)ub + (same_leaves ? lay_t.u_level_off[l] : lay_q.u_level_off[l]) + plan.lv[l].qg_first;
+            }
+            NTlev[l] = sct ? NT + lay_t.plan.lv[l].t_off : NT + plan.lv[l].t_off;
+        }
 
-        // 0. 16-byte aligned records: leaf volumes, and the node levels the refinement reads as targets
+        // 0. 16-byte aligned records: leaf volumes, and the node levels the refinement reads as targets (unless a sidecar has them)
         const int64_t qend_c = q_end < n_query_total ? q_end : n_query_total;
         if (same_leaves) {
-            // targets == queries: one pass packs the volumes AND builds the finest level of the query pyramid
-            const int64_t groups = (bvh.ti.n + 8 + 3) / 4;
-            { ProfScope _ps(h, st, "pyr_pack_groups_kernel");
-            pyr_pack_groups_kernel<LT, T><<<(unsigned)((groups + 255) / 256), 256, 0, st>>>(bvh.leaves, bvh.ti.n, bvh.ti.n + 8, PT, q_begin, qend_c, plan.lv[0], U);
+            if (!sct) {
+                // targets == queries: one pass packs the volumes AND builds the finest level of the query pyramid
+                const int64_t groups = (bvh.ti.n + 8 + 3) / 4;
+                { ProfScope _ps(h, st, "pyr_pack_groups_kernel");
+                pyr_pack_groups_kernel<LT, T><<<(unsigned)((groups + 255) / 256), 256, 0, st>>>(bvh.leaves, bvh.ti.n, bvh.ti.n + 8, PT, q_begin, qend_c, plan.lv[0], U);
+                }
+                IBVH_LAUNCH_CHECK(h, "pyr_pack_groups_kernel");
             }
-            IBVH_LAUNCH_CHECK(h, "pyr_pack_groups_kernel");
         } else {
-            { ProfScope _ps(h, st, "pyr_pack_volumes_kernel");
-            pyr_pack_volumes_kernel<LT><<<(unsigned)((bvh.ti.n + 8 + 255) / 256), 256, 0, st>>>(bvh.leaves, bvh.ti.n, bvh.ti.n + 8, PT);
+            if (!sct) {
+                { ProfScope _ps(h, st, "pyr_pack_volumes_kernel");
+                pyr_pack_volumes_kernel<LT><<<(unsigned)((bvh.ti.n + 8 + 255) / 256), 256, 0, st>>>(bvh.leaves, bvh.ti.n, bvh.ti.n + 8, PT);
+                }
+                IBVH_LAUNCH_CHECK(h, "pyr_pack_volumes_kernel");
             }
-            IBVH_LAUNCH_CHECK(h, "pyr_pack_volumes_kernel");
-            const int64_t groups = (n_query_total + 8 + 3) / 4;
-            { ProfScope _ps(h, st, "pyr_pack_groups_kernel");
-            pyr_pack_groups_kernel<LQ, T><<<(unsigned)((groups + 255) / 256), 256, 0, st>>>(qleaves, n_query_total, n_query_total + 8, PQ, q_begin, qend_c, plan.lv[0], U);
+            if (!scq) {
+                const int64_t groups = (n_query_total + 8 + 3) / 4;
+                { ProfScope _ps(h, st, "pyr_pack_groups_kernel");
+                pyr_pack_groups_kernel<LQ, T><<<(unsigned)((groups + 255) / 256), 256, 0, st>>>(qleaves, n_query_total, n_query_total + 8, PQ, q_begin, qend_c, plan.lv[0], U);
+                }
+                IBVH_LAUNCH_CHECK(h, "pyr_pack_groups_kernel");
             }
-            IBVH_LAUNCH_CHECK(h, "pyr_pack_groups_kernel");
         }
-        for (int l = 0; l + 1 < nl; ++l)
-            IBVH_CUDA_TRY(h, cudaMemcpyAsync(NT + plan.lv[l].t_off, bvh.nodes + plan.lv[l].tnode0, (size_t)plan.lv[l].ntg * sizeof(N), cudaMemcpyDeviceToDevice, st));
-        // 1. query pyramid (the finest level was built with the packing pass)
-        for (int l = 1; l < nl; ++l) {
+        if (!sct)
+            for (int l = 0; l + 1 < nl; ++l)
+                IBVH_CUDA_TRY(h, cudaMemcpyAsync(NT + plan.lv[l].t_off, bvh.nodes + plan.lv[l].tnode0, (size_t)plan.lv[l].ntg * sizeof(N), cudaMemcpyDeviceToDevice, st));
+        // 1. query pyramid above the levels at hand (level 0 comes from the packing pass, levels 0 .. 2 from a sidecar)
+        for (int l = std::max(1, q_ulevels); l < nl; ++l) {
             { ProfScope _ps(h, st, "pyr_up_kernel");
-            pyr_up_kernel<T><<<(unsigned)((plan.lv[l].nqg + 255) / 256), 256, 0, st>>>(plan.lv[l - 1], plan.lv[l], U);
+            pyr_up_kernel<T><<<(unsigned)((plan.lv[l].nqg + 255) / 256), 256, 0, st>>>(plan.lv[l - 1], plan.lv[l], Ulev[l - 1], U + plan.lv[l].u_off);
             }
             IBVH_LAUNCH_CHECK(h, "pyr_up_kernel");
         }
@@ -818,7 +938,7 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
             int64_t tot = top.nqg * top.ntg;
             int tg = (int)std::min<int64_t>((tot + 255) / 256, (int64_t)h->sm_count * 16);
             { ProfScope _ps(h, st, "pyr_top_kernel");
-            pyr_top_kernel<KIND, T><<<tg, 256, 0, st>>>(top, U, bvh.nodes, lists[nl - 1]);
+            pyr_top_kernel<KIND, T><<<tg, 256, 0, st>>>(top, Ulev[nl - 1], bvh.nodes, lists[nl - 1]);
             }
             IBVH_LAUNCH_CHECK(h, "pyr_top_kernel");
         }
@@ -826,9 +946,9 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
         for (int l = nl - 1; l >= 1; --l) {
             { ProfScope _ps(h, st, "pyr_refine_kernel");
             if (h->cfg.pyr_tma)
-                pyr_refine_tma_kernel<KIND, T><<<grid, kPyrWarps * 32, 0, st>>>(U + plan.lv[l - 1].u_off, NT + plan.lv[l - 1].t_off, (uint32_t)plan.lv[l - 1].qg_first, (uint32_t)plan.lv[l - 1].nqg, (uint32_t)plan.lv[l - 1].ntg, lists[l], lists[l - 1], d_tick + l);
+                pyr_refine_tma_kernel<KIND, T><<<grid, kPyrWarps * 32, 0, st>>>(Ulev[l - 1], NTlev[l - 1], (uint32_t)plan.lv[l - 1].qg_first, (uint32_t)plan.lv[l - 1].nqg, (uint32_t)plan.lv[l - 1].ntg, lists[l], lists[l - 1], d_tick + l);
             else
-                pyr_refine_kernel<KIND, T><<<grid, kPyrWarps * 32, 0, st>>>(U + plan.lv[l - 1].u_off, NT + plan.lv[l - 1].t_off, (uint32_t)plan.lv[l - 1].qg_first, (uint32_t)plan.lv[l - 1].nqg, (uint32_t)plan.lv[l - 1].ntg, lists[l], lists[l - 1], d_tick + l);
+                pyr_refine_kernel<KIND, T><<<grid, kPyrWarps * 32, 0, st>>>(Ulev[l - 1], NTlev[l - 1], (uint32_t)plan.lv[l - 1].qg_first, (uint32_t)plan.lv[l - 1].nqg, (uint32_t)plan.lv[l - 1].ntg, lists[l], lists[l - 1], d_tick + l);
             }
             IBVH_LAUNCH_CHECK(h, "pyr_refine_kernel");
         }
@@ -1174,6 +1294,7 @@ int ibvh_destroy(ibvh_handle_t* h) {
     DeviceGuard g(h->device);
     if (h->ws) cudaFree(h->ws);
     if (h->aux) cudaFree(h->aux);
+    for (int k = 0; k < 2; ++k) if (h->sidecars[k].buf) cudaFree(h->sidecars[k].buf);
     if (h->d_small) cudaFree(h->d_small);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     if (h->side) cudaStreamDestroy(h->side);
@@ -1189,6 +1310,11 @@ int ibvh_release_workspace(ibvh_handle_t* h) {
     DeviceGuard g(h->device);
     if (h->ws) { IBVH_CUDA_TRY(h, cudaFree(h->ws)); h->ws = nullptr; h->ws_bytes = 0; }
     if (h->aux) { IBVH_CUDA_TRY(h, cudaFree(h->aux)); h->aux = nullptr; h->aux_bytes = 0; }
+    for (int k = 0; k < 2; ++k) {
+        ibvh_handle::Sidecar& sc = h->sidecars[k];
+        if (sc.buf) { IBVH_CUDA_TRY(h, cudaFree(sc.buf)); sc.buf = nullptr; sc.bytes = 0; }
+        sc.id = 0;
+    }
     return IBVH_OK;
 }
 
@@ -1246,6 +1372,8 @@ int ibvh_traverse_cancel(ibvh_handle_t* h) {
     if (e != cudaSuccess) { h->set_cuda_error(e, "cudaEventSynchronize(cancelled deferred traversal)"); return IBVH_ERR_CUDA; }
     return IBVH_OK;
 }
+
+uint64_t ibvh_last_build_id(ibvh_handle_t* h) { return h ? h->last_build_id : 0; }
 
 int ibvh_peer_last_counts(ibvh_handle_t* h, int64_t* counts, int32_t world) {
     if (!h || !counts || world < 1 || world > IBVH_MAX_PEERS) return IBVH_ERR_ARGUMENT;
@@ -1520,6 +1648,7 @@ int ibvh_traverse_single(ibvh_handle_t* h, const ibvh_bvh_t* bvh, const ibvh_tra
             a.flip = 0;
             a.peer = p->peer;
             a.positions = (p->flags & IBVH_TRAVERSE_POSITIONS) ? 1 : 0;
+            a.t_build_id = a.q_build_id = bvh->build_id;
             return traverse_leaf_queries<kSingle, L, L, N, I>(h, d.leaves, bvh->n, d, bvh->built_level, a, p->flags, d_counts, d_contacts, capacity, num_contacts, st);
         });
     });
@@ -1559,6 +1688,7 @@ int ibvh_traverse_pair(ibvh_handle_t* h, const ibvh_bvh_t* queries, const ibvh_b
             a.flip = p->flip ? 1 : 0;
             a.peer = p->peer;
             a.positions = (p->flags & IBVH_TRAVERSE_POSITIONS) ? 1 : 0;
+            a.t_build_id = target->build_id; a.q_build_id = queries->build_id;
             return traverse_leaf_queries<kPair, L, L, N, I>(h, (const L*)queries->d_leaves, queries->n, d, target->built_level, a, p->flags, d_counts, d_contacts, capacity, num_contacts, st);
         });
     });

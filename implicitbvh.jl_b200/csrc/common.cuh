@@ -413,6 +413,39 @@ inline TreeInfo make_tree_info(const ibvh_tree_t& t) {
     return ti;
 }
 
+// ---- 16-byte aligned records of the pyramid traversal (written by the build's sidecar and by the pack kernels) ----
+#ifdef __CUDACC__
+template <class T> IBVH_D BBox<T> empty_box() {
+    BBox<T> b;
+    const T inf = T(1) / T(0);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { b.lo[k] = inf; b.up[k] = -inf; }
+    return b;
+}
+
+// Records the pyramid kernels load with 128-bit accesses (the refine / tile kernels are bound by L1 wavefronts,
+// not by DRAM: AoS structs read as 8-byte pieces at a 24-byte stride cost 3-7x the wavefronts of aligned
+// 16-byte loads). UBox = one query-pyramid box, Packed<V> = one leaf volume, both padded to 16 bytes.
+template <class T> struct alignas(16) UBox { BBox<T> b; };
+template <class V> struct alignas(16) Packed { V v; };
+template <class R> IBVH_D R load16(const R* p) {
+    static_assert(sizeof(R) % 16 == 0, "16-byte records");
+    alignas(16) R out;
+    const uint4* s = reinterpret_cast<const uint4*>(p);
+    uint4* d = reinterpret_cast<uint4*>(&out);
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(R) / 16); ++k) d[k] = __ldg(s + k);
+    return out;
+}
+template <class R> IBVH_D void store16(R* p, const R& v) {
+    const uint4* s = reinterpret_cast<const uint4*>(&v);
+    uint4* d = reinterpret_cast<uint4*>(p);
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(R) / 16); ++k) d[k] = s[k];
+}
+
+#endif  // __CUDACC__
+
 // CUDA error plumbing
 #define IBVH_CUDA_TRY(h, expr)                                                     \
     do {                                                                           \

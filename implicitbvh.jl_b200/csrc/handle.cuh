@@ -58,6 +58,28 @@ struct ibvh_handle {
         return IBVH_OK;
     }
 
+    // Sidecar of a build (round 2): what the pyramid traversal used to re-derive from the tree on EVERY call — the leaf
+    // volumes as 16-byte records, the refinement's node levels in 64-byte aligned runs, the three finest levels of the
+    // query pyramid — is written once by the build's own gather / merge kernels (they hold the data in registers /
+    // shared memory anyway) into library-owned memory, tagged with a build id the caller hands back in ibvh_bvh_t.
+    // Two slots (a pair traversal needs the sidecars of two trees); a traversal whose id matches neither packs on the fly.
+    struct Sidecar {
+        unsigned long long id = 0;             // 0 = empty
+        long long n = 0;
+        int leaf_kind = 0, float_bytes = 0, built_level = 0, levels = 0;
+        char* buf = nullptr;                   // grow-only
+        size_t bytes = 0;
+        size_t pt_off = 0, nt_off = 0, u_off = 0;      // byte offsets of the packed volumes, aligned node levels, query pyramid
+        int u_levels = 0;                      // pyramid levels present (<= 3)
+    } sidecars[2];
+    unsigned long long next_build_id = 1, last_build_id = 0;
+    int side_next = 0;
+    Sidecar* find_sidecar(unsigned long long id, long long n) {
+        if (id == 0) return nullptr;
+        for (int k = 0; k < 2; ++k) if (sidecars[k].id == id && sidecars[k].n == n) return &sidecars[k];
+        return nullptr;
+    }
+
     // pyramid schedule: learned list-capacity factor (pairs per query group), see traverse_pyramid
     double pyr_factor = 0.0;
     long long stash_hint = 0;     // contact total of the last ordered pyramid traversal (sizes the hit stash of the next one)

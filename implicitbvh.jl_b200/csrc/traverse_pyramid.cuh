@@ -86,35 +86,6 @@ IBVH_D uint32_t pyr_chunk_steps(uint32_t count, int slots) {
 IBVH_D void atomic_inc(int32_t* p) { atomicAdd(p, 1); }
 IBVH_D void atomic_inc(int64_t* p) { atomicAdd(reinterpret_cast<unsigned long long*>(p), 1ull); }
 
-template <class T> IBVH_D BBox<T> empty_box() {
-    BBox<T> b;
-    const T inf = T(1) / T(0);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { b.lo[k] = inf; b.up[k] = -inf; }
-    return b;
-}
-
-// Records the pyramid kernels load with 128-bit accesses (the refine / tile kernels are bound by L1 wavefronts,
-// not by DRAM: AoS structs read as 8-byte pieces at a 24-byte stride cost 3-7x the wavefronts of aligned
-// 16-byte loads). UBox = one query-pyramid box, Packed<V> = one leaf volume, both padded to 16 bytes.
-template <class T> struct alignas(16) UBox { BBox<T> b; };
-template <class V> struct alignas(16) Packed { V v; };
-template <class R> IBVH_D R load16(const R* p) {
-    static_assert(sizeof(R) % 16 == 0, "16-byte records");
-    alignas(16) R out;
-    const uint4* s = reinterpret_cast<const uint4*>(p);
-    uint4* d = reinterpret_cast<uint4*>(&out);
-#pragma unroll
-    for (int k = 0; k < (int)(sizeof(R) / 16); ++k) d[k] = __ldg(s + k);
-    return out;
-}
-template <class R> IBVH_D void store16(R* p, const R& v) {
-    const uint4* s = reinterpret_cast<const uint4*>(&v);
-    uint4* d = reinterpret_cast<uint4*>(p);
-#pragma unroll
-    for (int k = 0; k < (int)(sizeof(R) / 16); ++k) d[k] = s[k];
-}
-
 // ---- TMA bulk copies + mbarrier (sm_90+ PTX; SASS: UBLKCP / SYNCS) -----------------------------------------------
 // One lane arms the warp's mbarrier with the bytes it expects (arrive.expect_tx) and issues
 // cp.async.bulk.shared::cluster.global: the copy engine moves whole 16-byte-aligned runs from global to shared memory
@@ -202,8 +173,9 @@ __global__ void __launch_bounds__(256) pyr_pack_groups_kernel(const L* __restric
 }
 
 // ---- 1. query pyramid ------------------------------------------------------------------------------------
+// Uf / Uc: the fine / coarse level's boxes, index = group - level.qg_first (the fine level may live in a build's sidecar)
 template <class T>
-__global__ void __launch_bounds__(256) pyr_up_kernel(PyrLevel fine, PyrLevel coarse, UBox<T>* __restrict__ U) {
+__global__ void __launch_bounds__(256) pyr_up_kernel(PyrLevel fine, PyrLevel coarse, const UBox<T>* __restrict__ Uf, UBox<T>* __restrict__ Uc) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= coarse.nqg) return;
     const int64_t c0 = (coarse.qg_first + t) << kPyrFan;
@@ -211,9 +183,9 @@ __global__ void __launch_bounds__(256) pyr_up_kernel(PyrLevel fine, PyrLevel coa
 #pragma unroll
     for (int i = 0; i < (1 << kPyrFan); ++i) {
         int64_t c = c0 + i - fine.qg_first;
-        if (c >= 0 && c < fine.nqg) u = merge(u, load16(U + fine.u_off + c).b);
+        if (c >= 0 && c < fine.nqg) u = merge(u, load16(Uf + c).b);
     }
-    U[coarse.u_off + t].b = u;
+    Uc[t].b = u;
 }
 
 // warp-aggregated direct append (top kernel)
@@ -232,6 +204,7 @@ IBVH_D void pyr_append_direct(const PairList& out, bool pred, uint2 e) {
 
 // ---- 2. top: all pairs ---------------------------------------------------------------------------------------
 template <int KIND, class T>
+// U: the top level's boxes, index = group - lv.qg_first
 __global__ void __launch_bounds__(256) pyr_top_kernel(PyrLevel lv, const UBox<T>* __restrict__ U, const BBox<T>* __restrict__ nodes, PairList out) {
     const int64_t total = lv.nqg * lv.ntg;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -245,7 +218,7 @@ __global__ void __launch_bounds__(256) pyr_top_kernel(PyrLevel lv, const UBox<T>
             bool ok = true;
             if constexpr (KIND == kSingle) ok = b >= A;           // the target group must reach right of the query group
             if (ok) {
-                BBox<T> u = load16(U + lv.u_off + a).b;
+                BBox<T> u = load16(U + a).b;
                 BBox<T> nb = load_struct(nodes + lv.tnode0 + b);
                 pred = iscontact(u, nb);
                 e = make_uint2((uint32_t)A, (uint32_t)b);

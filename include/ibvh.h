@@ -89,6 +89,13 @@ typedef struct ibvh_bvh {
     int64_t n;                /* number of leaves                                            */
     int64_t built_level;      /* level up to which nodes are valid                           */
     ibvh_types_t types;
+    uint64_t build_id;        /* 0, or the value ibvh_last_build_id returned right after the ibvh_build that produced
+                                 these arrays: the library then reuses what that build left in its own memory for the
+                                 traversal (the leaf volumes as aligned records, aligned copies of the node levels, the
+                                 finest query-pyramid levels) instead of re-deriving it from the arrays on every call.
+                                 Purely an accelerator: with 0, a stale id or arrays from elsewhere the traversal packs
+                                 on the fly and returns the same result. The caller must not modify leaves / nodes
+                                 between the build and a traversal that passes its id. */
 } ibvh_bvh_t;
 
 /* Traversal flags */
@@ -224,6 +231,10 @@ IBVH_API int ibvh_build(ibvh_handle_t* h, const void* d_volumes, void* d_leaves,
  * IBVH_TRAVERSE_REFERENCE_SHAPED. BSphere{Float32} / Int32 / UInt32 / BBox{Float32} only (else IBVH_ERR_UNSUPPORTED). */
 IBVH_API int ibvh_build_reference_shaped(ibvh_handle_t* h, const void* d_volumes, void* d_leaves, int64_t n,
                                 const ibvh_types_t* types, void* d_nodes, int64_t built_level, void* stream);
+
+/* Id of the sidecar the last successful ibvh_build on this handle left behind (0 = none: not a pyramid-eligible tree,
+ * or sidecars disabled). Store it with the BVH and pass it in ibvh_bvh_t.build_id. The handle keeps the two newest. */
+IBVH_API uint64_t ibvh_last_build_id(ibvh_handle_t* h);
 
 /* ---- LVT traversals ------------------------------------------------------------------------ */
 /* Common output protocol (replaces the count -> accumulate -> allocate -> write sequence of

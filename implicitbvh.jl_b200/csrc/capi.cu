@@ -846,7 +846,10 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
             }
         }
         const int q_ulevels = scq ? std::min(nl, same_leaves ? lay_t.u_levels : lay_q.u_levels) : 0;
+        // refine over conservatively quantised boxes (traverse_pyramid.cuh, 3a): needs the target's root box as the frame
+        const bool quant = h->cfg.pyr_quant && !h->cfg.pyr_tma && ta.t_built_level == 1 && nl >= 2;
         size_t bytes = ibvh_handle::padded((size_t)plan.u_total * sizeof(UBox<T>)) +
+                       (quant ? ibvh_handle::padded((size_t)plan.u_total * sizeof(QBoxU)) + ibvh_handle::padded((size_t)plan.t_total * sizeof(QBoxT)) : 0) +
                        (sct ? 0 : ibvh_handle::padded((size_t)plan.t_total * sizeof(N)) + ibvh_handle::padded((size_t)(bvh.ti.n + 8) * sizeof(Packed<VT>))) +
                        ((same_leaves || scq) ? 0 : ibvh_handle::padded((size_t)(n_query_total + 8) * sizeof(Packed<VQ>))) +
                        (stash_mode ? ibvh_handle::padded((size_t)stash_cap * sizeof(uint4)) : 0);
@@ -862,6 +865,11 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
         if (rc != IBVH_OK) return rc;
         char* ap = h->aux;
         UBox<T>* U = (UBox<T>*)ap; ap += ibvh_handle::padded((size_t)plan.u_total * sizeof(UBox<T>));
+        QBoxU* Uq = nullptr; QBoxT* NTq = nullptr;
+        if (quant) {
+            Uq = (QBoxU*)ap; ap += ibvh_handle::padded((size_t)plan.u_total * sizeof(QBoxU));
+            NTq = (QBoxT*)ap; ap += ibvh_handle::padded((size_t)plan.t_total * sizeof(QBoxT));
+        }
         N* NT = nullptr;                                             // aligned copy of the target node levels
         Packed<VT>* PT = nullptr;
         if (sct) {
@@ -943,9 +951,23 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
             IBVH_LAUNCH_CHECK(h, "pyr_top_kernel");
         }
         // 3. refine down to the 4-leaf groups
+        if (quant) {
+            // the fine levels of every refinement step as 15-bit integer boxes in the frame of the target's root box
+            for (int l = 0; l + 1 < nl; ++l) {
+                const PyrLevel& v = plan.lv[l];
+                { ProfScope _ps(h, st, "pyr_quantize_kernel");
+                pyr_quantize_kernel<T, UBox<T>, QBoxU><<<(unsigned)((v.nqg + 255) / 256), 256, 0, st>>>(Ulev[l], v.nqg, bvh.nodes, Uq + v.u_off);
+                const int64_t nt_pad = (v.ntg + 7) & ~int64_t(7);
+                pyr_quantize_kernel<T, N, QBoxT><<<(unsigned)((nt_pad + 255) / 256), 256, 0, st>>>(NTlev[l], nt_pad, bvh.nodes, NTq + v.t_off);
+                }
+                IBVH_LAUNCH_CHECK(h, "pyr_quantize_kernel");
+            }
+        }
         for (int l = nl - 1; l >= 1; --l) {
             { ProfScope _ps(h, st, "pyr_refine_kernel");
-            if (h->cfg.pyr_tma)
+            if (quant)
+                pyr_refine_q_kernel<KIND><<<grid, kPyrWarps * 32, 0, st>>>(Uq + plan.lv[l - 1].u_off, NTq + plan.lv[l - 1].t_off, (uint32_t)plan.lv[l - 1].qg_first, (uint32_t)plan.lv[l - 1].nqg, (uint32_t)plan.lv[l - 1].ntg, lists[l], lists[l - 1], d_tick + l);
+            else if (h->cfg.pyr_tma)
                 pyr_refine_tma_kernel<KIND, T><<<grid, kPyrWarps * 32, 0, st>>>(Ulev[l - 1], NTlev[l - 1], (uint32_t)plan.lv[l - 1].qg_first, (uint32_t)plan.lv[l - 1].nqg, (uint32_t)plan.lv[l - 1].ntg, lists[l], lists[l - 1], d_tick + l);
             else
                 pyr_refine_kernel<KIND, T><<<grid, kPyrWarps * 32, 0, st>>>(Ulev[l - 1], NTlev[l - 1], (uint32_t)plan.lv[l - 1].qg_first, (uint32_t)plan.lv[l - 1].nqg, (uint32_t)plan.lv[l - 1].ntg, lists[l], lists[l - 1], d_tick + l);
@@ -1649,6 +1671,7 @@ int ibvh_traverse_single(ibvh_handle_t* h, const ibvh_bvh_t* bvh, const ibvh_tra
             a.peer = p->peer;
             a.positions = (p->flags & IBVH_TRAVERSE_POSITIONS) ? 1 : 0;
             a.t_build_id = a.q_build_id = bvh->build_id;
+            a.t_built_level = bvh->built_level;
             return traverse_leaf_queries<kSingle, L, L, N, I>(h, d.leaves, bvh->n, d, bvh->built_level, a, p->flags, d_counts, d_contacts, capacity, num_contacts, st);
         });
     });
@@ -1689,6 +1712,7 @@ int ibvh_traverse_pair(ibvh_handle_t* h, const ibvh_bvh_t* queries, const ibvh_b
             a.peer = p->peer;
             a.positions = (p->flags & IBVH_TRAVERSE_POSITIONS) ? 1 : 0;
             a.t_build_id = target->build_id; a.q_build_id = queries->build_id;
+            a.t_built_level = target->built_level;
             return traverse_leaf_queries<kPair, L, L, N, I>(h, (const L*)queries->d_leaves, queries->n, d, target->built_level, a, p->flags, d_counts, d_contacts, capacity, num_contacts, st);
         });
     });

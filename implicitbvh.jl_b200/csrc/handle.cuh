@@ -23,6 +23,7 @@ struct ibvh_handle {
         bool force_wide_lookback = false;     // IBVH_SORT_WIDE_LOOKBACK: 64-bit look-back words at any size (tests the n >= 2^30 path)
         bool no_sidecar = false;              // IBVH_NO_SIDECAR: the build does not keep the traversal's packed records
         int pyr_grid = 20;                    // IBVH_PYR_GRID: CTAs per SM of the refine / tile kernels
+        bool pyr_quant = true;                // IBVH_PYR_QUANT=0: refine over the float boxes instead of the conservatively quantised ones
         bool pyr_tma = false;                 // IBVH_PYR_TMA=1: refine kernel with TMA bulk copies + mbarrier instead of LDG -> STS (measured slower: see traverse_pyramid.cuh)
         int fused_flush = -1;                 // IBVH_FUSED_FLUSH: buffered contacts per output reservation in fused mode
         void parse() {
@@ -35,6 +36,7 @@ struct ibvh_handle {
             force_wide_lookback = on("IBVH_SORT_WIDE_LOOKBACK");
             no_sidecar = on("IBVH_NO_SIDECAR");
             pyr_tma = on("IBVH_PYR_TMA");
+            if (const char* v = getenv("IBVH_PYR_QUANT")) pyr_quant = !(v[0] == '0' && v[1] == '\0');
             if (const char* v = getenv("IBVH_PYR_GRID")) { int g = atoi(v); if (g > 0) pyr_grid = g; }
             if (const char* v = getenv("IBVH_FUSED_FLUSH")) fused_flush = atoi(v);
         }

@@ -49,7 +49,7 @@ struct TraverseArgs {
     const ibvh_peer_t* peer;     // fused traversal + all-gather over peer memory (pyramid schedule, unordered), else nullptr
     int32_t positions;           // IBVH_TRAVERSE_POSITIONS: report 1-based leaf POSITIONS in the sorted arrays instead of .index
     unsigned long long t_build_id, q_build_id;   // ibvh_bvh_t.build_id of the target / query tree (0 = none): selects a build's sidecar
-    int64_t q_built_level;       // built_level of the query tree (pair traversal; layout of its sidecar)
+    int64_t t_built_level;       // built_level of the target tree
 };
 
 // 8-byte vectorised struct loads (volumes are 8-byte aligned by layout; see common.cuh)

@@ -382,6 +382,180 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_refine_kernel(const UBox<T
     if (nbuf) flush(nbuf);
 }
 
+// ---- 3a. refine over conservatively quantised boxes -------------------------------------------------------------------
+// The refinement levels only PRUNE: any test that never rejects a pair of overlapping boxes keeps the result exact (the
+// leaf tiles evaluate the reference's predicate itself). So the refine kernel need not see the float boxes: it reads
+// 15-bit integer boxes in the frame of the target tree's root box, rounded OUTWARDS (lo down, up up, clamped — every
+// step monotone, hence conservative whatever the frame), packed so that ONE box test is three 32-bit subtractions:
+//   target box  B' = (lo.x, lo.y | lo.z, M - up.x | M - up.y, M - up.z)          two 15-bit fields per word, M = 32767
+//   query box   A' = (up.x, up.y | up.z, M - lo.x | M - lo.y, M - lo.z)  | G     G = 0x80008000: a guard bit above each field
+//   overlap  <=>  every field of A' >= the same field of B'  <=>  no guard bit borrows in (A' | G) - B'
+// 12 bytes per target box instead of 24 and 16 instead of 32 per query box: the 8 children of a target group are 6
+// LDS.128 per lane instead of 12, one LDG.128 + STS.128 per slot lane instead of two, and a test is 3 IADD + 2 LOP3
+// instead of 6 FSETP + SEL. ncu had the float kernel at 93 % of the LSU data pipe (shared-memory wavefronts).
+struct QBoxT { uint32_t w[3]; };
+struct alignas(16) QBoxU { uint32_t w[3]; uint32_t pad; };
+constexpr uint32_t kQGuard = 0x80008000u;
+constexpr float kQMax = 32767.0f;
+
+template <class T> IBVH_D uint32_t quant_down(T v, T origin, T scale) {
+    T x = floor((v - origin) * scale);
+    if (!(x > T(0))) x = T(0);                    // (also NaN)
+    if (x > T(kQMax)) x = T(kQMax);
+    return (uint32_t)x;
+}
+template <class T> IBVH_D uint32_t quant_up(T v, T origin, T scale) {
+    T x = ceil((v - origin) * scale);
+    if (!(x > T(0))) x = T(0);
+    if (x > T(kQMax)) x = T(kQMax);
+    return (uint32_t)x;
+}
+// SRC = BBox<T> (aligned node copy -> QBoxT) or UBox<T> (query pyramid -> QBoxU); root = the target tree's root box
+template <class T, class SRC, class DST>
+__global__ void __launch_bounds__(256) pyr_quantize_kernel(const SRC* __restrict__ src, int64_t n, const BBox<T>* __restrict__ root, DST* __restrict__ dst) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const BBox<T> r = load_struct(root);
+    BBox<T> b;
+    if constexpr (std::is_same<SRC, BBox<T>>::value) b = load_struct(src + i); else b = load16(src + i).b;
+    uint32_t lo[3], up[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const T scale = T(kQMax) / (r.up[k] - r.lo[k]);
+        lo[k] = quant_down(b.lo[k], r.lo[k], scale);
+        up[k] = quant_up(b.up[k], r.lo[k], scale);
+    }
+    const uint32_t M = 32767u;
+    if constexpr (std::is_same<DST, QBoxT>::value) {
+        dst[i].w[0] = lo[0] | (lo[1] << 16);
+        dst[i].w[1] = lo[2] | ((M - up[0]) << 16);
+        dst[i].w[2] = (M - up[1]) | ((M - up[2]) << 16);
+    } else {
+        dst[i].w[0] = (up[0] | (up[1] << 16)) | kQGuard;
+        dst[i].w[1] = (up[2] | ((M - lo[0]) << 16)) | kQGuard;
+        dst[i].w[2] = ((M - lo[1]) | ((M - lo[2]) << 16)) | kQGuard;
+        dst[i].pad = 0u;
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(kPyrWarps * 32) pyr_refine_q_kernel(const QBoxU* __restrict__ Uf, const QBoxT* __restrict__ Nf,
+                                                                     uint32_t f_first, uint32_t f_nqg, uint32_t f_ntg,
+                                                                     PairList in, PairList out, uint32_t* ticket) {
+    constexpr int F = 1 << kPyrFan;          // 8
+    constexpr int SLOTS = 32 / F;            // 4 pairs per warp step
+    constexpr int PIECES = F * (int)sizeof(QBoxT) / 16;                   // 6 sixteen-byte pieces = the 8 child boxes of one target group
+    constexpr int SLOT_BYTES = F * (int)sizeof(QBoxT) + 16;               // 112: the four slots start in different banks
+    static_assert(F == 8 && sizeof(QBoxT) == 12 && PIECES <= F, "piece mapping");
+    __shared__ __align__(16) unsigned char s_raw[kPyrWarps][SLOTS][SLOT_BYTES];
+    __shared__ uint2 s_buf[kPyrWarps][32 * F + kPyrFlush];
+    __shared__ uint32_t s_n[kPyrWarps];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int slot = lane / F, i = lane % F;
+    if (lane == 0) s_n[w] = 0;
+    __syncwarp();
+    unsigned long long count64 = *in.count;
+    if (count64 > in.cap) count64 = in.cap;
+    const uint32_t count = (uint32_t)count64;
+    uint32_t nbuf = 0;
+    auto flush = [&](uint32_t n) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(out.count, (unsigned long long)n);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const uint32_t b0 = nbuf - n;
+        for (uint32_t k = lane; k < n; k += 32) if (base + k < out.cap) out.data[base + k] = s_buf[w][b0 + k];
+        nbuf = b0;
+    };
+    struct Stage { uint32_t Ac, Bc0; bool a_ok; uint4 u; uint4 tp; };
+    auto fetch = [&](uint2 pr, bool have) -> Stage {
+        Stage sg;
+        sg.Ac = (pr.x << kPyrFan) + (uint32_t)i;
+        sg.Bc0 = pr.y << kPyrFan;
+        const uint32_t ua = sg.Ac - f_first;                               // wraps to a huge value if Ac < f_first
+        sg.a_ok = have && ua < f_nqg;
+        sg.u = __ldg(reinterpret_cast<const uint4*>(Uf + min(ua, f_nqg - 1u)));
+        sg.tp = make_uint4(0u, 0u, 0u, 0u);
+        if (i < PIECES) sg.tp = __ldg(reinterpret_cast<const uint4*>(Nf + sg.Bc0) + i);     // (the copy is padded to whole groups)
+        return sg;
+    };
+    volatile uint32_t* s_nv = s_n;
+    auto process = [&](const Stage& cur) {
+        if (i < PIECES) reinterpret_cast<uint4*>(s_raw[w][slot])[i] = cur.tp;
+        __syncwarp();
+        uint32_t hits = 0;
+        if (cur.a_ok) {
+            const uint4* sp = reinterpret_cast<const uint4*>(s_raw[w][slot]);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {                                  // 3 pieces = 4 boxes
+                const uint4 p0 = sp[3 * q], p1 = sp[3 * q + 1], p2 = sp[3 * q + 2];
+                const uint32_t bw[12] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t r = (cur.u.x - bw[3 * j]) & (cur.u.y - bw[3 * j + 1]) & (cur.u.z - bw[3 * j + 2]);
+                    if ((r & kQGuard) == kQGuard) hits |= 1u << (4 * q + j);
+                }
+            }
+            bool edge = cur.Bc0 + (uint32_t)F > f_ntg;
+            if constexpr (KIND == kSingle) edge = edge || cur.Ac > cur.Bc0;
+            if (edge) {
+                const uint32_t nval = f_ntg - cur.Bc0;
+                uint32_t allowed = nval >= (uint32_t)F ? ((1u << F) - 1u) : ((1u << nval) - 1u);
+                if constexpr (KIND == kSingle) {
+                    if (cur.Ac > cur.Bc0) {                                  // child j admissible iff Bc0 + j >= Ac
+                        const uint32_t lo = cur.Ac - cur.Bc0;
+                        allowed &= lo >= (uint32_t)F ? 0u : ~((1u << lo) - 1u);
+                    }
+                }
+                hits &= allowed;
+            }
+        }
+        if (hits) {
+            uint32_t wpos = atomicAdd(&s_n[w], (uint32_t)__popc(hits));
+            do {
+                const int j = __ffs(hits) - 1;
+                hits &= hits - 1;
+                s_buf[w][wpos++] = make_uint2(cur.Ac, cur.Bc0 + (uint32_t)j);
+            } while (hits);
+        }
+        __syncwarp();
+        nbuf = s_nv[w];
+        if (nbuf >= (uint32_t)kPyrFlush) { flush(nbuf & ~31u); if (lane == 0) s_nv[w] = nbuf; }
+        __syncwarp();
+    };
+    const uint32_t chunk = SLOTS * pyr_chunk_steps(count, SLOTS);
+    for (;;) {
+        uint32_t c = 0;
+        if (lane == 0) c = atomicAdd(ticket, 1u);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        const unsigned long long base64 = (unsigned long long)c * chunk;
+        if (base64 >= count) break;
+        const uint32_t base = (uint32_t)base64;
+        const uint32_t end = count - base > chunk ? base + chunk : count;
+        uint32_t p = base + slot;
+        uint2 e1 = make_uint2(0u, 0u), e2 = make_uint2(0u, 0u);
+        if (p < end) e1 = in.data[p];
+        if (p + SLOTS < end) e2 = in.data[p + SLOTS];
+        auto next_entry = [&]() {
+            uint2 e = make_uint2(0u, 0u);
+            if (p + 2 * SLOTS < end) e = in.data[p + 2 * SLOTS];
+            return e;
+        };
+        Stage sa = fetch(e1, p < end), sb;
+        for (uint32_t p0 = base; p0 < end;) {
+            sb = fetch(e2, p + SLOTS < end);
+            e2 = next_entry();
+            process(sa);
+            p0 += SLOTS; p += SLOTS;
+            if (p0 >= end) break;
+            sa = fetch(e2, p + SLOTS < end);
+            e2 = next_entry();
+            process(sb);
+            p0 += SLOTS; p += SLOTS;
+        }
+    }
+    if (nbuf) flush(nbuf);
+}
+
 // ---- 3b. refine, TMA form ------------------------------------------------------------------------------------------
 // Same work, same pair lists as pyr_refine_kernel. Per warp step (4 pairs) ONE lane arms the stage's mbarrier and four
 // lanes issue two bulk copies each: the 8 child boxes of B (one aligned run of F * sizeof(N) bytes in the aligned node

@@ -84,6 +84,7 @@ SIGNATURES = {
     "ibvh_traverse_cancel": (_ci, [_vp]),
     "ibvh_last_build_id": (C.c_uint64, [_vp]),
     "ibvh_peer_last_counts": (_ci, [_vp, C.POINTER(_i64), C.c_int32]),
+    "ibvh_peer_compact_plan": (_ci, [C.c_int32, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), C.c_int32]),
     "ibvh_allgather_pairs": (_ci, [_vp, C.POINTER(Peer), _vp, _i64, C.c_int32, C.POINTER(_i64), C.POINTER(_i64), _vp]),
 }
 

@@ -48,7 +48,7 @@ template <class V, class N> struct SideOut {
 template <class L, class SRC>
 __global__ void __launch_bounds__(256) gather_kernel(const SRC* __restrict__ src, const uint32_t* __restrict__ perm,
                                                     const typename L::mor_t* __restrict__ keys_sorted, L* __restrict__ leaves, int64_t n, int vec,
-                                                    Packed<typename L::vol_t>* __restrict__ packed) {
+                                                    Packed<typename L::vol_t>* __restrict__ packed, typename L::idx_t* __restrict__ idx_out) {
     constexpr int PER = 4;
     const int64_t base = ((int64_t)blockIdx.x * blockDim.x) * PER + threadIdx.x;
     uint32_t pp[PER];
@@ -77,6 +77,7 @@ __global__ void __launch_bounds__(256) gather_kernel(const SRC* __restrict__ src
                 r.v = words_volume<L>(wv[u]);
                 store16(packed + i, r);
             }
+            if (idx_out) idx_out[i] = words_index<L>(wv[u]);      // sidecar: the indices alone (4 / 8 bytes per leaf: L2-resident at 10 M)
         }
     }
     if (packed && blockIdx.x == 0 && threadIdx.x < 8) {      // NaN records past the end: no bounds masks on the target side

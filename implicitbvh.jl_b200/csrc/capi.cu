@@ -166,7 +166,7 @@ template <class L, class N> struct SidecarLayout {
     using V = typename L::vol_t;
     using T = typename N::value_type;
     PyrPlan plan;                 // the full-range plan (q = [0, n))
-    size_t pt_off, nt_off, u_off, bytes;
+    size_t pt_off, nt_off, u_off, idx_off, bytes;
     int u_levels;
     int64_t u_level_off[3], u_level_n[3];
     bool ok;
@@ -191,6 +191,7 @@ template <class L, class N> SidecarLayout<L, N> sidecar_layout(const TreeInfo& t
         uo += groups + (int64_t(2) << kPyrFan);
     }
     off += ibvh_handle::padded((size_t)uo * sizeof(UBox<typename N::value_type>));
+    s.idx_off = off; off += ibvh_handle::padded((size_t)ti.n * sizeof(typename L::idx_t));
     s.bytes = off;
     s.ok = true;
     return s;
@@ -358,6 +359,7 @@ int build_impl(ibvh_handle* h, const void* d_volumes, void* d_leaves, int64_t n,
     h->last_build_id = 0;
     SideOut<V, N> so{};
     SideLevels<N> sl{};
+    typename L::idx_t* side_idx = nullptr;
     ibvh_handle::Sidecar* sc = nullptr;
     if (!h->cfg.no_sidecar && !h->cfg.fused_gather && tree.real_nodes >= 2) {
         SidecarLayout<L, N> lay = sidecar_layout<L, N>(ti, built_level);
@@ -375,6 +377,8 @@ int build_impl(ibvh_handle* h, const void* d_volumes, void* d_leaves, int64_t n,
         if (sc) {
             sc->n = n; sc->leaf_kind = V::kind; sc->float_bytes = (int)sizeof(typename L::value_type); sc->built_level = (int)built_level; sc->levels = (int)tree.levels;
             sc->pt_off = lay.pt_off; sc->nt_off = lay.nt_off; sc->u_off = lay.u_off; sc->u_levels = lay.u_levels;
+            sc->idx_off = lay.idx_off; sc->index_bytes = (int)sizeof(typename L::idx_t);
+            side_idx = (typename L::idx_t*)(sc->buf + lay.idx_off);
             so.pt = (Packed<V>*)(sc->buf + lay.pt_off);
             for (int l = 0; l + 1 < lay.plan.n; ++l) {               // (the top level is read straight from the caller's nodes)
                 const int tl = lay.plan.lv[l].tree_level;
@@ -395,8 +399,8 @@ int build_impl(ibvh_handle* h, const void* d_volumes, void* d_leaves, int64_t n,
         { ProfScope _ps(h, st, "gather_kernel");
         const uintptr_t va = (uintptr_t)d_volumes;
         const int vec = va % 16 == 0 ? 16 : (va % 8 == 0 ? 8 : 4);
-        if (wrap) gather_kernel<L, V><<<gb, 256, 0, st>>>((const V*)d_volumes, perm, keys_sorted, (L*)d_leaves, n, vec, so.pt);
-        else gather_kernel<L, L><<<gb, 256, 0, st>>>((const L*)s.copy, perm, keys_sorted, (L*)d_leaves, n, 8, so.pt);
+        if (wrap) gather_kernel<L, V><<<gb, 256, 0, st>>>((const V*)d_volumes, perm, keys_sorted, (L*)d_leaves, n, vec, so.pt, side_idx);
+        else gather_kernel<L, L><<<gb, 256, 0, st>>>((const L*)s.copy, perm, keys_sorted, (L*)d_leaves, n, 8, so.pt, side_idx);
         }
         IBVH_LAUNCH_CHECK(h, "gather_kernel");
         rc = launch_gather_merge<L, L, N, false>(h, (const L*)nullptr, nullptr, nullptr, (L*)d_leaves, (N*)d_nodes, ti, stop_level, st, &so);
@@ -879,6 +883,10 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
             NT = (N*)ap; ap += ibvh_handle::padded((size_t)plan.t_total * sizeof(N));
             PT = (Packed<VT>*)ap; ap += ibvh_handle::padded((size_t)(bvh.ti.n + 8) * sizeof(Packed<VT>));
         }
+        // compact leaf-index arrays of the sidecars (else the kernels fetch .index from the 24 / 32-byte leaf structs: two
+        // random 32-byte sectors per contact, 2.5 GB of the tile kernel's 3.2 GB of DRAM traffic at 10 M leaves)
+        const I* TIDX = (sct && sct->index_bytes == (int)sizeof(I)) ? (const I*)(sct->buf + lay_t.idx_off) : nullptr;
+        const I* QIDX = same_leaves ? TIDX : ((scq && scq->index_bytes == (int)sizeof(I)) ? (const I*)(scq->buf + lay_q.idx_off) : nullptr);
         Packed<VQ>* PQ = (Packed<VQ>*)PT;
         if (!same_leaves) {
             if (scq) PQ = (Packed<VQ>*)(scq->buf + lay_q.pt_off);
@@ -1007,7 +1015,7 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
                 if (rcw != IBVH_OK) return rcw;
             }
             { ProfScope _ps(h, st, "pyr_leaf_tile_kernel");
-            pyr_leaf_tile_kernel<KIND, kAtomic, 0, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], pflip, capacity, out_total, (I*)nullptr, nullptr, out_ptr, 1, d_tick + 16 + (tile_launch++), PQ, PT);
+            pyr_leaf_tile_kernel<KIND, kAtomic, 0, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], pflip, capacity, out_total, (I*)nullptr, nullptr, out_ptr, 1, d_tick + 16 + (tile_launch++), PQ, PT, QIDX, TIDX);
             }
             IBVH_LAUNCH_CHECK(h, "pyr_leaf_tile_kernel");
             return fused_finish();
@@ -1016,20 +1024,20 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
         if (unordered || count_only) {
             if (unordered) {
                 { ProfScope _ps(h, st, "pyr_leaf_tile_kernel");
-                pyr_leaf_tile_kernel<KIND, kAtomic, 0, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], pflip, capacity, out_total, (I*)nullptr, nullptr, out_ptr, fused ? 1 : 0, d_tick + 16 + (tile_launch++), PQ, PT);
+                pyr_leaf_tile_kernel<KIND, kAtomic, 0, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], pflip, capacity, out_total, (I*)nullptr, nullptr, out_ptr, fused ? 1 : 0, d_tick + 16 + (tile_launch++), PQ, PT, QIDX, TIDX);
                 }
             } else if (d_counts) {
                 // count-only call of the ordered protocol: per-query counts + scan (cache2), total from the scan
                 IBVH_CUDA_TRY(h, cudaMemsetAsync(counts, 0, (size_t)ta.q_count * sizeof(I), st));
                 { ProfScope _ps(h, st, "pyr_leaf_tile_kernel");
-                pyr_leaf_tile_kernel<KIND, kCount, 1, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], pflip, 0, d_total, counts, nullptr, (IndexPair<I>*)nullptr, 0, d_tick + 16 + (tile_launch++), PQ, PT);
+                pyr_leaf_tile_kernel<KIND, kCount, 1, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], pflip, 0, d_total, counts, nullptr, (IndexPair<I>*)nullptr, 0, d_tick + 16 + (tile_launch++), PQ, PT, QIDX, TIDX);
                 }
                 IBVH_LAUNCH_CHECK(h, "pyr_leaf_tile_kernel");
                 rc = scan_counts<I>(h, counts, ta.q_count, qsums, d_total, st);
                 if (rc != IBVH_OK) return rc;
             } else {
                 { ProfScope _ps(h, st, "pyr_leaf_tile_kernel");
-                pyr_leaf_tile_kernel<KIND, kCount, 0, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], pflip, 0, d_total, (I*)nullptr, nullptr, (IndexPair<I>*)nullptr, 0, d_tick + 16 + (tile_launch++), PQ, PT);
+                pyr_leaf_tile_kernel<KIND, kCount, 0, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], pflip, 0, d_total, (I*)nullptr, nullptr, (IndexPair<I>*)nullptr, 0, d_tick + 16 + (tile_launch++), PQ, PT, QIDX, TIDX);
                 }
             }
             IBVH_LAUNCH_CHECK(h, "pyr_leaf_tile_kernel");
@@ -1037,9 +1045,9 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
             IBVH_CUDA_TRY(h, cudaMemsetAsync(counts, 0, (size_t)ta.q_count * sizeof(I), st));
             { ProfScope _ps(h, st, "pyr_leaf_tile_kernel");
             if (stash_mode)
-                pyr_leaf_tile_kernel<KIND, kAtomic, 3, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], pflip, stash_cap, d_total, counts, nullptr, (IndexPair<I>*)stash, 0, d_tick + 16 + (tile_launch++), PQ, PT);
+                pyr_leaf_tile_kernel<KIND, kAtomic, 3, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], pflip, stash_cap, d_total, counts, nullptr, (IndexPair<I>*)stash, 0, d_tick + 16 + (tile_launch++), PQ, PT, QIDX, TIDX);
             else
-                pyr_leaf_tile_kernel<KIND, kCount, 1, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], pflip, 0, d_total, counts, nullptr, (IndexPair<I>*)nullptr, 0, d_tick + 16 + (tile_launch++), PQ, PT);
+                pyr_leaf_tile_kernel<KIND, kCount, 1, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], pflip, 0, d_total, counts, nullptr, (IndexPair<I>*)nullptr, 0, d_tick + 16 + (tile_launch++), PQ, PT, QIDX, TIDX);
             }
             IBVH_LAUNCH_CHECK(h, "pyr_leaf_tile_kernel");
             rc = scan_counts<I>(h, counts, ta.q_count, qsums, d_total, st);
@@ -1109,7 +1117,7 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
             IBVH_LAUNCH_CHECK(h, "pyr_scatter_kernel");
         } else {
             { ProfScope _ps(h, st, "pyr_leaf_tile_kernel");
-            pyr_leaf_tile_kernel<KIND, kWrite, 2, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], pflip, capacity, d_total, counts, cursors, (IndexPair<I>*)d_contacts, 0, d_tick + 16 + (tile_launch++), PQ, PT);
+            pyr_leaf_tile_kernel<KIND, kWrite, 2, LQ, LT, I><<<grid, kPyrWarps * 32, 0, st>>>(qleaves, q_begin, qe, bvh, lists[0], pflip, capacity, d_total, counts, cursors, (IndexPair<I>*)d_contacts, 0, d_tick + 16 + (tile_launch++), PQ, PT, QIDX, TIDX);
             }
             IBVH_LAUNCH_CHECK(h, "pyr_leaf_tile_kernel");
         }

@@ -71,7 +71,8 @@ struct ibvh_handle {
         int leaf_kind = 0, float_bytes = 0, built_level = 0, levels = 0;
         char* buf = nullptr;                   // grow-only
         size_t bytes = 0;
-        size_t pt_off = 0, nt_off = 0, u_off = 0;      // byte offsets of the packed volumes, aligned node levels, query pyramid
+        size_t pt_off = 0, nt_off = 0, u_off = 0, idx_off = 0;      // byte offsets of the packed volumes, aligned node levels, query pyramid, leaf indices
+        int index_bytes = 0;
         int u_levels = 0;                      // pyramid levels present (<= 3)
     } sidecars[2];
     unsigned long long next_build_id = 1, last_build_id = 0;

@@ -137,3 +137,17 @@ extern "C" IBVH_API int ibvh_allgather_pairs(ibvh_handle_t* h, const ibvh_peer_t
     if (h_out[2] != 0) { h->set_error("ibvh_allgather_pairs: kernel did not report"); return IBVH_ERR_CUDA; }
     return IBVH_OK;
 }
+
+// Host-only: the gap-filling moves a fused traversal applies to its segmented list (peer.cuh: make_compact_moves), exposed
+// so that the multi-GPU host logic can be tested without a GPU. Units are list ENTRIES. Returns the number of moves.
+extern "C" IBVH_API int ibvh_peer_compact_plan(int32_t world, const int64_t* region_begin, const int64_t* counts,
+                                               int64_t* src, int64_t* dst, int64_t* len, int32_t max_moves) {
+    if (world < 1 || world > IBVH_MAX_PEERS || !region_begin || !counts || !src || !dst || !len) return -1;
+    long long b[IBVH_MAX_PEERS + 1], c[IBVH_MAX_PEERS];
+    for (int r = 0; r < world; ++r) { b[r] = region_begin[r]; c[r] = counts[r]; }
+    b[world] = region_begin[world];
+    const PeerMoves mv = make_compact_moves(world, b, c, 1);
+    if (mv.n > max_moves) return -1;
+    for (int k = 0; k < mv.n; ++k) { src[k] = mv.src[k]; dst[k] = mv.dst[k]; len[k] = mv.len[k]; }
+    return mv.n;
+}

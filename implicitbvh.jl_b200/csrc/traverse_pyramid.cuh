@@ -101,6 +101,9 @@ IBVH_D void atomic_inc(int64_t* p) { atomicAdd(reinterpret_cast<unsigned long lo
 #ifndef IBVH_PYR_TMA
 #define IBVH_PYR_TMA 0
 #endif
+#ifndef IBVH_PYR_QPL
+#define IBVH_PYR_QPL 2            // query leaves per lane in the leaf-tile kernel (register tile QPL x 4)
+#endif
 #ifndef IBVH_PYR_TILE_MINB
 #define IBVH_PYR_TILE_MINB 8      // resident CTAs per SM the tile kernel's registers are capped for (8 -> 64 registers)
 #endif
@@ -720,7 +723,11 @@ __global__ void __launch_bounds__(kPyrWarps * 32, IBVH_PYR_TILE_MINB) pyr_leaf_t
                                                                       int64_t capacity, unsigned long long* total,
                                                                       I* counts, unsigned int* cursors, IndexPair<I>* contacts, int fused, uint32_t* ticket,
                                                                       const Packed<typename LQ::vol_t>* __restrict__ pq,
-                                                                      const Packed<typename LT::vol_t>* __restrict__ pt) {
+                                                                      const Packed<typename LT::vol_t>* __restrict__ pt,
+                                                                      const I* __restrict__ qidx_arr, const I* __restrict__ tidx_arr) {
+    // qidx_arr / tidx_arr: the leaves' indices as compact arrays (a build's sidecar) or nullptr (read them from the leaf structs)
+    auto q_index = [&](uint32_t pos) -> I { return qidx_arr ? __ldg(qidx_arr + pos) : (I)qleaves[pos].index; };
+    auto t_index = [&](uint32_t pos) -> I { return tidx_arr ? __ldg(tidx_arr + pos) : (I)bvh.leaves[pos].index; };
     // pq / pt: the query / target leaf volumes as 16-byte aligned records (pyr_pack_volumes_kernel)
     // fused != 0 (multi-GPU, atomic mode): `contacts` is the NVSwitch multicast alias of this rank's region of every
     // rank's list (multimem.st) and `capacity` the region's size; `total` is a local counter as in the other modes
@@ -733,7 +740,7 @@ __global__ void __launch_bounds__(kPyrWarps * 32, IBVH_PYR_TILE_MINB) pyr_leaf_t
     // wavefronts) and by issue slots, and both costs per pair halve against one query per lane: the target
     // volumes read from shared memory serve two queries, the per-step overhead serves 16 pairs.
     constexpr int G = 1 << kPyrLeafLog;      // 4
-    constexpr int QPL = 2;                   // query leaves per lane
+    constexpr int QPL = sizeof(Packed<VT>) <= 16 ? IBVH_PYR_QPL : 2;      // query leaves per lane (larger volumes: shared-memory budget)
     constexpr int LPP = G / QPL;             // lanes per pair
     constexpr int SLOTS = 32 / LPP;          // 16 pairs per warp step
     constexpr bool kNeedParent = !std::is_same<VT, N>::value || !std::is_same<VQ, N>::value;   // box leaves: implied by the leaf test
@@ -794,7 +801,7 @@ __global__ void __launch_bounds__(kPyrWarps * 32, IBVH_PYR_TILE_MINB) pyr_leaf_t
                     const unsigned int rr = atomicAdd(&cursors[qi], 1u);
                     // (target index, target position) for now — the leaf is still warm in L1 / L2 here, so the index
                     // is fetched now; pyr_fixup_kernel sorts the segment by position and writes the reported pair
-                    contacts[seg + rr] = IndexPair<I>{positions ? (I)(e.y + 1u) : (I)bvh.leaves[e.y].index, (I)e.y};
+                    contacts[seg + rr] = IndexPair<I>{positions ? (I)(e.y + 1u) : t_index(e.y), (I)e.y};
                 }
             } else {
                 if constexpr (PMODE == 3) { if (ok) atomic_inc(&counts[e.x - qb32]); }
@@ -817,7 +824,7 @@ __global__ void __launch_bounds__(kPyrWarps * 32, IBVH_PYR_TILE_MINB) pyr_leaf_t
                 uint4* stash = reinterpret_cast<uint4*>(contacts);
                 for (uint32_t k = lane; k < kept; k += 32) {
                     const uint2 e = s_buf[w][b0 + k];
-                    const unsigned long long li = positions ? (unsigned long long)(e.y + 1u) : (unsigned long long)(long long)bvh.leaves[e.y].index;
+                    const unsigned long long li = positions ? (unsigned long long)(e.y + 1u) : (unsigned long long)(long long)t_index(e.y);
                     if ((int64_t)(base + k) < capacity) stash[base + k] = make_uint4(e.x - qb32, e.y, (uint32_t)li, (uint32_t)(li >> 32));
                 }
             }
@@ -830,8 +837,8 @@ __global__ void __launch_bounds__(kPyrWarps * 32, IBVH_PYR_TILE_MINB) pyr_leaf_t
                 if (lane == 0) base = atomicAdd(total, (unsigned long long)kept);      // (fused: a LOCAL counter too; the slots index this rank's region)
                 base = __shfl_sync(0xffffffffu, base, 0);
                 auto to_pair = [&](uint2 e) -> IndexPair<I> {
-                    const I qidx = positions ? (I)(e.x + 1u) : (I)qleaves[e.x].index;
-                    const I li = positions ? (I)(e.y + 1u) : (I)bvh.leaves[e.y].index;
+                    const I qidx = positions ? (I)(e.x + 1u) : q_index(e.x);
+                    const I li = positions ? (I)(e.y + 1u) : t_index(e.y);
                     I ea, eb;
                     if constexpr (KIND == kSingle) { if (qidx > li) { ea = li; eb = qidx; } else { ea = qidx; eb = li; } }
                     else { if (flip) { ea = li; eb = qidx; } else { ea = qidx; eb = li; } }

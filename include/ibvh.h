@@ -318,6 +318,12 @@ IBVH_API int ibvh_traverse_cancel(ibvh_handle_t* h);
 /* Per-rank contact / hit counts of the last FUSED traversal on this handle (world entries). */
 IBVH_API int ibvh_peer_last_counts(ibvh_handle_t* h, int64_t* counts, int32_t world);
 
+/* Host-only: the moves (in list entries) with which a fused traversal closes the gaps of its segmented list — rank r holds
+ * counts[r] entries from region_begin[r] on; entries at positions >= sum(counts) move into the uncovered positions below
+ * it. Returns the number of (src, dst, len) moves written (<= max_moves), -1 on bad arguments. For testing the host logic. */
+IBVH_API int ibvh_peer_compact_plan(int32_t world, const int64_t* region_begin, const int64_t* counts,
+                                    int64_t* src, int64_t* dst, int64_t* len, int32_t max_moves);
+
 IBVH_API int ibvh_allgather_pairs(ibvh_handle_t* h, const ibvh_peer_t* peer, const void* d_shard, int64_t count,
                                   int32_t pair_bytes, int64_t* out_total, int64_t* out_offset, void* stream);
 

@@ -190,3 +190,37 @@ def test_bench_reference_arm_contract():
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert "workload" in d["config"]
+
+
+def test_fused_gather_regions_and_gap_filling(ib):
+    """Host logic of the fused multi-GPU traversal (no GPU): the regions PeerGather.set_regions lays out and the moves
+    ibvh_peer_compact_plan derives close every gap — applying them to a segmented list leaves the entries [0, total)
+    a permutation of all ranks' entries."""
+    import ctypes as C
+    lib = ib.capi.lib()
+    rng = np.random.default_rng(3)
+    for world in (1, 2, 3, 4, 8, 16):
+        for trial in range(40):
+            counts = rng.integers(0, 5000, world).astype(np.int64)
+            if trial % 5 == 0:
+                counts[rng.integers(0, world)] = 0
+            slack = rng.integers(0, 400, world).astype(np.int64) * 2
+            begin = np.zeros(world + 1, np.int64)
+            begin[1:] = np.cumsum(((counts + 1) & ~1) + slack)
+            total = int(counts.sum())
+            lst = np.full(int(begin[-1]) + 8, -1, np.int64)
+            for r in range(world):
+                lst[begin[r]:begin[r] + counts[r]] = r * 1_000_000 + np.arange(counts[r])
+            want = np.sort(lst[lst >= 0])
+            src, dst, ln = (np.zeros(64, np.int64) for _ in range(3))
+            p = lambda a: a.ctypes.data_as(C.POINTER(C.c_int64))
+            nm = lib.ibvh_peer_compact_plan(world, p(begin), p(counts), p(src), p(dst), p(ln), 64)
+            assert 0 <= nm <= 2 * world + 2
+            moved = 0
+            for k in range(nm):
+                assert ln[k] > 0 and src[k] >= total and dst[k] + ln[k] <= total       # from beyond the total into a gap below it
+                lst[dst[k]:dst[k] + ln[k]] = lst[src[k]:src[k] + ln[k]]
+                moved += int(ln[k])
+            assert (np.sort(lst[:total]) == want).all(), (world, trial)
+            assert moved <= int(begin[-1]) - total                                      # never more than the slack
+    assert lib.ibvh_peer_compact_plan(0, None, None, None, None, None, 0) == -1

@@ -651,24 +651,62 @@ def main():
                 return int(sum(cs))
             return t.num_contacts
 
-        for _ in range(2):
-            hits = step_rays()
-        sync_all()
-        ray_steps = 3
-        e0.record()
-        for _ in range(ray_steps):
-            hits = step_rays()
-        e1.record()
-        sync_all()
-        rms = e0.elapsed_time(e1) / ray_steps
-        if world > 1:
-            t = torch.tensor([rms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            rms = float(t.item())
-        rays = {"metric": "rays/s @1M leaves", "value": R / (rms * 1e-3), "unit": "rays/s", "ms_per_step": rms, "rays": R, "hits_per_step": int(hits),
+        def step_rays_sharded():
+            """Every rank traces its ray range; the hits stay where they are found (rank order = ray order: the shards
+            concatenated are the single-GPU list). No exchange."""
+            t = ib.traverse_rays(rbvh, rp, rd, cache=rcache, ordered=ordered, id_base=rb[0])
+            return t
+
+        def timed_rays(fn, steps=3, warm_steps=2):
+            for _ in range(warm_steps):
+                out = fn()
+            sync_all()
+            e0.record()
+            for _ in range(steps):
+                out = fn()
+            e1.record()
+            sync_all()
+            ms = e0.elapsed_time(e1) / steps
+            if world > 1:
+                t = torch.tensor([ms], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            return ms, out
+
+        ray_verify = None
+        gathered = None
+        if world == 1:
+            rms, hits = timed_rays(step_rays)
+        else:
+            # headline: rays sharded by range, hits left sharded (BASELINE configs[3]: "rays sharded across 1/2/4/8 B200")
+            rms, tsh = timed_rays(step_rays_sharded)
+            mine = pair_checksum(torch, tsh.cache1.tensor, tsh.num_contacts)
+            acc = torch.tensor([mine[0], mine[1], mine[2]], dtype=torch.int64, device=dev)
+            dist.all_reduce(acc)                                         # (int64 sums wrap mod 2^64, like the checksums)
+            hits = int(acc[0].item())
+            # the same with every rank receiving ALL hits (fused into the rays kernel / library all-gather / NCCL)
+            gms, ghits = timed_rays(step_rays)
+            gathered = {"ms_per_step": gms, "value": R / (gms * 1e-3), "unit": "rays/s", "hits_per_step": int(ghits),
+                        "how": ("fused into the rays kernel: multimem.st over NVLink into every rank's list" if rays_fused else
+                                "ibvh_allgather_pairs over NVLink peer memory" if args.gather != "nccl" else "NCCL")}
+            # verification on rank 0: the whole ray set on one GPU against the sum of the shards (count + checksum)
+            ok = 1
+            if rank == 0:
+                fp, fd = synth.random_rays_torch(R, dev, seed=7)
+                full = ib.traverse_rays(rbvh, fp, fd, ordered=False)
+                want = pair_checksum(torch, full.cache1.tensor, full.num_contacts)
+                wrap = lambda v: (v + (1 << 63)) % (1 << 64) - (1 << 63)
+                got = (int(acc[0].item()), int(acc[1].item()), int(acc[2].item()))
+                ok = 1 if (want[0] == got[0] and wrap(want[1]) == got[1] and wrap(want[2]) == got[2] and int(ghits) == want[0]) else 0
+                del fp, fd, full
+            okt = torch.tensor([ok], dtype=torch.int64, device=dev)
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+            ray_verify = {"shards_equal_single_gpu_hit_list": bool(okt.item()),
+                          "what": "hit count + order-independent checksum summed over the ranks' shards against rank 0 tracing all rays alone; the gathered variant's total too"}
+        rays = {"metric": "rays/s @1M leaves", "value": R / (rms * 1e-3), "unit": "rays/s", "ms_per_step": rms, "rays": R, "hits_per_step": int(hits if world > 1 else hits),
                 "workload": "configs[3]: 1000x1000 shell of BSphere{Float32} (1 M leaves, BBox{Float32} nodes), %d random rays, traverse_rays (LVT), "
-                            "rays sharded by contiguous ranges over %d GPU(s), hit shards all-gathered to every rank (%s)" % (R, world, "n/a" if world == 1 else ("fused into the rays kernel: multimem.st over NVLink" if rays_fused else "ibvh_allgather_pairs over NVLink peer memory" if args.gather != "nccl" else "NCCL")),
-                "scaling": "strong"}
+                            "rays sharded by contiguous ranges over %d GPU(s)%s" % (R, world, "" if world == 1 else "; every rank keeps the hits of its own rays (rank order = ray order); `gathered_to_every_rank` is the same step with all hits delivered to every rank"),
+                "gathered_to_every_rank": gathered, "verify": ray_verify, "scaling": "strong"}
         del rp, rd, rcache, rt
 
 

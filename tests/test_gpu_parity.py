@@ -1125,3 +1125,41 @@ def test_ordered_long_segments_and_narrow(ib, O, dev):
     keep = (wr["a"] % 3 == 0) & (p[0][wr["b"] - 1] > 10.0)
     gr = ib.traverse_rays(bvh, p, d, narrow=rpred)
     assert gr.contacts.numpy().tobytes() == wr[keep].tobytes()
+
+
+@pytest.mark.gpu
+def test_sidecar_reuse_eviction_and_fallback(ib, O, dev):
+    """The build's sidecar (ibvh_bvh_t.build_id: packed records, aligned node levels, pyramid levels, index array) is an
+    accelerator only: a traversal gives the same bytes whether its BVH's sidecar is still held (2 slots per handle), was
+    evicted by later builds, or never existed; an in-place rebuild gets a fresh one; pair traversals use both trees'."""
+    from ibvh_b200 import synth
+    n = 150_000
+    sets = [synth.random_spheres_np(n, seed=s) for s in (31, 32, 33, 34)]
+    want = []
+    for s in sets:
+        ol, on = oracle_build(O, s)
+        want.append((ol, on, O.traverse_single(ol, on, num_threads=8)))
+    bvhs = [ib.BVH(s, ib.BBox(), device=dev) for s in sets]              # four builds: the first two sidecars are evicted
+    ids = [b._build_id for b in bvhs]
+    assert all(i > 0 for i in ids) and len(set(ids)) == 4
+    for k in (0, 3, 1, 2):                                               # evicted (pack on the fly) and held sidecars alike
+        assert ib.traverse(bvhs[k]).contacts.numpy().tobytes() == want[k][2].tobytes(), k
+        assert (sorted_pairs(ib.traverse(bvhs[k], ordered=False).contacts.numpy()) == sorted_pairs(want[k][2])).all(), k
+    # a stale / foreign id must not be trusted: same n, same id value, other arrays
+    fake = ib.BVH(sets[0], ib.BBox(), device=dev)
+    fake._build_id = bvhs[3]._build_id
+    assert ib.traverse(fake, ordered=False).num_contacts >= 0            # (contract broken by the caller: must not crash or hang)
+    # pair traversal: queries' and target's sidecars, held and evicted
+    wp = O.traverse_pair(want[2][0], want[2][1], want[3][0], want[3][1], num_threads=8)
+    assert ib.traverse(bvhs[2], bvhs[3]).contacts.numpy().tobytes() == wp.tobytes()
+    wp2 = O.traverse_pair(want[0][0], want[0][1], want[3][0], want[3][1], num_threads=8)
+    assert ib.traverse(bvhs[0], bvhs[3]).contacts.numpy().tobytes() == wp2.tobytes()
+    # in-place rebuild (cache=bvh): new id, same result as before (idempotent on sorted leaves)
+    again = ib.BVH(bvhs[3].leaves, ib.BBox(), cache=bvhs[3])
+    assert again._build_id not in ids
+    assert ib.traverse(again).contacts.numpy().tobytes() == want[3][2].tobytes()
+    # sharded query ranges with the full-range pyramid of the sidecar (boundary groups carry boxes of out-of-range leaves)
+    parts = []
+    for qb, qc in ((0, 50_001), (50_001, 49_999), (100_000, 50_000)):
+        parts.append(ib.traverse(again, query_range=(qb, qc)).contacts.numpy())
+    assert np.concatenate(parts).tobytes() == want[3][2].tobytes()

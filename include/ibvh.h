@@ -180,7 +180,16 @@ IBVH_API int64_t ibvh_leaf_bytes(const ibvh_types_t* types);
 IBVH_API int64_t ibvh_volume_bytes(int32_t kind, int32_t float_bytes);
 IBVH_API int64_t ibvh_num_nodes(int64_t n);   /* real_nodes - real_leaves, build.jl:256 */
 
-/* ---- handle / workspace (replaces AK's temporary allocations) ----------------------------- */
+/* ---- handle / workspace (replaces AK's temporary allocations) -----------------------------
+ * Memory the library owns per handle (all grow-only, freed by ibvh_release_workspace / ibvh_destroy):
+ *   build scratch     ~40 B / leaf for 32-bit keys (ibvh_workspace_query gives the exact figure): radix keys x2,
+ *                     permutation x2, look-back words, and a copy of the leaves on the in-place path;
+ *   sidecars          two slots of ~30 B / leaf (16-byte volume records, aligned node levels, pyramid levels, index array)
+ *                     left by the two most recent pyramid-eligible builds (see ibvh_bvh_t.build_id);
+ *   traversal scratch pair lists + quantised boxes (~70 B / leaf at 10 M uniformly random spheres; grows with the
+ *                     density of the scene) and, for ORDERED traversals with a contacts buffer, a 16-byte-per-contact hit
+ *                     stash sized from the contact totals this handle has SEEN (last total + 25 %, or 6 per query before the
+ *                     first), never from the caller's `capacity`: a generously pre-sized cache1 costs no extra scratch. */
 IBVH_API int ibvh_create(ibvh_handle_t** out, int device);
 IBVH_API int ibvh_destroy(ibvh_handle_t* h);
 /* Bytes of scratch a build of n leaves will hold on to (sort ping-pong, keys, look-back).    */

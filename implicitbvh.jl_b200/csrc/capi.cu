@@ -120,9 +120,9 @@ int sort_pairs(ibvh_handle* h, M* keysA, M* keysB, uint32_t* valsA, uint32_t* va
     auto scope = [&](const char* name) { return ProfScope(h, st, name); };
     cudaError_t e;
     if (sort_wide_lookback(n) || h->cfg.force_wide_lookback)
-        e = sort_pairs_impl<M, unsigned long long, kSortThreads, sort_items<M>(), sort_minb<M>()>(keysA, keysB, valsA, valsB, n, hist, lookback, tickets, st, keys_out, vals_out, scope);
+        e = sort_pairs_impl<M, unsigned long long, sort_threads<M>(), sort_items<M>(), sort_minb<M>()>(keysA, keysB, valsA, valsB, n, hist, lookback, tickets, st, keys_out, vals_out, scope);
     else
-        e = sort_pairs_impl<M, uint32_t, kSortThreads, sort_items<M>(), sort_minb<M>()>(keysA, keysB, valsA, valsB, n, hist, lookback, tickets, st, keys_out, vals_out, scope);
+        e = sort_pairs_impl<M, uint32_t, sort_threads<M>(), sort_items<M>(), sort_minb<M>()>(keysA, keysB, valsA, valsB, n, hist, lookback, tickets, st, keys_out, vals_out, scope);
     if (e != cudaSuccess) { h->set_cuda_error(e, "onesweep_kernel"); return IBVH_ERR_CUDA; }
     return IBVH_OK;
 }
@@ -251,8 +251,8 @@ template <class L> size_t build_workspace_bytes(int64_t n, bool need_copy) {
     size_t b = 0;
     b += 2 * ibvh_handle::padded((size_t)n * sizeof(M));
     b += 2 * ibvh_handle::padded((size_t)n * 4);
-    b += ibvh_handle::padded((size_t)P * kRadixBins * 4);
-    b += ibvh_handle::padded((size_t)P * tiles * kRadixBins * 8);       // (8-byte look-back words from 2^30 leaves; sized for them always)
+    b += ibvh_handle::padded((size_t)P * radix_bins<M>() * 4);
+    b += ibvh_handle::padded((size_t)P * tiles * radix_bins<M>() * 8);       // (8-byte look-back words from 2^30 leaves; sized for them always)
     if (need_copy) b += ibvh_handle::padded((size_t)n * sizeof(L));
     return b + 4096;
 }
@@ -268,12 +268,12 @@ template <class L> int carve_sort_scratch(ibvh_handle* h, int64_t n, bool need_c
     h->reset();
     s->keysA = h->alloc<M>(n); s->keysB = h->alloc<M>(n);
     s->valsA = h->alloc<uint32_t>(n); s->valsB = h->alloc<uint32_t>(n);
-    s->hist = h->alloc<uint32_t>((size_t)P * kRadixBins);
-    s->lookback = h->alloc<unsigned char>((size_t)P * tiles * kRadixBins * lb_bytes);
+    s->hist = h->alloc<uint32_t>((size_t)P * radix_bins<M>());
+    s->lookback = h->alloc<unsigned char>((size_t)P * tiles * radix_bins<M>() * lb_bytes);
     s->copy = need_copy ? (void*)h->alloc<L>(n) : nullptr;
     s->tickets = (uint32_t*)(h->d_small + kSmallTickets);
     if (!s->keysA || !s->keysB || !s->valsA || !s->valsB || !s->hist || !s->lookback || (need_copy && !s->copy)) { h->set_error("workspace carve failed"); return IBVH_ERR_ALLOC; }
-    IBVH_CUDA_TRY(h, cudaMemsetAsync(s->lookback, 0, (size_t)P * tiles * kRadixBins * lb_bytes, st));
+    IBVH_CUDA_TRY(h, cudaMemsetAsync(s->lookback, 0, (size_t)P * tiles * radix_bins<M>() * lb_bytes, st));
     return IBVH_OK;
 }
 
@@ -312,7 +312,7 @@ int launch_encode(ibvh_handle* h, const SRC* src, int64_t n, int compute_extrema
     T* user = nullptr;
     if (!compute_extrema) { int rc = upload_user_bounds<T>(h, mins, maxs, st, &user); if (rc != IBVH_OK) return rc; }
     { ProfScope _ps(h, st, "init_build_kernel");
-    init_build_kernel<T><<<8, 256, 0, st>>>(bounds, hist, P * kRadixBins, tickets, 16);
+    init_build_kernel<T><<<8, 256, 0, st>>>(bounds, hist, P * radix_bins<M>(), tickets, 16);
     }
     IBVH_LAUNCH_CHECK(h, "init_build_kernel");
     const int grid = grid_for(n, 256, 4, h->sm_count * 8);
@@ -1473,11 +1473,11 @@ int ibvh_morton_encode(ibvh_handle_t* h, void* d_leaves, int64_t n, const ibvh_t
     return dispatch_leaf(*types, [&](auto tag) -> int {
         using L = typename decltype(tag)::type; using M = typename L::mor_t; using T = typename L::value_type;
         constexpr int P = radix_passes<M>();
-        int rc = h->reserve(ibvh_handle::padded((size_t)n * sizeof(M)) + ibvh_handle::padded(P * kRadixBins * 4) + 4096);
+        int rc = h->reserve(ibvh_handle::padded((size_t)n * sizeof(M)) + ibvh_handle::padded(P * radix_bins<M>() * 4) + 4096);
         if (rc != IBVH_OK) return rc;
         h->reset();
         M* keys = h->alloc<M>(n);
-        uint32_t* hist = h->alloc<uint32_t>(P * kRadixBins);
+        uint32_t* hist = h->alloc<uint32_t>(P * radix_bins<M>());
         rc = launch_encode<L, L, false>(h, (const L*)d_leaves, n, compute_extrema, mins, maxs, keys, nullptr, hist, (uint32_t*)(h->d_small + kSmallTickets), st);
         if (rc != IBVH_OK) return rc;
         { ProfScope _ps(h, st, "scatter_morton_kernel");
@@ -1501,7 +1501,7 @@ int ibvh_sort_leaves(ibvh_handle_t* h, void* d_leaves, int64_t n, const ibvh_typ
         int rc = carve_sort_scratch<L>(h, n, true, &s, st);
         if (rc != IBVH_OK) return rc;
         { ProfScope _ps(h, st, "init_build_kernel");
-        init_build_kernel<T><<<8, 256, 0, st>>>((typename OrdOf<T>::type*)(h->d_small + kSmallBounds), s.hist, P * kRadixBins, s.tickets, 16);
+        init_build_kernel<T><<<8, 256, 0, st>>>((typename OrdOf<T>::type*)(h->d_small + kSmallBounds), s.hist, P * radix_bins<M>(), s.tickets, 16);
         }
         IBVH_LAUNCH_CHECK(h, "init_build_kernel");
         { ProfScope _ps(h, st, "extract_keys_kernel");

@@ -25,7 +25,6 @@ struct ibvh_handle {
         int pyr_grid = 20;                    // IBVH_PYR_GRID: CTAs per SM of the refine / tile kernels
         bool pyr_quant = true;                // IBVH_PYR_QUANT=0: refine over the float boxes instead of the conservatively quantised ones
         bool pyr_tma = false;                 // IBVH_PYR_TMA=1: refine kernel with TMA bulk copies + mbarrier instead of LDG -> STS (measured slower: see traverse_pyramid.cuh)
-        int fused_flush = -1;                 // IBVH_FUSED_FLUSH: buffered contacts per output reservation in fused mode
         void parse() {
             auto on = [](const char* k) { const char* v = getenv(k); return v != nullptr && v[0] != '\0' && !(v[0] == '0' && v[1] == '\0'); };
             fused_gather = on("IBVH_FUSED_GATHER");
@@ -38,7 +37,6 @@ struct ibvh_handle {
             pyr_tma = on("IBVH_PYR_TMA");
             if (const char* v = getenv("IBVH_PYR_QUANT")) pyr_quant = !(v[0] == '0' && v[1] == '\0');
             if (const char* v = getenv("IBVH_PYR_GRID")) { int g = atoi(v); if (g > 0) pyr_grid = g; }
-            if (const char* v = getenv("IBVH_FUSED_FLUSH")) fused_flush = atoi(v);
         }
     } cfg;
 

@@ -121,10 +121,20 @@ template <class T> IBVH_HD void pad_extrema(T mins[3], T maxs[3]) {
     }
 }
 
+// Radix digit width per key type (radix_sort.cuh; the histograms of encode_kernel follow it). 8 bits for every code
+// width: 30-bit codes in three 10-bit passes and 63-bit codes in seven 9-bit passes were measured slower (radix_sort.cuh,
+// tile-shape notes) and stay available as build-time variants for tools/sort_bench.cu.
+#ifndef IBVH_SORT_RB32
+#define IBVH_SORT_RB32 8
+#endif
+#ifndef IBVH_SORT_RB64
+#define IBVH_SORT_RB64 8
+#endif
 constexpr int kMaxRadixPasses = 8;
-constexpr int kRadixBits = 8;
-constexpr int kRadixBins = 1 << kRadixBits;
-template <class M> constexpr int radix_passes() { return (MortonTraits<M>::key_bits + kRadixBits - 1) / kRadixBits; }
+template <class M> constexpr int radix_bits() { return sizeof(M) == 4 ? IBVH_SORT_RB32 : (sizeof(M) == 8 ? IBVH_SORT_RB64 : 8); }
+template <class M> constexpr int radix_bins() { return 1 << radix_bits<M>(); }
+template <class M> constexpr int radix_passes() { return (MortonTraits<M>::key_bits + radix_bits<M>() - 1) / radix_bits<M>(); }
+constexpr int kMaxRadixBins = 1024;
 
 // ---- init: bounds seeds (floatmax / floatmin — morton/utils.jl:28-29,39-40), zero histograms ------------
 template <class T>
@@ -216,10 +226,11 @@ __global__ void __launch_bounds__(256) encode_kernel(const SRC* __restrict__ src
     using T = typename L::value_type;
     using M = typename L::mor_t;
     constexpr int P = radix_passes<M>();
+    constexpr int RB = radix_bits<M>(), BINS = radix_bins<M>();
     constexpr int HW = IBVH_ENCODE_HIST == 2 ? 8 : 1;                      // private histograms per block
-    __shared__ uint32_t sh[HW][P][kRadixBins];
-    for (int i = threadIdx.x; i < HW * P * kRadixBins; i += blockDim.x) (&sh[0][0][0])[i] = 0;
-    uint32_t (*myh)[kRadixBins] = sh[HW == 1 ? 0 : (threadIdx.x >> 5)];
+    __shared__ uint32_t sh[HW][P][BINS];
+    for (int i = threadIdx.x; i < HW * P * BINS; i += blockDim.x) (&sh[0][0][0])[i] = 0;
+    uint32_t (*myh)[BINS] = sh[HW == 1 ? 0 : (threadIdx.x >> 5)];
     T mins[3], maxs[3];
     if (bounds_in) {
 #pragma unroll
@@ -239,7 +250,7 @@ __global__ void __launch_bounds__(256) encode_kernel(const SRC* __restrict__ src
         keys[i] = m;
 #if IBVH_ENCODE_HIST
 #pragma unroll
-        for (int p = 0; p < P; ++p) atomicAdd(&myh[p][(uint32_t)(m >> (p * kRadixBits)) & (kRadixBins - 1)], 1u);
+        for (int p = 0; p < P; ++p) atomicAdd(&myh[p][(uint32_t)(m >> (p * RB)) & (BINS - 1)], 1u);
 #endif
     };
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -272,7 +283,7 @@ __global__ void __launch_bounds__(256) encode_kernel(const SRC* __restrict__ src
         }
     }
     __syncthreads();
-    for (int i2 = threadIdx.x; i2 < P * kRadixBins; i2 += blockDim.x) {
+    for (int i2 = threadIdx.x; i2 < P * BINS; i2 += blockDim.x) {
         uint32_t v = 0;
 #pragma unroll
         for (int hw = 0; hw < HW; ++hw) v += (&sh[hw][0][0])[i2];

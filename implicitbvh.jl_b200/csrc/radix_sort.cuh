@@ -37,13 +37,11 @@ namespace ibvh {
 // look-back words in flight per round (512x16): 1 -> 0.267, 2 -> 0.240, 3 -> 0.238, 4 -> 0.236, 8 -> 0.249, 16 -> 0.294 ms
 // (the nearest published inclusive prefix is usually 1-3 tiles back: wider batches only add instructions);
 // requesting them BEFORE the reorder: slower (0.277: the predecessors have not published yet, the words are re-read).
-// 8-byte keys: 512x12 is best (0.623 ms for 8 passes at 10 M, 5.7 ms at 100 M).
-#ifndef IBVH_SORT_THREADS
-#define IBVH_SORT_THREADS 512
-#endif
-#ifndef IBVH_SORT_MINB
-#define IBVH_SORT_MINB 2
-#endif
+// 8-byte keys (8 passes, 10 M): 256x16 (3) 0.582, 512x12 (2) 0.623, 256x16 (4) 0.662, 512x16 (2) 0.679, 1024x8 (1) 0.741 ms.
+// Digit width (IBVH_SORT_RB32 / RB64 in morton.cuh; same harness, gpurun_out/r2s): 30-bit keys in THREE 10-bit passes
+// 0.263 ms against 0.237 for four 8-bit ones; 63-bit keys in SEVEN 9-bit passes 0.610 against 0.582 for eight 8-bit ones.
+// A pass gets dearer faster than passes get fewer: the per-warp digit counters (warps x bins: 16 K counters beside an
+// 8 K-key tile at 10 bits) are zeroed, scanned over the warps and looked back once per tile. 8 bits stays.
 #ifndef IBVH_SORT_PREFETCH
 #define IBVH_SORT_PREFETCH 0      // request the nearest predecessors' look-back words before the reorder (measured: slower)
 #endif
@@ -56,15 +54,23 @@ namespace ibvh {
 #ifndef IBVH_SORT_PACKRANK
 #define IBVH_SORT_PACKRANK 1      // two 16-bit ranks per register, pinned when computed
 #endif
-constexpr int kSortThreads = IBVH_SORT_THREADS;
+// threads per tile, keys per thread, resident tiles per SM the register budget is set for
+#ifdef IBVH_SORT_THREADS
+template <class K> constexpr int sort_threads() { return IBVH_SORT_THREADS; }
+#else
+template <class K> constexpr int sort_threads() { return sizeof(K) == 8 ? 256 : 512; }
+#endif
 #ifdef IBVH_SORT_ITEMS
 template <class K> constexpr int sort_items() { return IBVH_SORT_ITEMS; }
 #else
-template <class K> constexpr int sort_items() { return sizeof(K) == 8 ? 12 : 16; }
+template <class K> constexpr int sort_items() { return 16; }
 #endif
-template <class K> constexpr int sort_tile() { return kSortThreads * sort_items<K>(); }
-// resident tiles per SM the register budget is set for
+#ifdef IBVH_SORT_MINB
 template <class K> constexpr int sort_minb() { return IBVH_SORT_MINB; }
+#else
+template <class K> constexpr int sort_minb() { return sizeof(K) == 8 ? 3 : 2; }
+#endif
+template <class K> constexpr int sort_tile() { return sort_threads<K>() * sort_items<K>(); }
 
 // look-back words: 2 flag bits on top of a count / prefix
 template <class LB> struct LookbackWord;
@@ -75,27 +81,29 @@ template <> struct LookbackWord<unsigned long long> {
     static constexpr unsigned long long kAgg = 1ull << 62, kIncl = 2ull << 62, kFlags = 3ull << 62;
 };
 
-// exclusive scan of each pass's 256-bin histogram, in place. grid = passes, block = 256.
-static __global__ void __launch_bounds__(256) scan_hist_kernel(uint32_t* hist) {
-    __shared__ uint32_t wsum[8];
-    uint32_t* h = hist + blockIdx.x * kRadixBins;
-    uint32_t v = h[threadIdx.x];
+// exclusive scan of each pass's histogram (BINS <= 1024 bins), in place. grid = passes, block = 1024.
+template <int BINS>
+static __global__ void __launch_bounds__(1024) scan_hist_kernel(uint32_t* hist) {
+    __shared__ uint32_t wsum[32];
+    uint32_t* h = hist + blockIdx.x * BINS;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const uint32_t v = t < BINS ? h[t] : 0u;
     uint32_t incl = v;
-    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += o; }
     if (lane == 31) wsum[w] = incl;
     __syncthreads();
     uint32_t base = 0;
     for (int j = 0; j < w; ++j) base += wsum[j];
-    h[threadIdx.x] = base + incl - v;
+    if (t < BINS) h[t] = base + incl - v;
 }
 
-template <class K> IBVH_D uint32_t digit_of(K key, int shift) { return (uint32_t)(key >> shift) & (kRadixBins - 1); }
+template <int BINS, class K> IBVH_D uint32_t digit_of(K key, int shift) { return (uint32_t)(key >> shift) & (uint32_t)(BINS - 1); }
 
 // One bit of the warp-wide digit match: keep the lanes whose bit B of the digit equals mine. Written in PTX because
 // nvcc derived TWO predicates per bit from the C++ form (shift + and + setp for the ballot, and + setp + sel for the
-// mask: 5.5 instructions per bit); this is and+setp (one LOP3), VOTE, a predicated NOT and an AND: 4 per bit.
+// mask: 5.5 instructions per bit); this is and+setp (one LOP3, or one R2P for a whole byte), VOTE, a predicated NOT
+// and an AND: ~3.4 per bit.
 template <int B> IBVH_D void match_bit(uint32_t d, uint32_t& peers) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t.reg .b32 t, b;\n\t"
@@ -107,6 +115,7 @@ template <int B> IBVH_D void match_bit(uint32_t d, uint32_t& peers) {
         : "+r"(peers) : "r"(d), "n"(1u << B));
 }
 template <int BITS> IBVH_D uint32_t match_digit(uint32_t d) {
+    static_assert(BITS >= 1 && BITS <= 10, "digit width");
     uint32_t peers = 0xffffffffu;
     match_bit<0>(d, peers);
     if constexpr (BITS > 1) match_bit<1>(d, peers);
@@ -116,24 +125,29 @@ template <int BITS> IBVH_D uint32_t match_digit(uint32_t d) {
     if constexpr (BITS > 5) match_bit<5>(d, peers);
     if constexpr (BITS > 6) match_bit<6>(d, peers);
     if constexpr (BITS > 7) match_bit<7>(d, peers);
+    if constexpr (BITS > 8) match_bit<8>(d, peers);
+    if constexpr (BITS > 9) match_bit<9>(d, peers);
     return peers;
 }
 
-template <class K, int THREADS, int ITEMS> constexpr size_t onesweep_smem_bytes() {
-    return (size_t)THREADS * ITEMS * (sizeof(K) + 4) + (size_t)(THREADS / 32) * kRadixBins * 2 + 2 * kRadixBins * 4;
+template <class K, int THREADS, int ITEMS, int BINS> constexpr size_t onesweep_smem_bytes() {
+    return (size_t)THREADS * ITEMS * (sizeof(K) + 4) + (size_t)(THREADS / 32) * BINS * 2 + 2 * (size_t)BINS * 4;
 }
 
 // One radix pass. keys_in/vals_in -> keys_out/vals_out. vals_in == nullptr: values are the global
 // item index (first pass: the permutation starts as iota and need not be read).
-// hist_excl: this pass's exclusive-scanned global histogram. lookback: [tiles][256] zero-initialised.
-// BITS: digit bits that can differ in this pass (8, or what is left of the key in the top pass).
-// sentinel: a key with every key bit set (pads the last tile).
-template <class K, class LB, int THREADS, int ITEMS, int BITS, int MINB>
+// hist_excl: this pass's exclusive-scanned global histogram. lookback: [tiles][BINS] zero-initialised.
+// RB: radix bits of the sort (BINS = 2^RB digit values); BITS: digit bits that can differ in this pass (RB, or what
+// is left of the key in the top pass). sentinel: a key with every key bit set (pads the last tile).
+// Thread t owns the digits t, t + THREADS, ... in the scans and in the look-back.
+template <class K, class LB, int THREADS, int ITEMS, int RB, int BITS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) onesweep_kernel(const K* __restrict__ keys_in, K* __restrict__ keys_out,
                                                                 const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out,
                                                                 int64_t n, const uint32_t* __restrict__ hist_excl,
                                                                 volatile LB* lookback, uint32_t* ticket, int shift, K sentinel) {
-    static_assert(THREADS >= kRadixBins && THREADS % 32 == 0, "one thread per digit in the scans");
+    constexpr int BINS = 1 << RB;
+    constexpr int DPT = (BINS + THREADS - 1) / THREADS;        // digits per thread
+    static_assert(THREADS % 32 == 0, "whole warps");
     static_assert(32 * ITEMS <= 65535 && THREADS * ITEMS <= 65535, "16-bit per-warp counters / offsets");
     constexpr int WARPS = THREADS / 32;
     constexpr int TILE = THREADS * ITEMS;
@@ -142,15 +156,15 @@ __global__ void __launch_bounds__(THREADS, MINB) onesweep_kernel(const K* __rest
     extern __shared__ __align__(16) unsigned char onesweep_smem[];
     K* skeys = reinterpret_cast<K*>(onesweep_smem);                                   // TILE keys, tile-sorted
     uint32_t* svals = reinterpret_cast<uint32_t*>(skeys + TILE);                      // TILE values
-    uint16_t* whist = reinterpret_cast<uint16_t*>(svals + TILE);                      // [WARPS][256] counts -> exclusive offsets over warps
-    uint32_t* tile_start = reinterpret_cast<uint32_t*>(whist + WARPS * kRadixBins);   // exclusive scan of the tile's digit counts
-    uint32_t* gofs = tile_start + kRadixBins;                                         // global position - position in the tile order (mod 2^32)
+    uint16_t* whist = reinterpret_cast<uint16_t*>(svals + TILE);                      // [WARPS][BINS] counts -> exclusive offsets over warps
+    uint32_t* tile_start = reinterpret_cast<uint32_t*>(whist + WARPS * BINS);         // exclusive scan of the tile's digit counts
+    uint32_t* gofs = tile_start + BINS;                                               // global position - position in the tile order (mod 2^32)
     __shared__ uint32_t s_tile;
-    __shared__ uint32_t wsum[8];
+    __shared__ uint32_t wsum[DPT][WARPS];
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     if (tid == 0) s_tile = atomicAdd(ticket, 1u);
-    for (int i = tid; i < WARPS * kRadixBins / 8; i += THREADS) reinterpret_cast<uint4*>(whist)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < WARPS * BINS / 8; i += THREADS) reinterpret_cast<uint4*>(whist)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
     const uint32_t tile = s_tile;
     const int64_t tile_base = (int64_t)tile * TILE;
@@ -178,11 +192,11 @@ __global__ void __launch_bounds__(THREADS, MINB) onesweep_kernel(const K* __rest
     uint32_t rank1[ITEMS];
 #endif
     {
-        uint16_t* wh = whist + w * kRadixBins;
+        uint16_t* wh = whist + w * BINS;
         const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
         for (int r = 0; r < ITEMS; ++r) {
-            const uint32_t d = digit_of(key[r], shift);
+            const uint32_t d = digit_of<BINS>(key[r], shift);
             const uint32_t peers = match_digit<BITS>(d);
             const uint32_t old = wh[d];                                   // every peer reads the same counter (broadcast)
             const uint32_t rk = old + __popc(peers & lt);
@@ -214,45 +228,49 @@ __global__ void __launch_bounds__(THREADS, MINB) onesweep_kernel(const K* __rest
     }
     __syncthreads();
 
-    // ---- per digit (thread d): exclusive offsets over warps, tile count, publish, tile-level scan ---------
-    // Look-back, part 1: the words of the kBatch nearest predecessors are requested HERE, right after this tile's own
-    // count is published — they travel while the scans, two barriers and the reorder run (ncu, round 2: with the
-    // loads issued only after the reorder the walk was 16 % of the stall samples and the barrier behind it 15 %).
+    // ---- per digit (thread t: digits t + k * THREADS): exclusive offsets over warps, tile count, publish, tile-level scan ----
     constexpr int kBatch = IBVH_SORT_BATCH;
-    uint32_t tcount = 0, incl = 0;
-#if IBVH_SORT_PREFETCH
-    LB pre[kBatch];
-#endif
-    if (tid < kRadixBins) {
-        const int d = tid;
+    uint32_t tcount[DPT], incl[DPT];
+    const int dsent = (int)digit_of<BINS>(sentinel, shift);
 #pragma unroll
-        for (int j = 0; j < WARPS; ++j) { const uint32_t c = whist[j * kRadixBins + d]; whist[j * kRadixBins + d] = (uint16_t)tcount; tcount += c; }
-        // sentinels of a partial tile were ranked like keys: they hold the largest digit and the last tile positions
-        if (tile_n < TILE && d == (int)digit_of(sentinel, shift)) tcount -= (uint32_t)(TILE - tile_n);
-        lookback[(size_t)tile * kRadixBins + d] = (tile == 0 ? kIncl : kAgg) | (LB)tcount;
-#if IBVH_SORT_PREFETCH
+    for (int k = 0; k < DPT; ++k) {
+        const int d = tid + k * THREADS;
+        tcount[k] = 0; incl[k] = 0;
+        if (d < BINS) {
+            uint32_t tc = 0;
 #pragma unroll
-        for (int k = 0; k < kBatch; ++k) pre[k] = ((int64_t)tile - 1 - k >= 0) ? lookback[((size_t)tile - 1 - k) * kRadixBins + d] : kIncl;
-#endif
-        incl = tcount;
+            for (int j = 0; j < WARPS; ++j) { const uint32_t c = whist[j * BINS + d]; whist[j * BINS + d] = (uint16_t)tc; tc += c; }
+            // sentinels of a partial tile were ranked like keys: they hold the largest digit and the last tile positions
+            if (tile_n < TILE && d == dsent) tc -= (uint32_t)(TILE - tile_n);
+            lookback[(size_t)tile * BINS + d] = (tile == 0 ? kIncl : kAgg) | (LB)tc;
+            tcount[k] = tc;
+        }
+        uint32_t in = tcount[k];
 #pragma unroll
-        for (int off = 1; off < 32; off <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += o; }
-        if (lane == 31) wsum[w] = incl;
+        for (int off = 1; off < 32; off <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, in, off); if (lane >= off) in += o; }
+        incl[k] = in;
+        if (lane == 31) wsum[k][w] = in;
     }
     __syncthreads();
-    if (tid < kRadixBins) {
-        uint32_t base = 0;
-        for (int j = 0; j < w; ++j) base += wsum[j];
-        tile_start[tid] = base + incl - tcount;
+#pragma unroll
+    for (int k = 0; k < DPT; ++k) {
+        const int d = tid + k * THREADS;
+        if (d < BINS) {
+            uint32_t base = 0;
+            for (int kk = 0; kk < k; ++kk)
+                for (int j = 0; j < WARPS; ++j) base += wsum[kk][j];
+            for (int j = 0; j < w; ++j) base += wsum[k][j];
+            tile_start[d] = base + incl[k] - tcount[k];
+        }
     }
     __syncthreads();
 
     // ---- reorder the tile in shared memory -------------------------------------------------------------
     {
-        const uint16_t* wh = whist + w * kRadixBins;
+        const uint16_t* wh = whist + w * BINS;
 #pragma unroll
         for (int r = 0; r < ITEMS; ++r) {
-            const uint32_t d = digit_of(key[r], shift);
+            const uint32_t d = digit_of<BINS>(key[r], shift);
 #if IBVH_SORT_PACKRANK
             const uint32_t pos = tile_start[d] + wh[d] + ((r & 1) ? (rank2[r / 2] >> 16) : (rank2[r / 2] & 0xffffu));
 #else
@@ -267,41 +285,38 @@ __global__ void __launch_bounds__(THREADS, MINB) onesweep_kernel(const K* __rest
         }
     }
 
-    // ---- decoupled look-back, part 2 (thread d resolves digit d) ---------------------------------------
-    if (tid < kRadixBins) {
-        const int d = tid;
-        LB excl = 0;
-        if (tile > 0) {
-            // Walk back over the predecessors' (flag | count) words, kBatch independent loads in flight per round: the
-            // chain to the nearest published inclusive prefix is as long as the number of tiles in flight. An entry is
-            // consumed while every nearer one was published; the walk ends at the first inclusive prefix.
-            int64_t t = (int64_t)tile - 1;
-            bool done = false;
-            auto consume = [&](const LB (&v)[kBatch]) {
-                bool alive = true;
-                int used = 0;
+    // ---- decoupled look-back (thread t resolves its digits) --------------------------------------------
 #pragma unroll
-                for (int k = 0; k < kBatch; ++k) {
-                    const LB f = v[k] & kFlags;
-                    const bool take = alive && f != 0;
-                    if (take) { excl += v[k] & ~kFlags; ++used; }
-                    if (take && f == kIncl) done = true;
-                    alive = take && f != kIncl;
+    for (int k = 0; k < DPT; ++k) {
+        const int d = tid + k * THREADS;
+        if (d < BINS) {
+            LB excl = 0;
+            if (tile > 0) {
+                // Walk back over the predecessors' (flag | count) words, kBatch independent loads in flight per round: the
+                // chain to the nearest published inclusive prefix is as long as the number of tiles in flight. An entry is
+                // consumed while every nearer one was published; the walk ends at the first inclusive prefix.
+                int64_t t = (int64_t)tile - 1;
+                bool done = false;
+                while (!done) {
+                    LB v[kBatch];
+#pragma unroll
+                    for (int q = 0; q < kBatch; ++q) v[q] = (t - q >= 0) ? lookback[(size_t)(t - q) * BINS + d] : kIncl;
+                    bool alive = true;
+                    int used = 0;
+#pragma unroll
+                    for (int q = 0; q < kBatch; ++q) {
+                        const LB f = v[q] & kFlags;
+                        const bool take = alive && f != 0;
+                        if (take) { excl += v[q] & ~kFlags; ++used; }
+                        if (take && f == kIncl) done = true;
+                        alive = take && f != kIncl;
+                    }
+                    t -= used;                                  // an unpublished predecessor is simply re-read
                 }
-                t -= used;                                  // an unpublished predecessor is simply re-read
-            };
-#if IBVH_SORT_PREFETCH
-            consume(pre);
-#endif
-            while (!done) {
-                LB v[kBatch];
-#pragma unroll
-                for (int k = 0; k < kBatch; ++k) v[k] = (t - k >= 0) ? lookback[(size_t)(t - k) * kRadixBins + d] : kIncl;
-                consume(v);
+                lookback[(size_t)tile * BINS + d] = kIncl | (excl + (LB)tcount[k]);
             }
-            lookback[(size_t)tile * kRadixBins + d] = kIncl | (excl + (LB)tcount);
+            gofs[d] = hist_excl[d] + (uint32_t)excl - tile_start[d];
         }
-        gofs[d] = hist_excl[d] + (uint32_t)excl - tile_start[d];
     }
     __syncthreads();
 
@@ -310,7 +325,7 @@ __global__ void __launch_bounds__(THREADS, MINB) onesweep_kernel(const K* __rest
         K kk; uint32_t vv;
         if constexpr (kPairStage) { const uint2 kv = reinterpret_cast<const uint2*>(onesweep_smem)[i]; kk = (K)kv.x; vv = kv.y; }
         else { kk = skeys[i]; vv = svals[i]; }
-        const uint32_t dst = gofs[digit_of(kk, shift)] + (uint32_t)i;
+        const uint32_t dst = gofs[digit_of<BINS>(kk, shift)] + (uint32_t)i;
         keys_out[dst] = kk;
         vals_out[dst] = vv;
     };
@@ -328,8 +343,9 @@ __global__ void __launch_bounds__(256) extract_keys_kernel(const L* __restrict__
                                                           L* __restrict__ copy_out, uint32_t* __restrict__ hist) {
     using M = typename L::mor_t;
     constexpr int P = radix_passes<M>();
-    __shared__ uint32_t sh[P][kRadixBins];
-    for (int i = threadIdx.x; i < P * kRadixBins; i += blockDim.x) (&sh[0][0])[i] = 0;
+    constexpr int RB = radix_bits<M>(), BINS = radix_bins<M>();
+    __shared__ uint32_t sh[P][BINS];
+    for (int i = threadIdx.x; i < P * BINS; i += blockDim.x) (&sh[0][0])[i] = 0;
     __syncthreads();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -338,27 +354,27 @@ __global__ void __launch_bounds__(256) extract_keys_kernel(const L* __restrict__
         keys[i] = m;
         store_words(copy_out + i, wv);
 #pragma unroll
-        for (int p = 0; p < P; ++p) atomicAdd(&sh[p][(uint32_t)(m >> (p * kRadixBits)) & (kRadixBins - 1)], 1u);
+        for (int p = 0; p < P; ++p) atomicAdd(&sh[p][(uint32_t)(m >> (p * RB)) & (BINS - 1)], 1u);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < P * kRadixBins; i += blockDim.x) {
+    for (int i = threadIdx.x; i < P * BINS; i += blockDim.x) {
         uint32_t v = (&sh[0][0])[i];
         if (v) atomicAdd(&hist[i], v);
     }
 }
 
 // ---- host driver ---------------------------------------------------------------------------------------
-// keysA holds the input keys; hist the raw per-pass histograms; lookback is zeroed and holds
-// passes * tiles * 256 words of LB. On return the sorted keys / the permutation are in *keys_out / *vals_out.
-// LAUNCHER(name) brackets one launch (profiling scope); returns the first CUDA launch error.
+// keysA holds the input keys; hist the raw per-pass histograms ([passes][BINS]); lookback is zeroed and holds
+// passes * tiles * BINS words of LB. On return the sorted keys / the permutation are in *keys_out / *vals_out.
 // a key with every key bit set (15 / 30 / 63 bits): pads the last tile
 template <class K> constexpr K sort_sentinel() { return (K)((1ull << MortonTraits<K>::key_bits) - 1ull); }
 
 template <class K, class LB, int THREADS, int ITEMS, int MINB, int BITS>
 inline cudaError_t launch_onesweep_pass(const K* kin, K* kout, const uint32_t* vin, uint32_t* vout, int64_t n, const uint32_t* hist_excl,
                                         LB* lookback, uint32_t* ticket, int shift, cudaStream_t st) {
-    auto kern = onesweep_kernel<K, LB, THREADS, ITEMS, BITS, MINB>;
-    constexpr size_t smem = onesweep_smem_bytes<K, THREADS, ITEMS>();
+    constexpr int RB = radix_bits<K>();
+    auto kern = onesweep_kernel<K, LB, THREADS, ITEMS, RB, BITS, MINB>;
+    constexpr size_t smem = onesweep_smem_bytes<K, THREADS, ITEMS, (1 << RB)>();
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -372,12 +388,13 @@ template <class K, class LB, int THREADS, int ITEMS, int MINB, class SCOPE>
 inline cudaError_t sort_pairs_impl(K* keysA, K* keysB, uint32_t* valsA, uint32_t* valsB, int64_t n, uint32_t* hist, void* lookback_raw,
                                    uint32_t* tickets, cudaStream_t st, K** keys_out, uint32_t** vals_out, SCOPE&& scope) {
     constexpr int P = radix_passes<K>();
-    constexpr int kTopBits = MortonTraits<K>::key_bits - kRadixBits * (P - 1);
+    constexpr int RB = radix_bits<K>(), BINS = radix_bins<K>();
+    constexpr int kTopBits = MortonTraits<K>::key_bits - RB * (P - 1);
     const int64_t tiles = (n + (int64_t)THREADS * ITEMS - 1) / ((int64_t)THREADS * ITEMS);
     LB* lookback = (LB*)lookback_raw;
     {
         auto s = scope("scan_hist_kernel");
-        scan_hist_kernel<<<P, 256, 0, st>>>(hist);
+        scan_hist_kernel<BINS><<<P, 1024, 0, st>>>(hist);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
@@ -386,10 +403,10 @@ inline cudaError_t sort_pairs_impl(K* keysA, K* keysB, uint32_t* valsA, uint32_t
     for (int p = 0; p < P; ++p) {
         {
             auto s = scope("onesweep_kernel");
-            if (p == P - 1 && kTopBits < kRadixBits)
-                e = launch_onesweep_pass<K, LB, THREADS, ITEMS, MINB, kTopBits>(kin, kout, vin, vout, n, hist + p * kRadixBins, lookback + (size_t)p * tiles * kRadixBins, tickets + p, p * kRadixBits, st);
+            if (p == P - 1 && kTopBits < RB)
+                e = launch_onesweep_pass<K, LB, THREADS, ITEMS, MINB, kTopBits>(kin, kout, vin, vout, n, hist + p * BINS, lookback + (size_t)p * tiles * BINS, tickets + p, p * RB, st);
             else
-                e = launch_onesweep_pass<K, LB, THREADS, ITEMS, MINB, kRadixBits>(kin, kout, vin, vout, n, hist + p * kRadixBins, lookback + (size_t)p * tiles * kRadixBins, tickets + p, p * kRadixBits, st);
+                e = launch_onesweep_pass<K, LB, THREADS, ITEMS, MINB, RB>(kin, kout, vin, vout, n, hist + p * BINS, lookback + (size_t)p * tiles * BINS, tickets + p, p * RB, st);
         }
         if (e != cudaSuccess) return e;
         K* tk = kin; kin = kout; kout = tk;

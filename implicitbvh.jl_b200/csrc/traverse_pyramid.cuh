@@ -107,6 +107,8 @@ IBVH_D void atomic_inc(int64_t* p) { atomicAdd(reinterpret_cast<unsigned long lo
 #ifndef IBVH_PYR_TILE_MINB
 #define IBVH_PYR_TILE_MINB 8      // resident CTAs per SM the tile kernel's registers are capped for (8 -> 64 registers)
 #endif
+// Float64 volumes: half as many resident CTAs, twice the registers (BBox<double> leaves spilled ~300 bytes per thread at 64)
+template <class L> constexpr int pyr_tile_minb() { return sizeof(typename L::value_type) == 8 ? (IBVH_PYR_TILE_MINB + 1) / 2 : IBVH_PYR_TILE_MINB; }
 IBVH_D void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
@@ -715,10 +717,10 @@ __global__ void __launch_bounds__(kPyrWarps * 32, 8) pyr_refine_tma_kernel(const
 // MODE kAtomic: append contacts (unordered). kCount: only add the number of contacts to *total.
 // PMODE (ordered protocol): 0 = none; 1 = count per query (atomicAdd counts[qi]); 2 = write (qpos, tpos) into the
 // query's segment via a per-query cursor (fixed up into reference order by pyr_fixup_kernel).
-// FLUSH: buffered hits per output-slot reservation. The fused multi-GPU mode on >= 4 ranks uses 512: every
-// reservation is a system-scope atomic on ONE counter of rank 0, which sustains ~190 M/s in total.
+// FLUSH: buffered hits per output-slot reservation (one device-scope atomic on this rank's own counter, also in the fused
+// multi-GPU mode: every rank appends inside its own region of the list).
 template <int KIND, int MODE, int PMODE, class LQ, class LT, class I, int FLUSH = kPyrFlush>
-__global__ void __launch_bounds__(kPyrWarps * 32, IBVH_PYR_TILE_MINB) pyr_leaf_tile_kernel(const LQ* __restrict__ qleaves, int64_t q_begin, int64_t q_end,
+__global__ void __launch_bounds__(kPyrWarps * 32, pyr_tile_minb<LQ>()) pyr_leaf_tile_kernel(const LQ* __restrict__ qleaves, int64_t q_begin, int64_t q_end,
                                                                       DBvh<LT, BBox<typename LT::value_type>> bvh, PairList in, int flip,
                                                                       int64_t capacity, unsigned long long* total,
                                                                       I* counts, unsigned int* cursors, IndexPair<I>* contacts, int fused, uint32_t* ticket,

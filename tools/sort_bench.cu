@@ -28,17 +28,17 @@ template <class K> __global__ void gen_keys(K* keys, int64_t n, int dist) {
     keys[i] = (K)k;
 }
 template <class K> __global__ void hist_kernel(const K* keys, int64_t n, uint32_t* hist) {
-    constexpr int P = radix_passes<K>();
-    __shared__ uint32_t sh[P][256];
-    for (int i = threadIdx.x; i < P * 256; i += blockDim.x) (&sh[0][0])[i] = 0;
+    constexpr int P = radix_passes<K>(), RB = radix_bits<K>(), BINS = radix_bins<K>();
+    __shared__ uint32_t sh[P][BINS];
+    for (int i = threadIdx.x; i < P * BINS; i += blockDim.x) (&sh[0][0])[i] = 0;
     __syncthreads();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         K m = keys[i];
 #pragma unroll
-        for (int p = 0; p < P; ++p) atomicAdd(&sh[p][(uint32_t)(m >> (8 * p)) & 255], 1u);
+        for (int p = 0; p < P; ++p) atomicAdd(&sh[p][(uint32_t)(m >> (RB * p)) & (BINS - 1)], 1u);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < P * 256; i += blockDim.x) if ((&sh[0][0])[i]) atomicAdd(&hist[i], (&sh[0][0])[i]);
+    for (int i = threadIdx.x; i < P * BINS; i += blockDim.x) if ((&sh[0][0])[i]) atomicAdd(&hist[i], (&sh[0][0])[i]);
 }
 
 struct NoScope { int operator()(const char*) const { return 0; } };
@@ -48,23 +48,23 @@ static int g_reps = 10;
 template <class K, class LB, int THREADS, int ITEMS, int MINB>
 void run_variant(const char* name, const K* d_keys, int64_t n, const K* ref_keys, const uint32_t* ref_vals, int reps) {
     if (g_filter && !strstr(name, g_filter)) return;
-    constexpr int P = radix_passes<K>();
+    constexpr int P = radix_passes<K>(), RB = radix_bits<K>(), BINS = radix_bins<K>();
     const int64_t tiles = (n + THREADS * ITEMS - 1) / (THREADS * ITEMS);
     K *kA, *kB; uint32_t *vA, *vB, *hist, *tickets; LB* lb;
     CK(cudaMalloc(&kA, n * sizeof(K))); CK(cudaMalloc(&kB, n * sizeof(K)));
     CK(cudaMalloc(&vA, n * 4)); CK(cudaMalloc(&vB, n * 4));
-    CK(cudaMalloc(&hist, P * 256 * 4)); CK(cudaMalloc(&tickets, 64));
-    CK(cudaMalloc(&lb, (size_t)P * tiles * 256 * sizeof(LB)));
+    CK(cudaMalloc(&hist, P * BINS * 4)); CK(cudaMalloc(&tickets, 64));
+    CK(cudaMalloc(&lb, (size_t)P * tiles * BINS * sizeof(LB)));
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     float best = 1e9f, sum = 0;
     K* ko = nullptr; uint32_t* vo = nullptr;
     for (int it = 0; it < reps + 2; ++it) {
         CK(cudaMemcpy(kA, d_keys, n * sizeof(K), cudaMemcpyDeviceToDevice));
-        CK(cudaMemset(hist, 0, P * 256 * 4)); CK(cudaMemset(tickets, 0, 64));
+        CK(cudaMemset(hist, 0, P * BINS * 4)); CK(cudaMemset(tickets, 0, 64));
         hist_kernel<K><<<148 * 8, 256>>>(kA, n, hist);
         CK(cudaDeviceSynchronize());
         CK(cudaEventRecord(e0));
-        CK(cudaMemsetAsync(lb, 0, (size_t)P * tiles * 256 * sizeof(LB)));
+        CK(cudaMemsetAsync(lb, 0, (size_t)P * tiles * BINS * sizeof(LB)));
         cudaError_t e = sort_pairs_impl<K, LB, THREADS, ITEMS, MINB>(kA, kB, vA, vB, n, hist, lb, tickets, 0, &ko, &vo, NoScope{});
         CK(e);
         CK(cudaEventRecord(e1));
@@ -79,7 +79,7 @@ void run_variant(const char* name, const K* d_keys, int64_t n, const K* ref_keys
     int64_t bad = 0;
     for (int64_t i = 0; i < n; ++i) if (hk[i] != ref_keys[i] || hv[i] != ref_vals[i]) { if (bad < 3) printf("   mismatch at %lld: key %llx/%llx val %u/%u\n", (long long)i, (unsigned long long)hk[i], (unsigned long long)ref_keys[i], hv[i], ref_vals[i]); ++bad; }
     const double bytes = (double)n * (sizeof(K) + (double)P * 2 * (sizeof(K) + 4));      // SURVEY.md §8d S2 formula (histogram read + P passes of key + 4-byte value, read and written)
-    int nb = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, onesweep_kernel<K, LB, THREADS, ITEMS, 8, MINB>, THREADS, onesweep_smem_bytes<K, THREADS, ITEMS>());
+    int nb = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, onesweep_kernel<K, LB, THREADS, ITEMS, RB, RB, MINB>, THREADS, onesweep_smem_bytes<K, THREADS, ITEMS, BINS>());
     printf("%-28s n=%lld: best %.4f ms avg %.4f ms  %.1f Gpairs/s  %.0f GB/s (S2 bytes)  CTAs/SM %d  %s\n", name, (long long)n, best, sum / reps, n / best / 1e6,
            bytes / best / 1e6, nb, bad ? "MISMATCH" : "ok");
     fflush(stdout);
@@ -87,7 +87,7 @@ void run_variant(const char* name, const K* d_keys, int64_t n, const K* ref_keys
 }
 
 template <class K> void run_all(int64_t n, int dist, int reps) {
-    printf("== key bytes %d, n %lld, dist %d\n", (int)sizeof(K), (long long)n, dist);
+    printf("== key bytes %d, n %lld, dist %d, radix bits %d (%d passes)\n", (int)sizeof(K), (long long)n, dist, radix_bits<K>(), radix_passes<K>());
     K* d_keys; CK(cudaMalloc(&d_keys, n * sizeof(K)));
     gen_keys<K><<<(unsigned)((n + 255) / 256), 256>>>(d_keys, n, dist);
     // CUB reference (stable LSD), iota values

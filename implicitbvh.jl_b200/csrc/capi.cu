@@ -478,12 +478,28 @@ int launch_traverse(ibvh_handle* h, const LQ* qleaves, const typename LT::value_
                     rays_kernel<MODE, LT, N, I><<<(unsigned)blocks, 128, 0, st>>>(points, dirs, bvh, a, counts, contacts);
                     }
                 } else {
+                    // [ticket | long-ray queue length | ticket of rays_wide_kernel]
                     unsigned long long* ticket = (unsigned long long*)(h->d_small + kSmallTotal + 24);
-                    IBVH_CUDA_TRY(h, cudaMemsetAsync(ticket, 0, 8, st));
+                    IBVH_CUDA_TRY(h, cudaMemsetAsync(ticket, 0, 24, st));
                     const unsigned pblocks = (unsigned)std::min<int64_t>(blocks, (int64_t)h->sm_count * 12);
+                    // long rays are exported to a queue and finished one warp per ray (order-free modes only; traverse.cuh)
+                    RayWideQueue wq{nullptr, ticket + 1, 0u, 0u};
+                    if constexpr (MODE == kAtomic || MODE == kCount) {
+                        if (a.wq_data) { wq.data = (RayWideEntry*)a.wq_data; wq.cap = a.wq_cap; wq.after = a.wq_after; }
+                    }
+                    constexpr int kHB = MODE == kAtomic ? 512 : 128;                 // hit buffer of the fused multi-GPU variant
                     { ProfScope _ps(h, st, "rays_persistent_kernel");
-                    if (a.peer && MODE == kAtomic) rays_persistent_kernel<MODE, LT, N, I, (MODE == kAtomic ? 512 : 128)><<<pblocks, 128, 0, st>>>(points, dirs, bvh, a, counts, contacts, ticket);
-                    else rays_persistent_kernel<MODE, LT, N, I><<<pblocks, 128, 0, st>>>(points, dirs, bvh, a, counts, contacts, ticket);
+                    if (a.peer && MODE == kAtomic) rays_persistent_kernel<MODE, LT, N, I, kHB><<<pblocks, 128, 0, st>>>(points, dirs, bvh, a, counts, contacts, ticket, wq);
+                    else rays_persistent_kernel<MODE, LT, N, I><<<pblocks, 128, 0, st>>>(points, dirs, bvh, a, counts, contacts, ticket, wq);
+                    }
+                    if constexpr (MODE == kAtomic || MODE == kCount) {
+                        if (wq.data) {
+                            IBVH_LAUNCH_CHECK(h, "rays_persistent_kernel");
+                            const unsigned wblocks = (unsigned)std::min<int64_t>((int64_t)wq.cap / 4 + 1, (int64_t)h->sm_count * 8);
+                            ProfScope _ps(h, st, "rays_wide_kernel");
+                            if (a.peer && MODE == kAtomic) rays_wide_kernel<MODE, LT, N, I, kHB><<<wblocks, 128, 0, st>>>(points, dirs, bvh, a, counts, contacts, wq, ticket + 2);
+                            else rays_wide_kernel<MODE, LT, N, I><<<wblocks, 128, 0, st>>>(points, dirs, bvh, a, counts, contacts, wq, ticket + 2);
+                        }
                     }
                 }
                 IBVH_LAUNCH_CHECK(h, "rays_kernel");
@@ -496,6 +512,20 @@ int launch_traverse(ibvh_handle* h, const LQ* qleaves, const typename LT::value_
         IBVH_LAUNCH_CHECK(h, "lvt_thread_kernel");
     }
     return IBVH_OK;
+}
+
+// rays: capacity of the long-ray queue (0 = long rays stay with their lanes) — see rays_wide_kernel
+inline int64_t ray_queue_cap(const ibvh_handle* h, const TraverseArgs& a, int levels) {
+    if (h->cfg.rays_wide <= 0 || a.start_level >= levels || a.q_count <= 0) return 0;
+    return std::min<int64_t>(int64_t(1) << 22, std::max<int64_t>(4096, a.q_count / h->cfg.rays_wide_div));
+}
+inline size_t ray_queue_bytes(int64_t cap) { return cap > 0 ? ibvh_handle::padded((size_t)cap * sizeof(RayWideEntry)) : 0; }
+// carve the queue from the (already reserved and reset) workspace
+inline void ray_queue_carve(ibvh_handle* h, TraverseArgs* a, int64_t cap) {
+    a->wq_data = nullptr; a->wq_cap = 0; a->wq_after = 0;
+    if (cap <= 0) return;
+    a->wq_data = h->alloc<RayWideEntry>((size_t)cap);
+    if (a->wq_data) { a->wq_cap = (uint32_t)cap; a->wq_after = (uint32_t)h->cfg.rays_wide; }
 }
 
 template <int KIND, bool PACKET, class LQ, class LT, class N, class I>
@@ -513,6 +543,7 @@ int traverse_impl(ibvh_handle* h, const LQ* qleaves, const typename LT::value_ty
     if (a.q_count <= 0 && !(KIND == kRays && a.peer)) return IBVH_OK;      // (a fused call is collective: an empty shard still joins)
     const bool unordered = (flags & IBVH_TRAVERSE_UNORDERED) != 0 && d_contacts != nullptr;
     int rc;
+    const int64_t wq_cap = KIND == kRays ? ray_queue_cap(h, a, bvh.ti.levels) : 0;
     if constexpr (KIND == kRays) {
         if (a.peer) {
             // fused ray traversal + all-gather of the hits (see traverse_pyramid for the contact version)
@@ -528,6 +559,10 @@ int traverse_impl(ibvh_handle* h, const LQ* qleaves, const typename LT::value_ty
             int64_t* h_peer = (int64_t*)(h->h_pinned + 3072);
             h_peer[1] = 0;
             IBVH_CUDA_TRY(h, cudaMemsetAsync(d_total, 0, 8, st));       // local slot counter
+            rc = h->reserve(ray_queue_bytes(wq_cap) + 4096);
+            if (rc != IBVH_OK) return rc;
+            h->reset();
+            ray_queue_carve(h, &a, wq_cap);
             { ProfScope _ps(h, st, "peer_fused_begin_kernel");
             peer_fused_begin_kernel<<<1, 32, 0, st>>>(pa);
             }
@@ -561,6 +596,12 @@ int traverse_impl(ibvh_handle* h, const LQ* qleaves, const typename LT::value_ty
     }
     if (unordered) {
         IBVH_CUDA_TRY(h, cudaMemsetAsync(d_total, 0, 8, st));
+        if (wq_cap > 0) {
+            rc = h->reserve(ray_queue_bytes(wq_cap) + 4096);
+            if (rc != IBVH_OK) return rc;
+            h->reset();
+            ray_queue_carve(h, &a, wq_cap);
+        }
         rc = launch_traverse<KIND, kAtomic, PACKET, LQ, LT, N, I>(h, qleaves, points, dirs, bvh, a, (I*)nullptr, (IndexPair<I>*)d_contacts, st);
         if (rc != IBVH_OK) return rc;
         rc = read_total(h, d_total, num_contacts, st);
@@ -569,13 +610,14 @@ int traverse_impl(ibvh_handle* h, const LQ* qleaves, const typename LT::value_ty
     }
     // ordered: count -> inclusive scan -> (read total) -> write
     const int64_t blocks = (a.q_count + kScanTile - 1) / kScanTile;
-    size_t need = ibvh_handle::padded((size_t)blocks * 8) + (d_counts ? 0 : ibvh_handle::padded((size_t)a.q_count * sizeof(I))) + 4096;
+    size_t need = ibvh_handle::padded((size_t)blocks * 8) + (d_counts ? 0 : ibvh_handle::padded((size_t)a.q_count * sizeof(I))) + ray_queue_bytes(wq_cap) + 4096;
     rc = h->reserve(need);
     if (rc != IBVH_OK) return rc;
     h->reset();
     long long* block_sums = h->alloc<long long>(blocks);
     I* counts = d_counts ? (I*)d_counts : h->alloc<I>(a.q_count);
     if (!block_sums || !counts) { h->set_error("workspace carve failed"); return IBVH_ERR_ALLOC; }
+    ray_queue_carve(h, &a, wq_cap);                       // (used by the count pass; the write pass keeps every ray with its lane)
     if ((flags & IBVH_TRAVERSE_COUNTS_VALID) && d_counts && d_contacts) {
         // second pass only (traverse_single.jl:75): the total is the last entry of the scan
         I* hp = (I*)(h->h_pinned + 64);
@@ -1663,6 +1705,7 @@ int ibvh_traverse_single(ibvh_handle_t* h, const ibvh_bvh_t* bvh, const ibvh_tra
     int rc = check_bvh(bvh, &tree);
     if (rc != IBVH_OK) return rc;
     if (!(bvh->built_level <= p->start_level && p->start_level <= tree.levels)) return IBVH_ERR_ARGUMENT;   // traverse_single.jl:9-11
+    if (d_contacts && (reinterpret_cast<uintptr_t>(d_contacts) % (2u * (unsigned)bvh->types.index_bytes)) != 0) { h->set_error("d_contacts must be aligned to the size of one IndexPair (2 * index_bytes)"); return IBVH_ERR_ARGUMENT; }
     *num_contacts = 0;
     if (tree.real_nodes <= 1) return IBVH_OK;                               // traverse_single.jl:17-21
     DeviceGuard g(h->device);
@@ -1705,6 +1748,7 @@ int ibvh_traverse_pair(ibvh_handle_t* h, const ibvh_bvh_t* queries, const ibvh_b
     if (a1.leaf_kind != a2.leaf_kind || a1.float_bytes != a2.float_bytes || a1.index_bytes != a2.index_bytes ||
         a1.morton_bytes != a2.morton_bytes || a1.node_kind != a2.node_kind || a1.node_float_bytes != a2.node_float_bytes) return IBVH_ERR_ARGUMENT;
     if (!(target->built_level <= p->start_level && p->start_level <= tt.levels)) return IBVH_ERR_ARGUMENT;   // traverse_pair.jl:11-12
+    if (d_contacts && (reinterpret_cast<uintptr_t>(d_contacts) % (2u * (unsigned)target->types.index_bytes)) != 0) { h->set_error("d_contacts must be aligned to the size of one IndexPair (2 * index_bytes)"); return IBVH_ERR_ARGUMENT; }
     *num_contacts = 0;
     DeviceGuard g(h->device);
     cudaStream_t st = (cudaStream_t)stream;
@@ -1739,6 +1783,7 @@ int ibvh_traverse_rays(ibvh_handle_t* h, const ibvh_bvh_t* bvh, const void* d_po
     int rc = check_bvh(bvh, &tree);
     if (rc != IBVH_OK) return rc;
     if (!(bvh->built_level <= p->start_level && p->start_level <= tree.levels)) return IBVH_ERR_ARGUMENT;   // leaf_vs_tree.jl:11-15
+    if (d_contacts && (reinterpret_cast<uintptr_t>(d_contacts) % (2u * (unsigned)bvh->types.index_bytes)) != 0) { h->set_error("d_contacts must be aligned to the size of one IndexPair (2 * index_bytes)"); return IBVH_ERR_ARGUMENT; }
     *num_contacts = 0;
     if (nrays == 0 && !p->peer) return IBVH_OK;                               // leaf_vs_tree.jl:22-26
     if (nrays > 0 && (!d_points || !d_directions)) return IBVH_ERR_ARGUMENT;

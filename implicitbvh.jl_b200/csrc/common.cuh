@@ -24,7 +24,9 @@ template <class V, class I, class M> struct Leaf {
     V volume; I index; M morton;
     using vol_t = V; using idx_t = I; using mor_t = M; using value_type = typename V::value_type;
 };
-template <class I> struct IndexPair { I a, b; };
+// aligned to its size (8 / 16 bytes): one vector store per contact. Every element of a cudaMalloc'ed / CuArray / torch
+// IndexPair array is; the entry points reject a misaligned cache1 (IBVH_ERR_ARGUMENT) instead of faulting.
+template <class I> struct alignas(2 * sizeof(I)) IndexPair { I a, b; };
 
 static_assert(sizeof(Leaf<BSphere<float>, int32_t, uint32_t>) == 24, "layout");
 static_assert(sizeof(Leaf<BSphere<float>, int32_t, uint16_t>) == 24, "layout");
@@ -348,6 +350,26 @@ template <class T> IBVH_HD bool isintersection(const BBox<T>& b, const T p[3], c
     tmax = minimum2(tmax, maximum2(t1, t2));
     return (tmin <= tmax) && (tmax >= T(0));
 }
+// the same slab test with inv = 1 / d computed once per ray by the caller (the same three IEEE divisions, hoisted)
+template <class T> IBVH_HD bool isintersection_inv(const BBox<T>& b, const T p[3], const T inv[3]) {
+    T t1 = (b.lo[0] - p[0]) * inv[0];
+    T t2 = (b.up[0] - p[0]) * inv[0];
+    T tmin = minimum2(t1, t2);
+    T tmax = maximum2(t1, t2);
+    t1 = (b.lo[1] - p[1]) * inv[1];
+    t2 = (b.up[1] - p[1]) * inv[1];
+    tmin = maximum2(tmin, minimum2(t1, t2));
+    tmax = minimum2(tmax, maximum2(t1, t2));
+    t1 = (b.lo[2] - p[2]) * inv[2];
+    t2 = (b.up[2] - p[2]) * inv[2];
+    tmin = maximum2(tmin, minimum2(t1, t2));
+    tmax = minimum2(tmax, maximum2(t1, t2));
+    return (tmin <= tmax) && (tmax >= T(0));
+}
+// node test of the ray kernels: BBox nodes take the hoisted reciprocals, BSphere nodes the direction itself
+template <class T> IBVH_HD bool ray_hits_node(const BBox<T>& b, const T p[3], const T d[3], const T inv[3]) { (void)d; return isintersection_inv(b, p, inv); }
+template <class T> IBVH_HD bool isintersection(const BSphere<T>& s, const T p[3], const T d[3]);
+template <class T> IBVH_HD bool ray_hits_node(const BSphere<T>& s, const T p[3], const T d[3], const T inv[3]) { (void)inv; return isintersection(s, p, d); }
 template <class T> IBVH_HD bool isintersection(const BSphere<T>& s, const T p[3], const T d[3]) {
     T a = (d[0] * d[0] + d[1] * d[1]) + d[2] * d[2];
     T b = T(2) * (((p[0] - s.x[0]) * d[0] + (p[1] - s.x[1]) * d[1]) + (p[2] - s.x[2]) * d[2]);

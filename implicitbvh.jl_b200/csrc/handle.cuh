@@ -18,6 +18,8 @@ struct ibvh_handle {
         bool fused_gather = false;            // IBVH_FUSED_GATHER: gather fused into the bottom-level merge kernel
         bool rays_reference_shaped = false;   // IBVH_RAYS_REFERENCE_SHAPED: one thread per ray, local stack (proxy of the reference kernel)
         bool rays_static = false;             // IBVH_RAYS_STATIC: one ray per thread, no persistent refill
+        int rays_wide_div = 16;               // IBVH_RAYS_WIDE_DIV: the long-ray queue holds rays / this many entries (32 bytes each; 4096 .. 4 M)
+        int rays_wide = 512;                  // IBVH_RAYS_WIDE: node steps after which a long ray is exported to rays_wide_kernel (one warp per ray); 0 = never
         bool debug = false;                   // IBVH_DEBUG: print schedule statistics to stderr
         bool peer_no_multicast = false;       // IBVH_PEER_NO_MULTICAST: plain peer stores instead of multimem.st
         bool force_wide_lookback = false;     // IBVH_SORT_WIDE_LOOKBACK: 64-bit look-back words at any size (tests the n >= 2^30 path)
@@ -30,6 +32,8 @@ struct ibvh_handle {
             fused_gather = on("IBVH_FUSED_GATHER");
             rays_reference_shaped = on("IBVH_RAYS_REFERENCE_SHAPED");
             rays_static = on("IBVH_RAYS_STATIC");
+            if (const char* v = getenv("IBVH_RAYS_WIDE")) { int g = atoi(v); if (g >= 0) rays_wide = g; }
+            if (const char* v = getenv("IBVH_RAYS_WIDE_DIV")) { int g = atoi(v); if (g > 0) rays_wide_div = g; }
             debug = on("IBVH_DEBUG");
             peer_no_multicast = on("IBVH_PEER_NO_MULTICAST");
             force_wide_lookback = on("IBVH_SORT_WIDE_LOOKBACK");

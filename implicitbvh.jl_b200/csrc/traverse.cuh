@@ -50,6 +50,8 @@ struct TraverseArgs {
     int32_t positions;           // IBVH_TRAVERSE_POSITIONS: report 1-based leaf POSITIONS in the sorted arrays instead of .index
     unsigned long long t_build_id, q_build_id;   // ibvh_bvh_t.build_id of the target / query tree (0 = none): selects a build's sidecar
     int64_t t_built_level;       // built_level of the target tree
+    void* wq_data;               // rays: queue of long rays for rays_wide_kernel (RayWideEntry[wq_cap], workspace) or nullptr
+    uint32_t wq_cap, wq_after;   //       its capacity; node steps after which a lane exports its ray
 };
 
 // 8-byte vectorised struct loads (volumes are 8-byte aligned by layout; see common.cuh)
@@ -301,6 +303,189 @@ __global__ void __launch_bounds__(128) rays_kernel(const typename LT::value_type
     if constexpr (MODE == kCount) counts[qi] = (I)em.pos;
 }
 
+// ---- long rays --------------------------------------------------------------------------------------------------
+// A ray grazing the 1 M-sphere shell of configs[3] hits up to ~2300 leaves, and one lane walks ~10 dependent L2-latency
+// node steps per hit (a ray with 94 hits took 0.65 ms on its own). Such rays set a fixed ~2 ms tail per call — which is
+// what kept the 8-GPU ray scaling at 6.8x (tools/rays_scaling_probe.py: t(R) = 0.091 ms / M rays + 2.1 ms).
+// In the order-free modes (unordered list, counts) a lane of rays_persistent_kernel whose ray is still running after
+// `after` node steps EXPORTS it — ray number, current node, pending right children, hits so far: 32 bytes — to a queue
+// and takes the next ray; rays_wide_kernel then finishes each queued ray with a whole warp: the exported nodes (all
+// already box-tested) seed a shared-memory stack, and every step the 32 lanes pop the 32 newest nodes, test their
+// children and push the hit ones back (ballot-compacted) until the stack is empty. Popping the newest nodes keeps the
+// walk depth-first, 32 wide: the stack grows by <= 32 per level; above kRaysWideFull entries one node is popped per
+// step (plain depth-first, +1 per level), so it cannot overflow. A full queue just leaves the ray with its lane.
+// (Finishing the ray inside the persistent kernel, inlined or as a called function, cost the per-lane loop its register
+// budget: 47 -> 56 registers + spills, 100 M rays 93 -> 133 ms, with a 48-register cap 216 ms. Hence the second kernel.)
+struct alignas(16) RayWideEntry { uint32_t q_lo, q_hi, inode, pending, level, root, count, pad; };
+struct RayWideQueue {
+    RayWideEntry* data;              // nullptr = no export
+    unsigned long long* count;       // entries requested (may exceed cap: only the first cap were stored)
+    uint32_t cap;
+    uint32_t after;                  // node steps before a ray is exported
+};
+constexpr int kRaysWideFull = 768;                         // above this many stacked nodes: pop one per step
+constexpr int kRaysWideCap = kRaysWideFull + 64 + 64;      // + one full step's pushes + a depth-first descent
+
+// Hit buffer of one warp (unordered mode): `hit` holds *nhit_slot buffered (leaf, ray) pairs. Flushes whole 32-entry
+// rounds (all = everything) with one atomic on `total` + one coalesced store per round; the fused multi-GPU variant
+// (HB > 128) flushes once >= HB - 128 hits are buffered, two hits per 16-byte multimem.st. Warp-uniform.
+template <int MODE, class I, int HB>
+IBVH_D void rays_flush_hits(IndexPair<I>* hit, unsigned int* nhit_slot, int lane, unsigned long long* total, int64_t capacity,
+                            IndexPair<I>* contacts, bool all) {
+    constexpr bool kFused = HB > 128;
+    if constexpr (MODE == kAtomic) {
+        __syncwarp();
+        unsigned int n = *nhit_slot;
+        if constexpr (kFused) {
+            if (n >= (unsigned)(HB - 128) || (all && n > 0u)) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(total, (unsigned long long)n);      // local counter: slots index this rank's region
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if ((int64_t)(base + n) <= capacity) {
+                    if constexpr (sizeof(IndexPair<I>) == 8) {
+                        const unsigned head = (unsigned)(base & 1ull), npair = (n - head) >> 1;
+                        for (unsigned k = lane; k < npair; k += 32) {
+                            const IndexPair<I> p0 = hit[head + 2 * k], p1 = hit[head + 2 * k + 1];
+                            uint4 v;
+                            v.x = (uint32_t)p0.a; v.y = (uint32_t)p0.b; v.z = (uint32_t)p1.a; v.w = (uint32_t)p1.b;
+                            multimem_st_v4(contacts + base + head + 2 * k, v);
+                        }
+                        if (lane == 0 && head) multimem_store_pair(contacts + base, hit[0]);
+                        if (lane == 1 && ((n - head) & 1u)) multimem_store_pair(contacts + base + n - 1, hit[n - 1]);
+                    } else {
+                        for (unsigned k = lane; k < n; k += 32) multimem_store_pair(contacts + base + k, hit[k]);
+                    }
+                }
+                n = 0;
+            }
+        }
+        while (!kFused && (n >= 32u || (all && n > 0u))) {
+            const unsigned int take = n >= 32u ? 32u : n;
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(total, (unsigned long long)take);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if ((unsigned)lane < take && (int64_t)(base + lane) < capacity) contacts[base + lane] = hit[n - take + lane];
+            n -= take;
+        }
+        __syncwarp();
+        if (lane == 0) *nhit_slot = n;
+        __syncwarp();
+    }
+}
+
+// One warp per exported ray (ticket order). MODE kAtomic: hits appended to the list; kCount: counts[ray] = hits so far
+// (as exported) + the hits found here.
+template <int MODE, class LT, class N, class I, int HB = 128>
+__global__ void __launch_bounds__(128) rays_wide_kernel(const typename LT::value_type* __restrict__ points,
+                                                       const typename LT::value_type* __restrict__ dirs,
+                                                       DBvh<LT, N> bvh, TraverseArgs a, I* counts, IndexPair<I>* contacts,
+                                                       RayWideQueue wq, unsigned long long* ticket) {
+    static_assert(MODE == kAtomic || MODE == kCount, "order-free modes");
+    using T = typename LT::value_type;
+    using V = typename LT::vol_t;
+    __shared__ uint32_t s_skip[34];
+    __shared__ uint32_t s_nreal[34];
+    __shared__ IndexPair<I> s_hit[4][MODE == kAtomic ? HB : 1];
+    __shared__ unsigned int s_nhit[4];
+    __shared__ uint32_t s_stack[4][kRaysWideCap];
+    for (int i = threadIdx.x; i < 34; i += blockDim.x) { s_skip[i] = (uint32_t)bvh.ti.skips[i]; s_nreal[i] = (uint32_t)bvh.ti.level_nreal[i]; }
+    if (threadIdx.x < 4) s_nhit[threadIdx.x] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int levels = bvh.ti.levels;
+    const uint32_t leaf0 = 1u << (levels - 1);
+    const uint32_t inode_end = (1u << (a.start_level - 1)) + s_nreal[a.start_level] - 1u;
+    unsigned long long nq = *wq.count;
+    if (nq > wq.cap) nq = wq.cap;
+    uint32_t* stack = s_stack[w];
+    const unsigned lt = (1u << lane) - 1u;
+    while (true) {
+        unsigned long long e = 0;
+        if (lane == 0) e = atomicAdd(ticket, 1ull);
+        e = __shfl_sync(0xffffffffu, e, 0);
+        if (e >= nq) break;
+        const RayWideEntry en = wq.data[e];
+        const int64_t qi = (int64_t)(((unsigned long long)en.q_hi << 32) | en.q_lo);
+        const int64_t q = a.q_begin + qi;
+        T p[3], d[3], inv[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { p[k] = points[3 * q + k]; d[k] = dirs[3 * q + k]; inv[k] = T(1) / d[k]; }
+        const I ray_id = (I)(a.id_base + q + 1);
+        uint32_t nhit = 0;
+        uint32_t n = 0;                                                    // stacked nodes (warp-uniform)
+        auto leaf_hit = [&](uint32_t node) -> bool {
+            const LT* lp = bvh.leaves + (node - leaf0);
+            V v;
+            const uint2* sp = reinterpret_cast<const uint2*>(lp);
+            uint2* dp = reinterpret_cast<uint2*>(&v);
+#pragma unroll
+            for (int k = 0; k < (int)(sizeof(V) / 8); ++k) dp[k] = __ldg(sp + k);
+            if (!isintersection(v, p, d)) return false;
+            if constexpr (MODE == kAtomic) {
+                const I li = a.positions ? (I)(node - leaf0 + 1u) : (I)lp->index;
+                s_hit[w][atomicAdd(&s_nhit[w], 1u)] = IndexPair<I>{li, ray_id};
+            }
+            return true;
+        };
+        auto run = [&]() {
+            __syncwarp();
+            while (n > 0u) {
+                const uint32_t take = n > (uint32_t)kRaysWideFull ? 1u : (n < 32u ? n : 32u);
+                const bool have = (uint32_t)lane < take;
+                uint32_t node = 0;
+                if (have) node = stack[n - 1u - (uint32_t)lane];
+                n -= take;
+                __syncwarp();
+                bool h0 = false, h1 = false;
+                const uint32_t c0 = 2u * node;
+                if (have) {
+                    const int lv = 32 - __clz(node);
+                    const int cl = lv + 1;
+                    const bool c1_real = (c0 + 1u - (1u << lv)) < s_nreal[cl];
+                    if (cl == levels) {
+                        if (leaf_hit(c0)) nhit += 1;
+                        if (c1_real && leaf_hit(c0 + 1u)) nhit += 1;
+                    } else {
+                        const N* cp = bvh.nodes + (c0 - s_skip[cl] - 1u);
+                        const N b0 = load_struct(cp);
+                        h0 = ray_hits_node(b0, p, d, inv);
+                        if (c1_real) { const N b1 = load_struct(cp + 1); h1 = ray_hits_node(b1, p, d, inv); }
+                    }
+                }
+                const unsigned m0 = __ballot_sync(0xffffffffu, h0), m1 = __ballot_sync(0xffffffffu, h1);
+                const uint32_t n0 = (uint32_t)__popc(m0);
+                if (h0) stack[n + (uint32_t)__popc(m0 & lt)] = c0;
+                if (h1) stack[n + n0 + (uint32_t)__popc(m1 & lt)] = c0 + 1u;
+                n += n0 + (uint32_t)__popc(m1);
+                __syncwarp();
+                rays_flush_hits<MODE, I, HB>(s_hit[w], &s_nhit[w], lane, a.total, a.capacity, contacts, false);
+            }
+        };
+        // seeds: the node the lane was about to expand and the pending right children of its ancestors (bit k = the
+        // ancestor at level k), all already box-tested
+        n = 1u + (uint32_t)__popc(en.pending);
+        if (lane == 0) stack[0] = en.inode;
+        if ((en.pending >> lane) & 1u) stack[1 + __popc(en.pending & lt)] = 2u * (en.inode >> ((int)en.level - lane)) + 1u;
+        run();
+        // the roots right of the exported one (start_level > 1): 32 box tests at a time
+        for (uint32_t r0 = en.root + 1u; r0 <= inode_end && r0 != 0u; r0 += 32u) {
+            const uint32_t r = r0 + (uint32_t)lane;
+            bool h = false;
+            if (r <= inode_end && r >= r0) h = ray_hits_node(load_struct(bvh.nodes + (r - s_skip[a.start_level] - 1u)), p, d, inv);
+            const unsigned m = __ballot_sync(0xffffffffu, h);
+            if (h) stack[__popc(m & lt)] = r;
+            n = (uint32_t)__popc(m);
+            run();
+        }
+        if constexpr (MODE == kCount) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) nhit += __shfl_xor_sync(0xffffffffu, nhit, off);
+            if (lane == 0) counts[qi] = (I)(en.count + nhit);
+        }
+    }
+    rays_flush_hits<MODE, I, HB>(s_hit[w], &s_nhit[w], lane, a.total, a.capacity, contacts, true);
+}
+
 // Persistent variant of rays_kernel. Random rays are incoherent: with one ray per thread a warp runs until
 // its longest ray is done with a handful of lanes active (measured: 4.2 of 32). Here every warp keeps
 // pulling rays from a global ticket counter and a lane that finishes its ray is refilled, so the lanes
@@ -312,8 +497,9 @@ template <int MODE, class LT, class N, class I, int HB = 128>
 __global__ void __launch_bounds__(128) rays_persistent_kernel(const typename LT::value_type* __restrict__ points,
                                                              const typename LT::value_type* __restrict__ dirs,
                                                              DBvh<LT, N> bvh, TraverseArgs a, I* counts, IndexPair<I>* contacts,
-                                                             unsigned long long* ticket) {
+                                                             unsigned long long* ticket, RayWideQueue wq) {
     constexpr bool kFused = HB > 128;
+    constexpr bool kWide = MODE == kAtomic || MODE == kCount;             // (kWrite reports a ray's hits in DFS order: it stays with its lane)
     using T = typename LT::value_type;
     using V = typename LT::vol_t;
     __shared__ uint32_t s_skip[34];
@@ -333,7 +519,7 @@ __global__ void __launch_bounds__(128) rays_persistent_kernel(const typename LT:
     const uint32_t inode_end = inode_start + s_nreal[a.start_level] - 1u;
 
     int64_t qi = -1;                      // ray handled by this lane (index within the shard), -1 = idle
-    T p[3] = {0, 0, 0}, d[3] = {0, 0, 0};
+    T p[3] = {0, 0, 0}, d[3] = {0, 0, 0}, inv[3] = {0, 0, 0};      // inv = 1 / d, once per ray (isintersection.jl:6-8 computes it per test)
     I ray_id = 0;
     uint32_t root = 0, inode = 0, pending = 0;
     int level = 0;
@@ -358,46 +544,9 @@ __global__ void __launch_bounds__(128) rays_persistent_kernel(const typename LT:
             else em.emit(li, ray_id);
         }
     };
-    auto flush_hits = [&](bool all) {
-        if constexpr (MODE == kAtomic) {
-            __syncwarp();
-            unsigned int n = s_nhit[w];
-            if constexpr (kFused) {
-                if (n >= (unsigned)(HB - 128) || (all && n > 0u)) {
-                    unsigned long long base = 0;
-                    if (lane == 0) base = atomicAdd(a.total, (unsigned long long)n);      // local counter: slots index this rank's region
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if ((int64_t)(base + n) <= a.capacity) {
-                        if constexpr (sizeof(IndexPair<I>) == 8) {
-                            const unsigned head = (unsigned)(base & 1ull), npair = (n - head) >> 1;
-                            for (unsigned k = lane; k < npair; k += 32) {
-                                const IndexPair<I> p0 = s_hit[w][head + 2 * k], p1 = s_hit[w][head + 2 * k + 1];
-                                uint4 v;
-                                v.x = (uint32_t)p0.a; v.y = (uint32_t)p0.b; v.z = (uint32_t)p1.a; v.w = (uint32_t)p1.b;
-                                multimem_st_v4(contacts + base + head + 2 * k, v);
-                            }
-                            if (lane == 0 && head) multimem_store_pair(contacts + base, s_hit[w][0]);
-                            if (lane == 1 && ((n - head) & 1u)) multimem_store_pair(contacts + base + n - 1, s_hit[w][n - 1]);
-                        } else {
-                            for (unsigned k = lane; k < n; k += 32) multimem_store_pair(contacts + base + k, s_hit[w][k]);
-                        }
-                    }
-                    n = 0;
-                }
-            }
-            while (!kFused && (n >= 32u || (all && n > 0u))) {
-                const unsigned int take = n >= 32u ? 32u : n;
-                unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(a.total, (unsigned long long)take);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if ((unsigned)lane < take && (int64_t)(base + lane) < a.capacity) contacts[base + lane] = s_hit[w][n - take + lane];
-                n -= take;
-            }
-            __syncwarp();
-            if (lane == 0) s_nhit[w] = n;
-            __syncwarp();
-        }
-    };
+    auto flush_hits = [&](bool all) { rays_flush_hits<MODE, I, HB>(s_hit[w], &s_nhit[w], lane, a.total, a.capacity, contacts, all); };
+    uint32_t steps = 0;                   // node steps of this lane's ray
+    const uint32_t export_after = (kWide && wq.data) ? wq.after : 0xffffffffu;
 
     while (true) {
         flush_hits(false);
@@ -415,10 +564,11 @@ __global__ void __launch_bounds__(128) rays_persistent_kernel(const typename LT:
                     qi = r;
                     const int64_t q = a.q_begin + r;
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) { p[k] = points[3 * q + k]; d[k] = dirs[3 * q + k]; }
+                    for (int k = 0; k < 3; ++k) { p[k] = points[3 * q + k]; d[k] = dirs[3 * q + k]; inv[k] = T(1) / d[k]; }
                     ray_id = (I)(a.id_base + q + 1);
                     root = inode_start;
                     need_root = true;
+                    steps = 0;
                     em.pos = 0;
                     if constexpr (MODE == kWrite) em.pos = (r == 0) ? 0 : (int64_t)counts[r - 1];
                 }
@@ -436,10 +586,23 @@ __global__ void __launch_bounds__(128) rays_persistent_kernel(const typename LT:
                 root += 1;
             } else {
                 N rb = load_struct(bvh.nodes + (root - s_skip[a.start_level] - 1u));
-                if (isintersection(rb, p, d)) { inode = root; level = a.start_level; pending = 0; need_root = false; }
+                if (ray_hits_node(rb, p, d, inv)) { inode = root; level = a.start_level; pending = 0; need_root = false; }
                 else root += 1;
             }
             continue;
+        }
+        if constexpr (kWide) {
+            if (++steps > export_after) {                              // a long ray: hand it to rays_wide_kernel
+                const unsigned long long slot = atomicAdd(wq.count, 1ull);
+                if (slot < wq.cap) {
+                    uint4* dst = reinterpret_cast<uint4*>(wq.data + slot);
+                    dst[0] = make_uint4((uint32_t)qi, (uint32_t)((unsigned long long)qi >> 32), inode, pending);
+                    dst[1] = make_uint4((uint32_t)level, root, (uint32_t)em.pos, 0u);
+                    qi = -1;
+                    continue;
+                }
+                steps = 0;                                               // queue full: the ray stays with this lane
+            }
         }
         const uint32_t c0 = 2u * inode, c1 = c0 + 1u;
         const int cl = level + 1;
@@ -451,9 +614,9 @@ __global__ void __launch_bounds__(128) rays_persistent_kernel(const typename LT:
         } else {
             const N* cp = bvh.nodes + (c0 - s_skip[cl] - 1u);
             const N b0 = load_struct(cp);
-            const bool h0 = isintersection(b0, p, d);
+            const bool h0 = ray_hits_node(b0, p, d, inv);
             bool h1 = false;
-            if (c1_real) { const N b1 = load_struct(cp + 1); h1 = isintersection(b1, p, d); }
+            if (c1_real) { const N b1 = load_struct(cp + 1); h1 = ray_hits_node(b1, p, d, inv); }
             if (h0) { if (h1) pending |= 1u << level; inode = c0; level = cl; descended = true; }
             else if (h1) { inode = c1; level = cl; descended = true; }
         }

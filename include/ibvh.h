@@ -250,7 +250,8 @@ IBVH_API uint64_t ibvh_last_build_id(ibvh_handle_t* h);
  * leaf_vs_tree/traverse_single.jl:52-78):
  *   d_counts   : I[query_count] or NULL. ORDERED mode fills it with the inclusive scan of
  *                per-query contact counts (the GPU form of BVHTraversal.cache2).
- *   d_contacts : IndexPair{I}[capacity] or NULL (NULL = count only).
+ *   d_contacts : IndexPair{I}[capacity] or NULL (NULL = count only). Aligned to sizeof(IndexPair{I}) = 2 * index_bytes
+ *                (any element of a cudaMalloc'ed / CuArray allocation is); a misaligned pointer is IBVH_ERR_ARGUMENT.
  *   num_contacts (host): total found. If it exceeds `capacity` the call returns
  *                IBVH_ERR_CAPACITY and the caller grows cache1 and calls again
  *                ("resize only if too small", traverse_single.jl:61-67). */

@@ -5,6 +5,7 @@ BIT-EXACT; BSphere node merges within 1e-6 relative (we check exact equality fir
 the tolerance). Run on the B200 box: `pytest -m gpu`.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -551,6 +552,27 @@ def test_rays_mesh_like_against_oracle(ib, O, dev):
     got = ib.traverse_rays(bvh, p.T, d.T)
     assert got.contacts.numpy().tobytes() == want.tobytes()
     assert len(want) > 20_000
+    un = ib.traverse_rays(bvh, p.T, d.T, ordered=False)
+    assert (sorted_pairs(un.contacts.numpy()) == sorted_pairs(want)).all()
+    for sl in (3, bvh.tree.levels - 2):                      # several roots per ray
+        w2 = O.traverse_rays(ol, on, p.T[:, :4000], d.T[:, :4000], start_level=sl, num_threads=8)
+        assert ib.traverse_rays(bvh, p.T[:, :4000], d.T[:, :4000], start_level=sl).contacts.numpy().tobytes() == w2.tobytes()
+        un2 = ib.traverse_rays(bvh, p.T[:, :4000], d.T[:, :4000], start_level=sl, ordered=False)
+        assert (sorted_pairs(un2.contacts.numpy()) == sorted_pairs(w2)).all()
+
+
+@pytest.mark.parametrize("after", ["2", "40", "0"])
+def test_rays_long_ray_queue_thresholds(after):
+    """The ray tests again, in a fresh process, with long rays exported to rays_wide_kernel after 2 node steps (nearly every
+    ray; the 20 k-ray case overflows the 4096-entry queue, so the queue-full path runs too), after 40, and never (0):
+    the same oracle lists come out whichever kernel finishes a ray."""
+    import subprocess, sys
+    env = dict(os.environ, IBVH_RAYS_WIDE=after)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider",
+                        "-k", "rays_small or ray_grid or pair_and_ray_doctests or rays_mesh_like"],
+                       env=env, capture_output=True, text=True, timeout=900, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "4 passed" in r.stdout, r.stdout[-1000:]
 
 
 # ---- full BASELINE sizes: size-independent properties ------------------------------------------------

@@ -482,24 +482,20 @@ int launch_traverse(ibvh_handle* h, const LQ* qleaves, const typename LT::value_
                     unsigned long long* ticket = (unsigned long long*)(h->d_small + kSmallTotal + 24);
                     IBVH_CUDA_TRY(h, cudaMemsetAsync(ticket, 0, 24, st));
                     const unsigned pblocks = (unsigned)std::min<int64_t>(blocks, (int64_t)h->sm_count * 12);
-                    // long rays are exported to a queue and finished one warp per ray (order-free modes only; traverse.cuh)
+                    // long rays are exported to a queue and finished one warp per ray (traverse.cuh)
                     RayWideQueue wq{nullptr, ticket + 1, 0u, 0u};
-                    if constexpr (MODE == kAtomic || MODE == kCount) {
-                        if (a.wq_data) { wq.data = (RayWideEntry*)a.wq_data; wq.cap = a.wq_cap; wq.after = a.wq_after; }
-                    }
+                    if (a.wq_data) { wq.data = (RayWideEntry*)a.wq_data; wq.cap = a.wq_cap; wq.after = a.wq_after; }
                     constexpr int kHB = MODE == kAtomic ? 512 : 128;                 // hit buffer of the fused multi-GPU variant
                     { ProfScope _ps(h, st, "rays_persistent_kernel");
                     if (a.peer && MODE == kAtomic) rays_persistent_kernel<MODE, LT, N, I, kHB><<<pblocks, 128, 0, st>>>(points, dirs, bvh, a, counts, contacts, ticket, wq);
                     else rays_persistent_kernel<MODE, LT, N, I><<<pblocks, 128, 0, st>>>(points, dirs, bvh, a, counts, contacts, ticket, wq);
                     }
-                    if constexpr (MODE == kAtomic || MODE == kCount) {
-                        if (wq.data) {
-                            IBVH_LAUNCH_CHECK(h, "rays_persistent_kernel");
-                            const unsigned wblocks = (unsigned)std::min<int64_t>((int64_t)wq.cap / 4 + 1, (int64_t)h->sm_count * 8);
-                            ProfScope _ps(h, st, "rays_wide_kernel");
-                            if (a.peer && MODE == kAtomic) rays_wide_kernel<MODE, LT, N, I, kHB><<<wblocks, 128, 0, st>>>(points, dirs, bvh, a, counts, contacts, wq, ticket + 2);
-                            else rays_wide_kernel<MODE, LT, N, I><<<wblocks, 128, 0, st>>>(points, dirs, bvh, a, counts, contacts, wq, ticket + 2);
-                        }
+                    if (wq.data) {
+                        IBVH_LAUNCH_CHECK(h, "rays_persistent_kernel");
+                        const unsigned wblocks = (unsigned)std::min<int64_t>((int64_t)wq.cap / 4 + 1, (int64_t)h->sm_count * 8);
+                        ProfScope _ps(h, st, "rays_wide_kernel");
+                        if (a.peer && MODE == kAtomic) rays_wide_kernel<MODE, LT, N, I, kHB><<<wblocks, 128, 0, st>>>(points, dirs, bvh, a, counts, contacts, wq, ticket + 2);
+                        else rays_wide_kernel<MODE, LT, N, I><<<wblocks, 128, 0, st>>>(points, dirs, bvh, a, counts, contacts, wq, ticket + 2);
                     }
                 }
                 IBVH_LAUNCH_CHECK(h, "rays_kernel");
@@ -617,7 +613,7 @@ int traverse_impl(ibvh_handle* h, const LQ* qleaves, const typename LT::value_ty
     long long* block_sums = h->alloc<long long>(blocks);
     I* counts = d_counts ? (I*)d_counts : h->alloc<I>(a.q_count);
     if (!block_sums || !counts) { h->set_error("workspace carve failed"); return IBVH_ERR_ALLOC; }
-    ray_queue_carve(h, &a, wq_cap);                       // (used by the count pass; the write pass keeps every ray with its lane)
+    ray_queue_carve(h, &a, wq_cap);                       // (used by the count pass and by the write pass)
     if ((flags & IBVH_TRAVERSE_COUNTS_VALID) && d_counts && d_contacts) {
         // second pass only (traverse_single.jl:75): the total is the last entry of the scan
         I* hp = (I*)(h->h_pinned + 64);

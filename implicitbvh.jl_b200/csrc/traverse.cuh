@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(128) rays_kernel(const typename LT::value_type
 // A ray grazing the 1 M-sphere shell of configs[3] hits up to ~2300 leaves, and one lane walks ~10 dependent L2-latency
 // node steps per hit (a ray with 94 hits took 0.65 ms on its own). Such rays set a fixed ~2 ms tail per call — which is
 // what kept the 8-GPU ray scaling at 6.8x (tools/rays_scaling_probe.py: t(R) = 0.091 ms / M rays + 2.1 ms).
-// In the order-free modes (unordered list, counts) a lane of rays_persistent_kernel whose ray is still running after
+// A lane of rays_persistent_kernel whose ray is still running after
 // `after` node steps EXPORTS it — ray number, current node, pending right children, hits so far: 32 bytes — to a queue
 // and takes the next ray; rays_wide_kernel then finishes each queued ray with a whole warp: the exported nodes (all
 // already box-tested) seed a shared-memory stack, and every step the 32 lanes pop the 32 newest nodes, test their
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(128) rays_kernel(const typename LT::value_type
 // step (plain depth-first, +1 per level), so it cannot overflow. A full queue just leaves the ray with its lane.
 // (Finishing the ray inside the persistent kernel, inlined or as a called function, cost the per-lane loop its register
 // budget: 47 -> 56 registers + spills, 100 M rays 93 -> 133 ms, with a 48-register cap 216 ms. Hence the second kernel.)
-struct alignas(16) RayWideEntry { uint32_t q_lo, q_hi, inode, pending, level, root, count, pad; };
+struct alignas(16) RayWideEntry { uint32_t q_lo, q_hi, inode, pending, level, root, count, count_hi; };   // count: hits so far (kCount) / next output slot (kWrite)
 struct RayWideQueue {
     RayWideEntry* data;              // nullptr = no export
     unsigned long long* count;       // entries requested (may exceed cap: only the first cap were stored)
@@ -374,13 +374,17 @@ IBVH_D void rays_flush_hits(IndexPair<I>* hit, unsigned int* nhit_slot, int lane
 }
 
 // One warp per exported ray (ticket order). MODE kAtomic: hits appended to the list; kCount: counts[ray] = hits so far
-// (as exported) + the hits found here.
+// (as exported) + the hits found here; kWrite: the remaining hits written from the exported slot on, IN THE REFERENCE'S
+// ORDER. That order is depth-first, left child first = ascending leaf position, and the stack keeps it: it is sorted
+// with the leftmost node on top, the popped nodes' children are pushed back in order (they lie left of everything
+// below), and a popped leaf parent emits its hits only if no internal node was popped left of it in the same step —
+// otherwise it is pushed back as it is and comes up again after that node's subtree.
 template <int MODE, class LT, class N, class I, int HB = 128>
 __global__ void __launch_bounds__(128) rays_wide_kernel(const typename LT::value_type* __restrict__ points,
                                                        const typename LT::value_type* __restrict__ dirs,
                                                        DBvh<LT, N> bvh, TraverseArgs a, I* counts, IndexPair<I>* contacts,
                                                        RayWideQueue wq, unsigned long long* ticket) {
-    static_assert(MODE == kAtomic || MODE == kCount, "order-free modes");
+    constexpr bool kOrdered = MODE == kWrite;
     using T = typename LT::value_type;
     using V = typename LT::vol_t;
     __shared__ uint32_t s_skip[34];
@@ -411,70 +415,94 @@ __global__ void __launch_bounds__(128) rays_wide_kernel(const typename LT::value
 #pragma unroll
         for (int k = 0; k < 3; ++k) { p[k] = points[3 * q + k]; d[k] = dirs[3 * q + k]; inv[k] = T(1) / d[k]; }
         const I ray_id = (I)(a.id_base + q + 1);
-        uint32_t nhit = 0;
+        uint32_t nhit = 0;                                                 // kCount: hits found by this lane
+        int64_t pos = (int64_t)(((unsigned long long)en.count_hi << 32) | en.count);      // kWrite: next slot (warp-uniform)
         uint32_t n = 0;                                                    // stacked nodes (warp-uniform)
-        auto leaf_hit = [&](uint32_t node) -> bool {
-            const LT* lp = bvh.leaves + (node - leaf0);
+        auto leaf_test = [&](uint32_t node) -> bool {
             V v;
-            const uint2* sp = reinterpret_cast<const uint2*>(lp);
+            const uint2* sp = reinterpret_cast<const uint2*>(bvh.leaves + (node - leaf0));
             uint2* dp = reinterpret_cast<uint2*>(&v);
 #pragma unroll
             for (int k = 0; k < (int)(sizeof(V) / 8); ++k) dp[k] = __ldg(sp + k);
-            if (!isintersection(v, p, d)) return false;
-            if constexpr (MODE == kAtomic) {
-                const I li = a.positions ? (I)(node - leaf0 + 1u) : (I)lp->index;
-                s_hit[w][atomicAdd(&s_nhit[w], 1u)] = IndexPair<I>{li, ray_id};
-            }
-            return true;
+            return isintersection(v, p, d);
         };
+        auto reported = [&](uint32_t node) -> I { return a.positions ? (I)(node - leaf0 + 1u) : (I)bvh.leaves[node - leaf0].index; };
         auto run = [&]() {
             __syncwarp();
             while (n > 0u) {
                 const uint32_t take = n > (uint32_t)kRaysWideFull ? 1u : (n < 32u ? n : 32u);
                 const bool have = (uint32_t)lane < take;
-                uint32_t node = 0;
-                if (have) node = stack[n - 1u - (uint32_t)lane];
+                uint32_t node = 1u;
+                if (have) node = stack[n - 1u - (uint32_t)lane];         // lane 0 = top = leftmost
                 n -= take;
                 __syncwarp();
-                bool h0 = false, h1 = false;
+                const int lv = 32 - __clz(node);
+                const int cl = lv + 1;
                 const uint32_t c0 = 2u * node;
-                if (have) {
-                    const int lv = 32 - __clz(node);
-                    const int cl = lv + 1;
-                    const bool c1_real = (c0 + 1u - (1u << lv)) < s_nreal[cl];
-                    if (cl == levels) {
-                        if (leaf_hit(c0)) nhit += 1;
-                        if (c1_real && leaf_hit(c0 + 1u)) nhit += 1;
-                    } else {
-                        const N* cp = bvh.nodes + (c0 - s_skip[cl] - 1u);
-                        const N b0 = load_struct(cp);
-                        h0 = ray_hits_node(b0, p, d, inv);
-                        if (c1_real) { const N b1 = load_struct(cp + 1); h1 = ray_hits_node(b1, p, d, inv); }
-                    }
+                const bool c1_real = (c0 + 1u - (1u << lv)) < s_nreal[cl];
+                const bool leafpar = have && cl == levels;
+                const bool inner = have && cl != levels;
+                bool do_leaves = leafpar, repush = false;
+                if constexpr (kOrdered) {
+                    const unsigned im = __ballot_sync(0xffffffffu, inner);
+                    const int first_inner = im ? __ffs(im) - 1 : 32;
+                    do_leaves = leafpar && lane < first_inner;
+                    repush = leafpar && lane > first_inner;
                 }
-                const unsigned m0 = __ballot_sync(0xffffffffu, h0), m1 = __ballot_sync(0xffffffffu, h1);
-                const uint32_t n0 = (uint32_t)__popc(m0);
-                if (h0) stack[n + (uint32_t)__popc(m0 & lt)] = c0;
-                if (h1) stack[n + n0 + (uint32_t)__popc(m1 & lt)] = c0 + 1u;
-                n += n0 + (uint32_t)__popc(m1);
+                bool h0 = false, h1 = false;
+                if (do_leaves) {
+                    h0 = leaf_test(c0);
+                    h1 = c1_real && leaf_test(c0 + 1u);
+                    if constexpr (MODE == kCount) nhit += (uint32_t)h0 + (uint32_t)h1;
+                    if constexpr (MODE == kAtomic) {
+                        if (h0) s_hit[w][atomicAdd(&s_nhit[w], 1u)] = IndexPair<I>{reported(c0), ray_id};
+                        if (h1) s_hit[w][atomicAdd(&s_nhit[w], 1u)] = IndexPair<I>{reported(c0 + 1u), ray_id};
+                    }
+                } else if (inner) {
+                    const N* cp = bvh.nodes + (c0 - s_skip[cl] - 1u);
+                    const N b0 = load_struct(cp);
+                    h0 = ray_hits_node(b0, p, d, inv);
+                    if (c1_real) { const N b1 = load_struct(cp + 1); h1 = ray_hits_node(b1, p, d, inv); }
+                }
+                if constexpr (kOrdered) {
+                    const unsigned e0 = __ballot_sync(0xffffffffu, do_leaves && h0), e1 = __ballot_sync(0xffffffffu, do_leaves && h1);
+                    if (do_leaves) {
+                        const int64_t at = pos + __popc(e0 & lt) + __popc(e1 & lt);
+                        if (h0) contacts[at] = IndexPair<I>{reported(c0), ray_id};
+                        if (h1) contacts[at + (h0 ? 1 : 0)] = IndexPair<I>{reported(c0 + 1u), ray_id};
+                    }
+                    pos += __popc(e0) + __popc(e1);
+                }
+                // push back, leftmost on top: lane order = left to right, a lane's left child above its right child
+                const unsigned m0 = __ballot_sync(0xffffffffu, inner && h0), m1 = __ballot_sync(0xffffffffu, inner && h1);
+                const unsigned mr = __ballot_sync(0xffffffffu, repush);
+                const uint32_t total = (uint32_t)(__popc(m0) + __popc(m1) + __popc(mr));
+                uint32_t idx = n + total - 1u - (uint32_t)(__popc(m0 & lt) + __popc(m1 & lt) + __popc(mr & lt));
+                if (repush) stack[idx] = node;
+                else if (inner) {
+                    if (h0) { stack[idx] = c0; idx -= 1u; }
+                    if (h1) stack[idx] = c0 + 1u;
+                }
+                n += total;
                 __syncwarp();
                 rays_flush_hits<MODE, I, HB>(s_hit[w], &s_nhit[w], lane, a.total, a.capacity, contacts, false);
             }
         };
-        // seeds: the node the lane was about to expand and the pending right children of its ancestors (bit k = the
-        // ancestor at level k), all already box-tested
-        n = 1u + (uint32_t)__popc(en.pending);
-        if (lane == 0) stack[0] = en.inode;
-        if ((en.pending >> lane) & 1u) stack[1 + __popc(en.pending & lt)] = 2u * (en.inode >> ((int)en.level - lane)) + 1u;
+        // seeds, all already box-tested, left to right: the node the lane was about to expand, then the pending right
+        // children of its ancestors from the deepest ancestor up (bit k of pending = the ancestor at level k)
+        const uint32_t npend = (uint32_t)__popc(en.pending);
+        n = 1u + npend;
+        if (lane == 0) stack[npend] = en.inode;
+        if ((en.pending >> lane) & 1u) stack[__popc(en.pending & lt)] = 2u * (en.inode >> ((int)en.level - lane)) + 1u;
         run();
-        // the roots right of the exported one (start_level > 1): 32 box tests at a time
+        // the roots right of the exported one (start_level > 1): 32 box tests at a time, leftmost on top
         for (uint32_t r0 = en.root + 1u; r0 <= inode_end && r0 != 0u; r0 += 32u) {
             const uint32_t r = r0 + (uint32_t)lane;
             bool h = false;
             if (r <= inode_end && r >= r0) h = ray_hits_node(load_struct(bvh.nodes + (r - s_skip[a.start_level] - 1u)), p, d, inv);
             const unsigned m = __ballot_sync(0xffffffffu, h);
-            if (h) stack[__popc(m & lt)] = r;
             n = (uint32_t)__popc(m);
+            if (h) stack[n - 1u - (uint32_t)__popc(m & lt)] = r;
             run();
         }
         if constexpr (MODE == kCount) {
@@ -499,7 +527,7 @@ __global__ void __launch_bounds__(128) rays_persistent_kernel(const typename LT:
                                                              DBvh<LT, N> bvh, TraverseArgs a, I* counts, IndexPair<I>* contacts,
                                                              unsigned long long* ticket, RayWideQueue wq) {
     constexpr bool kFused = HB > 128;
-    constexpr bool kWide = MODE == kAtomic || MODE == kCount;             // (kWrite reports a ray's hits in DFS order: it stays with its lane)
+    constexpr bool kWide = true;
     using T = typename LT::value_type;
     using V = typename LT::vol_t;
     __shared__ uint32_t s_skip[34];
@@ -597,7 +625,7 @@ __global__ void __launch_bounds__(128) rays_persistent_kernel(const typename LT:
                 if (slot < wq.cap) {
                     uint4* dst = reinterpret_cast<uint4*>(wq.data + slot);
                     dst[0] = make_uint4((uint32_t)qi, (uint32_t)((unsigned long long)qi >> 32), inode, pending);
-                    dst[1] = make_uint4((uint32_t)level, root, (uint32_t)em.pos, 0u);
+                    dst[1] = make_uint4((uint32_t)level, root, (uint32_t)em.pos, (uint32_t)((unsigned long long)em.pos >> 32));
                     qi = -1;
                     continue;
                 }

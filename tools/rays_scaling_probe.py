@@ -27,4 +27,15 @@ for R, start in [(100_000_000, 0), (50_000_000, 50_000_000), (25_000_000, 75_000
     top = torch.topk(per_ray, 5).values.tolist()
     print(f"   hits per ray: max {top}  rays with > 100 hits: {int((per_ray > 100).sum())}  > 1000: {int((per_ray > 1000).sum())}")
     print(f"R={R:>11} start={start:>10}: {np.median(ms):8.3f} ms (min {min(ms):.3f})  {R / np.median(ms) / 1e6:.3f} G rays/s  hits {t.num_contacts}", flush=True)
+    if R <= 25_000_000:
+        to = ib.traverse_rays(bvh, rp, rd, ordered=True, id_base=start)
+        oc = ib.BVHTraversal(1, 0, 0, 0, ib.DeviceArray.empty(int(to.num_contacts) + 1024, ib.pair_dtype(), dev), to.cache2)
+        ms = []
+        for _ in range(4):
+            e0.record()
+            to = ib.traverse_rays(bvh, rp, rd, cache=oc, ordered=True, id_base=start)
+            e1.record(); torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        print(f"   ordered (count + scan + write): {np.median(ms[1:]):8.3f} ms", flush=True)
+        del to, oc
     del rp, rd, cache, t

@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_refine_kernel(const UBox<T
         }
         __syncwarp();
         nbuf = s_nv[w];
-        if (nbuf >= (uint32_t)kPyrFlush) { flush(nbuf & ~31u); if (lane == 0) s_nv[w] = nbuf; }
+        if (nbuf >= (uint32_t)kPyrFlush) { flush(nbuf & ~31u); __syncwarp(); if (lane == 0) s_nv[w] = nbuf; }
         __syncwarp();
     };
     // Work distribution: warps draw chunks of consecutive list entries from a ticket counter. A warp's output
@@ -524,7 +524,7 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_refine_q_kernel(const QBox
         }
         __syncwarp();
         nbuf = s_nv[w];
-        if (nbuf >= (uint32_t)kPyrFlush) { flush(nbuf & ~31u); if (lane == 0) s_nv[w] = nbuf; }
+        if (nbuf >= (uint32_t)kPyrFlush) { flush(nbuf & ~31u); __syncwarp(); if (lane == 0) s_nv[w] = nbuf; }
         __syncwarp();
     };
     const uint32_t chunk = SLOTS * pyr_chunk_steps(count, SLOTS);
@@ -676,7 +676,7 @@ __global__ void __launch_bounds__(kPyrWarps * 32, 8) pyr_refine_tma_kernel(const
         }
         __syncwarp();
         nbuf = s_nv[w];
-        if (nbuf >= (uint32_t)kPyrFlush) { flush(nbuf & ~31u); if (lane == 0) s_nv[w] = nbuf; }
+        if (nbuf >= (uint32_t)kPyrFlush) { flush(nbuf & ~31u); __syncwarp(); if (lane == 0) s_nv[w] = nbuf; }
         __syncwarp();
     };
     const uint32_t chunk = SLOTS * pyr_chunk_steps(count, SLOTS);
@@ -941,7 +941,7 @@ __global__ void __launch_bounds__(kPyrWarps * 32, pyr_tile_minb<LQ>()) pyr_leaf_
         }
         __syncwarp();
         nbuf = s_nv[w];
-        if (nbuf >= (uint32_t)FLUSH) { flush(nbuf & ~31u); if (lane == 0) s_nv[w] = nbuf; }
+        if (nbuf >= (uint32_t)FLUSH) { flush(nbuf & ~31u); __syncwarp(); if (lane == 0) s_nv[w] = nbuf; }
         __syncwarp();
     };
     auto process = [&](Stage& cur, int buf) {

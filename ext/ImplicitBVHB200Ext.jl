@@ -16,7 +16,7 @@ module ImplicitBVHB200Ext
 
 using ImplicitBVH
 using ImplicitBVH: BVH, BVHOptions, BVHTraversal, BoundingVolume, BSphere, BBox, IndexPair, ImplicitTree,
-                   LVTTraversal, get_index_type, compute_build_level, compute_skips!, default_start_level,
+                   LVTTraversal, BFSTraversal, get_index_type, compute_build_level, compute_skips!, default_start_level,
                    check_bounding_volume_types
 using CUDA
 
@@ -266,6 +266,128 @@ function ImplicitBVH.traverse_rays(
         total = length(cache1)
     end
     BVHTraversal(start_level, 0, num_checks(h), total, cache1, cache2)
+end
+
+# ---- BFSTraversal — src/traverse/breadth_first/*.jl, src/raytrace/breadth_first/*.jl ----------------------------------
+# cache1 / cache2 are both Vector{IndexPair{I}} in the reference (its two BVTT buffers, traverse_single.jl:88-101); here the
+# BVTT lives in library scratch, cache1 receives the contacts and cache2 is handed through. A cache1 that is too small is
+# grown to the exact need and only the leaf level is repeated (COUNTS_VALID).
+function bfs_protocol(call, h, ::Type{I}, cache, flags::UInt32) where I
+    if !isnothing(cache)
+        eltype(cache.cache1) === IndexPair{I} || throw(ArgumentError("eltype(cache.cache1) === IndexPair{I} must hold"))
+        eltype(cache.cache2) === IndexPair{I} || throw(ArgumentError("eltype(cache.cache2) === IndexPair{I} must hold"))
+    end
+    cache1 = isnothing(cache) ? CuVector{IndexPair{I}}(undef, 0) : cache.cache1
+    cache2 = isnothing(cache) ? CuVector{IndexPair{I}}(undef, 0) : cache.cache2
+    total = Ref{Int64}(0); checks = Ref{Int64}(0)
+    if length(cache1) > 0
+        rc = call(flags, pointer(cache1), length(cache1), total, checks)
+        rc == 0 && return Int(total[]), Int(checks[]), cache1, cache2
+        rc == ERR_CAPACITY || check(rc, h)
+    else
+        check(call(flags, CU_NULL, 0, total, checks), h)                            # count only
+        total[] == 0 && return 0, Int(checks[]), cache1, cache2
+    end
+    cache1 = CuVector{IndexPair{I}}(undef, Int(total[]))
+    check(call(flags | COUNTS_VALID, pointer(cache1), length(cache1), total, checks), h)
+    Int(total[]), Int(checks[]), cache1, cache2
+end
+
+ImplicitBVH.default_start_level(bvh::BVH{I, <:CuVector}, ::BFSTraversal) where I =
+    Int(ccall((:ibvh_bfs_default_start_level, LIB), Int64, (Int64, Int64), bvh.tree.levels, bvh.built_level))
+
+function ImplicitBVH.traverse(
+    bvh::BVH{I, <:CuVector, <:CuVector{N}, <:CuVector{L}},
+    alg::BFSTraversal;
+    start_level::Int=default_start_level(bvh, alg),
+    narrow=nothing,
+    cache::Union{Nothing, BVHTraversal}=nothing,
+    options=BVHOptions(),
+) where {I, N, L}
+    bvh.tree.levels >= start_level >= bvh.built_level ||
+        throw(ArgumentError("bvh.tree.levels >= start_level >= bvh.built_level must hold"))    # breadth_first/traverse_single.jl:10
+    if bvh.tree.real_nodes <= 1
+        return BVHTraversal(start_level, 0, 0, CuVector{IndexPair{I}}(undef, 0), CuVector{IndexPair{I}}(undef, 0))
+    end
+    h = handle()
+    cb = cbvh(bvh, types(L, N))
+    flags = isdefault(narrow) ? UInt32(0) : POSITIONS
+    call(fl, pcontacts, cap, total, checks) = ccall((:ibvh_traverse_bfs_single, LIB), Cint,
+        (Ptr{Cvoid}, Ref{CBvh}, Ref{Params}, CuPtr{Cvoid}, Int64, Ref{Int64}, Ref{Int64}, Ptr{Cvoid}),
+        h, cb, Params(start_level, 0, -1, fl, 0, 0, C_NULL), pcontacts, cap, total, checks, stream())
+    total, checks, cache1, cache2 = bfs_protocol(call, h, I, isdefault(narrow) ? cache : nothing, flags)
+    if !isdefault(narrow)
+        cache1 = apply_narrow(narrow, view(cache1, 1:total), bvh.leaves, bvh.leaves, true)
+        total = length(cache1)
+    end
+    BVHTraversal(start_level, checks, total, cache1, cache2)
+end
+
+function ImplicitBVH.traverse(
+    bvh1::BVH{I, <:CuVector, <:CuVector{N}, <:CuVector{L}},
+    bvh2::BVH{I, <:CuVector, <:CuVector{N}, <:CuVector{L}},
+    alg::BFSTraversal;
+    start_level1::Int=default_start_level(bvh1, alg),
+    start_level2::Int=default_start_level(bvh2, alg),
+    narrow=nothing,
+    cache::Union{Nothing, BVHTraversal}=nothing,
+    options=BVHOptions(),
+) where {I, N, L}
+    bvh1.tree.levels >= start_level1 >= bvh1.built_level ||
+        throw(ArgumentError("bvh1.tree.levels >= start_level1 >= bvh1.built_level must hold"))  # breadth_first/traverse_pair.jl:10-11
+    bvh2.tree.levels >= start_level2 >= bvh2.built_level ||
+        throw(ArgumentError("bvh2.tree.levels >= start_level2 >= bvh2.built_level must hold"))
+    h = handle()
+    t = types(L, N)
+    c1 = cbvh(bvh1, t)
+    c2 = cbvh(bvh2, t)
+    flags = isdefault(narrow) ? UInt32(0) : POSITIONS
+    call(fl, pcontacts, cap, total, checks) = ccall((:ibvh_traverse_bfs_pair, LIB), Cint,
+        (Ptr{Cvoid}, Ref{CBvh}, Ref{CBvh}, Int64, Int64, UInt32, CuPtr{Cvoid}, Int64, Ref{Int64}, Ref{Int64}, Ptr{Cvoid}),
+        h, c1, c2, start_level1, start_level2, fl, pcontacts, cap, total, checks, stream())
+    total, checks, cache1, cache2 = bfs_protocol(call, h, I, isdefault(narrow) ? cache : nothing, flags)
+    if !isdefault(narrow)
+        cache1 = apply_narrow(narrow, view(cache1, 1:total), bvh1.leaves, bvh2.leaves, false)
+        total = length(cache1)
+    end
+    BVHTraversal(start_level1, start_level2, checks, total, cache1, cache2)
+end
+
+function ImplicitBVH.traverse_rays(
+    bvh::BVH{I, <:CuVector, <:CuVector{N}, <:CuVector{L}},
+    points::CuMatrix,
+    directions::CuMatrix,
+    alg::BFSTraversal;
+    start_level::Int=1,
+    narrow=nothing,
+    cache::Union{Nothing, BVHTraversal}=nothing,
+    options=BVHOptions(),
+) where {I, N, L}
+    bvh.tree.levels >= start_level >= bvh.built_level ||
+        throw(ArgumentError("bvh.tree.levels >= start_level >= bvh.built_level must hold"))    # raytrace/breadth_first/breadth_first.jl:12
+    size(points, 1) == size(directions, 1) == 3 || throw(ArgumentError("size(points, 1) == size(directions, 1) == 3 must hold"))
+    size(points, 2) == size(directions, 2) || throw(ArgumentError("size(points, 2) == size(directions, 2) must hold"))
+    T = floattype(L.parameters[1])
+    nrays = size(points, 2)
+    if nrays == 0                                                                   # :25-29
+        return BVHTraversal(start_level, 0, 0, CuVector{IndexPair{I}}(undef, 0), CuVector{IndexPair{I}}(undef, 0))
+    end
+    p = eltype(points) === T ? points : T.(points)
+    d = eltype(directions) === T ? directions : T.(directions)
+    h = handle()
+    cb = cbvh(bvh, types(L, N))
+    flags = isdefault(narrow) ? UInt32(0) : POSITIONS
+    call(fl, pcontacts, cap, total, checks) = ccall((:ibvh_traverse_bfs_rays, LIB), Cint,
+        (Ptr{Cvoid}, Ref{CBvh}, CuPtr{Cvoid}, CuPtr{Cvoid}, Int64, Ref{Params}, CuPtr{Cvoid}, Int64, Ref{Int64}, Ref{Int64}, Ptr{Cvoid}),
+        h, cb, pointer(p), pointer(d), nrays, Params(start_level, 0, -1, fl, 0, 0, C_NULL), pcontacts, cap, total, checks, stream())
+    total, checks, cache1, cache2 = bfs_protocol(call, h, I, isdefault(narrow) ? cache : nothing, flags)
+    if !isdefault(narrow)
+        hits = view(cache1, 1:total)
+        keep = map(hp -> narrow(bvh.leaves[hp[1]], (p[1, hp[2]], p[2, hp[2]], p[3, hp[2]]), (d[1, hp[2]], d[2, hp[2]], d[3, hp[2]])), hits)
+        cache1 = map(hp -> (bvh.leaves[hp[1]].index, hp[2]), hits[keep])
+        total = length(cache1)
+    end
+    BVHTraversal(start_level, checks, total, cache1, cache2)
 end
 
 # ---- opt-in extension: asynchronous contact detection (IBVH_TRAVERSE_DEFER) ----------------------------------------

@@ -4,7 +4,7 @@ The package directory is named `implicitbvh.jl_b200` (not importable by that dot
 through the repo-root shim: `import ibvh_b200`.
 """
 from . import _capi as capi
-from .api import (ArgumentError, BBox, BBOX, BSphere, BSPHERE, BVH, BVHOptions, BVHTraversal, CudaError,
+from .api import (ArgumentError, BBox, BBOX, BFSTraversal, BSphere, BSPHERE, BVH, BVHOptions, BVHTraversal, CudaError,
                   DefaultMortonAlgorithm, DeviceArray, DomainError, ImplicitTree, LVTTraversal, VolumeType,
                   aggregate, bboxes, bspheres, default_start_level, get_handle, isvirtual, leaf_dtype,
                   level_indices, memory_index, morton_encode, pair_dtype, sort_leaves, traverse,
@@ -12,6 +12,6 @@ from .api import (ArgumentError, BBox, BBOX, BSphere, BSPHERE, BVH, BVHOptions, 
 
 __all__ = [
     "BVH", "BVHTraversal", "BVHOptions", "traverse", "traverse_rays", "default_start_level",
-    "ImplicitTree", "memory_index", "level_indices", "isvirtual", "DefaultMortonAlgorithm", "LVTTraversal",
+    "ImplicitTree", "memory_index", "level_indices", "isvirtual", "DefaultMortonAlgorithm", "LVTTraversal", "BFSTraversal",
     "BSphere", "BBox", "DeviceArray", "ArgumentError", "DomainError", "CudaError",
 ]

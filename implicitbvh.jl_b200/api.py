@@ -288,6 +288,15 @@ class LVTTraversal:
         return "LVTTraversal()"
 
 
+class BFSTraversal:
+    """Simultaneous breadth-first traversal, nodes paired level by level (traverse/breadth_first/breadth_first.jl:1;
+    traverse/traverse.jl:19-24): fewest checks, BVTT lists of 10-20x the contacts in library scratch. Contacts come back
+    as a set in unspecified order, like the reference's GPU backend; `num_checks` is exact."""
+
+    def __repr__(self):
+        return "BFSTraversal()"
+
+
 # ---------------------------------------------------------------------------------------------
 # implicit tree (implicit_tree.jl) — host-only integer math done by the C library
 # ---------------------------------------------------------------------------------------------
@@ -522,7 +531,9 @@ class BVHTraversal:
 
 
 def default_start_level(bvh: BVH, alg=None) -> int:
-    """leaf_vs_tree/leaf_vs_tree.jl:4-6."""
+    """leaf_vs_tree/leaf_vs_tree.jl:4-6; breadth_first/breadth_first.jl:4-6."""
+    if isinstance(alg, BFSTraversal):
+        return int(capi.lib().ibvh_bfs_default_start_level(bvh.tree.levels, bvh.built_level))
     if alg is not None and not isinstance(alg, LVTTraversal):
         raise ArgumentError(f"default_start_level not implemented for: {alg}")
     return max(1, bvh.built_level)
@@ -684,6 +695,101 @@ def _run_two_phase(call, handle, device, I: np.dtype, nqueries: int, cache: Opti
     return int(total.value), cache1, cache2
 
 
+def _bfs_protocol(call, handle, device, I: np.dtype, cache: Optional[BVHTraversal], extra_flags: int = 0):
+    """BFS output protocol: cache1 / cache2 are IndexPair vectors as in the reference (traverse_single.jl:88-101: both are
+    BVTT buffers there; here the BVTT lives in library scratch and cache1 only receives contacts). A too-small cache1 is
+    grown to the exact need and only the leaf level is repeated (IBVH_TRAVERSE_COUNTS_VALID)."""
+    pdt = pair_dtype(I)
+    if cache is not None:
+        if cache.cache1.dtype != pdt:
+            raise ArgumentError("eltype(cache.cache1) === IndexPair{I} must hold")
+        if cache.cache2.dtype != pdt:
+            raise ArgumentError("eltype(cache.cache2) === IndexPair{I} must hold")
+    cache1 = cache.cache1 if (cache is not None and cache.cache1.device == device) else None
+    cache2 = cache.cache2 if (cache is not None and cache.cache2.device == device) else DeviceArray.empty(0, pdt, device)
+    total, checks = C.c_int64(0), C.c_int64(0)
+    if cache1 is not None and len(cache1) > 0:
+        rc = call(extra_flags, cache1.ptr, len(cache1), total, checks)
+        if rc == capi.OK:
+            return int(total.value), int(checks.value), cache1, cache2
+        if rc != capi.ERR_CAPACITY:
+            _raise(rc, handle, "traverse (BFS)")
+    else:
+        rc = call(extra_flags, None, 0, total, checks)
+        if rc != capi.OK:
+            _raise(rc, handle, "traverse (BFS, count)")
+    need = int(total.value)
+    cache1 = DeviceArray.empty(need, pdt, device)
+    if need == 0:
+        return 0, int(checks.value), cache1, cache2
+    rc = call(extra_flags | capi.TRAVERSE_COUNTS_VALID, cache1.ptr, need, total, checks)
+    if rc != capi.OK:
+        _raise(rc, handle, "traverse (BFS, write)")
+    return int(total.value), int(checks.value), cache1, cache2
+
+
+def _bfs_narrow(narrow, tr: "BVHTraversal", leaves1: "DeviceArray", leaves2: "DeviceArray", single: bool, I: np.dtype) -> "BVHTraversal":
+    """`narrow(leaf1, leaf2)` after a positive leaf test (traverse_single_gpu.jl:188, traverse_pair_gpu.jl): post-filter over
+    the positions reported under IBVH_TRAVERSE_POSITIONS."""
+    tI = torch.int32 if I.itemsize == 4 else torch.int64
+    pos = tr.contacts.tensor.view(tI).reshape(-1, 2)
+    b1 = _gather_records(leaves1, pos[:, 0] - 1)
+    b2 = _gather_records(leaves2, pos[:, 1] - 1)
+    keep = _eval_narrow(narrow, b1, b2)
+    i1, i2 = b1["index"][keep], b2["index"][keep]
+    out = np.zeros(int(keep.sum()), pair_dtype(I))
+    if single:
+        out["a"], out["b"] = np.minimum(i1, i2), np.maximum(i1, i2)
+    else:
+        out["a"], out["b"] = i1, i2
+    return BVHTraversal(tr.start_level1, tr.start_level2, tr.num_checks, len(out), DeviceArray.from_numpy(out, device=leaves1.device), tr.cache2)
+
+
+def _traverse_bfs(bvh: BVH, bvh2, alg, start_level, start_level1, start_level2, narrow, cache) -> BVHTraversal:
+    """traverse(bvh[, bvh2], BFSTraversal(); ...) — breadth_first/traverse_single.jl:1-66, traverse_pair.jl:1-158."""
+    lib = capi.lib()
+    device = bvh.leaves.device
+    _resolve_outstanding(device.index)
+    I = bvh.index_dtype
+    pos_flag = capi.TRAVERSE_POSITIONS if narrow is not None else 0
+    use_cache = None if narrow is not None else cache
+    if bvh2 is None:
+        sl = default_start_level(bvh, alg) if start_level is None else int(start_level)
+        if not (bvh.tree.levels >= sl >= bvh.built_level):                              # traverse_single.jl:10
+            raise ArgumentError("bvh.tree.levels >= start_level >= bvh.built_level must hold")
+        if bvh.tree.real_nodes <= 1:                                                    # :17-21
+            return BVHTraversal(sl, 0, 0, 0, DeviceArray.empty(0, pair_dtype(I), device), DeviceArray.empty(0, pair_dtype(I), device))
+        cb = bvh._c_bvh()
+
+        def call(flags, p_contacts, capacity, total, checks):
+            params = capi.TraverseParams(sl, 0, -1, flags, 0, 0, None)
+            return lib.ibvh_traverse_bfs_single(bvh._handle, C.byref(cb), C.byref(params), p_contacts, capacity, C.byref(total),
+                                                C.byref(checks), _stream_ptr(device.index))
+
+        total, checks, c1, c2 = _bfs_protocol(call, bvh._handle, device, I, use_cache, pos_flag)
+        out = BVHTraversal(sl, 0, checks, total, c1, c2)
+        return _bfs_narrow(narrow, out, bvh.leaves, bvh.leaves, True, I) if narrow is not None else out
+    sl1 = default_start_level(bvh, alg) if start_level1 is None else int(start_level1)
+    sl2 = default_start_level(bvh2, alg) if start_level2 is None else int(start_level2)
+    if not (bvh.tree.levels >= sl1 >= bvh.built_level):                                 # traverse_pair.jl:10-11
+        raise ArgumentError("bvh1.tree.levels >= start_level1 >= bvh1.built_level must hold")
+    if not (bvh2.tree.levels >= sl2 >= bvh2.built_level):
+        raise ArgumentError("bvh2.tree.levels >= start_level2 >= bvh2.built_level must hold")
+    if bvh.index_dtype != bvh2.index_dtype:
+        raise ArgumentError("both BVHs must use one index type")
+    if bvh.leaves.device != bvh2.leaves.device:
+        raise ArgumentError("both BVHs must live on the same device")
+    c1b, c2b = bvh._c_bvh(), bvh2._c_bvh()
+
+    def call(flags, p_contacts, capacity, total, checks):
+        return lib.ibvh_traverse_bfs_pair(bvh._handle, C.byref(c1b), C.byref(c2b), sl1, sl2, flags, p_contacts, capacity, C.byref(total),
+                                          C.byref(checks), _stream_ptr(device.index))
+
+    total, checks, c1, c2 = _bfs_protocol(call, bvh._handle, device, I, use_cache, pos_flag)
+    out = BVHTraversal(sl1, sl2, checks, total, c1, c2)
+    return _bfs_narrow(narrow, out, bvh.leaves, bvh2.leaves, False, I) if narrow is not None else out
+
+
 def traverse(bvh: BVH, bvh2=None, alg=None, *, start_level: Optional[int] = None, start_level1: Optional[int] = None,
              start_level2: Optional[int] = None, narrow=None, cache: Optional[BVHTraversal] = None, options: BVHOptions = None,
              ordered: bool = True, reference_shaped: bool = False, packet: bool = False, walk: bool = False,
@@ -700,8 +806,14 @@ def traverse(bvh: BVH, bvh2=None, alg=None, *, start_level: Optional[int] = None
     `peer=dist.PeerGather(...)` (with `ordered=False`) fuses the sharded traversal with the all-gather of the
     contact shards: collective over the ranks, the returned (unordered) list holds the contacts of ALL ranks.
     """
+    if isinstance(bvh2, (int, np.integer)) and not isinstance(bvh2, bool):   # old interface traverse(bvh, start_level[, cache]): BFS (traverse/traverse.jl:233-241)
+        start_level, alg, bvh2 = int(bvh2), BFSTraversal(), None
     if bvh2 is not None and not isinstance(bvh2, BVH):       # traverse(bvh, alg)
         alg, bvh2 = bvh2, None
+    if isinstance(alg, BFSTraversal):
+        if defer or peer is not None or query_range is not None or reference_shaped or packet or walk:
+            raise ArgumentError("BFSTraversal takes start_level[1,2], narrow and cache only")
+        return _traverse_bfs(bvh, bvh2, alg, start_level, start_level1, start_level2, narrow, cache)
     if alg is not None and not isinstance(alg, LVTTraversal):
         raise ArgumentError(f"Traversal algorithm not implemented: {alg}")
     if narrow is not None and (defer or peer is not None):
@@ -801,8 +913,11 @@ def traverse_rays(bvh: BVH, points, directions, alg=None, *, start_level: int = 
     `points` / `directions`: (3, R) numpy arrays (the reference's column-major 3xR matrices), or torch
     CUDA tensors of shape (R, 3) — the same memory layout — in the BVH float type.
     """
-    if alg is not None and not isinstance(alg, LVTTraversal):
+    bfs = isinstance(alg, BFSTraversal)
+    if alg is not None and not bfs and not isinstance(alg, LVTTraversal):
         raise ArgumentError(f"Raytracing algorithm not implemented: {alg}")
+    if bfs and peer is not None:
+        raise ArgumentError("BFSTraversal takes start_level, narrow and cache only")
     if narrow is not None and peer is not None:
         raise ArgumentError("a custom `narrow` predicate is a post-filter on the host: not with peer=...")
     lib = capi.lib()
@@ -833,6 +948,26 @@ def traverse_rays(bvh: BVH, points, directions, alg=None, *, start_level: int = 
     if nrays == 0 and peer is None:                                                   # leaf_vs_tree.jl:22-26
         return BVHTraversal(start_level, 0, 0, 0, DeviceArray.empty(0, pair_dtype(I), device), DeviceArray.empty(0, pair_dtype(I), device))
     cb = bvh._c_bvh()
+
+    if bfs:                                        # raytrace/breadth_first/breadth_first.jl:1-66
+        def call_bfs(flags, p_contacts, capacity, total, checks):
+            params = capi.TraverseParams(int(start_level), 0, -1, flags, 0, int(id_base), None)
+            return lib.ibvh_traverse_bfs_rays(bvh._handle, C.byref(cb), p.data_ptr(), d.data_ptr(), nrays, C.byref(params), p_contacts, capacity,
+                                              C.byref(total), C.byref(checks), _stream_ptr(device.index))
+
+        total, checks, c1, c2 = _bfs_protocol(call_bfs, bvh._handle, device, I, None if narrow is not None else cache,
+                                              capi.TRAVERSE_POSITIONS if narrow is not None else 0)
+        out = BVHTraversal(start_level, 0, checks, total, c1, c2)
+        if narrow is not None:
+            tI = torch.int32 if I.itemsize == 4 else torch.int64
+            pr = out.contacts.tensor.view(tI).reshape(-1, 2)
+            lv = _gather_records(bvh.leaves, pr[:, 0] - 1)
+            rid = (pr[:, 1].to(torch.int64) - 1 - int(id_base))
+            keep = _eval_narrow(narrow, lv, p.index_select(0, rid).cpu().numpy(), d.index_select(0, rid).cpu().numpy())
+            res = np.zeros(int(keep.sum()), pair_dtype(I))
+            res["a"], res["b"] = lv["index"][keep], pr[:, 1].cpu().numpy()[keep]
+            out = BVHTraversal(start_level, 0, checks, len(res), DeviceArray.from_numpy(res, device=device), c2)
+        return out
 
     def call(flags, p_counts, p_contacts, capacity, total, peer_ref=None):
         params = capi.TraverseParams(int(start_level), 0, -1, flags, 0, int(id_base), peer_ref)

@@ -1,9 +1,9 @@
 // capi.cu — extern "C" entry points of libibvh_b200.so (declared in include/ibvh.h): argument
 // checks mirroring the reference's @argcheck's, type dispatch onto the kernel templates, workspace
 // carving and the launch sequences. No CPU fallback: without a device every call fails loudly.
-// The file is compiled once per IBVH_PART_* macro (HOST, BUILD, SINGLE, PAIR, RAYS) so that the template
-// instantiations of the five groups of entry points build in parallel (see Makefile).
-#if !defined(IBVH_PART_HOST) && !defined(IBVH_PART_BUILD) && !defined(IBVH_PART_SINGLE) && !defined(IBVH_PART_PAIR) && !defined(IBVH_PART_RAYS)
+// The file is compiled once per IBVH_PART_* macro (HOST, BUILD, SINGLE, PAIR, RAYS, BFS) so that the template
+// instantiations of the six groups of entry points build in parallel (see Makefile).
+#if !defined(IBVH_PART_HOST) && !defined(IBVH_PART_BUILD) && !defined(IBVH_PART_SINGLE) && !defined(IBVH_PART_PAIR) && !defined(IBVH_PART_RAYS) && !defined(IBVH_PART_BFS)
 #define IBVH_PART_ALL 1
 #endif
 #include <climits>
@@ -20,6 +20,7 @@
 #include "radix_sort.cuh"
 #include "reference_shaped.cuh"
 #include "traverse.cuh"
+#include "traverse_bfs.cuh"
 #include "traverse_tile.cuh"
 #include "traverse_pyramid.cuh"
 
@@ -1220,6 +1221,129 @@ int traverse_leaf_queries(ibvh_handle* h, const LQ* qleaves, int64_t n_query_tot
     return traverse_impl<KIND, true, LQ, LT, N, I>(h, qleaves, nullptr, nullptr, d, a, flags, d_counts, d_contacts, capacity, num_contacts, st);
 }
 
+// ---- BFS traversal driver (traverse_bfs.cuh) -----------------------------------------------------------------------------
+// Level-synchronous: one kernel per BVTT level, one 8-byte read-back per level (the reference reads `dst_offsets[level]`
+// the same way, traverse_single_gpu.jl:24), the two entry lists ping-pong between two library-owned buffers.
+template <class F> int bfs_dispatch_volume(int kind, int fbytes, F&& f) {
+    if (fbytes == 4) {
+        if (kind == IBVH_BSPHERE) return f(Tag<BSphere<float>>{});
+        if (kind == IBVH_BBOX) return f(Tag<BBox<float>>{});
+    }
+#ifdef IBVH_ENABLE_F64
+    if (fbytes == 8) {
+        if (kind == IBVH_BSPHERE) return f(Tag<BSphere<double>>{});
+        if (kind == IBVH_BBOX) return f(Tag<BBox<double>>{});
+    }
+#endif
+    return IBVH_ERR_UNSUPPORTED;
+}
+template <class F> int bfs_dispatch_index(int ibytes, F&& f) {
+    if (ibytes == 4) return f(Tag<int32_t>{});
+    if (ibytes == 8) return f(Tag<int64_t>{});
+    return IBVH_ERR_UNSUPPORTED;
+}
+inline int bfs_node_fbytes(const ibvh_types_t& t) { return t.node_float_bytes ? t.node_float_bytes : t.float_bytes; }
+// sizeof(BoundingVolume{V,I,M}) and offsetof(index) under natural alignment (bounding_volumes.jl:55-59)
+inline void bfs_leaf_layout(const ibvh_types_t& t, uint32_t* stride, uint32_t* index_offset) {
+    auto up = [](uint32_t v, uint32_t a) { return (v + a - 1) / a * a; };
+    const uint32_t vol = (uint32_t)(t.leaf_kind == IBVH_BSPHERE ? 4 : 6) * (uint32_t)t.float_bytes;
+    const uint32_t io = up(vol, (uint32_t)t.index_bytes);
+    const uint32_t mo = up(io + (uint32_t)t.index_bytes, (uint32_t)t.morton_bytes);
+    const uint32_t al = std::max((uint32_t)t.float_bytes, std::max((uint32_t)t.index_bytes, (uint32_t)t.morton_bytes));
+    *stride = up(mo + (uint32_t)t.morton_bytes, al);
+    *index_offset = io;
+}
+// BSphere nodes exist only over BSphere leaves (merge.jl); node floats are the leaf floats or Float32 over Float64 leaves
+inline bool bfs_types_ok(const ibvh_types_t& t) {
+    if (!types_ok(&t)) return false;
+    if (t.node_kind == IBVH_BSPHERE && t.leaf_kind != IBVH_BSPHERE) return false;
+    return true;
+}
+inline BfsSide bfs_node_side(const ibvh_bvh_t* b, const ibvh_tree_t& tree, int64_t level) {       // level < levels
+    BfsSide s{};
+    s.base = b->d_nodes;
+    s.sub = (uint32_t)(skip_of_level(tree, level) + 1);
+    s.stride = (uint32_t)((b->types.node_kind == IBVH_BSPHERE ? 4 : 6) * bfs_node_fbytes(b->types));
+    s.child_first = (uint32_t)(int64_t(1) << level);
+    s.child_nreal = (uint32_t)((int64_t(1) << level) - shr64(tree.virtual_leaves, tree.levels - (level + 1)));
+    return s;
+}
+inline BfsSide bfs_leaf_side(const ibvh_bvh_t* b, const ibvh_tree_t& tree) {
+    BfsSide s{};
+    uint32_t stride, io;
+    bfs_leaf_layout(b->types, &stride, &io);
+    s.base = b->d_leaves;
+    s.sub = (uint32_t)(int64_t(1) << (tree.levels - 1));
+    s.stride = stride;
+    s.child_first = 0; s.child_nreal = 0;
+    return s;
+}
+
+struct BfsRun {
+    ibvh_handle* h; cudaStream_t st;
+    int cur = 0;                       // buffer that holds the current list
+    unsigned long long count = 0;      // entries in it
+    long long checks = 0;              // BVHTraversal.num_checks so far
+    unsigned long long* d_counter() const { return (unsigned long long*)(h->d_small + kSmallBfs); }
+    uint2* list(int which) const { return (uint2*)h->bfs_buf[which]; }
+    int grid() const { return (int)std::min<unsigned long long>((count + kBfsTile - 1) / kBfsTile, (unsigned long long)h->sm_count * 8ull); }
+    int reserve(int which, unsigned long long entries) {
+        if (entries > (1ull << 40)) { h->set_error("BFS traversal: the BVTT would need more than 2^40 entries"); return IBVH_ERR_ALLOC; }
+        return h->reserve_bfs(which, (size_t)(entries + 4) * sizeof(uint2));
+    }
+    int begin_step(unsigned long long bound) {
+        int rc = reserve(cur ^ 1, bound);
+        if (rc != IBVH_OK) return rc;
+        IBVH_CUDA_TRY(h, cudaMemsetAsync(d_counter(), 0, 8, st));
+        return IBVH_OK;
+    }
+    int read_counter(unsigned long long* out) {
+        unsigned long long* hp = (unsigned long long*)h->h_pinned;
+        IBVH_CUDA_TRY(h, cudaMemcpyAsync(hp, d_counter(), 8, cudaMemcpyDeviceToHost, st));
+        IBVH_CUDA_TRY(h, cudaStreamSynchronize(st));
+        *out = *hp;
+        return IBVH_OK;
+    }
+    int end_step() {
+        unsigned long long c;
+        int rc = read_counter(&c);
+        if (rc != IBVH_OK) return rc;
+        count = c; checks += (long long)c; cur ^= 1;
+        return IBVH_OK;
+    }
+};
+
+// one node level: VA / VB are the volume types read on the two sides
+template <int MODE, class VA, class VB>
+int bfs_nodes_step(BfsRun& r, const BfsSide& sa, const BfsSide& sb, int self_checks) {
+    if (r.count == 0) return IBVH_OK;
+    const unsigned long long mult = (MODE == kBfsLeft || MODE == kBfsRight) ? 2ull : 4ull;
+    int rc = r.begin_step(mult * r.count);
+    if (rc != IBVH_OK) return rc;
+    { ProfScope _ps(r.h, r.st, "bfs_nodes_kernel");
+    bfs_nodes_kernel<MODE, VA, VB><<<r.grid(), kBfsThreads, 0, r.st>>>(r.list(r.cur), r.count, sa, sb, self_checks, r.list(r.cur ^ 1), r.d_counter());
+    }
+    IBVH_LAUNCH_CHECK(r.h, "bfs_nodes_kernel");
+    return r.end_step();
+}
+
+// What a BFS call that ended in IBVH_ERR_CAPACITY leaves behind, so that the repeat call with a larger cache1
+// (IBVH_TRAVERSE_COUNTS_VALID) only redoes the leaf level.
+inline bool bfs_resume(ibvh_handle* h, uint32_t flags, int kind, const void* l1, int64_t n1, const void* l2, int64_t n2, int64_t s1, int64_t s2, BfsRun* r) {
+    auto& p = h->bfs_pending;
+    const bool ok = (flags & IBVH_TRAVERSE_COUNTS_VALID) && p.valid && p.kind == kind && p.leaves1 == l1 && p.n1 == n1 && p.leaves2 == l2 && p.n2 == n2 &&
+                    p.start1 == s1 && p.start2 == s2;
+    p.valid = false;
+    if (!ok) return false;
+    r->cur = p.cur; r->count = p.count; r->checks = p.checks;
+    return true;
+}
+inline void bfs_remember(ibvh_handle* h, int kind, const void* l1, int64_t n1, const void* l2, int64_t n2, int64_t s1, int64_t s2, const BfsRun& r) {
+    auto& p = h->bfs_pending;
+    p.valid = true; p.kind = kind; p.leaves1 = l1; p.n1 = n1; p.leaves2 = l2; p.n2 = n2; p.start1 = s1; p.start2 = s2;
+    p.cur = r.cur; p.count = r.count; p.checks = r.checks;
+}
+
 int check_bvh(const ibvh_bvh_t* b, ibvh_tree_t* tree) {
     if (!b || !types_ok(&b->types)) return IBVH_ERR_ARGUMENT;
     int rc = make_tree(b->n, tree);
@@ -1362,6 +1486,7 @@ int ibvh_destroy(ibvh_handle_t* h) {
     DeviceGuard g(h->device);
     if (h->ws) cudaFree(h->ws);
     if (h->aux) cudaFree(h->aux);
+    h->free_bfs();
     for (int k = 0; k < 2; ++k) if (h->sidecars[k].buf) cudaFree(h->sidecars[k].buf);
     if (h->d_small) cudaFree(h->d_small);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
@@ -1378,6 +1503,7 @@ int ibvh_release_workspace(ibvh_handle_t* h) {
     DeviceGuard g(h->device);
     if (h->ws) { IBVH_CUDA_TRY(h, cudaFree(h->ws)); h->ws = nullptr; h->ws_bytes = 0; }
     if (h->aux) { IBVH_CUDA_TRY(h, cudaFree(h->aux)); h->aux = nullptr; h->aux_bytes = 0; }
+    h->free_bfs();
     for (int k = 0; k < 2; ++k) {
         ibvh_handle::Sidecar& sc = h->sidecars[k];
         if (sc.buf) { IBVH_CUDA_TRY(h, cudaFree(sc.buf)); sc.buf = nullptr; sc.bytes = 0; }
@@ -1807,5 +1933,256 @@ int ibvh_traverse_rays(ibvh_handle_t* h, const ibvh_bvh_t* bvh, const void* d_po
 }
 
 #endif  // IBVH_PART_RAYS
+
+#if defined(IBVH_PART_BFS) || defined(IBVH_PART_ALL)
+int64_t ibvh_bfs_default_start_level(int64_t levels, int64_t built_level) {     // breadth_first/breadth_first.jl:4-6
+    const int64_t half = levels / 2;
+    return half > built_level ? half : built_level;
+}
+
+// common argument checks of the three BFS entry points
+static int bfs_common_checks(ibvh_handle_t* h, const ibvh_bvh_t* b, void* d_contacts, int64_t* num_contacts, int64_t* num_checks) {
+    if (!h || !b || !num_contacts) return IBVH_ERR_ARGUMENT;
+    if (h->deferred.active) { h->set_error("a deferred traversal is outstanding on this handle: call ibvh_traverse_finish (or ibvh_traverse_cancel) first"); return IBVH_ERR_ARGUMENT; }
+    if (!bfs_types_ok(b->types)) return IBVH_ERR_ARGUMENT;
+    if (d_contacts && (reinterpret_cast<uintptr_t>(d_contacts) % (2u * (unsigned)b->types.index_bytes)) != 0) { h->set_error("d_contacts must be aligned to the size of one IndexPair (2 * index_bytes)"); return IBVH_ERR_ARGUMENT; }
+    *num_contacts = 0;
+    if (num_checks) *num_checks = 0;
+    return IBVH_OK;
+}
+
+int ibvh_traverse_bfs_single(ibvh_handle_t* h, const ibvh_bvh_t* bvh, const ibvh_traverse_params_t* p, void* d_contacts, int64_t capacity,
+                             int64_t* num_contacts, int64_t* num_checks, void* stream) {
+    if (!p) return IBVH_ERR_ARGUMENT;
+    int rc = bfs_common_checks(h, bvh, d_contacts, num_contacts, num_checks);
+    if (rc != IBVH_OK) return rc;
+    ibvh_tree_t tree;
+    rc = check_bvh(bvh, &tree);
+    if (rc != IBVH_OK) return rc;
+    if (!(bvh->built_level <= p->start_level && p->start_level <= tree.levels)) return IBVH_ERR_ARGUMENT;   // breadth_first/traverse_single.jl:10
+    if (tree.real_nodes <= 1) return IBVH_OK;                                                             // :17-21
+    DeviceGuard g(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    BfsRun r{h, st};
+    const int64_t levels = tree.levels, sl = p->start_level;
+    if (!bfs_resume(h, p->flags, 1, bvh->d_leaves, bvh->n, bvh->d_leaves, bvh->n, sl, sl, &r)) {
+        // initial_bvtt, traverse_single.jl:69-157: every pair (i <= j) of the real nodes of the start level
+        const int64_t first = int64_t(1) << (sl - 1);
+        const int64_t nreal = first - shr64(tree.virtual_leaves, levels - sl);
+        const bool with_self = sl != levels;
+        const unsigned long long n0 = (unsigned long long)nreal * (unsigned long long)(nreal - 1) / 2 + (with_self ? (unsigned long long)nreal : 0ull);
+        rc = r.reserve(0, n0);
+        if (rc != IBVH_OK) return rc;
+        if (n0) {
+            const unsigned long long threads = (unsigned long long)nreal * (unsigned long long)nreal;
+            { ProfScope _ps(h, st, "bfs_init_kernel");
+            bfs_init_single_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(r.list(0), (uint32_t)first, (uint32_t)nreal, with_self ? 1 : 0);
+            }
+            IBVH_LAUNCH_CHECK(h, "bfs_init_single_kernel");
+        }
+        r.cur = 0; r.count = n0; r.checks = (long long)n0;
+        rc = bfs_dispatch_volume(bvh->types.node_kind, bfs_node_fbytes(bvh->types), [&](auto ntag) -> int {
+            using N = typename decltype(ntag)::type;
+            for (int64_t level = sl; level < levels; ++level) {
+                const BfsSide s = bfs_node_side(bvh, tree, level);
+                int rc2 = bfs_nodes_step<kBfsSingle, N, N>(r, s, s, level < levels - 1 ? 1 : 0);   // self-checks only sprout above the second-to-last level
+                if (rc2 != IBVH_OK) return rc2;
+            }
+            return IBVH_OK;
+        });
+        if (rc != IBVH_OK) return rc;
+    }
+    if (num_checks) *num_checks = r.checks;
+    if (r.count == 0) return IBVH_OK;
+    // traverse_leaves!, traverse_single_gpu.jl:114-211
+    const BfsSide ls = bfs_leaf_side(bvh, tree);
+    uint32_t stride, io;
+    bfs_leaf_layout(bvh->types, &stride, &io);
+    IBVH_CUDA_TRY(h, cudaMemsetAsync(r.d_counter(), 0, 8, st));
+    rc = bfs_dispatch_volume(bvh->types.leaf_kind, bvh->types.float_bytes, [&](auto vtag) -> int {
+        using V = typename decltype(vtag)::type;
+        return bfs_dispatch_index(bvh->types.index_bytes, [&](auto itag) -> int {
+            using I = typename decltype(itag)::type;
+            { ProfScope _ps(h, st, "bfs_leaves_kernel");
+            bfs_leaves_kernel<true, V, I><<<r.grid(), kBfsThreads, 0, st>>>(r.list(r.cur), r.count, ls, ls, io, (p->flags & IBVH_TRAVERSE_POSITIONS) ? 1 : 0,
+                                                                            (IndexPair<I>*)d_contacts, d_contacts ? (unsigned long long)std::max<int64_t>(capacity, 0) : 0ull, r.d_counter());
+            }
+            IBVH_LAUNCH_CHECK(h, "bfs_leaves_kernel");
+            return IBVH_OK;
+        });
+    });
+    if (rc != IBVH_OK) return rc;
+    unsigned long long total;
+    rc = r.read_counter(&total);
+    if (rc != IBVH_OK) return rc;
+    *num_contacts = (int64_t)total;
+    if (d_contacts && (int64_t)total > capacity) { bfs_remember(h, 1, bvh->d_leaves, bvh->n, bvh->d_leaves, bvh->n, sl, sl, r); return IBVH_ERR_CAPACITY; }
+    if (!d_contacts && total > 0) bfs_remember(h, 1, bvh->d_leaves, bvh->n, bvh->d_leaves, bvh->n, sl, sl, r);   // count-only call: the write call follows
+    return IBVH_OK;
+}
+
+int ibvh_traverse_bfs_pair(ibvh_handle_t* h, const ibvh_bvh_t* bvh1, const ibvh_bvh_t* bvh2, int64_t start_level1, int64_t start_level2,
+                           uint32_t flags, void* d_contacts, int64_t capacity, int64_t* num_contacts, int64_t* num_checks, void* stream) {
+    if (!bvh2) return IBVH_ERR_ARGUMENT;
+    int rc = bfs_common_checks(h, bvh1, d_contacts, num_contacts, num_checks);
+    if (rc != IBVH_OK) return rc;
+    ibvh_tree_t t1, t2;
+    rc = check_bvh(bvh1, &t1);
+    if (rc != IBVH_OK) return rc;
+    rc = check_bvh(bvh2, &t2);
+    if (rc != IBVH_OK) return rc;
+    const ibvh_types_t &a1 = bvh1->types, &a2 = bvh2->types;
+    if (a1.leaf_kind != a2.leaf_kind || a1.float_bytes != a2.float_bytes || a1.index_bytes != a2.index_bytes ||
+        a1.morton_bytes != a2.morton_bytes || a1.node_kind != a2.node_kind || bfs_node_fbytes(a1) != bfs_node_fbytes(a2)) return IBVH_ERR_ARGUMENT;
+    if (!(bvh1->built_level <= start_level1 && start_level1 <= t1.levels)) return IBVH_ERR_ARGUMENT;     // breadth_first/traverse_pair.jl:10-11
+    if (!(bvh2->built_level <= start_level2 && start_level2 <= t2.levels)) return IBVH_ERR_ARGUMENT;
+    DeviceGuard g(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    BfsRun r{h, st};
+    if (!bfs_resume(h, flags, 2, bvh1->d_leaves, bvh1->n, bvh2->d_leaves, bvh2->n, start_level1, start_level2, &r)) {
+        // initial_bvtt, traverse_pair.jl:161-221: the product of the real nodes of the two start levels
+        const int64_t f1 = int64_t(1) << (start_level1 - 1), f2 = int64_t(1) << (start_level2 - 1);
+        const int64_t n1 = f1 - shr64(t1.virtual_leaves, t1.levels - start_level1), n2 = f2 - shr64(t2.virtual_leaves, t2.levels - start_level2);
+        const unsigned long long n0 = (unsigned long long)n1 * (unsigned long long)n2;
+        rc = r.reserve(0, n0);
+        if (rc != IBVH_OK) return rc;
+        { ProfScope _ps(h, st, "bfs_init_kernel");
+        bfs_init_product_kernel<<<(unsigned)std::min<unsigned long long>((n0 + 255) / 256, 1u << 20), 256, 0, st>>>(r.list(0), (uint32_t)f1, (unsigned long long)n1, (uint32_t)f2, (unsigned long long)n2);
+        }
+        IBVH_LAUNCH_CHECK(h, "bfs_init_product_kernel");
+        r.cur = 0; r.count = n0; r.checks = (long long)n0;
+        rc = bfs_dispatch_volume(a1.node_kind, bfs_node_fbytes(a1), [&](auto ntag) -> int {
+            using N = typename decltype(ntag)::type;
+            return bfs_dispatch_volume(a1.leaf_kind, a1.float_bytes, [&](auto vtag) -> int {
+                using V = typename decltype(vtag)::type;
+                if constexpr (N::kind == IBVH_BSPHERE && V::kind != IBVH_BSPHERE) return (int)IBVH_ERR_ARGUMENT;
+                else {
+                    // the stages of traverse_pair.jl:39-140
+                    int64_t l1 = start_level1, l2 = start_level2;
+                    int rc2 = IBVH_OK;
+                    auto both = [&]() { return bfs_nodes_step<kBfsBoth, N, N>(r, bfs_node_side(bvh1, t1, l1), bfs_node_side(bvh2, t2, l2), 0); };
+                    while (l1 < t1.levels - 1 && l2 < t2.levels - 1) { if ((rc2 = both()) != IBVH_OK) return rc2; ++l1; ++l2; }
+                    while (l1 < t1.levels - 1 && l2 == t2.levels - 1) {
+                        if ((rc2 = bfs_nodes_step<kBfsLeft, N, N>(r, bfs_node_side(bvh1, t1, l1), bfs_node_side(bvh2, t2, l2), 0)) != IBVH_OK) return rc2;
+                        ++l1;
+                    }
+                    while (l2 < t2.levels - 1 && l1 == t1.levels - 1) {
+                        if ((rc2 = bfs_nodes_step<kBfsRight, N, N>(r, bfs_node_side(bvh1, t1, l1), bfs_node_side(bvh2, t2, l2), 0)) != IBVH_OK) return rc2;
+                        ++l2;
+                    }
+                    while (l2 == t2.levels && l1 < t1.levels) {          // bvh2 already at its leaves: node (bvh1) against leaf volume (bvh2)
+                        if ((rc2 = bfs_nodes_step<kBfsLeft, N, V>(r, bfs_node_side(bvh1, t1, l1), bfs_leaf_side(bvh2, t2), 0)) != IBVH_OK) return rc2;
+                        ++l1;
+                    }
+                    while (l1 == t1.levels && l2 < t2.levels) {
+                        if ((rc2 = bfs_nodes_step<kBfsRight, V, N>(r, bfs_leaf_side(bvh1, t1), bfs_node_side(bvh2, t2, l2), 0)) != IBVH_OK) return rc2;
+                        ++l2;
+                    }
+                    if (l1 == t1.levels - 1 && l2 == t2.levels - 1) { if ((rc2 = both()) != IBVH_OK) return rc2; }
+                    return IBVH_OK;
+                }
+            });
+        });
+        if (rc != IBVH_OK) return rc;
+    }
+    if (num_checks) *num_checks = r.checks;
+    if (r.count == 0) return IBVH_OK;
+    const BfsSide ls1 = bfs_leaf_side(bvh1, t1), ls2 = bfs_leaf_side(bvh2, t2);
+    uint32_t stride, io;
+    bfs_leaf_layout(a1, &stride, &io);
+    IBVH_CUDA_TRY(h, cudaMemsetAsync(r.d_counter(), 0, 8, st));
+    rc = bfs_dispatch_volume(a1.leaf_kind, a1.float_bytes, [&](auto vtag) -> int {
+        using V = typename decltype(vtag)::type;
+        return bfs_dispatch_index(a1.index_bytes, [&](auto itag) -> int {
+            using I = typename decltype(itag)::type;
+            { ProfScope _ps(h, st, "bfs_leaves_kernel");
+            bfs_leaves_kernel<false, V, I><<<r.grid(), kBfsThreads, 0, st>>>(r.list(r.cur), r.count, ls1, ls2, io, (flags & IBVH_TRAVERSE_POSITIONS) ? 1 : 0,
+                                                                             (IndexPair<I>*)d_contacts, d_contacts ? (unsigned long long)std::max<int64_t>(capacity, 0) : 0ull, r.d_counter());
+            }
+            IBVH_LAUNCH_CHECK(h, "bfs_leaves_kernel");
+            return IBVH_OK;
+        });
+    });
+    if (rc != IBVH_OK) return rc;
+    unsigned long long total;
+    rc = r.read_counter(&total);
+    if (rc != IBVH_OK) return rc;
+    *num_contacts = (int64_t)total;
+    if ((d_contacts && (int64_t)total > capacity) || (!d_contacts && total > 0)) bfs_remember(h, 2, bvh1->d_leaves, bvh1->n, bvh2->d_leaves, bvh2->n, start_level1, start_level2, r);
+    return d_contacts && (int64_t)total > capacity ? IBVH_ERR_CAPACITY : IBVH_OK;
+}
+
+int ibvh_traverse_bfs_rays(ibvh_handle_t* h, const ibvh_bvh_t* bvh, const void* d_points, const void* d_directions, int64_t nrays,
+                           const ibvh_traverse_params_t* p, void* d_contacts, int64_t capacity, int64_t* num_contacts, int64_t* num_checks, void* stream) {
+    if (!p || nrays < 0) return IBVH_ERR_ARGUMENT;
+    int rc = bfs_common_checks(h, bvh, d_contacts, num_contacts, num_checks);
+    if (rc != IBVH_OK) return rc;
+    ibvh_tree_t tree;
+    rc = check_bvh(bvh, &tree);
+    if (rc != IBVH_OK) return rc;
+    if (!(bvh->built_level <= p->start_level && p->start_level <= tree.levels)) return IBVH_ERR_ARGUMENT;   // raytrace/breadth_first/breadth_first.jl:12
+    if (bfs_node_fbytes(bvh->types) != bvh->types.float_bytes) return IBVH_ERR_ARGUMENT;                    // isintersection.jl:1-5: one float type
+    if (nrays == 0) return IBVH_OK;                                                                         // :25-29
+    if (!d_points || !d_directions) return IBVH_ERR_ARGUMENT;
+    if (nrays >= (int64_t(1) << 32)) { h->set_error("BFS ray traversal: ray ids are kept in 32 bits (nrays < 2^32)"); return IBVH_ERR_UNSUPPORTED; }
+    DeviceGuard g(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    BfsRun r{h, st};
+    const int64_t levels = tree.levels, sl = p->start_level;
+    if (!bfs_resume(h, p->flags, 3, bvh->d_leaves, bvh->n, d_points, nrays, sl, sl, &r)) {
+        const int64_t first = int64_t(1) << (sl - 1);
+        const int64_t nreal = first - shr64(tree.virtual_leaves, levels - sl);
+        const unsigned long long n0 = (unsigned long long)nreal * (unsigned long long)nrays;
+        rc = r.reserve(0, n0);
+        if (rc != IBVH_OK) return rc;
+        { ProfScope _ps(h, st, "bfs_init_kernel");
+        bfs_init_product_kernel<<<(unsigned)std::min<unsigned long long>((n0 + 255) / 256, 1u << 20), 256, 0, st>>>(r.list(0), (uint32_t)first, (unsigned long long)nreal, 1u, (unsigned long long)nrays);
+        }
+        IBVH_LAUNCH_CHECK(h, "bfs_init_product_kernel");
+        r.cur = 0; r.count = n0; r.checks = (long long)n0;
+        rc = bfs_dispatch_volume(bvh->types.node_kind, bvh->types.float_bytes, [&](auto ntag) -> int {
+            using N = typename decltype(ntag)::type; using T = typename N::value_type;
+            for (int64_t level = sl; level < levels && r.count; ++level) {
+                int rc2 = r.begin_step(2ull * r.count);
+                if (rc2 != IBVH_OK) return rc2;
+                { ProfScope _ps(h, st, "bfs_rays_nodes_kernel");
+                bfs_rays_nodes_kernel<N><<<r.grid(), kBfsThreads, 0, st>>>(r.list(r.cur), r.count, bfs_node_side(bvh, tree, level), (const T*)d_points, (const T*)d_directions,
+                                                                            r.list(r.cur ^ 1), r.d_counter());
+                }
+                IBVH_LAUNCH_CHECK(h, "bfs_rays_nodes_kernel");
+                if ((rc2 = r.end_step()) != IBVH_OK) return rc2;
+            }
+            return IBVH_OK;
+        });
+        if (rc != IBVH_OK) return rc;
+    }
+    if (num_checks) *num_checks = r.checks;
+    if (r.count == 0) return IBVH_OK;
+    const BfsSide ls = bfs_leaf_side(bvh, tree);
+    uint32_t stride, io;
+    bfs_leaf_layout(bvh->types, &stride, &io);
+    IBVH_CUDA_TRY(h, cudaMemsetAsync(r.d_counter(), 0, 8, st));
+    rc = bfs_dispatch_volume(bvh->types.leaf_kind, bvh->types.float_bytes, [&](auto vtag) -> int {
+        using V = typename decltype(vtag)::type; using T = typename V::value_type;
+        return bfs_dispatch_index(bvh->types.index_bytes, [&](auto itag) -> int {
+            using I = typename decltype(itag)::type;
+            { ProfScope _ps(h, st, "bfs_rays_leaves_kernel");
+            bfs_rays_leaves_kernel<V, I><<<r.grid(), kBfsThreads, 0, st>>>(r.list(r.cur), r.count, ls, (const T*)d_points, (const T*)d_directions, io,
+                                                                           (p->flags & IBVH_TRAVERSE_POSITIONS) ? 1 : 0, (long long)p->id_base,
+                                                                           (IndexPair<I>*)d_contacts, d_contacts ? (unsigned long long)std::max<int64_t>(capacity, 0) : 0ull, r.d_counter());
+            }
+            IBVH_LAUNCH_CHECK(h, "bfs_rays_leaves_kernel");
+            return IBVH_OK;
+        });
+    });
+    if (rc != IBVH_OK) return rc;
+    unsigned long long total;
+    rc = r.read_counter(&total);
+    if (rc != IBVH_OK) return rc;
+    *num_contacts = (int64_t)total;
+    if ((d_contacts && (int64_t)total > capacity) || (!d_contacts && total > 0)) bfs_remember(h, 3, bvh->d_leaves, bvh->n, d_points, nrays, sl, sl, r);
+    return d_contacts && (int64_t)total > capacity ? IBVH_ERR_CAPACITY : IBVH_OK;
+}
+#endif  // IBVH_PART_BFS
 
 }  // extern "C"

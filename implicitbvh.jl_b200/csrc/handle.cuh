@@ -62,6 +62,32 @@ struct ibvh_handle {
         return IBVH_OK;
     }
 
+    // BFS traversal (traverse_bfs.cuh): the two ping-pong lists of BVTT entries. Grow-only, allocated apart from each
+    // other because the destination of a level may have to grow while the source is still being read.
+    char* bfs_buf[2] = {nullptr, nullptr};
+    size_t bfs_bytes[2] = {0, 0};
+    int reserve_bfs(int which, size_t bytes) {
+        if (bytes <= bfs_bytes[which]) return IBVH_OK;
+        if (bfs_buf[which]) { cudaFree(bfs_buf[which]); bfs_buf[which] = nullptr; bfs_bytes[which] = 0; }
+        size_t want = bytes + (bytes >> 3) + (1u << 16);
+        cudaError_t e = cudaMalloc((void**)&bfs_buf[which], want);
+        if (e != cudaSuccess) { set_cuda_error(e, "cudaMalloc(BFS list)"); bfs_buf[which] = nullptr; cudaGetLastError(); return IBVH_ERR_ALLOC; }
+        bfs_bytes[which] = want;
+        return IBVH_OK;
+    }
+    void free_bfs() {
+        for (int k = 0; k < 2; ++k) { if (bfs_buf[k]) cudaFree(bfs_buf[k]); bfs_buf[k] = nullptr; bfs_bytes[k] = 0; }
+        bfs_pending.valid = false;
+    }
+    // leaf-level list of a BFS call that returned IBVH_ERR_CAPACITY (the repeat call only redoes the leaf level)
+    struct BfsPending {
+        bool valid = false;
+        int kind = 0, cur = 0;
+        const void *leaves1 = nullptr, *leaves2 = nullptr;
+        long long n1 = 0, n2 = 0, start1 = 0, start2 = 0, checks = 0;
+        unsigned long long count = 0;
+    } bfs_pending;
+
     // Sidecar of a build (round 2): what the pyramid traversal used to re-derive from the tree on EVERY call — the leaf
     // volumes as 16-byte records, the refinement's node levels in 64-byte aligned runs, the three finest levels of the
     // query pyramid — is written once by the build's own gather / merge kernels (they hold the data in registers /
@@ -162,6 +188,7 @@ constexpr size_t kSmallStats = 128;       // 3 x u64
 constexpr size_t kSmallTickets = 256;     // 16 x u32 tile tickets (one per radix pass)
 constexpr size_t kSmallBoundsF = 512;     // 6 floats/doubles: padded bounds actually used
 constexpr size_t kSmallFixup = 960;       // 2 x u32: lengths of the long-segment lists of the ordered fix-up
+constexpr size_t kSmallBfs = 1024;        // u64: entries appended by the current BFS level
 
 // RAII scope that brackets one kernel launch with events when profiling is enabled.
 struct ProfScope {

@@ -1,0 +1,313 @@
+// traverse_bfs.cuh — BFSTraversal: simultaneous breadth-first descent over the bounding-volume test tree (BVTT).
+// Replaces src/traverse/breadth_first/{traverse_single,traverse_pair}*.jl and src/raytrace/breadth_first/*.jl.
+//
+// The reference's GPU backend runs one kernel per level: a thread takes one BVTT entry (two implicit node indices, or a
+// node and a ray id), tests the two volumes, and on contact appends the 1..4 pairs of children to the next level's list
+// through a per-block buffer and one global atomic per block; the last level tests leaf volumes and appends contacts the
+// same way. Its lists are therefore sets (the append order depends on block scheduling), and so are ours: same entries at
+// every level (hence the same `num_checks`) and the same contacts, in unspecified order.
+//
+// What is different here:
+//   * entries are 8 bytes ((u32, u32): implicit indices are < 2^32 because levels <= 32) whatever the index type, and live
+//     in two library-owned ping-pong buffers — the caller's cache1 only ever receives contacts;
+//   * a thread owns FOUR consecutive entries (two 16-byte loads): consecutive entries are mostly the four child pairs of
+//     one parent pair, so their node loads hit the same sectors; the block reserves its output with ONE atomic per 1024
+//     entries (shuffle scan + one shared-memory round), and every thread's children land contiguously;
+//   * the node kernels depend on the NODE type only and the leaf kernels on (leaf volume, index type) only — leaves are
+//     read through a byte stride — so the Morton type of the leaves does not multiply the instantiations;
+//   * "is the right child virtual" is one compare against the child level's real-node count (passed by the host) instead
+//     of the ilog2 + shifts of implicit_tree.jl:191-199 per entry.
+#pragma once
+#include "common.cuh"
+
+namespace ibvh {
+
+constexpr int kBfsThreads = 256;
+constexpr int kBfsItems = 4;                      // entries per thread
+constexpr int kBfsTile = kBfsThreads * kBfsItems;
+
+// One side of a BVTT level: where its volumes are and how its children behave.
+struct BfsSide {
+    const void* base;          // nodes of this level's tree (whole node array) or leaves
+    uint32_t sub;              // memory position (0-based) = implicit - sub: num_skips + 1 for a node level, 2^(levels-1) for leaves
+    uint32_t stride;           // bytes between elements (leaf arrays: sizeof(BoundingVolume))
+    uint32_t child_first;      // implicit index of the first node of the CHILD level (2^level)
+    uint32_t child_nreal;      // real nodes on the child level: child 2i+1 is virtual iff 2i+1 - child_first >= child_nreal
+};
+IBVH_D bool bfs_right_real(const BfsSide& s, uint32_t implicit) { return 2u * implicit + 1u - s.child_first < s.child_nreal; }
+template <class V> IBVH_D V bfs_load(const BfsSide& s, uint32_t implicit) {
+    const char* p = (const char*)s.base + (size_t)(implicit - s.sub) * s.stride;
+    V v;
+    using T = typename V::value_type;
+    const T* f = reinterpret_cast<const T*>(p);
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(V) / sizeof(T)); ++k) reinterpret_cast<T*>(&v)[k] = __ldg(f + k);
+    return v;
+}
+
+// ---- tests between volumes of possibly different float types (pair traversal started at / reaching a leaf level on one
+// side only: traverse_pair_gpu.jl `_traverse_nodes_leaves_*`; Julia promotes operation by operation == convert first) ----
+template <class C, class T> IBVH_D BBox<C> bfs_box_as(const BBox<T>& b) {
+    BBox<C> o;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { o.lo[k] = (C)b.lo[k]; o.up[k] = (C)b.up[k]; }
+    return o;
+}
+template <class C, class T> IBVH_D BSphere<C> bfs_sphere_as(const BSphere<T>& s) {
+    BSphere<C> o;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) o.x[k] = (C)s.x[k];
+    o.r = (C)s.r;
+    return o;
+}
+template <class TA, class TB> struct BfsCommon { using type = float; };
+template <> struct BfsCommon<double, float> { using type = double; };
+template <> struct BfsCommon<float, double> { using type = double; };
+template <> struct BfsCommon<double, double> { using type = double; };
+template <class TA, class TB> IBVH_D bool bfs_contact(const BBox<TA>& a, const BBox<TB>& b) {
+    using C = typename BfsCommon<TA, TB>::type;
+    return iscontact(bfs_box_as<C>(a), bfs_box_as<C>(b));
+}
+template <class TA, class TB> IBVH_D bool bfs_contact(const BSphere<TA>& a, const BSphere<TB>& b) {
+    using C = typename BfsCommon<TA, TB>::type;
+    return iscontact(bfs_sphere_as<C>(a), bfs_sphere_as<C>(b));
+}
+template <class TA, class TB> IBVH_D bool bfs_contact(const BSphere<TA>& a, const BBox<TB>& b) {     // iscontact.jl:17-23
+    return bfs_contact(to_box(a), b);                                                                // box of the sphere in ITS type
+}
+template <class TA, class TB> IBVH_D bool bfs_contact(const BBox<TA>& a, const BSphere<TB>& b) { return bfs_contact(b, a); }
+
+// ---- block-level reservation: every thread has `k` outputs; returns where its first one goes --------------------------------
+// One shuffle scan per warp, one shared-memory round over the warp totals, ONE global atomic per block call.
+IBVH_D unsigned long long bfs_reserve(uint32_t k, unsigned long long* counter, uint32_t* s_warp, unsigned long long* s_base) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t incl = k;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    if (lane == 31) s_warp[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        uint32_t t = lane < kBfsThreads / 32 ? s_warp[lane] : 0u;
+        uint32_t ti = t;
+#pragma unroll
+        for (int d = 1; d < kBfsThreads / 32; d <<= 1) {
+            uint32_t o = __shfl_up_sync(0xffffffffu, ti, d);
+            if (lane >= d) ti += o;
+        }
+        if (lane < kBfsThreads / 32) s_warp[lane] = ti - t;                 // exclusive offset of each warp
+        if (lane == kBfsThreads / 32 - 1) *s_base = ti ? atomicAdd(counter, (unsigned long long)ti) : 0ull;
+    }
+    __syncthreads();
+    const unsigned long long pos = *s_base + s_warp[w] + (incl - k);
+    __syncthreads();                                                        // s_warp / s_base are reused by the next call
+    return pos;
+}
+
+// Loads the (up to) four consecutive entries of a thread. Buffers are 256-byte aligned and a thread's first entry index is
+// a multiple of 4, so the two 16-byte loads are aligned; entries past `count` read as zero (implicit index 0 = "none").
+IBVH_D void bfs_load_entries(const uint2* src, unsigned long long first, unsigned long long count, uint2 e[kBfsItems]) {
+    if (first + kBfsItems <= count) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(src + first));
+        const uint4 b = __ldg(reinterpret_cast<const uint4*>(src + first) + 1);
+        e[0] = make_uint2(a.x, a.y); e[1] = make_uint2(a.z, a.w); e[2] = make_uint2(b.x, b.y); e[3] = make_uint2(b.z, b.w);
+    } else {
+#pragma unroll
+        for (int j = 0; j < kBfsItems; ++j) e[j] = first + j < count ? __ldg(src + first + j) : make_uint2(0u, 0u);
+    }
+}
+
+// ---- node levels ------------------------------------------------------------------------------------------------------------
+// MODE: which sides sprout, as in traverse_pair.jl:39-140.
+enum { kBfsSingle = 0, kBfsBoth = 1, kBfsLeft = 2, kBfsRight = 3 };
+
+// VA / VB: volume types read on the two sides (node types; a leaf volume type on the side that already is at its leaves).
+template <int MODE, class VA, class VB>
+__global__ void __launch_bounds__(kBfsThreads) bfs_nodes_kernel(const uint2* __restrict__ src, unsigned long long count, BfsSide sa, BfsSide sb,
+                                                                int self_checks, uint2* __restrict__ dst, unsigned long long* counter) {
+    __shared__ uint32_t s_warp[kBfsThreads / 32];
+    __shared__ unsigned long long s_base;
+    const unsigned long long tiles = (count + kBfsTile - 1) / kBfsTile;
+    for (unsigned long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const unsigned long long first = tile * kBfsTile + (unsigned long long)threadIdx.x * kBfsItems;
+        uint2 e[kBfsItems];
+        bfs_load_entries(src, first, count, e);
+        // 4 bits per entry: which of (left,left) (left,right) (right,left) (right,right) [or the one-sided forms] to emit
+        uint32_t mask = 0, k = 0;
+#pragma unroll
+        for (int j = 0; j < kBfsItems; ++j) {
+            if (e[j].x == 0u) continue;
+            uint32_t m = 0;
+            if (MODE == kBfsSingle && e[j].x == e[j].y) {
+                // self-check (traverse_single_gpu.jl:63-80): (l,l) (l,r) (r,r); below the second-to-last level only (l,r)
+                const bool rr = bfs_right_real(sa, e[j].x);
+                if (self_checks) m = rr ? 0xBu : 0x1u;          // bits: 0 = (2a,2b), 1 = (2a,2b+1), 2 = (2a+1,2b), 3 = (2a+1,2b+1)
+                else m = rr ? 0x2u : 0x0u;
+            } else {
+                const VA va = bfs_load<VA>(sa, e[j].x);
+                const VB vb = bfs_load<VB>(sb, e[j].y);
+                if (bfs_contact(va, vb)) {
+                    if (MODE == kBfsSingle) m = bfs_right_real(sb, e[j].y) ? 0xFu : 0x5u;       // node 1 is left of node 2: its children are real
+                    else if (MODE == kBfsBoth) {
+                        const bool r1 = bfs_right_real(sa, e[j].x), r2 = bfs_right_real(sb, e[j].y);
+                        m = 0x1u | (r2 ? 0x2u : 0u) | (r1 ? 0x4u : 0u) | (r1 && r2 ? 0x8u : 0u);
+                    } else if (MODE == kBfsLeft) m = 0x1u | (bfs_right_real(sa, e[j].x) ? 0x4u : 0u);   // (2a, b), (2a+1, b)
+                    else m = 0x1u | (bfs_right_real(sb, e[j].y) ? 0x2u : 0u);                           // (a, 2b), (a, 2b+1)
+                }
+            }
+            mask |= m << (4 * j);
+            k += __popc(m);
+        }
+        unsigned long long pos = bfs_reserve(k, counter, s_warp, &s_base);
+#pragma unroll
+        for (int j = 0; j < kBfsItems; ++j) {
+            const uint32_t m = (mask >> (4 * j)) & 0xFu;
+            if (!m) continue;
+            const uint32_t a2 = (MODE == kBfsRight) ? e[j].x : 2u * e[j].x, b2 = (MODE == kBfsLeft) ? e[j].y : 2u * e[j].y;
+            if (m & 1u) dst[pos++] = make_uint2(a2, b2);
+            if (m & 2u) dst[pos++] = make_uint2(a2, b2 + 1u);
+            if (m & 4u) dst[pos++] = make_uint2(a2 + 1u, b2);
+            if (m & 8u) dst[pos++] = make_uint2(a2 + 1u, b2 + 1u);
+        }
+    }
+}
+
+// ---- leaf level: contacts (traverse_single_gpu.jl:143-211, traverse_pair_gpu.jl `_traverse_leaves_pair_gpu!`) --------------------
+// SORT_PAIR: single tree — the indices of a contact are emitted in ascending order; pair — (index in bvh1, index in bvh2).
+// positions != 0: leaf positions (1-based) instead of the leaves' indices (how the caller applies `narrow`).
+template <bool SORT_PAIR, class V, class I>
+__global__ void __launch_bounds__(kBfsThreads) bfs_leaves_kernel(const uint2* __restrict__ src, unsigned long long count, BfsSide sa, BfsSide sb,
+                                                                 uint32_t index_offset, int positions, IndexPair<I>* __restrict__ out,
+                                                                 unsigned long long capacity, unsigned long long* counter) {
+    __shared__ uint32_t s_warp[kBfsThreads / 32];
+    __shared__ unsigned long long s_base;
+    const unsigned long long tiles = (count + kBfsTile - 1) / kBfsTile;
+    for (unsigned long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const unsigned long long first = tile * kBfsTile + (unsigned long long)threadIdx.x * kBfsItems;
+        uint2 e[kBfsItems];
+        bfs_load_entries(src, first, count, e);
+        uint32_t mask = 0;
+#pragma unroll
+        for (int j = 0; j < kBfsItems; ++j) {
+            if (e[j].x == 0u) continue;
+            const V va = bfs_load<V>(sa, e[j].x);
+            const V vb = bfs_load<V>(sb, e[j].y);
+            if (iscontact(va, vb)) mask |= 1u << j;
+        }
+        unsigned long long pos = bfs_reserve(__popc(mask), counter, s_warp, &s_base);
+#pragma unroll
+        for (int j = 0; j < kBfsItems; ++j) {
+            if (!((mask >> j) & 1u)) continue;
+            I ia, ib;
+            if (positions) { ia = (I)(e[j].x - sa.sub + 1u); ib = (I)(e[j].y - sb.sub + 1u); }
+            else {
+                ia = *reinterpret_cast<const I*>((const char*)sa.base + (size_t)(e[j].x - sa.sub) * sa.stride + index_offset);
+                ib = *reinterpret_cast<const I*>((const char*)sb.base + (size_t)(e[j].y - sb.sub) * sb.stride + index_offset);
+                if (SORT_PAIR && ia > ib) { const I t = ia; ia = ib; ib = t; }
+            }
+            if (pos < capacity) out[pos] = IndexPair<I>{ia, ib};
+            ++pos;
+        }
+    }
+}
+
+// ---- rays (raytrace/breadth_first/raytrace_gpu.jl): entries are (implicit node index, 1-based ray id) ------------------------
+template <class T> IBVH_D void bfs_load_ray(const T* points, const T* dirs, uint32_t iray, T p[3], T d[3]) {
+    const size_t o = (size_t)(iray - 1u) * 3u;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { p[k] = __ldg(points + o + k); d[k] = __ldg(dirs + o + k); }
+}
+template <class N>
+__global__ void __launch_bounds__(kBfsThreads) bfs_rays_nodes_kernel(const uint2* __restrict__ src, unsigned long long count, BfsSide sa,
+                                                                     const typename N::value_type* __restrict__ points,
+                                                                     const typename N::value_type* __restrict__ dirs,
+                                                                     uint2* __restrict__ dst, unsigned long long* counter) {
+    using T = typename N::value_type;
+    __shared__ uint32_t s_warp[kBfsThreads / 32];
+    __shared__ unsigned long long s_base;
+    const unsigned long long tiles = (count + kBfsTile - 1) / kBfsTile;
+    for (unsigned long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const unsigned long long first = tile * kBfsTile + (unsigned long long)threadIdx.x * kBfsItems;
+        uint2 e[kBfsItems];
+        bfs_load_entries(src, first, count, e);
+        uint32_t mask = 0, k = 0;
+#pragma unroll
+        for (int j = 0; j < kBfsItems; ++j) {
+            if (e[j].x == 0u) continue;
+            T p[3], d[3];
+            bfs_load_ray(points, dirs, e[j].y, p, d);
+            if (isintersection(bfs_load<N>(sa, e[j].x), p, d)) {
+                const uint32_t m = bfs_right_real(sa, e[j].x) ? 3u : 1u;
+                mask |= m << (2 * j);
+                k += __popc(m);
+            }
+        }
+        unsigned long long pos = bfs_reserve(k, counter, s_warp, &s_base);
+#pragma unroll
+        for (int j = 0; j < kBfsItems; ++j) {
+            const uint32_t m = (mask >> (2 * j)) & 3u;
+            if (m & 1u) dst[pos++] = make_uint2(2u * e[j].x, e[j].y);
+            if (m & 2u) dst[pos++] = make_uint2(2u * e[j].x + 1u, e[j].y);
+        }
+    }
+}
+template <class V, class I>
+__global__ void __launch_bounds__(kBfsThreads) bfs_rays_leaves_kernel(const uint2* __restrict__ src, unsigned long long count, BfsSide sa,
+                                                                      const typename V::value_type* __restrict__ points,
+                                                                      const typename V::value_type* __restrict__ dirs,
+                                                                      uint32_t index_offset, int positions, long long id_base,
+                                                                      IndexPair<I>* __restrict__ out, unsigned long long capacity,
+                                                                      unsigned long long* counter) {
+    using T = typename V::value_type;
+    __shared__ uint32_t s_warp[kBfsThreads / 32];
+    __shared__ unsigned long long s_base;
+    const unsigned long long tiles = (count + kBfsTile - 1) / kBfsTile;
+    for (unsigned long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const unsigned long long first = tile * kBfsTile + (unsigned long long)threadIdx.x * kBfsItems;
+        uint2 e[kBfsItems];
+        bfs_load_entries(src, first, count, e);
+        uint32_t mask = 0;
+#pragma unroll
+        for (int j = 0; j < kBfsItems; ++j) {
+            if (e[j].x == 0u) continue;
+            T p[3], d[3];
+            bfs_load_ray(points, dirs, e[j].y, p, d);
+            if (isintersection(bfs_load<V>(sa, e[j].x), p, d)) mask |= 1u << j;
+        }
+        unsigned long long pos = bfs_reserve(__popc(mask), counter, s_warp, &s_base);
+#pragma unroll
+        for (int j = 0; j < kBfsItems; ++j) {
+            if (!((mask >> j) & 1u)) continue;
+            I ia;
+            if (positions) ia = (I)(e[j].x - sa.sub + 1u);
+            else ia = *reinterpret_cast<const I*>((const char*)sa.base + (size_t)(e[j].x - sa.sub) * sa.stride + index_offset);
+            if (pos < capacity) out[pos] = IndexPair<I>{ia, (I)(id_base + (long long)e[j].y)};
+            ++pos;
+        }
+    }
+}
+
+// ---- initial BVTT (traverse_single.jl:69-157, traverse_pair.jl:161-221, raytrace/breadth_first/breadth_first.jl:69-140) --------
+// Single tree: all pairs (i, j), i <= j (i < j when starting at the leaf level), of the real nodes of the start level, row-major
+// as in the reference's CPU loop; entry positions are computed in closed form (no float sqrt as in the reference's tri_ij).
+static __global__ void bfs_init_single_kernel(uint2* dst, uint32_t first, uint32_t nreal, int with_self) {
+    const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long total = (unsigned long long)nreal * nreal;
+    if (t >= total) return;
+    const uint32_t i = (uint32_t)(t / nreal), j = (uint32_t)(t % nreal);
+    if (j < i || (!with_self && j == i)) return;
+    // rows before i hold (nreal - r) entries each with the diagonal, (nreal - 1 - r) without
+    const unsigned long long n = nreal, r = i;
+    const unsigned long long row0 = with_self ? r * n - r * (r - 1) / 2 : r * (n - 1) - r * (r - 1) / 2;
+    dst[row0 + (j - i) - (with_self ? 0 : 1)] = make_uint2(first + i, first + j);
+}
+// Pair / rays: the full product, row-major: entry k = (first_a + k / nb, first_b + k % nb)
+static __global__ void bfs_init_product_kernel(uint2* dst, uint32_t first_a, unsigned long long na, uint32_t first_b, unsigned long long nb) {
+    const unsigned long long total = na * nb;
+    for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (unsigned long long)gridDim.x * blockDim.x)
+        dst[t] = make_uint2(first_a + (uint32_t)(t / nb), first_b + (uint32_t)(t % nb));
+}
+
+}  // namespace ibvh

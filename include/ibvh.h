@@ -186,6 +186,8 @@ IBVH_API int64_t ibvh_num_nodes(int64_t n);   /* real_nodes - real_leaves, build
  *                     permutation x2, look-back words, and a copy of the leaves on the in-place path;
  *   sidecars          two slots of ~30 B / leaf (16-byte volume records, aligned node levels, pyramid levels, index array)
  *                     left by the two most recent pyramid-eligible builds (see ibvh_bvh_t.build_id);
+ *   BFS lists         the two ping-pong BVTT lists of the BFS traversals (8 bytes per entry; the destination of a level is
+ *                     sized 4x / 2x its source like the reference's bvtt2, traverse_single.jl:42);
  *   traversal scratch pair lists + quantised boxes (~70 B / leaf at 10 M uniformly random spheres; grows with the
  *                     density of the scene) and, for ORDERED traversals with a contacts buffer, a 16-byte-per-contact hit
  *                     stash sized from the contact totals this handle has SEEN (last total + 25 %, or 6 per query before the
@@ -273,6 +275,39 @@ IBVH_API int ibvh_traverse_pair(ibvh_handle_t* h, const ibvh_bvh_t* queries, con
 IBVH_API int ibvh_traverse_rays(ibvh_handle_t* h, const ibvh_bvh_t* bvh, const void* d_points, const void* d_directions,
                        int64_t nrays, const ibvh_traverse_params_t* params, void* d_counts, void* d_contacts,
                        int64_t capacity, int64_t* num_contacts, void* stream);
+
+/* ---- BFS traversals ------------------------------------------------------------------------ */
+/* BFSTraversal (src/traverse/traverse.jl:19-24): simultaneous breadth-first descent, node pairs level by level. The
+ * BVTT lists (8 bytes per entry, 10-20x the contacts at their widest) live in two grow-only buffers the library owns;
+ * `d_contacts` only ever receives contacts. Like the reference's GPU backend (atomic appends, traverse_single_gpu.jl:
+ * 84-101) the contacts come back as a SET in unspecified order; *num_checks (may be NULL) is BVHTraversal.num_checks =
+ * the sum of the BVTT list lengths over the levels (traverse_single.jl:28,51), which is deterministic.
+ * Output protocol: d_contacts == NULL counts only; more contacts than `capacity` -> IBVH_ERR_CAPACITY with the need in
+ * *num_contacts. Either way the library keeps the leaf-level list: repeating the SAME call with a large enough buffer and
+ * IBVH_TRAVERSE_COUNTS_VALID only redoes the leaf level. Other flags honoured: IBVH_TRAVERSE_POSITIONS.
+ * One host read-back per level (the reference reads dst_offsets[level] the same way). */
+/* default_start_level(bvh, ::BFSTraversal) = max(levels / 2, built_level), breadth_first/breadth_first.jl:4-6 */
+IBVH_API int64_t ibvh_bfs_default_start_level(int64_t levels, int64_t built_level);
+
+/* traverse(bvh, BFSTraversal(); start_level), breadth_first/traverse_single.jl:1-157 + traverse_single_gpu.jl:
+ * every pair of the real nodes of params->start_level (self pairs included) is descended; contacts are emitted as
+ * (smaller index, larger index). params: start_level and flags are read. */
+IBVH_API int ibvh_traverse_bfs_single(ibvh_handle_t* h, const ibvh_bvh_t* bvh, const ibvh_traverse_params_t* params,
+                             void* d_contacts, int64_t capacity, int64_t* num_contacts, int64_t* num_checks, void* stream);
+
+/* traverse(bvh1, bvh2, BFSTraversal(); start_level1, start_level2), breadth_first/traverse_pair.jl:1-221 +
+ * traverse_pair_gpu.jl: both trees descend in step, then the deeper one alone, down to leaf pairs; contacts are
+ * (index in bvh1, index in bvh2). Both BVHs must share leaf / index / Morton / node types. */
+IBVH_API int ibvh_traverse_bfs_pair(ibvh_handle_t* h, const ibvh_bvh_t* bvh1, const ibvh_bvh_t* bvh2, int64_t start_level1,
+                           int64_t start_level2, uint32_t flags, void* d_contacts, int64_t capacity, int64_t* num_contacts,
+                           int64_t* num_checks, void* stream);
+
+/* traverse_rays(bvh, points, directions, BFSTraversal(); start_level), raytrace/breadth_first/breadth_first.jl:1-140 +
+ * raytrace_gpu.jl: entries are (node, ray); emits (leaf.index, id_base + r + 1). nrays < 2^32.
+ * params: start_level, flags and id_base are read. */
+IBVH_API int ibvh_traverse_bfs_rays(ibvh_handle_t* h, const ibvh_bvh_t* bvh, const void* d_points, const void* d_directions,
+                           int64_t nrays, const ibvh_traverse_params_t* params, void* d_contacts, int64_t capacity,
+                           int64_t* num_contacts, int64_t* num_checks, void* stream);
 
 /* ---- per-kernel timing (measurement aid; bench.py's roofline uses it) ----------------------
  * When enabled, every kernel launch of this handle is bracketed by CUDA events on the launching

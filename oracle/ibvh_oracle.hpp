@@ -665,4 +665,214 @@ inline int64_t two_pass(int64_t nqueries, int num_threads, int64_t min_elems, In
     return total;
 }
 
+// ---------------------------------------------------------------------------------------------
+// BFS traversals — src/traverse/breadth_first/*.jl, src/raytrace/breadth_first/*.jl (CPU bodies).
+// The reference's task-parallel form gives every task a contiguous range of the source list and
+// compacts the tasks' outputs in task order (traverse_single_cpu.jl:28-56), so its lists are the
+// ones this sequential loop produces, whatever the thread count. (The reference's GPU backend
+// appends with atomics: same lists as sets, order unspecified.)
+// A BVTT entry is a pair of implicit indices (or implicit index, ray id), 1-based as in Julia.
+// ---------------------------------------------------------------------------------------------
+struct BvttPair { int64_t a, b; };
+
+// Node-vs-leaf-volume tests of the pair traversal's special cases (traverse_pair_cpu.jl, the
+// `traverse_nodes_leaves_*` bodies): Julia promotes mixed float types operation by operation, which is
+// the same as converting both operands to the wider type first (the conversion is exact).
+template <class TA, class TB> inline bool iscontact_promoted(const BBox<TA>& a, const BBox<TB>& b) {
+    using C = typename std::common_type<TA, TB>::type;
+    return ((C)a.up[0] >= (C)b.lo[0] && (C)a.lo[0] <= (C)b.up[0]) &&
+           ((C)a.up[1] >= (C)b.lo[1] && (C)a.lo[1] <= (C)b.up[1]) &&
+           ((C)a.up[2] >= (C)b.lo[2] && (C)a.lo[2] <= (C)b.up[2]);
+}
+template <class TA, class TB> inline bool iscontact_promoted(const BSphere<TA>& a, const BSphere<TB>& b) {
+    using C = typename std::common_type<TA, TB>::type;
+    C ax[3] = {(C)a.x[0], (C)a.x[1], (C)a.x[2]}, bx[3] = {(C)b.x[0], (C)b.x[1], (C)b.x[2]};
+    return dist3sq(ax, bx) <= ((C)a.r + (C)b.r) * ((C)a.r + (C)b.r);
+}
+template <class TA, class TB> inline bool iscontact_promoted(const BSphere<TA>& a, const BBox<TB>& b) {   // iscontact.jl:17-23
+    BBox<TA> ab;
+    for (int k = 0; k < 3; ++k) { ab.lo[k] = a.x[k] - a.r; ab.up[k] = a.x[k] + a.r; }
+    return iscontact_promoted(ab, b);
+}
+template <class TA, class TB> inline bool iscontact_promoted(const BBox<TA>& a, const BSphere<TB>& b) { return iscontact_promoted(b, a); }
+
+// traverse_single.jl:79-157 (fill_initial_bvtt_single!, CPU branch)
+inline void bfs_initial_single(const Tree& tr, int64_t start_level, std::vector<BvttPair>& out) {
+    int64_t level_nodes = int64_t(1) << (start_level - 1);
+    int64_t num_real = level_nodes - shr(tr.virtual_leaves, tr.levels - start_level);
+    out.clear();
+    for (int64_t i = level_nodes; i <= level_nodes + num_real - 1; ++i) {
+        if (start_level != tr.levels) out.push_back({i, i});
+        for (int64_t j = i + 1; j <= level_nodes + num_real - 1; ++j) out.push_back({i, j});
+    }
+}
+
+// traverse_single_cpu.jl:62-128 (traverse_nodes_range!)
+template <class N>
+inline void bfs_nodes_single(const Tree& tr, const N* nodes, const std::vector<BvttPair>& src, std::vector<BvttPair>& dst,
+                             int64_t level, bool self_checks) {
+    int64_t vl = shr(tr.virtual_leaves, tr.levels - (level - 1));
+    int64_t num_skips = 2 * vl - __builtin_popcountll((uint64_t)vl);
+    dst.clear();
+    for (const BvttPair& e : src) {
+        int64_t i1 = e.a, i2 = e.b;
+        if (i1 == i2) {
+            if (isvirtual(tr, 2 * i1 + 1)) {
+                if (self_checks) dst.push_back({2 * i1, 2 * i1});
+            } else if (self_checks) {
+                dst.push_back({2 * i1, 2 * i1});
+                dst.push_back({2 * i1, 2 * i1 + 1});
+                dst.push_back({2 * i1 + 1, 2 * i1 + 1});
+            } else {
+                dst.push_back({2 * i1, 2 * i1 + 1});
+            }
+        } else if (iscontact(nodes[i1 - num_skips - 1], nodes[i2 - num_skips - 1])) {
+            if (isvirtual(tr, 2 * i2 + 1)) {
+                dst.push_back({2 * i1, 2 * i2});
+                dst.push_back({2 * i1 + 1, 2 * i2});
+            } else {
+                dst.push_back({2 * i1, 2 * i2});
+                dst.push_back({2 * i1, 2 * i2 + 1});
+                dst.push_back({2 * i1 + 1, 2 * i2});
+                dst.push_back({2 * i1 + 1, 2 * i2 + 1});
+            }
+        }
+    }
+}
+
+// traverse(bvh, BFSTraversal()) — traverse_single.jl:1-66, traverse_single_cpu.jl:179-219.
+// positions: emit (leaf position 1, leaf position 2) instead of the sorted index pair.
+template <class L, class N, class I>
+inline int64_t traverse_bfs_single(const BVHView<L, N>& bvh, int64_t start_level, bool positions,
+                                   std::vector<IndexPair<I>>& contacts, int64_t* num_checks) {
+    const Tree& tr = bvh.tree;
+    contacts.clear();
+    *num_checks = 0;
+    if (tr.real_nodes <= 1) return 0;
+    std::vector<BvttPair> a, b;
+    bfs_initial_single(tr, start_level, a);
+    int64_t checks = (int64_t)a.size();
+    for (int64_t level = start_level; level < tr.levels; ++level) {
+        bool self_checks = level < tr.levels - 1;
+        bfs_nodes_single<N>(tr, bvh.nodes, a, b, level, self_checks);
+        checks += (int64_t)b.size();
+        a.swap(b);
+    }
+    int64_t num_above = (int64_t(1) << (tr.levels - 1)) - 1;
+    for (const BvttPair& e : a) {
+        const L& l1 = bvh.leaves[e.a - num_above - 1];
+        const L& l2 = bvh.leaves[e.b - num_above - 1];
+        if (iscontact(l1.volume, l2.volume)) {
+            if (positions) contacts.push_back({(I)(e.a - num_above), (I)(e.b - num_above)});
+            else if (l1.index > l2.index) contacts.push_back({l2.index, l1.index});
+            else contacts.push_back({l1.index, l2.index});
+        }
+    }
+    *num_checks = checks;
+    return (int64_t)contacts.size();
+}
+
+// traverse(bvh1, bvh2, BFSTraversal()) — traverse_pair.jl:1-158, traverse_pair_cpu.jl. mode: which side sprouts.
+enum BfsPairMode { kBfsBoth, kBfsLeft, kBfsRight, kBfsLeafLeft, kBfsLeafRight };
+template <class L, class N>
+inline void bfs_nodes_pair(const BVHView<L, N>& b1, const BVHView<L, N>& b2, const std::vector<BvttPair>& src,
+                           std::vector<BvttPair>& dst, int64_t level1, int64_t level2, BfsPairMode mode) {
+    const Tree &t1 = b1.tree, &t2 = b2.tree;
+    int64_t v1 = shr(t1.virtual_leaves, t1.levels - (level1 - 1)), v2 = shr(t2.virtual_leaves, t2.levels - (level2 - 1));
+    int64_t skips1 = 2 * v1 - __builtin_popcountll((uint64_t)v1), skips2 = 2 * v2 - __builtin_popcountll((uint64_t)v2);
+    int64_t above1 = (int64_t(1) << (t1.levels - 1)) - 1, above2 = (int64_t(1) << (t2.levels - 1)) - 1;
+    dst.clear();
+    for (const BvttPair& e : src) {
+        int64_t i1 = e.a, i2 = e.b;
+        bool hit;
+        if (mode == kBfsLeafLeft) hit = iscontact_promoted(b1.nodes[i1 - skips1 - 1], b2.leaves[i2 - above2 - 1].volume);
+        else if (mode == kBfsLeafRight) hit = iscontact_promoted(b1.leaves[i1 - above1 - 1].volume, b2.nodes[i2 - skips2 - 1]);
+        else hit = iscontact(b1.nodes[i1 - skips1 - 1], b2.nodes[i2 - skips2 - 1]);
+        if (!hit) continue;
+        bool r1 = !isvirtual(t1, 2 * i1 + 1), r2 = !isvirtual(t2, 2 * i2 + 1);
+        if (mode == kBfsBoth) {
+            dst.push_back({2 * i1, 2 * i2});
+            if (r2) dst.push_back({2 * i1, 2 * i2 + 1});
+            if (r1) dst.push_back({2 * i1 + 1, 2 * i2});
+            if (r1 && r2) dst.push_back({2 * i1 + 1, 2 * i2 + 1});
+        } else if (mode == kBfsLeft || mode == kBfsLeafLeft) {
+            dst.push_back({2 * i1, i2});
+            if (r1) dst.push_back({2 * i1 + 1, i2});
+        } else {
+            dst.push_back({i1, 2 * i2});
+            if (r2) dst.push_back({i1, 2 * i2 + 1});
+        }
+    }
+}
+
+template <class L, class N, class I>
+inline int64_t traverse_bfs_pair(const BVHView<L, N>& b1, const BVHView<L, N>& b2, int64_t start_level1, int64_t start_level2,
+                                 bool positions, std::vector<IndexPair<I>>& contacts, int64_t* num_checks) {
+    const Tree &t1 = b1.tree, &t2 = b2.tree;
+    contacts.clear();
+    std::vector<BvttPair> a, b;
+    // initial_bvtt / fill_initial_bvtt_pair!, traverse_pair.jl:161-221
+    int64_t ln1 = int64_t(1) << (start_level1 - 1), ln2 = int64_t(1) << (start_level2 - 1);
+    int64_t nr1 = ln1 - shr(t1.virtual_leaves, t1.levels - start_level1), nr2 = ln2 - shr(t2.virtual_leaves, t2.levels - start_level2);
+    for (int64_t i = ln1; i <= ln1 + nr1 - 1; ++i) for (int64_t j = ln2; j <= ln2 + nr2 - 1; ++j) a.push_back({i, j});
+    int64_t checks = (int64_t)a.size();
+    int64_t level1 = start_level1, level2 = start_level2;
+    auto step = [&](BfsPairMode m) { bfs_nodes_pair<L, N>(b1, b2, a, b, level1, level2, m); checks += (int64_t)b.size(); a.swap(b); };
+    while (level1 < t1.levels - 1 && level2 < t2.levels - 1) { step(kBfsBoth); ++level1; ++level2; }
+    while (level1 < t1.levels - 1 && level2 == t2.levels - 1) { step(kBfsLeft); ++level1; }
+    while (level2 < t2.levels - 1 && level1 == t1.levels - 1) { step(kBfsRight); ++level2; }
+    while (level2 == t2.levels && level1 < t1.levels) { step(kBfsLeafLeft); ++level1; }
+    while (level1 == t1.levels && level2 < t2.levels) { step(kBfsLeafRight); ++level2; }
+    if (level1 == t1.levels - 1 && level2 == t2.levels - 1) { step(kBfsBoth); ++level1; ++level2; }
+    int64_t above1 = (int64_t(1) << (t1.levels - 1)) - 1, above2 = (int64_t(1) << (t2.levels - 1)) - 1;
+    for (const BvttPair& e : a) {                                                      // traverse_leaves_pair!
+        const L& l1 = b1.leaves[e.a - above1 - 1];
+        const L& l2 = b2.leaves[e.b - above2 - 1];
+        if (iscontact(l1.volume, l2.volume)) {
+            if (positions) contacts.push_back({(I)(e.a - above1), (I)(e.b - above2)});
+            else contacts.push_back({l1.index, l2.index});
+        }
+    }
+    *num_checks = checks;
+    return (int64_t)contacts.size();
+}
+
+// traverse_rays(bvh, points, directions, BFSTraversal()) — raytrace/breadth_first/breadth_first.jl:1-66, raytrace_cpu.jl
+template <class L, class N, class I, class T>
+inline int64_t traverse_bfs_rays(const BVHView<L, N>& bvh, const T* points, const T* dirs, int64_t nrays, int64_t start_level,
+                                 bool positions, std::vector<IndexPair<I>>& hits, int64_t* num_checks) {
+    const Tree& tr = bvh.tree;
+    hits.clear();
+    *num_checks = 0;
+    if (nrays == 0) return 0;
+    std::vector<BvttPair> a, b;
+    int64_t ln = int64_t(1) << (start_level - 1);
+    int64_t nr = ln - shr(tr.virtual_leaves, tr.levels - start_level);
+    for (int64_t i = ln; i <= ln + nr - 1; ++i) for (int64_t j = 1; j <= nrays; ++j) a.push_back({i, j});
+    int64_t checks = (int64_t)a.size();
+    for (int64_t level = start_level; level < tr.levels; ++level) {
+        int64_t vl = shr(tr.virtual_leaves, tr.levels - (level - 1));
+        int64_t num_skips = 2 * vl - __builtin_popcountll((uint64_t)vl);
+        b.clear();
+        for (const BvttPair& e : a) {
+            if (isintersection(bvh.nodes[e.a - num_skips - 1], points + 3 * (e.b - 1), dirs + 3 * (e.b - 1))) {
+                b.push_back({2 * e.a, e.b});
+                if (!isvirtual(tr, 2 * e.a + 1)) b.push_back({2 * e.a + 1, e.b});
+            }
+        }
+        checks += (int64_t)b.size();
+        a.swap(b);
+    }
+    int64_t num_above = (int64_t(1) << (tr.levels - 1)) - 1;
+    for (const BvttPair& e : a) {
+        const L& leaf = bvh.leaves[e.a - num_above - 1];
+        if (isintersection(leaf.volume, points + 3 * (e.b - 1), dirs + 3 * (e.b - 1))) {
+            if (positions) hits.push_back({(I)(e.a - num_above), (I)e.b});
+            else hits.push_back({(I)leaf.index, (I)e.b});
+        }
+    }
+    *num_checks = checks;
+    return (int64_t)hits.size();
+}
+
 }  // namespace orc

@@ -303,6 +303,89 @@ int64_t orc_traverse_rays(const void* leaves, int64_t n, int kind, int fbytes, i
     return rc < 0 ? rc : total;
 }
 
+// ---- BFS traversals (src/traverse/breadth_first, src/raytrace/breadth_first) ------------------------
+// Each call runs the whole traversal and keeps the list in a process-wide stash; orc_bfs_fetch copies it
+// out (the list length is the call's return value). *num_checks receives BVHTraversal.num_checks.
+static std::vector<char> g_bfs_stash;
+#define bfs_stash(v)                                                                        \
+    do {                                                                                    \
+        g_bfs_stash.resize((v).size() * sizeof((v)[0]));                                    \
+        if (!(v).empty()) std::memcpy(g_bfs_stash.data(), (v).data(), g_bfs_stash.size());  \
+    } while (0)
+int64_t orc_bfs_fetch(void* out, int64_t bytes) {
+    if ((int64_t)g_bfs_stash.size() != bytes) return -1;
+    if (bytes) std::memcpy(out, g_bfs_stash.data(), (size_t)bytes);
+    return 0;
+}
+int64_t orc_traverse_bfs_single(const void* leaves, int64_t n, int kind, int fbytes, int ibytes, int mbytes,
+                                const void* nodes, int node_kind, int node_fbytes, int64_t built_level,
+                                int64_t start_level, int positions, int64_t* num_checks) {
+    int64_t total = -1;
+    int rc = dispatch_leaf({kind, fbytes, ibytes, mbytes}, [&](auto tag) {
+        using L = typename decltype(tag)::type; using I = typename L::idx_t;
+        return dispatch_node<L>({node_kind, node_fbytes}, [&](auto ntag) {
+            using N = typename decltype(ntag)::type;
+            Tree t = make_tree(n);
+            if (!(built_level <= start_level && start_level <= t.levels)) return -3;      // traverse_single.jl:10
+            std::vector<int64_t> sk; skips_vec(t, sk);
+            BVHView<L, N> bvh{t, sk.data(), (const N*)nodes, (const L*)leaves, built_level};
+            std::vector<IndexPair<I>> out;
+            total = traverse_bfs_single<L, N, I>(bvh, start_level, positions != 0, out, num_checks);
+            bfs_stash(out);
+            return 0;
+        });
+    });
+    return rc < 0 ? rc : total;
+}
+int64_t orc_traverse_bfs_pair(const void* leaves1, int64_t n1, const void* nodes1, int64_t built_level1, int64_t start_level1,
+                              const void* leaves2, int64_t n2, const void* nodes2, int64_t built_level2, int64_t start_level2,
+                              int kind, int fbytes, int ibytes, int mbytes, int node_kind, int node_fbytes,
+                              int positions, int64_t* num_checks) {
+    int64_t total = -1;
+    int rc = dispatch_leaf({kind, fbytes, ibytes, mbytes}, [&](auto tag) {
+        using L = typename decltype(tag)::type; using I = typename L::idx_t;
+        return dispatch_node<L>({node_kind, node_fbytes}, [&](auto ntag) {
+            using N = typename decltype(ntag)::type;
+            Tree t1 = make_tree(n1), t2 = make_tree(n2);
+            if (!(built_level1 <= start_level1 && start_level1 <= t1.levels)) return -3;  // traverse_pair.jl:10-11
+            if (!(built_level2 <= start_level2 && start_level2 <= t2.levels)) return -3;
+            std::vector<int64_t> s1, s2; skips_vec(t1, s1); skips_vec(t2, s2);
+            BVHView<L, N> b1{t1, s1.data(), (const N*)nodes1, (const L*)leaves1, built_level1};
+            BVHView<L, N> b2{t2, s2.data(), (const N*)nodes2, (const L*)leaves2, built_level2};
+            std::vector<IndexPair<I>> out;
+            total = traverse_bfs_pair<L, N, I>(b1, b2, start_level1, start_level2, positions != 0, out, num_checks);
+            bfs_stash(out);
+            return 0;
+        });
+    });
+    return rc < 0 ? rc : total;
+}
+int64_t orc_traverse_bfs_rays(const void* leaves, int64_t n, int kind, int fbytes, int ibytes, int mbytes,
+                              const void* nodes, int node_kind, int node_fbytes, int64_t built_level,
+                              int64_t start_level, const void* points, const void* directions, int64_t nrays,
+                              int positions, int64_t* num_checks) {
+    int64_t total = -1;
+    int rc = dispatch_leaf({kind, fbytes, ibytes, mbytes}, [&](auto tag) {
+        using L = typename decltype(tag)::type; using I = typename L::idx_t; using T = typename L::vol_t::value_type;
+        return dispatch_node<L>({node_kind, node_fbytes}, [&](auto ntag) {
+            using N = typename decltype(ntag)::type;
+            if constexpr (!std::is_same<typename N::value_type, T>::value) return -1;   // isintersection needs one T
+            else {
+                Tree t = make_tree(n);
+                if (!(built_level <= start_level && start_level <= t.levels)) return -3;
+                std::vector<int64_t> sk; skips_vec(t, sk);
+                BVHView<L, N> bvh{t, sk.data(), (const N*)nodes, (const L*)leaves, built_level};
+                std::vector<IndexPair<I>> out;
+                total = traverse_bfs_rays<L, N, I, T>(bvh, (const T*)points, (const T*)directions, nrays, start_level,
+                                                      positions != 0, out, num_checks);
+                bfs_stash(out);
+                return 0;
+            }
+        });
+    });
+    return rc < 0 ? rc : total;
+}
+
 // Brute force O(n^2) single-set contacts in *input order* (test/runtests.jl:851-859): pairs (i, j),
 // i < j, 1-based, iscontact on the raw volumes. Returns count; writes up to capacity pairs (int64).
 int64_t orc_brute_single(const void* volumes, int64_t n, int kind, int fbytes, int64_t* pairs, int64_t capacity) {

@@ -72,6 +72,14 @@ def lib() -> C.CDLL:
         _lib.orc_traverse_pair.argtypes = [vp, i64, vp, i64, i64, vp, i64, vp, i64, i64, ci, ci, ci, ci, ci, ci, vp, i64, vp, ci, i64]
         _lib.orc_traverse_rays.restype = i64
         _lib.orc_traverse_rays.argtypes = [vp, i64, ci, ci, ci, ci, vp, ci, ci, i64, i64, vp, vp, ci, i64, vp, i64, vp, ci, i64]
+        _lib.orc_bfs_fetch.restype = i64
+        _lib.orc_bfs_fetch.argtypes = [vp, i64]
+        _lib.orc_traverse_bfs_single.restype = i64
+        _lib.orc_traverse_bfs_single.argtypes = [vp, i64, ci, ci, ci, ci, vp, ci, ci, i64, i64, ci, vp]
+        _lib.orc_traverse_bfs_pair.restype = i64
+        _lib.orc_traverse_bfs_pair.argtypes = [vp, i64, vp, i64, i64, vp, i64, vp, i64, i64, ci, ci, ci, ci, ci, ci, ci, vp]
+        _lib.orc_traverse_bfs_rays.restype = i64
+        _lib.orc_traverse_bfs_rays.argtypes = [vp, i64, ci, ci, ci, ci, vp, ci, ci, i64, i64, vp, vp, i64, ci, vp]
         _lib.orc_brute_single.restype = i64
         _lib.orc_brute_single.argtypes = [vp, i64, ci, ci, vp, i64]
         _lib.orc_brute_pair.restype = i64
@@ -275,6 +283,54 @@ def traverse_rays(leaves, nodes, points, directions, built_level=1, start_level=
     if total:
         _check(lib().orc_traverse_rays(*args, _p(contacts), total, None, num_threads, min_elems), "traverse_rays")
     return contacts
+
+
+# ---- BFS traversals (src/traverse/breadth_first, src/raytrace/breadth_first): (list in the reference's CPU order, num_checks)
+def bfs_default_start_level(n: int, built_level: int = 1) -> int:
+    """default_start_level(bvh, ::BFSTraversal) — breadth_first/breadth_first.jl:4-6."""
+    return max(tree_shape(n)["levels"] // 2, built_level)
+
+
+def _bfs_fetch(total, ib):
+    out = np.zeros(total, pair_dtype(ib))
+    _check(lib().orc_bfs_fetch(_p(out), out.nbytes), "bfs_fetch")
+    return out
+
+
+def traverse_bfs_single(leaves, nodes, built_level=1, start_level=None, positions=False):
+    kind, fbytes, ib, mb = _desc(leaves)
+    nk, nf = _node_desc(nodes)
+    n = len(leaves)
+    start_level = start_level or bfs_default_start_level(n, built_level)
+    checks = C.c_int64(0)
+    total = _check(lib().orc_traverse_bfs_single(_p(leaves), n, kind, fbytes, ib, mb, _p(nodes), nk, nf, built_level, start_level,
+                                                 int(positions), C.byref(checks)), "traverse_bfs_single")
+    return _bfs_fetch(total, ib), int(checks.value)
+
+
+def traverse_bfs_pair(leaves1, nodes1, leaves2, nodes2, built_level1=1, built_level2=1, start_level1=None, start_level2=None,
+                      positions=False):
+    kind, fbytes, ib, mb = _desc(leaves1)
+    assert _desc(leaves2) == (kind, fbytes, ib, mb)
+    nk, nf = _node_desc(nodes2 if len(nodes2) or not len(nodes1) else nodes1)
+    start_level1 = start_level1 or bfs_default_start_level(len(leaves1), built_level1)
+    start_level2 = start_level2 or bfs_default_start_level(len(leaves2), built_level2)
+    checks = C.c_int64(0)
+    total = _check(lib().orc_traverse_bfs_pair(_p(leaves1), len(leaves1), _p(nodes1), built_level1, start_level1,
+                                               _p(leaves2), len(leaves2), _p(nodes2), built_level2, start_level2,
+                                               kind, fbytes, ib, mb, nk, nf, int(positions), C.byref(checks)), "traverse_bfs_pair")
+    return _bfs_fetch(total, ib), int(checks.value)
+
+
+def traverse_bfs_rays(leaves, nodes, points, directions, built_level=1, start_level=1, positions=False):
+    kind, fbytes, ib, mb = _desc(leaves)
+    nk, nf = _node_desc(nodes)
+    p = np.ascontiguousarray(np.asarray(points).T.astype(_f(fbytes)))
+    d = np.ascontiguousarray(np.asarray(directions).T.astype(_f(fbytes)))
+    checks = C.c_int64(0)
+    total = _check(lib().orc_traverse_bfs_rays(_p(leaves), len(leaves), kind, fbytes, ib, mb, _p(nodes), nk, nf, built_level,
+                                               start_level, _p(p), _p(d), len(p), int(positions), C.byref(checks)), "traverse_bfs_rays")
+    return _bfs_fetch(total, ib), int(checks.value)
 
 
 def brute_single(volumes):

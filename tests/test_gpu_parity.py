@@ -1185,3 +1185,168 @@ def test_sidecar_reuse_eviction_and_fallback(ib, O, dev):
     for qb, qc in ((0, 50_001), (50_001, 49_999), (100_000, 50_000)):
         parts.append(ib.traverse(again, query_range=(qb, qc)).contacts.numpy())
     assert np.concatenate(parts).tobytes() == want[3][2].tobytes()
+
+
+# ---- BFSTraversal (src/traverse/breadth_first, src/raytrace/breadth_first) ------------------------------------------------
+# The reference's GPU backend appends with atomics, so its BFS lists are sets: contacts are compared as sorted lists
+# (test/gputests.jl:73-78 sorts too); num_checks (the summed BVTT lengths) is deterministic and compared exactly.
+@pytest.mark.gpu
+def test_bfs_doctests_and_old_interface(ib, golden, dev):
+    g = golden["five_spheres"]
+    want = sorted(tuple(p) for p in g["contacts_lvt_order"])
+    for node in ("bbox", "sphere"):
+        for ibytes, mbytes in ((4, 4), (8, 8), (4, 2)):
+            bvh = gpu_build(ib, ib.bspheres(g["centers"], g["radii"]), node, ibytes, mbytes)
+            tr = ib.traverse(bvh, ib.BFSTraversal())
+            assert sorted(pairs_list(tr.contacts.numpy())) == want
+            assert tr.start_level1 == ib.default_start_level(bvh, ib.BFSTraversal()) == 2      # breadth_first.jl:4-6
+            assert tr.contacts.numpy().dtype == ib.pair_dtype(I_of(ibytes)) and tr.cache2.dtype == ib.pair_dtype(I_of(ibytes))
+            tr2 = ib.traverse(bvh, ib.BFSTraversal(), cache=tr)
+            assert tr2.cache1.ptr == tr.cache1.ptr and sorted(pairs_list(tr2.contacts.numpy())) == want
+            old = ib.traverse(bvh, 3)                                                         # traverse(bvh, start_level) = BFS, traverse.jl:233-241
+            assert old.start_level1 == 3 and sorted(pairs_list(old.contacts.numpy())) == want
+    bvh = gpu_build(ib, ib.bspheres(g["centers"], g["radii"]))
+    with pytest.raises(ib.ArgumentError):
+        ib.traverse(bvh, ib.BFSTraversal(), cache=ib.traverse(bvh))          # an LVT cache: eltype(cache.cache2) === IndexPair{I} fails
+    with pytest.raises(ib.ArgumentError):
+        ib.traverse(bvh, ib.BFSTraversal(), start_level=5)
+    g = golden["pair_example"]
+    b1 = gpu_build(ib, ib.bspheres(g["centers1"], g["radii1"]))
+    b2 = gpu_build(ib, ib.bspheres(g["centers2"], g["radii2"]))
+    tr = ib.traverse(b1, b2, ib.BFSTraversal(), start_level1=g["start_level1"], start_level2=g["start_level2"])
+    assert sorted(pairs_list(tr.contacts.numpy())) == sorted(tuple(p) for p in g["contacts_lvt_order"])
+    gr = golden["ray_example"]
+    tr = ib.traverse_rays(bvh, np.array(gr["points"]), np.array(gr["directions"]), ib.BFSTraversal())
+    assert sorted(pairs_list(tr.contacts.numpy())) == sorted(tuple(p) for p in gr["contacts_lvt_order"])
+    one = gpu_build(ib, ib.bspheres([[0, 0, 0]], [1.0]))
+    assert ib.traverse(one, ib.BFSTraversal()).num_contacts == 0             # traverse_single.jl:17-21
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("node", ["bbox", "sphere"])
+def test_bfs_single_all_start_levels(ib, O, dev, node):
+    """runtests.jl:839-900 / gputests.jl:51-127 with alg = BFSTraversal()."""
+    rng = np.random.default_rng(42)
+    for n in range(1, 200, 11):
+        s = random_spheres(rng, n)
+        ol, on = oracle_build(O, s, node)
+        bvh = gpu_build(ib, s, node)
+        brute = sorted_pairs(O.brute_single(s))
+        cache = None
+        for sl in range(1, bvh.tree.levels + 1):
+            want, checks = O.traverse_bfs_single(ol, on, start_level=sl)
+            got = ib.traverse(bvh, ib.BFSTraversal(), start_level=sl, cache=cache)
+            assert (sorted_pairs(got.contacts.numpy()) == sorted_pairs(want)).all(), (n, sl)
+            assert (sorted_pairs(want) == brute).all()
+            assert got.num_checks == checks, (n, sl, got.num_checks, checks)
+            cache = got
+
+
+@pytest.mark.gpu
+def test_bfs_pair_all_start_levels(ib, O, dev):
+    """runtests.jl:1009-1081 / gputests.jl:132-208 with alg = BFSTraversal(): every stage of traverse_pair.jl:39-140
+    (both descend, one side at its last node level, one side already at its leaves — incl. single-leaf trees)."""
+    rng = np.random.default_rng(44)
+    sizes = [1, 2, 22, 64, 127, 190]
+    for node in ("bbox", "sphere"):
+        for n1 in sizes:
+            for n2 in sizes:
+                s1, s2 = random_spheres(rng, n1), random_spheres(rng, n2)
+                o1, on1 = oracle_build(O, s1, node)
+                o2, on2 = oracle_build(O, s2, node)
+                b1, b2 = gpu_build(ib, s1, node), gpu_build(ib, s2, node)
+                brute = sorted_pairs(O.brute_pair(s1, s2))
+                lv1, lv2 = b1.tree.levels, b2.tree.levels
+                for sl1 in sorted({1, max(1, lv1 // 2), max(1, lv1 - 1), lv1}):
+                    for sl2 in sorted({1, max(1, lv2 // 2), max(1, lv2 - 1), lv2}):
+                        want, checks = O.traverse_bfs_pair(o1, on1, o2, on2, start_level1=sl1, start_level2=sl2)
+                        got = ib.traverse(b1, b2, ib.BFSTraversal(), start_level1=sl1, start_level2=sl2)
+                        assert (sorted_pairs(got.contacts.numpy()) == brute).all(), (node, n1, n2, sl1, sl2)
+                        assert (sorted_pairs(want) == brute).all()
+                        assert got.num_checks == checks, (node, n1, n2, sl1, sl2)
+                        assert (got.start_level1, got.start_level2) == (sl1, sl2)
+
+
+@pytest.mark.gpu
+def test_bfs_rays_types_partial_builds_and_narrow(ib, O, dev):
+    rng = np.random.default_rng(45)
+    # rays: raytrace/breadth_first, every start level, both node kinds; Float64 too
+    for fbytes in (4, 8):
+        for node in ("bbox", "sphere"):
+            for n in (1, 7, 190):
+                s = random_spheres(rng, n, fbytes=fbytes)
+                ol, on = oracle_build(O, s, node)
+                bvh = gpu_build(ib, s, node)
+                f = np.float32 if fbytes == 4 else np.float64
+                p = (6 * rng.random((3, 300))).astype(f)
+                d = rng.standard_normal((3, 300)).astype(f)
+                for sl in range(1, bvh.tree.levels + 1):
+                    want, checks = O.traverse_bfs_rays(ol, on, p, d, start_level=sl)
+                    got = ib.traverse_rays(bvh, p, d, ib.BFSTraversal(), start_level=sl)
+                    assert (sorted_pairs(got.contacts.numpy()) == sorted_pairs(want)).all(), (fbytes, node, n, sl)
+                    assert got.num_checks == checks
+                    assert (sorted_pairs(want) == sorted_pairs(O.brute_rays(s, p, d))).all()
+    # the reference's default call: Float64 leaves under Float32 nodes, partially built; box leaves; Int64 / UInt64
+    s = random_spheres(rng, 3000, fbytes=8, spread=12.0)
+    for node_t, onode in ((ib.BBox(np.float32), O.BBOX), (ib.BSphere(np.float32), O.BSPHERE)):
+        bvh = ib.BVH(s, node_t, built_level=3)
+        ol = O.wrap(s)
+        on, _, _ = O.build(ol, onode, node_fbytes=4, built_level=3)
+        for sl in (3, 6, bvh.tree.levels):
+            want, checks = O.traverse_bfs_single(ol, on, built_level=3, start_level=sl)
+            got = ib.traverse(bvh, ib.BFSTraversal(), start_level=sl)
+            assert (sorted_pairs(got.contacts.numpy()) == sorted_pairs(want)).all() and got.num_checks == checks
+        one = ib.BVH(random_spheres(rng, 1, fbytes=8, spread=12.0), node_t)
+        o1 = O.wrap(one.leaves.numpy()["volume"].copy())
+        on1, _, _ = O.build(o1, onode, node_fbytes=4)
+        want, checks = O.traverse_bfs_pair(ol, on, o1, on1, built_level1=3, start_level1=4, start_level2=1)
+        got = ib.traverse(bvh, one, ib.BFSTraversal(), start_level1=4, start_level2=1)     # node (Float32) against leaf volume (Float64)
+        assert (sorted_pairs(got.contacts.numpy()) == sorted_pairs(want)).all() and got.num_checks == checks
+    lo = (6 * rng.random((500, 3))).astype(np.float32)
+    boxes = ib.bboxes(lo, lo + (0.2 + 0.6 * rng.random((500, 3))).astype(np.float32))
+    bvh = gpu_build(ib, boxes, "bbox", 8, 8)
+    ol, on = oracle_build(O, boxes, "bbox", 8, 8)
+    want, checks = O.traverse_bfs_single(ol, on)
+    got = ib.traverse(bvh, ib.BFSTraversal())
+    assert (sorted_pairs(got.contacts.numpy()) == sorted_pairs(want)).all() and got.num_checks == checks
+    # narrow: runtests.jl:1228-1266 / gputests.jl:251-290 — BFS == LVT under the same predicate
+    s = random_spheres(rng, 190)
+    bvh = gpu_build(ib, s)
+    pred = lambda a, b: a["morton"] < b["morton"]
+    bfs = ib.traverse(bvh, ib.BFSTraversal(), narrow=pred)
+    lvt = ib.traverse(bvh, ib.LVTTraversal(), narrow=pred)
+    assert 0 < bfs.num_contacts < ib.traverse(bvh).num_contacts
+    assert (sorted_pairs(bfs.contacts.numpy()) == sorted_pairs(lvt.contacts.numpy())).all()
+    b2 = gpu_build(ib, random_spheres(rng, 64))
+    bfs = ib.traverse(bvh, b2, ib.BFSTraversal(), narrow=pred)
+    lvt = ib.traverse(bvh, b2, ib.LVTTraversal(), narrow=pred)
+    assert (sorted_pairs(bfs.contacts.numpy()) == sorted_pairs(lvt.contacts.numpy())).all()
+
+
+@pytest.mark.gpu
+def test_bfs_100k_against_oracle_and_capacity_protocol(ib, O, dev):
+    """configs[0] scene: BFS contacts == the oracle's BFS == the LVT list as sets, num_checks exact; a too-small cache1 is
+    grown and only the leaf level repeated."""
+    from ibvh_b200 import synth
+    n = 100_000
+    s = synth.random_spheres_np(n, seed=42)
+    ol, on = oracle_build(O, s)
+    bvh = gpu_build(ib, s)
+    want, checks = O.traverse_bfs_single(ol, on)
+    got = ib.traverse(bvh, ib.BFSTraversal())
+    assert got.num_checks == checks and got.num_contacts == len(want)
+    assert (sorted_pairs(got.contacts.numpy()) == sorted_pairs(want)).all()
+    assert (sorted_pairs(want) == sorted_pairs(O.traverse_single(ol, on, num_threads=8))).all()
+    small = ib.BVHTraversal(1, 0, 0, 0, ib.DeviceArray.empty(1000, ib.pair_dtype(np.int32), dev), ib.DeviceArray.empty(0, ib.pair_dtype(np.int32), dev))
+    again = ib.traverse(bvh, ib.BFSTraversal(), cache=small)
+    assert again.num_contacts == len(want) and len(again.cache1) == len(want) and again.num_checks == checks
+    assert (sorted_pairs(again.contacts.numpy()) == sorted_pairs(want)).all()
+    # pair: two trees of different depth
+    s2 = synth.random_spheres_np(30_000, seed=43)
+    o2, on2 = oracle_build(O, s2)
+    b2 = gpu_build(ib, s2)
+    want, checks = O.traverse_bfs_pair(ol, on, o2, on2)
+    got = ib.traverse(bvh, b2, ib.BFSTraversal())
+    assert got.num_checks == checks
+    assert (sorted_pairs(got.contacts.numpy()) == sorted_pairs(want)).all()
+    assert (sorted_pairs(want) == sorted_pairs(O.traverse_pair(ol, on, o2, on2, num_threads=8))).all()

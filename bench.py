@@ -230,11 +230,12 @@ def main():
                          "(same set; the parity bar is the SORTED contact list)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-rays", action="store_true", help="skip the secondary rays/s measurement")
-    ap.add_argument("--workloads", default="ordered,pair,rebuild64,reference_shaped",
+    ap.add_argument("--workloads", default="ordered,bfs,pair,rebuild64,reference_shaped",
                     help="comma list of the extra BASELINE.json workloads to time after the headline (reported under `workloads`): "
                          "ordered (the headline step in the reference's contact order), pair (configs[2]: 5 M + 5 M BVH-vs-BVH, "
                          "partial and full build), rebuild64 (configs[4]: 100 M leaves, UInt64 / Int64, cached rebuild + contacts), "
-                         "reference_shaped (the naive GPU proxy of the reference's CUDA.jl backend on the headline step). 'none' skips them")
+                         "reference_shaped (the naive GPU proxy of the reference's CUDA.jl backend on the headline step), bfs (the headline step "
+                         "with traverse(bvh, BFSTraversal()), single GPU). 'none' skips them")
     ap.add_argument("--no-defer", action="store_true", help="single GPU: synchronous traversal calls (the host reads each step's contact count before it enqueues the next build)")
     ap.add_argument("--gather", default="fused", choices=["fused", "peer", "nccl"],
                     help="N > 1: how the contact shards reach every rank. fused: the traversal kernel itself writes each contact "
@@ -744,6 +745,40 @@ def main():
                                 "workload": "the headline step with contacts in the reference's order (count -> scan -> write protocol; "
                                             "byte-identical to the oracle's list); N > 1: ordered shards all-gathered in rank order"}
         st_o.clear()
+
+    if "bfs" in extra and world == 1:
+        # the headline step with the reference's other traversal algorithm, BFSTraversal (src/traverse/breadth_first): level-synchronous
+        # BVTT descent from the default start level (levels / 2); same contact set (checked here by count + order-independent
+        # checksum against an LVT traversal of the same tree), exact num_checks
+        st_b = {"bvh": state["bvh"], "tr": None}
+
+        def step_bfs():
+            bvh = ib.BVH(src, ib.BBox(), cache=st_b["bvh"])
+            tr = ib.traverse(bvh, ib.BFSTraversal(), cache=st_b["tr"])
+            st_b["bvh"], st_b["tr"] = bvh, tr
+            return tr
+
+        ms_b, tr_b = timed_steps(torch, step_bfs, 5, 3)
+        lvt = ib.traverse(st_b["bvh"], ordered=False)
+        same = pair_checksum(torch, tr_b.cache1.tensor, tr_b.num_contacts) == pair_checksum(torch, lvt.cache1.tensor, lvt.num_contacts)
+        lib.ibvh_profile_enable(handle, 1)
+        step_bfs()
+        torch.cuda.synchronize()
+        prow = profile_rows(ib, handle)
+        lib.ibvh_profile_enable(handle, 0)
+        pk = {}
+        for k, v in prow:
+            pk[k] = pk.get(k, 0.0) + v
+        trav_ms = sum(v for k, v in pk.items() if k.startswith("bfs_"))
+        workloads["bfs"] = {"metric": METRIC, "value": n / (ms_b * 1e-3), "unit": UNIT, "ms_per_step": ms_b, "contacts_per_step": int(tr_b.num_contacts),
+                            "num_checks": int(tr_b.num_checks), "start_level": int(tr_b.start_level1), "traverse_kernels_ms": round(trav_ms, 4),
+                            "checks_per_s": tr_b.num_checks / (trav_ms * 1e-3) if trav_ms > 0 else None,
+                            "same_contact_set_as_lvt": bool(same),
+                            "per_kernel_ms": {k: round(v, 4) for k, v in sorted(pk.items(), key=lambda kv: -kv[1])},
+                            "workload": "the headline step with traverse(bvh, BFSTraversal()) — the reference's breadth-first algorithm (fewest checks, "
+                                        "BVTT lists in library scratch); contacts unordered like the reference's GPU backend"}
+        del lvt, tr_b
+        st_b.clear()
 
     if "reference_shaped" in extra and world == 1:
         # proxy of the reference's CUDA.jl backend (cannot run here: no Julia): the launches BVH(...) + traverse(...) make through

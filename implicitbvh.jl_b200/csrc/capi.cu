@@ -1259,6 +1259,10 @@ inline bool bfs_types_ok(const ibvh_types_t& t) {
     if (t.node_kind == IBVH_BSPHERE && t.leaf_kind != IBVH_BSPHERE) return false;
     return true;
 }
+inline uint32_t bfs_vec(const void* base, uint32_t stride) {
+    const uintptr_t m = reinterpret_cast<uintptr_t>(base) | (uintptr_t)stride;
+    return (m & 15u) == 0 ? 16u : (m & 7u) == 0 ? 8u : 4u;
+}
 inline BfsSide bfs_node_side(const ibvh_bvh_t* b, const ibvh_tree_t& tree, int64_t level) {       // level < levels
     BfsSide s{};
     s.base = b->d_nodes;
@@ -1266,6 +1270,7 @@ inline BfsSide bfs_node_side(const ibvh_bvh_t* b, const ibvh_tree_t& tree, int64
     s.stride = (uint32_t)((b->types.node_kind == IBVH_BSPHERE ? 4 : 6) * bfs_node_fbytes(b->types));
     s.child_first = (uint32_t)(int64_t(1) << level);
     s.child_nreal = (uint32_t)((int64_t(1) << level) - shr64(tree.virtual_leaves, tree.levels - (level + 1)));
+    s.vec = bfs_vec(s.base, s.stride);
     return s;
 }
 inline BfsSide bfs_leaf_side(const ibvh_bvh_t* b, const ibvh_tree_t& tree) {
@@ -1276,6 +1281,7 @@ inline BfsSide bfs_leaf_side(const ibvh_bvh_t* b, const ibvh_tree_t& tree) {
     s.sub = (uint32_t)(int64_t(1) << (tree.levels - 1));
     s.stride = stride;
     s.child_first = 0; s.child_nreal = 0;
+    s.vec = bfs_vec(s.base, s.stride);
     return s;
 }
 
@@ -1327,20 +1333,73 @@ int bfs_nodes_step(BfsRun& r, const BfsSide& sa, const BfsSide& sb, int self_che
     return r.end_step();
 }
 
+// Leaf level of the single / pair traversals: `fused` = r holds the list of the LAST NODE levels (both trees one above their
+// leaves) and bfs_last_kernel tests nodes and leaves in one pass; else r holds leaf pairs (traversal started at / reached a leaf
+// level on one side first) and bfs_leaves_kernel tests them. r.checks comes back complete. MODE: kBfsSingle / kBfsBoth.
+template <int MODE>
+int bfs_leaf_level(ibvh_handle* h, cudaStream_t st, BfsRun& r, bool fused, const ibvh_bvh_t* b1, const ibvh_tree_t& t1, const ibvh_bvh_t* b2,
+                   const ibvh_tree_t& t2, uint32_t flags, void* d_contacts, int64_t capacity, unsigned long long* total, long long* checks_out) {
+    *total = 0;
+    *checks_out = r.checks;
+    if (r.count == 0) return IBVH_OK;
+    const ibvh_types_t& ty = b1->types;
+    const BfsSide ls1 = bfs_leaf_side(b1, t1), ls2 = bfs_leaf_side(b2, t2);
+    uint32_t stride, io;
+    bfs_leaf_layout(ty, &stride, &io);
+    const int positions = (flags & IBVH_TRAVERSE_POSITIONS) ? 1 : 0;
+    const unsigned long long cap = d_contacts ? (unsigned long long)std::max<int64_t>(capacity, 0) : 0ull;
+    unsigned long long* d_cnt = r.d_counter();
+    IBVH_CUDA_TRY(h, cudaMemsetAsync(d_cnt, 0, 16, st));
+    int rc = bfs_dispatch_volume(ty.leaf_kind, ty.float_bytes, [&](auto vtag) -> int {
+        using V = typename decltype(vtag)::type;
+        return bfs_dispatch_index(ty.index_bytes, [&](auto itag) -> int {
+            using I = typename decltype(itag)::type;
+            if (!fused) {
+                { ProfScope _ps(h, st, "bfs_leaves_kernel");
+                bfs_leaves_kernel<MODE == kBfsSingle, V, I><<<r.grid(), kBfsThreads, 0, st>>>(r.list(r.cur), r.count, ls1, ls2, io, positions, (IndexPair<I>*)d_contacts, cap, d_cnt);
+                }
+                IBVH_LAUNCH_CHECK(h, "bfs_leaves_kernel");
+                return IBVH_OK;
+            }
+            return bfs_dispatch_volume(ty.node_kind, bfs_node_fbytes(ty), [&](auto ntag) -> int {
+                using N = typename decltype(ntag)::type;
+                if constexpr (N::kind == IBVH_BSPHERE && V::kind != IBVH_BSPHERE) return (int)IBVH_ERR_ARGUMENT;
+                else {
+                    const BfsSide n1 = bfs_node_side(b1, t1, t1.levels - 1), n2 = bfs_node_side(b2, t2, t2.levels - 1);
+                    { ProfScope _ps(h, st, "bfs_last_kernel");
+                    bfs_last_kernel<MODE, MODE == kBfsSingle, N, V, I><<<r.grid(), kBfsThreads, 0, st>>>(r.list(r.cur), r.count, n1, n2, ls1, ls2, io, positions,
+                                                                                                       (IndexPair<I>*)d_contacts, cap, d_cnt, d_cnt + 1);
+                    }
+                    IBVH_LAUNCH_CHECK(h, "bfs_last_kernel");
+                    return IBVH_OK;
+                }
+            });
+        });
+    });
+    if (rc != IBVH_OK) return rc;
+    unsigned long long* hp = (unsigned long long*)h->h_pinned;
+    IBVH_CUDA_TRY(h, cudaMemcpyAsync(hp, d_cnt, 16, cudaMemcpyDeviceToHost, st));
+    IBVH_CUDA_TRY(h, cudaStreamSynchronize(st));
+    *total = hp[0];
+    if (fused) *checks_out = r.checks + (long long)hp[1];
+    return IBVH_OK;
+}
+
 // What a BFS call that ended in IBVH_ERR_CAPACITY leaves behind, so that the repeat call with a larger cache1
 // (IBVH_TRAVERSE_COUNTS_VALID) only redoes the leaf level.
-inline bool bfs_resume(ibvh_handle* h, uint32_t flags, int kind, const void* l1, int64_t n1, const void* l2, int64_t n2, int64_t s1, int64_t s2, BfsRun* r) {
+inline bool bfs_resume(ibvh_handle* h, uint32_t flags, int kind, const void* l1, int64_t n1, const void* l2, int64_t n2, int64_t s1, int64_t s2, BfsRun* r, bool* fused = nullptr) {
     auto& p = h->bfs_pending;
     const bool ok = (flags & IBVH_TRAVERSE_COUNTS_VALID) && p.valid && p.kind == kind && p.leaves1 == l1 && p.n1 == n1 && p.leaves2 == l2 && p.n2 == n2 &&
                     p.start1 == s1 && p.start2 == s2;
     p.valid = false;
     if (!ok) return false;
     r->cur = p.cur; r->count = p.count; r->checks = p.checks;
+    if (fused) *fused = p.fused;
     return true;
 }
-inline void bfs_remember(ibvh_handle* h, int kind, const void* l1, int64_t n1, const void* l2, int64_t n2, int64_t s1, int64_t s2, const BfsRun& r) {
+inline void bfs_remember(ibvh_handle* h, int kind, const void* l1, int64_t n1, const void* l2, int64_t n2, int64_t s1, int64_t s2, const BfsRun& r, bool fused = false) {
     auto& p = h->bfs_pending;
-    p.valid = true; p.kind = kind; p.leaves1 = l1; p.n1 = n1; p.leaves2 = l2; p.n2 = n2; p.start1 = s1; p.start2 = s2;
+    p.valid = true; p.fused = fused; p.kind = kind; p.leaves1 = l1; p.n1 = n1; p.leaves2 = l2; p.n2 = n2; p.start1 = s1; p.start2 = s2;
     p.cur = r.cur; p.count = r.count; p.checks = r.checks;
 }
 
@@ -1965,7 +2024,8 @@ int ibvh_traverse_bfs_single(ibvh_handle_t* h, const ibvh_bvh_t* bvh, const ibvh
     cudaStream_t st = (cudaStream_t)stream;
     BfsRun r{h, st};
     const int64_t levels = tree.levels, sl = p->start_level;
-    if (!bfs_resume(h, p->flags, 1, bvh->d_leaves, bvh->n, bvh->d_leaves, bvh->n, sl, sl, &r)) {
+    bool fused = sl < levels;                 // the last node level runs fused with the leaf level (a start at the leaf level has none)
+    if (!bfs_resume(h, p->flags, 1, bvh->d_leaves, bvh->n, bvh->d_leaves, bvh->n, sl, sl, &r, &fused)) {
         // initial_bvtt, traverse_single.jl:69-157: every pair (i <= j) of the real nodes of the start level
         const int64_t first = int64_t(1) << (sl - 1);
         const int64_t nreal = first - shr64(tree.virtual_leaves, levels - sl);
@@ -1983,42 +2043,24 @@ int ibvh_traverse_bfs_single(ibvh_handle_t* h, const ibvh_bvh_t* bvh, const ibvh
         r.cur = 0; r.count = n0; r.checks = (long long)n0;
         rc = bfs_dispatch_volume(bvh->types.node_kind, bfs_node_fbytes(bvh->types), [&](auto ntag) -> int {
             using N = typename decltype(ntag)::type;
-            for (int64_t level = sl; level < levels; ++level) {
+            for (int64_t level = sl; level < levels - 1; ++level) {     // (level levels - 1 is the fused one; self-checks sprout on all of these)
                 const BfsSide s = bfs_node_side(bvh, tree, level);
-                int rc2 = bfs_nodes_step<kBfsSingle, N, N>(r, s, s, level < levels - 1 ? 1 : 0);   // self-checks only sprout above the second-to-last level
+                int rc2 = bfs_nodes_step<kBfsSingle, N, N>(r, s, s, 1);
                 if (rc2 != IBVH_OK) return rc2;
             }
             return IBVH_OK;
         });
         if (rc != IBVH_OK) return rc;
     }
-    if (num_checks) *num_checks = r.checks;
-    if (r.count == 0) return IBVH_OK;
-    // traverse_leaves!, traverse_single_gpu.jl:114-211
-    const BfsSide ls = bfs_leaf_side(bvh, tree);
-    uint32_t stride, io;
-    bfs_leaf_layout(bvh->types, &stride, &io);
-    IBVH_CUDA_TRY(h, cudaMemsetAsync(r.d_counter(), 0, 8, st));
-    rc = bfs_dispatch_volume(bvh->types.leaf_kind, bvh->types.float_bytes, [&](auto vtag) -> int {
-        using V = typename decltype(vtag)::type;
-        return bfs_dispatch_index(bvh->types.index_bytes, [&](auto itag) -> int {
-            using I = typename decltype(itag)::type;
-            { ProfScope _ps(h, st, "bfs_leaves_kernel");
-            bfs_leaves_kernel<true, V, I><<<r.grid(), kBfsThreads, 0, st>>>(r.list(r.cur), r.count, ls, ls, io, (p->flags & IBVH_TRAVERSE_POSITIONS) ? 1 : 0,
-                                                                            (IndexPair<I>*)d_contacts, d_contacts ? (unsigned long long)std::max<int64_t>(capacity, 0) : 0ull, r.d_counter());
-            }
-            IBVH_LAUNCH_CHECK(h, "bfs_leaves_kernel");
-            return IBVH_OK;
-        });
-    });
+    // traverse_leaves!, traverse_single_gpu.jl:114-211 (+ the last traverse_nodes! level when fused)
+    unsigned long long total = 0;
+    long long checks = 0;
+    rc = bfs_leaf_level<kBfsSingle>(h, st, r, fused, bvh, tree, bvh, tree, p->flags, d_contacts, capacity, &total, &checks);
     if (rc != IBVH_OK) return rc;
-    unsigned long long total;
-    rc = r.read_counter(&total);
-    if (rc != IBVH_OK) return rc;
+    if (num_checks) *num_checks = checks;
     *num_contacts = (int64_t)total;
-    if (d_contacts && (int64_t)total > capacity) { bfs_remember(h, 1, bvh->d_leaves, bvh->n, bvh->d_leaves, bvh->n, sl, sl, r); return IBVH_ERR_CAPACITY; }
-    if (!d_contacts && total > 0) bfs_remember(h, 1, bvh->d_leaves, bvh->n, bvh->d_leaves, bvh->n, sl, sl, r);   // count-only call: the write call follows
-    return IBVH_OK;
+    if ((d_contacts && (int64_t)total > capacity) || (!d_contacts && total > 0)) bfs_remember(h, 1, bvh->d_leaves, bvh->n, bvh->d_leaves, bvh->n, sl, sl, r, fused);
+    return d_contacts && (int64_t)total > capacity ? IBVH_ERR_CAPACITY : IBVH_OK;
 }
 
 int ibvh_traverse_bfs_pair(ibvh_handle_t* h, const ibvh_bvh_t* bvh1, const ibvh_bvh_t* bvh2, int64_t start_level1, int64_t start_level2,
@@ -2039,7 +2081,8 @@ int ibvh_traverse_bfs_pair(ibvh_handle_t* h, const ibvh_bvh_t* bvh1, const ibvh_
     DeviceGuard g(h->device);
     cudaStream_t st = (cudaStream_t)stream;
     BfsRun r{h, st};
-    if (!bfs_resume(h, flags, 2, bvh1->d_leaves, bvh1->n, bvh2->d_leaves, bvh2->n, start_level1, start_level2, &r)) {
+    bool fused = false;
+    if (!bfs_resume(h, flags, 2, bvh1->d_leaves, bvh1->n, bvh2->d_leaves, bvh2->n, start_level1, start_level2, &r, &fused)) {
         // initial_bvtt, traverse_pair.jl:161-221: the product of the real nodes of the two start levels
         const int64_t f1 = int64_t(1) << (start_level1 - 1), f2 = int64_t(1) << (start_level2 - 1);
         const int64_t n1 = f1 - shr64(t1.virtual_leaves, t1.levels - start_level1), n2 = f2 - shr64(t2.virtual_leaves, t2.levels - start_level2);
@@ -2060,8 +2103,10 @@ int ibvh_traverse_bfs_pair(ibvh_handle_t* h, const ibvh_bvh_t* bvh1, const ibvh_
                     // the stages of traverse_pair.jl:39-140
                     int64_t l1 = start_level1, l2 = start_level2;
                     int rc2 = IBVH_OK;
-                    auto both = [&]() { return bfs_nodes_step<kBfsBoth, N, N>(r, bfs_node_side(bvh1, t1, l1), bfs_node_side(bvh2, t2, l2), 0); };
-                    while (l1 < t1.levels - 1 && l2 < t2.levels - 1) { if ((rc2 = both()) != IBVH_OK) return rc2; ++l1; ++l2; }
+                    while (l1 < t1.levels - 1 && l2 < t2.levels - 1) {
+                        if ((rc2 = bfs_nodes_step<kBfsBoth, N, N>(r, bfs_node_side(bvh1, t1, l1), bfs_node_side(bvh2, t2, l2), 0)) != IBVH_OK) return rc2;
+                        ++l1; ++l2;
+                    }
                     while (l1 < t1.levels - 1 && l2 == t2.levels - 1) {
                         if ((rc2 = bfs_nodes_step<kBfsLeft, N, N>(r, bfs_node_side(bvh1, t1, l1), bfs_node_side(bvh2, t2, l2), 0)) != IBVH_OK) return rc2;
                         ++l1;
@@ -2078,37 +2123,21 @@ int ibvh_traverse_bfs_pair(ibvh_handle_t* h, const ibvh_bvh_t* bvh1, const ibvh_
                         if ((rc2 = bfs_nodes_step<kBfsRight, V, N>(r, bfs_leaf_side(bvh1, t1), bfs_node_side(bvh2, t2, l2), 0)) != IBVH_OK) return rc2;
                         ++l2;
                     }
-                    if (l1 == t1.levels - 1 && l2 == t2.levels - 1) { if ((rc2 = both()) != IBVH_OK) return rc2; }
+                    // both one above their leaves: that node level runs fused with the leaf level (bfs_leaf_level)
+                    fused = (l1 == t1.levels - 1 && l2 == t2.levels - 1);
                     return IBVH_OK;
                 }
             });
         });
         if (rc != IBVH_OK) return rc;
     }
-    if (num_checks) *num_checks = r.checks;
-    if (r.count == 0) return IBVH_OK;
-    const BfsSide ls1 = bfs_leaf_side(bvh1, t1), ls2 = bfs_leaf_side(bvh2, t2);
-    uint32_t stride, io;
-    bfs_leaf_layout(a1, &stride, &io);
-    IBVH_CUDA_TRY(h, cudaMemsetAsync(r.d_counter(), 0, 8, st));
-    rc = bfs_dispatch_volume(a1.leaf_kind, a1.float_bytes, [&](auto vtag) -> int {
-        using V = typename decltype(vtag)::type;
-        return bfs_dispatch_index(a1.index_bytes, [&](auto itag) -> int {
-            using I = typename decltype(itag)::type;
-            { ProfScope _ps(h, st, "bfs_leaves_kernel");
-            bfs_leaves_kernel<false, V, I><<<r.grid(), kBfsThreads, 0, st>>>(r.list(r.cur), r.count, ls1, ls2, io, (flags & IBVH_TRAVERSE_POSITIONS) ? 1 : 0,
-                                                                             (IndexPair<I>*)d_contacts, d_contacts ? (unsigned long long)std::max<int64_t>(capacity, 0) : 0ull, r.d_counter());
-            }
-            IBVH_LAUNCH_CHECK(h, "bfs_leaves_kernel");
-            return IBVH_OK;
-        });
-    });
+    unsigned long long total = 0;
+    long long checks = 0;
+    rc = bfs_leaf_level<kBfsBoth>(h, st, r, fused, bvh1, t1, bvh2, t2, flags, d_contacts, capacity, &total, &checks);
     if (rc != IBVH_OK) return rc;
-    unsigned long long total;
-    rc = r.read_counter(&total);
-    if (rc != IBVH_OK) return rc;
+    if (num_checks) *num_checks = checks;
     *num_contacts = (int64_t)total;
-    if ((d_contacts && (int64_t)total > capacity) || (!d_contacts && total > 0)) bfs_remember(h, 2, bvh1->d_leaves, bvh1->n, bvh2->d_leaves, bvh2->n, start_level1, start_level2, r);
+    if ((d_contacts && (int64_t)total > capacity) || (!d_contacts && total > 0)) bfs_remember(h, 2, bvh1->d_leaves, bvh1->n, bvh2->d_leaves, bvh2->n, start_level1, start_level2, r, fused);
     return d_contacts && (int64_t)total > capacity ? IBVH_ERR_CAPACITY : IBVH_OK;
 }
 

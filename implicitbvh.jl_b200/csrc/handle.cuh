@@ -81,7 +81,7 @@ struct ibvh_handle {
     }
     // leaf-level list of a BFS call that returned IBVH_ERR_CAPACITY (the repeat call only redoes the leaf level)
     struct BfsPending {
-        bool valid = false;
+        bool valid = false, fused = false;       // fused: the list is the LAST NODE level's (its leaf level runs fused, bfs_last_kernel)
         int kind = 0, cur = 0;
         const void *leaves1 = nullptr, *leaves2 = nullptr;
         long long n1 = 0, n2 = 0, start1 = 0, start2 = 0, checks = 0;

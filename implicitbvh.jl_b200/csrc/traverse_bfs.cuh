@@ -33,15 +33,25 @@ struct BfsSide {
     uint32_t stride;           // bytes between elements (leaf arrays: sizeof(BoundingVolume))
     uint32_t child_first;      // implicit index of the first node of the CHILD level (2^level)
     uint32_t child_nreal;      // real nodes on the child level: child 2i+1 is virtual iff 2i+1 - child_first >= child_nreal
+    uint32_t vec;              // widest load every element address allows: 16, 8 or 4 bytes (from the base pointer and the stride)
 };
 IBVH_D bool bfs_right_real(const BfsSide& s, uint32_t implicit) { return 2u * implicit + 1u - s.child_first < s.child_nreal; }
 template <class V> IBVH_D V bfs_load(const BfsSide& s, uint32_t implicit) {
     const char* p = (const char*)s.base + (size_t)(implicit - s.sub) * s.stride;
-    V v;
+    alignas(16) V v;
     using T = typename V::value_type;
-    const T* f = reinterpret_cast<const T*>(p);
+    // (warp-uniform choice: a BBox{Float32} is three 8-byte loads instead of six 4-byte ones, a BSphere{Float32} node one 16-byte load)
+    if (sizeof(V) % 16 == 0 && s.vec >= 16u) {
 #pragma unroll
-    for (int k = 0; k < (int)(sizeof(V) / sizeof(T)); ++k) reinterpret_cast<T*>(&v)[k] = __ldg(f + k);
+        for (int k = 0; k < (int)(sizeof(V) / 16); ++k) reinterpret_cast<uint4*>(&v)[k] = __ldg(reinterpret_cast<const uint4*>(p) + k);
+    } else if (sizeof(V) % 8 == 0 && s.vec >= 8u) {
+#pragma unroll
+        for (int k = 0; k < (int)(sizeof(V) / 8); ++k) reinterpret_cast<uint2*>(&v)[k] = __ldg(reinterpret_cast<const uint2*>(p) + k);
+    } else {
+        const T* f = reinterpret_cast<const T*>(p);
+#pragma unroll
+        for (int k = 0; k < (int)(sizeof(V) / sizeof(T)); ++k) reinterpret_cast<T*>(&v)[k] = __ldg(f + k);
+    }
     return v;
 }
 
@@ -211,6 +221,75 @@ __global__ void __launch_bounds__(kBfsThreads) bfs_leaves_kernel(const uint2* __
             ++pos;
         }
     }
+}
+
+// ---- last node level fused with the leaf level ---------------------------------------------------------------------------------
+// The children of a contacting pair of leaf parents are leaf pairs. The reference writes them to the next list — the widest of
+// the whole descent, ~40 % of all entries — and a second kernel reads them back; here the thread that sprouts them tests the
+// leaf volumes at once and appends the contacts. The children are still counted (*children): they are part of num_checks.
+template <int MODE, bool SORT_PAIR, class N, class V, class I>
+__global__ void __launch_bounds__(kBfsThreads) bfs_last_kernel(const uint2* __restrict__ src, unsigned long long count, BfsSide na, BfsSide nb,
+                                                               BfsSide la, BfsSide lb, uint32_t index_offset, int positions,
+                                                               IndexPair<I>* __restrict__ out, unsigned long long capacity,
+                                                               unsigned long long* counter, unsigned long long* children) {
+    __shared__ uint32_t s_warp[kBfsThreads / 32];
+    __shared__ unsigned long long s_base;
+    unsigned long long nchild = 0;
+    const unsigned long long tiles = (count + kBfsTile - 1) / kBfsTile;
+    for (unsigned long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const unsigned long long first = tile * kBfsTile + (unsigned long long)threadIdx.x * kBfsItems;
+        uint2 e[kBfsItems];
+        bfs_load_entries(src, first, count, e);
+        uint32_t hitmask = 0;                       // 4 bits per entry, bit layout of bfs_nodes_kernel
+#pragma unroll
+        for (int j = 0; j < kBfsItems; ++j) {
+            if (e[j].x == 0u) continue;
+            uint32_t m = 0;
+            if (MODE == kBfsSingle && e[j].x == e[j].y) m = bfs_right_real(na, e[j].x) ? 0x2u : 0x0u;     // leaf self-checks are pointless: only (l, r)
+            else if (bfs_contact(bfs_load<N>(na, e[j].x), bfs_load<N>(nb, e[j].y))) {
+                if (MODE == kBfsSingle) m = bfs_right_real(nb, e[j].y) ? 0xFu : 0x5u;
+                else {
+                    const bool r1 = bfs_right_real(na, e[j].x), r2 = bfs_right_real(nb, e[j].y);
+                    m = 0x1u | (r2 ? 0x2u : 0u) | (r1 ? 0x4u : 0u) | (r1 && r2 ? 0x8u : 0u);
+                }
+            }
+            if (!m) continue;
+            nchild += __popc(m);
+            // the (up to) four leaves involved, loaded once
+            const uint32_t a2 = 2u * e[j].x, b2 = 2u * e[j].y;
+            const V va0 = bfs_load<V>(la, a2), vb0 = bfs_load<V>(lb, (m & 0x5u) ? b2 : b2 + 1u);
+            const V va1 = (m & 0xCu) ? bfs_load<V>(la, a2 + 1u) : va0;
+            const V vb1 = ((m & 0xAu) && (m & 0x5u)) ? bfs_load<V>(lb, b2 + 1u) : vb0;
+            uint32_t hm = 0;
+            if ((m & 0x1u) && iscontact(va0, vb0)) hm |= 0x1u;
+            if ((m & 0x2u) && iscontact(va0, vb1)) hm |= 0x2u;
+            if ((m & 0x4u) && iscontact(va1, vb0)) hm |= 0x4u;
+            if ((m & 0x8u) && iscontact(va1, vb1)) hm |= 0x8u;
+            hitmask |= hm << (4 * j);
+        }
+        unsigned long long pos = bfs_reserve(__popc(hitmask), counter, s_warp, &s_base);
+#pragma unroll
+        for (int j = 0; j < kBfsItems; ++j) {
+            uint32_t hm = (hitmask >> (4 * j)) & 0xFu;
+            while (hm) {
+                const int b = __ffs(hm) - 1;
+                hm &= hm - 1;
+                const uint32_t ca = 2u * e[j].x + (uint32_t)(b >> 1), cb = 2u * e[j].y + (uint32_t)(b & 1);
+                I ia, ib;
+                if (positions) { ia = (I)(ca - la.sub + 1u); ib = (I)(cb - lb.sub + 1u); }
+                else {
+                    ia = *reinterpret_cast<const I*>((const char*)la.base + (size_t)(ca - la.sub) * la.stride + index_offset);
+                    ib = *reinterpret_cast<const I*>((const char*)lb.base + (size_t)(cb - lb.sub) * lb.stride + index_offset);
+                    if (SORT_PAIR && ia > ib) { const I t = ia; ia = ib; ib = t; }
+                }
+                if (pos < capacity) out[pos] = IndexPair<I>{ia, ib};
+                ++pos;
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) nchild += __shfl_xor_sync(0xffffffffu, nchild, d);
+    if ((threadIdx.x & 31) == 0 && nchild) atomicAdd(children, nchild);
 }
 
 // ---- rays (raytrace/breadth_first/raytrace_gpu.jl): entries are (implicit node index, 1-based ray id) ------------------------

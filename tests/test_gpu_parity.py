@@ -1315,6 +1315,10 @@ def test_bfs_rays_types_partial_builds_and_narrow(ib, O, dev):
     pred = lambda a, b: a["morton"] < b["morton"]
     bfs = ib.traverse(bvh, ib.BFSTraversal(), narrow=pred)
     lvt = ib.traverse(bvh, ib.LVTTraversal(), narrow=pred)
+    assert (sorted_pairs(bfs.contacts.numpy()) == sorted_pairs(lvt.contacts.numpy())).all()
+    by_index = lambda a, b: a["index"] < b["index"]          # (bv1 is the LEFT leaf in both algorithms: about half survive)
+    bfs = ib.traverse(bvh, ib.BFSTraversal(), narrow=by_index)
+    lvt = ib.traverse(bvh, ib.LVTTraversal(), narrow=by_index)
     assert 0 < bfs.num_contacts < ib.traverse(bvh).num_contacts
     assert (sorted_pairs(bfs.contacts.numpy()) == sorted_pairs(lvt.contacts.numpy())).all()
     b2 = gpu_build(ib, random_spheres(rng, 64))

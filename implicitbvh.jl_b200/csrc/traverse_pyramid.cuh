@@ -101,9 +101,6 @@ IBVH_D void atomic_inc(int64_t* p) { atomicAdd(reinterpret_cast<unsigned long lo
 #ifndef IBVH_PYR_TMA
 #define IBVH_PYR_TMA 0
 #endif
-#ifndef IBVH_PYR_F32X2
-#define IBVH_PYR_F32X2 1          // leaf-tile kernel, BSphere{Float32} leaves: the sphere tests of a lane's two queries as packed f32x2 instructions
-#endif
 #ifndef IBVH_PYR_QPL
 #define IBVH_PYR_QPL 2            // query leaves per lane in the leaf-tile kernel (register tile QPL x 4)
 #endif
@@ -716,14 +713,6 @@ __global__ void __launch_bounds__(kPyrWarps * 32, 8) pyr_refine_tma_kernel(const
     if (nbuf) flush(nbuf);
 }
 
-// ---- packed FP32 pairs (sm_100: FADD2 / FMUL2; every half rounds like the scalar instruction) --------------------------------
-IBVH_D unsigned long long f32x2_pack(float lo, float hi) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-IBVH_D float f32x2_lo(unsigned long long v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); (void)b; return a; }
-IBVH_D float f32x2_hi(unsigned long long v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); (void)a; return b; }
-IBVH_D unsigned long long f32x2_sub(unsigned long long a, unsigned long long b) { unsigned long long r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-IBVH_D unsigned long long f32x2_add(unsigned long long a, unsigned long long b) { unsigned long long r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-IBVH_D unsigned long long f32x2_mul(unsigned long long a, unsigned long long b) { unsigned long long r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-
 // ---- 4. leaf tiles ------------------------------------------------------------------------------------------------
 // MODE kAtomic: append contacts (unordered). kCount: only add the number of contacts to *total.
 // PMODE (ordered protocol): 0 = none; 1 = count per query (atomicAdd counts[qi]); 2 = write (qpos, tpos) into the
@@ -975,35 +964,8 @@ __global__ void __launch_bounds__(kPyrWarps * 32, pyr_tile_minb<LQ>()) pyr_leaf_
         uint32_t hits[QPL];
 #pragma unroll
         for (int k = 0; k < QPL; ++k) hits[k] = 0;
-        if constexpr (IBVH_PYR_F32X2 != 0 && QPL == 2 && std::is_same<VQ, BSphere<float>>::value && std::is_same<VT, BSphere<float>>::value) {
-            // Blackwell packed FP32 (FADD2 / FMUL2 work on aligned register pairs): a sphere record (x, y, z, r) is two such
-            // pairs as it comes out of a 16-byte load, so one test is
-            //   (dx, dy) = (t.x, t.y) - (q.x, q.y)          (dz, rs) = (t.z, t.r) - (q.z, -q.r)         2 FADD2
-            //   (dx^2, dy^2), (dz^2, rs^2)                                                               2 FMUL2
-            //   d = (dx^2 + dy^2) + dz^2 ;  hit = d <= rs^2                                              2 FADD + FSETP
-            // = 7 instructions instead of 11, with no packing moves. Each half rounds like the scalar instruction and is the
-            // reference's expression bit for bit: (t - q)^2 == (q - t)^2, t.r - (-q.r) == q.r + t.r, and the three-term sum
-            // keeps the reference's association as scalar FADDs — ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2
-            // even under -fmad=false, so no packed add may follow a packed mul (this kernel's SASS holds no FFMA / FFMA2).
-            unsigned long long qxy[QPL], qzr[QPL];
-#pragma unroll
-            for (int k = 0; k < QPL; ++k) {
-                qxy[k] = f32x2_pack(cur.q[k].v.x[0], cur.q[k].v.x[1]);
-                qzr[k] = f32x2_pack(cur.q[k].v.x[2], -cur.q[k].v.r);
-            }
-#pragma unroll
-            for (int j = 0; j < G; ++j) {
-                const float4 tv = *reinterpret_cast<const float4*>(s_vraw[w][buf][slot] + j * sizeof(TVol));
-                const unsigned long long txy = f32x2_pack(tv.x, tv.y), tzr = f32x2_pack(tv.z, tv.w);
-#pragma unroll
-                for (int k = 0; k < QPL; ++k) {
-                    const unsigned long long dxy = f32x2_sub(txy, qxy[k]), dzr = f32x2_sub(tzr, qzr[k]);
-                    const unsigned long long mxy = f32x2_mul(dxy, dxy), mzr = f32x2_mul(dzr, dzr);
-                    const float d = (f32x2_lo(mxy) + f32x2_hi(mxy)) + f32x2_lo(mzr);
-                    if (d <= f32x2_hi(mzr)) hits[k] |= 1u << j;
-                }
-            }
-        } else {
+        // (BSphere{Float32}: leaf_contact is the packed-FP32 form, traverse_tile.cuh — FADD2 / FMUL2 straight on the register
+        // pairs of the 16-byte loads, 7 instructions per test instead of 11: 1.229 -> 1.121 ms at 10 M leaves)
 #pragma unroll
         for (int j = 0; j < G; ++j) {
             alignas(16) TVol tv;
@@ -1013,7 +975,6 @@ __global__ void __launch_bounds__(kPyrWarps * 32, pyr_tile_minb<LQ>()) pyr_leaf_
             for (int k = 0; k < (int)(sizeof(TVol) / 16); ++k) dp[k] = sp[k];
 #pragma unroll
             for (int k = 0; k < QPL; ++k) if (leaf_contact(cur.q[k].v, tv.v)) hits[k] |= 1u << j;
-        }
         }
         const uint32_t qp0 = cur.qpos0 + (uint32_t)(QPL * i);
         // rare masks: tail lanes of a chunk, query groups cut by the shard range, and (single tree) the diagonal

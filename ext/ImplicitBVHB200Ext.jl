@@ -390,6 +390,16 @@ function ImplicitBVH.traverse_rays(
     BVHTraversal(start_level, checks, total, cache1, cache2)
 end
 
+# ---- opt-in extension: sort (and deduplicate) a contact list on the device — what `sort(traversal.contacts)` does on the host in
+# the reference's tests (test/gputests.jl:73-78); for the unordered emission modes, whose lists are sets (SURVEY.md §8f-2)
+function sort_contacts!(t::BVHTraversal{<:CuVector{IndexPair{I}}}; unique::Bool=false) where I
+    kept = Ref{Int64}(t.num_contacts)
+    h = handle()
+    check(ccall((:ibvh_sort_contacts, LIB), Cint, (Ptr{Cvoid}, CuPtr{Cvoid}, Int64, Int32, Cint, Ref{Int64}, Ptr{Cvoid}),
+                h, pointer(t.cache1), t.num_contacts, sizeof(I), unique ? 1 : 0, kept, stream()), h)
+    BVHTraversal(t.start_level1, t.start_level2, t.num_checks, Int(kept[]), t.cache1, t.cache2)
+end
+
 # ---- opt-in extension: asynchronous contact detection (IBVH_TRAVERSE_DEFER) ----------------------------------------
 # `pending = traverse_deferred(bvh; cache)` only enqueues the (unordered) traversal; `BVH(next...; cache=other)` can be
 # enqueued behind it; `finish!(pending)` waits for the count. At most one may be outstanding per device; a pending

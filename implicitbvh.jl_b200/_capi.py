@@ -79,6 +79,7 @@ SIGNATURES = {
     "ibvh_traverse_bfs_single": (_ci, [_vp, C.POINTER(Bvh), C.POINTER(TraverseParams), _vp, _i64, C.POINTER(_i64), C.POINTER(_i64), _vp]),
     "ibvh_traverse_bfs_pair": (_ci, [_vp, C.POINTER(Bvh), C.POINTER(Bvh), _i64, _i64, C.c_uint32, _vp, _i64, C.POINTER(_i64), C.POINTER(_i64), _vp]),
     "ibvh_traverse_bfs_rays": (_ci, [_vp, C.POINTER(Bvh), _vp, _vp, _i64, C.POINTER(TraverseParams), _vp, _i64, C.POINTER(_i64), C.POINTER(_i64), _vp]),
+    "ibvh_sort_contacts": (_ci, [_vp, _vp, _i64, C.c_int32, _ci, C.POINTER(_i64), _vp]),
     "ibvh_profile_enable": (_ci, [_vp, _ci]),
     "ibvh_profile_count": (_ci, [_vp]),
     "ibvh_profile_get": (_ci, [_vp, _ci, C.c_char_p, _ci, C.POINTER(C.c_float)]),

@@ -905,6 +905,25 @@ def traverse(bvh: BVH, bvh2=None, alg=None, *, start_level: Optional[int] = None
     return out
 
 
+def sort_contacts(traversal: BVHTraversal, unique: bool = False) -> BVHTraversal:
+    """Sort a traversal's contact list ascending by (a, b) on the device, in place (optionally dropping repeated pairs) — what
+    the reference's tests do on the host with `sort(traversal.contacts)` (test/gputests.jl:73-78) before comparing lists.
+    For the unordered emission modes (`ordered=False`, `BFSTraversal()`), whose lists are sets. SURVEY.md §8f-2."""
+    c1 = traversal.cache1
+    n = traversal.num_contacts
+    if not c1.is_cuda:
+        raise ArgumentError("sort_contacts: the contacts must live on a CUDA device")
+    handle = get_handle(c1.device)
+    _resolve_outstanding(c1.device.index)
+    kept = C.c_int64(n)
+    rc = capi.lib().ibvh_sort_contacts(handle, c1.ptr if n else None, n, c1.dtype.itemsize // 2, 1 if unique else 0, C.byref(kept),
+                                       _stream_ptr(c1.device.index))
+    if rc != capi.OK:
+        _raise(rc, handle, "sort_contacts")
+    traversal.num_contacts = int(kept.value)
+    return traversal
+
+
 def traverse_rays(bvh: BVH, points, directions, alg=None, *, start_level: int = 1, narrow=None,
                   cache: Optional[BVHTraversal] = None, options: BVHOptions = None, ordered: bool = True,
                   id_base: int = 0, peer=None) -> BVHTraversal:

@@ -2212,6 +2212,78 @@ int ibvh_traverse_bfs_rays(ibvh_handle_t* h, const ibvh_bvh_t* bvh, const void* 
     if ((d_contacts && (int64_t)total > capacity) || (!d_contacts && total > 0)) bfs_remember(h, 3, bvh->d_leaves, bvh->n, d_points, nrays, sl, sl, r);
     return d_contacts && (int64_t)total > capacity ? IBVH_ERR_CAPACITY : IBVH_OK;
 }
+// Opt-in post-processing of a contact list on the device: ascending by (a, b), optionally unique.
+int ibvh_sort_contacts(ibvh_handle_t* h, void* d_contacts, int64_t count, int32_t index_bytes, int unique, int64_t* out_count, void* stream) {
+    if (!h || count < 0 || (index_bytes != 4 && index_bytes != 8) || (count > 0 && !d_contacts)) return IBVH_ERR_ARGUMENT;
+    if (h->deferred.active) { h->set_error("a deferred traversal is outstanding on this handle: call ibvh_traverse_finish (or ibvh_traverse_cancel) first"); return IBVH_ERR_ARGUMENT; }
+    if (out_count) *out_count = count;
+    if (count <= 1) return IBVH_OK;
+    if (count > (int64_t(1) << 31)) { h->set_error("ibvh_sort_contacts: more than 2^31 pairs"); return IBVH_ERR_UNSUPPORTED; }
+    if (reinterpret_cast<uintptr_t>(d_contacts) % (2u * (unsigned)index_bytes) != 0) return IBVH_ERR_ARGUMENT;
+    DeviceGuard g(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    using M = uint64_t;
+    constexpr int P = radix_passes<M>();
+    const int64_t n = count;
+    const size_t lb_bytes = (sort_wide_lookback(n) || h->cfg.force_wide_lookback) ? 8 : 4;
+    const int64_t tiles = (n + sort_tile<M>() - 1) / sort_tile<M>();
+    const int64_t scan_blocks = (n + kScanTile - 1) / kScanTile;
+    size_t need = 2 * ibvh_handle::padded((size_t)n * 8) + 2 * ibvh_handle::padded((size_t)n * 4) + ibvh_handle::padded((size_t)P * radix_bins<M>() * 4) +
+                  ibvh_handle::padded((size_t)P * tiles * radix_bins<M>() * lb_bytes) + ibvh_handle::padded((size_t)scan_blocks * 8) + 4096;
+    int rc = h->reserve(need);
+    if (rc != IBVH_OK) return rc;
+    h->reset();
+    M* keysA = h->alloc<M>(n); M* keysB = h->alloc<M>(n);
+    uint32_t* valsA = h->alloc<uint32_t>(n); uint32_t* valsB = h->alloc<uint32_t>(n);
+    uint32_t* hist = h->alloc<uint32_t>((size_t)P * radix_bins<M>());
+    unsigned char* lookback = h->alloc<unsigned char>((size_t)P * tiles * radix_bins<M>() * lb_bytes);
+    long long* block_sums = h->alloc<long long>((size_t)scan_blocks);
+    uint32_t* tickets = (uint32_t*)(h->d_small + kSmallTickets);
+    if (!keysA || !keysB || !valsA || !valsB || !hist || !lookback || !block_sums) { h->set_error("workspace carve failed"); return IBVH_ERR_ALLOC; }
+    IBVH_CUDA_TRY(h, cudaMemsetAsync(lookback, 0, (size_t)P * tiles * radix_bins<M>() * lb_bytes, st));
+    IBVH_CUDA_TRY(h, cudaMemsetAsync(hist, 0, (size_t)P * radix_bins<M>() * 4, st));
+    IBVH_CUDA_TRY(h, cudaMemsetAsync(tickets, 0, 16 * 4, st));
+    uint32_t* d_bad = (uint32_t*)(h->d_small + kSmallBfs + 16);
+    unsigned long long* d_total = (unsigned long long*)(h->d_small + kSmallBfs);
+    IBVH_CUDA_TRY(h, cudaMemsetAsync(d_total, 0, 24, st));
+    const int grid = grid_for(n, 256, 4, h->sm_count * 8);
+    { ProfScope _ps(h, st, "contact_keys_kernel");
+    if (index_bytes == 4) contact_keys_kernel<int32_t><<<grid, 256, 0, st>>>((const IndexPair<int32_t>*)d_contacts, n, keysA, hist, d_bad);
+    else contact_keys_kernel<int64_t><<<grid, 256, 0, st>>>((const IndexPair<int64_t>*)d_contacts, n, keysA, hist, d_bad);
+    }
+    IBVH_LAUNCH_CHECK(h, "contact_keys_kernel");
+    unsigned long long* hp = (unsigned long long*)h->h_pinned;
+    IBVH_CUDA_TRY(h, cudaMemcpyAsync(hp, d_bad, 4, cudaMemcpyDeviceToHost, st));
+    IBVH_CUDA_TRY(h, cudaStreamSynchronize(st));
+    if (((const uint32_t*)hp)[0] != 0) {
+        h->set_error("ibvh_sort_contacts: an index outside [0, 2^31) x [0, 2^32) (the keys are a << 32 | b); the list is untouched");
+        return IBVH_ERR_UNSUPPORTED;
+    }
+    M* sorted; uint32_t* perm;
+    rc = sort_pairs<M>(h, keysA, keysB, valsA, valsB, n, hist, lookback, tickets, st, &sorted, &perm);
+    if (rc != IBVH_OK) return rc;
+    int32_t* slots = nullptr;
+    if (unique) {
+        slots = (int32_t*)(perm == valsA ? valsB : valsA);          // the permutation is not needed: its other buffer holds the flags
+        { ProfScope _ps(h, st, "contact_flags_kernel");
+        contact_flags_kernel<<<grid, 256, 0, st>>>(sorted, n, slots);
+        }
+        IBVH_LAUNCH_CHECK(h, "contact_flags_kernel");
+        rc = scan_counts<int32_t>(h, slots, n, block_sums, d_total, st);
+        if (rc != IBVH_OK) return rc;
+    }
+    { ProfScope _ps(h, st, "contact_unpack_kernel");
+    if (index_bytes == 4) contact_unpack_kernel<int32_t><<<grid, 256, 0, st>>>(sorted, n, slots, (IndexPair<int32_t>*)d_contacts);
+    else contact_unpack_kernel<int64_t><<<grid, 256, 0, st>>>(sorted, n, slots, (IndexPair<int64_t>*)d_contacts);
+    }
+    IBVH_LAUNCH_CHECK(h, "contact_unpack_kernel");
+    if (unique) {
+        IBVH_CUDA_TRY(h, cudaMemcpyAsync(hp, d_total, 8, cudaMemcpyDeviceToHost, st));
+        IBVH_CUDA_TRY(h, cudaStreamSynchronize(st));
+        if (out_count) *out_count = (int64_t)hp[0];
+    }
+    return IBVH_OK;
+}
 #endif  // IBVH_PART_BFS
 
 }  // extern "C"

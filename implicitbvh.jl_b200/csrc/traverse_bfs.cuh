@@ -19,6 +19,7 @@
 //     of the ilog2 + shifts of implicit_tree.jl:191-199 per entry.
 #pragma once
 #include "common.cuh"
+#include "radix_sort.cuh"
 
 namespace ibvh {
 
@@ -387,6 +388,55 @@ static __global__ void bfs_init_product_kernel(uint2* dst, uint32_t first_a, uns
     const unsigned long long total = na * nb;
     for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (unsigned long long)gridDim.x * blockDim.x)
         dst[t] = make_uint2(first_a + (uint32_t)(t / nb), first_b + (uint32_t)(t % nb));
+}
+
+// ---- sorted / unique contact lists ------------------------------------------------------------------------
+// The reference's tests compare `sort(traversal.contacts)` (test/gputests.jl:73-78, runtests.jl:1246-1250): lexicographic by
+// (a, b). On the device that is the onesweep radix sort of radix_sort.cuh over the 64-bit keys (a << 32 | b).
+// pairs -> keys (+ the digit histograms of all passes; *bad is set if an index does not fit 32 unsigned bits)
+template <class I>
+__global__ void __launch_bounds__(256) contact_keys_kernel(const IndexPair<I>* __restrict__ pairs, int64_t n, uint64_t* __restrict__ keys,
+                                                          uint32_t* __restrict__ hist, uint32_t* bad) {
+    constexpr int P = radix_passes<uint64_t>();
+    constexpr int RB = radix_bits<uint64_t>(), BINS = radix_bins<uint64_t>();
+    __shared__ uint32_t sh[P][BINS];
+    for (int i = threadIdx.x; i < P * BINS; i += blockDim.x) (&sh[0][0])[i] = 0;
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const IndexPair<I> pr = pairs[i];
+        const uint64_t a = (uint64_t)(long long)pr.a, b = (uint64_t)(long long)pr.b;
+        if ((a >> 31) != 0 || (b >> 32) != 0) *bad = 1u;          // (a < 2^31: the key keeps bit 63 clear, as the sort's sentinel needs)
+        const uint64_t m = (a << 32) | (b & 0xffffffffull);
+        keys[i] = m;
+#pragma unroll
+        for (int p = 0; p < P; ++p) atomicAdd(&sh[p][(uint32_t)(m >> (p * RB)) & (BINS - 1)], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < P * BINS; i += blockDim.x) {
+        const uint32_t v = (&sh[0][0])[i];
+        if (v) atomicAdd(&hist[i], v);
+    }
+}
+// flags[i] = 1 if sorted key i starts a run of equal keys
+static __global__ void __launch_bounds__(256) contact_flags_kernel(const uint64_t* __restrict__ keys, int64_t n, int32_t* __restrict__ flags) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+}
+// sorted keys -> pairs; slots != nullptr: the inclusive scan of the run-start flags (unique: key i goes to slot slots[i] - 1 if it starts a run)
+template <class I>
+__global__ void __launch_bounds__(256) contact_unpack_kernel(const uint64_t* __restrict__ keys, int64_t n, const int32_t* __restrict__ slots,
+                                                            IndexPair<I>* __restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t m = keys[i];
+        int64_t dst = i;
+        if (slots) {
+            if (i > 0 && keys[i - 1] == m) continue;
+            dst = (int64_t)slots[i] - 1;
+        }
+        out[dst] = IndexPair<I>{(I)(m >> 32), (I)(m & 0xffffffffull)};
+    }
 }
 
 }  // namespace ibvh

@@ -309,6 +309,16 @@ IBVH_API int ibvh_traverse_bfs_rays(ibvh_handle_t* h, const ibvh_bvh_t* bvh, con
                            int64_t nrays, const ibvh_traverse_params_t* params, void* d_contacts, int64_t capacity,
                            int64_t* num_contacts, int64_t* num_checks, void* stream);
 
+/* ---- sorted / unique contact lists (opt-in post-processing on the device) ---------
+ * Sorts the `count` pairs of a contact list ascending by (a, b) — the order in which the reference's tests compare lists
+ * (`sort(traversal.contacts)`, test/gputests.jl:73-78, runtests.jl:1246-1250) — in place, with the library's onesweep radix
+ * sort over the keys a << 32 | b; `unique != 0` also drops repeated pairs (*out_count = pairs kept; the tail of the
+ * buffer is unspecified). Meant for the unordered emission modes (IBVH_TRAVERSE_UNORDERED, the BFS traversals), whose
+ * lists are sets. Indices must lie in [0, 2^31) x [0, 2^32) — true for the 1..n that wrap_bounding_volumes assigns —
+ * else IBVH_ERR_UNSUPPORTED and the list is untouched. count <= 2^31. Synchronises the stream. */
+IBVH_API int ibvh_sort_contacts(ibvh_handle_t* h, void* d_contacts, int64_t count, int32_t index_bytes, int unique,
+                       int64_t* out_count, void* stream);
+
 /* ---- per-kernel timing (measurement aid; bench.py's roofline uses it) ----------------------
  * When enabled, every kernel launch of this handle is bracketed by CUDA events on the launching
  * stream. ibvh_profile_get(i) synchronises event i and returns the kernel family name and its

@@ -1354,3 +1354,39 @@ def test_bfs_100k_against_oracle_and_capacity_protocol(ib, O, dev):
     assert got.num_checks == checks
     assert (sorted_pairs(got.contacts.numpy()) == sorted_pairs(want)).all()
     assert (sorted_pairs(want) == sorted_pairs(O.traverse_pair(ol, on, o2, on2, num_threads=8))).all()
+
+
+@pytest.mark.gpu
+def test_sort_contacts_sorted_and_unique(ib, O, dev):
+    """the unordered lists sorted on the device == the oracle's list sorted on the host
+    (`sort(traversal.contacts)`, gputests.jl:73-78); unique drops repeated pairs."""
+    import torch
+    from ibvh_b200 import synth
+    for n, ibytes, mbytes in ((100_000, 4, 4), (20_000, 8, 8), (3, 4, 4)):
+        s = synth.random_spheres_np(n, seed=42) if n > 3 else ib.bspheres([[0, 0, 0], [0, 0, 1], [0, 0, 5]], [0.6, 0.6, 0.1])
+        ol, on = oracle_build(O, s, "bbox", ibytes, mbytes)
+        bvh = gpu_build(ib, s, "bbox", ibytes, mbytes)
+        want = sorted_pairs(O.traverse_single(ol, on, num_threads=8))
+        for tr in (ib.traverse(bvh, ordered=False), ib.traverse(bvh, ib.BFSTraversal())):
+            out = ib.sort_contacts(tr)
+            got = out.contacts.numpy()
+            assert out.num_contacts == len(want)
+            assert (np.stack([got["a"], got["b"]], 1).astype(np.int64) == want).all(), (n, ibytes)
+    # unique: a list that holds every pair three times
+    I = np.int32
+    tr = ib.traverse(gpu_build(ib, synth.random_spheres_np(50_000, seed=1)), ordered=False)
+    k = tr.num_contacts
+    trip = torch.cat([tr.contacts.tensor] * 3)
+    rep = ib.BVHTraversal(1, 0, 0, 3 * k, ib.DeviceArray(trip, ib.pair_dtype(I)), tr.cache2)
+    uni = ib.sort_contacts(rep, unique=True)
+    assert uni.num_contacts == k
+    ref = ib.sort_contacts(tr).contacts.numpy()
+    assert uni.contacts.numpy().tobytes() == ref.tobytes()
+    assert ib.sort_contacts(rep).num_contacts == k          # (already unique: sorting again keeps it)
+    # indices that do not fit the 64-bit key: refused, list untouched
+    bad = np.zeros(4, ib.pair_dtype(np.int64))
+    bad["a"] = [1, 2, -3, 4]; bad["b"] = [5, 6, 7, 1 << 40]
+    d = ib.DeviceArray.from_numpy(bad, device=dev)
+    with pytest.raises(Exception):
+        ib.sort_contacts(ib.BVHTraversal(1, 0, 0, 4, d, d))
+    assert d.numpy().tobytes() == bad.tobytes()

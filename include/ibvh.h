@@ -1,6 +1,6 @@
 /* ibvh.h — C ABI of libibvh_b200.so: the B200-native (sm_100a) replacement for the data-parallel
  * hot path of ImplicitBVH.jl (Morton encode + scene bounds, Morton sort, bottom-up implicit-tree
- * merge, LVT single / pair / ray traversal).
+ * merge, LVT and BFS single / pair / ray traversal).
  *
  * The reference has no FFI: its extension points are Julia multiple dispatch on
  * `MortonAlgorithm` (src/morton/morton.jl:4-15), `TraversalAlgorithm`

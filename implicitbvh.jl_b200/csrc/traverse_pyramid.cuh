@@ -561,6 +561,138 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_refine_q_kernel(const QBox
     if (nbuf) flush(nbuf);
 }
 
+// ---- 3a'. the same with TWO query children per lane ---------------------------------------------------------------------
+// ncu has pyr_refine_q_kernel issue-bound (80 %) at 200 warp instructions per 256-test step, of which the tests are 58: the
+// rest is per-step overhead (entry / box fetch, staging, masks, append, loop). Here a lane owns the children 2i and 2i+1 of A,
+// a pair takes 4 lanes and a warp step covers 8 pairs = 512 tests: the target boxes read from shared memory serve two
+// queries and the per-step overhead serves twice the tests (the move that took the leaf-tile kernel from 1193 M to 955 M
+// instructions in round 1). Same pair lists as a set; the order inside a flush differs (the leaf tiles do not depend on it).
+template <int KIND>
+__global__ void __launch_bounds__(kPyrWarps * 32) pyr_refine_q2_kernel(const QBoxU* __restrict__ Uf, const QBoxT* __restrict__ Nf,
+                                                                      uint32_t f_first, uint32_t f_nqg, uint32_t f_ntg,
+                                                                      PairList in, PairList out, uint32_t* ticket) {
+    constexpr int F = 1 << kPyrFan;          // 8
+    constexpr int QPL = 2;                   // query children per lane
+    constexpr int LPP = F / QPL;             // 4 lanes per pair
+    constexpr int SLOTS = 32 / LPP;          // 8 pairs per warp step
+    constexpr int PIECES = F * (int)sizeof(QBoxT) / 16;                   // 6
+    constexpr int SLOT_BYTES = F * (int)sizeof(QBoxT) + 16;               // 112
+    static_assert(F == 8 && sizeof(QBoxT) == 12 && PIECES <= 2 * LPP, "piece mapping");
+    __shared__ __align__(16) unsigned char s_raw[kPyrWarps][SLOTS][SLOT_BYTES];
+    __shared__ uint2 s_buf[kPyrWarps][32 * QPL * F + kPyrFlush];
+    __shared__ uint32_t s_n[kPyrWarps];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int slot = lane / LPP, i = lane % LPP;
+    if (lane == 0) s_n[w] = 0;
+    __syncwarp();
+    unsigned long long count64 = *in.count;
+    if (count64 > in.cap) count64 = in.cap;
+    const uint32_t count = (uint32_t)count64;
+    uint32_t nbuf = 0;
+    auto flush = [&](uint32_t n) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(out.count, (unsigned long long)n);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const uint32_t b0 = nbuf - n;
+        for (uint32_t k = lane; k < n; k += 32) if (base + k < out.cap) out.data[base + k] = s_buf[w][b0 + k];
+        nbuf = b0;
+    };
+    struct Stage { uint32_t Ac, Bc0, ok; uint4 u0, u1, tp0, tp1; };
+    auto fetch = [&](uint2 pr, bool have) -> Stage {
+        Stage sg;
+        sg.Ac = (pr.x << kPyrFan) + (uint32_t)(QPL * i);                   // my first child of A (the second is Ac + 1)
+        sg.Bc0 = pr.y << kPyrFan;
+        const uint32_t ua = sg.Ac - f_first;                               // wraps if Ac < f_first; ua + 1 wraps back to 0 when only the second child is inside
+        sg.ok = have ? ((ua < f_nqg ? 1u : 0u) | (ua + 1u < f_nqg ? 2u : 0u)) : 0u;
+        sg.u0 = __ldg(reinterpret_cast<const uint4*>(Uf + min(ua, f_nqg - 1u)));
+        sg.u1 = __ldg(reinterpret_cast<const uint4*>(Uf + min(ua + 1u, f_nqg - 1u)));
+        sg.tp0 = __ldg(reinterpret_cast<const uint4*>(Nf + sg.Bc0) + i);     // pieces 0..3 (the copy is padded to whole groups)
+        sg.tp1 = make_uint4(0u, 0u, 0u, 0u);
+        if (i + LPP < PIECES) sg.tp1 = __ldg(reinterpret_cast<const uint4*>(Nf + sg.Bc0) + i + LPP);   // pieces 4, 5
+        return sg;
+    };
+    volatile uint32_t* s_nv = s_n;
+    auto process = [&](const Stage& cur) {
+        reinterpret_cast<uint4*>(s_raw[w][slot])[i] = cur.tp0;
+        if (i + LPP < PIECES) reinterpret_cast<uint4*>(s_raw[w][slot])[i + LPP] = cur.tp1;
+        __syncwarp();
+        uint32_t hits = 0;                                                 // bits [0, 8): targets hit by child 0, [8, 16): by child 1
+        if (cur.ok) {
+            const uint4* sp = reinterpret_cast<const uint4*>(s_raw[w][slot]);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {                                  // 3 pieces = 4 boxes
+                const uint4 p0 = sp[3 * q], p1 = sp[3 * q + 1], p2 = sp[3 * q + 2];
+                const uint32_t bw[12] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t r0 = (cur.u0.x - bw[3 * j]) & (cur.u0.y - bw[3 * j + 1]) & (cur.u0.z - bw[3 * j + 2]);
+                    const uint32_t r1 = (cur.u1.x - bw[3 * j]) & (cur.u1.y - bw[3 * j + 1]) & (cur.u1.z - bw[3 * j + 2]);
+                    if ((r0 & kQGuard) == kQGuard) hits |= 1u << (4 * q + j);
+                    if ((r1 & kQGuard) == kQGuard) hits |= 1u << (F + 4 * q + j);
+                }
+            }
+            uint32_t keep = ((cur.ok & 1u) ? 0xffu : 0u) | ((cur.ok & 2u) ? 0xff00u : 0u);
+            bool edge = cur.Bc0 + (uint32_t)F > f_ntg;
+            if constexpr (KIND == kSingle) edge = edge || cur.Ac + 1u > cur.Bc0;
+            if (edge) {
+                const uint32_t nval = f_ntg - cur.Bc0;
+                const uint32_t inside = nval >= (uint32_t)F ? ((1u << F) - 1u) : ((1u << nval) - 1u);
+                uint32_t a0 = inside, a1 = inside;
+                if constexpr (KIND == kSingle) {                             // child j of B admissible for child c of A iff Bc0 + j >= Ac + c
+                    if (cur.Ac > cur.Bc0) { const uint32_t lo = cur.Ac - cur.Bc0; a0 &= lo >= (uint32_t)F ? 0u : ~((1u << lo) - 1u); }
+                    if (cur.Ac + 1u > cur.Bc0) { const uint32_t lo = cur.Ac + 1u - cur.Bc0; a1 &= lo >= (uint32_t)F ? 0u : ~((1u << lo) - 1u); }
+                }
+                keep &= a0 | (a1 << F);
+            }
+            hits &= keep;
+        }
+        if (hits) {
+            uint32_t wpos = atomicAdd(&s_n[w], (uint32_t)__popc(hits));
+            do {
+                const int b = __ffs(hits) - 1;
+                hits &= hits - 1;
+                s_buf[w][wpos++] = make_uint2(cur.Ac + (uint32_t)(b >> kPyrFan), cur.Bc0 + (uint32_t)(b & (F - 1)));
+            } while (hits);
+        }
+        __syncwarp();
+        nbuf = s_nv[w];
+        if (nbuf >= (uint32_t)kPyrFlush) { flush(nbuf & ~31u); __syncwarp(); if (lane == 0) s_nv[w] = nbuf; }
+        __syncwarp();
+    };
+    const uint32_t chunk = SLOTS * pyr_chunk_steps(count, SLOTS);
+    for (;;) {
+        uint32_t c = 0;
+        if (lane == 0) c = atomicAdd(ticket, 1u);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        const unsigned long long base64 = (unsigned long long)c * chunk;
+        if (base64 >= count) break;
+        const uint32_t base = (uint32_t)base64;
+        const uint32_t end = count - base > chunk ? base + chunk : count;
+        uint32_t p = base + slot;
+        uint2 e1 = make_uint2(0u, 0u), e2 = make_uint2(0u, 0u);
+        if (p < end) e1 = in.data[p];
+        if (p + SLOTS < end) e2 = in.data[p + SLOTS];
+        auto next_entry = [&]() {
+            uint2 e = make_uint2(0u, 0u);
+            if (p + 2 * SLOTS < end) e = in.data[p + 2 * SLOTS];
+            return e;
+        };
+        Stage sa = fetch(e1, p < end), sb;
+        for (uint32_t p0 = base; p0 < end;) {
+            sb = fetch(e2, p + SLOTS < end);
+            e2 = next_entry();
+            process(sa);
+            p0 += SLOTS; p += SLOTS;
+            if (p0 >= end) break;
+            sa = fetch(e2, p + SLOTS < end);
+            e2 = next_entry();
+            process(sb);
+            p0 += SLOTS; p += SLOTS;
+        }
+    }
+    if (nbuf) flush(nbuf);
+}
+
 // ---- 3b. refine, TMA form ------------------------------------------------------------------------------------------
 // Same work, same pair lists as pyr_refine_kernel. Per warp step (4 pairs) ONE lane arms the stage's mbarrier and four
 // lanes issue two bulk copies each: the 8 child boxes of B (one aligned run of F * sizeof(N) bytes in the aligned node

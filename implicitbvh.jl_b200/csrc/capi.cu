@@ -1012,8 +1012,10 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
         }
         for (int l = nl - 1; l >= 1; --l) {
             { ProfScope _ps(h, st, "pyr_refine_kernel");
-            if (quant && h->cfg.pyr_q2)
-                pyr_refine_q2_kernel<KIND><<<grid, kPyrWarps * 32, 0, st>>>(Uq + plan.lv[l - 1].u_off, NTq + plan.lv[l - 1].t_off, (uint32_t)plan.lv[l - 1].qg_first, (uint32_t)plan.lv[l - 1].nqg, (uint32_t)plan.lv[l - 1].ntg, lists[l], lists[l - 1], d_tick + l);
+            if (quant && h->cfg.pyr_q2 == 4)
+                pyr_refine_q2_kernel<KIND, 4><<<grid, kPyrWarps * 32, 0, st>>>(Uq + plan.lv[l - 1].u_off, NTq + plan.lv[l - 1].t_off, (uint32_t)plan.lv[l - 1].qg_first, (uint32_t)plan.lv[l - 1].nqg, (uint32_t)plan.lv[l - 1].ntg, lists[l], lists[l - 1], d_tick + l);
+            else if (quant && h->cfg.pyr_q2)
+                pyr_refine_q2_kernel<KIND, 2><<<grid, kPyrWarps * 32, 0, st>>>(Uq + plan.lv[l - 1].u_off, NTq + plan.lv[l - 1].t_off, (uint32_t)plan.lv[l - 1].qg_first, (uint32_t)plan.lv[l - 1].nqg, (uint32_t)plan.lv[l - 1].ntg, lists[l], lists[l - 1], d_tick + l);
             else if (quant)
                 pyr_refine_q_kernel<KIND><<<grid, kPyrWarps * 32, 0, st>>>(Uq + plan.lv[l - 1].u_off, NTq + plan.lv[l - 1].t_off, (uint32_t)plan.lv[l - 1].qg_first, (uint32_t)plan.lv[l - 1].nqg, (uint32_t)plan.lv[l - 1].ntg, lists[l], lists[l - 1], d_tick + l);
             else if (h->cfg.pyr_tma)

@@ -26,7 +26,7 @@ struct ibvh_handle {
         bool no_sidecar = false;              // IBVH_NO_SIDECAR: the build does not keep the traversal's packed records
         int pyr_grid = 20;                    // IBVH_PYR_GRID: CTAs per SM of the refine / tile kernels
         bool pyr_quant = true;                // IBVH_PYR_QUANT=0: refine over the float boxes instead of the conservatively quantised ones
-        bool pyr_q2 = true;                   // IBVH_PYR_Q2=0: quantised refine kernel with one query child per lane (round-2 form) instead of two
+        int pyr_q2 = 2;                       // IBVH_PYR_Q2: query children per lane of the quantised refine kernel: 2 (default), 4, or 0 = the one-child form
         bool pyr_tma = false;                 // IBVH_PYR_TMA=1: refine kernel with TMA bulk copies + mbarrier instead of LDG -> STS (measured slower: see traverse_pyramid.cuh)
         void parse() {
             auto on = [](const char* k) { const char* v = getenv(k); return v != nullptr && v[0] != '\0' && !(v[0] == '0' && v[1] == '\0'); };
@@ -41,7 +41,7 @@ struct ibvh_handle {
             no_sidecar = on("IBVH_NO_SIDECAR");
             pyr_tma = on("IBVH_PYR_TMA");
             if (const char* v = getenv("IBVH_PYR_QUANT")) pyr_quant = !(v[0] == '0' && v[1] == '\0');
-            if (const char* v = getenv("IBVH_PYR_Q2")) pyr_q2 = !(v[0] == '0' && v[1] == '\0');
+            if (const char* v = getenv("IBVH_PYR_Q2")) { int g = atoi(v); pyr_q2 = (g == 4) ? 4 : (g == 0 ? 0 : 2); }
             if (const char* v = getenv("IBVH_PYR_GRID")) { int g = atoi(v); if (g > 0) pyr_grid = g; }
         }
     } cfg;

@@ -561,23 +561,23 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_refine_q_kernel(const QBox
     if (nbuf) flush(nbuf);
 }
 
-// ---- 3a'. the same with TWO query children per lane ---------------------------------------------------------------------
+// ---- 3a'. the same with TWO (or four) query children per lane ---------------------------------------------------------------------
 // ncu has pyr_refine_q_kernel issue-bound (80 %) at 200 warp instructions per 256-test step, of which the tests are 58: the
 // rest is per-step overhead (entry / box fetch, staging, masks, append, loop). Here a lane owns the children 2i and 2i+1 of A,
 // a pair takes 4 lanes and a warp step covers 8 pairs = 512 tests: the target boxes read from shared memory serve two
 // queries and the per-step overhead serves twice the tests (the move that took the leaf-tile kernel from 1193 M to 955 M
 // instructions in round 1). Same pair lists as a set; the order inside a flush differs (the leaf tiles do not depend on it).
-template <int KIND>
+template <int KIND, int QPL>
 __global__ void __launch_bounds__(kPyrWarps * 32) pyr_refine_q2_kernel(const QBoxU* __restrict__ Uf, const QBoxT* __restrict__ Nf,
                                                                       uint32_t f_first, uint32_t f_nqg, uint32_t f_ntg,
                                                                       PairList in, PairList out, uint32_t* ticket) {
     constexpr int F = 1 << kPyrFan;          // 8
-    constexpr int QPL = 2;                   // query children per lane
-    constexpr int LPP = F / QPL;             // 4 lanes per pair
-    constexpr int SLOTS = 32 / LPP;          // 8 pairs per warp step
+    constexpr int LPP = F / QPL;             // lanes per pair: 4 (QPL = 2) or 2 (QPL = 4)
+    constexpr int SLOTS = 32 / LPP;          // pairs per warp step: 8 or 16
     constexpr int PIECES = F * (int)sizeof(QBoxT) / 16;                   // 6
+    constexpr int PPL = (PIECES + LPP - 1) / LPP;                         // 16-byte pieces of the target group a lane stages: 2 or 3
     constexpr int SLOT_BYTES = F * (int)sizeof(QBoxT) + 16;               // 112
-    static_assert(F == 8 && sizeof(QBoxT) == 12 && PIECES <= 2 * LPP, "piece mapping");
+    static_assert(F == 8 && sizeof(QBoxT) == 12 && (QPL == 2 || QPL == 4), "piece mapping");
     __shared__ __align__(16) unsigned char s_raw[kPyrWarps][SLOTS][SLOT_BYTES];
     __shared__ uint2 s_buf[kPyrWarps][32 * QPL * F + kPyrFlush];
     __shared__ uint32_t s_n[kPyrWarps];
@@ -597,26 +597,31 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_refine_q2_kernel(const QBo
         for (uint32_t k = lane; k < n; k += 32) if (base + k < out.cap) out.data[base + k] = s_buf[w][b0 + k];
         nbuf = b0;
     };
-    struct Stage { uint32_t Ac, Bc0, ok; uint4 u0, u1, tp0, tp1; };
+    struct Stage { uint32_t Ac, Bc0, ok; uint4 u[QPL]; uint4 tp[PPL]; };
     auto fetch = [&](uint2 pr, bool have) -> Stage {
         Stage sg;
-        sg.Ac = (pr.x << kPyrFan) + (uint32_t)(QPL * i);                   // my first child of A (the second is Ac + 1)
+        sg.Ac = (pr.x << kPyrFan) + (uint32_t)(QPL * i);                   // my first child of A (the others follow it)
         sg.Bc0 = pr.y << kPyrFan;
-        const uint32_t ua = sg.Ac - f_first;                               // wraps if Ac < f_first; ua + 1 wraps back to 0 when only the second child is inside
-        sg.ok = have ? ((ua < f_nqg ? 1u : 0u) | (ua + 1u < f_nqg ? 2u : 0u)) : 0u;
-        sg.u0 = __ldg(reinterpret_cast<const uint4*>(Uf + min(ua, f_nqg - 1u)));
-        sg.u1 = __ldg(reinterpret_cast<const uint4*>(Uf + min(ua + 1u, f_nqg - 1u)));
-        sg.tp0 = __ldg(reinterpret_cast<const uint4*>(Nf + sg.Bc0) + i);     // pieces 0..3 (the copy is padded to whole groups)
-        sg.tp1 = make_uint4(0u, 0u, 0u, 0u);
-        if (i + LPP < PIECES) sg.tp1 = __ldg(reinterpret_cast<const uint4*>(Nf + sg.Bc0) + i + LPP);   // pieces 4, 5
+        const uint32_t ua = sg.Ac - f_first;                               // wraps if Ac < f_first; ua + c wraps back when a later child is inside
+        sg.ok = 0u;
+#pragma unroll
+        for (int c = 0; c < QPL; ++c) {
+            if (have && ua + (uint32_t)c < f_nqg) sg.ok |= 1u << c;
+            sg.u[c] = __ldg(reinterpret_cast<const uint4*>(Uf + min(ua + (uint32_t)c, f_nqg - 1u)));
+        }
+#pragma unroll
+        for (int k = 0; k < PPL; ++k) {                                    // (the copy is padded to whole groups)
+            sg.tp[k] = make_uint4(0u, 0u, 0u, 0u);
+            if (i + k * LPP < PIECES) sg.tp[k] = __ldg(reinterpret_cast<const uint4*>(Nf + sg.Bc0) + i + k * LPP);
+        }
         return sg;
     };
     volatile uint32_t* s_nv = s_n;
     auto process = [&](const Stage& cur) {
-        reinterpret_cast<uint4*>(s_raw[w][slot])[i] = cur.tp0;
-        if (i + LPP < PIECES) reinterpret_cast<uint4*>(s_raw[w][slot])[i + LPP] = cur.tp1;
+#pragma unroll
+        for (int k = 0; k < PPL; ++k) if (i + k * LPP < PIECES) reinterpret_cast<uint4*>(s_raw[w][slot])[i + k * LPP] = cur.tp[k];
         __syncwarp();
-        uint32_t hits = 0;                                                 // bits [0, 8): targets hit by child 0, [8, 16): by child 1
+        uint32_t hits = 0;                                                 // bits [8c, 8c + 8): targets hit by child c
         if (cur.ok) {
             const uint4* sp = reinterpret_cast<const uint4*>(s_raw[w][slot]);
 #pragma unroll
@@ -625,24 +630,31 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_refine_q2_kernel(const QBo
                 const uint32_t bw[12] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const uint32_t r0 = (cur.u0.x - bw[3 * j]) & (cur.u0.y - bw[3 * j + 1]) & (cur.u0.z - bw[3 * j + 2]);
-                    const uint32_t r1 = (cur.u1.x - bw[3 * j]) & (cur.u1.y - bw[3 * j + 1]) & (cur.u1.z - bw[3 * j + 2]);
-                    if ((r0 & kQGuard) == kQGuard) hits |= 1u << (4 * q + j);
-                    if ((r1 & kQGuard) == kQGuard) hits |= 1u << (F + 4 * q + j);
+#pragma unroll
+                    for (int c = 0; c < QPL; ++c) {
+                        const uint32_t r = (cur.u[c].x - bw[3 * j]) & (cur.u[c].y - bw[3 * j + 1]) & (cur.u[c].z - bw[3 * j + 2]);
+                        if ((r & kQGuard) == kQGuard) hits |= 1u << (F * c + 4 * q + j);
+                    }
                 }
             }
-            uint32_t keep = ((cur.ok & 1u) ? 0xffu : 0u) | ((cur.ok & 2u) ? 0xff00u : 0u);
+            uint32_t keep = 0;
+#pragma unroll
+            for (int c = 0; c < QPL; ++c) if (cur.ok & (1u << c)) keep |= 0xffu << (F * c);
             bool edge = cur.Bc0 + (uint32_t)F > f_ntg;
-            if constexpr (KIND == kSingle) edge = edge || cur.Ac + 1u > cur.Bc0;
+            if constexpr (KIND == kSingle) edge = edge || cur.Ac + (uint32_t)(QPL - 1) > cur.Bc0;
             if (edge) {
                 const uint32_t nval = f_ntg - cur.Bc0;
                 const uint32_t inside = nval >= (uint32_t)F ? ((1u << F) - 1u) : ((1u << nval) - 1u);
-                uint32_t a0 = inside, a1 = inside;
-                if constexpr (KIND == kSingle) {                             // child j of B admissible for child c of A iff Bc0 + j >= Ac + c
-                    if (cur.Ac > cur.Bc0) { const uint32_t lo = cur.Ac - cur.Bc0; a0 &= lo >= (uint32_t)F ? 0u : ~((1u << lo) - 1u); }
-                    if (cur.Ac + 1u > cur.Bc0) { const uint32_t lo = cur.Ac + 1u - cur.Bc0; a1 &= lo >= (uint32_t)F ? 0u : ~((1u << lo) - 1u); }
+                uint32_t allowed = 0;
+#pragma unroll
+                for (int c = 0; c < QPL; ++c) {
+                    uint32_t a = inside;
+                    if constexpr (KIND == kSingle) {                         // child j of B admissible for child c of A iff Bc0 + j >= Ac + c
+                        if (cur.Ac + (uint32_t)c > cur.Bc0) { const uint32_t lo = cur.Ac + (uint32_t)c - cur.Bc0; a &= lo >= (uint32_t)F ? 0u : ~((1u << lo) - 1u); }
+                    }
+                    allowed |= a << (F * c);
                 }
-                keep &= a0 | (a1 << F);
+                keep &= allowed;
             }
             hits &= keep;
         }

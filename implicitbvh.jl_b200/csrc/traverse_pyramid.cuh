@@ -1244,57 +1244,81 @@ IBVH_D void fixup_bitonic(IndexPair<I>* seg, int64_t m, int tid, int nthreads, S
 }
 
 template <int KIND, class LQ, class LT, class I>
-__global__ void __launch_bounds__(256) pyr_fixup_kernel(const LQ* __restrict__ qleaves, const LT* __restrict__ tleaves, int64_t q_begin,
+__global__ void __launch_bounds__(256) pyr_fixup_kernel(const LQ* __restrict__ qleaves, const I* __restrict__ qidx_arr, int64_t q_begin,
                                                        int64_t q_count, int flip, const I* __restrict__ counts, IndexPair<I>* contacts,
                                                        uint32_t* long_lists, uint32_t* long_counts, uint32_t long_cap) {
-    const int64_t qi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (qi >= q_count) return;
-    const int64_t b = qi == 0 ? 0 : (int64_t)counts[qi - 1];
-    const int64_t e = (int64_t)counts[qi];
-    if (e <= b) return;
-    const bool positions = (flip & 2) != 0;
-    flip &= 1;
-    const I qidx = positions ? (I)(q_begin + qi + 1) : (I)qleaves[q_begin + qi].index;
-    auto report = [&](I li) -> IndexPair<I> {
-        I ea, eb;
-        if constexpr (KIND == kSingle) { if (qidx > li) { ea = li; eb = qidx; } else { ea = qidx; eb = li; } }
-        else { if (flip) { ea = li; eb = qidx; } else { ea = qidx; eb = li; } }
-        return IndexPair<I>{ea, eb};
-    };
-    // entries are (target index, target position): sort by position — in registers for the usual handful of hits
-    constexpr int kReg = 8;
-    const int64_t m = e - b;
-    if (m <= kReg) {
-        IndexPair<I> v[kReg];
+    // A block owns 256 consecutive queries, whose segments are ONE contiguous range of the list: the range travels
+    // global -> shared -> global with coalesced accesses and every thread sorts its segment in shared memory (round 2 had
+    // each thread read and write its own 8-byte entries in global memory: 0.51 ms for 2 x 318 MB at 10 M leaves). A range
+    // that does not fit (a dense cluster) is sorted in place in global memory as before.
+    constexpr int CAP = 24576 / (int)sizeof(IndexPair<I>);
+    __shared__ IndexPair<I> s_seg[CAP];
+    const int64_t q0 = (int64_t)blockIdx.x * blockDim.x;
+    const int64_t qlast = (q0 + blockDim.x < q_count ? q0 + blockDim.x : q_count) - 1;
+    const int64_t B = q0 == 0 ? 0 : (int64_t)counts[q0 - 1];
+    const int64_t M = (int64_t)counts[qlast] - B;
+    const bool staged = M <= CAP;                                        // block-uniform
+    if (staged) {
+        for (int64_t k = threadIdx.x; k < M; k += blockDim.x) s_seg[k] = contacts[B + k];
+        __syncthreads();
+    }
+    const int64_t qi = q0 + threadIdx.x;
+    const int64_t b = qi >= q_count ? 0 : (qi == 0 ? 0 : (int64_t)counts[qi - 1]);
+    const int64_t e = qi >= q_count ? 0 : (int64_t)counts[qi];
+    if (e > b) {
+        const bool positions = (flip & 2) != 0;
+        const int f = flip & 1;
+        const I qidx = positions ? (I)(q_begin + qi + 1) : (qidx_arr ? __ldg(qidx_arr + q_begin + qi) : (I)qleaves[q_begin + qi].index);
+        auto report = [&](I li) -> IndexPair<I> {
+            I ea, eb;
+            if constexpr (KIND == kSingle) { if (qidx > li) { ea = li; eb = qidx; } else { ea = qidx; eb = li; } }
+            else { if (f) { ea = li; eb = qidx; } else { ea = qidx; eb = li; } }
+            return IndexPair<I>{ea, eb};
+        };
+        IndexPair<I>* seg = staged ? s_seg + (b - B) : contacts + b;
+        // entries are (target index, target position): sort by position — in registers for the usual handful of hits
+        constexpr int kReg = 8;
+        const int64_t m = e - b;
+        bool queued = false;
+        if (m <= kReg) {
+            IndexPair<I> v[kReg];
 #pragma unroll
-        for (int x = 0; x < kReg; ++x) v[x] = x < m ? contacts[b + x] : IndexPair<I>{I(0), I(0)};
+            for (int x = 0; x < kReg; ++x) v[x] = x < m ? seg[x] : IndexPair<I>{I(0), I(0)};
 #pragma unroll
-        for (int x = 1; x < kReg; ++x) {
+            for (int x = 1; x < kReg; ++x) {
 #pragma unroll
-            for (int y = x; y > 0; --y) {
-                const bool sw = y < m && v[y - 1].b > v[y].b;       // slots >= m never move
-                const IndexPair<I> lo = sw ? v[y] : v[y - 1], hi = sw ? v[y - 1] : v[y];
-                v[y - 1] = lo; v[y] = hi;
+                for (int y = x; y > 0; --y) {
+                    const bool sw = y < m && v[y - 1].b > v[y].b;       // slots >= m never move
+                    const IndexPair<I> lo = sw ? v[y] : v[y - 1], hi = sw ? v[y - 1] : v[y];
+                    v[y - 1] = lo; v[y] = hi;
+                }
+            }
+#pragma unroll
+            for (int x = 0; x < kReg; ++x) if (x < m) seg[x] = report(v[x].a);
+        } else {
+            if (m > kFixupInsertion) {
+                // long segment: queue it for the cooperative kernels that follow (list 0: one warp each, list 1: one block each);
+                // they work on global memory, where a staged block writes the segment back unchanged
+                const int which = m > kFixupWarp ? 1 : 0;
+                const uint32_t slot = atomicAdd(&long_counts[which], 1u);
+                if (slot < long_cap) { long_lists[(size_t)which * long_cap + slot] = (uint32_t)qi; queued = true; }
+                // (slot >= long_cap cannot happen: long_cap covers every possible long segment; the insertion sort below would do)
+            }
+            if (!queued) {
+                for (int64_t x = 1; x < m; ++x) {
+                    const IndexPair<I> v = seg[x];
+                    int64_t y = x - 1;
+                    while (y >= 0 && seg[y].b > v.b) { seg[y + 1] = seg[y]; --y; }
+                    seg[y + 1] = v;
+                }
+                for (int64_t x = 0; x < m; ++x) seg[x] = report(seg[x].a);
             }
         }
-#pragma unroll
-        for (int x = 0; x < kReg; ++x) if (x < m) contacts[b + x] = report(v[x].a);
-        return;
     }
-    if (m > kFixupInsertion) {
-        // long segment: queue it for the cooperative kernel (list 0: one warp each, list 1: one block each)
-        const int which = m > kFixupWarp ? 1 : 0;
-        const uint32_t slot = atomicAdd(&long_counts[which], 1u);
-        if (slot < long_cap) { long_lists[(size_t)which * long_cap + slot] = (uint32_t)qi; return; }
-        // (cannot happen: long_cap covers every possible long segment; fall through to the insertion sort if it did)
+    if (staged) {
+        __syncthreads();
+        for (int64_t k = threadIdx.x; k < M; k += blockDim.x) contacts[B + k] = s_seg[k];
     }
-    for (int64_t x = b + 1; x < e; ++x) {
-        IndexPair<I> v = contacts[x];
-        int64_t y = x - 1;
-        while (y >= b && contacts[y].b > v.b) { contacts[y + 1] = contacts[y]; --y; }
-        contacts[y + 1] = v;
-    }
-    for (int64_t x = b; x < e; ++x) contacts[x] = report(contacts[x].a);
 }
 
 // long segments: bitonic sort in place by target position, then the reported pairs. WARP_EACH: one warp per listed

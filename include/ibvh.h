@@ -284,7 +284,9 @@ IBVH_API int ibvh_traverse_rays(ibvh_handle_t* h, const ibvh_bvh_t* bvh, const v
  * the sum of the BVTT list lengths over the levels (traverse_single.jl:28,51), which is deterministic.
  * Output protocol: d_contacts == NULL counts only; more contacts than `capacity` -> IBVH_ERR_CAPACITY with the need in
  * *num_contacts. Either way the library keeps the leaf-level list: repeating the SAME call with a large enough buffer and
- * IBVH_TRAVERSE_COUNTS_VALID only redoes the leaf level. Other flags honoured: IBVH_TRAVERSE_POSITIONS.
+ * IBVH_TRAVERSE_COUNTS_VALID only redoes the leaf level (the repeat must be the next BFS call on the handle, with the trees
+ * untouched in between; anything else — other arguments, no kept list — simply runs the whole traversal again). Other flags
+ * honoured: IBVH_TRAVERSE_POSITIONS.
  * One host read-back per level (the reference reads dst_offsets[level] the same way). */
 /* default_start_level(bvh, ::BFSTraversal) = max(levels / 2, built_level), breadth_first/breadth_first.jl:4-6 */
 IBVH_API int64_t ibvh_bfs_default_start_level(int64_t levels, int64_t built_level);

@@ -83,6 +83,62 @@ IBVH_D uint32_t pyr_chunk_steps(uint32_t count, int slots) {
     return s < 1u ? 1u : (s > (uint32_t)IBVH_PYR_CHUNK_MAX ? (uint32_t)IBVH_PYR_CHUNK_MAX : s);
 }
 
+// The pair lists (475 MB at the last refinement level) and the contact list (318 MB) are written once and read once or
+// never by the GPU, while the 160 MB of leaf records and the node levels are re-read many times and almost fit the 126 MB L2:
+// IBVH_STREAM_HINTS marks the list traffic evict-first (ld.global.cs / st.global.cs) so that it does not push them out
+// (A/B of two builds in one gpurun call, twice each: tile 1.133 -> 1.116 ms, refine 0.677 -> 0.673, step 2.651 -> 2.632 ms).
+#ifndef IBVH_STREAM_HINTS
+#define IBVH_STREAM_HINTS 1
+#endif
+IBVH_D uint2 pyr_stream_load(const uint2* p) {
+#if IBVH_STREAM_HINTS
+    return __ldcs(p);
+#else
+    return *p;
+#endif
+}
+IBVH_D void pyr_stream_store(uint2* p, uint2 v) {
+#if IBVH_STREAM_HINTS
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
+template <class I> IBVH_D void pyr_stream_store(IndexPair<I>* p, const IndexPair<I>& v) {
+#if IBVH_STREAM_HINTS
+    if constexpr (sizeof(I) == 4) __stcs(reinterpret_cast<uint2*>(p), make_uint2((uint32_t)v.a, (uint32_t)v.b));
+    else __stcs(reinterpret_cast<ulonglong2*>(p), make_ulonglong2((unsigned long long)v.a, (unsigned long long)v.b));
+#else
+    *p = v;
+#endif
+}
+// EXPERIMENT -DIBVH_L2_KEEP=<percent>: the leaf records of the tile kernel are fetched with an L2 evict-last policy for that
+// fraction of the accesses (createpolicy.fractional + ld / cp.async ... L2::cache_hint).
+#ifndef IBVH_L2_KEEP
+#define IBVH_L2_KEEP 0
+#endif
+IBVH_D unsigned long long pyr_keep_policy() {
+    unsigned long long pol = 0;
+#if IBVH_L2_KEEP > 0
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, %1;" : "=l"(pol) : "f"((float)IBVH_L2_KEEP / 100.0f));
+#endif
+    return pol;
+}
+template <class R> IBVH_D R load16_keep(const R* p, unsigned long long pol) {
+#if IBVH_L2_KEEP > 0
+    static_assert(sizeof(R) % 16 == 0, "16-byte records");
+    alignas(16) R out;
+    uint4* d = reinterpret_cast<uint4*>(&out);
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(R) / 16); ++k)
+        asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(d[k].x), "=r"(d[k].y), "=r"(d[k].z), "=r"(d[k].w)
+                     : "l"(reinterpret_cast<const uint4*>(p) + k), "l"(pol));
+    return out;
+#else
+    (void)pol;
+    return load16(p);
+#endif
+}
 IBVH_D void atomic_inc(int32_t* p) { atomicAdd(p, 1); }
 IBVH_D void atomic_inc(int64_t* p) { atomicAdd(reinterpret_cast<unsigned long long*>(p), 1ull); }
 
@@ -274,7 +330,7 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_refine_kernel(const UBox<T
         if (lane == 0) base = atomicAdd(out.count, (unsigned long long)n);
         base = __shfl_sync(0xffffffffu, base, 0);
         const uint32_t b0 = nbuf - n;
-        for (uint32_t k = lane; k < n; k += 32) if (base + k < out.cap) out.data[base + k] = s_buf[w][b0 + k];
+        for (uint32_t k = lane; k < n; k += 32) if (base + k < out.cap) pyr_stream_store(out.data + base + k, s_buf[w][b0 + k]);
         nbuf = b0;
     };
     // Software pipeline: while step t is computed, the boxes of step t+1 and the list entry of step t+2 are in flight
@@ -364,11 +420,11 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_refine_kernel(const UBox<T
         const uint32_t end = count - base > chunk ? base + chunk : count;
         uint32_t p = base + slot;
         uint2 e1 = make_uint2(0u, 0u), e2 = make_uint2(0u, 0u);
-        if (p < end) e1 = in.data[p];
-        if (p + SLOTS < end) e2 = in.data[p + SLOTS];
+        if (p < end) e1 = pyr_stream_load(in.data + p);
+        if (p + SLOTS < end) e2 = pyr_stream_load(in.data + p + SLOTS);
         auto next_entry = [&]() {                                          // entry of the step after the next
             uint2 e = make_uint2(0u, 0u);
-            if (p + 2 * SLOTS < end) e = in.data[p + 2 * SLOTS];
+            if (p + 2 * SLOTS < end) e = pyr_stream_load(in.data + p + 2 * SLOTS);
             return e;
         };
         Stage sa = fetch(e1, p < end), sb;
@@ -468,7 +524,7 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_refine_q_kernel(const QBox
         if (lane == 0) base = atomicAdd(out.count, (unsigned long long)n);
         base = __shfl_sync(0xffffffffu, base, 0);
         const uint32_t b0 = nbuf - n;
-        for (uint32_t k = lane; k < n; k += 32) if (base + k < out.cap) out.data[base + k] = s_buf[w][b0 + k];
+        for (uint32_t k = lane; k < n; k += 32) if (base + k < out.cap) pyr_stream_store(out.data + base + k, s_buf[w][b0 + k]);
         nbuf = b0;
     };
     struct Stage { uint32_t Ac, Bc0; bool a_ok; uint4 u; uint4 tp; };
@@ -538,11 +594,11 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_refine_q_kernel(const QBox
         const uint32_t end = count - base > chunk ? base + chunk : count;
         uint32_t p = base + slot;
         uint2 e1 = make_uint2(0u, 0u), e2 = make_uint2(0u, 0u);
-        if (p < end) e1 = in.data[p];
-        if (p + SLOTS < end) e2 = in.data[p + SLOTS];
+        if (p < end) e1 = pyr_stream_load(in.data + p);
+        if (p + SLOTS < end) e2 = pyr_stream_load(in.data + p + SLOTS);
         auto next_entry = [&]() {
             uint2 e = make_uint2(0u, 0u);
-            if (p + 2 * SLOTS < end) e = in.data[p + 2 * SLOTS];
+            if (p + 2 * SLOTS < end) e = pyr_stream_load(in.data + p + 2 * SLOTS);
             return e;
         };
         Stage sa = fetch(e1, p < end), sb;
@@ -594,7 +650,7 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_refine_q2_kernel(const QBo
         if (lane == 0) base = atomicAdd(out.count, (unsigned long long)n);
         base = __shfl_sync(0xffffffffu, base, 0);
         const uint32_t b0 = nbuf - n;
-        for (uint32_t k = lane; k < n; k += 32) if (base + k < out.cap) out.data[base + k] = s_buf[w][b0 + k];
+        for (uint32_t k = lane; k < n; k += 32) if (base + k < out.cap) pyr_stream_store(out.data + base + k, s_buf[w][b0 + k]);
         nbuf = b0;
     };
     struct Stage { uint32_t Ac, Bc0, ok; uint4 u[QPL]; uint4 tp[PPL]; };
@@ -682,11 +738,11 @@ __global__ void __launch_bounds__(kPyrWarps * 32) pyr_refine_q2_kernel(const QBo
         const uint32_t end = count - base > chunk ? base + chunk : count;
         uint32_t p = base + slot;
         uint2 e1 = make_uint2(0u, 0u), e2 = make_uint2(0u, 0u);
-        if (p < end) e1 = in.data[p];
-        if (p + SLOTS < end) e2 = in.data[p + SLOTS];
+        if (p < end) e1 = pyr_stream_load(in.data + p);
+        if (p + SLOTS < end) e2 = pyr_stream_load(in.data + p + SLOTS);
         auto next_entry = [&]() {
             uint2 e = make_uint2(0u, 0u);
-            if (p + 2 * SLOTS < end) e = in.data[p + 2 * SLOTS];
+            if (p + 2 * SLOTS < end) e = pyr_stream_load(in.data + p + 2 * SLOTS);
             return e;
         };
         Stage sa = fetch(e1, p < end), sb;
@@ -744,7 +800,7 @@ __global__ void __launch_bounds__(kPyrWarps * 32, 8) pyr_refine_tma_kernel(const
         if (lane == 0) base = atomicAdd(out.count, (unsigned long long)n);
         base = __shfl_sync(0xffffffffu, base, 0);
         const uint32_t b0 = nbuf - n;
-        for (uint32_t k = lane; k < n; k += 32) if (base + k < out.cap) out.data[base + k] = s_buf[w][b0 + k];
+        for (uint32_t k = lane; k < n; k += 32) if (base + k < out.cap) pyr_stream_store(out.data + base + k, s_buf[w][b0 + k]);
         nbuf = b0;
     };
     struct Stage { uint32_t Ac, Bc0; bool a_ok; };
@@ -834,11 +890,11 @@ __global__ void __launch_bounds__(kPyrWarps * 32, 8) pyr_refine_tma_kernel(const
         const uint32_t end = count - base > chunk ? base + chunk : count;
         uint32_t p = base + slot;
         uint2 e1 = make_uint2(0u, 0u), e2 = make_uint2(0u, 0u);
-        if (p < end) e1 = in.data[p];
-        if (p + SLOTS < end) e2 = in.data[p + SLOTS];
+        if (p < end) e1 = pyr_stream_load(in.data + p);
+        if (p + SLOTS < end) e2 = pyr_stream_load(in.data + p + SLOTS);
         auto next_entry = [&]() {
             uint2 e = make_uint2(0u, 0u);
-            if (p + 2 * SLOTS < end) e = in.data[p + 2 * SLOTS];
+            if (p + 2 * SLOTS < end) e = pyr_stream_load(in.data + p + 2 * SLOTS);
             return e;
         };
         Stage sa = fetch(e1, p < end, 0), sb;
@@ -971,7 +1027,14 @@ __global__ void __launch_bounds__(kPyrWarps * 32, pyr_tile_minb<LQ>()) pyr_leaf_
                 for (uint32_t k = lane; k < kept; k += 32) {
                     const uint2 e = s_buf[w][b0 + k];
                     const unsigned long long li = positions ? (unsigned long long)(e.y + 1u) : (unsigned long long)(long long)t_index(e.y);
-                    if ((int64_t)(base + k) < capacity) stash[base + k] = make_uint4(e.x - qb32, e.y, (uint32_t)li, (uint32_t)(li >> 32));
+                    if ((int64_t)(base + k) < capacity) {
+                        const uint4 sv = make_uint4(e.x - qb32, e.y, (uint32_t)li, (uint32_t)(li >> 32));
+#if IBVH_STREAM_HINTS
+                        __stcs(stash + base + k, sv);
+#else
+                        stash[base + k] = sv;
+#endif
+                    }
                 }
             }
         }
@@ -1008,7 +1071,7 @@ __global__ void __launch_bounds__(kPyrWarps * 32, pyr_tile_minb<LQ>()) pyr_leaf_
                         const unsigned long long wp = base + k;
                         if ((int64_t)wp < capacity) {
                             if (fused) multimem_store_pair(contacts + wp, pr);
-                            else contacts[wp] = pr;
+                            else pyr_stream_store(contacts + wp, pr);
                         }
                     }
                 }
@@ -1032,6 +1095,8 @@ __global__ void __launch_bounds__(kPyrWarps * 32, pyr_tile_minb<LQ>()) pyr_leaf_
         else return (k * 32 + lane) % TPIECES;
     };
     const uint32_t vraw_base = (uint32_t)__cvta_generic_to_shared(s_vraw[w][0][0]);
+    const unsigned long long keep_pol = pyr_keep_policy();
+    (void)keep_pol;
     struct Stage { uint32_t qpos0, j0, have; Packed<VQ> q[QPL]; };
     auto fetch = [&](uint2 pr, bool have, int buf) -> Stage {
         Stage sg;
@@ -1054,7 +1119,7 @@ __global__ void __launch_bounds__(kPyrWarps * 32, pyr_tile_minb<LQ>()) pyr_leaf_
             return sg;
         }
 #pragma unroll
-        for (int k = 0; k < QPL; ++k) sg.q[k] = load16(pq + sg.qpos0 + (uint32_t)(QPL * i + k));
+        for (int k = 0; k < QPL; ++k) sg.q[k] = load16_keep(pq + sg.qpos0 + (uint32_t)(QPL * i + k), keep_pol);
         // Target copy global -> shared, 16 bytes per lane and instruction. The copy mapping is NOT the compute mapping:
         // for 16-byte volumes one instruction moves 8 whole slots, lanes 4c .. 4c+3 of a quarter-warp writing the
         // 64 bytes of slot a and the next four lanes those of slot a + 4 — with the 80-byte slot stride these are
@@ -1066,7 +1131,11 @@ __global__ void __launch_bounds__(kPyrWarps * 32, pyr_tile_minb<LQ>()) pyr_leaf_
             const uint32_t tj0 = __shfl_sync(0xffffffffu, sg.j0, cslot * LPP);
             const uint4* src = reinterpret_cast<const uint4*>(pt + tj0) + copy_piece(k);
             const uint32_t dst = vraw_base + (uint32_t)(buf * SLOTS * SLOT_BYTES + cslot * SLOT_BYTES + 16 * copy_piece(k));
+#if IBVH_L2_KEEP > 0
+            asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "l"(keep_pol) : "memory");
+#else
             asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+#endif
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
         return sg;
@@ -1159,11 +1228,11 @@ __global__ void __launch_bounds__(kPyrWarps * 32, pyr_tile_minb<LQ>()) pyr_leaf_
         if (base + 16u * lane < end) asm volatile("prefetch.global.L1 [%0];" ::"l"(in.data + base + 16u * lane));
         uint32_t p = base + slot;
         uint2 e1 = make_uint2(0u, 0u), e2 = make_uint2(0u, 0u);
-        if (p < end) e1 = in.data[p];
-        if (p + SLOTS < end) e2 = in.data[p + SLOTS];
+        if (p < end) e1 = pyr_stream_load(in.data + p);
+        if (p + SLOTS < end) e2 = pyr_stream_load(in.data + p + SLOTS);
         auto next_entry = [&]() {
             uint2 e = make_uint2(0u, 0u);
-            if (p + 2 * SLOTS < end) e = in.data[p + 2 * SLOTS];
+            if (p + 2 * SLOTS < end) e = pyr_stream_load(in.data + p + 2 * SLOTS);
             return e;
         };
         // optional (-DIBVH_PYR_AHEAD=k): volumes of the step k steps away towards L2. Measured: no gain at k = 4 or 8
@@ -1171,7 +1240,7 @@ __global__ void __launch_bounds__(kPyrWarps * 32, pyr_tile_minb<LQ>()) pyr_leaf_
         constexpr uint32_t kAhead = IBVH_PYR_AHEAD;
         auto l2_ahead = [&]() {
             if (kAhead && i == 0 && p + kAhead * SLOTS < end) {
-                const uint2 e = in.data[p + kAhead * SLOTS];
+                const uint2 e = pyr_stream_load(in.data + p + kAhead * SLOTS);
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(pq + (e.x << kPyrLeafLog)));
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(pt + (e.y << kPyrLeafLog)));
             }
@@ -1206,7 +1275,11 @@ __global__ void __launch_bounds__(256) pyr_scatter_kernel(const uint4* __restric
     if ((long long)n > cap) n = (unsigned long long)cap;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+#if IBVH_STREAM_HINTS
+        const uint4 e = __ldcs(stash + i);
+#else
         const uint4 e = stash[i];
+#endif
         const int64_t seg = e.x == 0 ? 0 : (int64_t)counts[e.x - 1];
         const unsigned int rr = atomicAdd(&cursors[e.x], 1u);
         const long long li = (long long)((unsigned long long)e.z | ((unsigned long long)e.w << 32));

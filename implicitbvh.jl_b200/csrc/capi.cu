@@ -834,7 +834,8 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
     // the hits, then scan + scatter into the query segments (instead of a count pass and a write pass of the tile kernel)
     const bool stash_mode = !unordered && !count_only && capacity > 0 && !((flags & IBVH_TRAVERSE_COUNTS_VALID) && d_counts);
     const int nl = plan.n;
-    const int grid = h->sm_count * h->cfg.pyr_grid;
+    const int grid = h->sm_count * h->cfg.pyr_grid;               // leaf-tile kernel
+    const int grid_refine = h->sm_count * h->cfg.pyr_grid_refine;   // refine kernels
     const int pflip = (ta.flip ? 1 : 0) | (ta.positions ? 2 : 0);      // bit 1: report leaf positions (IBVH_TRAVERSE_POSITIONS)
     // The 16-byte hit stash of the one-pass ordered protocol is sized from what the traversals on this handle actually
     // produced (last total + 25 %, or 6 hits per query before the first one), never from the caller's `capacity`: a
@@ -1015,15 +1016,15 @@ int traverse_pyramid(ibvh_handle* h, const LQ* qleaves, int64_t n_query_total, c
         for (int l = nl - 1; l >= 1; --l) {
             { ProfScope _ps(h, st, "pyr_refine_kernel");
             if (quant && h->cfg.pyr_q2 == 4)
-                pyr_refine_q2_kernel<KIND, 4><<<grid, kPyrWarps * 32, 0, st>>>(Uq + plan.lv[l - 1].u_off, NTq + plan.lv[l - 1].t_off, (uint32_t)plan.lv[l - 1].qg_first, (uint32_t)plan.lv[l - 1].nqg, (uint32_t)plan.lv[l - 1].ntg, lists[l], lists[l - 1], d_tick + l);
+                pyr_refine_q2_kernel<KIND, 4><<<grid_refine, kPyrWarps * 32, 0, st>>>(Uq + plan.lv[l - 1].u_off, NTq + plan.lv[l - 1].t_off, (uint32_t)plan.lv[l - 1].qg_first, (uint32_t)plan.lv[l - 1].nqg, (uint32_t)plan.lv[l - 1].ntg, lists[l], lists[l - 1], d_tick + l);
             else if (quant && h->cfg.pyr_q2)
-                pyr_refine_q2_kernel<KIND, 2><<<grid, kPyrWarps * 32, 0, st>>>(Uq + plan.lv[l - 1].u_off, NTq + plan.lv[l - 1].t_off, (uint32_t)plan.lv[l - 1].qg_first, (uint32_t)plan.lv[l - 1].nqg, (uint32_t)plan.lv[l - 1].ntg, lists[l], lists[l - 1], d_tick + l);
+                pyr_refine_q2_kernel<KIND, 2><<<grid_refine, kPyrWarps * 32, 0, st>>>(Uq + plan.lv[l - 1].u_off, NTq + plan.lv[l - 1].t_off, (uint32_t)plan.lv[l - 1].qg_first, (uint32_t)plan.lv[l - 1].nqg, (uint32_t)plan.lv[l - 1].ntg, lists[l], lists[l - 1], d_tick + l);
             else if (quant)
-                pyr_refine_q_kernel<KIND><<<grid, kPyrWarps * 32, 0, st>>>(Uq + plan.lv[l - 1].u_off, NTq + plan.lv[l - 1].t_off, (uint32_t)plan.lv[l - 1].qg_first, (uint32_t)plan.lv[l - 1].nqg, (uint32_t)plan.lv[l - 1].ntg, lists[l], lists[l - 1], d_tick + l);
+                pyr_refine_q_kernel<KIND><<<grid_refine, kPyrWarps * 32, 0, st>>>(Uq + plan.lv[l - 1].u_off, NTq + plan.lv[l - 1].t_off, (uint32_t)plan.lv[l - 1].qg_first, (uint32_t)plan.lv[l - 1].nqg, (uint32_t)plan.lv[l - 1].ntg, lists[l], lists[l - 1], d_tick + l);
             else if (h->cfg.pyr_tma)
-                pyr_refine_tma_kernel<KIND, T><<<grid, kPyrWarps * 32, 0, st>>>(Ulev[l - 1], NTlev[l - 1], (uint32_t)plan.lv[l - 1].qg_first, (uint32_t)plan.lv[l - 1].nqg, (uint32_t)plan.lv[l - 1].ntg, lists[l], lists[l - 1], d_tick + l);
+                pyr_refine_tma_kernel<KIND, T><<<grid_refine, kPyrWarps * 32, 0, st>>>(Ulev[l - 1], NTlev[l - 1], (uint32_t)plan.lv[l - 1].qg_first, (uint32_t)plan.lv[l - 1].nqg, (uint32_t)plan.lv[l - 1].ntg, lists[l], lists[l - 1], d_tick + l);
             else
-                pyr_refine_kernel<KIND, T><<<grid, kPyrWarps * 32, 0, st>>>(Ulev[l - 1], NTlev[l - 1], (uint32_t)plan.lv[l - 1].qg_first, (uint32_t)plan.lv[l - 1].nqg, (uint32_t)plan.lv[l - 1].ntg, lists[l], lists[l - 1], d_tick + l);
+                pyr_refine_kernel<KIND, T><<<grid_refine, kPyrWarps * 32, 0, st>>>(Ulev[l - 1], NTlev[l - 1], (uint32_t)plan.lv[l - 1].qg_first, (uint32_t)plan.lv[l - 1].nqg, (uint32_t)plan.lv[l - 1].ntg, lists[l], lists[l - 1], d_tick + l);
             }
             IBVH_LAUNCH_CHECK(h, "pyr_refine_kernel");
         }

@@ -24,7 +24,10 @@ struct ibvh_handle {
         bool peer_no_multicast = false;       // IBVH_PEER_NO_MULTICAST: plain peer stores instead of multimem.st
         bool force_wide_lookback = false;     // IBVH_SORT_WIDE_LOOKBACK: 64-bit look-back words at any size (tests the n >= 2^30 path)
         bool no_sidecar = false;              // IBVH_NO_SIDECAR: the build does not keep the traversal's packed records
-        int pyr_grid = 20;                    // IBVH_PYR_GRID: CTAs per SM of the refine / tile kernels
+        int pyr_grid = 40;                    // IBVH_PYR_GRID: CTAs launched per SM by the leaf-tile kernel (8 resident; they draw chunks from a ticket counter)
+        int pyr_grid_refine = 8;              // IBVH_PYR_GRID_REFINE: ... by the refine kernels (7 resident). Swept at 10 M leaves with the final kernels
+                                              // (gpurun_out/r2aq): CTAs per SM 8 / 12 / 16 / 20 / 28 / 40 -> refine 0.659 / 0.664 / 0.670 / 0.675 / 0.694 /
+                                              // 0.769 ms, leaf tiles 1.133 / 1.128 / 1.128 / 1.126 / 1.122 / 1.118 ms (both were 20 before)
         bool pyr_quant = true;                // IBVH_PYR_QUANT=0: refine over the float boxes instead of the conservatively quantised ones
         int pyr_q2 = 2;                       // IBVH_PYR_Q2: query children per lane of the quantised refine kernel: 2 (default), 4, or 0 = the one-child form
         bool pyr_tma = false;                 // IBVH_PYR_TMA=1: refine kernel with TMA bulk copies + mbarrier instead of LDG -> STS (measured slower: see traverse_pyramid.cuh)
@@ -43,6 +46,7 @@ struct ibvh_handle {
             if (const char* v = getenv("IBVH_PYR_QUANT")) pyr_quant = !(v[0] == '0' && v[1] == '\0');
             if (const char* v = getenv("IBVH_PYR_Q2")) { int g = atoi(v); pyr_q2 = (g == 4) ? 4 : (g == 0 ? 0 : 2); }
             if (const char* v = getenv("IBVH_PYR_GRID")) { int g = atoi(v); if (g > 0) pyr_grid = g; }
+            if (const char* v = getenv("IBVH_PYR_GRID_REFINE")) { int g = atoi(v); if (g > 0) pyr_grid_refine = g; }
         }
     } cfg;
 

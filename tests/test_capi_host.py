@@ -128,6 +128,23 @@ def test_no_cpu_fallback(ib):
     assert ib.capi.lib().ibvh_create(C.byref(out), 0) == ib.capi.ERR_CUDA
 
 
+def test_bfs_default_start_level_and_null_arguments(ib, O):
+    """default_start_level(bvh, ::BFSTraversal) = max(levels / 2, built_level) (breadth_first/breadth_first.jl:4-6), host-only;
+    the BFS / sort entry points reject null handles and arguments with a status, not a crash."""
+    lib = ib.capi.lib()
+    for n in (1, 2, 5, 11, 1000, 10_000_000, 100_000_000):
+        levels = ib.ImplicitTree(n).levels
+        for built in (1, 2, levels // 2, levels):
+            want = max(levels // 2, built)
+            assert lib.ibvh_bfs_default_start_level(levels, built) == want
+            assert O.bfs_default_start_level(n, built) == want
+    total, checks = C.c_int64(7), C.c_int64(7)
+    assert lib.ibvh_traverse_bfs_single(None, None, None, None, 0, C.byref(total), C.byref(checks), None) == ib.capi.ERR_ARGUMENT
+    assert lib.ibvh_traverse_bfs_pair(None, None, None, 1, 1, 0, None, 0, C.byref(total), C.byref(checks), None) == ib.capi.ERR_ARGUMENT
+    assert lib.ibvh_traverse_bfs_rays(None, None, None, None, 0, None, None, 0, C.byref(total), C.byref(checks), None) == ib.capi.ERR_ARGUMENT
+    assert lib.ibvh_sort_contacts(None, None, 0, 4, 0, None, None) == ib.capi.ERR_ARGUMENT
+
+
 def test_product_never_imports_oracle():
     pkg = os.path.join(ROOT, "implicitbvh.jl_b200")
     for dirpath, _, files in os.walk(pkg):

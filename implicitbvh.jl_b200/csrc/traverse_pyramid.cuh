@@ -15,21 +15,25 @@
 //      bound by the LSU data pipe, and AoS structs read as 8-byte pieces cost 3-7x the wavefronts.
 //   1. query pyramid: exact union boxes of the query leaves at group sizes 4, 32, 256, ... (min / max).
 //   2. top: all pairs (query group, tree node) at the coarsest size (<= 2048 groups per side).
-//   3. refine x (levels): each surviving pair (A, B) expands to its 8 x 8 child pairs; a warp handles 4
-//      pairs per step, lane = (pair slot, child of A); the 8 child boxes of B are fetched cooperatively as
-//      aligned 16-byte pieces into shared memory and read back as LDS.128 broadcasts; predicate-chained test.
+//   3. refine x (levels): each surviving pair (A, B) expands to its 8 x 8 child pairs over conservatively
+//      quantised 15-bit boxes (a test = three integer subtractions); a warp handles 8 pairs per step, a lane
+//      owns TWO children of A; the 8 child boxes of B are fetched cooperatively as aligned 16-byte pieces into
+//      shared memory and read back as LDS.128 broadcasts (pyr_refine_q2_kernel; the float and one-child
+//      forms are kept for A/B and for trees the quantisation does not cover).
 //   4. leaf tiles: pairs of 4-leaf groups, 16 pairs per warp step, a lane owns TWO query leaves (register
 //      tile 2 x 4), targets travel global -> shared with cp.async (double buffer, conflict-free mapping),
-//      lazy leaf-parent test on a hit.
+//      the sphere tests run on the packed FP32 pipe (FADD2 / FMUL2: traverse_tile.cuh), lazy leaf-parent
+//      test on a hit. Pair lists, contact list and hit stash are read / written with evict-first hints.
 // Work distribution: warps draw chunks of consecutive list entries from a ticket counter, so the spatial
 // order of the top-level list survives from level to level. Survivors are appended to flat (A, B) lists
 // through a per-warp shared-memory buffer (one shared atomic per lane with hits) that is flushed with one
 // global atomic per >= 256 entries and coalesced stores. List sizes stay on the device (the next phase reads
 // the count), so the whole traversal needs a single host synchronisation: the read-back of the contact
 // total, as in the reference — or none at all in the deferred form (IBVH_TRAVERSE_DEFER).
-// Output modes of the leaf-tile kernel: unordered append; fused multi-GPU append (slots from rank 0's
-// counter, multimem.st into every rank's list); ordered = count per query + stash, then scan, scatter and a
-// per-query register sort (pyr_scatter_kernel, pyr_fixup_kernel).
+// Output modes of the leaf-tile kernel: unordered append; fused multi-GPU append (slots inside this rank's
+// region of the gathered list from a LOCAL counter, multimem.st into every rank's list); ordered = count per
+// query + stash, then scan, scatter and a per-query sort staged through shared memory (pyr_scatter_kernel,
+// pyr_fixup_kernel).
 #pragma once
 #include "peer.cuh"
 #include <type_traits>

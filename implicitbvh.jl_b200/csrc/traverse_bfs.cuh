@@ -112,9 +112,10 @@ IBVH_D unsigned long long bfs_reserve(uint32_t k, unsigned long long* counter, u
         if (lane == kBfsThreads / 32 - 1) *s_base = ti ? atomicAdd(counter, (unsigned long long)ti) : 0ull;
     }
     __syncthreads();
-    const unsigned long long pos = *s_base + s_warp[w] + (incl - k);
-    __syncthreads();                                                        // s_warp / s_base are reused by the next call
-    return pos;
+    // No third barrier: the callers alternate between two sets of (s_warp, s_base). A thread can only write a set again two
+    // calls later, i.e. after it has passed the second barrier of the call in between — which every thread reaches only
+    // after its reads of this call.
+    return *s_base + s_warp[w] + (incl - k);
 }
 
 // Loads the (up to) four consecutive entries of a thread. Buffers are 256-byte aligned and a thread's first entry index is
@@ -135,11 +136,14 @@ IBVH_D void bfs_load_entries(const uint2* src, unsigned long long first, unsigne
 enum { kBfsSingle = 0, kBfsBoth = 1, kBfsLeft = 2, kBfsRight = 3 };
 
 // VA / VB: volume types read on the two sides (node types; a leaf volume type on the side that already is at its leaves).
+// (float nodes: 34 registers left 6 of the 8 CTAs launched per SM resident — profiles/r2_ncu_bfs.csv; capped at 32 for 8)
+template <class VA, class VB> constexpr int bfs_nodes_minb() { return (sizeof(typename VA::value_type) == 4 && sizeof(typename VB::value_type) == 4) ? 8 : 1; }
 template <int MODE, class VA, class VB>
-__global__ void __launch_bounds__(kBfsThreads) bfs_nodes_kernel(const uint2* __restrict__ src, unsigned long long count, BfsSide sa, BfsSide sb,
+__global__ void __launch_bounds__(kBfsThreads, bfs_nodes_minb<VA, VB>()) bfs_nodes_kernel(const uint2* __restrict__ src, unsigned long long count, BfsSide sa, BfsSide sb,
                                                                 int self_checks, uint2* __restrict__ dst, unsigned long long* counter) {
-    __shared__ uint32_t s_warp[kBfsThreads / 32];
-    __shared__ unsigned long long s_base;
+    __shared__ uint32_t s_warp[2][kBfsThreads / 32];
+    __shared__ unsigned long long s_base[2];
+    int par = 0;                                 // which set this tile's reservation uses (see bfs_reserve)
     const unsigned long long tiles = (count + kBfsTile - 1) / kBfsTile;
     for (unsigned long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const unsigned long long first = tile * kBfsTile + (unsigned long long)threadIdx.x * kBfsItems;
@@ -171,7 +175,8 @@ __global__ void __launch_bounds__(kBfsThreads) bfs_nodes_kernel(const uint2* __r
             mask |= m << (4 * j);
             k += __popc(m);
         }
-        unsigned long long pos = bfs_reserve(k, counter, s_warp, &s_base);
+        unsigned long long pos = bfs_reserve(k, counter, s_warp[par], &s_base[par]);
+        par ^= 1;
 #pragma unroll
         for (int j = 0; j < kBfsItems; ++j) {
             const uint32_t m = (mask >> (4 * j)) & 0xFu;
@@ -192,8 +197,9 @@ template <bool SORT_PAIR, class V, class I>
 __global__ void __launch_bounds__(kBfsThreads) bfs_leaves_kernel(const uint2* __restrict__ src, unsigned long long count, BfsSide sa, BfsSide sb,
                                                                  uint32_t index_offset, int positions, IndexPair<I>* __restrict__ out,
                                                                  unsigned long long capacity, unsigned long long* counter) {
-    __shared__ uint32_t s_warp[kBfsThreads / 32];
-    __shared__ unsigned long long s_base;
+    __shared__ uint32_t s_warp[2][kBfsThreads / 32];
+    __shared__ unsigned long long s_base[2];
+    int par = 0;                                 // which set this tile's reservation uses (see bfs_reserve)
     const unsigned long long tiles = (count + kBfsTile - 1) / kBfsTile;
     for (unsigned long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const unsigned long long first = tile * kBfsTile + (unsigned long long)threadIdx.x * kBfsItems;
@@ -207,7 +213,8 @@ __global__ void __launch_bounds__(kBfsThreads) bfs_leaves_kernel(const uint2* __
             const V vb = bfs_load<V>(sb, e[j].y);
             if (iscontact(va, vb)) mask |= 1u << j;
         }
-        unsigned long long pos = bfs_reserve(__popc(mask), counter, s_warp, &s_base);
+        unsigned long long pos = bfs_reserve(__popc(mask), counter, s_warp[par], &s_base[par]);
+        par ^= 1;
 #pragma unroll
         for (int j = 0; j < kBfsItems; ++j) {
             if (!((mask >> j) & 1u)) continue;
@@ -233,8 +240,9 @@ __global__ void __launch_bounds__(kBfsThreads) bfs_last_kernel(const uint2* __re
                                                                BfsSide la, BfsSide lb, uint32_t index_offset, int positions,
                                                                IndexPair<I>* __restrict__ out, unsigned long long capacity,
                                                                unsigned long long* counter, unsigned long long* children) {
-    __shared__ uint32_t s_warp[kBfsThreads / 32];
-    __shared__ unsigned long long s_base;
+    __shared__ uint32_t s_warp[2][kBfsThreads / 32];
+    __shared__ unsigned long long s_base[2];
+    int par = 0;                                 // which set this tile's reservation uses (see bfs_reserve)
     unsigned long long nchild = 0;
     const unsigned long long tiles = (count + kBfsTile - 1) / kBfsTile;
     for (unsigned long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -268,7 +276,8 @@ __global__ void __launch_bounds__(kBfsThreads) bfs_last_kernel(const uint2* __re
             if ((m & 0x8u) && iscontact(va1, vb1)) hm |= 0x8u;
             hitmask |= hm << (4 * j);
         }
-        unsigned long long pos = bfs_reserve(__popc(hitmask), counter, s_warp, &s_base);
+        unsigned long long pos = bfs_reserve(__popc(hitmask), counter, s_warp[par], &s_base[par]);
+        par ^= 1;
 #pragma unroll
         for (int j = 0; j < kBfsItems; ++j) {
             uint32_t hm = (hitmask >> (4 * j)) & 0xFu;
@@ -305,8 +314,9 @@ __global__ void __launch_bounds__(kBfsThreads) bfs_rays_nodes_kernel(const uint2
                                                                      const typename N::value_type* __restrict__ dirs,
                                                                      uint2* __restrict__ dst, unsigned long long* counter) {
     using T = typename N::value_type;
-    __shared__ uint32_t s_warp[kBfsThreads / 32];
-    __shared__ unsigned long long s_base;
+    __shared__ uint32_t s_warp[2][kBfsThreads / 32];
+    __shared__ unsigned long long s_base[2];
+    int par = 0;                                 // which set this tile's reservation uses (see bfs_reserve)
     const unsigned long long tiles = (count + kBfsTile - 1) / kBfsTile;
     for (unsigned long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const unsigned long long first = tile * kBfsTile + (unsigned long long)threadIdx.x * kBfsItems;
@@ -324,7 +334,8 @@ __global__ void __launch_bounds__(kBfsThreads) bfs_rays_nodes_kernel(const uint2
                 k += __popc(m);
             }
         }
-        unsigned long long pos = bfs_reserve(k, counter, s_warp, &s_base);
+        unsigned long long pos = bfs_reserve(k, counter, s_warp[par], &s_base[par]);
+        par ^= 1;
 #pragma unroll
         for (int j = 0; j < kBfsItems; ++j) {
             const uint32_t m = (mask >> (2 * j)) & 3u;
@@ -341,8 +352,9 @@ __global__ void __launch_bounds__(kBfsThreads) bfs_rays_leaves_kernel(const uint
                                                                       IndexPair<I>* __restrict__ out, unsigned long long capacity,
                                                                       unsigned long long* counter) {
     using T = typename V::value_type;
-    __shared__ uint32_t s_warp[kBfsThreads / 32];
-    __shared__ unsigned long long s_base;
+    __shared__ uint32_t s_warp[2][kBfsThreads / 32];
+    __shared__ unsigned long long s_base[2];
+    int par = 0;                                 // which set this tile's reservation uses (see bfs_reserve)
     const unsigned long long tiles = (count + kBfsTile - 1) / kBfsTile;
     for (unsigned long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const unsigned long long first = tile * kBfsTile + (unsigned long long)threadIdx.x * kBfsItems;
@@ -356,7 +368,8 @@ __global__ void __launch_bounds__(kBfsThreads) bfs_rays_leaves_kernel(const uint
             bfs_load_ray(points, dirs, e[j].y, p, d);
             if (isintersection(bfs_load<V>(sa, e[j].x), p, d)) mask |= 1u << j;
         }
-        unsigned long long pos = bfs_reserve(__popc(mask), counter, s_warp, &s_base);
+        unsigned long long pos = bfs_reserve(__popc(mask), counter, s_warp[par], &s_base[par]);
+        par ^= 1;
 #pragma unroll
         for (int j = 0; j < kBfsItems; ++j) {
             if (!((mask >> j) & 1u)) continue;

@@ -145,6 +145,51 @@ def test_bfs_default_start_level_and_null_arguments(ib, O):
     assert lib.ibvh_sort_contacts(None, None, 0, 4, 0, None, None) == ib.capi.ERR_ARGUMENT
 
 
+def test_julia_extension_ccalls_match_the_header():
+    """ext/ImplicitBVHB200Ext.jl cannot be executed here (no Julia): at least every `ccall` in it must name an entry point
+    of include/ibvh.h with the header's number of arguments, and its struct mirrors must have the C structs' field counts."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = re.sub(r"/\*.*?\*/", "", open(os.path.join(root, "include", "ibvh.h")).read(), flags=re.S)
+    decl = {}
+    for m in re.finditer(r"IBVH_API\s+[\w\s\*]+?\b(ibvh_\w+)\s*\(([^;]*?)\)\s*;", header, flags=re.S):
+        params = m.group(2).strip()
+        decl[m.group(1)] = 0 if params in ("", "void") else len([p for p in params.split(",") if p.strip()])
+    jl = open(os.path.join(root, "ext", "ImplicitBVHB200Ext.jl")).read()
+
+    def top_level_items(text):
+        depth, items, cur = 0, [], ""
+        for ch in text:
+            depth += ch == "{"
+            depth -= ch == "}"
+            if ch == "," and depth == 0:
+                items.append(cur.strip()); cur = ""
+            else:
+                cur += ch
+        items.append(cur.strip())
+        return [i for i in items if i]
+
+    calls = list(re.finditer(r"ccall\(\(:(\w+),\s*LIB\),\s*[\w\{\}]+,\s*\(([^)]*)\)", jl, flags=re.S))
+    assert len(calls) >= 16
+    for m in calls:
+        name, types = m.group(1), top_level_items(m.group(2))
+        assert name in decl, f"{name}: not declared in include/ibvh.h"
+        assert decl[name] == len(types), f"{name}: header has {decl[name]} arguments, the ccall passes {len(types)}"
+    for needed in ("ibvh_build", "ibvh_traverse_single", "ibvh_traverse_pair", "ibvh_traverse_rays", "ibvh_traverse_bfs_single",
+                   "ibvh_traverse_bfs_pair", "ibvh_traverse_bfs_rays", "ibvh_sort_contacts", "ibvh_traverse_finish", "ibvh_traverse_cancel"):
+        assert any(m.group(1) == needed for m in calls), f"the extension does not bind {needed}"
+    # struct mirrors: field counts of ibvh_types_t / ibvh_bvh_t / ibvh_traverse_params_t
+    def c_fields(struct):
+        body = re.search(r"typedef struct " + struct + r"\s*\{(.*?)\}", header, flags=re.S).group(1)
+        return sum(len(stmt.split(",")) for stmt in body.split(";") if stmt.strip())
+    def jl_fields(struct):
+        body = re.search(r"struct " + struct + r"\b[^\n]*\n(.*?)\nend", jl, flags=re.S).group(1)
+        return sum(len([f for f in line.split("#")[0].split(";") if f.strip()]) for line in body.splitlines())
+    assert c_fields("ibvh_types") == jl_fields("Types") == 6
+    assert c_fields("ibvh_bvh") == jl_fields("CBvh") == 6
+    assert c_fields("ibvh_traverse_params") == jl_fields("Params") == 7
+
+
 def test_product_never_imports_oracle():
     pkg = os.path.join(ROOT, "implicitbvh.jl_b200")
     for dirpath, _, files in os.walk(pkg):

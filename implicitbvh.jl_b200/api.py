@@ -810,6 +810,8 @@ def traverse(bvh: BVH, bvh2=None, alg=None, *, start_level: Optional[int] = None
         start_level, alg, bvh2 = int(bvh2), BFSTraversal(), None
     if bvh2 is not None and not isinstance(bvh2, BVH):       # traverse(bvh, alg)
         alg, bvh2 = bvh2, None
+    if isinstance(alg, (int, np.integer)) and not isinstance(alg, bool):     # old interface traverse(bvh1, bvh2, start_level1[, start_level2]): BFS (traverse/traverse.jl:244-256)
+        start_level1, alg = int(alg), BFSTraversal()
     if isinstance(alg, BFSTraversal):
         if defer or peer is not None or query_range is not None or reference_shaped or packet or walk:
             raise ArgumentError("BFSTraversal takes start_level[1,2], narrow and cache only")

@@ -1215,6 +1215,9 @@ def test_bfs_doctests_and_old_interface(ib, golden, dev):
     b2 = gpu_build(ib, ib.bspheres(g["centers2"], g["radii2"]))
     tr = ib.traverse(b1, b2, ib.BFSTraversal(), start_level1=g["start_level1"], start_level2=g["start_level2"])
     assert sorted(pairs_list(tr.contacts.numpy())) == sorted(tuple(p) for p in g["contacts_lvt_order"])
+    old = ib.traverse(b1, b2, g["start_level1"], start_level2=g["start_level2"])      # traverse(bvh1, bvh2, start_level1, start_level2) = BFS, traverse.jl:244-256
+    assert (old.start_level1, old.start_level2, old.num_checks) == (tr.start_level1, tr.start_level2, tr.num_checks)
+    assert sorted(pairs_list(old.contacts.numpy())) == sorted(tuple(p) for p in g["contacts_lvt_order"])
     gr = golden["ray_example"]
     tr = ib.traverse_rays(bvh, np.array(gr["points"]), np.array(gr["directions"]), ib.BFSTraversal())
     assert sorted(pairs_list(tr.contacts.numpy())) == sorted(tuple(p) for p in gr["contacts_lvt_order"])
